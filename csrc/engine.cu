@@ -1,0 +1,250 @@
+// Native step executor.  The Python planner lowers a model + optimizer + PS algorithm into flat
+// lists of device ops once (pointers, shapes, pre-encoded TMA descriptors); `dk_engine_run`
+// then enqueues a whole list on a stream with no Python in the loop, which is what gets
+// captured into the per-window CUDA graph (forward, loss, backward, optimizer, commit / pull).
+//
+// This replaces the reference's per-batch Python hot loop (distkeras/workers.py:327-342:
+// train_on_batch -> get_weights -> numpy -> pickle -> socket) with a replayable device program.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "engine.h"
+#include "gemm.h"
+#include "kernels.h"
+#include "ps.h"
+
+namespace {
+
+struct Op {
+  int kind;
+  int64_t i[DK_OP_MAX_I];
+  double f[DK_OP_MAX_F];
+  // GEMM only
+  alignas(64) CUtensorMap ta;
+  alignas(64) CUtensorMap tb;
+  DkGemmEpilogue ep;
+};
+
+struct Engine {
+  std::vector<std::vector<Op>> lists;
+  void* slots[DK_ENGINE_SLOTS];
+  long launches;  // kernels enqueued so far (bench "gpu_launches" accounting)
+};
+
+inline void* resolve(const Engine* e, int64_t v) {
+  if (v < 0) return e->slots[-v - 1];
+  return reinterpret_cast<void*>(static_cast<uintptr_t>(v));
+}
+
+template <typename T>
+inline T* rp(const Engine* e, int64_t v) {
+  return reinterpret_cast<T*>(resolve(e, v));
+}
+
+int run_op(Engine* e, Op& op, void* st) {
+  const int64_t* a = op.i;
+  const double* f = op.f;
+  switch (op.kind) {
+    case DK_OP_INPUT:
+      // x, in_dtype, B, F, xb, ldx, xt, ldxt, step_counter | scale, shift
+      return dk_input_stage(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (float)f[0], (float)f[1],
+                            resolve(e, a[4]), (int)a[5], resolve(e, a[6]), (int)a[7], rp<int>(e, a[8]), st);
+    case DK_OP_GEMM:
+      // M, N, K, bn, tf32 (tensor maps + epilogue pre-encoded)
+      return dk_gemm_tn_launch(&op.ta, &op.tb, &op.ep, (int)a[0], (int)a[1], (int)a[2], (int)a[3],
+                               (int)a[4], st);
+    case DK_OP_XENT:
+      // logits, ldl, labels, labels_dense, B, C, dz, ldz, dzt, ldzt, probs, hist, step, hist_slots
+      return dk_softmax_xent(rp<const float>(e, a[0]), (int)a[1], rp<const int>(e, a[2]),
+                             rp<const float>(e, a[3]), (int)a[4], (int)a[5], resolve(e, a[6]), (int)a[7],
+                             resolve(e, a[8]), (int)a[9], rp<float>(e, a[10]), rp<float>(e, a[11]),
+                             rp<const int>(e, a[12]), (int)a[13], st);
+    case DK_OP_ELOSS:
+      // kind, out, target, B, C, dz, ldz, dzt, ldzt, hist, step, hist_slots
+      return dk_elementwise_loss((int)a[0], rp<const float>(e, a[1]), rp<const float>(e, a[2]), (int)a[3],
+                                 (int)a[4], resolve(e, a[5]), (int)a[6], resolve(e, a[7]), (int)a[8],
+                                 rp<float>(e, a[9]), rp<const int>(e, a[10]), (int)a[11], st);
+    case DK_OP_ROWSUM:
+      // src, rows, cols, lds, out | scale
+      return dk_rowsum_bf16(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], rp<float>(e, a[4]),
+                            (float)f[0], st);
+    case DK_OP_TRANSPOSE:
+      // src, rows, cols, lds, dst, ldd
+      return dk_transpose_bf16(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], resolve(e, a[4]),
+                               (int)a[5], st);
+    case DK_OP_OPTIM:
+      // kind, w, g, s0, s1, wb, n, nesterov, step | lr, p0, p1, eps, decay, grad_scale
+      return dk_optim_step((int)a[0], rp<float>(e, a[1]), rp<const float>(e, a[2]), rp<float>(e, a[3]),
+                           rp<float>(e, a[4]), resolve(e, a[5]), (long)a[6], (float)f[0], (float)f[1],
+                           (float)f[2], (float)f[3], (float)f[4], (int)a[7], rp<const int>(e, a[8]),
+                           (float)f[5], st);
+    case DK_OP_IM2COL:
+      // x, B, H, W, C, KH, KW, stride, pad, OH, OW, col, ldcol
+      return dk_im2col(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], (int)a[6],
+                       (int)a[7], (int)a[8], (int)a[9], (int)a[10], resolve(e, a[11]), (int)a[12], st);
+    case DK_OP_COL2IM:
+      // col, ldcol, B, H, W, C, KH, KW, stride, pad, OH, OW, dx
+      return dk_col2im(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], (int)a[6],
+                       (int)a[7], (int)a[8], (int)a[9], (int)a[10], (int)a[11], resolve(e, a[12]), st);
+    case DK_OP_MAXPOOL_FWD:
+      // x, B, H, W, C, k, stride, y
+      return dk_maxpool_fwd(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5],
+                            (int)a[6], resolve(e, a[7]), st);
+    case DK_OP_MAXPOOL_BWD:
+      // x, y, dy, B, H, W, C, k, stride, dx
+      return dk_maxpool_bwd(resolve(e, a[0]), resolve(e, a[1]), resolve(e, a[2]), (int)a[3], (int)a[4],
+                            (int)a[5], (int)a[6], (int)a[7], (int)a[8], resolve(e, a[9]), st);
+    case DK_OP_RELU_MASK:
+      return dk_relu_mask_bf16(resolve(e, a[0]), resolve(e, a[1]), (long)a[2], st);
+    case DK_OP_ADD:
+      return dk_add_bf16(resolve(e, a[0]), resolve(e, a[1]), resolve(e, a[2]), (long)a[3], (int)a[4], st);
+    case DK_OP_MEMSET:
+      return dk_memset_async(resolve(e, a[0]), (int)a[1], (long)a[2], st);
+    case DK_OP_MEMCPY:
+      // dst, src, bytes, kind
+      return dk_memcpy_async(resolve(e, a[0]), resolve(e, a[1]), (long)a[2], (int)a[3], st);
+    case DK_OP_CAST:
+      return dk_cast_bf16(rp<const float>(e, a[0]), resolve(e, a[1]), (long)a[2], st);
+    case DK_OP_PS_COMMIT:
+      // center, w, w1, n, scale_dev, ctrl, worker, iteration | scale
+      return dk_ps_commit(rp<float>(e, a[0]), rp<const float>(e, a[1]), rp<const float>(e, a[2]), (long)a[3],
+                          (float)f[0], rp<const float>(e, a[4]), rp<unsigned>(e, a[5]), (int)a[6],
+                          (unsigned)a[7], st);
+    case DK_OP_PS_PULL:
+      // center, w, w1, wb, n, ctrl, last_update
+      return dk_ps_pull(rp<const float>(e, a[0]), rp<float>(e, a[1]), rp<float>(e, a[2]), resolve(e, a[3]),
+                        (long)a[4], rp<const unsigned>(e, a[5]), rp<unsigned>(e, a[6]), st);
+    case DK_OP_PS_EXCHANGE:
+      // center, w, w1, wb, n, scale_dev, ctrl, worker, iteration, last_update | scale
+      return dk_ps_exchange(rp<float>(e, a[0]), rp<float>(e, a[1]), rp<float>(e, a[2]), resolve(e, a[3]),
+                            (long)a[4], (float)f[0], rp<const float>(e, a[5]), rp<unsigned>(e, a[6]),
+                            (int)a[7], (unsigned)a[8], rp<unsigned>(e, a[9]), st);
+    case DK_OP_PS_ELASTIC:
+      // center, w, wb, n, ctrl, worker, iteration | alpha
+      return dk_ps_elastic(rp<float>(e, a[0]), rp<float>(e, a[1]), resolve(e, a[2]), (long)a[3], (float)f[0],
+                           rp<unsigned>(e, a[4]), (int)a[5], (unsigned)a[6], st);
+    case DK_OP_PS_DAMPED:
+      // center, w, w1, wb, n, ctrl, worker, iteration | scale, inv_lr
+      return dk_ps_damped_exchange(rp<float>(e, a[0]), rp<float>(e, a[1]), rp<float>(e, a[2]),
+                                   resolve(e, a[3]), (long)a[4], (float)f[0], (float)f[1],
+                                   rp<unsigned>(e, a[5]), (int)a[6], (unsigned)a[7], st);
+    case DK_OP_PS_TICKET:
+      return dk_ps_ticket(rp<unsigned>(e, a[0]), rp<const unsigned>(e, a[1]), rp<float>(e, a[2]), st);
+    case DK_OP_LOCK_ACQUIRE:
+      return dk_ps_lock_acquire(rp<unsigned>(e, a[0]), rp<unsigned>(e, a[1]), st);
+    case DK_OP_LOCK_RELEASE:
+      return dk_ps_lock_release(rp<unsigned>(e, a[0]), rp<const unsigned>(e, a[1]), st);
+    case DK_OP_EAMSGD_PRE:
+      // w, r, wcopy, wb, n | mu
+      return dk_eamsgd_pre(rp<float>(e, a[0]), rp<float>(e, a[1]), rp<float>(e, a[2]), resolve(e, a[3]),
+                           (long)a[4], (float)f[0], st);
+    case DK_OP_EAMSGD_POST:
+      return dk_eamsgd_post(rp<float>(e, a[0]), rp<float>(e, a[1]), rp<const float>(e, a[2]),
+                            resolve(e, a[3]), (long)a[4], (float)f[0], st);
+    case DK_OP_LABEL_INDEX:
+      // probs, B, C, default_index, out_index, labels, correct | threshold
+      return dk_label_index(rp<const float>(e, a[0]), (int)a[1], (int)a[2], (float)f[0], (int)a[3],
+                            rp<int>(e, a[4]), rp<const int>(e, a[5]), rp<int>(e, a[6]), st);
+    default:
+      return -1000;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void* dk_engine_create() {
+  Engine* e = new Engine();
+  memset(e->slots, 0, sizeof(e->slots));
+  e->launches = 0;
+  return e;
+}
+
+void dk_engine_destroy(void* h) { delete reinterpret_cast<Engine*>(h); }
+
+int dk_engine_new_list(void* h) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  e->lists.emplace_back();
+  return static_cast<int>(e->lists.size()) - 1;
+}
+
+int dk_engine_clear_list(void* h, int list) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (list < 0 || list >= (int)e->lists.size()) return -1;
+  e->lists[list].clear();
+  return 0;
+}
+
+int dk_engine_set_slot(void* h, int slot, void* p) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (slot < 0 || slot >= DK_ENGINE_SLOTS) return -1;
+  e->slots[slot] = p;
+  return 0;
+}
+
+int dk_engine_add_op(void* h, int list, int kind, const int64_t* iargs, int ni, const double* fargs,
+                     int nf) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (list < 0 || list >= (int)e->lists.size() || ni > DK_OP_MAX_I || nf > DK_OP_MAX_F) return -1;
+  Op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = kind;
+  for (int k = 0; k < ni; ++k) op.i[k] = iargs[k];
+  for (int k = 0; k < nf; ++k) op.f[k] = fargs[k];
+  e->lists[list].push_back(op);
+  return static_cast<int>(e->lists[list].size()) - 1;
+}
+
+// GEMM: D = epilogue(A[M,K] * B[N,K]^T); operands must be fixed device buffers.
+int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B, long ldb, int M, int N,
+                       int K, int tf32, int bn, const DkGemmEpilogue* ep) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (list < 0 || list >= (int)e->lists.size()) return -1;
+  Op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = DK_OP_GEMM;
+  if (bn <= 0) bn = dk_gemm_pick_bn(N);
+  int r = dk_tmap_encode_2d(&op.ta, A, tf32 ? DK_F32 : DK_BF16, M, K, lda, 128);
+  if (r != 0) return r;
+  r = dk_tmap_encode_2d(&op.tb, B, tf32 ? DK_F32 : DK_BF16, N, K, ldb, bn);
+  if (r != 0) return r;
+  op.ep = *ep;
+  op.i[0] = M; op.i[1] = N; op.i[2] = K; op.i[3] = bn; op.i[4] = tf32;
+  e->lists[list].push_back(op);
+  return static_cast<int>(e->lists[list].size()) - 1;
+}
+
+int dk_engine_run(void* h, int list, void* stream) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (list < 0 || list >= (int)e->lists.size()) return -1;
+  for (Op& op : e->lists[list]) {
+    int r = run_op(e, op, stream);
+    if (r != 0) return r;
+    if (op.kind != DK_OP_MEMSET && op.kind != DK_OP_MEMCPY) e->launches += 1;
+  }
+  return 0;
+}
+
+int dk_engine_list_size(void* h, int list) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (list < 0 || list >= (int)e->lists.size()) return -1;
+  return static_cast<int>(e->lists[list].size());
+}
+
+// number of kernel launches a run of `list` performs (memset / memcpy nodes excluded)
+int dk_engine_list_kernels(void* h, int list) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (list < 0 || list >= (int)e->lists.size()) return -1;
+  int n = 0;
+  for (const Op& op : e->lists[list])
+    if (op.kind != DK_OP_MEMSET && op.kind != DK_OP_MEMCPY) ++n;
+  return n;
+}
+
+long dk_engine_launches(void* h) { return reinterpret_cast<Engine*>(h)->launches; }
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// C ABI of the native op-list executor (engine.cu).
+#pragma once
+#include <stdint.h>
+
+#include "gemm.h"
+
+#define DK_OP_MAX_I 16
+#define DK_OP_MAX_F 8
+#define DK_ENGINE_SLOTS 16
+
+enum {
+  DK_OP_INPUT = 0,
+  DK_OP_GEMM = 1,
+  DK_OP_XENT = 2,
+  DK_OP_ROWSUM = 3,
+  DK_OP_TRANSPOSE = 4,
+  DK_OP_OPTIM = 5,
+  DK_OP_IM2COL = 6,
+  DK_OP_COL2IM = 7,
+  DK_OP_MAXPOOL_FWD = 8,
+  DK_OP_MAXPOOL_BWD = 9,
+  DK_OP_RELU_MASK = 10,
+  DK_OP_ADD = 11,
+  DK_OP_MEMSET = 12,
+  DK_OP_PS_COMMIT = 13,
+  DK_OP_PS_PULL = 14,
+  DK_OP_PS_EXCHANGE = 15,
+  DK_OP_PS_ELASTIC = 16,
+  DK_OP_PS_DAMPED = 17,
+  DK_OP_PS_TICKET = 18,
+  DK_OP_LOCK_ACQUIRE = 19,
+  DK_OP_LOCK_RELEASE = 20,
+  DK_OP_EAMSGD_PRE = 21,
+  DK_OP_EAMSGD_POST = 22,
+  DK_OP_CAST = 23,
+  DK_OP_ELOSS = 24,
+  DK_OP_MEMCPY = 25,
+  DK_OP_LABEL_INDEX = 26
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+void* dk_engine_create();
+void dk_engine_destroy(void* h);
+int dk_engine_new_list(void* h);
+int dk_engine_clear_list(void* h, int list);
+int dk_engine_set_slot(void* h, int slot, void* p);
+// pointer arguments: a device address, or -(slot + 1) to read the pointer from a slot at run time
+int dk_engine_add_op(void* h, int list, int kind, const int64_t* iargs, int ni, const double* fargs,
+                     int nf);
+int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B, long ldb, int M, int N,
+                       int K, int tf32, int bn, const DkGemmEpilogue* ep);
+int dk_engine_run(void* h, int list, void* stream);
+int dk_engine_list_size(void* h, int list);
+int dk_engine_list_kernels(void* h, int list);
+long dk_engine_launches(void* h);
+
+// from fabric.cu
+int dk_memcpy_async(void* dst, const void* src, long bytes, int kind, void* stream);
+int dk_memset_async(void* dst, int value, long bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,52 @@
+// C ABI of the tcgen05 GEMM (see gemm_tcgen05.cu).
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#include <cuda_bf16.h>
+typedef __nv_bfloat16 dk_bf16;
+#else
+typedef uint16_t dk_bf16;
+#endif
+
+enum { DK_BF16 = 0, DK_F32 = 1 };
+
+// Fused epilogue description: out = mask( act( alpha * acc + bias ) )
+typedef struct DkGemmEpilogue {
+  const float* bias;     // nullptr, or [N] (bias_along_m == 0) / [M] (bias_along_m == 1)
+  int bias_along_m;
+  int act;               // 0 = identity, 1 = ReLU
+  const dk_bf16* mask;   // nullptr, or [M, ld_mask]: out = 0 where mask <= 0 (dReLU)
+  int ld_mask;
+  void* d;               // row-major output [M, ldd] (bf16, or fp32 if d_fp32), may be nullptr
+  int ldd;
+  int d_fp32;
+  int accumulate;        // fp32 output only: d += result
+  dk_bf16* dt;           // optional transposed bf16 copy [N, lddt]
+  int lddt;
+  float alpha;
+  float drop_p;          // > 0: inverted dropout applied after the activation (training forward)
+  uint32_t drop_seed;
+  const int* step;       // device step counter mixed into the dropout hash (graph-replay safe)
+} DkGemmEpilogue;
+
+#ifdef __cplusplus
+namespace dk {
+typedef DkGemmEpilogue GemmEpilogue;
+}
+extern "C" {
+#endif
+
+// Encodes a CUtensorMap (128 bytes, 64-byte aligned) for a row-major [rows, cols] matrix with
+// leading dimension ld (elements), box = [box_rows, 128 bytes], SWIZZLE_128B, zero OOB fill.
+int dk_tmap_encode_2d(void* out_tmap, const void* base, int dtype, long rows, long cols, long ld,
+                      int box_rows);
+int dk_gemm_pick_bn(int N);
+int dk_gemm_tn_launch(const void* tmap_a, const void* tmap_b, const DkGemmEpilogue* ep, int M, int N,
+                      int K, int bn, int tf32, void* stream);
+int dk_gemm_tn(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M,
+               int N, int K, int tf32, int bn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif

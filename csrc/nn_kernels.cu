@@ -1,0 +1,345 @@
+// Layout / elementwise kernels around the tcgen05 GEMMs: fused input stage (dtype cast +
+// MinMaxTransformer affine + transposed copy), bf16 transposes, bias-gradient row sums, im2col /
+// col2im (reference op K8 lowered to GEMM), 2x2 max-pool (K9) and residual helpers.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dk {
+
+// ------------------------------------------------------------------------------------------
+// input stage
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p);
+template <>
+__device__ __forceinline__ float load_as_float<uint8_t>(const uint8_t* p) { return static_cast<float>(*p); }
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+input_stage_kernel(const T* __restrict__ x, int B, int F, float scale, float shift,
+                   __nv_bfloat16* __restrict__ xb, int ldx, __nv_bfloat16* __restrict__ xt, int ldxt,
+                   int* step_counter) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int f0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int b = b0 + r, f = f0 + tx;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (b < B && f < F) {
+      v = __float2bfloat16_rn(load_as_float<T>(x + static_cast<size_t>(b) * F + f) * scale + shift);
+      if (xb != nullptr) xb[static_cast<size_t>(b) * ldx + f] = v;
+    }
+    tile[r][tx] = v;
+  }
+  if (xt != nullptr) {
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int f = f0 + r, b = b0 + tx;
+      if (f < F && b < B) xt[static_cast<size_t>(f) * ldxt + b] = tile[tx][r];
+    }
+  }
+  if (step_counter != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+    *step_counter += 1;
+}
+
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, int lds,
+                      __nv_bfloat16* __restrict__ dst, int ldd) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8)
+    if (r0 + r < rows && c0 + tx < cols) tile[r][tx] = src[static_cast<size_t>(r0 + r) * lds + c0 + tx];
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8)
+    if (c0 + r < cols && r0 + tx < rows) dst[static_cast<size_t>(c0 + r) * ldd + r0 + tx] = tile[tx][r];
+}
+
+// out[r] = scale * sum_c src[r, c]; one warp per row, 16-byte loads when aligned.
+__global__ void __launch_bounds__(256)
+rowsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, int lds,
+                   float* __restrict__ out, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __nv_bfloat16* p = src + static_cast<size_t>(row) * lds;
+  float acc = 0.f;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const int c8 = cols >> 3;
+    for (int i = lane; i < c8; i += 32) {
+      const uint4 q = reinterpret_cast<const uint4*>(p)[i];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __bfloat1622float2(h[t]);
+        acc += f.x + f.y;
+      }
+    }
+    for (int c = (c8 << 3) + lane; c < cols; c += 32) acc += __bfloat162float(p[c]);
+  } else {
+    for (int c = lane; c < cols; c += 32) acc += __bfloat162float(p[c]);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc * scale;
+}
+
+// ------------------------------------------------------------------------------------------
+// convolution lowering (NHWC, bf16): col[(b, oh, ow), (kh, kw, c)]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int KH, int KW,
+              int stride, int pad, int OH, int OW, __nv_bfloat16* __restrict__ col, int ldcol) {
+  // one thread per (row, kh, kw, c8-chunk); channels are innermost -> contiguous copies
+  const int cvec = (C % 8 == 0) ? 8 : 1;
+  const int cchunks = C / cvec;
+  const long total = static_cast<long>(B) * OH * OW * KH * KW * cchunks;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    long t = i;
+    const int cc = static_cast<int>(t % cchunks); t /= cchunks;
+    const int kw = static_cast<int>(t % KW); t /= KW;
+    const int kh = static_cast<int>(t % KH); t /= KH;
+    const int ow = static_cast<int>(t % OW); t /= OW;
+    const int oh = static_cast<int>(t % OH); t /= OH;
+    const int b = static_cast<int>(t);
+    const int ih = oh * stride - pad + kh, iw = ow * stride - pad + kw;
+    const long row = (static_cast<long>(b) * OH + oh) * OW + ow;
+    __nv_bfloat16* dst = col + row * ldcol + (kh * KW + kw) * C + cc * cvec;
+    const bool inside = ih >= 0 && ih < H && iw >= 0 && iw < W;
+    const __nv_bfloat16* srcp = x + ((static_cast<long>(b) * H + ih) * W + iw) * C + cc * cvec;
+    if (cvec == 8) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (inside) v = *reinterpret_cast<const uint4*>(srcp);
+      *reinterpret_cast<uint4*>(dst) = v;
+    } else {
+      *dst = inside ? *srcp : __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+// dx[b, ih, iw, c] = sum over the (kh, kw) windows that cover it (gather form: no atomics)
+__global__ void __launch_bounds__(256)
+col2im_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int H, int W, int C, int KH,
+              int KW, int stride, int pad, int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+  const long total = static_cast<long>(B) * H * W * C;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    long t = i;
+    const int c = static_cast<int>(t % C); t /= C;
+    const int iw = static_cast<int>(t % W); t /= W;
+    const int ih = static_cast<int>(t % H); t /= H;
+    const int b = static_cast<int>(t);
+    float acc = 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      const int ohs = ih + pad - kh;
+      if (ohs < 0 || ohs % stride != 0) continue;
+      const int oh = ohs / stride;
+      if (oh >= OH) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ows = iw + pad - kw;
+        if (ows < 0 || ows % stride != 0) continue;
+        const int ow = ows / stride;
+        if (ow >= OW) continue;
+        const long row = (static_cast<long>(b) * OH + oh) * OW + ow;
+        acc += __bfloat162float(col[row * ldcol + (kh * KW + kw) * C + c]);
+      }
+    }
+    dx[i] = __float2bfloat16_rn(acc);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int k, int stride,
+                   int OH, int OW, __nv_bfloat16* __restrict__ y) {
+  const long total = static_cast<long>(B) * OH * OW * C;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    long t = i;
+    const int c = static_cast<int>(t % C); t /= C;
+    const int ow = static_cast<int>(t % OW); t /= OW;
+    const int oh = static_cast<int>(t % OH); t /= OH;
+    const int b = static_cast<int>(t);
+    float m = -INFINITY;
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) {
+        const int ih = oh * stride + kh, iw = ow * stride + kw;
+        if (ih < H && iw < W)
+          m = fmaxf(m, __bfloat162float(x[((static_cast<long>(b) * H + ih) * W + iw) * C + c]));
+      }
+    y[i] = __float2bfloat16_rn(m);
+  }
+}
+
+// dx = dy routed to the first arg-max position of each window (non-overlapping windows: k == stride)
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                   const __nv_bfloat16* __restrict__ dy, int B, int H, int W, int C, int k, int stride,
+                   int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+  const long total = static_cast<long>(B) * H * W * C;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    long t = i;
+    const int c = static_cast<int>(t % C); t /= C;
+    const int iw = static_cast<int>(t % W); t /= W;
+    const int ih = static_cast<int>(t % H); t /= H;
+    const int b = static_cast<int>(t);
+    const int oh = ih / stride, ow = iw / stride;
+    float g = 0.f;
+    if (oh < OH && ow < OW && ih - oh * stride < k && iw - ow * stride < k) {
+      const long o = ((static_cast<long>(b) * OH + oh) * OW + ow) * C + c;
+      const float yv = __bfloat162float(y[o]);
+      if (__bfloat162float(x[i]) == yv) {
+        // first-match tie break: only the earliest window position equal to the max gets the grad
+        int fh = -1, fw = -1;
+        for (int kh = 0; kh < k; ++kh)
+          for (int kw = 0; kw < k; ++kw) {
+            const int jh = oh * stride + kh, jw = ow * stride + kw;
+            if (fh < 0 && jh < H && jw < W &&
+                __bfloat162float(x[((static_cast<long>(b) * H + jh) * W + jw) * C + c]) == yv) {
+              fh = jh;
+              fw = jw;
+            }
+          }
+        if (fh == ih && fw == iw) g = __bfloat162float(dy[o]);
+      }
+    }
+    dx[i] = __float2bfloat16_rn(g);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+relu_mask_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ act, long n) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x)
+    if (!(__bfloat162float(act[i]) > 0.f)) dy[i] = __float2bfloat16_rn(0.f);
+}
+
+__global__ void __launch_bounds__(256)
+add_bf16_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ a,
+                const __nv_bfloat16* __restrict__ b, long n, int relu) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float v = __bfloat162float(a[i]) + __bfloat162float(b[i]);
+    if (relu) v = fmaxf(v, 0.f);
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+static inline int ew_grid(long n) {
+  long b = (n + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > 148 * 16) b = 148 * 16;
+  return static_cast<int>(b);
+}
+
+}  // namespace dk
+
+using namespace dk;
+
+extern "C" {
+
+int dk_input_stage(const void* x, int in_dtype, int B, int F, float scale, float shift, void* xb,
+                   int ldx, void* xt, int ldxt, int* step_counter, void* stream) {
+  dim3 grid((F + 31) / 32, (B + 31) / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* xbp = reinterpret_cast<__nv_bfloat16*>(xb);
+  __nv_bfloat16* xtp = reinterpret_cast<__nv_bfloat16*>(xt);
+  if (in_dtype == DK_IN_U8)
+    input_stage_kernel<uint8_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(x), B, F, scale,
+                                                      shift, xbp, ldx, xtp, ldxt, step_counter);
+  else if (in_dtype == DK_IN_F32)
+    input_stage_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), B, F, scale,
+                                                    shift, xbp, ldx, xtp, ldxt, step_counter);
+  else
+    input_stage_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                            B, F, scale, shift, xbp, ldx, xtp, ldxt,
+                                                            step_counter);
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_transpose_bf16(const void* src, int rows, int cols, int lds, void* dst, int ldd, void* stream) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), rows, cols, lds, reinterpret_cast<__nv_bfloat16*>(dst),
+      ldd);
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_rowsum_bf16(const void* src, int rows, int cols, int lds, float* out, float scale, void* stream) {
+  rowsum_bf16_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), rows, cols, lds, out, scale);
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_im2col(const void* x, int B, int H, int W, int C, int KH, int KW, int stride, int pad, int OH,
+              int OW, void* col, int ldcol, void* stream) {
+  const int cvec = (C % 8 == 0) ? 8 : 1;
+  const long total = static_cast<long>(B) * OH * OW * KH * KW * (C / cvec);
+  im2col_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, KH, KW, stride, pad, OH, OW,
+      reinterpret_cast<__nv_bfloat16*>(col), ldcol);
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_col2im(const void* col, int ldcol, int B, int H, int W, int C, int KH, int KW, int stride, int pad,
+              int OH, int OW, void* dx, void* stream) {
+  const long total = static_cast<long>(B) * H * W * C;
+  col2im_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(col), ldcol, B, H, W, C, KH, KW, stride, pad, OH, OW,
+      reinterpret_cast<__nv_bfloat16*>(dx));
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_maxpool_fwd(const void* x, int B, int H, int W, int C, int k, int stride, void* y, void* stream) {
+  const int OH = (H - k) / stride + 1, OW = (W - k) / stride + 1;
+  const long total = static_cast<long>(B) * OH * OW * C;
+  maxpool_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, k, stride, OH, OW,
+      reinterpret_cast<__nv_bfloat16*>(y));
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_maxpool_bwd(const void* x, const void* y, const void* dy, int B, int H, int W, int C, int k,
+                   int stride, void* dx, void* stream) {
+  const int OH = (H - k) / stride + 1, OW = (W - k) / stride + 1;
+  const long total = static_cast<long>(B) * H * W * C;
+  maxpool_bwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(y),
+      reinterpret_cast<const __nv_bfloat16*>(dy), B, H, W, C, k, stride, OH, OW,
+      reinterpret_cast<__nv_bfloat16*>(dx));
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_relu_mask_bf16(void* dy, const void* act, long n, void* stream) {
+  relu_mask_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(act), n);
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_add_bf16(void* dst, const void* a, const void* b, long n, int relu, void* stream) {
+  add_bf16_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<const __nv_bfloat16*>(a),
+      reinterpret_cast<const __nv_bfloat16*>(b), n, relu);
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

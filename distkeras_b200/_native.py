@@ -1,0 +1,183 @@
+"""ctypes binding of the native sm_100a runtime (``csrc/`` -> ``lib/libdistkeras_b200.so``).
+
+The library is built in-tree by ``build_native.py`` (``__graft_entry__.build``).  On a machine
+with a GPU the native path is mandatory: :func:`lib` raises if the shared object is missing
+instead of silently falling back to PyTorch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdistkeras_b200.so")
+
+_lib: Optional[C.CDLL] = None
+_lock = threading.Lock()
+
+i32, i64, f32, f64, vp = C.c_int, C.c_long, C.c_float, C.c_double, C.c_void_p
+u32 = C.c_uint
+
+
+class GemmEpilogue(C.Structure):
+    """Mirror of ``DkGemmEpilogue`` (csrc/gemm.h)."""
+
+    _fields_ = [
+        ("bias", vp), ("bias_along_m", i32), ("act", i32), ("mask", vp), ("ld_mask", i32),
+        ("d", vp), ("ldd", i32), ("d_fp32", i32), ("accumulate", i32), ("dt", vp), ("lddt", i32),
+        ("alpha", f32), ("drop_p", f32), ("drop_seed", u32), ("step", vp),
+    ]
+
+
+# op kinds (csrc/engine.h)
+OP_INPUT, OP_GEMM, OP_XENT, OP_ROWSUM, OP_TRANSPOSE, OP_OPTIM, OP_IM2COL, OP_COL2IM = range(8)
+OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_RELU_MASK, OP_ADD, OP_MEMSET = 8, 9, 10, 11, 12
+OP_PS_COMMIT, OP_PS_PULL, OP_PS_EXCHANGE, OP_PS_ELASTIC, OP_PS_DAMPED, OP_PS_TICKET = 13, 14, 15, 16, 17, 18
+OP_LOCK_ACQUIRE, OP_LOCK_RELEASE, OP_EAMSGD_PRE, OP_EAMSGD_POST, OP_CAST, OP_ELOSS = 19, 20, 21, 22, 23, 24
+OP_MEMCPY, OP_LABEL_INDEX = 25, 26
+
+OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6}
+IN_U8, IN_F32, IN_BF16 = 0, 1, 2
+LOSS_XENT, LOSS_MSE, LOSS_BCE = 0, 1, 2
+
+# control block words (csrc/ps.h)
+CTRL_NUM_UPDATES, CTRL_LOCK_NEXT, CTRL_LOCK_SERVING, CTRL_STOP = 0, 1, 2, 3
+CTRL_HEARTBEAT, CTRL_STALENESS_HIST, CTRL_WORDS = 16, 96, 128
+
+_SIGNATURES = {
+    # gemm
+    "dk_tmap_encode_2d": (i32, [vp, vp, i32, i64, i64, i64, i32]),
+    "dk_gemm_pick_bn": (i32, [i32]),
+    "dk_gemm_tn": (i32, [vp, i64, vp, i64, C.POINTER(GemmEpilogue), i32, i32, i32, i32, i32, vp]),
+    # ps
+    "dk_ps_commit": (i32, [vp, vp, vp, i64, f32, vp, vp, i32, u32, vp]),
+    "dk_ps_pull": (i32, [vp, vp, vp, vp, i64, vp, vp, vp]),
+    "dk_ps_exchange": (i32, [vp, vp, vp, vp, i64, f32, vp, vp, i32, u32, vp, vp]),
+    "dk_ps_elastic": (i32, [vp, vp, vp, i64, f32, vp, i32, u32, vp]),
+    "dk_ps_damped_exchange": (i32, [vp, vp, vp, vp, i64, f32, f32, vp, i32, u32, vp]),
+    "dk_ps_ticket": (i32, [vp, vp, vp, vp]),
+    "dk_ps_lock_acquire": (i32, [vp, vp, vp]),
+    "dk_ps_lock_release": (i32, [vp, vp, vp]),
+    "dk_ps_average": (i32, [C.POINTER(vp), i32, i64, i64, vp]),
+    "dk_ps_copy": (i32, [vp, vp, i64, vp]),
+    # optim / loss / nn
+    "dk_optim_step": (i32, [i32, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, f32, vp]),
+    "dk_eamsgd_pre": (i32, [vp, vp, vp, vp, i64, f32, vp]),
+    "dk_eamsgd_post": (i32, [vp, vp, vp, vp, i64, f32, vp]),
+    "dk_cast_bf16": (i32, [vp, vp, i64, vp]),
+    "dk_softmax_xent": (i32, [vp, i32, vp, vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, i32, vp]),
+    "dk_elementwise_loss": (i32, [i32, vp, vp, i32, i32, vp, i32, vp, i32, vp, vp, i32, vp]),
+    "dk_input_stage": (i32, [vp, i32, i32, i32, f32, f32, vp, i32, vp, i32, vp, vp]),
+    "dk_transpose_bf16": (i32, [vp, i32, i32, i32, vp, i32, vp]),
+    "dk_rowsum_bf16": (i32, [vp, i32, i32, i32, vp, f32, vp]),
+    "dk_im2col": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "dk_col2im": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "dk_maxpool_fwd": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "dk_maxpool_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "dk_relu_mask_bf16": (i32, [vp, vp, i64, vp]),
+    "dk_add_bf16": (i32, [vp, vp, vp, i64, i32, vp]),
+    "dk_label_index": (i32, [vp, i32, i32, f32, i32, vp, vp, vp, vp]),
+    # fabric
+    "dk_device_count": (i32, []),
+    "dk_set_device": (i32, [i32]),
+    "dk_fabric_alloc": (i32, [i64, C.POINTER(vp)]),
+    "dk_fabric_free": (i32, [vp]),
+    "dk_ipc_export": (i32, [vp, vp]),
+    "dk_ipc_open": (i32, [vp, C.POINTER(vp)]),
+    "dk_ipc_close": (i32, [vp]),
+    "dk_can_access_peer": (i32, [i32, i32]),
+    "dk_enable_peer_access": (i32, [i32, i32]),
+    "dk_host_alloc_pinned": (i32, [i64, C.POINTER(vp)]),
+    "dk_host_free_pinned": (i32, [vp]),
+    "dk_host_register": (i32, [vp, i64]),
+    "dk_host_unregister": (i32, [vp]),
+    "dk_memcpy_async": (i32, [vp, vp, i64, i32, vp]),
+    "dk_memset_async": (i32, [vp, i32, i64, vp]),
+    "dk_stream_sync": (i32, [vp]),
+    "dk_device_sync": (i32, []),
+    "dk_build_info": (C.c_char_p, []),
+    # engine
+    "dk_engine_create": (vp, []),
+    "dk_engine_destroy": (None, [vp]),
+    "dk_engine_new_list": (i32, [vp]),
+    "dk_engine_clear_list": (i32, [vp, i32]),
+    "dk_engine_set_slot": (i32, [vp, i32, vp]),
+    "dk_engine_add_op": (i32, [vp, i32, i32, C.POINTER(C.c_int64), i32, C.POINTER(f64), i32]),
+    "dk_engine_add_gemm": (i32, [vp, i32, vp, i64, vp, i64, i32, i32, i32, i32, i32, C.POINTER(GemmEpilogue)]),
+    "dk_engine_run": (i32, [vp, i32, vp]),
+    "dk_engine_list_size": (i32, [vp, i32]),
+    "dk_engine_list_kernels": (i32, [vp, i32]),
+    "dk_engine_launches": (i64, [vp]),
+}
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the native library; raise if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"native runtime {LIB_PATH} is missing: run `python build_native.py` "
+                "(the sm_100a kernels are mandatory on the GPU path; there is no PyTorch fallback)")
+        handle = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str = "native call") -> None:
+    if code != 0:
+        raise RuntimeError(f"{what} failed with code {code}")
+
+
+def ptr(t) -> int:
+    """Device (or host) address of a torch tensor, ``None`` -> 0."""
+    return 0 if t is None else int(t.data_ptr())
+
+
+def current_stream() -> int:
+    import torch
+
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+class CudaBuffer:
+    """Expose a raw device allocation to torch through ``__cuda_array_interface__``."""
+
+    def __init__(self, address: int, nbytes: int, typestr: str, shape, owner=None):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": typestr, "data": (int(address), False), "version": 2,
+            "strides": None,
+        }
+        self._owner = owner
+        self.nbytes = nbytes
+
+
+def as_tensor(address: int, shape, dtype, device_index: int, owner=None):
+    """Wrap raw device memory (e.g. a peer-mapped IPC pointer) as a torch tensor view."""
+    import numpy as np
+    import torch
+
+    np_dtype = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1", torch.bfloat16: None,
+                torch.int64: "<i8", torch.uint32 if hasattr(torch, "uint32") else None: "<u4"}.get(dtype)
+    shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    if np_dtype is None:  # bf16: view through int16
+        nbytes = int(np.prod(shape)) * 2
+        buf = CudaBuffer(address, nbytes, "<i2", shape, owner)
+        return torch.as_tensor(buf, device=torch.device("cuda", device_index)).view(torch.bfloat16)
+    nbytes = int(np.prod(shape)) * int(np_dtype[-1])
+    buf = CudaBuffer(address, nbytes, np_dtype, shape, owner)
+    return torch.as_tensor(buf, device=torch.device("cuda", device_index))

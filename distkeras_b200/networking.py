@@ -1,0 +1,118 @@
+"""Wire protocol of the socket parameter server (CPU / multi-host control path).
+
+Capability parity with ``distkeras/networking.py``: ``determine_host_address``, ``recvall``,
+``recv_data``, ``send_data``, ``connect``.  The reference frames every message as a 20-byte
+zero-padded ASCII length + a pickle (``networking.py:42-86``) and re-allocates the receive
+buffer on every chunk.  Here a message is an 16-byte binary header (magic, payload length) followed
+by a msgpack-free, copy-free encoding: a small pickled metadata dict plus the raw bytes of every
+tensor, received straight into a preallocated ``bytearray`` with ``recv_into``.
+
+On the GPU path none of this is used: commits and pulls are loads / atomics issued from CUDA
+kernels over NVLink (``csrc/ps_kernels.cu``).
+"""
+from __future__ import annotations
+
+import pickle
+import socket
+import struct
+from typing import Any
+
+import numpy as np
+
+_MAGIC = 0x444B3230  # "DK20"
+_HEADER = struct.Struct("!IIQ")  # magic, metadata length, raw payload length
+
+
+def determine_host_address() -> str:
+    """Address other processes can reach this host on (``networking.py:11-15``); falls back to
+    loopback when the hostname does not resolve (containers)."""
+    try:
+        return socket.gethostbyname(socket.gethostname())
+    except OSError:
+        return "127.0.0.1"
+
+
+def recvall(connection: socket.socket, num_bytes: int) -> bytearray:
+    """Read exactly ``num_bytes`` (``networking.py:18-39``) without quadratic re-allocation."""
+    buf = bytearray(num_bytes)
+    view = memoryview(buf)
+    got = 0
+    while got < num_bytes:
+        n = connection.recv_into(view[got:], num_bytes - got)
+        if n == 0:
+            raise ConnectionError("socket closed while receiving")
+        got += n
+    return buf
+
+
+def _encode(data: Any):
+    """Split ``data`` into (metadata, [raw buffers]); numpy arrays travel as raw bytes."""
+    buffers = []
+
+    def walk(obj):
+        if isinstance(obj, np.ndarray):
+            arr = np.ascontiguousarray(obj)
+            buffers.append(memoryview(arr).cast("B"))
+            return {"__nd__": len(buffers) - 1, "dtype": arr.dtype.str, "shape": arr.shape}
+        if isinstance(obj, dict):
+            return {k: walk(v) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return [walk(v) for v in obj]
+        try:
+            import torch
+
+            if isinstance(obj, torch.Tensor):
+                return walk(obj.detach().cpu().numpy())
+        except ImportError:  # pragma: no cover
+            pass
+        return obj
+
+    return walk(data), buffers
+
+
+def _decode(meta: Any, raw: memoryview, offsets):
+    def walk(obj):
+        if isinstance(obj, dict):
+            if "__nd__" in obj:
+                lo, hi = offsets[obj["__nd__"]]
+                return np.frombuffer(raw[lo:hi], dtype=np.dtype(obj["dtype"])).reshape(obj["shape"])
+            return {k: walk(v) for k, v in obj.items()}
+        if isinstance(obj, list):
+            return [walk(v) for v in obj]
+        return obj
+
+    return walk(meta)
+
+
+def send_data(connection: socket.socket, data: Any) -> None:
+    """Send one framed message (``networking.py:65-86``)."""
+    meta, buffers = _encode(data)
+    sizes = [len(b) for b in buffers]
+    meta_bytes = pickle.dumps({"meta": meta, "sizes": sizes}, -1)
+    connection.sendall(_HEADER.pack(_MAGIC, len(meta_bytes), sum(sizes)))
+    connection.sendall(meta_bytes)
+    for b in buffers:
+        connection.sendall(b)
+
+
+def recv_data(connection: socket.socket) -> Any:
+    """Receive one framed message (``networking.py:42-62``)."""
+    magic, meta_len, raw_len = _HEADER.unpack(bytes(recvall(connection, _HEADER.size)))
+    if magic != _MAGIC:
+        raise ConnectionError("bad frame magic")
+    info = pickle.loads(bytes(recvall(connection, meta_len)))
+    raw = memoryview(recvall(connection, raw_len)) if raw_len else memoryview(b"")
+    offsets, pos = [], 0
+    for s in info["sizes"]:
+        offsets.append((pos, pos + s))
+        pos += s
+    return _decode(info["meta"], raw, offsets)
+
+
+def connect(host: str, port: int, disable_nagle: bool = True) -> socket.socket:
+    """Open a TCP connection to the parameter server (``networking.py:89-99``)."""
+    fd = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+    if disable_nagle:
+        fd.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+    fd.connect((host, port))
+    return fd
