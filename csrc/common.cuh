@@ -238,6 +238,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Same for an MN-major operand tile: [K rows][64 MN elements = 128 bytes] boxes, 8-row atoms
+// along K at SBO = 1024 B, 64-element MN chunks at LBO = 8192 B (one 64-row TMA box each).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(8192 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16 / kind::tf32, fp32 accumulate, K-major A and B.
 //   bits [4,6)   D format: 1 = f32
 //   bits [7,10)  A format: 0 = f16, 1 = bf16, 2 = tf32

@@ -53,7 +53,7 @@ int run_op(Engine* e, Op& op, void* st) {
       return dk_input_stage(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (float)f[0], (float)f[1],
                             resolve(e, a[4]), (int)a[5], resolve(e, a[6]), (int)a[7], rp<int>(e, a[8]), st);
     case DK_OP_GEMM:
-      // M, N, K, bn, tf32 (tensor maps + epilogue pre-encoded)
+      // M, N, K, bn, flags (tensor maps + epilogue pre-encoded)
       return dk_gemm_tn_launch(&op.ta, &op.tb, &op.ep, (int)a[0], (int)a[1], (int)a[2], (int)a[3],
                                (int)a[4], st);
     case DK_OP_XENT:
@@ -71,6 +71,14 @@ int run_op(Engine* e, Op& op, void* st) {
       // src, rows, cols, lds, out | scale
       return dk_rowsum_bf16(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], rp<float>(e, a[4]),
                             (float)f[0], st);
+    case DK_OP_COLSUM:
+      // src, rows, cols, lds, out | scale
+      return dk_colsum_bf16(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], rp<float>(e, a[4]),
+                            (float)f[0], st);
+    case DK_OP_MEMCPY2D:
+      // dst, dpitch, src, spitch, width_bytes, height
+      return dk_memcpy2d_async(resolve(e, a[0]), (long)a[1], resolve(e, a[2]), (long)a[3], (long)a[4],
+                               (long)a[5], st);
     case DK_OP_TRANSPOSE:
       // src, rows, cols, lds, dst, ldd
       return dk_transpose_bf16(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], resolve(e, a[4]),
@@ -201,19 +209,18 @@ int dk_engine_add_op(void* h, int list, int kind, const int64_t* iargs, int ni, 
 
 // GEMM: D = epilogue(A[M,K] * B[N,K]^T); operands must be fixed device buffers.
 int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B, long ldb, int M, int N,
-                       int K, int tf32, int bn, const DkGemmEpilogue* ep) {
+                       int K, int flags, int bn, const DkGemmEpilogue* ep) {
   Engine* e = reinterpret_cast<Engine*>(h);
   if (list < 0 || list >= (int)e->lists.size()) return -1;
   Op op;
   memset(&op, 0, sizeof(op));
   op.kind = DK_OP_GEMM;
   if (bn <= 0) bn = dk_gemm_pick_bn(N);
-  int r = dk_tmap_encode_2d(&op.ta, A, tf32 ? DK_F32 : DK_BF16, M, K, lda, 128);
-  if (r != 0) return r;
-  r = dk_tmap_encode_2d(&op.tb, B, tf32 ? DK_F32 : DK_BF16, N, K, ldb, bn);
+  if ((flags & DK_GEMM_B_MN) && bn < 64) bn = 64;
+  int r = dk_gemm_encode_operands(&op.ta, &op.tb, A, lda, B, ldb, M, N, K, bn, flags);
   if (r != 0) return r;
   op.ep = *ep;
-  op.i[0] = M; op.i[1] = N; op.i[2] = K; op.i[3] = bn; op.i[4] = tf32;
+  op.i[0] = M; op.i[1] = N; op.i[2] = K; op.i[3] = bn; op.i[4] = flags;
   e->lists[list].push_back(op);
   return static_cast<int>(e->lists[list].size()) - 1;
 }
@@ -224,7 +231,7 @@ int dk_engine_run(void* h, int list, void* stream) {
   for (Op& op : e->lists[list]) {
     int r = run_op(e, op, stream);
     if (r != 0) return r;
-    if (op.kind != DK_OP_MEMSET && op.kind != DK_OP_MEMCPY) e->launches += 1;
+    if (op.kind != DK_OP_MEMSET && op.kind != DK_OP_MEMCPY && op.kind != DK_OP_MEMCPY2D) e->launches += 1;
   }
   return 0;
 }
@@ -241,7 +248,7 @@ int dk_engine_list_kernels(void* h, int list) {
   if (list < 0 || list >= (int)e->lists.size()) return -1;
   int n = 0;
   for (const Op& op : e->lists[list])
-    if (op.kind != DK_OP_MEMSET && op.kind != DK_OP_MEMCPY) ++n;
+    if (op.kind != DK_OP_MEMSET && op.kind != DK_OP_MEMCPY && op.kind != DK_OP_MEMCPY2D) ++n;
   return n;
 }
 

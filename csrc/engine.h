@@ -35,7 +35,9 @@ enum {
   DK_OP_CAST = 23,
   DK_OP_ELOSS = 24,
   DK_OP_MEMCPY = 25,
-  DK_OP_LABEL_INDEX = 26
+  DK_OP_LABEL_INDEX = 26,
+  DK_OP_COLSUM = 27,
+  DK_OP_MEMCPY2D = 28
 };
 
 #ifdef __cplusplus
@@ -51,7 +53,7 @@ int dk_engine_set_slot(void* h, int slot, void* p);
 int dk_engine_add_op(void* h, int list, int kind, const int64_t* iargs, int ni, const double* fargs,
                      int nf);
 int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B, long ldb, int M, int N,
-                       int K, int tf32, int bn, const DkGemmEpilogue* ep);
+                       int K, int flags, int bn, const DkGemmEpilogue* ep);
 int dk_engine_run(void* h, int list, void* stream);
 int dk_engine_list_size(void* h, int list);
 int dk_engine_list_kernels(void* h, int list);
@@ -60,6 +62,7 @@ long dk_engine_launches(void* h);
 // from fabric.cu
 int dk_memcpy_async(void* dst, const void* src, long bytes, int kind, void* stream);
 int dk_memset_async(void* dst, int value, long bytes, void* stream);
+int dk_memcpy2d_async(void* dst, long dpitch, const void* src, long spitch, long width, long height, void* stream);
 
 #ifdef __cplusplus
 }

@@ -127,6 +127,14 @@ int dk_memset_async(void* dst, int value, long bytes, void* stream) {
   return 0;
 }
 
+int dk_memcpy2d_async(void* dst, long dpitch, const void* src, long spitch, long width, long height,
+                      void* stream) {
+  DK_HOST_CHECK(cudaMemcpy2DAsync(dst, static_cast<size_t>(dpitch), src, static_cast<size_t>(spitch),
+                                  static_cast<size_t>(width), static_cast<size_t>(height),
+                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
 int dk_stream_sync(void* stream) {
   DK_HOST_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;

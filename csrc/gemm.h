@@ -10,6 +10,7 @@ typedef uint16_t dk_bf16;
 #endif
 
 enum { DK_BF16 = 0, DK_F32 = 1 };
+enum { DK_GEMM_TF32 = 1, DK_GEMM_A_MN = 2, DK_GEMM_B_MN = 4 };
 
 // Fused epilogue description: out = mask( act( alpha * acc + bias ) )
 typedef struct DkGemmEpilogue {
@@ -43,9 +44,11 @@ int dk_tmap_encode_2d(void* out_tmap, const void* base, int dtype, long rows, lo
                       int box_rows);
 int dk_gemm_pick_bn(int N);
 int dk_gemm_tn_launch(const void* tmap_a, const void* tmap_b, const DkGemmEpilogue* ep, int M, int N,
-                      int K, int bn, int tf32, void* stream);
+                      int K, int bn, int flags, void* stream);
+int dk_gemm_encode_operands(void* tmap_a, void* tmap_b, const void* A, long lda, const void* B, long ldb,
+                            int M, int N, int K, int bn, int flags);
 int dk_gemm_tn(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M,
-               int N, int K, int tf32, int bn, void* stream);
+               int N, int K, int flags, int bn, void* stream);
 
 #ifdef __cplusplus
 }

@@ -34,15 +34,22 @@ struct GemmSmem {
   static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;  // + align slack
 };
 
-template <int BN, int STAGES, bool TF32>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// AMN / BMN: the operand is MN-major in global memory, i.e. stored as [K, M] (resp. [K, N])
+// row-major with the M (N) index contiguous.  TMA then loads [64 K-rows x 64 MN-elements] boxes
+// (one 128-byte swizzle row per K index) and the UMMA descriptor walks K in 8-row atoms
+// (SBO = 1024 B) and MN in 64-element chunks (LBO = 8192 B).
+template <int BN, int STAGES, bool TF32, bool AMN, bool BMN>
+__global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 2 : 1))
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmEpilogue ep, const int M, const int N, const int K) {
   using S = GemmSmem<BN, STAGES, TF32>;
   constexpr int kBlockK = TF32 ? 32 : 64;   // elements per 128-byte swizzle row
   constexpr int kUmmaK = TF32 ? 8 : 16;     // 32 bytes of K per tcgen05.mma
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
-  constexpr uint32_t kIdesc = make_idesc(TF32 ? 2u : 1u, kBlockM, BN);
+  constexpr uint32_t kIdesc = make_idesc(TF32 ? 2u : 1u, kBlockM, BN) | (AMN ? (1u << 15) : 0u) |
+                              (BMN ? (1u << 16) : 0u);
+  static_assert(!(TF32 && (AMN || BMN)), "MN-major operands are implemented for 16-bit types only");
+  static_assert(!BMN || BN >= 64, "MN-major B needs BN >= 64");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -87,8 +94,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint8_t* sa = smem + stage * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
         mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-        tma_load_2d(sa, &tmap_a, kb * kBlockK, m0, &full_bar[stage]);
-        tma_load_2d(sb, &tmap_b, kb * kBlockK, n0, &full_bar[stage]);
+        if constexpr (AMN) {
+#pragma unroll
+          for (int c = 0; c < kBlockM / 64; ++c)
+            tma_load_2d(sa + c * 8192, &tmap_a, m0 + c * 64, kb * kBlockK, &full_bar[stage]);
+        } else {
+          tma_load_2d(sa, &tmap_a, kb * kBlockK, m0, &full_bar[stage]);
+        }
+        if constexpr (BMN) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_2d(sb + c * 8192, &tmap_b, n0 + c * 64, kb * kBlockK, &full_bar[stage]);
+        } else {
+          tma_load_2d(sb, &tmap_b, kb * kBlockK, n0, &full_bar[stage]);
+        }
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -105,15 +124,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (elect_one()) {
         const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
         const uint32_t sb = sa + S::kABytes;
-        const uint64_t adesc = make_smem_desc_sw128(sa);
-        const uint64_t bdesc = make_smem_desc_sw128(sb);
+        const uint64_t adesc = AMN ? make_smem_desc_sw128_mn(sa) : make_smem_desc_sw128(sa);
+        const uint64_t bdesc = BMN ? make_smem_desc_sw128_mn(sb) : make_smem_desc_sw128(sb);
+        // per-MMA advance along K in (addr >> 4) units: K-major = 32 bytes inside the swizzled
+        // row; MN-major = 16 K-rows = two 1024-byte atoms
+        constexpr uint32_t kAStep = AMN ? (2048 >> 4) : 2;
+        constexpr uint32_t kBStep = BMN ? (2048 >> 4) : 2;
 #pragma unroll
         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          // advance 32 bytes along K inside the swizzled row: +2 in (addr >> 4) units
           if constexpr (TF32)
-            umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+            umma_tf32(tmem_base, adesc + kAStep * k, bdesc + kBStep * k, kIdesc, (kb | k) != 0);
           else
-            umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+            umma_f16(tmem_base, adesc + kAStep * k, bdesc + kBStep * k, kIdesc, (kb | k) != 0);
         }
         umma_commit(&empty_bar[stage]);              // frees the smem slot once the MMAs retire
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulator complete
@@ -273,11 +295,11 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-template <int BN, int STAGES, bool TF32>
+template <int BN, int STAGES, bool TF32, bool AMN = false, bool BMN = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M,
                        int N, int K, cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES, TF32>;
-  auto kern = gemm_tn_kernel<BN, STAGES, TF32>;
+  auto kern = gemm_tn_kernel<BN, STAGES, TF32, AMN, BMN>;
   static bool configured = false;
   if (!configured) {
     DK_HOST_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -319,42 +341,80 @@ int dk_gemm_pick_bn(int N) {
   return 128;
 }
 
-// Launch with pre-encoded tensor maps (tmap_b must have been encoded with box_rows == bn).
+// Launch with pre-encoded tensor maps.  flags: DK_GEMM_TF32 | DK_GEMM_A_MN | DK_GEMM_B_MN.
+// K-major operand maps are encoded with box_rows = 128 (A) / bn (B) over a [rows, K] matrix;
+// MN-major operand maps with box_rows = 64 over the [K, rows] matrix.
 int dk_gemm_tn_launch(const void* tmap_a, const void* tmap_b, const DkGemmEpilogue* ep, int M, int N,
-                      int K, int bn, int tf32, void* stream) {
+                      int K, int bn, int flags, void* stream) {
   const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(tmap_a);
   const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(tmap_b);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (M <= 0 || N <= 0 || K <= 0) return -3;
+  const bool tf32 = flags & DK_GEMM_TF32, amn = flags & DK_GEMM_A_MN, bmn = flags & DK_GEMM_B_MN;
   if (tf32) {
+    if (amn || bmn) return -5;
     switch (bn) {
       case 16: return dk::launch_gemm<16, 4, true>(ta, tb, *ep, M, N, K, st);
       case 32: return dk::launch_gemm<32, 4, true>(ta, tb, *ep, M, N, K, st);
       case 64: return dk::launch_gemm<64, 4, true>(ta, tb, *ep, M, N, K, st);
-      case 128: return dk::launch_gemm<128, 4, true>(ta, tb, *ep, M, N, K, st);
+      case 128: return dk::launch_gemm<128, 3, true>(ta, tb, *ep, M, N, K, st);
       default: return -4;
     }
   }
-  switch (bn) {
-    case 16: return dk::launch_gemm<16, 6, false>(ta, tb, *ep, M, N, K, st);
-    case 32: return dk::launch_gemm<32, 6, false>(ta, tb, *ep, M, N, K, st);
-    case 64: return dk::launch_gemm<64, 6, false>(ta, tb, *ep, M, N, K, st);
-    case 128: return dk::launch_gemm<128, 4, false>(ta, tb, *ep, M, N, K, st);
-    case 256: return dk::launch_gemm<256, 4, false>(ta, tb, *ep, M, N, K, st);
+  if (!amn && !bmn) {
+    switch (bn) {
+      case 16: return dk::launch_gemm<16, 6, false>(ta, tb, *ep, M, N, K, st);
+      case 32: return dk::launch_gemm<32, 6, false>(ta, tb, *ep, M, N, K, st);
+      case 64: return dk::launch_gemm<64, 6, false>(ta, tb, *ep, M, N, K, st);
+      case 128: return dk::launch_gemm<128, 3, false>(ta, tb, *ep, M, N, K, st);
+      case 256: return dk::launch_gemm<256, 4, false>(ta, tb, *ep, M, N, K, st);
+      default: return -4;
+    }
+  }
+  if (!amn && bmn) {
+    switch (bn) {
+      case 64: return dk::launch_gemm<64, 6, false, false, true>(ta, tb, *ep, M, N, K, st);
+      case 128: return dk::launch_gemm<128, 3, false, false, true>(ta, tb, *ep, M, N, K, st);
+      case 256: return dk::launch_gemm<256, 4, false, false, true>(ta, tb, *ep, M, N, K, st);
+      default: return -4;
+    }
+  }
+  if (amn && bmn) {
+    switch (bn) {
+      case 64: return dk::launch_gemm<64, 6, false, true, true>(ta, tb, *ep, M, N, K, st);
+      case 128: return dk::launch_gemm<128, 3, false, true, true>(ta, tb, *ep, M, N, K, st);
+      case 256: return dk::launch_gemm<256, 4, false, true, true>(ta, tb, *ep, M, N, K, st);
+      default: return -4;
+    }
+  }
+  switch (bn) {  // A MN-major, B K-major
+    case 16: return dk::launch_gemm<16, 6, false, true, false>(ta, tb, *ep, M, N, K, st);
+    case 32: return dk::launch_gemm<32, 6, false, true, false>(ta, tb, *ep, M, N, K, st);
+    case 64: return dk::launch_gemm<64, 6, false, true, false>(ta, tb, *ep, M, N, K, st);
+    case 128: return dk::launch_gemm<128, 3, false, true, false>(ta, tb, *ep, M, N, K, st);
     default: return -4;
   }
 }
 
+int dk_gemm_encode_operands(void* tmap_a, void* tmap_b, const void* A, long lda, const void* B, long ldb,
+                            int M, int N, int K, int bn, int flags) {
+  const int dt = (flags & DK_GEMM_TF32) ? DK_F32 : DK_BF16;
+  int r = (flags & DK_GEMM_A_MN) ? dk_tmap_encode_2d(tmap_a, A, dt, K, M, lda, 64)
+                                 : dk_tmap_encode_2d(tmap_a, A, dt, M, K, lda, dk::kBlockM);
+  if (r != 0) return r;
+  return (flags & DK_GEMM_B_MN) ? dk_tmap_encode_2d(tmap_b, B, dt, K, N, ldb, 64)
+                                : dk_tmap_encode_2d(tmap_b, B, dt, N, K, ldb, bn);
+}
+
 // Convenience one-shot entry: encodes both tensor maps, then launches.
 int dk_gemm_tn(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M,
-               int N, int K, int tf32, int bn, void* stream) {
+               int N, int K, int flags, int bn, void* stream) {
   alignas(64) CUtensorMap ta, tb;
   if (bn <= 0) bn = dk_gemm_pick_bn(N);
-  int r = dk_tmap_encode_2d(&ta, A, tf32 ? DK_F32 : DK_BF16, M, K, lda, dk::kBlockM);
+  if ((flags & DK_GEMM_B_MN) && bn < 64) bn = 64;
+  int r = dk_gemm_encode_operands(&ta, &tb, A, lda, B, ldb, M, N, K, bn, flags);
   if (r != 0) return r;
-  r = dk_tmap_encode_2d(&tb, B, tf32 ? DK_F32 : DK_BF16, N, K, ldb, bn);
-  if (r != 0) return r;
-  return dk_gemm_tn_launch(&ta, &tb, ep, M, N, K, bn, tf32, stream);
+  return dk_gemm_tn_launch(&ta, &tb, ep, M, N, K, bn, flags, stream);
 }
 
 }  // extern "C"

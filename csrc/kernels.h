@@ -48,6 +48,9 @@ int dk_transpose_bf16(const void* src, int rows, int cols, int lds, void* dst, i
 // row sums of a bf16 matrix [rows, cols] (bias gradient from dZ^T): out[r] = sum_c src[r, c]
 int dk_rowsum_bf16(const void* src, int rows, int cols, int lds, float* out, float scale, void* stream);
 
+// column sums of a bf16 matrix [rows, cols]: out[c] += scale * sum_r src[r, c] (out pre-zeroed)
+int dk_colsum_bf16(const void* src, int rows, int cols, int lds, float* out, float scale, void* stream);
+
 // conv helpers (NHWC activations, bf16): im2col / col2im for KHxKW, stride, padding
 int dk_im2col(const void* x, int B, int H, int W, int C, int KH, int KW, int stride, int pad, int OH,
               int OW, void* col, int ldcol, void* stream);

@@ -93,6 +93,43 @@ rowsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, in
   if (lane == 0) out[row] = acc * scale;
 }
 
+// out[c] += scale * sum_r src[r, c]  (bias gradient from dZ [B, N]).  Grid = (column blocks of 64,
+// row splits); each warp reads 128-byte row segments (bf16x2 per lane), the block reduces through
+// shared memory and issues one fp32 atomicAdd per column.  `out` must be zeroed beforehand.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, int lds,
+                   float* __restrict__ out, float scale, int rows_per_block) {
+  __shared__ float red[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + lane * 2;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float a0 = 0.f, a1 = 0.f;
+  if (c + 1 < cols && (lds & 1) == 0) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + static_cast<size_t>(r) * lds + c);
+      const float2 f = __bfloat1622float2(v);
+      a0 += f.x;
+      a1 += f.y;
+    }
+  } else if (c < cols) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      a0 += __bfloat162float(src[static_cast<size_t>(r) * lds + c]);
+      if (c + 1 < cols) a1 += __bfloat162float(src[static_cast<size_t>(r) * lds + c + 1]);
+    }
+  }
+  red[warp][lane * 2] = a0;
+  red[warp][lane * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    const int col = blockIdx.x * 64 + threadIdx.x;
+    if (col < cols) atomicAdd(out + col, t * scale);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // convolution lowering (NHWC, bf16): col[(b, oh, ow), (kh, kw, c)]
 // ------------------------------------------------------------------------------------------
@@ -280,6 +317,17 @@ int dk_transpose_bf16(const void* src, int rows, int cols, int lds, void* dst, i
 int dk_rowsum_bf16(const void* src, int rows, int cols, int lds, float* out, float scale, void* stream) {
   rowsum_bf16_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(src), rows, cols, lds, out, scale);
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_colsum_bf16(const void* src, int rows, int cols, int lds, float* out, float scale, void* stream) {
+  int splits = (rows + 255) / 256;
+  if (splits > 64) splits = 64;
+  const int rpb = (rows + splits - 1) / splits;
+  dim3 grid((cols + 63) / 64, splits);
+  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows,
+                                                            cols, lds, out, scale, rpb);
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }

@@ -8,6 +8,8 @@ enum {
   DK_CTRL_LOCK_NEXT = 1,        // ticket lock (strict mode)
   DK_CTRL_LOCK_SERVING = 2,
   DK_CTRL_STOP = 3,             // stop flag (fault handling)
+  DK_CTRL_SHARD_NEXT = 4,       // dynamic shard queue: next unclaimed data partition
+  DK_CTRL_WORKERS_DONE = 5,     // workers that finished their shards
   DK_CTRL_HEARTBEAT = 16,       // + worker id: last iteration that committed
   DK_CTRL_STALENESS_HIST = 96,  // 32 buckets
   DK_CTRL_WORDS = 128
@@ -31,6 +33,7 @@ int dk_ps_elastic(float* center, float* w, void* wb, long n, float alpha, unsign
 int dk_ps_damped_exchange(float* center, float* w, float* w1, void* wb, long n, float scale,
                           float inv_lr, unsigned* ctrl, int worker, unsigned iteration, void* stream);
 int dk_ps_ticket(unsigned* ctrl, const unsigned* last_update, float* scale_out, void* stream);
+int dk_ps_fetch_add(unsigned* word, unsigned inc, unsigned* out, void* stream);
 int dk_ps_lock_acquire(unsigned* ctrl, unsigned* my_ticket, void* stream);
 int dk_ps_lock_release(unsigned* ctrl, const unsigned* my_ticket, void* stream);
 int dk_ps_average(float* const* peer_ptrs, int num_peers, long lo, long hi, void* stream);

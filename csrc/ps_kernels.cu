@@ -264,6 +264,14 @@ __global__ void ps_ticket_kernel(unsigned* ctrl, const unsigned* last_update, fl
   }
 }
 
+// Host-visible fetch-add on a control word (dynamic shard queue: workers claim the next data
+// partition; the replacement for Spark's task scheduler + `parallelism_factor` over-partitioning).
+__global__ void ps_fetch_add_kernel(unsigned* word, unsigned inc, unsigned* out) {
+  unsigned old;
+  asm volatile("atom.relaxed.sys.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(word), "r"(inc) : "memory");
+  *out = old;
+}
+
 // Ticket lock (strict mode): serialises whole commit(+pull) sequences like the reference's mutex.
 __global__ void ps_lock_acquire_kernel(unsigned* ctrl, unsigned* my_ticket) {
   unsigned t;
@@ -378,6 +386,12 @@ int dk_ps_damped_exchange(float* center, float* w, float* w1, void* wb, long n, 
 
 int dk_ps_ticket(unsigned* ctrl, const unsigned* last_update, float* scale_out, void* stream) {
   ps_ticket_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctrl, last_update, scale_out);
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_ps_fetch_add(unsigned* word, unsigned inc, unsigned* out, void* stream) {
+  ps_fetch_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(word, inc, out);
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }

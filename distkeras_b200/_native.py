@@ -36,14 +36,15 @@ OP_INPUT, OP_GEMM, OP_XENT, OP_ROWSUM, OP_TRANSPOSE, OP_OPTIM, OP_IM2COL, OP_COL
 OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_RELU_MASK, OP_ADD, OP_MEMSET = 8, 9, 10, 11, 12
 OP_PS_COMMIT, OP_PS_PULL, OP_PS_EXCHANGE, OP_PS_ELASTIC, OP_PS_DAMPED, OP_PS_TICKET = 13, 14, 15, 16, 17, 18
 OP_LOCK_ACQUIRE, OP_LOCK_RELEASE, OP_EAMSGD_PRE, OP_EAMSGD_POST, OP_CAST, OP_ELOSS = 19, 20, 21, 22, 23, 24
-OP_MEMCPY, OP_LABEL_INDEX = 25, 26
+OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D = 25, 26, 27, 28
+GEMM_TF32, GEMM_A_MN, GEMM_B_MN = 1, 2, 4
 
 OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6}
 IN_U8, IN_F32, IN_BF16 = 0, 1, 2
 LOSS_XENT, LOSS_MSE, LOSS_BCE = 0, 1, 2
 
 # control block words (csrc/ps.h)
-CTRL_NUM_UPDATES, CTRL_LOCK_NEXT, CTRL_LOCK_SERVING, CTRL_STOP = 0, 1, 2, 3
+CTRL_NUM_UPDATES, CTRL_LOCK_NEXT, CTRL_LOCK_SERVING, CTRL_STOP, CTRL_SHARD_NEXT, CTRL_WORKERS_DONE = 0, 1, 2, 3, 4, 5
 CTRL_HEARTBEAT, CTRL_STALENESS_HIST, CTRL_WORDS = 16, 96, 128
 
 _SIGNATURES = {
@@ -58,6 +59,7 @@ _SIGNATURES = {
     "dk_ps_elastic": (i32, [vp, vp, vp, i64, f32, vp, i32, u32, vp]),
     "dk_ps_damped_exchange": (i32, [vp, vp, vp, vp, i64, f32, f32, vp, i32, u32, vp]),
     "dk_ps_ticket": (i32, [vp, vp, vp, vp]),
+    "dk_ps_fetch_add": (i32, [vp, u32, vp, vp]),
     "dk_ps_lock_acquire": (i32, [vp, vp, vp]),
     "dk_ps_lock_release": (i32, [vp, vp, vp]),
     "dk_ps_average": (i32, [C.POINTER(vp), i32, i64, i64, vp]),
@@ -72,6 +74,7 @@ _SIGNATURES = {
     "dk_input_stage": (i32, [vp, i32, i32, i32, f32, f32, vp, i32, vp, i32, vp, vp]),
     "dk_transpose_bf16": (i32, [vp, i32, i32, i32, vp, i32, vp]),
     "dk_rowsum_bf16": (i32, [vp, i32, i32, i32, vp, f32, vp]),
+    "dk_colsum_bf16": (i32, [vp, i32, i32, i32, vp, f32, vp]),
     "dk_im2col": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
     "dk_col2im": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "dk_maxpool_fwd": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),

@@ -517,13 +517,13 @@ class Sequential:
         offset = 0
         for li, layer in enumerate(self.layers):
             for name, shp, trainable in layer.param_shapes(shape):
-                offset = (offset + 3) // 4 * 4  # keep every segment 16-byte aligned
+                offset = (offset + 7) // 8 * 8  # every segment 32-byte aligned (16 B in the bf16 shadow: TMA)
                 seg = ParamSegment(li, name, offset, shp, trainable)
                 self.segments.append(seg)
                 offset += seg.size
             shape = layer.output_shape(shape)
             self.shapes.append(shape)
-        total = (offset + 3) // 4 * 4
+        total = (offset + 7) // 8 * 8
         self.flat = torch.zeros(total, dtype=torch.float32)
         gen = torch.Generator()
         gen.manual_seed(self.seed if self.seed is not None else torch.seed() % (2 ** 31))

@@ -1,0 +1,509 @@
+"""Native sm_100a executor: planner + replica.
+
+``NativeReplica`` lowers a :class:`~distkeras_b200.models.core.Sequential` (Dense / Conv2D /
+MaxPooling2D / Flatten / Dropout / Activation stacks) with its loss and worker optimizer into flat
+op lists for the C++ executor (``csrc/engine.cu``).  One training step is
+
+    input stage (cast + MinMax affine)  ->  tcgen05 GEMM per layer (bias / ReLU / dropout fused)
+    -> fused softmax-xent (loss, accuracy, dZ)  ->  per layer: bias colsum, wgrad GEMM, dgrad GEMM
+    (dReLU / dropout mask fused)  ->  fused flat optimizer (+ bf16 shadow)
+
+All GEMMs are the hand-written tcgen05/TMEM/TMA kernel (``csrc/gemm_tcgen05.cu``); backward uses
+its MN-major operand mode, so no tensor is ever transposed in memory: dgrad reads the bf16 weight
+shadow ``[out, in]`` as an MN-major B operand and wgrad reads ``dZ [B, out]`` and the layer input
+``[B, in]`` as MN-major A / B operands.  The reference executes the same math through
+``keras_model.train_on_batch`` (``distkeras/workers.py:199-202, 327-342``).
+
+The replica owns flat buffers ``W`` (fp32 master = the ``get_weights()`` analogue), ``G``, ``Wb``
+(bf16 shadow), optimizer state and ``W1`` (last pulled center), which is exactly what the
+parameter-server kernels operate on.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..models.core import (Activation, Conv2D, Dense, Dropout, Flatten, MaxPooling2D, Sequential)
+from ..ops.flat_optim import FlatOptimizer, OptimizerSpec
+from .replica import Replica
+
+SLOT_X, SLOT_Y = 0, 1
+
+
+def _r8(n: int) -> int:
+    return (int(n) + 7) // 8 * 8
+
+
+class UnsupportedByNativeEngine(Exception):
+    """The model uses a layer / loss the native engine does not lower (autograd path is used)."""
+
+
+class _Block:
+    """One lowered layer group."""
+
+    def __init__(self, kind: str):
+        self.kind = kind  # dense | conv | pool | flatten
+        self.act: Optional[str] = None
+        self.drop_p = 0.0
+
+
+def _group_layers(model: Sequential) -> List[_Block]:
+    """Fold Activation / Dropout layers into the preceding Dense / Conv block."""
+    blocks: List[_Block] = []
+    model.build()
+    for li, layer in enumerate(model.layers):
+        in_shape, out_shape = model.shapes[li], model.shapes[li + 1]
+        if isinstance(layer, Dense):
+            if len(in_shape) != 1:
+                raise UnsupportedByNativeEngine("Dense on non-flat input")
+            b = _Block("dense")
+            b.layer_index, b.k_in, b.n_out = li, int(in_shape[0]), layer.units
+            b.act = layer.activation or "linear"
+            b.use_bias = layer.use_bias
+            blocks.append(b)
+        elif isinstance(layer, Conv2D):
+            b = _Block("conv")
+            b.layer_index = li
+            b.in_shape, b.out_shape = tuple(in_shape), tuple(out_shape)
+            b.kh, b.kw = layer.kernel_size
+            b.stride, b.pad = layer.strides[0], layer.pad_amount()
+            b.k_in = b.kh * b.kw * int(in_shape[-1])
+            b.n_out = layer.filters
+            b.act = layer.activation or "linear"
+            b.use_bias = layer.use_bias
+            if b.n_out % 8 != 0:
+                raise UnsupportedByNativeEngine("Conv2D filters must be a multiple of 8")
+            blocks.append(b)
+        elif isinstance(layer, MaxPooling2D):
+            if layer.pool_size[0] != layer.pool_size[1] or layer.strides != layer.pool_size:
+                raise UnsupportedByNativeEngine("only square non-overlapping max-pooling")
+            b = _Block("pool")
+            b.in_shape, b.out_shape, b.k = tuple(in_shape), tuple(out_shape), layer.pool_size[0]
+            blocks.append(b)
+        elif isinstance(layer, Flatten):
+            b = _Block("flatten")
+            blocks.append(b)
+        elif isinstance(layer, Activation):
+            if not blocks or blocks[-1].kind not in ("dense", "conv") or blocks[-1].act not in (None, "linear"):
+                raise UnsupportedByNativeEngine("free-standing Activation")
+            blocks[-1].act = layer.activation
+        elif isinstance(layer, Dropout):
+            if not blocks or blocks[-1].kind != "dense" or blocks[-1].drop_p:
+                raise UnsupportedByNativeEngine("Dropout must follow a Dense block")
+            blocks[-1].drop_p = layer.rate
+        else:
+            raise UnsupportedByNativeEngine(f"layer {layer.class_name}")
+    for b in blocks[:-1]:
+        if b.kind in ("dense", "conv") and b.act not in ("relu", "linear"):
+            raise UnsupportedByNativeEngine(f"hidden activation {b.act!r}")
+    last = blocks[-1]
+    if last.kind != "dense" or last.act not in ("softmax", "linear", "sigmoid"):
+        raise UnsupportedByNativeEngine("the model must end in a Dense softmax / linear / sigmoid head")
+    if last.drop_p:
+        raise UnsupportedByNativeEngine("dropout on the output layer")
+    return blocks
+
+
+class NativeReplica(Replica):
+    """A model replica executed by the native sm_100a engine on one GPU."""
+
+    def __init__(self, model: Sequential, optimizer, loss: str, batch_size: int, device_index: int = 0,
+                 in_dtype: str = "u8", input_affine: Tuple[float, float] = (1.0, 0.0), hist_slots: int = 1024,
+                 dense_labels: bool = False, seed: int = 1234, training: bool = True):
+        self.lib = N.lib()
+        model.build()
+        self.model = model
+        self.loss = loss
+        self.B = int(batch_size)
+        self.device = torch.device("cuda", device_index)
+        self.device_index = device_index
+        torch.cuda.set_device(self.device)
+        self.in_dtype = {"u8": N.IN_U8, "f32": N.IN_F32, "bf16": N.IN_BF16}[in_dtype]
+        self.in_torch_dtype = {"u8": torch.uint8, "f32": torch.float32, "bf16": torch.bfloat16}[in_dtype]
+        self.scale, self.shift = float(input_affine[0]), float(input_affine[1])
+        self.hist_slots = int(hist_slots)
+        self.dense_labels = bool(dense_labels)
+        self.seed = int(seed)
+        self.blocks = _group_layers(model)
+        head = self.blocks[-1]
+        self.num_classes = head.n_out
+        if loss in ("categorical_crossentropy", "sparse_categorical_crossentropy"):
+            if head.act != "softmax":
+                raise UnsupportedByNativeEngine("cross-entropy needs a softmax head")
+            self.loss_kind = "xent"
+        elif loss in ("mse", "mean_squared_error") and head.act == "linear":
+            self.loss_kind = "mse"
+            self.dense_labels = True
+        else:
+            raise UnsupportedByNativeEngine(f"loss {loss!r} with head {head.act!r}")
+
+        dev = self.device
+        P = model.num_params
+        self.P = P
+        self.W = model.get_flat_weights().detach().to(dev, torch.float32).clone().contiguous()
+        self.Wb = torch.zeros(P, dtype=torch.bfloat16, device=dev)
+        self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.hist = torch.zeros(self.hist_slots, 2, dtype=torch.float32, device=dev)
+        self.training = training
+        if training:
+            self.G = torch.zeros(P, dtype=torch.float32, device=dev)
+            self.opt = FlatOptimizer(optimizer, P, dev)
+            self.W1 = None
+        self._keep: list = []  # buffers referenced only by raw pointers
+        self.engine = self.lib.dk_engine_create()
+        self.L_step = self.lib.dk_engine_new_list(self.engine) if training else -1
+        self.L_fwd = self.lib.dk_engine_new_list(self.engine)
+        self._input_feats = int(np.prod(model.input_shape))
+        self._lower()
+        self.refresh_shadow()
+        self.iteration = 0
+        # eager single-step staging (train_on_batch / predict convenience API)
+        self._x_stage = torch.zeros(self.B, self._input_feats, dtype=self.in_torch_dtype, device=dev)
+        if self.dense_labels:
+            self._y_stage = torch.zeros(self.B, self.num_classes, dtype=torch.float32, device=dev)
+        else:
+            self._y_stage = torch.zeros(self.B, dtype=torch.int32, device=dev)
+
+    # ------------------------------------------------------------------------------------------
+    # op-list helpers
+    # ------------------------------------------------------------------------------------------
+    def _buf(self, *shape, dtype=torch.bfloat16) -> torch.Tensor:
+        t = torch.zeros(*shape, dtype=dtype, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def _add(self, lst: int, kind: int, iargs, fargs=()) -> None:
+        ia = (C.c_int64 * len(iargs))(*[int(v) for v in iargs])
+        fa = (C.c_double * max(1, len(fargs)))(*[float(v) for v in fargs]) if fargs else (C.c_double * 1)(0.0)
+        r = self.lib.dk_engine_add_op(self.engine, lst, kind, ia, len(iargs), fa, len(fargs))
+        if r < 0:
+            raise RuntimeError(f"dk_engine_add_op({kind}) failed: {r}")
+
+    def _gemm(self, lst: int, A: int, lda: int, Bp: int, ldb: int, M: int, Nn: int, K: int, flags: int,
+              ep: N.GemmEpilogue, bn: int = 0) -> None:
+        r = self.lib.dk_engine_add_gemm(self.engine, lst, C.c_void_p(A), lda, C.c_void_p(Bp), ldb, M, Nn, K,
+                                        flags, bn, C.byref(ep))
+        if r < 0:
+            raise RuntimeError(f"dk_engine_add_gemm(M={M}, N={Nn}, K={K}, flags={flags}) failed: {r}")
+
+    def _seg(self, layer_index: int, name: str):
+        for s in self.model.segments:
+            if s.layer_index == layer_index and s.name == name:
+                return s
+        return None
+
+    # ------------------------------------------------------------------------------------------
+    # lowering
+    # ------------------------------------------------------------------------------------------
+    def _lower(self) -> None:
+        B, lib = self.B, self.lib
+        F = self._input_feats
+        in_shape = tuple(self.model.input_shape)
+        # activation record: dict(ptr, rows, cols, ld, nhwc shape or None, tensor)
+        x0 = self._buf(B, _r8(F))
+        cur = dict(t=x0, rows=B, cols=F, ld=_r8(F), nhwc=in_shape if len(in_shape) == 3 else None)
+        if cur["nhwc"] is not None and F % 8 != 0 and False:
+            pass
+        lists = [l for l in (self.L_step, self.L_fwd) if l >= 0]
+        for lst in lists:
+            self._add(lst, N.OP_INPUT,
+                      [-(SLOT_X + 1), self.in_dtype, B, F, x0.data_ptr(), cur["ld"], 0, 0,
+                       self.step_counter.data_ptr() if lst == self.L_step else 0],
+                      [self.scale, self.shift])
+        # padded weight shadows are refreshed at the top of every program
+        self._pad_refresh: list = []
+        wptr_f32 = self.W.data_ptr()
+        wb_ptr = self.Wb.data_ptr()
+        fwd_records = []
+        nblocks = len(self.blocks)
+        for bi, b in enumerate(self.blocks):
+            is_last = bi == nblocks - 1
+            if b.kind in ("dense", "conv"):
+                kseg = self._seg(b.layer_index, "kernel")
+                bseg = self._seg(b.layer_index, "bias") if b.use_bias else None
+                K, Nout = b.k_in, b.n_out
+                # bf16 weight shadow [Nout, K] with a TMA-legal leading dimension
+                if K % 8 == 0:
+                    b.wb_ptr, b.wb_ld = wb_ptr + 2 * kseg.offset, K
+                else:
+                    pad = self._buf(Nout, _r8(K))
+                    b.wb_ptr, b.wb_ld = pad.data_ptr(), _r8(K)
+                    self._pad_refresh.append((pad.data_ptr(), _r8(K) * 2, wb_ptr + 2 * kseg.offset, K * 2, K * 2, Nout))
+                b.kseg, b.bseg = kseg, bseg
+                b.inp = cur
+                if b.kind == "conv":
+                    H, Wd, Cin = b.in_shape
+                    OH, OW, _ = b.out_shape
+                    rows = B * OH * OW
+                    col = self._buf(rows, _r8(K))
+                    b.col = dict(t=col, rows=rows, cols=K, ld=_r8(K), nhwc=None)
+                    for lst in lists:
+                        self._add(lst, N.OP_IM2COL, [cur["t"].data_ptr(), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad,
+                                                     OH, OW, col.data_ptr(), _r8(K)])
+                    a_in = b.col
+                else:
+                    rows = B
+                    a_in = cur
+                b.a_in = a_in
+                if is_last:
+                    out = self._buf(rows, Nout, dtype=torch.float32)
+                    rec = dict(t=out, rows=rows, cols=Nout, ld=Nout, nhwc=None)
+                else:
+                    out = self._buf(rows, _r8(Nout))
+                    rec = dict(t=out, rows=rows, cols=Nout, ld=_r8(Nout),
+                               nhwc=b.out_shape if b.kind == "conv" else None)
+                for lst in lists:
+                    ep = N.GemmEpilogue()
+                    ep.bias = (wptr_f32 + 4 * bseg.offset) if bseg is not None else None
+                    ep.act = 1 if b.act == "relu" else 0
+                    ep.d, ep.ldd, ep.d_fp32 = out.data_ptr(), rec["ld"], 1 if is_last else 0
+                    ep.alpha = 1.0
+                    if lst == self.L_step and b.drop_p > 0:
+                        ep.drop_p = b.drop_p
+                        ep.drop_seed = (self.seed * 7919 + bi * 104729) & 0xFFFFFFFF
+                        ep.step = self.step_counter.data_ptr()
+                    self._gemm(lst, a_in["t"].data_ptr(), a_in["ld"], b.wb_ptr, b.wb_ld, rows, Nout, K, 0, ep)
+                b.out = rec
+                cur = rec
+            elif b.kind == "pool":
+                H, Wd, Cc = b.in_shape
+                OH, OW, _ = b.out_shape
+                out = self._buf(B * OH * OW, Cc)
+                rec = dict(t=out, rows=B * OH * OW, cols=Cc, ld=Cc, nhwc=b.out_shape)
+                for lst in lists:
+                    self._add(lst, N.OP_MAXPOOL_FWD, [cur["t"].data_ptr(), B, H, Wd, Cc, b.k, b.k, out.data_ptr()])
+                b.inp, b.out = cur, rec
+                cur = rec
+            elif b.kind == "flatten":
+                if cur["ld"] != cur["cols"]:
+                    raise UnsupportedByNativeEngine("flatten of a padded activation")
+                feat = cur["rows"] * cur["cols"] // B
+                if feat % 8 != 0:
+                    raise UnsupportedByNativeEngine("flattened feature count must be a multiple of 8")
+                rec = dict(t=cur["t"], rows=B, cols=feat, ld=feat, nhwc=None)
+                b.inp, b.out = cur, rec
+                cur = rec
+        self.logits = cur["t"]
+        Cn = self.num_classes
+        self.probs = self._buf(B, Cn, dtype=torch.float32)
+        self._zero_labels = self._buf(B, dtype=torch.int32)
+        # inference tail: probabilities
+        self._add(self.L_fwd, N.OP_XENT, [self.logits.data_ptr(), Cn, self._zero_labels.data_ptr(), 0, B, Cn, 0, 0,
+                                          0, 0, self.probs.data_ptr(), 0, 0, 0])
+        self._prepend_pad_refresh(self.L_fwd)
+        if not self.training:
+            return
+        lst = self.L_step
+        # ---- loss ----
+        ldz = _r8(Cn)
+        dz = self._buf(B, ldz)
+        if self.loss_kind == "xent":
+            self._add(lst, N.OP_XENT, [self.logits.data_ptr(), Cn,
+                                       0 if self.dense_labels else -(SLOT_Y + 1),
+                                       -(SLOT_Y + 1) if self.dense_labels else 0,
+                                       B, Cn, dz.data_ptr(), ldz, 0, 0, 0, self.hist.data_ptr(),
+                                       self.step_counter.data_ptr(), self.hist_slots])
+        else:
+            self._add(lst, N.OP_ELOSS, [N.LOSS_MSE, self.logits.data_ptr(), -(SLOT_Y + 1), B, Cn, dz.data_ptr(), ldz,
+                                        0, 0, self.hist.data_ptr(), self.step_counter.data_ptr(), self.hist_slots])
+        self._add(lst, N.OP_MEMSET, [self.G.data_ptr(), 0, self.P * 4])
+        # ---- backward ----
+        g_ptr = self.G.data_ptr()
+        grad = dict(t=dz, rows=B, cols=Cn, ld=ldz)
+        premasked = True  # dZ of the head is already w.r.t. the logits
+        first_param_block = next(i for i, b in enumerate(self.blocks) if b.kind in ("dense", "conv"))
+        for bi in range(nblocks - 1, -1, -1):
+            b = self.blocks[bi]
+            if b.kind in ("dense", "conv"):
+                rows, K, Nout = b.out["rows"], b.k_in, b.n_out
+                if b.act == "relu" and not premasked:
+                    self._add(lst, N.OP_RELU_MASK, [grad["t"].data_ptr(), b.out["t"].data_ptr(), rows * grad["ld"]])
+                if b.bseg is not None:
+                    self._add(lst, N.OP_COLSUM, [grad["t"].data_ptr(), rows, Nout, grad["ld"],
+                                                 g_ptr + 4 * b.bseg.offset], [1.0])
+                # wgrad: dW[Nout, K] = dZ^T[Nout, rows] * In[rows, K]  (both operands MN-major views)
+                ep = N.GemmEpilogue()
+                ep.d, ep.ldd, ep.d_fp32, ep.alpha = g_ptr + 4 * b.kseg.offset, K, 1, 1.0
+                self._gemm(lst, grad["t"].data_ptr(), grad["ld"], b.a_in["t"].data_ptr(), b.a_in["ld"], Nout, K,
+                           rows, N.GEMM_A_MN | N.GEMM_B_MN, ep)
+                if bi == first_param_block:
+                    break
+                # dgrad: dIn[rows, K] = dZ[rows, Nout] * W[Nout, K]   (W read as an MN-major B operand)
+                prev = self.blocks[bi - 1]
+                din = self._buf(rows, _r8(K))
+                ep = N.GemmEpilogue()
+                ep.d, ep.ldd, ep.alpha = din.data_ptr(), _r8(K), 1.0
+                fuse_mask = b.kind == "dense" and prev.kind == "dense" and prev.act == "relu"
+                if fuse_mask:
+                    ep.mask, ep.ld_mask = prev.out["t"].data_ptr(), prev.out["ld"]
+                    if prev.drop_p > 0:
+                        ep.alpha = 1.0 / (1.0 - prev.drop_p)
+                elif b.kind == "dense" and prev.kind == "dense" and prev.drop_p > 0:
+                    raise UnsupportedByNativeEngine("dropout after a non-ReLU dense layer")
+                self._gemm(lst, grad["t"].data_ptr(), grad["ld"], b.wb_ptr, b.wb_ld, rows, K, Nout, N.GEMM_B_MN, ep)
+                if b.kind == "conv":
+                    H, Wd, Cin = b.in_shape
+                    OH, OW, _ = b.out_shape
+                    dx = self._buf(B * H * Wd, Cin)
+                    self._add(lst, N.OP_COL2IM, [din.data_ptr(), _r8(K), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad,
+                                                 OH, OW, dx.data_ptr()])
+                    grad = dict(t=dx, rows=B * H * Wd, cols=Cin, ld=Cin)
+                    premasked = False
+                else:
+                    grad = dict(t=din, rows=rows, cols=K, ld=_r8(K))
+                    premasked = fuse_mask
+            elif b.kind == "pool":
+                H, Wd, Cc = b.in_shape
+                dx = self._buf(B * H * Wd, Cc)
+                self._add(lst, N.OP_MAXPOOL_BWD, [b.inp["t"].data_ptr(), b.out["t"].data_ptr(), grad["t"].data_ptr(),
+                                                  B, H, Wd, Cc, b.k, b.k, dx.data_ptr()])
+                grad = dict(t=dx, rows=B * H * Wd, cols=Cc, ld=Cc)
+                premasked = False
+            elif b.kind == "flatten":
+                inp = b.inp
+                grad = dict(t=grad["t"], rows=inp["rows"], cols=inp["cols"], ld=inp["ld"])
+        # ---- optimizer (one fused launch over the flat buffer, emits the bf16 shadow) ----
+        o = self.opt
+        self._add(lst, N.OP_OPTIM, [N.OPT_KINDS[o.kernel_kind], self.W.data_ptr(), g_ptr, N.ptr(o.s0), N.ptr(o.s1),
+                                    self.Wb.data_ptr(), self.P, int(o.nesterov), self.step_counter.data_ptr()],
+                  [o.lr, o.p0, o.p1, o.eps, o.decay, 1.0])
+        self._prepend_pad_refresh(lst)
+
+    def _prepend_pad_refresh(self, lst: int) -> None:
+        # pad refresh ops are appended; order inside a list only matters relative to the GEMMs that
+        # read the padded shadows, so they live in a dedicated list run before `lst`.
+        if not self._pad_refresh:
+            return
+        if not hasattr(self, "L_pad"):
+            self.L_pad = self.lib.dk_engine_new_list(self.engine)
+            for dst, dpitch, src, spitch, width, height in self._pad_refresh:
+                self._add(self.L_pad, N.OP_MEMCPY2D, [dst, dpitch, src, spitch, width, height])
+
+    # ------------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------------
+    def _run(self, lst: int) -> None:
+        r = self.lib.dk_engine_run(self.engine, lst, C.c_void_p(N.current_stream()))
+        if r != 0:
+            raise RuntimeError(f"dk_engine_run(list {lst}) failed: {r}")
+
+    def refresh_shadow(self) -> None:
+        """Recompute the bf16 shadow from the fp32 master (after an external write to ``W``)."""
+        N.check(self.lib.dk_cast_bf16(self.W.data_ptr(), self.Wb.data_ptr(), self.P, C.c_void_p(N.current_stream())),
+                "dk_cast_bf16")
+
+    weights_changed = refresh_shadow
+
+    def enqueue_step(self, x_ptr: int, y_ptr: int) -> None:
+        """Enqueue one training step reading its batch from device pointers (graph-capturable)."""
+        self.lib.dk_engine_set_slot(self.engine, SLOT_X, C.c_void_p(x_ptr))
+        self.lib.dk_engine_set_slot(self.engine, SLOT_Y, C.c_void_p(y_ptr))
+        if hasattr(self, "L_pad"):
+            self._run(self.L_pad)
+        self._run(self.L_step)
+
+    def enqueue_forward(self, x_ptr: int) -> None:
+        self.lib.dk_engine_set_slot(self.engine, SLOT_X, C.c_void_p(x_ptr))
+        if hasattr(self, "L_pad"):
+            self._run(self.L_pad)
+        self._run(self.L_fwd)
+
+    def step_kernel_count(self) -> int:
+        n = self.lib.dk_engine_list_kernels(self.engine, self.L_step)
+        return n
+
+    def launches(self) -> int:
+        return int(self.lib.dk_engine_launches(self.engine))
+
+    # -- eager convenience API (Replica interface) ------------------------------------------------
+    def _stage_inputs(self, x, y=None) -> None:
+        x = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+        if x.shape[0] != self.B:
+            raise ValueError(f"native replica was planned for batch {self.B}, got {x.shape[0]}")
+        self._x_stage.copy_(x.reshape(self.B, -1).to(self.in_torch_dtype), non_blocking=True)
+        if y is not None:
+            y = y if isinstance(y, torch.Tensor) else torch.as_tensor(np.asarray(y))
+            if self.dense_labels:
+                self._y_stage.copy_(y.reshape(self.B, -1).to(torch.float32), non_blocking=True)
+            else:
+                if y.dim() == 2 and y.shape[1] > 1:
+                    y = y.argmax(dim=1)
+                self._y_stage.copy_(y.reshape(-1).to(torch.int32), non_blocking=True)
+
+    def train_on_batch(self, x, y):
+        self._stage_inputs(x, y)
+        slot = int(self.step_counter.item()) % self.hist_slots
+        self.hist[slot].zero_()
+        self.enqueue_step(self._x_stage.data_ptr(), self._y_stage.data_ptr())
+        self.iteration += 1
+        rec = self.hist[slot].tolist()
+        return float(rec[0]), float(rec[1])
+
+    @torch.no_grad()
+    def predict(self, x) -> torch.Tensor:
+        self._stage_inputs(x)
+        self.enqueue_forward(self._x_stage.data_ptr())
+        return self.probs.clone()
+
+    def set_flat(self, flat: torch.Tensor) -> None:
+        with torch.no_grad():
+            self.W.copy_(flat.to(self.W.device, torch.float32))
+        self.refresh_shadow()
+
+    def ensure_snapshot(self) -> torch.Tensor:
+        if self.W1 is None:
+            self.W1 = self.W.clone()
+        return self.W1
+
+    def set_learning_rate(self, lr: float) -> None:
+        raise NotImplementedError("re-plan the replica to change the learning rate")
+
+    def close(self) -> None:
+        if self.engine:
+            self.lib.dk_engine_destroy(self.engine)
+            self.engine = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def try_native_replica(model: Sequential, optimizer, loss: str, batch_size: int, device_index: int,
+                       **kw) -> Optional[NativeReplica]:
+    """``NativeReplica`` if the model is lowerable, else ``None`` (caller uses the autograd path)."""
+    try:
+        return NativeReplica(model, optimizer, loss, batch_size, device_index, **kw)
+    except UnsupportedByNativeEngine:
+        return None
+
+
+def native_predict(model: Sequential, x: torch.Tensor, batch_size: int, device) -> Optional[torch.Tensor]:
+    """Batched inference through the native engine (reference op K14); ``None`` if not lowerable."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    n = int(x.shape[0])
+    if n == 0:
+        return torch.empty(0, model.output_shape[-1])
+    bs = min(batch_size, max(8, _r8(n)))
+    in_dtype = "u8" if x.dtype == torch.uint8 else "f32"
+    try:
+        rep = NativeReplica(model, "sgd", "categorical_crossentropy", bs, idx, in_dtype=in_dtype, training=False)
+    except UnsupportedByNativeEngine:
+        return None
+    outs = []
+    flat = x.reshape(n, -1)
+    for i in range(0, n, bs):
+        chunk = flat[i:i + bs]
+        m = chunk.shape[0]
+        if m < bs:
+            pad = torch.zeros(bs - m, flat.shape[1], dtype=flat.dtype)
+            chunk = torch.cat([chunk, pad], dim=0)
+        outs.append(rep.predict(chunk)[:m].cpu())
+    rep.close()
+    return torch.cat(outs, dim=0)

@@ -1,0 +1,624 @@
+"""Multi-GPU runtime: fabric workers (CUDA-graph windows + in-kernel commit / pull) and the
+process orchestration behind ``trainer.train`` on B200.
+
+Topology: one process per GPU.  Rank 0 allocates the center variable + control block
+in its HBM (:class:`~distkeras_b200.parallel.fabric.FabricRegion`) and exports it over CUDA IPC;
+every rank (rank 0 included -- the parameter server is passive memory, so its SMs are free to run
+a worker too) maps it and runs a :class:`FabricWorker`.
+
+A fabric worker executes its algorithm as a device program.  For ADAG with window ``tau``:
+
+    graph[parity] = memset(hist) ; tau x {input stage, forward, loss, backward, optimizer} ;
+                    exchange kernel (commit (W - W1)/tau with atom.add.sys over NVLink, adopt the
+                    returned center) ; D2H of the window's loss / accuracy records
+
+and the host only (a) DMA-copies the next window's mini-batches from pinned memory on a copy
+stream and (b) replays the graph.  The reference does the same work with ``train_on_batch`` +
+numpy + pickle + TCP per window (``distkeras/workers.py:327-342``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import socket
+import tempfile
+import time
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..data import Dataset, Partition
+from ..utils import deserialize_keras_model, serialize_keras_model
+from .engine import NativeReplica, UnsupportedByNativeEngine
+from .fabric import FabricRegion
+
+
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+# ================================================================================================
+# fabric worker
+# ================================================================================================
+class FabricWorker:
+    """One worker replica driven by per-window CUDA graphs."""
+
+    def __init__(self, model, optimizer, loss: str, algorithm: dict, region: FabricRegion, worker_id: int,
+                 batch_size: int, device_index: int, in_dtype: str, input_affine=(1.0, 0.0), comm: str = "exchange",
+                 strict: bool = False, dense_labels: bool = False, seed: int = 0):
+        self.alg = dict(algorithm)
+        self.tau = int(self.alg["window"])
+        self.region = region
+        self.worker_id = int(worker_id)
+        self.B = int(batch_size)
+        self.comm = "commit_pull" if strict else comm
+        self.strict = strict
+        self.device_index = device_index
+        self.rep = NativeReplica(model, optimizer, loss, batch_size, device_index, in_dtype=in_dtype,
+                                 input_affine=input_affine, hist_slots=2 * self.tau, dense_labels=dense_labels,
+                                 seed=seed + 7 * worker_id)
+        rep = self.rep
+        dev = rep.device
+        self.lib = rep.lib
+        self.F = rep._input_feats
+        rep.ensure_snapshot()
+        self.last_update = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.scale_dev = torch.ones(1, dtype=torch.float32, device=dev)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.alg["kind"] == "eamsgd":
+            self.mom = torch.zeros(rep.P, dtype=torch.float32, device=dev)
+            self.wcopy = torch.zeros(rep.P, dtype=torch.float32, device=dev)
+        # double-buffered window staging
+        self.x_stage = [torch.zeros(self.tau * self.B, self.F, dtype=rep.in_torch_dtype, device=dev) for _ in (0, 1)]
+        if dense_labels:
+            self.y_stage = [torch.zeros(self.tau * self.B, rep.num_classes, dtype=torch.float32, device=dev)
+                            for _ in (0, 1)]
+        else:
+            self.y_stage = [torch.zeros(self.tau * self.B, dtype=torch.int32, device=dev) for _ in (0, 1)]
+        self.hist_host = [torch.zeros(self.tau, 2, dtype=torch.float32).pin_memory() for _ in (0, 1)]
+        self.compute = torch.cuda.Stream(device=dev)
+        self.copy = torch.cuda.Stream(device=dev)
+        self.copied = [torch.cuda.Event() for _ in (0, 1)]
+        self.done = [torch.cuda.Event() for _ in (0, 1)]
+        self.graphs: List[Optional[torch.cuda.CUDAGraph]] = [None, None]
+        self.kernels_per_window = 0
+        self.windows_run = 0
+        self.history: List[dict] = []
+        self.iteration = 0
+        self._pending: List[Optional[int]] = [None, None]  # first iteration of the window in flight per parity
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # -- device program pieces -------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(N.current_stream())
+
+    def _comm_ops(self) -> None:
+        """Enqueue the window-boundary communication of the algorithm on the current stream."""
+        rep, reg, lib, k = self.rep, self.region, self.lib, self.alg["kind"]
+        c, ctrl = C.c_void_p(reg.center_ptr), C.c_void_p(reg.ctrl_ptr)
+        W, W1, Wb = rep.W.data_ptr(), rep.W1.data_ptr(), rep.Wb.data_ptr()
+        st = self._stream()
+        it = 0  # heartbeat value is informational; the window index is added host-side
+        if self.strict:
+            N.check(lib.dk_ps_lock_acquire(ctrl, self.ticket.data_ptr(), st), "lock_acquire")
+        if k in ("adag", "downpour", "dynsgd"):
+            scale = 1.0 / self.tau if k == "adag" else 1.0
+            sdev = None
+            if k == "dynsgd":
+                N.check(lib.dk_ps_ticket(ctrl, self.last_update.data_ptr(), self.scale_dev.data_ptr(), st), "ticket")
+                sdev = self.scale_dev.data_ptr()
+            if self.comm == "exchange":
+                N.check(lib.dk_ps_exchange(c, W, W1, Wb, rep.P, scale, sdev, ctrl, self.worker_id, it,
+                                           self.last_update.data_ptr(), st), "exchange")
+            else:
+                N.check(lib.dk_ps_commit(c, W, W1, rep.P, scale, sdev, ctrl, self.worker_id, it, st), "commit")
+                N.check(lib.dk_ps_pull(c, W, W1, Wb, rep.P, ctrl, self.last_update.data_ptr(), st), "pull")
+        elif k in ("aeasgd", "eamsgd"):
+            N.check(lib.dk_ps_elastic(c, W, Wb, rep.P, float(self.alg["alpha"]), ctrl, self.worker_id, it, st),
+                    "elastic")
+        elif k == "experimental":
+            N.check(lib.dk_ps_damped_exchange(c, W, W1, Wb, rep.P, 1.0 / self.tau, float(self.alg["inv_lr"]), ctrl,
+                                              self.worker_id, it, st), "damped_exchange")
+        else:
+            raise ValueError(f"unknown algorithm {k!r}")
+        if self.strict:
+            N.check(lib.dk_ps_lock_release(ctrl, self.ticket.data_ptr(), st), "lock_release")
+
+    def comm_kernels(self) -> int:
+        k = self.alg["kind"]
+        n = 1 if (self.comm == "exchange" or k in ("aeasgd", "eamsgd", "experimental")) else 2
+        if k == "dynsgd":
+            n += 1
+        if self.strict:
+            n += 2
+        return n
+
+    def _step(self, parity: int, j: int) -> None:
+        rep = self.rep
+        xs, ys = self.x_stage[parity], self.y_stage[parity]
+        x_ptr = xs.data_ptr() + j * self.B * self.F * xs.element_size()
+        y_ptr = ys.data_ptr() + j * self.B * (ys.shape[1] if ys.dim() == 2 else 1) * ys.element_size()
+        if self.alg["kind"] == "eamsgd":
+            N.check(self.lib.dk_eamsgd_pre(rep.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(),
+                                           rep.Wb.data_ptr(), rep.P, float(self.alg["momentum"]), self._stream()),
+                    "eamsgd_pre")
+        rep.enqueue_step(x_ptr, y_ptr)
+        if self.alg["kind"] == "eamsgd":
+            N.check(self.lib.dk_eamsgd_post(rep.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(),
+                                            rep.Wb.data_ptr(), rep.P, float(self.alg["eta"]), self._stream()),
+                    "eamsgd_post")
+
+    def _window_program(self, parity: int) -> None:
+        """tau steps + the algorithm's communication, in reference order."""
+        rep = self.rep
+        half = rep.hist[parity * self.tau:(parity + 1) * self.tau]
+        half.zero_()
+        pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd")  # check happens before the batch
+        for j in range(self.tau):
+            if pre_batch and j == self.tau - 1:
+                self._comm_ops()
+            self._step(parity, j)
+        if not pre_batch:
+            self._comm_ops()
+        self.hist_host[parity].copy_(half, non_blocking=True)
+
+    def initial_pull(self) -> None:
+        """``pull(); set_weights(center)`` before the first batch (``workers.py:286-288``)."""
+        rep, reg = self.rep, self.region
+        with torch.cuda.stream(self.compute):
+            N.check(self.lib.dk_ps_pull(C.c_void_p(reg.center_ptr), rep.W.data_ptr(), rep.W1.data_ptr(),
+                                        rep.Wb.data_ptr(), rep.P, C.c_void_p(reg.ctrl_ptr),
+                                        self.last_update.data_ptr(), self._stream()), "pull")
+        self.compute.synchronize()
+
+    def capture(self) -> None:
+        """Warm every kernel once (lazy module load) on scratch state, then capture both parities."""
+        rep = self.rep
+        torch.cuda.synchronize(rep.device)
+        saved = (rep.W.clone(), rep.W1.clone(), rep.step_counter.clone(),
+                 None if rep.opt.s0 is None else rep.opt.s0.clone(), None if rep.opt.s1 is None else rep.opt.s1.clone())
+        launches0 = rep.launches()
+        with torch.cuda.stream(self.compute):
+            self._step(0, 0)
+        self.compute.synchronize()
+        per_step = rep.launches() - launches0
+        extra = 2 if self.alg["kind"] == "eamsgd" else 0
+        self.kernels_per_window = self.tau * (per_step + extra) + self.comm_kernels()
+        # restore the state touched by the warm-up step
+        rep.W.copy_(saved[0]); rep.W1.copy_(saved[1]); rep.step_counter.copy_(saved[2])
+        if saved[3] is not None:
+            rep.opt.s0.copy_(saved[3])
+        if saved[4] is not None:
+            rep.opt.s1.copy_(saved[4])
+        if self.alg["kind"] == "eamsgd":
+            self.mom.zero_()
+        rep.refresh_shadow()
+        rep.hist.zero_()
+        torch.cuda.synchronize(rep.device)
+        for parity in (0, 1):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.compute):
+                self._window_program(parity)
+            self.graphs[parity] = g
+        torch.cuda.synchronize(rep.device)
+
+    # -- host loop ----------------------------------------------------------------------------------
+    def _collect(self, parity: int) -> None:
+        first = self._pending[parity]
+        if first is None:
+            return
+        self.done[parity].synchronize()
+        recs = self.hist_host[parity].numpy()
+        now = time.time()
+        for j in range(self.tau):
+            self.history.append({"history": [float(recs[j, 0]), float(recs[j, 1])], "worker_id": self.worker_id,
+                                 "iteration": first + j, "timestamp": now})
+        self._pending[parity] = None
+
+    def run_window(self, x_host: torch.Tensor, y_host: torch.Tensor) -> None:
+        """Train one window on ``tau * B`` rows of (pinned) host data.  Asynchronous: returns once the
+        H2D copies and the graph replay are enqueued; at most two windows are in flight."""
+        p = self.windows_run & 1
+        self._collect(p)  # window (n - 2) used this parity: wait for it, harvest its history
+        with torch.cuda.stream(self.copy):
+            self.x_stage[p].copy_(x_host.reshape(self.tau * self.B, -1), non_blocking=True)
+            self.y_stage[p].copy_(y_host, non_blocking=True)
+            self.copied[p].record(self.copy)
+        self.h2d_bytes += x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()
+        self.compute.wait_event(self.copied[p])
+        with torch.cuda.stream(self.compute):
+            self.graphs[p].replay()
+            self.done[p].record(self.compute)
+        self.d2h_bytes += self.tau * 8
+        self._pending[p] = self.iteration + 1
+        self.iteration += self.tau
+        self.windows_run += 1
+
+    def drain(self) -> None:
+        for p in ((self.windows_run & 1), ((self.windows_run + 1) & 1)):
+            self._collect(p)
+        self.compute.synchronize()
+
+    def train_partition(self, part: Partition, features_col: str, label_col: str, num_epoch: int = 1) -> None:
+        """Consume a data partition: full windows through the graphs; the uncommitted tail (fewer
+        than ``tau`` batches) is trained eagerly and, like the reference, never committed."""
+        x_all, y_all = part.column(features_col), part.column(label_col)
+        if y_all.dim() == 2 and not self.rep.dense_labels:
+            y_all = y_all.argmax(dim=1)
+        if not self.rep.dense_labels and y_all.dtype != torch.int32:
+            y_all = y_all.to(torch.int32)
+        rows_per_window = self.tau * self.B
+        n = x_all.shape[0]
+        for _ in range(num_epoch):
+            full = n // rows_per_window
+            for w in range(full):
+                lo = w * rows_per_window
+                self.run_window(x_all[lo:lo + rows_per_window], y_all[lo:lo + rows_per_window])
+            tail_lo = full * rows_per_window
+            tail_batches = (n - tail_lo) // self.B
+            if tail_batches:
+                self.drain()
+                with torch.cuda.stream(self.compute):
+                    for j in range(tail_batches):
+                        lo = tail_lo + j * self.B
+                        loss, acc = self.rep.train_on_batch(x_all[lo:lo + self.B], y_all[lo:lo + self.B])
+                        self.iteration += 1
+                        self.history.append({"history": [loss, acc], "worker_id": self.worker_id,
+                                             "iteration": self.iteration, "timestamp": time.time()})
+                # realign the history ring with the window boundary for the next epoch
+                self.rep.step_counter.zero_().add_(self.windows_run * self.tau)
+        self.drain()
+
+
+# ================================================================================================
+# orchestration
+# ================================================================================================
+def _affine_for(dataset: Dataset, features_col: str):
+    """uint8 features are shipped raw and normalised to [0, 1] on the device (fused MinMax)."""
+    x = dataset[features_col]
+    if x.dtype == torch.uint8:
+        return "u8", (1.0 / 255.0, 0.0)
+    return "f32", (1.0, 0.0)
+
+
+def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, barrier) -> dict:
+    """Body shared by the SPMD (torchrun) and the spawned modes.  ``exchange_obj(obj, src)``
+    broadcasts a picklable object from rank ``src``; ``barrier()`` synchronises all ranks."""
+    from ..parameter_servers import FabricParameterServer
+
+    local = int(os.environ.get("LOCAL_RANK", rank)) % torch.cuda.device_count()
+    torch.cuda.set_device(local)
+    alg = trainer.algorithm()
+    model = deserialize_keras_model(trainer.master_model)
+    in_dtype, affine = _affine_for(dataset, trainer.features_column)
+    if getattr(trainer, "input_affine", None) is not None:
+        affine = trainer.input_affine
+    ps = None
+    if rank == 0:
+        ps = FabricParameterServer(model, device_index=local, kind=alg["kind"], learning_rate=trainer.learning_rate)
+        ps.initialize()
+        trainer.parameter_server = ps
+        info = ps.export()
+    else:
+        info = None
+    info = exchange_obj(info, 0)
+    region = ps.region if rank == 0 else FabricRegion.open(info, local)
+    num_workers = min(trainer.num_workers, world)
+    dedicated = bool(getattr(trainer, "dedicated_ps", False)) and world > 1
+    worker_ranks = list(range(1, world)) if dedicated else list(range(world))
+    worker_ranks = worker_ranks[:num_workers]
+    n_parts = max(len(worker_ranks), 1) * max(1, int(trainer.parallelism_factor))
+    parts = dataset.repartition(n_parts).partitions(n_parts)
+    history: List[dict] = []
+    stats = {"kernels_per_window": 0, "windows": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+    if rank in worker_ranks:
+        dataset.pin_memory()
+        parts = dataset.repartition(n_parts).partitions(n_parts)
+        wid = worker_ranks.index(rank)
+        worker = FabricWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid, trainer.batch_size,
+                              local, in_dtype, affine, comm=getattr(trainer, "comm", "exchange"),
+                              strict=trainer.strict, seed=getattr(trainer, "seed", 0))
+        worker.initial_pull()
+        worker.capture()
+        static = getattr(trainer, "shard_mode", "dynamic" if trainer.parallelism_factor > 1 else "static") == "static"
+        my_parts = [parts[i] for i in range(wid, n_parts, len(worker_ranks))] if static else None
+        if getattr(trainer, "data_is_local_shard", False):
+            # SPMD data loading: the dataset this rank was given IS its shard
+            static = True
+            f = max(1, int(trainer.parallelism_factor))
+            my_parts = dataset.repartition(f).partitions(f)
+        warm = int(getattr(trainer, "bench_warmup_steps", 0))
+        if warm and static and my_parts:
+            # untimed warm-up on the head of the first shard (bench contract: W warm-up steps)
+            head = my_parts[0]
+            rows = warm * trainer.batch_size
+            worker.train_partition(Partition(head.dataset, head.index, head.start, head.start + rows),
+                                   trainer.features_column, trainer.label_column, 1)
+            my_parts[0] = Partition(head.dataset, head.index, head.start + rows, head.stop)
+            worker.history = []
+            worker.h2d_bytes = worker.d2h_bytes = 0
+            worker.windows_run_at_start = worker.windows_run
+        torch.cuda.synchronize()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = worker.windows_run
+        it0 = worker.iteration
+        t0 = time.time()
+        with torch.cuda.stream(worker.compute):
+            ev0.record(worker.compute)
+        if static:
+            for part in my_parts:
+                worker.train_partition(part, trainer.features_column, trainer.label_column, trainer.num_epoch)
+        else:
+            # dynamic shard queue: claim partitions with a fetch-add on the PS control block
+            claim = torch.zeros(1, dtype=torch.int32, device=worker.rep.device)
+            word = C.c_void_p(region.ctrl_ptr + 4 * N.CTRL_SHARD_NEXT)
+            while True:
+                N.check(worker.lib.dk_ps_fetch_add(word, 1, claim.data_ptr(), C.c_void_p(N.current_stream())),
+                        "fetch_add")
+                idx = int(claim.item())
+                if idx >= n_parts:
+                    break
+                worker.train_partition(parts[idx], trainer.features_column, trainer.label_column, trainer.num_epoch)
+        with torch.cuda.stream(worker.compute):
+            ev1.record(worker.compute)
+        torch.cuda.synchronize()
+        steps_done = worker.iteration - it0
+        windows_done = worker.windows_run - w0
+        tail_steps = steps_done - windows_done * worker.tau
+        per_step = (worker.kernels_per_window - worker.comm_kernels()) // worker.tau
+        stats = {"kernels_per_window": worker.kernels_per_window, "windows": windows_done, "steps": steps_done,
+                 "gpu_launches": windows_done * worker.kernels_per_window + tail_steps * per_step,
+                 "h2d_bytes": worker.h2d_bytes, "d2h_bytes": worker.d2h_bytes, "seconds": time.time() - t0,
+                 "device_ms": ev0.elapsed_time(ev1)}
+        history = worker.history
+    else:
+        barrier()
+    barrier()
+    result = {"history": history, "stats": stats}
+    if rank == 0:
+        result["num_updates"] = ps.get_num_updates()
+        result["staleness_hist"] = ps.staleness_histogram().tolist()
+        ps.finalize()
+        result["model"] = serialize_keras_model(ps.get_model())
+    barrier()
+    if rank != 0:
+        region.close()
+    else:
+        ps.stop()
+    return result
+
+
+def _spmd_env() -> Optional[tuple]:
+    if "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+        return int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    return None
+
+
+def _init_pg(backend: str = "cpu:gloo,cuda:nccl"):
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        kwargs = {}
+        if torch.cuda.is_available() and "nccl" in backend:
+            kwargs["device_id"] = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count())
+        dist.init_process_group(backend=backend, **kwargs)
+    return dist
+
+
+def _dist_helpers(dist):
+    def exchange_obj(obj, src):
+        box = [obj]
+        dist.broadcast_object_list(box, src=src, device=torch.device("cpu"))
+        return box[0]
+
+    def barrier():
+        dist.barrier()
+
+    return exchange_obj, barrier
+
+
+def _spawn_entry(rank: int, world: int, port: int, payload_path: str, result_path: str) -> None:
+    os.environ.update({"RANK": str(rank), "LOCAL_RANK": str(rank), "WORLD_SIZE": str(world),
+                       "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
+    payload = torch.load(payload_path, weights_only=False)
+    trainer, dataset = payload["trainer"], payload["dataset"]
+    dist = _init_pg("gloo")
+    exchange_obj, barrier = _dist_helpers(dist)
+    res = _rank_train(trainer, dataset, rank, world, exchange_obj, barrier)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {"history": res["history"], "stats": res["stats"]})
+    if rank == 0:
+        res["history"] = [h for g in gathered for h in g["history"]]
+        res["all_stats"] = [g["stats"] for g in gathered]
+        torch.save(res, result_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def train_distributed_fabric(trainer, dataset: Dataset):
+    """Run a PS trainer on the NVLink fabric.  Under ``torchrun`` every rank calls this (SPMD);
+    from a plain driver process the ranks are spawned here, one per GPU."""
+    env = _spmd_env()
+    if env is not None:
+        rank, world = env
+        dist = _init_pg()
+        exchange_obj, barrier = _dist_helpers(dist)
+        res = _rank_train(trainer, dataset, rank, world, exchange_obj, barrier)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {"history": res["history"], "stats": res["stats"]})
+        history = [h for g in gathered for h in g["history"]]
+        box = [res.get("model"), res.get("num_updates"), res.get("staleness_hist")]
+        dist.broadcast_object_list(box, src=0, device=torch.device("cpu"))
+        trainer.fabric_stats = [g["stats"] for g in gathered]
+        trainer.fabric_num_updates, trainer.staleness_histogram = box[1], box[2]
+        return deserialize_keras_model(box[0]), history
+    world = min(max(1, trainer.num_workers + (1 if getattr(trainer, "dedicated_ps", False) else 0)),
+                torch.cuda.device_count())
+    if world == 1:
+        # single GPU: PS and worker share the device, no extra process needed
+        res = _rank_train(trainer, dataset, 0, 1, lambda obj, src: obj, lambda: None)
+        trainer.fabric_stats = [res["stats"]]
+        trainer.fabric_num_updates, trainer.staleness_histogram = res["num_updates"], res["staleness_hist"]
+        return deserialize_keras_model(res["model"]), res["history"]
+    import torch.multiprocessing as mp
+
+    tmp = tempfile.mkdtemp(prefix="dk_fabric_")
+    payload_path, result_path = os.path.join(tmp, "payload.pt"), os.path.join(tmp, "result.pt")
+    ps_obj, trainer.parameter_server = trainer.parameter_server, None
+    torch.save({"trainer": trainer, "dataset": dataset}, payload_path)
+    trainer.parameter_server = ps_obj
+    mp.spawn(_spawn_entry, args=(world, _free_port(), payload_path, result_path), nprocs=world, join=True)
+    res = torch.load(result_path, weights_only=False)
+    trainer.fabric_stats = res.get("all_stats")
+    trainer.fabric_num_updates, trainer.staleness_histogram = res["num_updates"], res["staleness_hist"]
+    for f in (payload_path, result_path):
+        try:
+            os.remove(f)
+        except OSError:
+            pass
+    return deserialize_keras_model(res["model"]), res["history"]
+
+
+# ------------------------------------------------------------------------------------------------
+# single-GPU / averaging trainers on the native engine
+# ------------------------------------------------------------------------------------------------
+def _sequential_native(trainer, part: Partition, model, device_index: int, worker_id: int, num_epoch: int):
+    dataset = part.dataset
+    in_dtype, affine = _affine_for(dataset, trainer.features_column)
+    rep = NativeReplica(model, trainer.worker_optimizer, trainer.loss, trainer.batch_size, device_index,
+                        in_dtype=in_dtype, input_affine=affine, hist_slots=4096)
+    x_all, y_all = part.column(trainer.features_column), part.column(trainer.label_column)
+    if y_all.dim() == 2:
+        y_all = y_all.argmax(dim=1)
+    y_all = y_all.to(torch.int32)
+    dev = rep.device
+    B = trainer.batch_size
+    history, it = [], 0
+    n_batches = x_all.shape[0] // B
+    chunk = 1024  # batches per device-resident chunk / history flush
+    for _ in range(num_epoch):
+        for c0 in range(0, n_batches, chunk):
+            c1 = min(n_batches, c0 + chunk)
+            xd = x_all[c0 * B:c1 * B].to(dev, non_blocking=True).reshape((c1 - c0) * B, -1)
+            yd = y_all[c0 * B:c1 * B].to(dev, non_blocking=True)
+            rep.hist.zero_()
+            base = int(rep.step_counter.item())
+            for j in range(c1 - c0):
+                rep.enqueue_step(xd.data_ptr() + j * B * xd.shape[1] * xd.element_size(), yd.data_ptr() + j * B * 4)
+            steps = (torch.arange(c1 - c0, device=dev) + base) % rep.hist_slots
+            recs = rep.hist[steps].cpu().numpy()
+            now = time.time()
+            for j in range(c1 - c0):
+                it += 1
+                history.append({"history": [float(recs[j, 0]), float(recs[j, 1])], "worker_id": worker_id,
+                                "iteration": it, "timestamp": now})
+    model.set_flat_weights(rep.W.detach().cpu())
+    rep.close()
+    return model, history
+
+
+def train_single_native(trainer, dataset: Dataset):
+    """``SingleTrainer`` on one GPU through the native engine."""
+    model = deserialize_keras_model(trainer.master_model)
+    try:
+        return _sequential_native(trainer, dataset.partitions(1)[0], model, torch.cuda.current_device(), 0,
+                                  trainer.num_epoch)
+    except UnsupportedByNativeEngine:
+        from ..trainers import _run_tasks
+
+        worker = trainer.allocate_worker()
+        results, workers = _run_tasks(worker, dataset.partitions(1), 1, lambda tid: "cuda:0")
+        return deserialize_keras_model(results[0][0]), workers[0].training_history
+
+
+def train_averaging_native(trainer, dataset: Dataset):
+    """``AveragingTrainer`` on the GPUs of this process: one replica per device trained in turn
+    streams, then the per-epoch mean computed by the in-kernel P2P all-reduce (``dk_ps_average``)."""
+    ndev = torch.cuda.device_count()
+    W = trainer.num_workers
+    parts = dataset.repartition(W).partitions(W)
+    master = deserialize_keras_model(trainer.master_model)
+    history: List[dict] = []
+    lib = N.lib()
+    for epoch in range(trainer.num_epoch):
+        flats = []
+        for w in range(W):
+            dev = w % ndev
+            torch.cuda.set_device(dev)
+            m, h = _sequential_native(trainer, parts[w], master.copy(), dev, w, 1)
+            for rec in h:
+                rec["epoch"] = epoch
+            history += h
+            flats.append(m.get_flat_weights().to(f"cuda:{dev}").contiguous())
+        distinct = sorted({f.device.index for f in flats})
+        if len(distinct) == W and W <= 16 and all(
+                a == b or lib.dk_can_access_peer(a, b) for a in distinct for b in distinct):
+            for a in distinct:
+                for b in distinct:
+                    if a != b:
+                        N.check(lib.dk_enable_peer_access(a, b), "peer access")
+            arr = (C.c_void_p * W)(*[f.data_ptr() for f in flats])
+            torch.cuda.set_device(flats[0].device)
+            n = flats[0].numel()
+            N.check(lib.dk_ps_average(arr, W, 0, n, C.c_void_p(N.current_stream())), "dk_ps_average")
+            torch.cuda.synchronize()
+            mean = flats[0].cpu()
+        else:
+            torch.cuda.set_device(0)
+            stack = torch.stack([f.to("cuda:0") for f in flats])
+            arr = (C.c_void_p * W)(*[stack[i].data_ptr() for i in range(W)])
+            N.check(lib.dk_ps_average(arr, W, 0, stack.shape[1], C.c_void_p(N.current_stream())), "dk_ps_average")
+            torch.cuda.synchronize()
+            mean = stack[0].cpu()
+        master.set_flat_weights(mean)
+        trainer.master_model = serialize_keras_model(master)
+    return master, history
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU multi-process (gloo) path: rank 0 hosts the socket PS, every rank runs a worker
+# ------------------------------------------------------------------------------------------------
+def train_distributed_spmd_socket(trainer, dataset: Dataset):
+    import threading
+
+    rank, world = _spmd_env()
+    dist = _init_pg("gloo")
+    exchange_obj, barrier = _dist_helpers(dist)
+    if rank == 0:
+        trainer.parameter_server = trainer.allocate_parameter_server()
+        trainer.parameter_server.master_port = 0
+        trainer.master_host = "127.0.0.1"
+        trainer.start_service()
+        addr = (trainer.master_host, trainer.master_port)
+    else:
+        addr = None
+    addr = exchange_obj(addr, 0)
+    n_parts = world * max(1, int(trainer.parallelism_factor))
+    parts = dataset.repartition(n_parts).partitions(n_parts)
+    worker = trainer.allocate_worker()
+    worker.master_host, worker.master_port = addr
+    history: List[dict] = []
+    import copy as _copy
+
+    for idx in range(rank, n_parts, world):
+        w = _copy.copy(worker)
+        w.training_history, w.iteration = [], 1
+        history += list(w.train(idx, parts[idx]))
+    barrier()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, history)
+    box = [None]
+    if rank == 0:
+        trainer.stop_service()
+        box = [serialize_keras_model(trainer.parameter_server.get_model())]
+    dist.broadcast_object_list(box, src=0)
+    return deserialize_keras_model(box[0]), [h for g in gathered for h in g]

@@ -1,0 +1,179 @@
+"""Native engine / fabric worker / trainers on a real GPU vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mlp(seed=0, dropout=False):
+    from distkeras_b200.models import Dense, Dropout, Sequential
+
+    layers = [Dense(256, activation="relu", input_shape=(64,))]
+    if dropout:
+        layers.append(Dropout(0.25))
+    layers += [Dense(128, activation="relu"), Dense(10, activation="softmax")]
+    return Sequential(layers, seed=seed)
+
+
+def _cnn(seed=0):
+    from distkeras_b200.models import Conv2D, Dense, Flatten, MaxPooling2D, Sequential
+
+    return Sequential([Conv2D(8, 3, padding="same", activation="relu", input_shape=(12, 12, 1)),
+                       Conv2D(16, 3, padding="valid", activation="relu"), MaxPooling2D(2), Flatten(),
+                       Dense(32, activation="relu"), Dense(10, activation="softmax")], seed=seed)
+
+
+@pytest.mark.parametrize("maker,in_shape", [(_mlp, (64,)), (_cnn, (12, 12, 1))])
+def test_native_gradients_match_autograd(maker, in_shape):
+    from distkeras_b200.parallel.engine import NativeReplica
+    from distkeras_b200.parallel.replica import TorchReplica
+
+    B = 128
+    model = maker(0)
+    torch.manual_seed(0)
+    x = torch.rand((B,) + in_shape)
+    y = torch.randint(0, 10, (B,))
+    ref = TorchReplica(model.copy(), {"class_name": "sgd", "config": {"lr": 0.0}}, "categorical_crossentropy", device="cpu")
+    lref, aref = ref.train_on_batch(x, y)
+    gref = ref.W.grad.clone()
+    nat = NativeReplica(model, {"class_name": "sgd", "config": {"lr": 0.0}}, "categorical_crossentropy", B, 0,
+                        in_dtype="f32")
+    lnat, anat = nat.train_on_batch(x, y.to(torch.int32))
+    torch.cuda.synchronize()
+    assert abs(lnat - lref) < 0.02 * max(1.0, abs(lref)), (lnat, lref)
+    assert abs(anat - aref) <= 4.0 / B
+    g = nat.G.cpu()
+    for seg in model.segments:
+        a, b = g[seg.offset:seg.offset + seg.size], gref[seg.offset:seg.offset + seg.size]
+        err = float((a - b).norm() / (b.norm() + 1e-12))
+        assert err < 0.05, (seg.layer_index, seg.name, err)
+    probs = nat.predict(x).cpu()
+    want = torch.softmax(model.forward(x, logits=True), 1)
+    assert torch.allclose(probs, want, atol=0.03)
+    nat.close()
+
+
+def test_native_training_learns_with_dropout_and_adam():
+    from distkeras_b200.parallel.engine import NativeReplica
+
+    B = 256
+    model = _mlp(1, dropout=True)
+    nat = NativeReplica(model, {"class_name": "adam", "config": {"lr": 0.003}}, "categorical_crossentropy", B, 0,
+                        in_dtype="u8", input_affine=(1 / 255.0, 0.0))
+    g = torch.Generator().manual_seed(0)
+    proto = torch.randint(0, 200, (10, 64), generator=g)
+    losses = []
+    for i in range(60):
+        y = torch.randint(0, 10, (B,), generator=g)
+        x = (proto[y] + torch.randint(0, 56, (B, 64), generator=g)).clamp(0, 255).to(torch.uint8)
+        losses.append(nat.train_on_batch(x, y.to(torch.int32))[0])
+    assert losses[-1] < 0.3 * losses[0], (losses[0], losses[-1])
+    nat.close()
+
+
+def test_fabric_adag_matches_cpu_oracle_single_worker():
+    """Same data, same init, SGD: the graph-window ADAG program tracks the thread-backend oracle."""
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.trainers import ADAG
+
+    torch.manual_seed(0)
+    n, B, tau = 16 * 64, 64, 4
+    x = torch.rand(n, 64)
+    y = torch.randint(0, 10, (n,)).to(torch.int32)
+    ds = Dataset({"features": x, "label": y})
+    outs = {}
+    for backend in ("thread", "fabric"):
+        t = ADAG(_mlp(0), {"class_name": "sgd", "config": {"lr": 0.05}}, "categorical_crossentropy", num_workers=1,
+                 batch_size=B, communication_window=tau)
+        t.backend = backend
+        outs[backend] = (t.train(ds).get_flat_weights().cpu(), t.get_history(), t)
+    wt, wf = outs["thread"][0], outs["fabric"][0]
+    rel = float((wt - wf).norm() / wt.norm())
+    assert rel < 0.02, rel
+    ht, hf = outs["thread"][1], outs["fabric"][1]
+    assert len(ht) == len(hf) == 16
+    assert abs(ht[-1]["history"][0] - hf[-1]["history"][0]) < 0.05
+    assert outs["fabric"][2].num_updates() == 16 // tau + 1  # reference counter starts at 1
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("ADAG", dict(communication_window=4)), ("DOWNPOUR", dict(communication_window=3)),
+    ("AEASGD", dict(communication_window=4, rho=1.0, learning_rate=0.1)),
+    ("EAMSGD", dict(communication_window=4, rho=0.1, learning_rate=1.0, momentum=0.5)),
+    ("DynSGD", dict(communication_window=3)), ("Experimental", dict(communication_window=3)),
+])
+def test_fabric_trainers_learn(name, kw):
+    from distkeras_b200 import trainers
+    from distkeras_b200.data import Dataset
+
+    g = torch.Generator().manual_seed(0)
+    n, B = 4096, 128
+    proto = torch.randint(0, 200, (10, 64), generator=g)
+    y = torch.randint(0, 10, (n,), generator=g)
+    x = (proto[y] + torch.randint(0, 56, (n, 64), generator=g)).clamp(0, 255).to(torch.uint8)
+    ds = Dataset({"features": x, "label": y.to(torch.int32)})
+    t = getattr(trainers, name)(_mlp(0), {"class_name": "adam", "config": {"lr": 0.003}}, "categorical_crossentropy",
+                                num_workers=1, batch_size=B, num_epoch=2, **kw)
+    t.backend = "fabric"
+    model = t.train(ds)
+    h = t.get_history()
+    assert len(h) == 2 * (n // B)
+    assert np.mean([r["history"][0] for r in h[-4:]]) < 0.5 * np.mean([r["history"][0] for r in h[:4]])
+    model.compile("categorical_crossentropy")
+    acc = model.evaluate(x.float() / 255.0, y)[1]
+    assert acc > 0.8, acc
+
+
+def test_strict_mode_and_commit_pull_paths():
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.trainers import ADAG
+
+    torch.manual_seed(0)
+    ds = Dataset({"features": torch.rand(1024, 64), "label": torch.randint(0, 10, (1024,)).to(torch.int32)})
+    outs = []
+    for strict, comm in ((False, "exchange"), (False, "commit_pull"), (True, "exchange")):
+        t = ADAG(_mlp(0), {"class_name": "sgd", "config": {"lr": 0.05}}, "categorical_crossentropy", num_workers=1,
+                 batch_size=64, communication_window=4)
+        t.backend, t.strict, t.comm = "fabric", strict, comm
+        outs.append(t.train(ds).get_flat_weights())
+    assert torch.allclose(outs[0], outs[1], atol=1e-6) and torch.allclose(outs[0], outs[2], atol=1e-6)
+
+
+def test_single_and_averaging_trainers_native():
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.trainers import AveragingTrainer, SingleTrainer
+
+    g = torch.Generator().manual_seed(0)
+    n = 2048
+    proto = torch.randint(0, 200, (10, 64), generator=g)
+    y = torch.randint(0, 10, (n,), generator=g)
+    x = (proto[y] + torch.randint(0, 56, (n, 64), generator=g)).clamp(0, 255).to(torch.uint8)
+    ds = Dataset({"features": x, "label": y.to(torch.int32)})
+    adam = {"class_name": "adam", "config": {"lr": 0.003}}
+    s = SingleTrainer(_mlp(0), adam, "categorical_crossentropy", batch_size=64, num_epoch=2)
+    m = s.train(ds)
+    assert len(s.get_history()) == 2 * n // 64
+    m.compile("categorical_crossentropy")
+    assert m.evaluate(x.float() / 255.0, y)[1] > 0.9
+    a = AveragingTrainer(_mlp(0), adam, "categorical_crossentropy", batch_size=64, num_epoch=2, num_workers=2)
+    ma = a.train(ds)
+    ma.compile("categorical_crossentropy")
+    assert ma.evaluate(x.float() / 255.0, y)[1] > 0.8
+
+
+def test_native_predictor_matches_autograd():
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.models import mnist_mlp
+    from distkeras_b200.predictors import ModelPredictor
+
+    m = mnist_mlp(seed=0)
+    x = torch.rand(1000, 784)
+    pred = ModelPredictor(m, device="cuda", batch_size=512).predict(Dataset({"features": x}))["prediction"]
+    assert torch.allclose(pred, torch.as_tensor(m.predict(x)), atol=0.02)
+
+
+def test_smoke_entry():
+    import __graft_entry__
+
+    __graft_entry__.smoke()

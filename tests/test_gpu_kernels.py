@@ -1,0 +1,237 @@
+"""Numerics of every native sm_100a kernel against a plain PyTorch fp32 reference (needs a B200)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def N():
+    from distkeras_b200 import _native
+
+    _native.lib()
+    torch.cuda.set_device(0)
+    return _native
+
+
+def st():
+    return C.c_void_p(int(torch.cuda.current_stream().cuda_stream))
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,Nn,K", [(128, 128, 64), (1024, 1000, 784), (37, 10, 200), (300, 77, 136), (4096, 200, 1000)])
+def test_gemm_k_major(N, M, Nn, K):
+    from distkeras_b200.ops.gemm import gemm_tn
+
+    torch.manual_seed(0)
+    a, b = bf(torch.randn(M, K, device="cuda")), bf(torch.randn(Nn, K, device="cuda"))
+    bias = torch.randn(Nn, device="cuda")
+    ref = torch.relu(a.float() @ b.float().t() + bias)
+    out = gemm_tn(a, b, bias=bias, relu=True, out_fp32=True)
+    assert torch.allclose(out, ref, atol=2e-3 * K ** 0.5, rtol=1e-3)
+    out16 = gemm_tn(a, b, bias=bias, relu=True)
+    assert torch.allclose(out16.float(), ref, atol=0.05 * K ** 0.5, rtol=2e-2)
+
+
+@pytest.mark.parametrize("M,Nn,K", [(128, 128, 64), (1000, 784, 1024), (16, 200, 4096), (200, 1000, 512)])
+def test_gemm_mn_major_operands(N, M, Nn, K):
+    """wgrad form (A and B MN-major) and dgrad form (B MN-major) of the tcgen05 kernel."""
+    from distkeras_b200.ops.gemm import gemm_tn
+
+    torch.manual_seed(1)
+    a, b = bf(torch.randn(M, K, device="cuda")), bf(torch.randn(Nn, K, device="cuda"))
+    ref = a.float() @ b.float().t()
+    tol = dict(atol=2e-3 * K ** 0.5, rtol=1e-3)
+    assert torch.allclose(gemm_tn(a.t().contiguous(), b.t().contiguous(), a_mn=True, b_mn=True, out_fp32=True), ref, **tol)
+    assert torch.allclose(gemm_tn(a, b.t().contiguous(), b_mn=True, out_fp32=True), ref, **tol)
+    mask = bf(torch.randn(M, Nn, device="cuda"))
+    got = gemm_tn(a, b.t().contiguous(), b_mn=True, mask=mask, out_fp32=True, alpha=1.25)
+    assert torch.allclose(got, torch.where(mask.float() > 0, 1.25 * ref, torch.zeros_like(ref)), **tol)
+
+
+def test_gemm_tf32(N):
+    from distkeras_b200.ops.gemm import gemm_tn
+
+    torch.manual_seed(2)
+    a, b = torch.randn(1000, 784, device="cuda"), torch.randn(256, 784, device="cuda")
+    out = gemm_tn(a, b, tf32=True, out_fp32=True)
+    assert torch.allclose(out, a @ b.t(), atol=0.15, rtol=1e-2)
+
+
+@pytest.mark.parametrize("name", ["sgd", "momentum", "adagrad", "rmsprop", "adam", "adadelta", "adamax"])
+def test_fused_optimizer_matches_reference(N, name):
+    from distkeras_b200.ops.flat_optim import FlatOptimizer
+
+    spec = {"class_name": "sgd", "config": {"lr": 0.05, "momentum": 0.9, "nesterov": True}} if name == "momentum" \
+        else {"class_name": name, "config": {}}
+    n = 100003
+    torch.manual_seed(3)
+    w0 = torch.randn(n)
+    gpu, cpu = FlatOptimizer(spec, n, "cuda"), FlatOptimizer(spec, n, "cpu")
+    wg, wc = w0.cuda(), w0.clone()
+    wb = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+    for i in range(4):
+        g = torch.randn(n)
+        gpu.step(wg, g.cuda(), wb)
+        cpu.step(wc, g)
+    assert torch.allclose(wg.cpu(), wc, atol=1e-5, rtol=1e-5), float((wg.cpu() - wc).abs().max())
+    assert torch.equal(wb, wg.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,Cc,dense", [(256, 10, False), (100, 2, True), (64, 1000, False), (33, 40, True)])
+def test_softmax_xent(N, B, Cc, dense):
+    torch.manual_seed(4)
+    z = torch.randn(B, Cc, device="cuda") * 3
+    labels = torch.randint(0, Cc, (B,), device="cuda")
+    y = F.one_hot(labels, Cc).float()
+    ldz = (Cc + 7) // 8 * 8
+    dz = torch.zeros(B, ldz, dtype=torch.bfloat16, device="cuda")
+    probs = torch.zeros(B, Cc, device="cuda")
+    hist = torch.zeros(4, 2, device="cuda")
+    step = torch.tensor([3], dtype=torch.int32, device="cuda")
+    li = labels.to(torch.int32)
+    N.check(N.lib().dk_softmax_xent(z.data_ptr(), Cc, None if dense else li.data_ptr(), y.data_ptr() if dense else None,
+                                    B, Cc, dz.data_ptr(), ldz, None, 0, probs.data_ptr(), hist.data_ptr(),
+                                    step.data_ptr(), 4, st()))
+    p = torch.softmax(z, 1)
+    assert torch.allclose(probs, p, atol=1e-5)
+    assert abs(float(hist[2, 0]) - float(F.cross_entropy(z, labels))) < 1e-3
+    assert abs(float(hist[2, 1]) - float((z.argmax(1) == labels).float().mean())) < 1e-6
+    assert torch.allclose(dz[:, :Cc].float(), (p - y) / B, atol=2e-3 / B + 1e-5, rtol=1e-2)
+
+
+def test_input_stage_and_colsum(N):
+    torch.manual_seed(5)
+    B, Fdim = 100, 30
+    x = torch.randint(0, 256, (B, Fdim), dtype=torch.uint8, device="cuda")
+    ld = 32
+    xb = torch.zeros(B, ld, dtype=torch.bfloat16, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    N.check(N.lib().dk_input_stage(x.data_ptr(), N.IN_U8, B, Fdim, 1 / 255.0, -0.5, xb.data_ptr(), ld, None, 0,
+                                   cnt.data_ptr(), st()))
+    assert int(cnt) == 1
+    assert torch.allclose(xb[:, :Fdim].float(), x.float() / 255.0 - 0.5, atol=4e-3)
+    assert float(xb[:, Fdim:].abs().max()) == 0.0
+    src = bf(torch.randn(1000, 200, device="cuda"))
+    out = torch.zeros(200, device="cuda")
+    N.check(N.lib().dk_colsum_bf16(src.data_ptr(), 1000, 200, 200, out.data_ptr(), 1.0, st()))
+    assert torch.allclose(out, src.float().sum(0), atol=1e-2, rtol=1e-4)
+
+
+@pytest.mark.parametrize("H,Cin,k,stride,pad", [(28, 1, 3, 1, 0), (32, 8, 3, 1, 1), (16, 16, 3, 2, 1), (8, 8, 1, 1, 0)])
+def test_im2col_col2im(N, H, Cin, k, stride, pad):
+    torch.manual_seed(6)
+    B = 3
+    x = bf(torch.randn(B, H, H, Cin, device="cuda"))
+    OH = (H + 2 * pad - k) // stride + 1
+    K = k * k * Cin
+    ld = (K + 7) // 8 * 8
+    col = torch.zeros(B * OH * OH, ld, dtype=torch.bfloat16, device="cuda")
+    N.check(N.lib().dk_im2col(x.data_ptr(), B, H, H, Cin, k, k, stride, pad, OH, OH, col.data_ptr(), ld, st()))
+    # reference: unfold gives (c, kh, kw) order -> reorder to (kh, kw, c)
+    u = F.unfold(x.float().permute(0, 3, 1, 2), k, padding=pad, stride=stride)  # [B, C*k*k, L]
+    u = u.view(B, Cin, k, k, OH * OH).permute(0, 4, 2, 3, 1).reshape(B * OH * OH, K)
+    assert torch.equal(col[:, :K].float(), u)
+    dcol = bf(torch.randn(B * OH * OH, ld, device="cuda"))
+    dx = torch.zeros(B, H, H, Cin, dtype=torch.bfloat16, device="cuda")
+    N.check(N.lib().dk_col2im(dcol.data_ptr(), ld, B, H, H, Cin, k, k, stride, pad, OH, OH, dx.data_ptr(), st()))
+    d = dcol[:, :K].float().view(B, OH * OH, k, k, Cin).permute(0, 4, 2, 3, 1).reshape(B, K, OH * OH)
+    ref = F.fold(d, (H, H), k, padding=pad, stride=stride).permute(0, 2, 3, 1)
+    assert torch.allclose(dx.float(), ref, atol=0.05, rtol=2e-2)
+
+
+def test_maxpool(N):
+    torch.manual_seed(7)
+    B, H, Cc = 4, 24, 32
+    x = bf(torch.randn(B, H, H, Cc, device="cuda"))
+    y = torch.zeros(B, H // 2, H // 2, Cc, dtype=torch.bfloat16, device="cuda")
+    N.check(N.lib().dk_maxpool_fwd(x.data_ptr(), B, H, H, Cc, 2, 2, y.data_ptr(), st()))
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 2)
+    assert torch.equal(y.float(), yr.permute(0, 2, 3, 1))
+    dy = bf(torch.randn_like(y.float()))
+    dx = torch.zeros_like(x)
+    N.check(N.lib().dk_maxpool_bwd(x.data_ptr(), y.data_ptr(), dy.data_ptr(), B, H, H, Cc, 2, 2, dx.data_ptr(), st()))
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert torch.allclose(dx.float(), xr.grad.permute(0, 2, 3, 1), atol=1e-6)
+
+
+def test_ps_kernels_same_device(N):
+    """commit / pull / exchange / elastic / damped / ticket against the formulas of SURVEY 2.6."""
+    lib = N.lib()
+    n = 100003
+    torch.manual_seed(8)
+    c = torch.randn(n, device="cuda")
+    ctrl = torch.zeros(N.CTRL_WORDS, dtype=torch.int32, device="cuda")
+    w, w1 = torch.randn(n, device="cuda"), torch.randn(n, device="cuda")
+    wb = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+    c0 = c.clone()
+    N.check(lib.dk_ps_commit(c.data_ptr(), w.data_ptr(), w1.data_ptr(), n, 0.25, None, ctrl.data_ptr(), 2, 7, st()))
+    assert torch.allclose(c, c0 + 0.25 * (w - w1), atol=1e-6)
+    assert int(ctrl[N.CTRL_NUM_UPDATES]) == 1 and int(ctrl[N.CTRL_HEARTBEAT + 2]) == 7
+    last = torch.zeros(1, dtype=torch.int32, device="cuda")
+    N.check(lib.dk_ps_pull(c.data_ptr(), w.data_ptr(), w1.data_ptr(), wb.data_ptr(), n, ctrl.data_ptr(), last.data_ptr(), st()))
+    assert torch.equal(w, c) and torch.equal(w1, c) and torch.equal(wb, c.to(torch.bfloat16)) and int(last) == 1
+    # exchange == commit + pull
+    w = c + torch.randn(n, device="cuda") * 0.1
+    c0, w0 = c.clone(), w.clone()
+    N.check(lib.dk_ps_exchange(c.data_ptr(), w.data_ptr(), w1.data_ptr(), wb.data_ptr(), n, 0.5, None, ctrl.data_ptr(), 0, 1,
+                               last.data_ptr(), st()))
+    want = c0 + 0.5 * (w0 - c0)
+    assert torch.allclose(c, want, atol=1e-6) and torch.allclose(w, want, atol=1e-6) and torch.equal(w, w1)
+    assert int(last) == 2
+    # elastic: W + C conserved, E = alpha (W - C)
+    w = c + torch.randn(n, device="cuda")
+    c0, w0 = c.clone(), w.clone()
+    N.check(lib.dk_ps_elastic(c.data_ptr(), w.data_ptr(), wb.data_ptr(), n, 0.3, ctrl.data_ptr(), 0, 1, st()))
+    e = 0.3 * (w0 - c0)
+    assert torch.allclose(w, w0 - e, atol=1e-6) and torch.allclose(c, c0 + e, atol=1e-6)
+    # damped exchange (Experimental PS)
+    w1 = c - 0.2 * torch.rand(n, device="cuda")
+    w = w1 + torch.randn(n, device="cuda") * 0.1
+    c0, stale, w0 = c.clone(), w1.clone(), w.clone()
+    N.check(lib.dk_ps_damped_exchange(c.data_ptr(), w.data_ptr(), w1.data_ptr(), wb.data_ptr(), n, 0.2, 2.0,
+                                      ctrl.data_ptr(), 0, 1, st()))
+    r = 0.2 * (w0 - stale) / (2.0 * (c0 - stale) ** 2 + 1.0)
+    assert torch.allclose(c, c0 + r, atol=1e-5) and torch.allclose(w, c, atol=1e-6)
+    # DynSGD ticket: scale = 1 / (num_updates - last_update + 1)
+    nu = int(ctrl[N.CTRL_NUM_UPDATES])
+    last.fill_(nu - 2)
+    scale = torch.zeros(1, device="cuda")
+    N.check(lib.dk_ps_ticket(ctrl.data_ptr(), last.data_ptr(), scale.data_ptr(), st()))
+    assert abs(float(scale) - 1.0 / 3.0) < 1e-6 and int(ctrl[N.CTRL_NUM_UPDATES]) == nu + 1
+    assert int(ctrl[N.CTRL_STALENESS_HIST + 3]) == 1
+    # strict-mode ticket lock round trip
+    t = torch.zeros(1, dtype=torch.int32, device="cuda")
+    N.check(lib.dk_ps_lock_acquire(ctrl.data_ptr(), t.data_ptr(), st()))
+    N.check(lib.dk_ps_lock_release(ctrl.data_ptr(), t.data_ptr(), st()))
+    torch.cuda.synchronize()
+    assert int(ctrl[N.CTRL_LOCK_SERVING]) == 1
+    # averaging kernel on views of one device
+    reps = [torch.randn(1024, device="cuda") for _ in range(3)]
+    mean = torch.stack(reps).mean(0)
+    arr = (C.c_void_p * 3)(*[r.data_ptr() for r in reps])
+    N.check(lib.dk_ps_average(arr, 3, 0, 1024, st()))
+    for r in reps:
+        assert torch.allclose(r, mean, atol=1e-6)
+
+
+def test_label_index_kernel(N):
+    from distkeras_b200.transformers import LabelIndexTransformer
+
+    torch.manual_seed(9)
+    p = torch.softmax(torch.randn(500, 10, device="cuda") * 2, 1)
+    labels = torch.randint(0, 10, (500,), device="cuda", dtype=torch.int32)
+    idx = torch.zeros(500, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    N.check(N.lib().dk_label_index(p.data_ptr(), 500, 10, 0.55, 0, idx.data_ptr(), labels.data_ptr(), cnt.data_ptr(), st()))
+    want = LabelIndexTransformer(10).indices(p.cpu())
+    assert torch.equal(idx.cpu().long(), want)
+    assert int(cnt) == int((want == labels.cpu().long()).sum())

@@ -1,0 +1,85 @@
+import numpy as np
+import pytest
+import torch
+
+from distkeras_b200.models import (Conv2D, Dense, Dropout, Flatten, MaxPooling2D, Sequential, cifar10_cnn, higgs_mlp,
+                                   mnist_convnet, mnist_mlp, model_from_json, resnet18)
+from distkeras_b200.utils import deserialize_keras_model, serialize_keras_model, uniform_weights
+
+
+def test_reference_parameter_counts():
+    # examples/mnist_analysis.ipynb:287, examples/mnist.py:150-162, examples/example_1_analysis.ipynb:346
+    assert mnist_mlp().count_params() == 987210
+    assert mnist_convnet().count_params() == 1048853
+    assert higgs_mlp().count_params() == 517502
+    assert cifar10_cnn().count_params() == 1250858
+
+
+def test_json_and_weight_roundtrip():
+    m = mnist_convnet(seed=1)
+    m.build()
+    m2 = model_from_json(m.to_json())
+    m2.set_weights(m.get_weights())
+    assert torch.equal(m.get_flat_weights(), m2.get_flat_weights())
+    # Keras layouts: Dense kernel [in, out], Conv kernel [kh, kw, cin, cout]
+    shapes = [w.shape for w in m.get_weights()]
+    assert shapes[0] == (3, 3, 1, 32) and shapes[4] == (4608, 225)
+    d = serialize_keras_model(m)
+    m3 = deserialize_keras_model(d)
+    x = torch.rand(4, 28, 28, 1)
+    assert torch.allclose(m.forward(x), m3.forward(x))
+
+
+def test_forward_matches_manual_dense():
+    m = Sequential([Dense(5, activation="relu", input_shape=(3,)), Dense(2, activation="softmax")], seed=0)
+    m.build()
+    w = m.get_weights()
+    x = np.random.RandomState(0).rand(7, 3).astype(np.float32)
+    h = np.maximum(x @ w[0] + w[1], 0)
+    z = h @ w[2] + w[3]
+    p = np.exp(z - z.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    assert np.allclose(m.predict(x), p, atol=1e-5)
+
+
+def test_train_on_batch_decreases_loss():
+    torch.manual_seed(0)
+    m = mnist_mlp(seed=0, dropout=False)
+    m.compile("categorical_crossentropy", "adam")
+    x = torch.rand(64, 784)
+    y = torch.randint(0, 10, (64,))
+    first = m.train_on_batch(x, y)
+    for _ in range(30):
+        last = m.train_on_batch(x, y)
+    assert last[0] < first[0] * 0.5 and last[1] > first[1]
+
+
+def test_one_hot_and_index_labels_agree():
+    m = higgs_mlp(seed=3, dropout=False)
+    m.compile("categorical_crossentropy", "sgd")
+    x = torch.randn(32, 30)
+    y = torch.randint(0, 2, (32,))
+    a = m.copy()
+    la = a.train_on_batch(x, y)
+    lb = m.train_on_batch(x, torch.nn.functional.one_hot(y, 2).float())
+    assert abs(la[0] - lb[0]) < 1e-5
+    assert torch.allclose(a.get_flat_weights(), m.get_flat_weights(), atol=1e-6)
+
+
+def test_resnet18_builds_and_steps():
+    m = resnet18(input_shape=(32, 32, 3), classes=10, seed=0)
+    assert m.count_params() > 11_000_000
+    m.compile("categorical_crossentropy", "sgd")
+    x = torch.rand(4, 32, 32, 3)
+    y = torch.randint(0, 10, (4,))
+    before = m.get_flat_weights().clone()
+    loss, acc = m.train_on_batch(x, y)
+    assert np.isfinite(loss)
+    assert not torch.equal(before, m.get_flat_weights())
+
+
+def test_uniform_weights():
+    m = mnist_mlp(seed=0)
+    uniform_weights(m, (-0.5, 0.5))
+    f = m.get_flat_weights()
+    assert float(f.min()) >= -0.5 and float(f.max()) <= 0.5 and float(f.std()) > 0.2
