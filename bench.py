@@ -276,7 +276,7 @@ def main() -> None:
                "h2d_bytes_per_step": int(sum(s["h2d_bytes"] for s in stats) / steps),
                "d2h_bytes_per_step": int(sum(s["d2h_bytes"] for s in stats) / steps),
                "api": f"distkeras_b200.trainers.{TrainerCls.__name__}(...).train(dataset)",
-               "num_updates": trainer.fabric_num_updates}
+               "num_updates": int(trainer.fabric_num_updates)}
 
     if rank == 0:
         value = n_workers * B * K / (ms_dev * 1e-3)
@@ -297,7 +297,7 @@ def main() -> None:
                                     "training, no flush; e2e: inputs streamed from pinned host memory every step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         }
-        print(json.dumps(out))
+        print(json.dumps(out, default=lambda o: o.item() if hasattr(o, 'item') else str(o)))
     if dist:
         dist.barrier()
         dist.destroy_process_group()

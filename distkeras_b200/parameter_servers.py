@@ -274,7 +274,7 @@ class FabricParameterServer(ParameterServer):
         if self.region is None:
             return self.num_updates
         # the control word starts at 0; the reference's counter starts at 1
-        return self.region.read_ctrl()[0] + 1
+        return int(self.region.read_ctrl()[0]) + 1
 
     def staleness_histogram(self):
         from . import _native
@@ -285,6 +285,7 @@ class FabricParameterServer(ParameterServer):
     def finalize(self) -> None:
         if self.region is not None:
             self.model.set_flat_weights(self.region.read_center())
+            self.num_updates = int(self.region.read_ctrl()[0]) + 1
 
     def stop(self) -> None:
         self.finalize()

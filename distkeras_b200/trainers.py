@@ -338,6 +338,8 @@ class DistributedTrainer(Trainer):
 
     def num_updates(self) -> int:
         """Commits applied by the parameter server (``trainers.py:462-464``, minus its bug)."""
+        if getattr(self, "fabric_num_updates", None) is not None:
+            return int(self.fabric_num_updates)
         return self.parameter_server.get_num_updates() if self.parameter_server is not None else 0
 
     # -- algorithm description consumed by the fabric backend ----------------------------------
