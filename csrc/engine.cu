@@ -25,7 +25,10 @@ struct Op {
   // GEMM only
   alignas(64) CUtensorMap ta;
   alignas(64) CUtensorMap tb;
+  alignas(64) CUtensorMap td;
+  alignas(64) CUtensorMap tm;
   DkGemmEpilogue ep;
+  int has_td, has_tm;
 };
 
 struct Engine {
@@ -54,8 +57,8 @@ int run_op(Engine* e, Op& op, void* st) {
                             resolve(e, a[4]), (int)a[5], resolve(e, a[6]), (int)a[7], rp<int>(e, a[8]), st);
     case DK_OP_GEMM:
       // M, N, K, bn, flags (tensor maps + epilogue pre-encoded)
-      return dk_gemm_tn_launch(&op.ta, &op.tb, &op.ep, (int)a[0], (int)a[1], (int)a[2], (int)a[3],
-                               (int)a[4], st);
+      return dk_gemm_tn_launch2(&op.ta, &op.tb, op.has_td ? &op.td : nullptr, op.has_tm ? &op.tm : nullptr, &op.ep,
+                                (int)a[0], (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], st);
     case DK_OP_XENT:
       // logits, ldl, labels, labels_dense, B, C, dz, ldz, dzt, ldzt, probs, hist, step, hist_slots
       return dk_softmax_xent(rp<const float>(e, a[0]), (int)a[1], rp<const int>(e, a[2]),
@@ -209,7 +212,7 @@ int dk_engine_add_op(void* h, int list, int kind, const int64_t* iargs, int ni, 
 
 // GEMM: D = epilogue(A[M,K] * B[N,K]^T); operands must be fixed device buffers.
 int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B, long ldb, int M, int N,
-                       int K, int flags, int bn, const DkGemmEpilogue* ep) {
+                       int K, int flags, int bn, int splits, const DkGemmEpilogue* ep) {
   Engine* e = reinterpret_cast<Engine*>(h);
   if (list < 0 || list >= (int)e->lists.size()) return -1;
   Op op;
@@ -220,7 +223,13 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
   int r = dk_gemm_encode_operands(&op.ta, &op.tb, A, lda, B, ldb, M, N, K, bn, flags);
   if (r != 0) return r;
   op.ep = *ep;
-  op.i[0] = M; op.i[1] = N; op.i[2] = K; op.i[3] = bn; op.i[4] = flags;
+  op.has_td = ep->d != nullptr && dk_gemm_encode_output(&op.td, ep->d, ep->ldd, M, N, ep->d_fp32) == 0;
+  op.has_tm = ep->mask != nullptr && dk_gemm_encode_output(&op.tm, ep->mask, ep->ld_mask, M, N, 0) == 0;
+  if (splits == 0)  // auto: split-K only for plain fp32 accumulations (wgrad)
+    splits = (ep->d_fp32 && ep->bias == nullptr && ep->act == 0 && ep->mask == nullptr)
+                 ? dk_gemm_pick_splits(M, N, K, bn, flags & DK_GEMM_TF32)
+                 : 1;
+  op.i[0] = M; op.i[1] = N; op.i[2] = K; op.i[3] = bn; op.i[4] = flags; op.i[5] = splits;
   e->lists[list].push_back(op);
   return static_cast<int>(e->lists[list].size()) - 1;
 }

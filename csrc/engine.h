@@ -53,7 +53,7 @@ int dk_engine_set_slot(void* h, int slot, void* p);
 int dk_engine_add_op(void* h, int list, int kind, const int64_t* iargs, int ni, const double* fargs,
                      int nf);
 int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B, long ldb, int M, int N,
-                       int K, int flags, int bn, const DkGemmEpilogue* ep);
+                       int K, int flags, int bn, int splits, const DkGemmEpilogue* ep);
 int dk_engine_run(void* h, int list, void* stream);
 int dk_engine_list_size(void* h, int list);
 int dk_engine_list_kernels(void* h, int list);

@@ -29,6 +29,8 @@ typedef struct DkGemmEpilogue {
   float drop_p;          // > 0: inverted dropout applied after the activation (training forward)
   uint32_t drop_seed;
   const int* step;       // device step counter mixed into the dropout hash (graph-replay safe)
+  int tma_store;         // set by the launcher: output goes through smem staging + TMA store
+  int tma_mask;          // set by the launcher: mask tile is fetched with TMA
 } DkGemmEpilogue;
 
 #ifdef __cplusplus
@@ -45,6 +47,12 @@ int dk_tmap_encode_2d(void* out_tmap, const void* base, int dtype, long rows, lo
 int dk_gemm_pick_bn(int N);
 int dk_gemm_tn_launch(const void* tmap_a, const void* tmap_b, const DkGemmEpilogue* ep, int M, int N,
                       int K, int bn, int flags, void* stream);
+int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_d, const void* tmap_m,
+                       const DkGemmEpilogue* ep, int M, int N, int K, int bn, int flags, int splits, void* stream);
+int dk_gemm_encode_output(void* tmap_d, const void* D, long ldd, int M, int N, int d_fp32);
+int dk_gemm_pick_splits(int M, int N, int K, int bn, int tf32);
+int dk_gemm_tn_ex(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M, int N,
+                  int K, int flags, int bn, int splits, void* stream);
 int dk_gemm_encode_operands(void* tmap_a, void* tmap_b, const void* A, long lda, const void* B, long ldb,
                             int M, int N, int K, int bn, int flags);
 int dk_gemm_tn(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M,

@@ -34,14 +34,58 @@ struct GemmSmem {
   static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;  // + align slack
 };
 
+// 16-byte chunk j of 128-byte row r inside a 1024-byte-aligned SWIZZLE_128B region
+__device__ __forceinline__ uint32_t sw128_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// smem -> global tile store with fp32 add-reduction (split-K accumulation)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d_addr(const void* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // AMN / BMN: the operand is MN-major in global memory, i.e. stored as [K, M] (resp. [K, N])
 // row-major with the M (N) index contiguous.  TMA then loads [64 K-rows x 64 MN-elements] boxes
 // (one 128-byte swizzle row per K index) and the UMMA descriptor walks K in 8-row atoms
 // (SBO = 1024 B) and MN in 64-element chunks (LBO = 8192 B).
+//
+// Epilogue: each of the 4 epilogue warps owns 32 accumulator rows.  It reads them from TMEM in
+// 32-column chunks, applies the fused elementwise work, stages the result in the (now idle)
+// pipeline shared memory in the 128-byte-swizzled layout and hands 32 x 128-byte boxes to the TMA
+// store engine, so global writes are full coalesced lines and ragged M / N edges are clipped by
+// the tensor map.  The dReLU / dropout mask tile is fetched the same way (TMA load).  With
+// split-K (gridDim.z > 1) the store is a TMA add-reduction into the fp32 output.
 template <int BN, int STAGES, bool TF32, bool AMN, bool BMN>
 __global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 2 : 1))
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmEpilogue ep, const int M, const int N, const int K) {
+               const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
+               const GemmEpilogue ep, const int M, const int N, const int K, const int kb_per_split) {
   using S = GemmSmem<BN, STAGES, TF32>;
   constexpr int kBlockK = TF32 ? 32 : 64;   // elements per 128-byte swizzle row
   constexpr int kUmmaK = TF32 ? 8 : 16;     // 32 bytes of K per tcgen05.mma
@@ -57,22 +101,30 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* mask_bar = tmem_full_bar + 1;  // [4], one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * kBlockM;
-  const int num_kb = (K + kBlockK - 1) / kBlockK;
+  const int total_kb = (K + kBlockK - 1) / kBlockK;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(total_kb, kb_begin + kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+  if (num_kb <= 0) return;  // uniform for the CTA
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (ep.tma_store) tma_prefetch_desc(&tmap_d);
+    if (ep.tma_mask) tma_prefetch_desc(&tmap_m);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(&mask_bar[q], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -89,7 +141,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
@@ -150,13 +202,38 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ------------------------------ epilogue ----------------------------------
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
     const int m = m0 + quarter * 32 + lane;        // output row owned by this thread
+    constexpr int kChunk = BN < 32 ? 16 : 32;
+    const bool tma_out = ep.tma_store != 0;
+    const int esize = ep.d_fp32 ? 4 : 2;
+    const int group_cols = 128 / esize;                        // columns per 128-byte staging row
+    // staging regions inside the (idle after the main loop) pipeline buffers
+    const uint32_t out_region = smem_u32(smem) + quarter * (32 * BN * esize);
+    const uint32_t mask_region = smem_u32(smem) + 4 * (32 * BN * esize) + quarter * (32 * BN * 2);
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
+    if (ep.tma_mask) {
+      // dReLU / dropout mask tile (bf16, same shape as the output) via TMA into swizzled smem
+      if (lane == 0) {
+        const int ngroups = (BN + 63) / 64;
+        mbar_expect_tx(&mask_bar[quarter], ngroups * 4096);
+        for (int g = 0; g < ngroups; ++g)
+          tma_load_2d_addr(mask_region + g * 4096, &tmap_m, n0 + g * 64, m0 + quarter * 32, &mask_bar[quarter]);
+      }
+      mbar_wait(&mask_bar[quarter], 0);
+    }
     const bool row_ok = m < M;
     const float bias_m = (ep.bias != nullptr && ep.bias_along_m && row_ok) ? ep.bias[m] : 0.f;
-    constexpr int kChunk = BN < 32 ? 16 : 32;
+    uint32_t drop_salt = 0, drop_thr = 0;
+    float keep_scale = 1.f;
+    if (ep.drop_p > 0.f) {
+      drop_salt = ep.drop_seed + (ep.step != nullptr ? static_cast<uint32_t>(*ep.step) : 0u) * 0x85EBCA77u;
+      drop_thr = static_cast<uint32_t>(ep.drop_p * 256.f + 0.5f);          // 8-bit resolution
+      keep_scale = 256.f / (256.f - static_cast<float>(drop_thr));
+    }
 #pragma unroll 1
     for (int c = 0; c < BN; c += kChunk) {
+      const int nc = n0 + c;
+      if (nc >= N) break;  // warp-uniform
       float v[kChunk];
       {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c;
@@ -174,32 +251,55 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
       }
-      const int nc = n0 + c;
-      if (nc >= N) break;  // warp-uniform
       const bool full_chunk = nc + kChunk <= N;
       // ---- fused elementwise epilogue ----
+      if (ep.alpha != 1.f) {
 #pragma unroll
-      for (int j = 0; j < kChunk; ++j) {
-        float x = v[j] * ep.alpha;
-        if (ep.bias != nullptr) {
-          if (ep.bias_along_m) x += bias_m;
-          else if (nc + j < N) x += __ldg(ep.bias + nc + j);
+        for (int j = 0; j < kChunk; ++j) v[j] *= ep.alpha;
+      }
+      if (ep.bias != nullptr) {
+        if (ep.bias_along_m) {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j) v[j] += bias_m;
+        } else if (full_chunk && ((reinterpret_cast<uintptr_t>(ep.bias + nc) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < kChunk; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j)
+            if (nc + j < N) v[j] += __ldg(ep.bias + nc + j);
         }
-        if (ep.act == 1) x = fmaxf(x, 0.f);
-        v[j] = x;
+      }
+      if (ep.act == 1) {
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.f);
       }
       if (ep.drop_p > 0.f) {
-        // inverted dropout (reference op K10): counter-based hash of (seed, step, element index)
-        const uint32_t salt = ep.drop_seed + (ep.step != nullptr ? static_cast<uint32_t>(*ep.step) : 0u) * 0x85EBCA77u;
-        const float keep_scale = 1.f / (1.f - ep.drop_p);
+        // inverted dropout (reference op K10): one counter-based hash per 4 elements, 8 bits each
 #pragma unroll
-        for (int j = 0; j < kChunk; ++j) {
-          uint32_t h = (static_cast<uint32_t>(m) * static_cast<uint32_t>(N) + static_cast<uint32_t>(nc + j)) * 0x9E3779B1u ^ salt;
+        for (int j = 0; j < kChunk; j += 4) {
+          uint32_t h = (static_cast<uint32_t>(m) * static_cast<uint32_t>(N) + static_cast<uint32_t>(nc + j)) * 0x9E3779B1u ^ drop_salt;
           h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
-          v[j] = (static_cast<float>(h) * 2.3283064365386963e-10f < ep.drop_p) ? 0.f : v[j] * keep_scale;
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            v[j + t] = (((h >> (8 * t)) & 0xFFu) < drop_thr) ? 0.f : v[j + t] * keep_scale;
         }
       }
-      if (ep.mask != nullptr && row_ok) {
+      if (ep.tma_mask) {
+        // chunk c covers 64 bytes of the 128-byte mask row: 16-byte pieces (c % 64) / 8 + 0..3
+        const int g = c >> 6, j0 = (c & 63) >> 3;
+#pragma unroll
+        for (int t = 0; t < kChunk / 8; ++t) {
+          const uint4 q = ld_shared_v4(mask_region + g * 4096 + sw128_off(lane, j0 + t));
+          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (!(__bfloat162float(h[u]) > 0.f)) v[t * 8 + u] = 0.f;
+        }
+      } else if (ep.mask != nullptr && row_ok) {
         const __nv_bfloat16* mrow = ep.mask + static_cast<size_t>(m) * ep.ld_mask + nc;
         if (full_chunk && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)) {
 #pragma unroll
@@ -216,11 +316,47 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (nc + j < N && !(__bfloat162float(mrow[j]) > 0.f)) v[j] = 0.f;
         }
       }
-      // ---- row-major store ----
+      if (tma_out) {
+        // ---- stage in swizzled smem, one TMA store per completed 128-byte column group ----
+        if (ep.d_fp32) {
+          const int g = c / 32;                      // kChunk == 32 here (host guarantees BN >= 32)
+#pragma unroll
+          for (int t = 0; t < kChunk / 4; ++t)
+            st_shared_v4(out_region + g * 4096 + sw128_off(lane, t), __float_as_uint(v[4 * t]),
+                         __float_as_uint(v[4 * t + 1]), __float_as_uint(v[4 * t + 2]), __float_as_uint(v[4 * t + 3]));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (gridDim.z > 1 || ep.accumulate)
+              tma_reduce_add_2d(&tmap_d, out_region + g * 4096, nc, m0 + quarter * 32);
+            else
+              tma_store_2d_addr(&tmap_d, out_region + g * 4096, nc, m0 + quarter * 32);
+          }
+        } else {
+          const int g = c >> 6, j0 = (c & 63) >> 3;
+#pragma unroll
+          for (int t = 0; t < kChunk / 8; ++t)
+            st_shared_v4(out_region + g * 4096 + sw128_off(lane, j0 + t), pack_bf16x2(v[8 * t], v[8 * t + 1]),
+                         pack_bf16x2(v[8 * t + 2], v[8 * t + 3]), pack_bf16x2(v[8 * t + 4], v[8 * t + 5]),
+                         pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
+          const bool group_done = ((c & 63) + kChunk >= 64) || (nc + kChunk >= N) || (c + kChunk >= BN);
+          if (group_done) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_2d_addr(&tmap_d, out_region + g * 4096, n0 + g * 64, m0 + quarter * 32);
+          }
+        }
+        continue;
+      }
+      // ---- direct row-major store (small / unaligned outputs) ----
       if (ep.d != nullptr && row_ok) {
         if (ep.d_fp32) {
           float* drow = reinterpret_cast<float*>(ep.d) + static_cast<size_t>(m) * ep.ldd + nc;
-          if (full_chunk && ((reinterpret_cast<uintptr_t>(drow) & 15) == 0)) {
+          if (gridDim.z > 1) {
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j)
+              if (nc + j < N) atomicAdd(drow + j, v[j]);
+          } else if (full_chunk && ((reinterpret_cast<uintptr_t>(drow) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < kChunk; j += 4) {
               float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -263,6 +399,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ep.dt[static_cast<size_t>(nc + j) * ep.lddt + m] = __float2bfloat16_rn(v[j]);
       }
     }
+    if (tma_out && lane == 0) {
+      tma_store_commit();
+      tma_store_wait_read<0>();  // smem must stay valid until the TMA engine has read it
+    }
     tcgen05_fence_before();
   }
 
@@ -295,9 +435,23 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+struct GemmLaunch {
+  const CUtensorMap* ta;
+  const CUtensorMap* tb;
+  const CUtensorMap* td;  // may be nullptr
+  const CUtensorMap* tm;  // may be nullptr
+  GemmEpilogue ep;
+  int M, N, K, splits;
+  cudaStream_t stream;
+};
+
 template <int BN, int STAGES, bool TF32, bool AMN = false, bool BMN = false>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M,
-                       int N, int K, cudaStream_t stream) {
+static int launch_gemm(const GemmLaunch& L) {
+  const CUtensorMap& ta = *L.ta;
+  const CUtensorMap& tb = *L.tb;
+  GemmEpilogue ep = L.ep;
+  const int M = L.M, N = L.N, K = L.K;
+  cudaStream_t stream = L.stream;
   using S = GemmSmem<BN, STAGES, TF32>;
   auto kern = gemm_tn_kernel<BN, STAGES, TF32, AMN, BMN>;
   static bool configured = false;
@@ -305,8 +459,22 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     DK_HOST_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + kBlockM - 1) / kBlockM);
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, ep, M, N, K);
+  constexpr int kBlockK = TF32 ? 32 : 64;
+  const int total_kb = (K + kBlockK - 1) / kBlockK;
+  int splits = L.splits < 1 ? 1 : L.splits;
+  if (splits > total_kb) splits = total_kb;
+  const int kb_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + kb_per_split - 1) / kb_per_split;
+  // the TMA-store epilogue stages 4 x 32 x BN outputs (+ the mask tile) in the pipeline buffers
+  const int esize = ep.d_fp32 ? 4 : 2;
+  const bool fits = 4 * 32 * BN * esize + (L.tm != nullptr ? 4 * 32 * BN * 2 : 0) <= STAGES * S::kStageBytes;
+  const bool wide = ep.d_fp32 ? BN >= 32 : BN >= 64;
+  ep.tma_store = (L.td != nullptr && fits && wide && ep.dt == nullptr) ? 1 : 0;
+  ep.tma_mask = (L.tm != nullptr && ep.tma_store && BN >= 64) ? 1 : 0;
+  if (splits > 1 && !ep.d_fp32) return -6;
+  dim3 grid((N + BN - 1) / BN, (M + kBlockM - 1) / kBlockM, splits);
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, ep.tma_store ? *L.td : ta, ep.tma_mask ? *L.tm : ta, ep, M,
+                                                  N, K, kb_per_split);
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -343,57 +511,85 @@ int dk_gemm_pick_bn(int N) {
 
 // Launch with pre-encoded tensor maps.  flags: DK_GEMM_TF32 | DK_GEMM_A_MN | DK_GEMM_B_MN.
 // K-major operand maps are encoded with box_rows = 128 (A) / bn (B) over a [rows, K] matrix;
-// MN-major operand maps with box_rows = 64 over the [K, rows] matrix.
-int dk_gemm_tn_launch(const void* tmap_a, const void* tmap_b, const DkGemmEpilogue* ep, int M, int N,
-                      int K, int bn, int flags, void* stream) {
-  const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(tmap_a);
-  const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(tmap_b);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+// MN-major operand maps with box_rows = 64 over the [K, rows] matrix.  tmap_d / tmap_m (optional)
+// describe the output / mask matrices [M, N] with box_rows = 32 for the TMA-store epilogue.
+int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_d, const void* tmap_m,
+                       const DkGemmEpilogue* ep, int M, int N, int K, int bn, int flags, int splits, void* stream) {
+  dk::GemmLaunch L;
+  L.ta = reinterpret_cast<const CUtensorMap*>(tmap_a);
+  L.tb = reinterpret_cast<const CUtensorMap*>(tmap_b);
+  L.td = reinterpret_cast<const CUtensorMap*>(tmap_d);
+  L.tm = reinterpret_cast<const CUtensorMap*>(tmap_m);
+  L.ep = *ep;
+  L.M = M; L.N = N; L.K = K; L.splits = splits;
+  L.stream = reinterpret_cast<cudaStream_t>(stream);
   if (M <= 0 || N <= 0 || K <= 0) return -3;
   const bool tf32 = flags & DK_GEMM_TF32, amn = flags & DK_GEMM_A_MN, bmn = flags & DK_GEMM_B_MN;
   if (tf32) {
     if (amn || bmn) return -5;
     switch (bn) {
-      case 16: return dk::launch_gemm<16, 4, true>(ta, tb, *ep, M, N, K, st);
-      case 32: return dk::launch_gemm<32, 4, true>(ta, tb, *ep, M, N, K, st);
-      case 64: return dk::launch_gemm<64, 4, true>(ta, tb, *ep, M, N, K, st);
-      case 128: return dk::launch_gemm<128, 3, true>(ta, tb, *ep, M, N, K, st);
+      case 16: return dk::launch_gemm<16, 4, true>(L);
+      case 32: return dk::launch_gemm<32, 4, true>(L);
+      case 64: return dk::launch_gemm<64, 4, true>(L);
+      case 128: return dk::launch_gemm<128, 3, true>(L);
       default: return -4;
     }
   }
   if (!amn && !bmn) {
     switch (bn) {
-      case 16: return dk::launch_gemm<16, 6, false>(ta, tb, *ep, M, N, K, st);
-      case 32: return dk::launch_gemm<32, 6, false>(ta, tb, *ep, M, N, K, st);
-      case 64: return dk::launch_gemm<64, 6, false>(ta, tb, *ep, M, N, K, st);
-      case 128: return dk::launch_gemm<128, 3, false>(ta, tb, *ep, M, N, K, st);
-      case 256: return dk::launch_gemm<256, 4, false>(ta, tb, *ep, M, N, K, st);
+      case 16: return dk::launch_gemm<16, 6, false>(L);
+      case 32: return dk::launch_gemm<32, 6, false>(L);
+      case 64: return dk::launch_gemm<64, 4, false>(L);
+      case 128: return dk::launch_gemm<128, 3, false>(L);
+      case 256: return dk::launch_gemm<256, 4, false>(L);
       default: return -4;
     }
   }
   if (!amn && bmn) {
     switch (bn) {
-      case 64: return dk::launch_gemm<64, 6, false, false, true>(ta, tb, *ep, M, N, K, st);
-      case 128: return dk::launch_gemm<128, 3, false, false, true>(ta, tb, *ep, M, N, K, st);
-      case 256: return dk::launch_gemm<256, 4, false, false, true>(ta, tb, *ep, M, N, K, st);
+      case 64: return dk::launch_gemm<64, 4, false, false, true>(L);
+      case 128: return dk::launch_gemm<128, 3, false, false, true>(L);
+      case 256: return dk::launch_gemm<256, 4, false, false, true>(L);
       default: return -4;
     }
   }
   if (amn && bmn) {
     switch (bn) {
-      case 64: return dk::launch_gemm<64, 6, false, true, true>(ta, tb, *ep, M, N, K, st);
-      case 128: return dk::launch_gemm<128, 3, false, true, true>(ta, tb, *ep, M, N, K, st);
-      case 256: return dk::launch_gemm<256, 4, false, true, true>(ta, tb, *ep, M, N, K, st);
+      case 64: return dk::launch_gemm<64, 4, false, true, true>(L);
+      case 128: return dk::launch_gemm<128, 3, false, true, true>(L);
+      case 256: return dk::launch_gemm<256, 4, false, true, true>(L);
       default: return -4;
     }
   }
   switch (bn) {  // A MN-major, B K-major
-    case 16: return dk::launch_gemm<16, 6, false, true, false>(ta, tb, *ep, M, N, K, st);
-    case 32: return dk::launch_gemm<32, 6, false, true, false>(ta, tb, *ep, M, N, K, st);
-    case 64: return dk::launch_gemm<64, 6, false, true, false>(ta, tb, *ep, M, N, K, st);
-    case 128: return dk::launch_gemm<128, 3, false, true, false>(ta, tb, *ep, M, N, K, st);
+    case 16: return dk::launch_gemm<16, 6, false, true, false>(L);
+    case 32: return dk::launch_gemm<32, 6, false, true, false>(L);
+    case 64: return dk::launch_gemm<64, 4, false, true, false>(L);
+    case 128: return dk::launch_gemm<128, 3, false, true, false>(L);
     default: return -4;
   }
+}
+
+int dk_gemm_tn_launch(const void* tmap_a, const void* tmap_b, const DkGemmEpilogue* ep, int M, int N,
+                      int K, int bn, int flags, void* stream) {
+  return dk_gemm_tn_launch2(tmap_a, tmap_b, nullptr, nullptr, ep, M, N, K, bn, flags, 1, stream);
+}
+
+// Output / mask tensor maps for the TMA-store epilogue; returns 0 on success, non-zero if the
+// matrix cannot be described (unaligned base / stride) in which case the direct-store path is used.
+int dk_gemm_encode_output(void* tmap_d, const void* D, long ldd, int M, int N, int d_fp32) {
+  return dk_tmap_encode_2d(tmap_d, D, d_fp32 ? DK_F32 : DK_BF16, M, N, ldd, 32);
+}
+
+// Split-K factor that fills the GPU (2 CTAs / SM) without making the slices too short.
+int dk_gemm_pick_splits(int M, int N, int K, int bn, int tf32) {
+  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  const int total_kb = (K + (tf32 ? 32 : 64) - 1) / (tf32 ? 32 : 64);
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  if (splits > total_kb / 4) splits = total_kb / 4;
+  if (splits < 1) splits = 1;
+  if (splits > 32) splits = 32;
+  return splits;
 }
 
 int dk_gemm_encode_operands(void* tmap_a, void* tmap_b, const void* A, long lda, const void* B, long ldb,
@@ -406,15 +602,25 @@ int dk_gemm_encode_operands(void* tmap_a, void* tmap_b, const void* A, long lda,
                                 : dk_tmap_encode_2d(tmap_b, B, dt, N, K, ldb, bn);
 }
 
-// Convenience one-shot entry: encodes both tensor maps, then launches.
-int dk_gemm_tn(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M,
-               int N, int K, int flags, int bn, void* stream) {
-  alignas(64) CUtensorMap ta, tb;
+// Convenience one-shot entry: encodes the tensor maps, then launches (splits: 0 = auto for fp32
+// outputs without bias / activation, otherwise 1).
+int dk_gemm_tn_ex(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M, int N,
+                  int K, int flags, int bn, int splits, void* stream) {
+  alignas(64) CUtensorMap ta, tb, td, tm;
   if (bn <= 0) bn = dk_gemm_pick_bn(N);
   if ((flags & DK_GEMM_B_MN) && bn < 64) bn = 64;
   int r = dk_gemm_encode_operands(&ta, &tb, A, lda, B, ldb, M, N, K, bn, flags);
   if (r != 0) return r;
-  return dk_gemm_tn_launch(&ta, &tb, ep, M, N, K, bn, flags, stream);
+  const bool has_d = ep->d != nullptr && dk_gemm_encode_output(&td, ep->d, ep->ldd, M, N, ep->d_fp32) == 0;
+  const bool has_m = ep->mask != nullptr && dk_gemm_encode_output(&tm, ep->mask, ep->ld_mask, M, N, 0) == 0;
+  if (splits <= 0) splits = 1;
+  return dk_gemm_tn_launch2(&ta, &tb, has_d ? &td : nullptr, has_m ? &tm : nullptr, ep, M, N, K, bn, flags, splits,
+                            stream);
+}
+
+int dk_gemm_tn(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M,
+               int N, int K, int flags, int bn, void* stream) {
+  return dk_gemm_tn_ex(A, lda, B, ldb, ep, M, N, K, flags, bn, 1, stream);
 }
 
 }  // extern "C"

@@ -27,7 +27,7 @@ class GemmEpilogue(C.Structure):
     _fields_ = [
         ("bias", vp), ("bias_along_m", i32), ("act", i32), ("mask", vp), ("ld_mask", i32),
         ("d", vp), ("ldd", i32), ("d_fp32", i32), ("accumulate", i32), ("dt", vp), ("lddt", i32),
-        ("alpha", f32), ("drop_p", f32), ("drop_seed", u32), ("step", vp),
+        ("alpha", f32), ("drop_p", f32), ("drop_seed", u32), ("step", vp), ("tma_store", i32), ("tma_mask", i32),
     ]
 
 
@@ -52,6 +52,8 @@ _SIGNATURES = {
     "dk_tmap_encode_2d": (i32, [vp, vp, i32, i64, i64, i64, i32]),
     "dk_gemm_pick_bn": (i32, [i32]),
     "dk_gemm_tn": (i32, [vp, i64, vp, i64, C.POINTER(GemmEpilogue), i32, i32, i32, i32, i32, vp]),
+    "dk_gemm_tn_ex": (i32, [vp, i64, vp, i64, C.POINTER(GemmEpilogue), i32, i32, i32, i32, i32, i32, vp]),
+    "dk_gemm_pick_splits": (i32, [i32, i32, i32, i32, i32]),
     # ps
     "dk_ps_commit": (i32, [vp, vp, vp, i64, f32, vp, vp, i32, u32, vp]),
     "dk_ps_pull": (i32, [vp, vp, vp, vp, i64, vp, vp, vp]),
@@ -108,7 +110,7 @@ _SIGNATURES = {
     "dk_engine_clear_list": (i32, [vp, i32]),
     "dk_engine_set_slot": (i32, [vp, i32, vp]),
     "dk_engine_add_op": (i32, [vp, i32, i32, C.POINTER(C.c_int64), i32, C.POINTER(f64), i32]),
-    "dk_engine_add_gemm": (i32, [vp, i32, vp, i64, vp, i64, i32, i32, i32, i32, i32, C.POINTER(GemmEpilogue)]),
+    "dk_engine_add_gemm": (i32, [vp, i32, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, C.POINTER(GemmEpilogue)]),
     "dk_engine_run": (i32, [vp, i32, vp]),
     "dk_engine_list_size": (i32, [vp, i32]),
     "dk_engine_list_kernels": (i32, [vp, i32]),

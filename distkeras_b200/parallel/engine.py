@@ -184,9 +184,9 @@ class NativeReplica(Replica):
             raise RuntimeError(f"dk_engine_add_op({kind}) failed: {r}")
 
     def _gemm(self, lst: int, A: int, lda: int, Bp: int, ldb: int, M: int, Nn: int, K: int, flags: int,
-              ep: N.GemmEpilogue, bn: int = 0) -> None:
+              ep: N.GemmEpilogue, bn: int = 0, splits: int = 0) -> None:
         r = self.lib.dk_engine_add_gemm(self.engine, lst, C.c_void_p(A), lda, C.c_void_p(Bp), ldb, M, Nn, K,
-                                        flags, bn, C.byref(ep))
+                                        flags, bn, splits, C.byref(ep))
         if r < 0:
             raise RuntimeError(f"dk_engine_add_gemm(M={M}, N={Nn}, K={K}, flags={flags}) failed: {r}")
 
@@ -250,8 +250,9 @@ class NativeReplica(Replica):
                     a_in = cur
                 b.a_in = a_in
                 if is_last:
-                    out = self._buf(rows, Nout, dtype=torch.float32)
-                    rec = dict(t=out, rows=rows, cols=Nout, ld=Nout, nhwc=None)
+                    ldl = _r8(Nout) if self.loss_kind == "xent" else Nout  # fp32 rows 16-byte aligned for TMA
+                    out = self._buf(rows, ldl, dtype=torch.float32)
+                    rec = dict(t=out, rows=rows, cols=Nout, ld=ldl, nhwc=None)
                 else:
                     out = self._buf(rows, _r8(Nout))
                     rec = dict(t=out, rows=rows, cols=Nout, ld=_r8(Nout),
@@ -292,7 +293,7 @@ class NativeReplica(Replica):
         self.probs = self._buf(B, Cn, dtype=torch.float32)
         self._zero_labels = self._buf(B, dtype=torch.int32)
         # inference tail: probabilities
-        self._add(self.L_fwd, N.OP_XENT, [self.logits.data_ptr(), Cn, self._zero_labels.data_ptr(), 0, B, Cn, 0, 0,
+        self._add(self.L_fwd, N.OP_XENT, [self.logits.data_ptr(), _r8(Cn), self._zero_labels.data_ptr(), 0, B, Cn, 0, 0,
                                           0, 0, self.probs.data_ptr(), 0, 0, 0])
         self._prepend_pad_refresh(self.L_fwd)
         if not self.training:
@@ -302,7 +303,7 @@ class NativeReplica(Replica):
         ldz = _r8(Cn)
         dz = self._buf(B, ldz)
         if self.loss_kind == "xent":
-            self._add(lst, N.OP_XENT, [self.logits.data_ptr(), Cn,
+            self._add(lst, N.OP_XENT, [self.logits.data_ptr(), _r8(Cn),
                                        0 if self.dense_labels else -(SLOT_Y + 1),
                                        -(SLOT_Y + 1) if self.dense_labels else 0,
                                        B, Cn, dz.data_ptr(), ldz, 0, 0, 0, self.hist.data_ptr(),
