@@ -20,6 +20,7 @@ namespace {
 
 struct Op {
   int kind;
+  int stream_id;  // 0 = caller's stream, 1 = engine side stream (parallel graph branch)
   int64_t i[DK_OP_MAX_I];
   double f[DK_OP_MAX_F];
   // GEMM only
@@ -35,7 +36,20 @@ struct Engine {
   std::vector<std::vector<Op>> lists;
   void* slots[DK_ENGINE_SLOTS];
   long launches;  // kernels enqueued so far (bench "gpu_launches" accounting)
+  int build_stream;            // stream id given to ops added from now on
+  cudaStream_t side;           // side stream: independent work (wgrad / bias-grad) overlaps the dgrad chain
+  std::vector<cudaEvent_t> events;
+  size_t next_event;
 };
+
+cudaEvent_t next_event(Engine* e) {
+  if (e->next_event >= e->events.size()) {
+    cudaEvent_t ev;
+    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    e->events.push_back(ev);
+  }
+  return e->events[e->next_event++];
+}
 
 inline void* resolve(const Engine* e, int64_t v) {
   if (v < 0) return e->slots[-v - 1];
@@ -47,9 +61,20 @@ inline T* rp(const Engine* e, int64_t v) {
   return reinterpret_cast<T*>(resolve(e, v));
 }
 
-int run_op(Engine* e, Op& op, void* st) {
+int run_op(Engine* e, Op& op, void* main_stream) {
   const int64_t* a = op.i;
   const double* f = op.f;
+  if (op.kind == DK_OP_FORK || op.kind == DK_OP_JOIN) {
+    // FORK: side stream waits for everything enqueued so far on the main stream.
+    // JOIN: main stream waits for everything enqueued so far on the side stream.
+    cudaStream_t from = op.kind == DK_OP_FORK ? (cudaStream_t)main_stream : e->side;
+    cudaStream_t to = op.kind == DK_OP_FORK ? e->side : (cudaStream_t)main_stream;
+    cudaEvent_t ev = next_event(e);
+    DK_HOST_CHECK(cudaEventRecord(ev, from));
+    DK_HOST_CHECK(cudaStreamWaitEvent(to, ev, 0));
+    return 0;
+  }
+  void* st = op.stream_id == 1 ? (void*)e->side : main_stream;
   switch (op.kind) {
     case DK_OP_INPUT:
       // x, in_dtype, B, F, xb, ldx, xt, ldxt, step_counter | scale, shift
@@ -172,10 +197,25 @@ void* dk_engine_create() {
   Engine* e = new Engine();
   memset(e->slots, 0, sizeof(e->slots));
   e->launches = 0;
+  e->build_stream = 0;
+  e->next_event = 0;
+  e->side = nullptr;
+  cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
   return e;
 }
 
-void dk_engine_destroy(void* h) { delete reinterpret_cast<Engine*>(h); }
+void dk_engine_destroy(void* h) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  for (cudaEvent_t ev : e->events) cudaEventDestroy(ev);
+  if (e->side != nullptr) cudaStreamDestroy(e->side);
+  delete e;
+}
+
+// ops added after this call run on stream `id` (0 = caller's stream, 1 = engine side stream)
+int dk_engine_set_build_stream(void* h, int id) {
+  reinterpret_cast<Engine*>(h)->build_stream = id;
+  return 0;
+}
 
 int dk_engine_new_list(void* h) {
   Engine* e = reinterpret_cast<Engine*>(h);
@@ -204,6 +244,7 @@ int dk_engine_add_op(void* h, int list, int kind, const int64_t* iargs, int ni, 
   Op op;
   memset(&op, 0, sizeof(op));
   op.kind = kind;
+  op.stream_id = e->build_stream;
   for (int k = 0; k < ni; ++k) op.i[k] = iargs[k];
   for (int k = 0; k < nf; ++k) op.f[k] = fargs[k];
   e->lists[list].push_back(op);
@@ -218,7 +259,9 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
   Op op;
   memset(&op, 0, sizeof(op));
   op.kind = DK_OP_GEMM;
-  if (bn <= 0) bn = dk_gemm_pick_bn(N);
+  op.stream_id = e->build_stream;
+  const bool splitk_ok = ep->d_fp32 && ep->bias == nullptr && ep->act == 0 && ep->mask == nullptr;
+  if (bn <= 0) bn = (splits == 0 && splitk_ok) ? dk_gemm_pick_bn_splitk(M, N, K) : dk_gemm_pick_bn2(M, N);
   if ((flags & DK_GEMM_B_MN) && bn < 64) bn = 64;
   int r = dk_gemm_encode_operands(&op.ta, &op.tb, A, lda, B, ldb, M, N, K, bn, flags);
   if (r != 0) return r;
@@ -237,9 +280,11 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
 int dk_engine_run(void* h, int list, void* stream) {
   Engine* e = reinterpret_cast<Engine*>(h);
   if (list < 0 || list >= (int)e->lists.size()) return -1;
+  e->next_event = 0;
   for (Op& op : e->lists[list]) {
     int r = run_op(e, op, stream);
     if (r != 0) return r;
+    if (op.kind == DK_OP_FORK || op.kind == DK_OP_JOIN) continue;
     if (op.kind != DK_OP_MEMSET && op.kind != DK_OP_MEMCPY && op.kind != DK_OP_MEMCPY2D) e->launches += 1;
   }
   return 0;
@@ -257,7 +302,9 @@ int dk_engine_list_kernels(void* h, int list) {
   if (list < 0 || list >= (int)e->lists.size()) return -1;
   int n = 0;
   for (const Op& op : e->lists[list])
-    if (op.kind != DK_OP_MEMSET && op.kind != DK_OP_MEMCPY && op.kind != DK_OP_MEMCPY2D) ++n;
+    if (op.kind != DK_OP_MEMSET && op.kind != DK_OP_MEMCPY && op.kind != DK_OP_MEMCPY2D && op.kind != DK_OP_FORK &&
+        op.kind != DK_OP_JOIN)
+      ++n;
   return n;
 }
 

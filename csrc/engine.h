@@ -37,7 +37,9 @@ enum {
   DK_OP_MEMCPY = 25,
   DK_OP_LABEL_INDEX = 26,
   DK_OP_COLSUM = 27,
-  DK_OP_MEMCPY2D = 28
+  DK_OP_MEMCPY2D = 28,
+  DK_OP_FORK = 29,
+  DK_OP_JOIN = 30
 };
 
 #ifdef __cplusplus
@@ -47,6 +49,7 @@ extern "C" {
 void* dk_engine_create();
 void dk_engine_destroy(void* h);
 int dk_engine_new_list(void* h);
+int dk_engine_set_build_stream(void* h, int id);
 int dk_engine_clear_list(void* h, int list);
 int dk_engine_set_slot(void* h, int slot, void* p);
 // pointer arguments: a device address, or -(slot + 1) to read the pointer from a slot at run time

@@ -45,6 +45,8 @@ extern "C" {
 int dk_tmap_encode_2d(void* out_tmap, const void* base, int dtype, long rows, long cols, long ld,
                       int box_rows);
 int dk_gemm_pick_bn(int N);
+int dk_gemm_pick_bn2(int M, int N);
+int dk_gemm_pick_bn_splitk(int M, int N, int K);
 int dk_gemm_tn_launch(const void* tmap_a, const void* tmap_b, const DkGemmEpilogue* ep, int M, int N,
                       int K, int bn, int flags, void* stream);
 int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_d, const void* tmap_m,

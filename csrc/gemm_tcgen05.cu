@@ -509,6 +509,24 @@ int dk_gemm_pick_bn(int N) {
   return 128;
 }
 
+// Tile width that also looks at M: narrow tiles when 128-wide ones cannot fill the 148 SMs.
+int dk_gemm_pick_bn2(int M, int N) {
+  const int bn = dk_gemm_pick_bn(N);
+  if (bn < 128) return bn;
+  const long tiles128 = static_cast<long>((M + 127) / 128) * ((N + 127) / 128);
+  if (tiles128 < 120 && N > 64) return 64;
+  // measured (profiles/): for the short-K forward / dgrad GEMMs two co-resident 128-wide CTAs per
+  // SM (epilogue of one overlapping the main loop of the other) beat one 256-wide CTA
+  return 128;
+}
+
+// wgrad-style GEMMs (fp32 output, split-K): wide tiles, the split factor restores the parallelism
+int dk_gemm_pick_bn_splitk(int M, int N, int K) {
+  if (N >= 512 && K >= 2048) return 256;
+  if (N > 64) return 128;
+  return dk_gemm_pick_bn(N) < 64 ? 64 : dk_gemm_pick_bn(N);
+}
+
 // Launch with pre-encoded tensor maps.  flags: DK_GEMM_TF32 | DK_GEMM_A_MN | DK_GEMM_B_MN.
 // K-major operand maps are encoded with box_rows = 128 (A) / bn (B) over a [rows, K] matrix;
 // MN-major operand maps with box_rows = 64 over the [K, rows] matrix.  tmap_d / tmap_m (optional)
@@ -585,7 +603,8 @@ int dk_gemm_encode_output(void* tmap_d, const void* D, long ldd, int M, int N, i
 int dk_gemm_pick_splits(int M, int N, int K, int bn, int tf32) {
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
   const int total_kb = (K + (tf32 ? 32 : 64) - 1) / (tf32 ? 32 : 64);
-  int splits = (2 * 148 + tiles - 1) / tiles;
+  const int slots = bn > 128 ? 148 : 2 * 148;  // resident CTAs (wide tiles run 1 CTA / SM)
+  int splits = (slots + tiles - 1) / tiles;
   if (splits > total_kb / 4) splits = total_kb / 4;
   if (splits < 1) splits = 1;
   if (splits > 32) splits = 32;

@@ -36,7 +36,7 @@ OP_INPUT, OP_GEMM, OP_XENT, OP_ROWSUM, OP_TRANSPOSE, OP_OPTIM, OP_IM2COL, OP_COL
 OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_RELU_MASK, OP_ADD, OP_MEMSET = 8, 9, 10, 11, 12
 OP_PS_COMMIT, OP_PS_PULL, OP_PS_EXCHANGE, OP_PS_ELASTIC, OP_PS_DAMPED, OP_PS_TICKET = 13, 14, 15, 16, 17, 18
 OP_LOCK_ACQUIRE, OP_LOCK_RELEASE, OP_EAMSGD_PRE, OP_EAMSGD_POST, OP_CAST, OP_ELOSS = 19, 20, 21, 22, 23, 24
-OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D = 25, 26, 27, 28
+OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D, OP_FORK, OP_JOIN = 25, 26, 27, 28, 29, 30
 GEMM_TF32, GEMM_A_MN, GEMM_B_MN = 1, 2, 4
 
 OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6}
@@ -107,6 +107,7 @@ _SIGNATURES = {
     "dk_engine_create": (vp, []),
     "dk_engine_destroy": (None, [vp]),
     "dk_engine_new_list": (i32, [vp]),
+    "dk_engine_set_build_stream": (i32, [vp, i32]),
     "dk_engine_clear_list": (i32, [vp, i32]),
     "dk_engine_set_slot": (i32, [vp, i32, vp]),
     "dk_engine_add_op": (i32, [vp, i32, i32, C.POINTER(C.c_int64), i32, C.POINTER(f64), i32]),

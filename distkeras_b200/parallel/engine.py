@@ -323,6 +323,10 @@ class NativeReplica(Replica):
                 rows, K, Nout = b.out["rows"], b.k_in, b.n_out
                 if b.act == "relu" and not premasked:
                     self._add(lst, N.OP_RELU_MASK, [grad["t"].data_ptr(), b.out["t"].data_ptr(), rows * grad["ld"]])
+                # parameter gradients only feed the optimizer: they run on the engine's side stream
+                # (a parallel branch of the captured graph) while the dgrad chain continues
+                self._add(lst, N.OP_FORK, [0])
+                self.lib.dk_engine_set_build_stream(self.engine, 1)
                 if b.bseg is not None:
                     self._add(lst, N.OP_COLSUM, [grad["t"].data_ptr(), rows, Nout, grad["ld"],
                                                  g_ptr + 4 * b.bseg.offset], [1.0])
@@ -331,6 +335,7 @@ class NativeReplica(Replica):
                 ep.d, ep.ldd, ep.d_fp32, ep.alpha = g_ptr + 4 * b.kseg.offset, K, 1, 1.0
                 self._gemm(lst, grad["t"].data_ptr(), grad["ld"], b.a_in["t"].data_ptr(), b.a_in["ld"], Nout, K,
                            rows, N.GEMM_A_MN | N.GEMM_B_MN, ep)
+                self.lib.dk_engine_set_build_stream(self.engine, 0)
                 if bi == first_param_block:
                     break
                 # dgrad: dIn[rows, K] = dZ[rows, Nout] * W[Nout, K]   (W read as an MN-major B operand)
@@ -368,6 +373,7 @@ class NativeReplica(Replica):
                 inp = b.inp
                 grad = dict(t=grad["t"], rows=inp["rows"], cols=inp["cols"], ld=inp["ld"])
         # ---- optimizer (one fused launch over the flat buffer, emits the bf16 shadow) ----
+        self._add(lst, N.OP_JOIN, [0])
         o = self.opt
         self._add(lst, N.OP_OPTIM, [N.OPT_KINDS[o.kernel_kind], self.W.data_ptr(), g_ptr, N.ptr(o.s0), N.ptr(o.s1),
                                     self.Wb.data_ptr(), self.P, int(o.nesterov), self.step_counter.data_ptr()],
