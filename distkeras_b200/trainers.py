@@ -47,7 +47,8 @@ def _default_backend() -> str:
     return "fabric" if torch.cuda.is_available() else "thread"
 
 
-def _run_tasks(worker_proto, partitions: List[Partition], num_threads: int, device_for=None) -> List[list]:
+def _run_tasks(worker_proto, partitions: List[Partition], num_threads: int, device_for=None,
+               tolerate_failures: bool = False) -> List[list]:
     """Run ``worker.train(index, partition)`` for every partition on a pool of ``num_threads``
     threads pulling from a shared queue (dynamic shard queue = the reference's
     over-partitioning straggler mitigation, ``trainers.py:624-629``).  Each task gets its own copy
@@ -58,6 +59,7 @@ def _run_tasks(worker_proto, partitions: List[Partition], num_threads: int, devi
     results: List[Optional[list]] = [None] * len(partitions)
     workers_out: List[Optional[object]] = [None] * len(partitions)
     errors: List[BaseException] = []
+    retries: dict = {}
 
     def loop(tid: int):
         while True:
@@ -75,6 +77,14 @@ def _run_tasks(worker_proto, partitions: List[Partition], num_threads: int, devi
                 workers_out[part.index] = w
             except BaseException as exc:  # surfaced to the caller, not swallowed
                 errors.append(exc)
+                if tolerate_failures:
+                    # the shard goes back to the queue for a surviving worker (Spark would re-run the
+                    # task; the lost worker's uncommitted window is dropped)
+                    retries[part.index] = retries.get(part.index, 0) + 1
+                    if retries[part.index] <= 2:
+                        tasks.put(part)
+                    results[part.index] = []
+                    continue
                 return
 
     threads = [threading.Thread(target=loop, args=(i,), daemon=True) for i in range(max(1, num_threads))]
@@ -82,8 +92,9 @@ def _run_tasks(worker_proto, partitions: List[Partition], num_threads: int, devi
         t.start()
     for t in threads:
         t.join()
-    if errors:
+    if errors and not tolerate_failures:
         raise errors[0]
+    worker_proto.failures = errors
     return results, workers_out
 
 
@@ -291,6 +302,8 @@ class DistributedTrainer(Trainer):
         self.communication_window = 1
         self.strict = bool(int(os.environ.get("DK_STRICT", "0")))
         self.checkpoint_path: Optional[str] = None
+        self.tolerate_worker_failures = False
+        self.worker_failures: list = []
 
     # -- accessors (``trainers.py:389-460``) ---------------------------------------------------
     def set_minibatch_size(self, size: int) -> None:
@@ -405,7 +418,9 @@ class DistributedTrainer(Trainer):
         dataframe = dataframe.repartition(n_parts)
         self.record_training_start()
         try:
-            results, _ = _run_tasks(worker, dataframe.partitions(n_parts), self.num_workers, self._thread_device)
+            results, _ = _run_tasks(worker, dataframe.partitions(n_parts), self.num_workers, self._thread_device,
+                                    tolerate_failures=self.tolerate_worker_failures)
+            self.worker_failures = list(getattr(worker, "failures", []))
         finally:
             self.record_training_end()
             if backend == "socket":
@@ -413,8 +428,14 @@ class DistributedTrainer(Trainer):
             else:
                 self.parameter_server.running = False
                 self.parameter_server.finalize()
-        self.history = [h for r in results for h in r]
-        return self.parameter_server.get_model()
+        self.history = [h for r in results for h in (r or [])]
+        model = self.parameter_server.get_model()
+        if self.checkpoint_path:
+            from .utils.checkpoint import save_checkpoint
+
+            save_checkpoint(self.checkpoint_path, model, self.parameter_server.get_num_updates(),
+                            max([h["iteration"] for h in self.history], default=0), history=None)
+        return model
 
 
 class AsynchronousDistributedTrainer(DistributedTrainer):

@@ -1,0 +1,39 @@
+"""Runtime configuration: constructor kwargs stay the primary interface, like the
+reference; this dataclass collects the process-wide switches with environment overrides."""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+
+def _env_bool(name: str, default: bool) -> bool:
+    v = os.environ.get(name)
+    return default if v is None else v.strip().lower() in ("1", "true", "yes", "on")
+
+
+@dataclass
+class RuntimeConfig:
+    backend: Optional[str] = field(default_factory=lambda: os.environ.get("DK_BACKEND"))  # fabric|thread|socket
+    strict: bool = field(default_factory=lambda: _env_bool("DK_STRICT", False))           # ticket-lock commits
+    comm: str = field(default_factory=lambda: os.environ.get("DK_COMM", "exchange"))      # exchange|commit_pull
+    dedicated_ps: bool = field(default_factory=lambda: _env_bool("DK_DEDICATED_PS", False))
+    fault: Optional[str] = field(default_factory=lambda: os.environ.get("DK_FAULT"))      # "<worker>:<iteration>"
+    log_level: str = field(default_factory=lambda: os.environ.get("DK_LOG", "WARNING"))
+
+    def apply(self, trainer) -> None:
+        if self.backend:
+            trainer.backend = self.backend
+        trainer.strict = self.strict
+        trainer.comm = self.comm
+        trainer.dedicated_ps = self.dedicated_ps
+
+
+def fault_injection_point(worker_id: int, iteration: int) -> None:
+    """Test hook: ``DK_FAULT=<worker>:<iteration>`` makes that worker fail there."""
+    spec = os.environ.get("DK_FAULT")
+    if not spec:
+        return
+    w, it = spec.split(":")
+    if int(w) == int(worker_id) and int(it) == int(iteration):
+        raise RuntimeError(f"injected fault: worker {worker_id} at iteration {iteration}")

@@ -136,6 +136,9 @@ class Worker:
         raise NotImplementedError
 
     def add_history(self, h: Sequence[float]) -> None:
+        from .utils.config import fault_injection_point
+
+        fault_injection_point(self.worker_id, self.iteration)
         self.training_history.append({"history": [float(v) for v in h], "worker_id": self.worker_id,
                                       "iteration": self.iteration, "timestamp": time.time()})
 

@@ -1,0 +1,129 @@
+"""Aux subsystems: job deployment, checkpoint/resume, fault injection, gloo multi-process (CPU)."""
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from distkeras_b200.data import Dataset
+from distkeras_b200.job_deployment import Job, Punchcard
+from distkeras_b200.models import Dense, Sequential
+from distkeras_b200.trainers import ADAG, SingleTrainer
+from distkeras_b200.utils.checkpoint import load_checkpoint, resume_trainer, save_checkpoint
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def tiny_model(seed=0):
+    return Sequential([Dense(16, activation="relu", input_shape=(8,)), Dense(3, activation="softmax")], seed=seed)
+
+
+def tiny_data(n=256, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 8, generator=g)
+    w = torch.randn(8, 3, generator=g)
+    return Dataset({"features": x, "label": (x @ w).argmax(1).to(torch.int32)})
+
+
+def test_checkpoint_roundtrip_and_resume(tmp_path):
+    m = tiny_model(3)
+    m.build()
+    path = str(tmp_path / "ck.pt")
+    save_checkpoint(path, m, num_updates=7, iteration=42, extra={"note": "x"})
+    p = load_checkpoint(path)
+    assert p["num_updates"] == 7 and p["iteration"] == 42 and p["extra"]["note"] == "x"
+    assert torch.equal(p["model"].get_flat_weights(), m.get_flat_weights())
+    t = ADAG(tiny_model(0), "sgd", "categorical_crossentropy", num_workers=1, batch_size=16, communication_window=2)
+    t.backend = "thread"
+    resume_trainer(t, path)
+    assert np.allclose(t.master_model["flat"], m.get_flat_weights().numpy())
+    t.checkpoint_path = str(tmp_path / "after.pt")
+    out = t.train(tiny_data())
+    after = load_checkpoint(t.checkpoint_path)
+    assert torch.equal(after["model"].get_flat_weights(), out.get_flat_weights()) and after["num_updates"] > 1
+
+
+def test_fault_injection_is_survivable(monkeypatch):
+    monkeypatch.setenv("DK_FAULT", "1:3")  # worker 1 dies at its 3rd batch
+    t = ADAG(tiny_model(0), "sgd", "categorical_crossentropy", num_workers=2, batch_size=16, communication_window=2)
+    t.backend = "thread"
+    with pytest.raises(RuntimeError, match="injected fault"):
+        t.train(tiny_data())  # default: failures surface (the reference prints and swallows them)
+    t2 = ADAG(tiny_model(0), "sgd", "categorical_crossentropy", num_workers=2, batch_size=16, communication_window=2)
+    t2.backend = "thread"
+    t2.tolerate_worker_failures = True
+    model = t2.train(tiny_data())  # PS never waits on a worker; the shard is retried by a survivor
+    assert len(t2.worker_failures) >= 1 and torch.isfinite(model.get_flat_weights()).all()
+
+
+def test_punchcard_job_roundtrip(tmp_path):
+    secrets = tmp_path / "secrets.json"
+    secrets.write_text(json.dumps([{"secret": "S3CRET", "identity": "tester"}]))
+    data = tmp_path / "data.pt"
+    torch.save(tiny_data(128), str(data))
+    daemon = Punchcard(secrets_path=str(secrets), port=0, host="127.0.0.1")
+    port = daemon.start()
+    try:
+        trainer = SingleTrainer(tiny_model(0), "adam", "categorical_crossentropy", batch_size=16)
+        trainer.backend = "thread"
+        bad = Job("WRONG", "j", str(data), 1, 1, trainer)
+        with pytest.raises(RuntimeError):
+            bad.send(f"http://127.0.0.1:{port}")
+        job = Job("S3CRET", "unit-test-job", str(data), 1, 1, trainer)
+        job.poll_interval = 0.2
+        job.send(f"http://127.0.0.1:{port}")
+        job.wait_completion()
+        assert job.error is None, job.error
+        model = job.get_trained_model()
+        assert model is not None and len(job.get_history()) == 8
+        assert not torch.equal(model.get_flat_weights(), tiny_model(0).build().get_flat_weights())
+    finally:
+        daemon.shutdown()
+
+
+def test_generate_secret_script():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "generate_secret.py"), "--identity", "bob"],
+                         capture_output=True, text=True, check=True).stdout
+    d = json.loads(out)
+    assert d["identity"] == "bob" and len(d["secret"]) == 64
+
+
+SPMD_SCRIPT = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+from distkeras_b200.data import Dataset
+from distkeras_b200.models import Dense, Sequential
+from distkeras_b200.trainers import ADAG
+g = torch.Generator().manual_seed(0)
+x = torch.randn(256, 8, generator=g); w = torch.randn(8, 3, generator=g)
+ds = Dataset({{"features": x, "label": (x @ w).argmax(1).to(torch.int32)}})
+m = Sequential([Dense(16, activation="relu", input_shape=(8,)), Dense(3, activation="softmax")], seed=0)
+t = ADAG(m, {{"class_name": "adam", "config": {{"lr": 0.02}}}}, "categorical_crossentropy", num_workers=2, batch_size=16,
+         communication_window=2, num_epoch=2)
+t.backend = "socket"
+model = t.train(ds)
+model.compile("categorical_crossentropy")
+acc = model.evaluate(ds["features"], ds["label"])[1]
+print("RANK", os.environ["RANK"], "HIST", len(t.get_history()), "ACC", round(acc, 3), "SUM", float(model.get_flat_weights().sum()))
+"""
+
+
+def test_spmd_gloo_two_processes(tmp_path):
+    """torchrun-style world_size=2 on CPU: rank 0 hosts the TCP parameter server, both ranks train."""
+    script = tmp_path / "spmd.py"
+    script.write_text(SPMD_SCRIPT.format(root=ROOT))
+    port = 29600 + os.getpid() % 300
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=240, env={**os.environ, "DK_BACKEND": "socket"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("RANK")]
+    assert len(lines) == 2
+    sums = {l.split("SUM")[1].strip() for l in lines}
+    assert len(sums) == 1  # both ranks return the same final model
+    assert all("HIST 32" in l for l in lines)
+    assert all(float(l.split("ACC")[1].split()[0]) > 0.5 for l in lines)
