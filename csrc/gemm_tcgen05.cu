@@ -454,10 +454,12 @@ static int launch_gemm(const GemmLaunch& L) {
   cudaStream_t stream = L.stream;
   using S = GemmSmem<BN, STAGES, TF32>;
   auto kern = gemm_tn_kernel<BN, STAGES, TF32, AMN, BMN>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};  // function attributes are per device
+  int dev = 0;
+  DK_HOST_CHECK(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
     DK_HOST_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    configured = true;
+    configured[dev & 63] = true;
   }
   constexpr int kBlockK = TF32 ? 32 : 64;
   const int total_kb = (K + kBlockK - 1) / kBlockK;

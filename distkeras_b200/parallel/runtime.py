@@ -277,6 +277,119 @@ class FabricWorker:
         self.drain()
 
 
+class FabricEagerWorker:
+    """Fabric worker for models the native planner does not lower yet (BatchNorm / residual
+    blocks): the autograd executor trains the replica on the GPU, while every commit / pull still
+    runs as the in-kernel NVLink program on the flat fp32 buffer (no NCCL, no host socket)."""
+
+    def __init__(self, model, optimizer, loss: str, algorithm: dict, region: FabricRegion, worker_id: int,
+                 batch_size: int, device_index: int, in_dtype: str, input_affine=(1.0, 0.0), comm: str = "exchange",
+                 strict: bool = False, dense_labels: bool = False, seed: int = 0):
+        from .replica import TorchReplica
+
+        self.alg = dict(algorithm)
+        self.tau = int(self.alg["window"])
+        self.region, self.worker_id, self.B = region, int(worker_id), int(batch_size)
+        self.comm = "commit_pull" if strict else comm
+        self.strict = strict
+        self.device = torch.device("cuda", device_index)
+        torch.cuda.set_device(self.device)
+        model = model.copy().to(self.device)
+        self.rep = TorchReplica(model, optimizer, loss, device=self.device, seed=seed + worker_id)
+        self.lib = N.lib()
+        self.scale, self.shift = float(input_affine[0]), float(input_affine[1])
+        self.W = self.rep.W.data
+        self.P = self.W.numel()
+        self.W1 = self.W.clone()
+        self.last_update = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.scale_dev = torch.ones(1, dtype=torch.float32, device=self.device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if self.alg["kind"] == "eamsgd":
+            self.mom = torch.zeros_like(self.W)
+            self.wcopy = torch.zeros_like(self.W)
+        self.compute = torch.cuda.current_stream(self.device)
+        self.history: List[dict] = []
+        self.iteration = 0
+        self.windows_run = 0
+        self.kernels_per_window = 0
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def comm_kernels(self) -> int:
+        return 1
+
+    def _stream(self):
+        return C.c_void_p(N.current_stream())
+
+    def _comm_ops(self) -> None:
+        reg, lib, k = self.region, self.lib, self.alg["kind"]
+        c, ctrl = C.c_void_p(reg.center_ptr), C.c_void_p(reg.ctrl_ptr)
+        W, W1, st = self.W.data_ptr(), self.W1.data_ptr(), self._stream()
+        if self.strict:
+            N.check(lib.dk_ps_lock_acquire(ctrl, self.ticket.data_ptr(), st), "lock_acquire")
+        if k in ("adag", "downpour", "dynsgd"):
+            scale = 1.0 / self.tau if k == "adag" else 1.0
+            sdev = None
+            if k == "dynsgd":
+                N.check(lib.dk_ps_ticket(ctrl, self.last_update.data_ptr(), self.scale_dev.data_ptr(), st), "ticket")
+                sdev = self.scale_dev.data_ptr()
+            if self.comm == "exchange":
+                N.check(lib.dk_ps_exchange(c, W, W1, None, self.P, scale, sdev, ctrl, self.worker_id, self.iteration,
+                                           self.last_update.data_ptr(), st), "exchange")
+            else:
+                N.check(lib.dk_ps_commit(c, W, W1, self.P, scale, sdev, ctrl, self.worker_id, self.iteration, st),
+                        "commit")
+                N.check(lib.dk_ps_pull(c, W, W1, None, self.P, ctrl, self.last_update.data_ptr(), st), "pull")
+        elif k in ("aeasgd", "eamsgd"):
+            N.check(lib.dk_ps_elastic(c, W, None, self.P, float(self.alg["alpha"]), ctrl, self.worker_id,
+                                      self.iteration, st), "elastic")
+        elif k == "experimental":
+            N.check(lib.dk_ps_damped_exchange(c, W, W1, None, self.P, 1.0 / self.tau, float(self.alg["inv_lr"]), ctrl,
+                                              self.worker_id, self.iteration, st), "damped_exchange")
+        if self.strict:
+            N.check(lib.dk_ps_lock_release(ctrl, self.ticket.data_ptr(), st), "lock_release")
+        self.windows_run += 1
+
+    def initial_pull(self) -> None:
+        reg = self.region
+        N.check(self.lib.dk_ps_pull(C.c_void_p(reg.center_ptr), self.W.data_ptr(), self.W1.data_ptr(), None, self.P,
+                                    C.c_void_p(reg.ctrl_ptr), self.last_update.data_ptr(), self._stream()), "pull")
+        torch.cuda.synchronize(self.device)
+
+    def capture(self) -> None:
+        pass
+
+    def drain(self) -> None:
+        torch.cuda.synchronize(self.device)
+
+    def train_partition(self, part: Partition, features_col: str, label_col: str, num_epoch: int = 1) -> None:
+        x_all, y_all = part.column(features_col), part.column(label_col)
+        pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd")
+        n = x_all.shape[0] // self.B
+        for _ in range(num_epoch):
+            for b in range(n):
+                self.iteration += 1
+                x = x_all[b * self.B:(b + 1) * self.B].to(self.device, non_blocking=True).float()
+                if self.scale != 1.0 or self.shift != 0.0:
+                    x = x * self.scale + self.shift
+                y = y_all[b * self.B:(b + 1) * self.B].to(self.device, non_blocking=True)
+                self.h2d_bytes += x_all[0].numel() * x_all.element_size() * self.B
+                if pre_batch and self.iteration % self.tau == 0:
+                    self._comm_ops()
+                if self.alg["kind"] == "eamsgd":
+                    N.check(self.lib.dk_eamsgd_pre(self.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(), None,
+                                                   self.P, float(self.alg["momentum"]), self._stream()), "eamsgd_pre")
+                loss, acc = self.rep.train_on_batch(x, y.long() if y.dim() == 1 else y)
+                if self.alg["kind"] == "eamsgd":
+                    N.check(self.lib.dk_eamsgd_post(self.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(), None,
+                                                    self.P, float(self.alg["eta"]), self._stream()), "eamsgd_post")
+                self.d2h_bytes += 8
+                self.history.append({"history": [loss, acc], "worker_id": self.worker_id, "iteration": self.iteration,
+                                     "timestamp": time.time()})
+                if not pre_batch and self.iteration % self.tau == 0:
+                    self._comm_ops()
+        self.drain()
+
+
 # ================================================================================================
 # orchestration
 # ================================================================================================
@@ -322,9 +435,13 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         dataset.pin_memory()
         parts = dataset.repartition(n_parts).partitions(n_parts)
         wid = worker_ranks.index(rank)
-        worker = FabricWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid, trainer.batch_size,
-                              local, in_dtype, affine, comm=getattr(trainer, "comm", "exchange"),
-                              strict=trainer.strict, seed=getattr(trainer, "seed", 0))
+        wkw = dict(comm=getattr(trainer, "comm", "exchange"), strict=trainer.strict, seed=getattr(trainer, "seed", 0))
+        try:
+            worker = FabricWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid, trainer.batch_size,
+                                  local, in_dtype, affine, **wkw)
+        except UnsupportedByNativeEngine:
+            worker = FabricEagerWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid,
+                                       trainer.batch_size, local, in_dtype, affine, **wkw)
         worker.initial_pull()
         worker.capture()
         static = getattr(trainer, "shard_mode", "dynamic" if trainer.parallelism_factor > 1 else "static") == "static"
@@ -373,11 +490,11 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         steps_done = worker.iteration - it0
         windows_done = worker.windows_run - w0
         tail_steps = steps_done - windows_done * worker.tau
-        per_step = (worker.kernels_per_window - worker.comm_kernels()) // worker.tau
+        per_step = max(0, worker.kernels_per_window - worker.comm_kernels()) // worker.tau
         stats = {"kernels_per_window": worker.kernels_per_window, "windows": windows_done, "steps": steps_done,
                  "gpu_launches": windows_done * worker.kernels_per_window + tail_steps * per_step,
                  "h2d_bytes": worker.h2d_bytes, "d2h_bytes": worker.d2h_bytes, "seconds": time.time() - t0,
-                 "device_ms": ev0.elapsed_time(ev1)}
+                 "device_ms": ev0.elapsed_time(ev1), "executor": type(worker).__name__}
         history = worker.history
     else:
         barrier()

@@ -173,6 +173,31 @@ def test_native_predictor_matches_autograd():
     assert torch.allclose(pred, torch.as_tensor(m.predict(x)), atol=0.02)
 
 
+def test_fabric_eager_worker_for_batchnorm_models():
+    """Models the native planner cannot lower (BatchNorm / residual) still train on the fabric:
+    autograd executor + in-kernel commit / pull (BN statistics travel through the PS)."""
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.models import BatchNormalization, Conv2D, Dense, GlobalAveragePooling2D, ResidualBlock, Sequential
+    from distkeras_b200.trainers import DynSGD
+
+    m = Sequential([Conv2D(8, 3, padding="same", use_bias=False, input_shape=(8, 8, 3)), BatchNormalization(),
+                    ResidualBlock(8), ResidualBlock(16, strides=2), GlobalAveragePooling2D(),
+                    Dense(4, activation="softmax")], seed=0)
+    g = torch.Generator().manual_seed(0)
+    y = torch.randint(0, 4, (512,), generator=g)
+    x = torch.rand(512, 8, 8, 3, generator=g) + y.view(-1, 1, 1, 1).float() * 0.5
+    ds = Dataset({"features": x, "label": y.to(torch.int32)})
+    t = DynSGD(m, {"class_name": "adam", "config": {"lr": 0.01}}, "categorical_crossentropy", num_workers=1,
+               batch_size=32, communication_window=2, num_epoch=3)
+    t.backend = "fabric"
+    model = t.train(ds)
+    h = t.get_history()
+    assert t.fabric_stats[0]["executor"] == "FabricEagerWorker"
+    assert np.mean([r["history"][0] for r in h[-4:]]) < np.mean([r["history"][0] for r in h[:4]])
+    assert t.num_updates() == 1 + len(h) // 2
+    assert sum(t.staleness_histogram) == len(h) // 2
+
+
 def test_smoke_entry():
     import __graft_entry__
 
