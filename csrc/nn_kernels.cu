@@ -233,6 +233,123 @@ col2im_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int H, in
   }
 }
 
+// 8-channel vector form of the gather (C % 8 == 0): one 16-byte load per covering window
+__global__ void __launch_bounds__(256)
+col2im_vec8_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int H, int W, int C, int KH,
+                   int KW, int stride, int pad, int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+  const int c8n = C >> 3;
+  const long total = static_cast<long>(B) * H * W * c8n;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    long t = i;
+    const int c = static_cast<int>(t % c8n) << 3; t /= c8n;
+    const int iw = static_cast<int>(t % W); t /= W;
+    const int ih = static_cast<int>(t % H); t /= H;
+    const int b = static_cast<int>(t);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int kh = 0; kh < KH; ++kh) {
+      const int ohs = ih + pad - kh;
+      if (ohs < 0 || ohs % stride != 0) continue;
+      const int oh = ohs / stride;
+      if (oh >= OH) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ows = iw + pad - kw;
+        if (ows < 0 || ows % stride != 0) continue;
+        const int ow = ows / stride;
+        if (ow >= OW) continue;
+        const long row = (static_cast<long>(b) * OH + oh) * OW + ow;
+        const uint4 q = *reinterpret_cast<const uint4*>(col + row * ldcol + (kh * KW + kw) * C + c);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = __bfloat1622float2(h[u]);
+          acc[2 * u] += f.x;
+          acc[2 * u + 1] += f.y;
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(dx + (i << 3)) = o;
+  }
+}
+
+// 8-channel vector forms of the pooling kernels (C % 8 == 0)
+__global__ void __launch_bounds__(256)
+maxpool_fwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int k, int stride,
+                        int OH, int OW, __nv_bfloat16* __restrict__ y) {
+  const int c8n = C >> 3;
+  const long total = static_cast<long>(B) * OH * OW * c8n;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    long t = i;
+    const int c = static_cast<int>(t % c8n) << 3; t /= c8n;
+    const int ow = static_cast<int>(t % OW); t /= OW;
+    const int oh = static_cast<int>(t % OH); t /= OH;
+    const int b = static_cast<int>(t);
+    float m[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m[u] = -INFINITY;
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) {
+        const int ih = oh * stride + kh, iw = ow * stride + kw;
+        if (ih < H && iw < W) {
+          const uint4 q = *reinterpret_cast<const uint4*>(x + ((static_cast<long>(b) * H + ih) * W + iw) * C + c);
+          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) m[u] = fmaxf(m[u], __bfloat162float(h[u]));
+        }
+      }
+    uint4 o;
+    o.x = pack_bf16x2(m[0], m[1]); o.y = pack_bf16x2(m[2], m[3]);
+    o.z = pack_bf16x2(m[4], m[5]); o.w = pack_bf16x2(m[6], m[7]);
+    *reinterpret_cast<uint4*>(y + (i << 3)) = o;
+  }
+}
+
+// one thread per OUTPUT window and 8 channels: writes the whole k x k input-gradient window
+// (non-overlapping windows), first-max position receives the gradient
+__global__ void __launch_bounds__(256)
+maxpool_bwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int B, int H,
+                        int W, int C, int k, int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+  const int c8n = C >> 3;
+  const long total = static_cast<long>(B) * OH * OW * c8n;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    long t = i;
+    const int c = static_cast<int>(t % c8n) << 3; t /= c8n;
+    const int ow = static_cast<int>(t % OW); t /= OW;
+    const int oh = static_cast<int>(t % OH); t /= OH;
+    const int b = static_cast<int>(t);
+    float m[8];
+    int arg[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { m[u] = -INFINITY; arg[u] = 0; }
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) {
+        const uint4 q = *reinterpret_cast<const uint4*>(
+            x + ((static_cast<long>(b) * H + oh * k + kh) * W + ow * k + kw) * C + c);
+        const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float v = __bfloat162float(h[u]);
+          if (v > m[u]) { m[u] = v; arg[u] = kh * k + kw; }
+        }
+      }
+    const uint4 gq = *reinterpret_cast<const uint4*>(dy + (i << 3));
+    const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&gq);
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) {
+        __nv_bfloat16 o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = (arg[u] == kh * k + kw) ? g[u] : __float2bfloat16_rn(0.f);
+        *reinterpret_cast<uint4*>(dx + ((static_cast<long>(b) * H + oh * k + kh) * W + ow * k + kw) * C + c) =
+            *reinterpret_cast<const uint4*>(o);
+      }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int k, int stride,
                    int OH, int OW, __nv_bfloat16* __restrict__ y) {
@@ -379,8 +496,11 @@ int dk_rowsum_bf16(const void* src, int rows, int cols, int lds, float* out, flo
 }
 
 int dk_colsum_bf16(const void* src, int rows, int cols, int lds, float* out, float scale, void* stream) {
+  const int colblocks = (cols + 63) / 64;
   int splits = (rows + 255) / 256;
-  if (splits > 64) splits = 64;
+  int cap = (148 * 8) / colblocks;  // fill the GPU even when the matrix is narrow
+  if (cap < 64) cap = 64;
+  if (splits > cap) splits = cap;
   const int rpb = (rows + splits - 1) / splits;
   dim3 grid((cols + 63) / 64, splits);
   colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows,
@@ -402,6 +522,14 @@ int dk_im2col(const void* x, int B, int H, int W, int C, int KH, int KW, int str
 
 int dk_col2im(const void* col, int ldcol, int B, int H, int W, int C, int KH, int KW, int stride, int pad,
               int OH, int OW, void* dx, void* stream) {
+  if (C % 8 == 0 && ldcol % 8 == 0) {
+    const long total8 = static_cast<long>(B) * H * W * (C / 8);
+    col2im_vec8_kernel<<<ew_grid(total8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(col), ldcol, B, H, W, C, KH, KW, stride, pad, OH, OW,
+        reinterpret_cast<__nv_bfloat16*>(dx));
+    DK_HOST_CHECK(cudaGetLastError());
+    return 0;
+  }
   const long total = static_cast<long>(B) * H * W * C;
   col2im_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(col), ldcol, B, H, W, C, KH, KW, stride, pad, OH, OW,
@@ -412,6 +540,13 @@ int dk_col2im(const void* col, int ldcol, int B, int H, int W, int C, int KH, in
 
 int dk_maxpool_fwd(const void* x, int B, int H, int W, int C, int k, int stride, void* y, void* stream) {
   const int OH = (H - k) / stride + 1, OW = (W - k) / stride + 1;
+  if (C % 8 == 0) {
+    const long total8 = static_cast<long>(B) * OH * OW * (C / 8);
+    maxpool_fwd_vec8_kernel<<<ew_grid(total8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, k, stride, OH, OW, reinterpret_cast<__nv_bfloat16*>(y));
+    DK_HOST_CHECK(cudaGetLastError());
+    return 0;
+  }
   const long total = static_cast<long>(B) * OH * OW * C;
   maxpool_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, k, stride, OH, OW,
@@ -423,6 +558,14 @@ int dk_maxpool_fwd(const void* x, int B, int H, int W, int C, int k, int stride,
 int dk_maxpool_bwd(const void* x, const void* y, const void* dy, int B, int H, int W, int C, int k,
                    int stride, void* dx, void* stream) {
   const int OH = (H - k) / stride + 1, OW = (W - k) / stride + 1;
+  if (C % 8 == 0 && k == stride && H % k == 0 && W % k == 0) {
+    const long total8 = static_cast<long>(B) * OH * OW * (C / 8);
+    maxpool_bwd_vec8_kernel<<<ew_grid(total8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), B, H, W, C, k, OH, OW,
+        reinterpret_cast<__nv_bfloat16*>(dx));
+    DK_HOST_CHECK(cudaGetLastError());
+    return 0;
+  }
   const long total = static_cast<long>(B) * H * W * C;
   maxpool_bwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(y),
