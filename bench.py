@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Headline benchmark: ADAG / DOWNPOUR / AEASGD samples/s on the MNIST MLP (or CIFAR-10 CNN) on N B200s.
 
-    python bench.py --gpus 1 --steps 240 --warmup 24
+    python bench.py --gpus 1 --steps 1200 --warmup 48
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-        --master-port 29511 bench.py --gpus 8 --steps 240 --warmup 24
+        --master-port 29511 bench.py --gpus 8 --steps 1200 --warmup 48
 
 A *step* is one mini-batch of ``--batch`` samples on EVERY worker (weak scaling: per-GPU work is
 fixed), including that worker's share of the parameter-server traffic (one fused commit + pull
@@ -60,7 +60,8 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self):
+    def __init__(self, n_gpus: int = 1):
+        self.n_gpus = n_gpus
         self.proc = None
         self.path = os.path.join("/tmp", f"dk_clocks_{os.getpid()}.csv")
 
@@ -68,7 +69,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
@@ -89,7 +90,7 @@ class ClockSampler:
             if len(parts) < 8:
                 continue
             try:
-                if float(parts[3]) < 250.0:  # idle GPU of the box: not under load
+                if int(parts[0]) >= self.n_gpus:  # GPUs of the box this job does not use
                     continue
                 sm.append(float(parts[1]))
                 mx.append(float(parts[2]))
@@ -109,8 +110,8 @@ class ClockSampler:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=240)
-    ap.add_argument("--warmup", type=int, default=24)
+    ap.add_argument("--steps", type=int, default=1200)
+    ap.add_argument("--warmup", type=int, default=48)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--algo", default="adag", choices=["adag", "downpour", "aeasgd", "dynsgd", "eamsgd", "experimental"])
     ap.add_argument("--model", default="mnist_mlp", choices=["mnist_mlp", "cifar10_cnn", "mnist_convnet", "higgs_mlp"])
@@ -176,7 +177,14 @@ def main() -> None:
     for s in in_shape:
         feat *= s
     g = torch.Generator().manual_seed(1234 + rank)
-    rows = (W + K) * B
+    # e2e host dataset: W warm-up steps + `chunk` steps replayed K / chunk times (keeps the pinned
+    # footprint bounded for long runs; the timed region is still exactly K steps streamed from host)
+    chunk = K
+    for c in (480, 360, 240, 120):
+        if K > c and K % c == 0 and c % tau == 0:
+            chunk = c
+            break
+    rows = (W + chunk) * B
     is_worker = (rank >= 1 or not args.dedicated_ps) or world == 1
 
     # ---------------------------------------------------------------- kernel-only (device-timed)
@@ -192,7 +200,7 @@ def main() -> None:
     info = exchange_obj(info, 0)
     region = ps.region if rank == 0 else FabricRegion.open(info, local)
     ms_dev, launches = 0.0, 0
-    sampler = ClockSampler()
+    sampler = ClockSampler(world)
     if is_worker:
         wid = rank - 1 if (args.dedicated_ps and world > 1) else rank
         in_dtype = "f32" if args.model == "higgs_mlp" else "u8"
@@ -267,6 +275,7 @@ def main() -> None:
         ds = Dataset({"features": x, "label": y})
         trainer.data_is_local_shard = True
         trainer.bench_warmup_steps = W
+        trainer.set_num_epoch(K // chunk)
         trainer.train(ds)
         stats = [s for s in trainer.fabric_stats if s.get("steps")]
         e2e_ms = max(s["device_ms"] for s in stats)

@@ -19,7 +19,52 @@
     }                                                                                \
   } while (0)
 
+#include <stdlib.h>
+
+#include <utility>
+
+// Programmatic dependent launch (PDL): every kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel of the stream (or graph
+// branch) may start its prologue while this one drains.  DK_PDL_WAIT() must precede the first
+// access to memory produced by earlier kernels; DK_PDL_TRIGGER() lets the dependent launch as soon
+// as all CTAs of this grid have started.  Set DK_PDL=0 to launch without the attribute.
+#define DK_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define DK_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define DK_PDL_ENTER() \
+  do {                 \
+    DK_PDL_WAIT();     \
+    DK_PDL_TRIGGER();  \
+  } while (0)
+
 namespace dk {
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DK_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+#define DK_LAUNCH(kern, grid, block, smem, stream, ...) \
+  dk::launch_kernel((kern), dim3(grid), dim3(block), (smem), (cudaStream_t)(stream), __VA_ARGS__)
 
 // ---------------------------------------------------------------------------
 // misc

@@ -135,6 +135,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail
+  // of the previous kernel; operands / bias / mask produced by it are only touched after this point
+  DK_PDL_WAIT();
+  DK_PDL_TRIGGER();
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -475,8 +479,8 @@ static int launch_gemm(const GemmLaunch& L) {
   ep.tma_mask = (L.tm != nullptr && ep.tma_store && BN >= 64) ? 1 : 0;
   if (splits > 1 && !ep.d_fp32) return -6;
   dim3 grid((N + BN - 1) / BN, (M + kBlockM - 1) / kBlockM, splits);
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, ep.tma_store ? *L.td : ta, ep.tma_mask ? *L.tm : ta, ep, M,
-                                                  N, K, kb_per_split);
+  DK_HOST_CHECK(DK_LAUNCH(kern, grid, kGemmThreads, S::kTotal, stream, ta, tb, ep.tma_store ? *L.td : ta, ep.tma_mask ? *L.tm : ta, ep, M,
+                                                  N, K, kb_per_split));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }

@@ -14,6 +14,7 @@ softmax_xent_kernel(const float* __restrict__ logits, int ldl, const int* __rest
                     __nv_bfloat16* __restrict__ dz, int ldz, __nv_bfloat16* __restrict__ dzt, int ldzt,
                     float* __restrict__ probs, float* __restrict__ hist, const int* __restrict__ step,
                     int hist_slots) {
+  DK_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
@@ -104,6 +105,7 @@ softmax_xent_small_kernel(const float* __restrict__ logits, int ldl, const int* 
                           __nv_bfloat16* __restrict__ dz, int ldz, __nv_bfloat16* __restrict__ dzt,
                           int ldzt, float* __restrict__ probs, float* __restrict__ hist,
                           const int* __restrict__ step, int hist_slots) {
+  DK_PDL_ENTER();
   const float inv_b = 1.f / static_cast<float>(B);
   float loss_acc = 0.f, correct_acc = 0.f;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < B; row += gridDim.x * blockDim.x) {
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(256)
 elementwise_loss_kernel(int kind, const float* __restrict__ out, const float* __restrict__ target, int B,
                         int C, __nv_bfloat16* __restrict__ dz, int ldz, __nv_bfloat16* __restrict__ dzt,
                         int ldzt, float* __restrict__ hist, const int* __restrict__ step, int hist_slots) {
+  DK_PDL_ENTER();
   const long n = static_cast<long>(B) * C;
   const float inv = 1.f / static_cast<float>(n);
   float loss = 0.f, corr = 0.f;
@@ -216,6 +219,7 @@ elementwise_loss_kernel(int kind, const float* __restrict__ out, const float* __
 __global__ void __launch_bounds__(256)
 label_index_kernel(const float* __restrict__ probs, int B, int C, float threshold, int default_index,
                    int* __restrict__ out_index, const int* __restrict__ labels, int* correct_count) {
+  DK_PDL_ENTER();
   int local = 0;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < B; r += gridDim.x * blockDim.x) {
     const float* p = probs + static_cast<size_t>(r) * C;
@@ -248,17 +252,17 @@ int dk_softmax_xent(const float* logits, int ldl, const int* labels, const float
                     const int* step, int hist_slots, void* stream) {
   if (C <= 16) {
     int blocks = (B + 127) / 128;
-    softmax_xent_small_kernel<16><<<blocks, 128, 0, (cudaStream_t)stream>>>(
+    DK_HOST_CHECK(DK_LAUNCH(softmax_xent_small_kernel<16>, blocks, 128, 0, (cudaStream_t)stream, 
         logits, ldl, labels, labels_dense, B, C, reinterpret_cast<__nv_bfloat16*>(dz), ldz,
-        reinterpret_cast<__nv_bfloat16*>(dzt), ldzt, probs, hist, step, hist_slots);
+        reinterpret_cast<__nv_bfloat16*>(dzt), ldzt, probs, hist, step, hist_slots));
     DK_HOST_CHECK(cudaGetLastError());
     return 0;
   }
   int blocks = (B + 7) / 8;
   if (blocks > 148 * 4) blocks = 148 * 4;
-  softmax_xent_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  DK_HOST_CHECK(DK_LAUNCH(softmax_xent_kernel, blocks, 256, 0, (cudaStream_t)stream, 
       logits, ldl, labels, labels_dense, B, C, reinterpret_cast<__nv_bfloat16*>(dz), ldz,
-      reinterpret_cast<__nv_bfloat16*>(dzt), ldzt, probs, hist, step, hist_slots);
+      reinterpret_cast<__nv_bfloat16*>(dzt), ldzt, probs, hist, step, hist_slots));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -268,9 +272,9 @@ int dk_elementwise_loss(int kind, const float* out, const float* target, int B, 
   long n = static_cast<long>(B) * C;
   int blocks = static_cast<int>((n + 255) / 256);
   if (blocks > 148 * 4) blocks = 148 * 4;
-  elementwise_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  DK_HOST_CHECK(DK_LAUNCH(elementwise_loss_kernel, blocks, 256, 0, (cudaStream_t)stream, 
       kind, out, target, B, C, reinterpret_cast<__nv_bfloat16*>(dz), ldz,
-      reinterpret_cast<__nv_bfloat16*>(dzt), ldzt, hist, step, hist_slots);
+      reinterpret_cast<__nv_bfloat16*>(dzt), ldzt, hist, step, hist_slots));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -279,8 +283,8 @@ int dk_label_index(const float* probs, int B, int C, float threshold, int defaul
                    const int* labels, int* correct_count, void* stream) {
   int blocks = (B + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
-  label_index_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(probs, B, C, threshold, default_index,
-                                                               out_index, labels, correct_count);
+  DK_HOST_CHECK(DK_LAUNCH(label_index_kernel, blocks, 256, 0, (cudaStream_t)stream, probs, B, C, threshold, default_index,
+                                                               out_index, labels, correct_count));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }

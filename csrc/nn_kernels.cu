@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256)
 input_stage_kernel(const T* __restrict__ x, int B, int F, float scale, float shift,
                    __nv_bfloat16* __restrict__ xb, int ldx, __nv_bfloat16* __restrict__ xt, int ldxt,
                    int* step_counter) {
+  DK_PDL_ENTER();
   __shared__ __nv_bfloat16 tile[32][33];
   const int f0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -55,6 +56,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 input_stage_vec_kernel(const T* __restrict__ x, long rows, int F, float scale, float shift,
                        __nv_bfloat16* __restrict__ xb, int ldx, int* step_counter) {
+  DK_PDL_ENTER();
   const int f8 = F >> 3;  // F % 8 == 0 guaranteed by the launcher
   const long total = rows * f8;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -91,6 +93,7 @@ input_stage_vec_kernel(const T* __restrict__ x, long rows, int F, float scale, f
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, int lds,
                       __nv_bfloat16* __restrict__ dst, int ldd) {
+  DK_PDL_ENTER();
   __shared__ __nv_bfloat16 tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -107,6 +110,7 @@ transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols,
 __global__ void __launch_bounds__(256)
 rowsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, int lds,
                    float* __restrict__ out, float scale) {
+  DK_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -137,6 +141,7 @@ rowsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, in
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, int lds,
                    float* __restrict__ out, float scale, int rows_per_block) {
+  DK_PDL_ENTER();
   __shared__ float red[8][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 64 + lane * 2;
@@ -174,6 +179,7 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, in
 __global__ void __launch_bounds__(256)
 im2col_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int KH, int KW,
               int stride, int pad, int OH, int OW, __nv_bfloat16* __restrict__ col, int ldcol) {
+  DK_PDL_ENTER();
   // one thread per (row, kh, kw, c8-chunk); channels are innermost -> contiguous copies
   const int cvec = (C % 8 == 0) ? 8 : 1;
   const int cchunks = C / cvec;
@@ -206,6 +212,7 @@ im2col_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, i
 __global__ void __launch_bounds__(256)
 col2im_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int H, int W, int C, int KH,
               int KW, int stride, int pad, int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+  DK_PDL_ENTER();
   const long total = static_cast<long>(B) * H * W * C;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -237,6 +244,7 @@ col2im_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int H, in
 __global__ void __launch_bounds__(256)
 col2im_vec8_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int H, int W, int C, int KH,
                    int KW, int stride, int pad, int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+  DK_PDL_ENTER();
   const int c8n = C >> 3;
   const long total = static_cast<long>(B) * H * W * c8n;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -279,6 +287,7 @@ col2im_vec8_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int 
 __global__ void __launch_bounds__(256)
 maxpool_fwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int k, int stride,
                         int OH, int OW, __nv_bfloat16* __restrict__ y) {
+  DK_PDL_ENTER();
   const int c8n = C >> 3;
   const long total = static_cast<long>(B) * OH * OW * c8n;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -313,6 +322,7 @@ maxpool_fwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W
 __global__ void __launch_bounds__(256)
 maxpool_bwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int B, int H,
                         int W, int C, int k, int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+  DK_PDL_ENTER();
   const int c8n = C >> 3;
   const long total = static_cast<long>(B) * OH * OW * c8n;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -353,6 +363,7 @@ maxpool_bwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int k, int stride,
                    int OH, int OW, __nv_bfloat16* __restrict__ y) {
+  DK_PDL_ENTER();
   const long total = static_cast<long>(B) * OH * OW * C;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -377,6 +388,7 @@ __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
                    const __nv_bfloat16* __restrict__ dy, int B, int H, int W, int C, int k, int stride,
                    int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+  DK_PDL_ENTER();
   const long total = static_cast<long>(B) * H * W * C;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -411,6 +423,7 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 
 __global__ void __launch_bounds__(256)
 relu_mask_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ act, long n) {
+  DK_PDL_ENTER();
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long>(gridDim.x) * blockDim.x)
     if (!(__bfloat162float(act[i]) > 0.f)) dy[i] = __float2bfloat16_rn(0.f);
@@ -419,6 +432,7 @@ relu_mask_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict
 __global__ void __launch_bounds__(256)
 add_bf16_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ a,
                 const __nv_bfloat16* __restrict__ b, long n, int relu) {
+  DK_PDL_ENTER();
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     float v = __bfloat162float(a[i]) + __bfloat162float(b[i]);
@@ -454,43 +468,43 @@ int dk_input_stage(const void* x, int in_dtype, int B, int F, float scale, float
     if (blocks > 148 * 16) blocks = 148 * 16;
     const int g = static_cast<int>(blocks < 1 ? 1 : blocks);
     if (in_dtype == DK_IN_U8)
-      input_stage_vec_kernel<uint8_t><<<g, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(x), B, F, scale, shift,
-                                                         xbp, ldx, step_counter);
+      DK_HOST_CHECK(DK_LAUNCH(input_stage_vec_kernel<uint8_t>, g, 256, 0, st, reinterpret_cast<const uint8_t*>(x), B, F, scale, shift,
+                                                         xbp, ldx, step_counter));
     else if (in_dtype == DK_IN_F32)
-      input_stage_vec_kernel<float><<<g, 256, 0, st>>>(reinterpret_cast<const float*>(x), B, F, scale, shift, xbp,
-                                                       ldx, step_counter);
+      DK_HOST_CHECK(DK_LAUNCH(input_stage_vec_kernel<float>, g, 256, 0, st, reinterpret_cast<const float*>(x), B, F, scale, shift, xbp,
+                                                       ldx, step_counter));
     else
-      input_stage_vec_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), B, F, scale,
-                                                               shift, xbp, ldx, step_counter);
+      DK_HOST_CHECK(DK_LAUNCH(input_stage_vec_kernel<__nv_bfloat16>, g, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(x), B, F, scale,
+                                                               shift, xbp, ldx, step_counter));
     DK_HOST_CHECK(cudaGetLastError());
     return 0;
   }
   if (in_dtype == DK_IN_U8)
-    input_stage_kernel<uint8_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(x), B, F, scale,
-                                                      shift, xbp, ldx, xtp, ldxt, step_counter);
+    DK_HOST_CHECK(DK_LAUNCH(input_stage_kernel<uint8_t>, grid, 256, 0, st, reinterpret_cast<const uint8_t*>(x), B, F, scale,
+                                                      shift, xbp, ldx, xtp, ldxt, step_counter));
   else if (in_dtype == DK_IN_F32)
-    input_stage_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), B, F, scale,
-                                                    shift, xbp, ldx, xtp, ldxt, step_counter);
+    DK_HOST_CHECK(DK_LAUNCH(input_stage_kernel<float>, grid, 256, 0, st, reinterpret_cast<const float*>(x), B, F, scale,
+                                                    shift, xbp, ldx, xtp, ldxt, step_counter));
   else
-    input_stage_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+    DK_HOST_CHECK(DK_LAUNCH(input_stage_kernel<__nv_bfloat16>, grid, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(x),
                                                             B, F, scale, shift, xbp, ldx, xtp, ldxt,
-                                                            step_counter);
+                                                            step_counter));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_transpose_bf16(const void* src, int rows, int cols, int lds, void* dst, int ldd, void* stream) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-  transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+  DK_HOST_CHECK(DK_LAUNCH(transpose_bf16_kernel, grid, 256, 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(src), rows, cols, lds, reinterpret_cast<__nv_bfloat16*>(dst),
-      ldd);
+      ldd));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_rowsum_bf16(const void* src, int rows, int cols, int lds, float* out, float scale, void* stream) {
-  rowsum_bf16_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), rows, cols, lds, out, scale);
+  DK_HOST_CHECK(DK_LAUNCH(rowsum_bf16_kernel, (rows + 7) / 8, 256, 0, (cudaStream_t)stream, 
+      reinterpret_cast<const __nv_bfloat16*>(src), rows, cols, lds, out, scale));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -503,8 +517,8 @@ int dk_colsum_bf16(const void* src, int rows, int cols, int lds, float* out, flo
   if (splits > cap) splits = cap;
   const int rpb = (rows + splits - 1) / splits;
   dim3 grid((cols + 63) / 64, splits);
-  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows,
-                                                            cols, lds, out, scale, rpb);
+  DK_HOST_CHECK(DK_LAUNCH(colsum_bf16_kernel, grid, 256, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(src), rows,
+                                                            cols, lds, out, scale, rpb));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -513,9 +527,9 @@ int dk_im2col(const void* x, int B, int H, int W, int C, int KH, int KW, int str
               int OW, void* col, int ldcol, void* stream) {
   const int cvec = (C % 8 == 0) ? 8 : 1;
   const long total = static_cast<long>(B) * OH * OW * KH * KW * (C / cvec);
-  im2col_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+  DK_HOST_CHECK(DK_LAUNCH(im2col_kernel, ew_grid(total), 256, 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, KH, KW, stride, pad, OH, OW,
-      reinterpret_cast<__nv_bfloat16*>(col), ldcol);
+      reinterpret_cast<__nv_bfloat16*>(col), ldcol));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -524,16 +538,16 @@ int dk_col2im(const void* col, int ldcol, int B, int H, int W, int C, int KH, in
               int OH, int OW, void* dx, void* stream) {
   if (C % 8 == 0 && ldcol % 8 == 0) {
     const long total8 = static_cast<long>(B) * H * W * (C / 8);
-    col2im_vec8_kernel<<<ew_grid(total8), 256, 0, (cudaStream_t)stream>>>(
+    DK_HOST_CHECK(DK_LAUNCH(col2im_vec8_kernel, ew_grid(total8), 256, 0, (cudaStream_t)stream, 
         reinterpret_cast<const __nv_bfloat16*>(col), ldcol, B, H, W, C, KH, KW, stride, pad, OH, OW,
-        reinterpret_cast<__nv_bfloat16*>(dx));
+        reinterpret_cast<__nv_bfloat16*>(dx)));
     DK_HOST_CHECK(cudaGetLastError());
     return 0;
   }
   const long total = static_cast<long>(B) * H * W * C;
-  col2im_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+  DK_HOST_CHECK(DK_LAUNCH(col2im_kernel, ew_grid(total), 256, 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(col), ldcol, B, H, W, C, KH, KW, stride, pad, OH, OW,
-      reinterpret_cast<__nv_bfloat16*>(dx));
+      reinterpret_cast<__nv_bfloat16*>(dx)));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -542,15 +556,15 @@ int dk_maxpool_fwd(const void* x, int B, int H, int W, int C, int k, int stride,
   const int OH = (H - k) / stride + 1, OW = (W - k) / stride + 1;
   if (C % 8 == 0) {
     const long total8 = static_cast<long>(B) * OH * OW * (C / 8);
-    maxpool_fwd_vec8_kernel<<<ew_grid(total8), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, k, stride, OH, OW, reinterpret_cast<__nv_bfloat16*>(y));
+    DK_HOST_CHECK(DK_LAUNCH(maxpool_fwd_vec8_kernel, ew_grid(total8), 256, 0, (cudaStream_t)stream, 
+        reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, k, stride, OH, OW, reinterpret_cast<__nv_bfloat16*>(y)));
     DK_HOST_CHECK(cudaGetLastError());
     return 0;
   }
   const long total = static_cast<long>(B) * OH * OW * C;
-  maxpool_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+  DK_HOST_CHECK(DK_LAUNCH(maxpool_fwd_kernel, ew_grid(total), 256, 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, k, stride, OH, OW,
-      reinterpret_cast<__nv_bfloat16*>(y));
+      reinterpret_cast<__nv_bfloat16*>(y)));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -560,32 +574,32 @@ int dk_maxpool_bwd(const void* x, const void* y, const void* dy, int B, int H, i
   const int OH = (H - k) / stride + 1, OW = (W - k) / stride + 1;
   if (C % 8 == 0 && k == stride && H % k == 0 && W % k == 0) {
     const long total8 = static_cast<long>(B) * OH * OW * (C / 8);
-    maxpool_bwd_vec8_kernel<<<ew_grid(total8), 256, 0, (cudaStream_t)stream>>>(
+    DK_HOST_CHECK(DK_LAUNCH(maxpool_bwd_vec8_kernel, ew_grid(total8), 256, 0, (cudaStream_t)stream, 
         reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), B, H, W, C, k, OH, OW,
-        reinterpret_cast<__nv_bfloat16*>(dx));
+        reinterpret_cast<__nv_bfloat16*>(dx)));
     DK_HOST_CHECK(cudaGetLastError());
     return 0;
   }
   const long total = static_cast<long>(B) * H * W * C;
-  maxpool_bwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+  DK_HOST_CHECK(DK_LAUNCH(maxpool_bwd_kernel, ew_grid(total), 256, 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(y),
       reinterpret_cast<const __nv_bfloat16*>(dy), B, H, W, C, k, stride, OH, OW,
-      reinterpret_cast<__nv_bfloat16*>(dx));
+      reinterpret_cast<__nv_bfloat16*>(dx)));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_relu_mask_bf16(void* dy, const void* act, long n, void* stream) {
-  relu_mask_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<__nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(act), n);
+  DK_HOST_CHECK(DK_LAUNCH(relu_mask_kernel, ew_grid(n), 256, 0, (cudaStream_t)stream, 
+      reinterpret_cast<__nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(act), n));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_add_bf16(void* dst, const void* a, const void* b, long n, int relu, void* stream) {
-  add_bf16_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
+  DK_HOST_CHECK(DK_LAUNCH(add_bf16_kernel, ew_grid(n), 256, 0, (cudaStream_t)stream, 
       reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<const __nv_bfloat16*>(a),
-      reinterpret_cast<const __nv_bfloat16*>(b), n, relu);
+      reinterpret_cast<const __nv_bfloat16*>(b), n, relu));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }

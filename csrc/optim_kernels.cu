@@ -57,6 +57,7 @@ __device__ __forceinline__ void optim_update(float& w, float g, float& s0, float
 
 template <int KIND>
 __global__ void __launch_bounds__(256) optim_kernel(const OptimArgs a) {
+  DK_PDL_ENTER();
   constexpr bool kS0 = KIND != DK_OPT_SGD;
   constexpr bool kS1 = KIND == DK_OPT_ADAM || KIND == DK_OPT_ADADELTA || KIND == DK_OPT_ADAMAX;
   const int t = a.step != nullptr ? max(*a.step, 1) : 1;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) optim_kernel(const OptimArgs a) {
 __global__ void __launch_bounds__(256)
 eamsgd_pre_kernel(float* __restrict__ w, float* __restrict__ r, float* __restrict__ wcopy,
                   __nv_bfloat16* __restrict__ wb, long n, float mu) {
+  DK_PDL_ENTER();
   const long stride = static_cast<long>(gridDim.x) * blockDim.x;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float rt = mu * r[i];
@@ -124,6 +126,7 @@ eamsgd_pre_kernel(float* __restrict__ w, float* __restrict__ r, float* __restric
 __global__ void __launch_bounds__(256)
 eamsgd_post_kernel(float* __restrict__ w, float* __restrict__ r, const float* __restrict__ wcopy,
                    __nv_bfloat16* __restrict__ wb, long n, float eta) {
+  DK_PDL_ENTER();
   const long stride = static_cast<long>(gridDim.x) * blockDim.x;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float rt = r[i];
@@ -138,6 +141,7 @@ eamsgd_post_kernel(float* __restrict__ w, float* __restrict__ r, const float* __
 
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long n) {
+  DK_PDL_ENTER();
   const long stride = static_cast<long>(gridDim.x) * blockDim.x;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     dst[i] = __float2bfloat16_rn(src[i]);
@@ -166,13 +170,13 @@ int dk_optim_step(int kind, float* w, const float* g, float* s0, float* s1, void
   const int grid = flat_grid(n, 4);
   cudaStream_t st = (cudaStream_t)stream;
   switch (kind) {
-    case DK_OPT_SGD: optim_kernel<DK_OPT_SGD><<<grid, 256, 0, st>>>(a); break;
-    case DK_OPT_MOMENTUM: optim_kernel<DK_OPT_MOMENTUM><<<grid, 256, 0, st>>>(a); break;
-    case DK_OPT_ADAGRAD: optim_kernel<DK_OPT_ADAGRAD><<<grid, 256, 0, st>>>(a); break;
-    case DK_OPT_RMSPROP: optim_kernel<DK_OPT_RMSPROP><<<grid, 256, 0, st>>>(a); break;
-    case DK_OPT_ADAM: optim_kernel<DK_OPT_ADAM><<<grid, 256, 0, st>>>(a); break;
-    case DK_OPT_ADADELTA: optim_kernel<DK_OPT_ADADELTA><<<grid, 256, 0, st>>>(a); break;
-    case DK_OPT_ADAMAX: optim_kernel<DK_OPT_ADAMAX><<<grid, 256, 0, st>>>(a); break;
+    case DK_OPT_SGD: DK_HOST_CHECK(DK_LAUNCH(optim_kernel<DK_OPT_SGD>, grid, 256, 0, st, a)); break;
+    case DK_OPT_MOMENTUM: DK_HOST_CHECK(DK_LAUNCH(optim_kernel<DK_OPT_MOMENTUM>, grid, 256, 0, st, a)); break;
+    case DK_OPT_ADAGRAD: DK_HOST_CHECK(DK_LAUNCH(optim_kernel<DK_OPT_ADAGRAD>, grid, 256, 0, st, a)); break;
+    case DK_OPT_RMSPROP: DK_HOST_CHECK(DK_LAUNCH(optim_kernel<DK_OPT_RMSPROP>, grid, 256, 0, st, a)); break;
+    case DK_OPT_ADAM: DK_HOST_CHECK(DK_LAUNCH(optim_kernel<DK_OPT_ADAM>, grid, 256, 0, st, a)); break;
+    case DK_OPT_ADADELTA: DK_HOST_CHECK(DK_LAUNCH(optim_kernel<DK_OPT_ADADELTA>, grid, 256, 0, st, a)); break;
+    case DK_OPT_ADAMAX: DK_HOST_CHECK(DK_LAUNCH(optim_kernel<DK_OPT_ADAMAX>, grid, 256, 0, st, a)); break;
     default: return -1;
   }
   DK_HOST_CHECK(cudaGetLastError());
@@ -180,22 +184,22 @@ int dk_optim_step(int kind, float* w, const float* g, float* s0, float* s1, void
 }
 
 int dk_eamsgd_pre(float* w, float* r, float* wcopy, void* wb, long n, float mu, void* stream) {
-  eamsgd_pre_kernel<<<flat_grid(n, 1), 256, 0, (cudaStream_t)stream>>>(
-      w, r, wcopy, reinterpret_cast<__nv_bfloat16*>(wb), n, mu);
+  DK_HOST_CHECK(DK_LAUNCH(eamsgd_pre_kernel, flat_grid(n, 1), 256, 0, (cudaStream_t)stream, 
+      w, r, wcopy, reinterpret_cast<__nv_bfloat16*>(wb), n, mu));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_eamsgd_post(float* w, float* r, const float* wcopy, void* wb, long n, float eta, void* stream) {
-  eamsgd_post_kernel<<<flat_grid(n, 1), 256, 0, (cudaStream_t)stream>>>(
-      w, r, wcopy, reinterpret_cast<__nv_bfloat16*>(wb), n, eta);
+  DK_HOST_CHECK(DK_LAUNCH(eamsgd_post_kernel, flat_grid(n, 1), 256, 0, (cudaStream_t)stream, 
+      w, r, wcopy, reinterpret_cast<__nv_bfloat16*>(wb), n, eta));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_cast_bf16(const float* src, void* dst, long n, void* stream) {
-  cast_bf16_kernel<<<flat_grid(n, 1), 256, 0, (cudaStream_t)stream>>>(
-      src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  DK_HOST_CHECK(DK_LAUNCH(cast_bf16_kernel, flat_grid(n, 1), 256, 0, (cudaStream_t)stream, 
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kPsThreads)
 ps_commit_kernel(float* __restrict__ center, const float* __restrict__ w, const float* __restrict__ w1,
                  long n, float scale, const float* __restrict__ scale_dev, unsigned* ctrl, int worker,
                  unsigned iteration) {
+  DK_PDL_ENTER();
   const float s = load_scale(scale_dev, scale);
   flat_for_each(
       n,
@@ -115,6 +116,7 @@ ps_commit_kernel(float* __restrict__ center, const float* __restrict__ w, const 
 __global__ void __launch_bounds__(kPsThreads)
 ps_pull_kernel(const float* __restrict__ center, float* __restrict__ w, float* __restrict__ w1,
                __nv_bfloat16* __restrict__ wb, long n, const unsigned* ctrl, unsigned* last_update) {
+  DK_PDL_ENTER();
   flat_for_each(
       n,
       [&](long i) {
@@ -142,6 +144,7 @@ ps_exchange_kernel(float* __restrict__ center, float* __restrict__ w, float* __r
                    __nv_bfloat16* __restrict__ wb, long n, float scale,
                    const float* __restrict__ scale_dev, unsigned* ctrl, int worker,
                    unsigned iteration, unsigned* last_update) {
+  DK_PDL_ENTER();
   const float s = load_scale(scale_dev, scale);
   flat_for_each(
       n,
@@ -179,6 +182,7 @@ ps_exchange_kernel(float* __restrict__ center, float* __restrict__ w, float* __r
 __global__ void __launch_bounds__(kPsThreads)
 ps_elastic_kernel(float* __restrict__ center, float* __restrict__ w, __nv_bfloat16* __restrict__ wb,
                   long n, float alpha, unsigned* ctrl, int worker, unsigned iteration) {
+  DK_PDL_ENTER();
   flat_for_each(
       n,
       [&](long i) {
@@ -212,6 +216,7 @@ __global__ void __launch_bounds__(kPsThreads)
 ps_damped_exchange_kernel(float* __restrict__ center, float* __restrict__ w, float* __restrict__ w1,
                           __nv_bfloat16* __restrict__ wb, long n, float scale, float inv_lr,
                           unsigned* ctrl, int worker, unsigned iteration) {
+  DK_PDL_ENTER();
   // w1 doubles as the stale center variable (the worker's last pulled copy, workers.py:553-563).
   flat_for_each(
       n,
@@ -252,6 +257,7 @@ ps_damped_exchange_kernel(float* __restrict__ center, float* __restrict__ w, flo
 
 // DynSGD ticket: num_updates += 1; scale = 1 / (num_updates_before - last_update + 1).
 __global__ void ps_ticket_kernel(unsigned* ctrl, const unsigned* last_update, float* scale_out) {
+  DK_PDL_ENTER();
   unsigned old;
   asm volatile("atom.relaxed.sys.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctrl + DK_CTRL_NUM_UPDATES) : "memory");
   const unsigned last = *last_update;
@@ -267,6 +273,7 @@ __global__ void ps_ticket_kernel(unsigned* ctrl, const unsigned* last_update, fl
 // Host-visible fetch-add on a control word (dynamic shard queue: workers claim the next data
 // partition; the replacement for Spark's task scheduler + `parallelism_factor` over-partitioning).
 __global__ void ps_fetch_add_kernel(unsigned* word, unsigned inc, unsigned* out) {
+  DK_PDL_ENTER();
   unsigned old;
   asm volatile("atom.relaxed.sys.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(word), "r"(inc) : "memory");
   *out = old;
@@ -274,6 +281,7 @@ __global__ void ps_fetch_add_kernel(unsigned* word, unsigned inc, unsigned* out)
 
 // Ticket lock (strict mode): serialises whole commit(+pull) sequences like the reference's mutex.
 __global__ void ps_lock_acquire_kernel(unsigned* ctrl, unsigned* my_ticket) {
+  DK_PDL_ENTER();
   unsigned t;
   asm volatile("atom.relaxed.sys.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(ctrl + DK_CTRL_LOCK_NEXT) : "memory");
   *my_ticket = t;
@@ -285,6 +293,7 @@ __global__ void ps_lock_acquire_kernel(unsigned* ctrl, unsigned* my_ticket) {
 }
 
 __global__ void ps_lock_release_kernel(unsigned* ctrl, const unsigned* my_ticket) {
+  DK_PDL_ENTER();
   const unsigned t = *my_ticket + 1u;
   asm volatile("fence.acq_rel.sys;" ::: "memory");
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ctrl + DK_CTRL_LOCK_SERVING), "r"(t) : "memory");
@@ -299,6 +308,7 @@ struct PeerPtrs {
 
 __global__ void __launch_bounds__(kPsThreads)
 ps_average_kernel(PeerPtrs peers, int num_peers, long lo, long hi, float inv) {
+  DK_PDL_ENTER();
   const long n = hi - lo;
   flat_for_each(
       n,
@@ -324,6 +334,7 @@ ps_average_kernel(PeerPtrs peers, int num_peers, long lo, long hi, float inv) {
 // Plain device copy/zero helpers used by benchmarks (peer read / write bandwidth).
 __global__ void __launch_bounds__(kPsThreads)
 ps_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, long n) {
+  DK_PDL_ENTER();
   flat_for_each(
       n, [&](long i) { *reinterpret_cast<float4*>(dst + i) = ld_sys_v4(src + i); },
       [&](long i) { dst[i] = ld_sys(src + i); });
@@ -344,16 +355,16 @@ extern "C" {
 
 int dk_ps_commit(float* center, const float* w, const float* w1, long n, float scale,
                  const float* scale_dev, unsigned* ctrl, int worker, unsigned iteration, void* stream) {
-  ps_commit_kernel<<<ps_grid(n), kPsThreads, 0, (cudaStream_t)stream>>>(center, w, w1, n, scale, scale_dev,
-                                                                       ctrl, worker, iteration);
+  DK_HOST_CHECK(DK_LAUNCH(ps_commit_kernel, ps_grid(n), kPsThreads, 0, (cudaStream_t)stream, center, w, w1, n, scale, scale_dev,
+                                                                       ctrl, worker, iteration));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_ps_pull(const float* center, float* w, float* w1, void* wb, long n, const unsigned* ctrl,
                unsigned* last_update, void* stream) {
-  ps_pull_kernel<<<ps_grid(n), kPsThreads, 0, (cudaStream_t)stream>>>(
-      center, w, w1, reinterpret_cast<__nv_bfloat16*>(wb), n, ctrl, last_update);
+  DK_HOST_CHECK(DK_LAUNCH(ps_pull_kernel, ps_grid(n), kPsThreads, 0, (cudaStream_t)stream, 
+      center, w, w1, reinterpret_cast<__nv_bfloat16*>(wb), n, ctrl, last_update));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -361,49 +372,49 @@ int dk_ps_pull(const float* center, float* w, float* w1, void* wb, long n, const
 int dk_ps_exchange(float* center, float* w, float* w1, void* wb, long n, float scale,
                    const float* scale_dev, unsigned* ctrl, int worker, unsigned iteration,
                    unsigned* last_update, void* stream) {
-  ps_exchange_kernel<<<ps_grid(n), kPsThreads, 0, (cudaStream_t)stream>>>(
+  DK_HOST_CHECK(DK_LAUNCH(ps_exchange_kernel, ps_grid(n), kPsThreads, 0, (cudaStream_t)stream, 
       center, w, w1, reinterpret_cast<__nv_bfloat16*>(wb), n, scale, scale_dev, ctrl, worker, iteration,
-      last_update);
+      last_update));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_ps_elastic(float* center, float* w, void* wb, long n, float alpha, unsigned* ctrl, int worker,
                   unsigned iteration, void* stream) {
-  ps_elastic_kernel<<<ps_grid(n), kPsThreads, 0, (cudaStream_t)stream>>>(
-      center, w, reinterpret_cast<__nv_bfloat16*>(wb), n, alpha, ctrl, worker, iteration);
+  DK_HOST_CHECK(DK_LAUNCH(ps_elastic_kernel, ps_grid(n), kPsThreads, 0, (cudaStream_t)stream, 
+      center, w, reinterpret_cast<__nv_bfloat16*>(wb), n, alpha, ctrl, worker, iteration));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_ps_damped_exchange(float* center, float* w, float* w1, void* wb, long n, float scale,
                           float inv_lr, unsigned* ctrl, int worker, unsigned iteration, void* stream) {
-  ps_damped_exchange_kernel<<<ps_grid(n), kPsThreads, 0, (cudaStream_t)stream>>>(
-      center, w, w1, reinterpret_cast<__nv_bfloat16*>(wb), n, scale, inv_lr, ctrl, worker, iteration);
+  DK_HOST_CHECK(DK_LAUNCH(ps_damped_exchange_kernel, ps_grid(n), kPsThreads, 0, (cudaStream_t)stream, 
+      center, w, w1, reinterpret_cast<__nv_bfloat16*>(wb), n, scale, inv_lr, ctrl, worker, iteration));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_ps_ticket(unsigned* ctrl, const unsigned* last_update, float* scale_out, void* stream) {
-  ps_ticket_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctrl, last_update, scale_out);
+  DK_HOST_CHECK(DK_LAUNCH(ps_ticket_kernel, 1, 1, 0, (cudaStream_t)stream, ctrl, last_update, scale_out));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_ps_fetch_add(unsigned* word, unsigned inc, unsigned* out, void* stream) {
-  ps_fetch_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(word, inc, out);
+  DK_HOST_CHECK(DK_LAUNCH(ps_fetch_add_kernel, 1, 1, 0, (cudaStream_t)stream, word, inc, out));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_ps_lock_acquire(unsigned* ctrl, unsigned* my_ticket, void* stream) {
-  ps_lock_acquire_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctrl, my_ticket);
+  DK_HOST_CHECK(DK_LAUNCH(ps_lock_acquire_kernel, 1, 1, 0, (cudaStream_t)stream, ctrl, my_ticket));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_ps_lock_release(unsigned* ctrl, const unsigned* my_ticket, void* stream) {
-  ps_lock_release_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctrl, my_ticket);
+  DK_HOST_CHECK(DK_LAUNCH(ps_lock_release_kernel, 1, 1, 0, (cudaStream_t)stream, ctrl, my_ticket));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -414,14 +425,14 @@ int dk_ps_average(float* const* peer_ptrs, int num_peers, long lo, long hi, void
   for (int i = 0; i < num_peers; ++i) pp.p[i] = peer_ptrs[i];
   // slice bounds must keep float4 alignment
   if ((lo & 3) != 0) return -2;
-  ps_average_kernel<<<ps_grid(hi - lo), kPsThreads, 0, (cudaStream_t)stream>>>(pp, num_peers, lo, hi,
-                                                                              1.f / num_peers);
+  DK_HOST_CHECK(DK_LAUNCH(ps_average_kernel, ps_grid(hi - lo), kPsThreads, 0, (cudaStream_t)stream, pp, num_peers, lo, hi,
+                                                                              1.f / num_peers));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dk_ps_copy(float* dst, const float* src, long n, void* stream) {
-  ps_copy_kernel<<<ps_grid(n), kPsThreads, 0, (cudaStream_t)stream>>>(dst, src, n);
+  DK_HOST_CHECK(DK_LAUNCH(ps_copy_kernel, ps_grid(n), kPsThreads, 0, (cudaStream_t)stream, dst, src, n));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
