@@ -118,7 +118,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=None, help="mini-batch per worker")
     ap.add_argument("--window", type=int, default=None, help="communication window (ADAG default 12)")
     ap.add_argument("--optimizer", default="adam")
-    ap.add_argument("--comm", default="exchange", choices=["exchange", "commit_pull"])
+    ap.add_argument("--comm", default="exchange", choices=["exchange", "commit_pull", "fused_pull"])
     ap.add_argument("--dedicated-ps", action="store_true", help="rank 0 hosts the center only (N-1 workers)")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()

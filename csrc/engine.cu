@@ -77,9 +77,14 @@ int run_op(Engine* e, Op& op, void* main_stream) {
   void* st = op.stream_id == 1 ? (void*)e->side : main_stream;
   switch (op.kind) {
     case DK_OP_INPUT:
-      // x, in_dtype, B, F, xb, ldx, xt, ldxt, step_counter | scale, shift
+      // x, in_dtype, B, F, xb, ldx, xt, ldxt, step_counter, xf, ldxf | scale, shift
       return dk_input_stage(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (float)f[0], (float)f[1],
-                            resolve(e, a[4]), (int)a[5], resolve(e, a[6]), (int)a[7], rp<int>(e, a[8]), st);
+                            resolve(e, a[4]), (int)a[5], resolve(e, a[6]), (int)a[7], rp<int>(e, a[8]),
+                            resolve(e, a[9]), (int)a[10], st);
+    case DK_OP_GEMM_PULL:
+      // M, N, K, w_local, w1_local, wb_local, ldw (tensor maps + epilogue pre-encoded)
+      return dk_gemm_pull_launch(&op.ta, &op.tb, op.has_td ? &op.td : nullptr, &op.ep, (int)a[0], (int)a[1], (int)a[2],
+                                 rp<float>(e, a[3]), rp<float>(e, a[4]), resolve(e, a[5]), (int)a[6], st);
     case DK_OP_GEMM:
       // M, N, K, bn, flags (tensor maps + epilogue pre-encoded)
       return dk_gemm_tn_launch2(&op.ta, &op.tb, op.has_td ? &op.td : nullptr, op.has_tm ? &op.tm : nullptr, &op.ep,
@@ -273,6 +278,29 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
                  ? dk_gemm_pick_splits(M, N, K, bn, flags & DK_GEMM_TF32)
                  : 1;
   op.i[0] = M; op.i[1] = N; op.i[2] = K; op.i[3] = bn; op.i[4] = flags; op.i[5] = splits;
+  e->lists[list].push_back(op);
+  return static_cast<int>(e->lists[list].size()) - 1;
+}
+
+// First-layer forward with the weight pull fused in: X fp32 [M, K] local, center_w fp32 [N, K] in the
+// parameter server's (peer-mapped) HBM; w / w1 / wb are the local copies refreshed by the kernel.
+int dk_engine_add_gemm_pull(void* h, int list, const void* X, long ldx, const void* center_w, long ldc, int M, int N,
+                            int K, void* w_local, void* w1_local, void* wb_local, const DkGemmEpilogue* ep) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (list < 0 || list >= (int)e->lists.size()) return -1;
+  Op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = DK_OP_GEMM_PULL;
+  op.stream_id = e->build_stream;
+  int r = dk_tmap_encode_2d(&op.ta, X, DK_F32, M, K, ldx, 128);
+  if (r != 0) return r;
+  r = dk_tmap_encode_2d(&op.tb, center_w, DK_F32, N, K, ldc, 128);
+  if (r != 0) return r;
+  op.ep = *ep;
+  op.has_td = ep->d != nullptr && dk_gemm_encode_output(&op.td, ep->d, ep->ldd, M, N, ep->d_fp32) == 0;
+  op.i[0] = M; op.i[1] = N; op.i[2] = K;
+  op.i[3] = (int64_t)(uintptr_t)w_local; op.i[4] = (int64_t)(uintptr_t)w1_local; op.i[5] = (int64_t)(uintptr_t)wb_local;
+  op.i[6] = ldc;
   e->lists[list].push_back(op);
   return static_cast<int>(e->lists[list].size()) - 1;
 }

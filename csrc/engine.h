@@ -39,7 +39,8 @@ enum {
   DK_OP_COLSUM = 27,
   DK_OP_MEMCPY2D = 28,
   DK_OP_FORK = 29,
-  DK_OP_JOIN = 30
+  DK_OP_JOIN = 30,
+  DK_OP_GEMM_PULL = 31
 };
 
 #ifdef __cplusplus
@@ -57,6 +58,8 @@ int dk_engine_add_op(void* h, int list, int kind, const int64_t* iargs, int ni, 
                      int nf);
 int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B, long ldb, int M, int N,
                        int K, int flags, int bn, int splits, const DkGemmEpilogue* ep);
+int dk_engine_add_gemm_pull(void* h, int list, const void* X, long ldx, const void* center_w, long ldc, int M, int N,
+                            int K, void* w_local, void* w1_local, void* wb_local, const DkGemmEpilogue* ep);
 int dk_engine_run(void* h, int list, void* stream);
 int dk_engine_list_size(void* h, int list);
 int dk_engine_list_kernels(void* h, int list);

@@ -55,6 +55,10 @@ int dk_gemm_encode_output(void* tmap_d, const void* D, long ldd, int M, int N, i
 int dk_gemm_pick_splits(int M, int N, int K, int bn, int tf32);
 int dk_gemm_tn_ex(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M, int N,
                   int K, int flags, int bn, int splits, void* stream);
+int dk_gemm_pull_launch(const void* tmap_a, const void* tmap_b, const void* tmap_d, const DkGemmEpilogue* ep, int M,
+                        int N, int K, float* w_local, float* w1_local, void* wb_local, int ldw, void* stream);
+int dk_gemm_pull(const float* X, long ldx, const float* center_w, long ldc, const DkGemmEpilogue* ep, int M, int N, int K,
+                 float* w_local, float* w1_local, void* wb_local, void* stream);
 int dk_gemm_encode_operands(void* tmap_a, void* tmap_b, const void* A, long lda, const void* B, long ldb,
                             int M, int N, int K, int bn, int flags);
 int dk_gemm_tn(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M,

@@ -70,6 +70,217 @@ __device__ __forceinline__ void tma_load_2d_addr(uint32_t smem_dst, const void* 
       : "memory");
 }
 
+// Epilogue of one 128 x BN accumulator tile (called by the 4 epilogue warps); see the kernel comment.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue(const CUtensorMap& tmap_d, const CUtensorMap& tmap_m,
+                                              const GemmEpilogue& ep, const int M, const int N, const int m0,
+                                              const int n0, const int warp, const int lane, const uint32_t tmem_base,
+                                              uint8_t* smem, uint64_t* tmem_full_bar, uint64_t* mask_bar) {
+  const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
+  const int m = m0 + quarter * 32 + lane;        // output row owned by this thread
+  constexpr int kChunk = BN < 32 ? 16 : 32;
+  const bool tma_out = ep.tma_store != 0;
+  const int esize = ep.d_fp32 ? 4 : 2;
+  const int group_cols = 128 / esize;                        // columns per 128-byte staging row
+  // staging regions inside the (idle after the main loop) pipeline buffers
+  const uint32_t out_region = smem_u32(smem) + quarter * (32 * BN * esize);
+  const uint32_t mask_region = smem_u32(smem) + 4 * (32 * BN * esize) + quarter * (32 * BN * 2);
+  mbar_wait(tmem_full_bar, 0);
+  tcgen05_fence_after();
+  if (ep.tma_mask) {
+    // dReLU / dropout mask tile (bf16, same shape as the output) via TMA into swizzled smem
+    if (lane == 0) {
+      const int ngroups = (BN + 63) / 64;
+      mbar_expect_tx(&mask_bar[quarter], ngroups * 4096);
+      for (int g = 0; g < ngroups; ++g)
+        tma_load_2d_addr(mask_region + g * 4096, &tmap_m, n0 + g * 64, m0 + quarter * 32, &mask_bar[quarter]);
+    }
+    mbar_wait(&mask_bar[quarter], 0);
+  }
+  const bool row_ok = m < M;
+  const float bias_m = (ep.bias != nullptr && ep.bias_along_m && row_ok) ? ep.bias[m] : 0.f;
+  uint32_t drop_salt = 0, drop_thr = 0;
+  float keep_scale = 1.f;
+  if (ep.drop_p > 0.f) {
+    drop_salt = ep.drop_seed + (ep.step != nullptr ? static_cast<uint32_t>(*ep.step) : 0u) * 0x85EBCA77u;
+    drop_thr = static_cast<uint32_t>(ep.drop_p * 256.f + 0.5f);          // 8-bit resolution
+    keep_scale = 256.f / (256.f - static_cast<float>(drop_thr));
+  }
+#pragma unroll 1
+  for (int c = 0; c < BN; c += kChunk) {
+    const int nc = n0 + c;
+    if (nc >= N) break;  // warp-uniform
+    float v[kChunk];
+    {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c;
+      if constexpr (kChunk == 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      } else {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(taddr, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      }
+    }
+    const bool full_chunk = nc + kChunk <= N;
+    // ---- fused elementwise epilogue ----
+    if (ep.alpha != 1.f) {
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j) v[j] *= ep.alpha;
+    }
+    if (ep.bias != nullptr) {
+      if (ep.bias_along_m) {
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) v[j] += bias_m;
+      } else if (full_chunk && ((reinterpret_cast<uintptr_t>(ep.bias + nc) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < kChunk; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + j));
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j)
+          if (nc + j < N) v[j] += __ldg(ep.bias + nc + j);
+      }
+    }
+    if (ep.act == 1) {
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (ep.drop_p > 0.f) {
+      // inverted dropout (reference op K10): one counter-based hash per 4 elements, 8 bits each
+#pragma unroll
+      for (int j = 0; j < kChunk; j += 4) {
+        uint32_t h = (static_cast<uint32_t>(m) * static_cast<uint32_t>(N) + static_cast<uint32_t>(nc + j)) * 0x9E3779B1u ^ drop_salt;
+        h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          v[j + t] = (((h >> (8 * t)) & 0xFFu) < drop_thr) ? 0.f : v[j + t] * keep_scale;
+      }
+    }
+    if (ep.tma_mask) {
+      // chunk c covers 64 bytes of the 128-byte mask row: 16-byte pieces (c % 64) / 8 + 0..3
+      const int g = c >> 6, j0 = (c & 63) >> 3;
+#pragma unroll
+      for (int t = 0; t < kChunk / 8; ++t) {
+        const uint4 q = ld_shared_v4(mask_region + g * 4096 + sw128_off(lane, j0 + t));
+        const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (!(__bfloat162float(h[u]) > 0.f)) v[t * 8 + u] = 0.f;
+      }
+    } else if (ep.mask != nullptr && row_ok) {
+      const __nv_bfloat16* mrow = ep.mask + static_cast<size_t>(m) * ep.ld_mask + nc;
+      if (full_chunk && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < kChunk; j += 8) {
+          const uint4 q = *reinterpret_cast<const uint4*>(mrow + j);
+          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (!(__bfloat162float(h[t]) > 0.f)) v[j + t] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j)
+          if (nc + j < N && !(__bfloat162float(mrow[j]) > 0.f)) v[j] = 0.f;
+      }
+    }
+    if (tma_out) {
+      // ---- stage in swizzled smem, one TMA store per completed 128-byte column group ----
+      if (ep.d_fp32) {
+        const int g = c / 32;                      // kChunk == 32 here (host guarantees BN >= 32)
+#pragma unroll
+        for (int t = 0; t < kChunk / 4; ++t)
+          st_shared_v4(out_region + g * 4096 + sw128_off(lane, t), __float_as_uint(v[4 * t]),
+                       __float_as_uint(v[4 * t + 1]), __float_as_uint(v[4 * t + 2]), __float_as_uint(v[4 * t + 3]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (gridDim.z > 1 || ep.accumulate)
+            tma_reduce_add_2d(&tmap_d, out_region + g * 4096, nc, m0 + quarter * 32);
+          else
+            tma_store_2d_addr(&tmap_d, out_region + g * 4096, nc, m0 + quarter * 32);
+        }
+      } else {
+        const int g = c >> 6, j0 = (c & 63) >> 3;
+#pragma unroll
+        for (int t = 0; t < kChunk / 8; ++t)
+          st_shared_v4(out_region + g * 4096 + sw128_off(lane, j0 + t), pack_bf16x2(v[8 * t], v[8 * t + 1]),
+                       pack_bf16x2(v[8 * t + 2], v[8 * t + 3]), pack_bf16x2(v[8 * t + 4], v[8 * t + 5]),
+                       pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
+        const bool group_done = ((c & 63) + kChunk >= 64) || (nc + kChunk >= N) || (c + kChunk >= BN);
+        if (group_done) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_2d_addr(&tmap_d, out_region + g * 4096, n0 + g * 64, m0 + quarter * 32);
+        }
+      }
+      continue;
+    }
+    // ---- direct row-major store (small / unaligned outputs) ----
+    if (ep.d != nullptr && row_ok) {
+      if (ep.d_fp32) {
+        float* drow = reinterpret_cast<float*>(ep.d) + static_cast<size_t>(m) * ep.ldd + nc;
+        if (gridDim.z > 1) {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j)
+            if (nc + j < N) atomicAdd(drow + j, v[j]);
+        } else if (full_chunk && ((reinterpret_cast<uintptr_t>(drow) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < kChunk; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (ep.accumulate) {
+              const float4 p = *reinterpret_cast<const float4*>(drow + j);
+              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            }
+            *reinterpret_cast<float4*>(drow + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j)
+            if (nc + j < N) drow[j] = ep.accumulate ? drow[j] + v[j] : v[j];
+        }
+      } else {
+        __nv_bfloat16* drow =
+            reinterpret_cast<__nv_bfloat16*>(ep.d) + static_cast<size_t>(m) * ep.ldd + nc;
+        if (full_chunk && ((reinterpret_cast<uintptr_t>(drow) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < kChunk; j += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(v[j], v[j + 1]);
+            o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+            o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+            o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(drow + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j)
+            if (nc + j < N) drow[j] = __float2bfloat16_rn(v[j]);
+        }
+      }
+    }
+    // ---- transposed bf16 copy: DT[n][m]; lanes are consecutive m -> coalesced ----
+    if (ep.dt != nullptr && row_ok) {
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j)
+        if (nc + j < N)
+          ep.dt[static_cast<size_t>(nc + j) * ep.lddt + m] = __float2bfloat16_rn(v[j]);
+    }
+  }
+  if (tma_out && lane == 0) {
+    tma_store_commit();
+    tma_store_wait_read<0>();  // smem must stay valid until the TMA engine has read it
+  }
+}
+
 // AMN / BMN: the operand is MN-major in global memory, i.e. stored as [K, M] (resp. [K, N])
 // row-major with the M (N) index contiguous.  TMA then loads [64 K-rows x 64 MN-elements] boxes
 // (one 128-byte swizzle row per K index) and the UMMA descriptor walks K in 8-row atoms
@@ -204,209 +415,155 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
-    const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
-    const int m = m0 + quarter * 32 + lane;        // output row owned by this thread
-    constexpr int kChunk = BN < 32 ? 16 : 32;
-    const bool tma_out = ep.tma_store != 0;
-    const int esize = ep.d_fp32 ? 4 : 2;
-    const int group_cols = 128 / esize;                        // columns per 128-byte staging row
-    // staging regions inside the (idle after the main loop) pipeline buffers
-    const uint32_t out_region = smem_u32(smem) + quarter * (32 * BN * esize);
-    const uint32_t mask_region = smem_u32(smem) + 4 * (32 * BN * esize) + quarter * (32 * BN * 2);
-    mbar_wait(tmem_full_bar, 0);
+    gemm_epilogue<BN>(tmap_d, tmap_m, ep, M, N, m0, n0, warp, lane, tmem_base, smem, tmem_full_bar, mask_bar);
+    tcgen05_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
     tcgen05_fence_after();
-    if (ep.tma_mask) {
-      // dReLU / dropout mask tile (bf16, same shape as the output) via TMA into swizzled smem
-      if (lane == 0) {
-        const int ngroups = (BN + 63) / 64;
-        mbar_expect_tx(&mask_bar[quarter], ngroups * 4096);
-        for (int g = 0; g < ngroups; ++g)
-          tma_load_2d_addr(mask_region + g * 4096, &tmap_m, n0 + g * 64, m0 + quarter * 32, &mask_bar[quarter]);
-      }
-      mbar_wait(&mask_bar[quarter], 0);
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Pull fused into the first GEMM (reference op K2): the forward GEMM of the first layer
+// whose B operand -- the layer's weights -- is read by TMA **straight from the parameter server's
+// HBM** (the peer-mapped center variable, fp32, consumed as tf32 by tcgen05.mma).  The CTAs of the
+// first M-tile row also persist every landed weight tile: while the MMA consumes it from shared
+// memory, the otherwise idle epilogue warps copy it to the local fp32 master W, the W1 snapshot
+// and the bf16 shadow.  The weights cross NVLink exactly once per N-tile column group and the
+// transfer is hidden behind the tensor-core work of the same kernel; no separate pull pass, no
+// NCCL call and no host socket is involved.
+//   A = X  [M = batch, K = in]  fp32 (local)      B = C_w [N = out, K = in] fp32 (peer HBM)
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+gemm_pull_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_d, const GemmEpilogue ep, const int M, const int N,
+                 const int K, float* __restrict__ w_local, float* __restrict__ w1_local,
+                 __nv_bfloat16* __restrict__ wb_local, const int ldw) {
+  using S = GemmSmem<BN, STAGES, true>;
+  constexpr int kBlockK = 32, kUmmaK = 8;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kIdesc = make_idesc(2u, kBlockM, BN);
+  static_assert(BN == 128 || BN == 64, "persist mapping assumes 32 or 16 weight rows per epilogue warp");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* mask_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * kBlockM;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+  const bool persist = blockIdx.y == 0;  // one CTA per weight-tile column writes the local copies
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    if (ep.tma_store) tma_prefetch_desc(&tmap_d);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], persist ? 5 : 1);  // MMA commit (+ the 4 persisting warps)
     }
-    const bool row_ok = m < M;
-    const float bias_m = (ep.bias != nullptr && ep.bias_along_m && row_ok) ? ep.bias[m] : 0.f;
-    uint32_t drop_salt = 0, drop_thr = 0;
-    float keep_scale = 1.f;
-    if (ep.drop_p > 0.f) {
-      drop_salt = ep.drop_seed + (ep.step != nullptr ? static_cast<uint32_t>(*ep.step) : 0u) * 0x85EBCA77u;
-      drop_thr = static_cast<uint32_t>(ep.drop_p * 256.f + 0.5f);          // 8-bit resolution
-      keep_scale = 256.f / (256.f - static_cast<float>(drop_thr));
-    }
-#pragma unroll 1
-    for (int c = 0; c < BN; c += kChunk) {
-      const int nc = n0 + c;
-      if (nc >= N) break;  // warp-uniform
-      float v[kChunk];
-      {
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c;
-        if constexpr (kChunk == 32) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        } else {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(taddr, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    mbar_init(tmem_full_bar, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(&mask_bar[q], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  DK_PDL_WAIT();
+  DK_PDL_TRIGGER();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+        tma_load_2d(sa, &tmap_a, kb * kBlockK, m0, &full_bar[stage]);  // local activations
+        tma_load_2d(sb, &tmap_b, kb * kBlockK, n0, &full_bar[stage]);  // weights from the PS GPU over NVLink
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
-      }
-      const bool full_chunk = nc + kChunk <= N;
-      // ---- fused elementwise epilogue ----
-      if (ep.alpha != 1.f) {
-#pragma unroll
-        for (int j = 0; j < kChunk; ++j) v[j] *= ep.alpha;
-      }
-      if (ep.bias != nullptr) {
-        if (ep.bias_along_m) {
-#pragma unroll
-          for (int j = 0; j < kChunk; ++j) v[j] += bias_m;
-        } else if (full_chunk && ((reinterpret_cast<uintptr_t>(ep.bias + nc) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < kChunk; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < kChunk; ++j)
-            if (nc + j < N) v[j] += __ldg(ep.bias + nc + j);
-        }
-      }
-      if (ep.act == 1) {
-#pragma unroll
-        for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (ep.drop_p > 0.f) {
-        // inverted dropout (reference op K10): one counter-based hash per 4 elements, 8 bits each
-#pragma unroll
-        for (int j = 0; j < kChunk; j += 4) {
-          uint32_t h = (static_cast<uint32_t>(m) * static_cast<uint32_t>(N) + static_cast<uint32_t>(nc + j)) * 0x9E3779B1u ^ drop_salt;
-          h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            v[j + t] = (((h >> (8 * t)) & 0xFFu) < drop_thr) ? 0.f : v[j + t] * keep_scale;
-        }
-      }
-      if (ep.tma_mask) {
-        // chunk c covers 64 bytes of the 128-byte mask row: 16-byte pieces (c % 64) / 8 + 0..3
-        const int g = c >> 6, j0 = (c & 63) >> 3;
-#pragma unroll
-        for (int t = 0; t < kChunk / 8; ++t) {
-          const uint4 q = ld_shared_v4(mask_region + g * 4096 + sw128_off(lane, j0 + t));
-          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (!(__bfloat162float(h[u]) > 0.f)) v[t * 8 + u] = 0.f;
-        }
-      } else if (ep.mask != nullptr && row_ok) {
-        const __nv_bfloat16* mrow = ep.mask + static_cast<size_t>(m) * ep.ld_mask + nc;
-        if (full_chunk && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < kChunk; j += 8) {
-            const uint4 q = *reinterpret_cast<const uint4*>(mrow + j);
-            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-              if (!(__bfloat162float(h[t]) > 0.f)) v[j + t] = 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < kChunk; ++j)
-            if (nc + j < N && !(__bfloat162float(mrow[j]) > 0.f)) v[j] = 0.f;
-        }
-      }
-      if (tma_out) {
-        // ---- stage in swizzled smem, one TMA store per completed 128-byte column group ----
-        if (ep.d_fp32) {
-          const int g = c / 32;                      // kChunk == 32 here (host guarantees BN >= 32)
-#pragma unroll
-          for (int t = 0; t < kChunk / 4; ++t)
-            st_shared_v4(out_region + g * 4096 + sw128_off(lane, t), __float_as_uint(v[4 * t]),
-                         __float_as_uint(v[4 * t + 1]), __float_as_uint(v[4 * t + 2]), __float_as_uint(v[4 * t + 3]));
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (gridDim.z > 1 || ep.accumulate)
-              tma_reduce_add_2d(&tmap_d, out_region + g * 4096, nc, m0 + quarter * 32);
-            else
-              tma_store_2d_addr(&tmap_d, out_region + g * 4096, nc, m0 + quarter * 32);
-          }
-        } else {
-          const int g = c >> 6, j0 = (c & 63) >> 3;
-#pragma unroll
-          for (int t = 0; t < kChunk / 8; ++t)
-            st_shared_v4(out_region + g * 4096 + sw128_off(lane, j0 + t), pack_bf16x2(v[8 * t], v[8 * t + 1]),
-                         pack_bf16x2(v[8 * t + 2], v[8 * t + 3]), pack_bf16x2(v[8 * t + 4], v[8 * t + 5]),
-                         pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
-          const bool group_done = ((c & 63) + kChunk >= 64) || (nc + kChunk >= N) || (c + kChunk >= BN);
-          if (group_done) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) tma_store_2d_addr(&tmap_d, out_region + g * 4096, n0 + g * 64, m0 + quarter * 32);
-          }
-        }
-        continue;
-      }
-      // ---- direct row-major store (small / unaligned outputs) ----
-      if (ep.d != nullptr && row_ok) {
-        if (ep.d_fp32) {
-          float* drow = reinterpret_cast<float*>(ep.d) + static_cast<size_t>(m) * ep.ldd + nc;
-          if (gridDim.z > 1) {
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j)
-              if (nc + j < N) atomicAdd(drow + j, v[j]);
-          } else if (full_chunk && ((reinterpret_cast<uintptr_t>(drow) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < kChunk; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (ep.accumulate) {
-                const float4 p = *reinterpret_cast<const float4*>(drow + j);
-                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-              }
-              *reinterpret_cast<float4*>(drow + j) = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j)
-              if (nc + j < N) drow[j] = ep.accumulate ? drow[j] + v[j] : v[j];
-          }
-        } else {
-          __nv_bfloat16* drow =
-              reinterpret_cast<__nv_bfloat16*>(ep.d) + static_cast<size_t>(m) * ep.ldd + nc;
-          if (full_chunk && ((reinterpret_cast<uintptr_t>(drow) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < kChunk; j += 8) {
-              uint4 o;
-              o.x = pack_bf16x2(v[j], v[j + 1]);
-              o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-              o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(drow + j) = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j)
-              if (nc + j < N) drow[j] = __float2bfloat16_rn(v[j]);
-          }
-        }
-      }
-      // ---- transposed bf16 copy: DT[n][m]; lanes are consecutive m -> coalesced ----
-      if (ep.dt != nullptr && row_ok) {
-#pragma unroll
-        for (int j = 0; j < kChunk; ++j)
-          if (nc + j < N)
-            ep.dt[static_cast<size_t>(nc + j) * ep.lddt + m] = __float2bfloat16_rn(v[j]);
       }
     }
-    if (tma_out && lane == 0) {
-      tma_store_commit();
-      tma_store_wait_read<0>();  // smem must stay valid until the TMA engine has read it
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+        const uint32_t sb = sa + S::kABytes;
+        const uint64_t adesc = make_smem_desc_sw128(sa);
+        const uint64_t bdesc = make_smem_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
     }
+  } else {
+    if (persist) {
+      // ---- persist the pulled weight tiles while the tensor core consumes them ----
+      const int quarter = warp & 3;
+      constexpr int kRowsPerWarp = BN / 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t sb = smem_u32(smem + stage * S::kStageBytes) + S::kABytes;
+        const int k = kb * kBlockK + ((lane & 7) << 2);  // this lane's 4 consecutive K elements
+#pragma unroll
+        for (int it = 0; it < kRowsPerWarp / 4; ++it) {
+          const int r = quarter * kRowsPerWarp + it * 4 + (lane >> 3);  // weight row inside the tile
+          const int n = n0 + r;
+          const uint4 q = ld_shared_v4(sb + sw128_off(r, lane & 7));
+          if (n < N && k + 3 < K) {
+            const size_t off = static_cast<size_t>(n) * ldw + k;
+            *reinterpret_cast<uint4*>(w_local + off) = q;
+            *reinterpret_cast<uint4*>(w1_local + off) = q;
+            uint2 h;
+            h.x = pack_bf16x2(__uint_as_float(q.x), __uint_as_float(q.y));
+            h.y = pack_bf16x2(__uint_as_float(q.z), __uint_as_float(q.w));
+            *reinterpret_cast<uint2*>(wb_local + off) = h;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    gemm_epilogue<BN>(tmap_d, tmap_d, ep, M, N, m0, n0, warp, lane, tmem_base, smem, tmem_full_bar, mask_bar);
     tcgen05_fence_before();
   }
 
@@ -625,6 +782,46 @@ int dk_gemm_encode_operands(void* tmap_a, void* tmap_b, const void* A, long lda,
   if (r != 0) return r;
   return (flags & DK_GEMM_B_MN) ? dk_tmap_encode_2d(tmap_b, B, dt, K, N, ldb, 64)
                                 : dk_tmap_encode_2d(tmap_b, B, dt, N, K, ldb, bn);
+}
+
+
+// Fused pull + forward GEMM of the first layer (see gemm_pull_kernel).  `center_w` is the layer's
+// weight block inside the peer-mapped center variable; w / w1 / wb are the local copies to refresh.
+int dk_gemm_pull_launch(const void* tmap_a, const void* tmap_b, const void* tmap_d, const DkGemmEpilogue* ep_in, int M,
+                        int N, int K, float* w_local, float* w1_local, void* wb_local, int ldw, void* stream) {
+  using S = dk::GemmSmem<128, 3, true>;
+  auto kern = dk::gemm_pull_kernel<128, 3>;
+  static bool configured[64] = {};
+  int dev = 0;
+  DK_HOST_CHECK(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    DK_HOST_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured[dev & 63] = true;
+  }
+  dk::GemmEpilogue ep = *ep_in;
+  ep.tma_store = tmap_d != nullptr ? 1 : 0;
+  ep.tma_mask = 0;
+  ep.mask = nullptr;
+  const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(tmap_a);
+  const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(tmap_b);
+  const CUtensorMap& td = tmap_d != nullptr ? *reinterpret_cast<const CUtensorMap*>(tmap_d) : ta;
+  dim3 grid((N + 127) / 128, (M + dk::kBlockM - 1) / dk::kBlockM, 1);
+  DK_HOST_CHECK(DK_LAUNCH(kern, grid, dk::kGemmThreads, S::kTotal, stream, ta, tb, td, ep, M, N, K, w_local, w1_local,
+                          reinterpret_cast<__nv_bfloat16*>(wb_local), ldw));
+  return 0;
+}
+
+// one-shot variant (tests): encodes the tensor maps first
+int dk_gemm_pull(const float* X, long ldx, const float* center_w, long ldc, const DkGemmEpilogue* ep, int M, int N, int K,
+                 float* w_local, float* w1_local, void* wb_local, void* stream) {
+  alignas(64) CUtensorMap ta, tb, td;
+  int r = dk_tmap_encode_2d(&ta, X, DK_F32, M, K, ldx, dk::kBlockM);
+  if (r != 0) return r;
+  r = dk_tmap_encode_2d(&tb, center_w, DK_F32, N, K, ldc, 128);
+  if (r != 0) return r;
+  const bool has_d = ep->d != nullptr && dk_gemm_encode_output(&td, ep->d, ep->ldd, M, N, ep->d_fp32) == 0 &&
+                     (ep->d_fp32 || true);
+  return dk_gemm_pull_launch(&ta, &tb, has_d ? &td : nullptr, ep, M, N, K, w_local, w1_local, wb_local, (int)ldc, stream);
 }
 
 // Convenience one-shot entry: encodes the tensor maps, then launches (splits: 0 = auto for fp32

@@ -41,7 +41,7 @@ int dk_elementwise_loss(int kind, const float* out, const float* target, int B, 
 // input stage: x [B, F] (u8 / f32 / bf16) -> xb bf16 [B, ldx] (and optional xt bf16 [F, ldxt]),
 // y = x * scale + shift (fused MinMaxTransformer); also increments the device step counter.
 int dk_input_stage(const void* x, int in_dtype, int B, int F, float scale, float shift, void* xb,
-                   int ldx, void* xt, int ldxt, int* step_counter, void* stream);
+                   int ldx, void* xt, int ldxt, int* step_counter, void* xf, int ldxf, void* stream);
 
 // batched bf16 transposes: dst[c, r] = src[r, c] for a table of matrices
 int dk_transpose_bf16(const void* src, int rows, int cols, int lds, void* dst, int ldd, void* stream);

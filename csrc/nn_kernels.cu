@@ -55,7 +55,7 @@ input_stage_kernel(const T* __restrict__ x, int B, int F, float scale, float shi
 template <typename T>
 __global__ void __launch_bounds__(256)
 input_stage_vec_kernel(const T* __restrict__ x, long rows, int F, float scale, float shift,
-                       __nv_bfloat16* __restrict__ xb, int ldx, int* step_counter) {
+                       __nv_bfloat16* __restrict__ xb, int ldx, float* __restrict__ xf, int ldxf, int* step_counter) {
   DK_PDL_ENTER();
   const int f8 = F >> 3;  // F % 8 == 0 guaranteed by the launcher
   const long total = rows * f8;
@@ -86,6 +86,13 @@ input_stage_vec_kernel(const T* __restrict__ x, long rows, int F, float scale, f
     o.z = pack_bf16x2(v[4] * scale + shift, v[5] * scale + shift);
     o.w = pack_bf16x2(v[6] * scale + shift, v[7] * scale + shift);
     *reinterpret_cast<uint4*>(xb + r * ldx + c) = o;
+    if (xf != nullptr) {  // fp32 copy: A operand of the tf32 pull-fused first-layer GEMM
+      float* dst = xf + r * ldxf + c;
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0] * scale + shift, v[1] * scale + shift, v[2] * scale + shift,
+                                                    v[3] * scale + shift);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4] * scale + shift, v[5] * scale + shift,
+                                                        v[6] * scale + shift, v[7] * scale + shift);
+    }
   }
   if (step_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_counter += 1;
 }
@@ -455,12 +462,13 @@ using namespace dk;
 extern "C" {
 
 int dk_input_stage(const void* x, int in_dtype, int B, int F, float scale, float shift, void* xb,
-                   int ldx, void* xt, int ldxt, int* step_counter, void* stream) {
+                   int ldx, void* xt, int ldxt, int* step_counter, void* xf, int ldxf, void* stream) {
   dim3 grid((F + 31) / 32, (B + 31) / 32);
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* xbp = reinterpret_cast<__nv_bfloat16*>(xb);
   __nv_bfloat16* xtp = reinterpret_cast<__nv_bfloat16*>(xt);
   const int in_size = in_dtype == DK_IN_U8 ? 1 : (in_dtype == DK_IN_F32 ? 4 : 2);
+  if (xf != nullptr && !(xt == nullptr && xb != nullptr && F % 8 == 0 && ldx % 8 == 0 && ldxf % 4 == 0)) return -7;
   if (xt == nullptr && xb != nullptr && F % 8 == 0 && ldx % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(x) % (8 * in_size > 16 ? 16 : 8 * in_size)) == 0) {
     long total = static_cast<long>(B) * (F / 8);
@@ -469,13 +477,13 @@ int dk_input_stage(const void* x, int in_dtype, int B, int F, float scale, float
     const int g = static_cast<int>(blocks < 1 ? 1 : blocks);
     if (in_dtype == DK_IN_U8)
       DK_HOST_CHECK(DK_LAUNCH(input_stage_vec_kernel<uint8_t>, g, 256, 0, st, reinterpret_cast<const uint8_t*>(x), B, F, scale, shift,
-                                                         xbp, ldx, step_counter));
+                                                         xbp, ldx, reinterpret_cast<float*>(xf), ldxf, step_counter));
     else if (in_dtype == DK_IN_F32)
       DK_HOST_CHECK(DK_LAUNCH(input_stage_vec_kernel<float>, g, 256, 0, st, reinterpret_cast<const float*>(x), B, F, scale, shift, xbp,
-                                                       ldx, step_counter));
+                                                       ldx, reinterpret_cast<float*>(xf), ldxf, step_counter));
     else
       DK_HOST_CHECK(DK_LAUNCH(input_stage_vec_kernel<__nv_bfloat16>, g, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(x), B, F, scale,
-                                                               shift, xbp, ldx, step_counter));
+                                                               shift, xbp, ldx, reinterpret_cast<float*>(xf), ldxf, step_counter));
     DK_HOST_CHECK(cudaGetLastError());
     return 0;
   }

@@ -36,7 +36,7 @@ OP_INPUT, OP_GEMM, OP_XENT, OP_ROWSUM, OP_TRANSPOSE, OP_OPTIM, OP_IM2COL, OP_COL
 OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_RELU_MASK, OP_ADD, OP_MEMSET = 8, 9, 10, 11, 12
 OP_PS_COMMIT, OP_PS_PULL, OP_PS_EXCHANGE, OP_PS_ELASTIC, OP_PS_DAMPED, OP_PS_TICKET = 13, 14, 15, 16, 17, 18
 OP_LOCK_ACQUIRE, OP_LOCK_RELEASE, OP_EAMSGD_PRE, OP_EAMSGD_POST, OP_CAST, OP_ELOSS = 19, 20, 21, 22, 23, 24
-OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D, OP_FORK, OP_JOIN = 25, 26, 27, 28, 29, 30
+OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D, OP_FORK, OP_JOIN, OP_GEMM_PULL = 25, 26, 27, 28, 29, 30, 31
 GEMM_TF32, GEMM_A_MN, GEMM_B_MN = 1, 2, 4
 
 OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6}
@@ -73,7 +73,8 @@ _SIGNATURES = {
     "dk_cast_bf16": (i32, [vp, vp, i64, vp]),
     "dk_softmax_xent": (i32, [vp, i32, vp, vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, i32, vp]),
     "dk_elementwise_loss": (i32, [i32, vp, vp, i32, i32, vp, i32, vp, i32, vp, vp, i32, vp]),
-    "dk_input_stage": (i32, [vp, i32, i32, i32, f32, f32, vp, i32, vp, i32, vp, vp]),
+    "dk_input_stage": (i32, [vp, i32, i32, i32, f32, f32, vp, i32, vp, i32, vp, vp, i32, vp]),
+    "dk_gemm_pull": (i32, [vp, i64, vp, i64, C.POINTER(GemmEpilogue), i32, i32, i32, vp, vp, vp, vp]),
     "dk_transpose_bf16": (i32, [vp, i32, i32, i32, vp, i32, vp]),
     "dk_rowsum_bf16": (i32, [vp, i32, i32, i32, vp, f32, vp]),
     "dk_colsum_bf16": (i32, [vp, i32, i32, i32, vp, f32, vp]),
@@ -112,6 +113,7 @@ _SIGNATURES = {
     "dk_engine_set_slot": (i32, [vp, i32, vp]),
     "dk_engine_add_op": (i32, [vp, i32, i32, C.POINTER(C.c_int64), i32, C.POINTER(f64), i32]),
     "dk_engine_add_gemm": (i32, [vp, i32, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, C.POINTER(GemmEpilogue)]),
+    "dk_engine_add_gemm_pull": (i32, [vp, i32, vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, C.POINTER(GemmEpilogue)]),
     "dk_engine_run": (i32, [vp, i32, vp]),
     "dk_engine_list_size": (i32, [vp, i32]),
     "dk_engine_list_kernels": (i32, [vp, i32]),

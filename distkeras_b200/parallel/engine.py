@@ -113,7 +113,8 @@ class NativeReplica(Replica):
 
     def __init__(self, model: Sequential, optimizer, loss: str, batch_size: int, device_index: int = 0,
                  in_dtype: str = "u8", input_affine: Tuple[float, float] = (1.0, 0.0), hist_slots: int = 1024,
-                 dense_labels: bool = False, seed: int = 1234, training: bool = True):
+                 dense_labels: bool = False, seed: int = 1234, training: bool = True,
+                 pull_center_ptr: int = 0):
         self.lib = N.lib()
         model.build()
         self.model = model
@@ -149,14 +150,22 @@ class NativeReplica(Replica):
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.hist = torch.zeros(self.hist_slots, 2, dtype=torch.float32, device=dev)
         self.training = training
+        self.pull_center_ptr = int(pull_center_ptr) if training else 0
+        self.W1 = None
         if training:
             self.G = torch.zeros(P, dtype=torch.float32, device=dev)
             self.opt = FlatOptimizer(optimizer, P, dev)
-            self.W1 = None
+            if self.pull_center_ptr:
+                self.W1 = self.W.clone()
         self._keep: list = []  # buffers referenced only by raw pointers
         self.engine = self.lib.dk_engine_create()
+        # L_step: training forward; L_bwd: loss + backward + optimizer; L_fwd: inference forward;
+        # L_step_pull: training forward whose first GEMM pulls its weights from the PS (fused pull)
         self.L_step = self.lib.dk_engine_new_list(self.engine) if training else -1
+        self.L_bwd = self.lib.dk_engine_new_list(self.engine) if training else -1
         self.L_fwd = self.lib.dk_engine_new_list(self.engine)
+        self.L_step_pull = -1
+        self.pull_segment = None
         self._input_feats = int(np.prod(model.input_shape))
         self._lower()
         self.refresh_shadow()
@@ -208,11 +217,17 @@ class NativeReplica(Replica):
         cur = dict(t=x0, rows=B, cols=F, ld=_r8(F), nhwc=in_shape if len(in_shape) == 3 else None)
         if cur["nhwc"] is not None and F % 8 != 0 and False:
             pass
-        lists = [l for l in (self.L_step, self.L_fwd) if l >= 0]
+        first = self.blocks[0]
+        if self.pull_center_ptr and first.kind == "dense" and first.k_in % 8 == 0 and F % 8 == 0:
+            self.L_step_pull = self.lib.dk_engine_new_list(self.engine)
+            x0f = self._buf(B, F, dtype=torch.float32)
+        lists = [l for l in (self.L_step, self.L_fwd, self.L_step_pull) if l >= 0]
+        train_lists = (self.L_step, self.L_step_pull)
         for lst in lists:
             self._add(lst, N.OP_INPUT,
                       [-(SLOT_X + 1), self.in_dtype, B, F, x0.data_ptr(), cur["ld"], 0, 0,
-                       self.step_counter.data_ptr() if lst == self.L_step else 0],
+                       self.step_counter.data_ptr() if lst in train_lists else 0,
+                       x0f.data_ptr() if lst == self.L_step_pull else 0, F],
                       [self.scale, self.shift])
         # padded weight shadows are refreshed at the top of every program
         self._pad_refresh: list = []
@@ -263,10 +278,23 @@ class NativeReplica(Replica):
                     ep.act = 1 if b.act == "relu" else 0
                     ep.d, ep.ldd, ep.d_fp32 = out.data_ptr(), rec["ld"], 1 if is_last else 0
                     ep.alpha = 1.0
-                    if lst == self.L_step and b.drop_p > 0:
+                    if lst in train_lists and b.drop_p > 0:
                         ep.drop_p = b.drop_p
                         ep.drop_seed = (self.seed * 7919 + bi * 104729) & 0xFFFFFFFF
                         ep.step = self.step_counter.data_ptr()
+                    if lst == self.L_step_pull and bi == 0:
+                        # pull fused into the first GEMM: B operand = this layer's block of the center
+                        # variable in the PS GPU's HBM; the kernel refreshes W / W1 / Wb on the way
+                        off = kseg.offset
+                        self.pull_segment = (off, kseg.size)
+                        r = self.lib.dk_engine_add_gemm_pull(
+                            self.engine, lst, C.c_void_p(x0f.data_ptr()), F, C.c_void_p(self.pull_center_ptr + 4 * off),
+                            K, rows, Nout, K, C.c_void_p(self.W.data_ptr() + 4 * off),
+                            C.c_void_p(self.W1.data_ptr() + 4 * off), C.c_void_p(self.Wb.data_ptr() + 2 * off),
+                            C.byref(ep))
+                        if r < 0:
+                            raise RuntimeError(f"dk_engine_add_gemm_pull failed: {r}")
+                        continue
                     self._gemm(lst, a_in["t"].data_ptr(), a_in["ld"], b.wb_ptr, b.wb_ld, rows, Nout, K, 0, ep)
                 b.out = rec
                 cur = rec
@@ -298,7 +326,7 @@ class NativeReplica(Replica):
         self._prepend_pad_refresh(self.L_fwd)
         if not self.training:
             return
-        lst = self.L_step
+        lst = self.L_bwd
         # ---- loss ----
         ldz = _r8(Cn)
         dz = self._buf(B, ldz)
@@ -380,6 +408,14 @@ class NativeReplica(Replica):
                   [o.lr, o.p0, o.p1, o.eps, o.decay, 1.0])
         self._prepend_pad_refresh(lst)
 
+    def pull_rest_ranges(self):
+        """Flat ranges NOT covered by the fused-pull GEMM (pulled by the plain pull kernel)."""
+        if self.pull_segment is None:
+            return [(0, self.P)]
+        off, size = self.pull_segment
+        size8 = (size + 7) // 8 * 8
+        return [(lo, hi) for lo, hi in ((0, off), (off + size8, self.P)) if hi > lo]
+
     def _prepend_pad_refresh(self, lst: int) -> None:
         # pad refresh ops are appended; order inside a list only matters relative to the GEMMs that
         # read the padded shadows, so they live in a dedicated list run before `lst`.
@@ -405,13 +441,21 @@ class NativeReplica(Replica):
 
     weights_changed = refresh_shadow
 
-    def enqueue_step(self, x_ptr: int, y_ptr: int) -> None:
-        """Enqueue one training step reading its batch from device pointers (graph-capturable)."""
+    def enqueue_step(self, x_ptr: int, y_ptr: int, fused_pull: bool = False) -> None:
+        """Enqueue one training step reading its batch from device pointers (graph-capturable).
+        With ``fused_pull`` the first layer's weights are pulled from the parameter server inside
+        its forward GEMM (the caller pulls every other segment beforehand)."""
         self.lib.dk_engine_set_slot(self.engine, SLOT_X, C.c_void_p(x_ptr))
         self.lib.dk_engine_set_slot(self.engine, SLOT_Y, C.c_void_p(y_ptr))
         if hasattr(self, "L_pad"):
             self._run(self.L_pad)
-        self._run(self.L_step)
+        if fused_pull:
+            if self.L_step_pull < 0:
+                raise RuntimeError("the replica was not planned with pull_center_ptr")
+            self._run(self.L_step_pull)
+        else:
+            self._run(self.L_step)
+        self._run(self.L_bwd)
 
     def enqueue_forward(self, x_ptr: int) -> None:
         self.lib.dk_engine_set_slot(self.engine, SLOT_X, C.c_void_p(x_ptr))
@@ -420,8 +464,8 @@ class NativeReplica(Replica):
         self._run(self.L_fwd)
 
     def step_kernel_count(self) -> int:
-        n = self.lib.dk_engine_list_kernels(self.engine, self.L_step)
-        return n
+        return (self.lib.dk_engine_list_kernels(self.engine, self.L_step)
+                + self.lib.dk_engine_list_kernels(self.engine, self.L_bwd))
 
     def launches(self) -> int:
         return int(self.lib.dk_engine_launches(self.engine))

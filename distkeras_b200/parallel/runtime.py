@@ -60,9 +60,19 @@ class FabricWorker:
         self.comm = "commit_pull" if strict else comm
         self.strict = strict
         self.device_index = device_index
+        # Fused pull: every M-tile row of the first GEMM fetches the weight tiles itself (peer memory
+        # bypasses the local L2), so it pays off while the batch spans few 128-row tiles; larger
+        # batches use the fused exchange kernel (cluster-multicast of the weight tile is the next step).
+        self.fused_pull = (comm == "fused_pull" and not strict and self.alg["kind"] in ("adag", "dynsgd")
+                           and int(batch_size) <= 512)
         self.rep = NativeReplica(model, optimizer, loss, batch_size, device_index, in_dtype=in_dtype,
                                  input_affine=input_affine, hist_slots=2 * self.tau, dense_labels=dense_labels,
-                                 seed=seed + 7 * worker_id)
+                                 seed=seed + 7 * worker_id,
+                                 pull_center_ptr=region.center_ptr if self.fused_pull else 0)
+        if self.fused_pull and self.rep.L_step_pull < 0:
+            self.fused_pull = False
+        if comm == "fused_pull" and not self.fused_pull:
+            self.comm = "exchange"
         rep = self.rep
         dev = rep.device
         self.lib = rep.lib
@@ -114,7 +124,10 @@ class FabricWorker:
             if k == "dynsgd":
                 N.check(lib.dk_ps_ticket(ctrl, self.last_update.data_ptr(), self.scale_dev.data_ptr(), st), "ticket")
                 sdev = self.scale_dev.data_ptr()
-            if self.comm == "exchange":
+            if self.fused_pull:
+                # commit only: the pull happens inside the next window's first forward GEMM
+                N.check(lib.dk_ps_commit(c, W, W1, rep.P, scale, sdev, ctrl, self.worker_id, it, st), "commit")
+            elif self.comm == "exchange":
                 N.check(lib.dk_ps_exchange(c, W, W1, Wb, rep.P, scale, sdev, ctrl, self.worker_id, it,
                                            self.last_update.data_ptr(), st), "exchange")
             else:
@@ -133,6 +146,8 @@ class FabricWorker:
 
     def comm_kernels(self) -> int:
         k = self.alg["kind"]
+        if self.fused_pull:
+            return 1 + len(self.rep.pull_rest_ranges()) + (1 if k == "dynsgd" else 0)
         n = 1 if (self.comm == "exchange" or k in ("aeasgd", "eamsgd", "experimental")) else 2
         if k == "dynsgd":
             n += 1
@@ -140,7 +155,16 @@ class FabricWorker:
             n += 2
         return n
 
-    def _step(self, parity: int, j: int) -> None:
+    def _pull_rest(self) -> None:
+        """Pull every segment the fused-pull GEMM does not cover (biases, later layers)."""
+        rep, reg = self.rep, self.region
+        for lo, hi in rep.pull_rest_ranges():
+            N.check(self.lib.dk_ps_pull(C.c_void_p(reg.center_ptr + 4 * lo), rep.W.data_ptr() + 4 * lo,
+                                        rep.W1.data_ptr() + 4 * lo, rep.Wb.data_ptr() + 2 * lo, hi - lo,
+                                        C.c_void_p(reg.ctrl_ptr), self.last_update.data_ptr(), self._stream()),
+                    "pull_rest")
+
+    def _step(self, parity: int, j: int, fused_pull: bool = False) -> None:
         rep = self.rep
         xs, ys = self.x_stage[parity], self.y_stage[parity]
         x_ptr = xs.data_ptr() + j * self.B * self.F * xs.element_size()
@@ -149,7 +173,7 @@ class FabricWorker:
             N.check(self.lib.dk_eamsgd_pre(rep.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(),
                                            rep.Wb.data_ptr(), rep.P, float(self.alg["momentum"]), self._stream()),
                     "eamsgd_pre")
-        rep.enqueue_step(x_ptr, y_ptr)
+        rep.enqueue_step(x_ptr, y_ptr, fused_pull=fused_pull)
         if self.alg["kind"] == "eamsgd":
             N.check(self.lib.dk_eamsgd_post(rep.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(),
                                             rep.Wb.data_ptr(), rep.P, float(self.alg["eta"]), self._stream()),
@@ -161,10 +185,12 @@ class FabricWorker:
         half = rep.hist[parity * self.tau:(parity + 1) * self.tau]
         half.zero_()
         pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd")  # check happens before the batch
+        if self.fused_pull:
+            self._pull_rest()
         for j in range(self.tau):
             if pre_batch and j == self.tau - 1:
                 self._comm_ops()
-            self._step(parity, j)
+            self._step(parity, j, fused_pull=self.fused_pull and j == 0)
         if not pre_batch:
             self._comm_ops()
         self.hist_host[parity].copy_(half, non_blocking=True)

@@ -115,7 +115,7 @@ def test_input_stage_and_colsum(N):
     xb = torch.zeros(B, ld, dtype=torch.bfloat16, device="cuda")
     cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     N.check(N.lib().dk_input_stage(x.data_ptr(), N.IN_U8, B, Fdim, 1 / 255.0, -0.5, xb.data_ptr(), ld, None, 0,
-                                   cnt.data_ptr(), st()))
+                                   cnt.data_ptr(), None, 0, st()))
     assert int(cnt) == 1
     assert torch.allclose(xb[:, :Fdim].float(), x.float() / 255.0 - 0.5, atol=4e-3)
     assert float(xb[:, Fdim:].abs().max()) == 0.0
@@ -235,3 +235,25 @@ def test_label_index_kernel(N):
     want = LabelIndexTransformer(10).indices(p.cpu())
     assert torch.equal(idx.cpu().long(), want)
     assert int(cnt) == int((want == labels.cpu().long()).sum())
+
+
+def test_gemm_pull_fused_kernel(N):
+    """First-layer forward with the weight pull fused in: B operand read by TMA from the (here:
+    same-device) center buffer as tf32, local W / W1 / bf16 shadow refreshed by the kernel."""
+    torch.manual_seed(11)
+    B, K, Nout = 256, 784, 1000
+    x = torch.rand(B, K, device="cuda")
+    center = torch.randn(Nout, K, device="cuda") * 0.05
+    bias = torch.randn(Nout, device="cuda")
+    w = torch.zeros(Nout, K, device="cuda")
+    w1 = torch.zeros_like(w)
+    wb = torch.zeros(Nout, K, dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros(B, Nout, dtype=torch.bfloat16, device="cuda")
+    ep = N.GemmEpilogue()
+    ep.bias, ep.act, ep.d, ep.ldd, ep.alpha = bias.data_ptr(), 1, out.data_ptr(), Nout, 1.0
+    N.check(N.lib().dk_gemm_pull(x.data_ptr(), K, center.data_ptr(), K, C.byref(ep), B, Nout, K, w.data_ptr(),
+                                 w1.data_ptr(), wb.data_ptr(), st()))
+    torch.cuda.synchronize()
+    assert torch.equal(w, center) and torch.equal(w1, center) and torch.equal(wb, center.to(torch.bfloat16))
+    ref = torch.relu(x @ center.t() + bias)
+    assert torch.allclose(out.float(), ref, atol=0.06, rtol=2e-2)
