@@ -149,7 +149,7 @@ def main() -> None:
         dist = runtime._init_pg()
     exchange_obj, barrier = runtime._dist_helpers(dist) if dist else ((lambda o, s: o), (lambda: None))
 
-    defaults = {"mnist_mlp": (4096, (784,)), "cifar10_cnn": (256, (32, 32, 3)), "mnist_convnet": (256, (28, 28, 1)),
+    defaults = {"mnist_mlp": (16384, (784,)), "cifar10_cnn": (256, (32, 32, 3)), "mnist_convnet": (256, (28, 28, 1)),
                 "higgs_mlp": (4096, (30,))}
     B = args.batch or defaults[args.model][0]
     in_shape = defaults[args.model][1]

@@ -6,6 +6,7 @@
 // This replaces the reference's per-batch Python hot loop (distkeras/workers.py:327-342:
 // train_on_batch -> get_weights -> numpy -> pickle -> socket) with a replayable device program.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -266,6 +267,19 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
   op.kind = DK_OP_GEMM;
   op.stream_id = e->build_stream;
   const bool splitk_ok = ep->d_fp32 && ep->bias == nullptr && ep->act == 0 && ep->mask == nullptr;
+  // bf16-output GEMMs of the forward / dgrad chain run on the persistent kernel (double-buffered
+  // TMEM accumulator, epilogue overlapped with the next tile); DK_PERSISTENT=0 disables it
+  static int persistent_env = -1;
+  if (persistent_env < 0) {
+    const char* pe = getenv("DK_PERSISTENT");
+    persistent_env = (pe != nullptr && pe[0] == '0') ? 0 : 1;
+  }
+  if (bn <= 0 && persistent_env && !ep->d_fp32 && ep->d != nullptr && ep->dt == nullptr && !ep->bias_along_m &&
+      !(flags & (DK_GEMM_A_MN | DK_GEMM_TF32)) && N > 64 && (ep->ldd % 8) == 0 &&
+      (ep->mask == nullptr || (ep->ld_mask % 8) == 0)) {
+    bn = N > 128 ? 256 : 128;
+    flags |= DK_GEMM_PERSISTENT;
+  }
   if (bn <= 0) bn = (splits == 0 && splitk_ok) ? dk_gemm_pick_bn_splitk(M, N, K) : dk_gemm_pick_bn2(M, N);
   if ((flags & DK_GEMM_B_MN) && bn < 64) bn = 64;
   int r = dk_gemm_encode_operands(&op.ta, &op.tb, A, lda, B, ldb, M, N, K, bn, flags);

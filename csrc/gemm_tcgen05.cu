@@ -642,6 +642,295 @@ static int launch_gemm(const GemmLaunch& L) {
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant for the bf16-output GEMMs of the forward / dgrad chain (short K, epilogue
+// heavy): one CTA per SM loops over output tiles; the fp32 accumulator is DOUBLE-BUFFERED in TMEM
+// (2 x BN columns) so the epilogue warps drain tile i (tcgen05.ld -> bias / ReLU / dropout / mask
+// -> swizzled smem slice -> TMA store, 64 columns at a time through a two-slot staging ring)
+// while the MMA warp already accumulates tile i+1 and the TMA producer prefetches its operands.
+// A is K-major; B is K-major (forward) or MN-major (dgrad).  256-wide tiles raise the arithmetic
+// intensity against L2 to 85 FLOP/B.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct PersistentSmem {
+  static constexpr int kABytes = kBlockM * 128;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutStage = 4 * 2 * 4096;   // 4 warps x 2 slots x (32 rows x 128 B)
+  static constexpr int kMaskStage = 4 * 2 * 4096;
+  static constexpr int kBarrierBytes = 512;
+  static constexpr int kTotal = STAGES * kStageBytes + kOutStage + kMaskStage + kBarrierBytes + 1024;
+};
+
+template <int BN, int STAGES, bool BMN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
+                       const GemmEpilogue ep, const int M, const int N, const int K) {
+  using S = PersistentSmem<BN, STAGES>;
+  constexpr int kBlockK = 64, kUmmaK = 16;
+  constexpr uint32_t kTmemCols = 2 * BN;  // two accumulators
+  constexpr uint32_t kIdesc = make_idesc(1u, kBlockM, BN) | (BMN ? (1u << 16) : 0u);
+  static_assert(BN == 128 || BN == 256, "persistent kernel: BN in {128, 256}");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* out_stage = smem + STAGES * S::kStageBytes;
+  uint8_t* mask_stage = out_stage + S::kOutStage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(mask_stage + S::kMaskStage);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint64_t* mask_bar = tmem_empty_bar + 2;        // [4 warps][2 slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int m_tiles = (M + kBlockM - 1) / kBlockM;
+  const int num_tiles = n_tiles * m_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_d);
+    if (ep.tma_mask) tma_prefetch_desc(&tmap_m);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);  // one arrival per epilogue warp
+    }
+    for (int i = 0; i < 8; ++i) mbar_init(&mask_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  DK_PDL_WAIT();
+  DK_PDL_TRIGGER();
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          tma_load_2d(sa, &tmap_a, kb * kBlockK, m0, &full_bar[stage]);
+          if constexpr (BMN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * 8192, &tmap_b, n0 + c * 64, kb * kBlockK, &full_bar[stage]);
+          } else {
+            tma_load_2d(sb, &tmap_b, kb * kBlockK, n0, &full_bar[stage]);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      tcgen05_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = BMN ? make_smem_desc_sw128_mn(sb) : make_smem_desc_sw128(sb);
+          constexpr uint32_t kBStep = BMN ? (2048 >> 4) : 2;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_f16(tmem_acc, adesc + 2 * k, bdesc + kBStep * k, kIdesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ----------------------------------
+    const int quarter = warp & 3;
+    const uint32_t out_region = smem_u32(out_stage) + quarter * 8192;    // 2 slots x 4 KB
+    const uint32_t mask_region = smem_u32(mask_stage) + quarter * 8192;
+    uint64_t* my_mask_bar = mask_bar + quarter * 2;
+    uint32_t mask_phase[2] = {0, 0};
+    uint32_t drop_salt = 0, drop_thr = 0;
+    float keep_scale = 1.f;
+    if (ep.drop_p > 0.f) {
+      drop_salt = ep.drop_seed + (ep.step != nullptr ? static_cast<uint32_t>(*ep.step) : 0u) * 0x85EBCA77u;
+      drop_thr = static_cast<uint32_t>(ep.drop_p * 256.f + 0.5f);
+      keep_scale = 256.f / (256.f - static_cast<float>(drop_thr));
+    }
+    constexpr int kSlices = BN / 64;
+    int it = 0;
+    int slot = 0;  // staging ring position (persists across tiles)
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * BN;
+      const int acc = it & 1;
+      const int m = m0 + quarter * 32 + lane;
+      const int valid_slices = min(kSlices, (N - n0 + 63) / 64);
+      // prefetch the first mask slice of this tile while the MMAs may still be running
+      if (ep.tma_mask && lane == 0 && valid_slices > 0) {
+        mbar_expect_tx(&my_mask_bar[slot], 4096);
+        tma_load_2d_addr(mask_region + slot * 4096, &tmap_m, n0, m0 + quarter * 32, &my_mask_bar[slot]);
+      }
+      mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int sl = 0; sl < valid_slices; ++sl) {
+        const int nc = n0 + sl * 64;
+        const int cur = slot;
+        const int nxt = slot ^ 1;
+        if (ep.tma_mask && lane == 0 && sl + 1 < valid_slices) {
+          mbar_expect_tx(&my_mask_bar[nxt], 4096);
+          tma_load_2d_addr(mask_region + nxt * 4096, &tmap_m, nc + 64, m0 + quarter * 32, &my_mask_bar[nxt]);
+        }
+        float v[64];
+        {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + sl * 64;
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(taddr, r0);
+          tmem_ld_32x32b_x32(taddr + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = __uint_as_float(r0[j]);
+            v[32 + j] = __uint_as_float(r1[j]);
+          }
+        }
+        if (sl == valid_slices - 1) {
+          // accumulator fully read: hand it back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (ep.alpha != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] *= ep.alpha;
+        }
+        if (ep.bias != nullptr) {
+          if (nc + 64 <= N && ((reinterpret_cast<uintptr_t>(ep.bias + nc) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (nc + j < N) v[j] += __ldg(ep.bias + nc + j);
+          }
+        }
+        if (ep.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (ep.drop_p > 0.f) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            uint32_t h = (static_cast<uint32_t>(m) * static_cast<uint32_t>(N) + static_cast<uint32_t>(nc + j)) * 0x9E3779B1u ^ drop_salt;
+            h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              v[j + t] = (((h >> (8 * t)) & 0xFFu) < drop_thr) ? 0.f : v[j + t] * keep_scale;
+          }
+        }
+        if (ep.tma_mask) {
+          mbar_wait(&my_mask_bar[cur], mask_phase[cur]);
+          mask_phase[cur] ^= 1;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const uint4 q = ld_shared_v4(mask_region + cur * 4096 + sw128_off(lane, t));
+            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (!(__bfloat162float(h[u]) > 0.f)) v[t * 8 + u] = 0.f;
+          }
+        }
+        // staging slot `cur` was last used two slices ago: its TMA store must have finished reading
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          st_shared_v4(out_region + cur * 4096 + sw128_off(lane, t), pack_bf16x2(v[8 * t], v[8 * t + 1]),
+                       pack_bf16x2(v[8 * t + 2], v[8 * t + 3]), pack_bf16x2(v[8 * t + 4], v[8 * t + 5]),
+                       pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d_addr(&tmap_d, out_region + cur * 4096, nc, m0 + quarter * 32);
+          tma_store_commit();
+        }
+        slot ^= 1;
+      }
+    }
+    if (lane == 0) tma_store_wait_read<0>();
+    tcgen05_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, int STAGES, bool BMN>
+static int launch_persistent(const GemmLaunch& L) {
+  using S = PersistentSmem<BN, STAGES>;
+  auto kern = gemm_persistent_kernel<BN, STAGES, BMN>;
+  static bool configured[64] = {};
+  static int sm_count[64] = {};
+  int dev = 0;
+  DK_HOST_CHECK(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    DK_HOST_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    DK_HOST_CHECK(cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    configured[dev & 63] = true;
+  }
+  GemmEpilogue ep = L.ep;
+  ep.tma_store = 1;
+  ep.tma_mask = L.tm != nullptr ? 1 : 0;
+  const int tiles = ((L.M + kBlockM - 1) / kBlockM) * ((L.N + BN - 1) / BN);
+  const int grid = tiles < sm_count[dev & 63] ? tiles : sm_count[dev & 63];
+  DK_HOST_CHECK(DK_LAUNCH(kern, grid, kGemmThreads, S::kTotal, L.stream, *L.ta, *L.tb, *L.td,
+                          ep.tma_mask ? *L.tm : *L.ta, ep, L.M, L.N, L.K));
+  return 0;
+}
+
 }  // namespace dk
 
 extern "C" {
@@ -706,6 +995,11 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
   L.stream = reinterpret_cast<cudaStream_t>(stream);
   if (M <= 0 || N <= 0 || K <= 0) return -3;
   const bool tf32 = flags & DK_GEMM_TF32, amn = flags & DK_GEMM_A_MN, bmn = flags & DK_GEMM_B_MN;
+  if ((flags & DK_GEMM_PERSISTENT) && !tf32 && !amn && L.td != nullptr && !ep->d_fp32 && ep->dt == nullptr &&
+      splits <= 1 && (ep->mask == nullptr || L.tm != nullptr) && !ep->bias_along_m) {
+    if (bn == 256) return bmn ? dk::launch_persistent<256, 3, true>(L) : dk::launch_persistent<256, 3, false>(L);
+    if (bn == 128) return bmn ? dk::launch_persistent<128, 4, true>(L) : dk::launch_persistent<128, 4, false>(L);
+  }
   if (tf32) {
     if (amn || bmn) return -5;
     switch (bn) {

@@ -692,16 +692,38 @@ def train_averaging_native(trainer, dataset: Dataset):
     master = deserialize_keras_model(trainer.master_model)
     history: List[dict] = []
     lib = N.lib()
+    import threading
+
     for epoch in range(trainer.num_epoch):
-        flats = []
-        for w in range(W):
-            dev = w % ndev
-            torch.cuda.set_device(dev)
-            m, h = _sequential_native(trainer, parts[w], master.copy(), dev, w, 1)
-            for rec in h:
-                rec["epoch"] = epoch
+        flats: List[Optional[torch.Tensor]] = [None] * W
+        hists: List[list] = [[] for _ in range(W)]
+        errors: list = []
+
+        def run(w: int) -> None:
+            try:
+                dev = w % ndev
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+                    m, h = _sequential_native(trainer, parts[w], master.copy(), dev, w, 1)
+                    flats[w] = m.get_flat_weights().to(f"cuda:{dev}").contiguous()
+                    torch.cuda.current_stream().synchronize()
+                for rec in h:
+                    rec["epoch"] = epoch
+                hists[w] = h
+            except BaseException as exc:
+                errors.append(exc)
+
+        # one host thread per replica: launches are asynchronous, so the W replicas train
+        # concurrently (one per GPU when W <= #GPUs)
+        threads = [threading.Thread(target=run, args=(w,), daemon=True) for w in range(W)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        for h in hists:
             history += h
-            flats.append(m.get_flat_weights().to(f"cuda:{dev}").contiguous())
         distinct = sorted({f.device.index for f in flats})
         if len(distinct) == W and W <= 16 and all(
                 a == b or lib.dk_can_access_peer(a, b) for a in distinct for b in distinct):
@@ -725,6 +747,48 @@ def train_averaging_native(trainer, dataset: Dataset):
         master.set_flat_weights(mean)
         trainer.master_model = serialize_keras_model(master)
     return master, history
+
+
+def train_ensemble_native(trainer, dataset: Dataset):
+    """``EnsembleTrainer``: independent replicas, one host thread + GPU each, native engine."""
+    import threading
+
+    ndev = torch.cuda.device_count()
+    E = trainer.num_ensembles
+    parts = dataset.repartition(E).partitions(E)
+    master = deserialize_keras_model(trainer.master_model)
+    models: List[Optional[object]] = [None] * E
+    hists: List[list] = [[] for _ in range(E)]
+    errors: list = []
+
+    def run(i: int) -> None:
+        try:
+            dev = i % ndev
+            torch.cuda.set_device(dev)
+            m = master.copy()
+            m.seed = (master.seed or 0) + 1 + i
+            from ..utils import uniform_weights  # noqa: F401  (ensembles differ by data shard + dropout stream)
+
+            with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+                try:
+                    models[i], hists[i] = _sequential_native(trainer, parts[i], m, dev, i, trainer.num_epoch)
+                except UnsupportedByNativeEngine:
+                    from ..trainers import _run_tasks
+
+                    res, ws = _run_tasks(trainer.allocate_worker(), [parts[i]], 1, lambda tid: f"cuda:{dev}")
+                    models[i], hists[i] = deserialize_keras_model(res[0][0]), ws[0].training_history
+                torch.cuda.current_stream().synchronize()
+        except BaseException as exc:
+            errors.append(exc)
+
+    threads = [threading.Thread(target=run, args=(i,), daemon=True) for i in range(E)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return models, [h for hs in hists for h in hs]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -54,8 +54,8 @@ def _run_tasks(worker_proto, partitions: List[Partition], num_threads: int, devi
     over-partitioning straggler mitigation, ``trainers.py:624-629``).  Each task gets its own copy
     of the worker, exactly like a pickled Spark closure."""
     tasks: "queue.Queue" = queue.Queue()
-    for p in partitions:
-        tasks.put(p)
+    for pos, p in enumerate(partitions):
+        tasks.put((pos, p))
     results: List[Optional[list]] = [None] * len(partitions)
     workers_out: List[Optional[object]] = [None] * len(partitions)
     errors: List[BaseException] = []
@@ -64,7 +64,7 @@ def _run_tasks(worker_proto, partitions: List[Partition], num_threads: int, devi
     def loop(tid: int):
         while True:
             try:
-                part = tasks.get_nowait()
+                pos, part = tasks.get_nowait()
             except queue.Empty:
                 return
             try:
@@ -73,17 +73,17 @@ def _run_tasks(worker_proto, partitions: List[Partition], num_threads: int, devi
                 w.iteration = 1
                 if device_for is not None:
                     w.set_device(device_for(tid))
-                results[part.index] = list(w.train(part.index, part))
-                workers_out[part.index] = w
+                results[pos] = list(w.train(part.index, part))
+                workers_out[pos] = w
             except BaseException as exc:  # surfaced to the caller, not swallowed
                 errors.append(exc)
                 if tolerate_failures:
                     # the shard goes back to the queue for a surviving worker (Spark would re-run the
                     # task; the lost worker's uncommitted window is dropped)
-                    retries[part.index] = retries.get(part.index, 0) + 1
-                    if retries[part.index] <= 2:
-                        tasks.put(part)
-                    results[part.index] = []
+                    retries[pos] = retries.get(pos, 0) + 1
+                    if retries[pos] <= 2:
+                        tasks.put((pos, part))
+                    results[pos] = []
                     continue
                 return
 
@@ -274,6 +274,13 @@ class EnsembleTrainer(Trainer):
     def train(self, dataframe: Dataset, shuffle: bool = False) -> List[Sequential]:
         dataframe = self._maybe_shuffle(dataframe, shuffle).repartition(self.num_ensembles)
         worker = self.allocate_worker()
+        if self.backend == "fabric" and torch.cuda.is_available():
+            from .parallel.runtime import train_ensemble_native
+
+            self.record_training_start()
+            models, self.history = train_ensemble_native(self, dataframe)
+            self.record_training_end()
+            return models
         self.record_training_start()
         results, workers = _run_tasks(worker, dataframe.partitions(self.num_ensembles), self.num_ensembles,
                                       self._thread_device)

@@ -160,6 +160,12 @@ def test_single_and_averaging_trainers_native():
     ma = a.train(ds)
     ma.compile("categorical_crossentropy")
     assert ma.evaluate(x.float() / 255.0, y)[1] > 0.8
+    from distkeras_b200.trainers import EnsembleTrainer
+
+    e = EnsembleTrainer(_mlp(0), adam, "categorical_crossentropy", batch_size=64, num_ensembles=3, num_epoch=2)
+    models = e.train(ds)
+    assert len(models) == 3 and len(e.get_history()) == 3 * 2 * ((n // 3) // 64)
+    assert not torch.equal(models[0].get_flat_weights(), models[1].get_flat_weights())
 
 
 def test_native_predictor_matches_autograd():

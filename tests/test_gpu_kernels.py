@@ -257,3 +257,24 @@ def test_gemm_pull_fused_kernel(N):
     assert torch.equal(w, center) and torch.equal(w1, center) and torch.equal(wb, center.to(torch.bfloat16))
     ref = torch.relu(x @ center.t() + bias)
     assert torch.allclose(out.float(), ref, atol=0.06, rtol=2e-2)
+
+
+@pytest.mark.parametrize("M,Nn,K,bn", [(128, 256, 64, 256), (1024, 1000, 784, 256), (4096, 200, 1000, 256),
+                                        (300, 130, 136, 256), (2048, 128, 512, 128), (37, 1000, 200, 256),
+                                        (16384, 1000, 784, 256)])
+def test_gemm_persistent(N, M, Nn, K, bn):
+    """Persistent kernel (double-buffered TMEM accumulator): forward form and dgrad form with mask."""
+    from distkeras_b200.ops.gemm import gemm_tn
+
+    torch.manual_seed(12)
+    a, b = bf(torch.randn(M, K, device="cuda")), bf(torch.randn(Nn, K, device="cuda"))
+    bias = torch.randn(Nn, device="cuda")
+    ref = torch.relu(a.float() @ b.float().t() + bias)
+    ld = (Nn + 7) // 8 * 8
+    if ld == Nn:
+        out = gemm_tn(a, b, bias=bias, relu=True, persistent=True, bn=bn)
+        assert torch.allclose(out.float(), ref, atol=0.05 * K ** 0.5, rtol=2e-2)
+        mask = bf(torch.randn(M, Nn, device="cuda"))
+        got = gemm_tn(a, b.t().contiguous(), b_mn=True, mask=mask, alpha=1.5, persistent=True, bn=bn)
+        want = torch.where(mask.float() > 0, 1.5 * (a.float() @ b.float().t()), torch.zeros_like(ref))
+        assert torch.allclose(got.float(), want, atol=0.05 * K ** 0.5, rtol=2e-2)
