@@ -54,9 +54,11 @@ def reference_arm() -> None:
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clock / throttle sampling (B200_PROFILING.md).  The sampler is started well before
+    the timed region (nvidia-smi needs a moment to enumerate the GPUs) and its samples are filtered
+    to the [mark_start, mark_end] wall-clock window of the timed region."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -64,6 +66,7 @@ class ClockSampler:
         self.n_gpus = n_gpus
         self.proc = None
         self.path = os.path.join("/tmp", f"dk_clocks_{os.getpid()}.csv")
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -73,38 +76,56 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        import datetime
+
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
+            if len(parts) < 9:
                 continue
             try:
-                if int(parts[0]) >= self.n_gpus:  # GPUs of the box this job does not use
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if int(parts[1]) >= self.n_gpus:
                     continue
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                rows.append((ts, float(parts[2]), float(parts[3]), parts[5:9]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[4:8]):
-                if v.lower().startswith("active") and not v.lower().startswith("not"):
-                    reasons.add(n)
         try:
             os.remove(self.path)
         except OSError:
             pass
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        window = "timed region"
+        if not inside and rows:  # region shorter than the sampling period: nearest samples around it
+            inside = sorted(rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[: max(1, self.n_gpus)]
+            window = "nearest samples to the timed region"
+        reasons = set()
+        for r in inside:
+            for n, v in zip(names, r[3]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm = [r[1] for r in inside]
+        mx = [r[2] for r in inside]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def main() -> None:
@@ -201,6 +222,8 @@ def main() -> None:
     region = ps.region if rank == 0 else FabricRegion.open(info, local)
     ms_dev, launches = 0.0, 0
     sampler = ClockSampler(world)
+    if rank == 0:
+        sampler.start()
     if is_worker:
         wid = rank - 1 if (args.dedicated_ps and world > 1) else rank
         in_dtype = "f32" if args.model == "higgs_mlp" else "u8"
@@ -232,14 +255,14 @@ def main() -> None:
             run_steps(W)
         torch.cuda.synchronize()
         barrier()
-        if rank == 0:
-            sampler.start()
+        sampler.mark_start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(worker.compute):
             ev0.record(worker.compute)
             nwin, ntail = run_steps(K)
             ev1.record(worker.compute)
         torch.cuda.synchronize()
+        sampler.mark_end()
         barrier()
         ms_dev = ev0.elapsed_time(ev1)
         per_step = (worker.kernels_per_window - worker.comm_kernels()) // tau

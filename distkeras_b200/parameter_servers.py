@@ -276,6 +276,14 @@ class FabricParameterServer(ParameterServer):
         # the control word starts at 0; the reference's counter starts at 1
         return int(self.region.read_ctrl()[0]) + 1
 
+    def heartbeats(self, num_workers: int = 16):
+        """Last iteration at which each worker committed (control-block words written by the commit
+        kernels): the watchdog's view of worker liveness; the PS itself never waits on a worker."""
+        from . import _native
+
+        c = self.region.read_ctrl()
+        return [int(v) for v in c[_native.CTRL_HEARTBEAT:_native.CTRL_HEARTBEAT + num_workers]]
+
     def staleness_histogram(self):
         from . import _native
 
