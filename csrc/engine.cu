@@ -275,9 +275,9 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
     persistent_env = (pe != nullptr && pe[0] == '0') ? 0 : 1;
   }
   if (bn <= 0 && persistent_env && !ep->d_fp32 && ep->d != nullptr && ep->dt == nullptr && !ep->bias_along_m &&
-      !(flags & (DK_GEMM_A_MN | DK_GEMM_TF32)) && N > 64 && (ep->ldd % 8) == 0 &&
+      !(flags & (DK_GEMM_A_MN | DK_GEMM_TF32)) && N >= 16 && (ep->ldd % 8) == 0 &&
       (ep->mask == nullptr || (ep->ld_mask % 8) == 0)) {
-    bn = N > 128 ? 256 : 128;
+    bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
     flags |= DK_GEMM_PERSISTENT;
   }
   if (bn <= 0) bn = (splits == 0 && splitk_ok) ? dk_gemm_pick_bn_splitk(M, N, K) : dk_gemm_pick_bn2(M, N);

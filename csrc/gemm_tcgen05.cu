@@ -672,7 +672,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   constexpr int kBlockK = 64, kUmmaK = 16;
   constexpr uint32_t kTmemCols = 2 * BN;  // two accumulators
   constexpr uint32_t kIdesc = make_idesc(1u, kBlockM, BN) | (BMN ? (1u << 16) : 0u);
-  static_assert(BN == 128 || BN == 256, "persistent kernel: BN in {128, 256}");
+  static_assert(BN == 64 || BN == 128 || BN == 256, "persistent kernel: BN in {64, 128, 256}");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -999,6 +999,7 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
       splits <= 1 && (ep->mask == nullptr || L.tm != nullptr) && !ep->bias_along_m) {
     if (bn == 256) return bmn ? dk::launch_persistent<256, 3, true>(L) : dk::launch_persistent<256, 3, false>(L);
     if (bn == 128) return bmn ? dk::launch_persistent<128, 4, true>(L) : dk::launch_persistent<128, 4, false>(L);
+    if (bn == 64) return bmn ? dk::launch_persistent<64, 6, true>(L) : dk::launch_persistent<64, 6, false>(L);
   }
   if (tf32) {
     if (amn || bmn) return -5;

@@ -107,9 +107,7 @@ ps_commit_kernel(float* __restrict__ center, const float* __restrict__ w, const 
   if (ctrl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
     if (scale_dev == nullptr)  // DynSGD already bumped the counter in its ticket kernel
       asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(ctrl + DK_CTRL_NUM_UPDATES) : "memory");
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(ctrl + DK_CTRL_HEARTBEAT + worker),
-                 "r"(iteration)
-                 : "memory");
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(ctrl + DK_CTRL_HEARTBEAT + worker) : "memory");  // commits by this worker (graph-replay safe liveness counter)
   }
 }
 
@@ -172,9 +170,7 @@ ps_exchange_kernel(float* __restrict__ center, float* __restrict__ w, float* __r
     else
       asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ctrl + DK_CTRL_NUM_UPDATES) : "memory");
     if (last_update != nullptr) *last_update = scale_dev == nullptr ? v + 1 : v;
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(ctrl + DK_CTRL_HEARTBEAT + worker),
-                 "r"(iteration)
-                 : "memory");
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(ctrl + DK_CTRL_HEARTBEAT + worker) : "memory");  // commits by this worker (graph-replay safe liveness counter)
   }
 }
 
@@ -205,9 +201,7 @@ ps_elastic_kernel(float* __restrict__ center, float* __restrict__ w, __nv_bfloat
       });
   if (ctrl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
     asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(ctrl + DK_CTRL_NUM_UPDATES) : "memory");
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(ctrl + DK_CTRL_HEARTBEAT + worker),
-                 "r"(iteration)
-                 : "memory");
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(ctrl + DK_CTRL_HEARTBEAT + worker) : "memory");  // commits by this worker (graph-replay safe liveness counter)
   }
 }
 
@@ -249,9 +243,7 @@ ps_damped_exchange_kernel(float* __restrict__ center, float* __restrict__ w, flo
       });
   if (ctrl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
     asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(ctrl + DK_CTRL_NUM_UPDATES) : "memory");
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(ctrl + DK_CTRL_HEARTBEAT + worker),
-                 "r"(iteration)
-                 : "memory");
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(ctrl + DK_CTRL_HEARTBEAT + worker) : "memory");  // commits by this worker (graph-replay safe liveness counter)
   }
 }
 

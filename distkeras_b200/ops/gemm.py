@@ -32,7 +32,7 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool 
     flags = (N.GEMM_TF32 if tf32 else 0) | (N.GEMM_A_MN if a_mn else 0) | (N.GEMM_B_MN if b_mn else 0)
     if persistent:
         flags |= N.GEMM_PERSISTENT
-        bn = bn or (256 if Nn > 128 else 128)
+        bn = bn or (256 if Nn > 128 else (128 if Nn > 64 else 64))
     if splits == 0:
         splits = N.lib().dk_gemm_pick_splits(M, Nn, K, bn or N.lib().dk_gemm_pick_bn(Nn), int(tf32))
     N.check(N.lib().dk_gemm_tn_ex(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), C.byref(ep), M, Nn, K, flags, bn,

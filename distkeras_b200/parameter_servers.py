@@ -277,8 +277,8 @@ class FabricParameterServer(ParameterServer):
         return int(self.region.read_ctrl()[0]) + 1
 
     def heartbeats(self, num_workers: int = 16):
-        """Last iteration at which each worker committed (control-block words written by the commit
-        kernels): the watchdog's view of worker liveness; the PS itself never waits on a worker."""
+        """Commits applied per worker (control-block counters bumped by the commit kernels): the
+        watchdog's view of worker liveness; the PS itself never waits on a worker."""
         from . import _native
 
         c = self.region.read_ctrl()

@@ -175,7 +175,7 @@ def test_ps_kernels_same_device(N):
     c0 = c.clone()
     N.check(lib.dk_ps_commit(c.data_ptr(), w.data_ptr(), w1.data_ptr(), n, 0.25, None, ctrl.data_ptr(), 2, 7, st()))
     assert torch.allclose(c, c0 + 0.25 * (w - w1), atol=1e-6)
-    assert int(ctrl[N.CTRL_NUM_UPDATES]) == 1 and int(ctrl[N.CTRL_HEARTBEAT + 2]) == 7
+    assert int(ctrl[N.CTRL_NUM_UPDATES]) == 1 and int(ctrl[N.CTRL_HEARTBEAT + 2]) == 1
     last = torch.zeros(1, dtype=torch.int32, device="cuda")
     N.check(lib.dk_ps_pull(c.data_ptr(), w.data_ptr(), w1.data_ptr(), wb.data_ptr(), n, ctrl.data_ptr(), last.data_ptr(), st()))
     assert torch.equal(w, c) and torch.equal(w1, c) and torch.equal(wb, c.to(torch.bfloat16)) and int(last) == 1
@@ -260,7 +260,7 @@ def test_gemm_pull_fused_kernel(N):
 
 
 @pytest.mark.parametrize("M,Nn,K,bn", [(128, 256, 64, 256), (1024, 1000, 784, 256), (4096, 200, 1000, 256),
-                                        (300, 130, 136, 256), (2048, 128, 512, 128), (37, 1000, 200, 256),
+                                        (300, 130, 136, 256), (2048, 128, 512, 128), (37, 1000, 200, 256), (4096, 32, 288, 64), (1000, 64, 32, 64),
                                         (16384, 1000, 784, 256)])
 def test_gemm_persistent(N, M, Nn, K, bn):
     """Persistent kernel (double-buffered TMEM accumulator): forward form and dgrad form with mask."""
