@@ -165,6 +165,9 @@ def main() -> None:
 
     local = int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count()
     torch.cuda.set_device(local)
+    from distkeras_b200.utils.numa import bind_to_gpu_numa_node
+
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         dist = runtime._init_pg()
@@ -327,7 +330,7 @@ def main() -> None:
                        "l2_policy": "kernel-only: inputs resident in device staging (2 x window, "
                                     f"{2 * tau * B * feat / 2**20:.0f} MiB) -- weights stay L2-resident as in real "
                                     "training, no flush; e2e: inputs streamed from pinned host memory every step"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "numa_node_rank0": numa_node,
         }
         print(json.dumps(out, default=lambda o: o.item() if hasattr(o, 'item') else str(o)))
     if dist:

@@ -1062,7 +1062,7 @@ int dk_gemm_pick_splits(int M, int N, int K, int bn, int tf32) {
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
   const int total_kb = (K + (tf32 ? 32 : 64) - 1) / (tf32 ? 32 : 64);
   const int slots = bn > 128 ? 148 : 2 * 148;  // resident CTAs (wide tiles run 1 CTA / SM)
-  int splits = (slots + tiles - 1) / tiles;
+  int splits = slots / tiles;  // floor: tiles x splits must fit in ONE wave (a 2nd, nearly empty wave doubles the time)
   if (splits > total_kb / 4) splits = total_kb / 4;
   if (splits < 1) splits = 1;
   if (splits > 32) splits = 32;

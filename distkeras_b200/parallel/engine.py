@@ -354,10 +354,14 @@ class NativeReplica(Replica):
                 # parameter gradients only feed the optimizer: they run on the engine's side stream
                 # (a parallel branch of the captured graph) while the dgrad chain continues
                 self._add(lst, N.OP_FORK, [0])
-                self.lib.dk_engine_set_build_stream(self.engine, 1)
+                # the last block of the backward chain has no dgrad to overlap with: its bias
+                # gradient stays on the main stream so it runs concurrently with the wgrad
+                colsum_on_side = bi != first_param_block
+                self.lib.dk_engine_set_build_stream(self.engine, 1 if colsum_on_side else 0)
                 if b.bseg is not None:
                     self._add(lst, N.OP_COLSUM, [grad["t"].data_ptr(), rows, Nout, grad["ld"],
                                                  g_ptr + 4 * b.bseg.offset], [1.0])
+                self.lib.dk_engine_set_build_stream(self.engine, 1)
                 # wgrad: dW[Nout, K] = dZ^T[Nout, rows] * In[rows, K]  (both operands MN-major views)
                 ep = N.GemmEpilogue()
                 ep.d, ep.ldd, ep.d_fp32, ep.alpha = g_ptr + 4 * b.kseg.offset, K, 1, 1.0

@@ -434,6 +434,10 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
 
     local = int(os.environ.get("LOCAL_RANK", rank)) % torch.cuda.device_count()
     torch.cuda.set_device(local)
+    if world > 1:
+        from ..utils.numa import bind_to_gpu_numa_node
+
+        bind_to_gpu_numa_node(local)  # pinned staging memory on the GPU's own socket
     alg = trainer.algorithm()
     model = deserialize_keras_model(trainer.master_model)
     in_dtype, affine = _affine_for(dataset, trainer.features_column)

@@ -223,6 +223,37 @@ def test_fused_pull_mode_matches_exchange():
     assert stats[1]["kernels_per_window"] == stats[0]["kernels_per_window"] + 1  # commit + pull_rest vs exchange
 
 
+def _needs_gpus(n):
+    return pytest.mark.skipif(torch.cuda.device_count() < n, reason=f"needs {n} GPUs")
+
+
+@_needs_gpus(2)
+@pytest.mark.parametrize("dedicated", [False, True])
+def test_spawned_multi_gpu_fabric(dedicated):
+    """Driver-style use (no torchrun): the trainer spawns one process per GPU; the center lives in
+    GPU 0's HBM and the other ranks commit / pull through the CUDA-IPC mapping over NVLink."""
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.trainers import ADAG
+
+    g = torch.Generator().manual_seed(0)
+    n, B = 8192, 128
+    proto = torch.randint(0, 200, (10, 64), generator=g)
+    y = torch.randint(0, 10, (n,), generator=g)
+    x = (proto[y] + torch.randint(0, 56, (n, 64), generator=g)).clamp(0, 255).to(torch.uint8)
+    ds = Dataset({"features": x, "label": y.to(torch.int32)})
+    workers = 1 if dedicated else 2
+    t = ADAG(_mlp(0), {"class_name": "adam", "config": {"lr": 0.003}}, "categorical_crossentropy",
+             num_workers=workers, batch_size=B, communication_window=4)
+    t.backend, t.dedicated_ps = "fabric", dedicated
+    model = t.train(ds)
+    h = t.get_history()
+    assert {r["worker_id"] for r in h} == set(range(workers))
+    assert len(h) == n // B
+    assert t.num_updates() == 1 + (n // B) // 4
+    model.compile("categorical_crossentropy")
+    assert model.evaluate(x.float() / 255.0, y)[1] > 0.8
+
+
 def test_smoke_entry():
     import __graft_entry__
 
