@@ -657,14 +657,17 @@ struct PersistentSmem {
   static constexpr int kABytes = kBlockM * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kOutStage = 4 * 2 * 4096;   // 4 warps x 2 slots x (32 rows x 128 B)
-  static constexpr int kMaskStage = 4 * 2 * 4096;
+  static constexpr int kOutStage = 8 * 4096;    // 8 epilogue warps x one 32-row x 128-byte slot
+  static constexpr int kMaskStage = 8 * 4096;
+  static constexpr int kBiasStage = 8 * 1024;   // per-warp copy of the tile's bias slice (<= 256 floats)
   static constexpr int kBarrierBytes = 512;
-  static constexpr int kTotal = STAGES * kStageBytes + kOutStage + kMaskStage + kBarrierBytes + 1024;
+  static constexpr int kTotal = STAGES * kStageBytes + kOutStage + kMaskStage + kBiasStage + kBarrierBytes + 1024;
 };
 
+constexpr int kPersistentThreads = 320;  // producer + MMA + 8 epilogue warps
+
 template <int BN, int STAGES, bool BMN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kPersistentThreads, 1)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
                        const GemmEpilogue ep, const int M, const int N, const int K) {
@@ -679,11 +682,12 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* out_stage = smem + STAGES * S::kStageBytes;
   uint8_t* mask_stage = out_stage + S::kOutStage;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(mask_stage + S::kMaskStage);
+  float* bias_stage = reinterpret_cast<float*>(mask_stage + S::kMaskStage);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(mask_stage + S::kMaskStage + S::kBiasStage);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint64_t* mask_bar = tmem_empty_bar + 2;        // [4 warps][2 slots]
+  uint64_t* mask_bar = tmem_empty_bar + 2;        // [8 epilogue warps]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 8);
 
   const int warp = threadIdx.x >> 5;
@@ -704,7 +708,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[a], 8);  // one arrival per epilogue warp
     }
     for (int i = 0; i < 8; ++i) mbar_init(&mask_bar[i], 1);
     fence_barrier_init();
@@ -782,11 +786,16 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
+    // 8 warps: warp e = warp - 2; TMEM lane quarter = warp & 3; the two warps of a quarter
+    // alternate over the 64-column slices (group = e >> 2 takes slices of matching parity).
+    const int e = warp - 2;
     const int quarter = warp & 3;
-    const uint32_t out_region = smem_u32(out_stage) + quarter * 8192;    // 2 slots x 4 KB
-    const uint32_t mask_region = smem_u32(mask_stage) + quarter * 8192;
-    uint64_t* my_mask_bar = mask_bar + quarter * 2;
-    uint32_t mask_phase[2] = {0, 0};
+    const int group = e >> 2;
+    const uint32_t out_region = smem_u32(out_stage) + e * 4096;
+    const uint32_t mask_region = smem_u32(mask_stage) + e * 4096;
+    float* my_bias = bias_stage + e * 256;
+    uint64_t* my_mask_bar = mask_bar + e;
+    uint32_t mask_phase = 0;
     uint32_t drop_salt = 0, drop_thr = 0;
     float keep_scale = 1.f;
     if (ep.drop_p > 0.f) {
@@ -796,28 +805,29 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
     constexpr int kSlices = BN / 64;
     int it = 0;
-    int slot = 0;  // staging ring position (persists across tiles)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * BN;
       const int acc = it & 1;
       const int m = m0 + quarter * 32 + lane;
       const int valid_slices = min(kSlices, (N - n0 + 63) / 64);
-      // prefetch the first mask slice of this tile while the MMAs may still be running
-      if (ep.tma_mask && lane == 0 && valid_slices > 0) {
-        mbar_expect_tx(&my_mask_bar[slot], 4096);
-        tma_load_2d_addr(mask_region + slot * 4096, &tmap_m, n0, m0 + quarter * 32, &my_mask_bar[slot]);
+      // first slice of this tile handled by this warp
+      int sl = ((it * kSlices) & 1) == group ? 0 : 1;
+      if (ep.tma_mask && lane == 0 && sl < valid_slices) {
+        mbar_expect_tx(my_mask_bar, 4096);
+        tma_load_2d_addr(mask_region, &tmap_m, n0 + sl * 64, m0 + quarter * 32, my_mask_bar);
+      }
+      if (ep.bias != nullptr) {
+        // stage this tile's bias slice once (broadcast reads from smem in the slice loop)
+#pragma unroll
+        for (int j = lane; j < BN; j += 32) my_bias[j] = (n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
+        __syncwarp();
       }
       mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
       tcgen05_fence_after();
+      bool arrived = false;
 #pragma unroll 1
-      for (int sl = 0; sl < valid_slices; ++sl) {
+      for (; sl < valid_slices; sl += 2) {
         const int nc = n0 + sl * 64;
-        const int cur = slot;
-        const int nxt = slot ^ 1;
-        if (ep.tma_mask && lane == 0 && sl + 1 < valid_slices) {
-          mbar_expect_tx(&my_mask_bar[nxt], 4096);
-          tma_load_2d_addr(mask_region + nxt * 4096, &tmap_m, nc + 64, m0 + quarter * 32, &my_mask_bar[nxt]);
-        }
         float v[64];
         {
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + sl * 64;
@@ -831,27 +841,22 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             v[32 + j] = __uint_as_float(r1[j]);
           }
         }
-        if (sl == valid_slices - 1) {
-          // accumulator fully read: hand it back to the MMA warp
+        if (sl + 2 >= valid_slices) {
+          // this warp's last read of the accumulator: hand it back to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          arrived = true;
         }
         if (ep.alpha != 1.f) {
 #pragma unroll
           for (int j = 0; j < 64; ++j) v[j] *= ep.alpha;
         }
         if (ep.bias != nullptr) {
-          if (nc + 64 <= N && ((reinterpret_cast<uintptr_t>(ep.bias + nc) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (nc + j < N) v[j] += __ldg(ep.bias + nc + j);
+          for (int j = 0; j < 64; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(my_bias + sl * 64 + j);
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
           }
         }
         if (ep.act == 1) {
@@ -869,32 +874,41 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           }
         }
         if (ep.tma_mask) {
-          mbar_wait(&my_mask_bar[cur], mask_phase[cur]);
-          mask_phase[cur] ^= 1;
+          mbar_wait(my_mask_bar, mask_phase);
+          mask_phase ^= 1;
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            const uint4 q = ld_shared_v4(mask_region + cur * 4096 + sw128_off(lane, t));
+            const uint4 q = ld_shared_v4(mask_region + sw128_off(lane, t));
             const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
 #pragma unroll
             for (int u = 0; u < 8; ++u)
               if (!(__bfloat162float(h[u]) > 0.f)) v[t * 8 + u] = 0.f;
           }
+          __syncwarp();
+          if (lane == 0 && sl + 2 < valid_slices) {  // prefetch this warp's next mask slice
+            mbar_expect_tx(my_mask_bar, 4096);
+            tma_load_2d_addr(mask_region, &tmap_m, nc + 128, m0 + quarter * 32, my_mask_bar);
+          }
         }
-        // staging slot `cur` was last used two slices ago: its TMA store must have finished reading
-        if (lane == 0) tma_store_wait_read<1>();
+        // the previous TMA store out of this warp's slot must have finished reading it
+        if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < 8; ++t)
-          st_shared_v4(out_region + cur * 4096 + sw128_off(lane, t), pack_bf16x2(v[8 * t], v[8 * t + 1]),
+          st_shared_v4(out_region + sw128_off(lane, t), pack_bf16x2(v[8 * t], v[8 * t + 1]),
                        pack_bf16x2(v[8 * t + 2], v[8 * t + 3]), pack_bf16x2(v[8 * t + 4], v[8 * t + 5]),
                        pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d_addr(&tmap_d, out_region + cur * 4096, nc, m0 + quarter * 32);
+          tma_store_2d_addr(&tmap_d, out_region, nc, m0 + quarter * 32);
           tma_store_commit();
         }
-        slot ^= 1;
+      }
+      if (!arrived) {  // no slice of this tile for this warp: still release the accumulator
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       }
     }
     if (lane == 0) tma_store_wait_read<0>();
@@ -926,7 +940,7 @@ static int launch_persistent(const GemmLaunch& L) {
   ep.tma_mask = L.tm != nullptr ? 1 : 0;
   const int tiles = ((L.M + kBlockM - 1) / kBlockM) * ((L.N + BN - 1) / BN);
   const int grid = tiles < sm_count[dev & 63] ? tiles : sm_count[dev & 63];
-  DK_HOST_CHECK(DK_LAUNCH(kern, grid, kGemmThreads, S::kTotal, L.stream, *L.ta, *L.tb, *L.td,
+  DK_HOST_CHECK(DK_LAUNCH(kern, grid, kPersistentThreads, S::kTotal, L.stream, *L.ta, *L.tb, *L.td,
                           ep.tma_mask ? *L.tm : *L.ta, ep, L.M, L.N, L.K));
   return 0;
 }
