@@ -106,7 +106,7 @@ class Worker:
         if isinstance(iterator, Partition):
             for batch in iterator.batches(fcols + lcols, self.batch_size, drop_last=True):
                 xs, ys = batch[:len(fcols)], batch[len(fcols):]
-                yield (xs[0] if len(xs) == 1 else list(xs)), (ys[0] if len(ys) == 1 else list(ys))
+                yield self._merge_columns(xs), (ys[0] if len(ys) == 1 else list(ys))
             return
         rows = []
         for row in iterator:
@@ -115,7 +115,15 @@ class Worker:
                 xs = [torch.as_tensor(np.stack([np.asarray(r[c]) for r in rows])) for c in fcols]
                 ys = [torch.as_tensor(np.stack([np.asarray(r[c]) for r in rows])) for c in lcols]
                 rows = []
-                yield (xs[0] if len(xs) == 1 else xs), (ys[0] if len(ys) == 1 else ys)
+                yield self._merge_columns(xs), (ys[0] if len(ys) == 1 else ys)
+
+    @staticmethod
+    def _merge_columns(xs):
+        """Several feature columns (the reference's multi-input form, ``workers.py:65-66``) feed a
+        ``Sequential`` as one vector: flattened and concatenated along the feature axis."""
+        if len(xs) == 1:
+            return xs[0]
+        return torch.cat([x.reshape(x.shape[0], -1).float() for x in xs], dim=1)
 
     def prefetching(self, iterator) -> None:
         """Producer: ``num_epoch`` passes over the partition, exact ``batch_size`` batches

@@ -246,3 +246,16 @@ def test_flat_optimizer_matches_torch(name):
         ref.step()
     tol = 2e-3 if name in ("adam", "adamax") else 1e-5  # Keras vs torch epsilon placement differs slightly
     assert torch.allclose(w, p.data, atol=tol), (name, float((w - p.data).abs().max()))
+
+
+def test_multiple_feature_columns_are_concatenated():
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(256, 5, generator=g), torch.randn(256, 3, generator=g)
+    w = torch.randn(8, 3, generator=g)
+    ds = Dataset({"fa": a, "fb": b, "label": (torch.cat([a, b], 1) @ w).argmax(1).to(torch.int32)})
+    t = SingleTrainer(tiny_model(0), {"class_name": "adam", "config": {"lr": 0.02}}, "categorical_crossentropy",
+                      features_col=["fa", "fb"], batch_size=16, num_epoch=3)
+    t.backend = "thread"
+    m = t.train(ds)
+    m.compile("categorical_crossentropy")
+    assert m.evaluate(torch.cat([a, b], 1), ds["label"])[1] > 0.6
