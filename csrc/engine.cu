@@ -62,6 +62,16 @@ inline T* rp(const Engine* e, int64_t v) {
   return reinterpret_cast<T*>(resolve(e, v));
 }
 
+// kernel launches performed by one op (memset / memcpy / fork / join nodes launch none)
+int kernels_in_op(int kind) {
+  switch (kind) {
+    case DK_OP_MEMSET: case DK_OP_MEMCPY: case DK_OP_MEMCPY2D: case DK_OP_FORK: case DK_OP_JOIN: return 0;
+    case DK_OP_BN_FWD: return 3;
+    case DK_OP_BN_BWD: return 2;
+    default: return 1;
+  }
+}
+
 int run_op(Engine* e, Op& op, void* main_stream) {
   const int64_t* a = op.i;
   const double* f = op.f;
@@ -113,6 +123,25 @@ int run_op(Engine* e, Op& op, void* main_stream) {
       // dst, dpitch, src, spitch, width_bytes, height
       return dk_memcpy2d_async(resolve(e, a[0]), (long)a[1], resolve(e, a[2]), (long)a[3], (long)a[4],
                                (long)a[5], st);
+    case DK_OP_BN_FWD:
+      // x, rows, C, sums, saved_mean, saved_invstd, moving_mean, moving_var, gamma, beta, relu, y | eps, momentum
+      return dk_bn_forward(resolve(e, a[0]), (long)a[1], (int)a[2], rp<float>(e, a[3]), rp<float>(e, a[4]),
+                           rp<float>(e, a[5]), rp<float>(e, a[6]), rp<float>(e, a[7]), rp<const float>(e, a[8]),
+                           rp<const float>(e, a[9]), (float)f[0], (float)f[1], (int)a[10], resolve(e, a[11]), st);
+    case DK_OP_BN_INF:
+      // x, rows, C, moving_mean, moving_var, gamma, beta, relu, y | eps
+      return dk_bn_inference(resolve(e, a[0]), (long)a[1], (int)a[2], rp<const float>(e, a[3]),
+                             rp<const float>(e, a[4]), rp<const float>(e, a[5]), rp<const float>(e, a[6]),
+                             (float)f[0], (int)a[7], resolve(e, a[8]), st);
+    case DK_OP_BN_BWD:
+      // dy, x, y_relu, rows, C, saved_mean, saved_invstd, gamma, sums, dgamma, dbeta, dx
+      return dk_bn_backward(resolve(e, a[0]), resolve(e, a[1]), resolve(e, a[2]), (long)a[3], (int)a[4],
+                            rp<const float>(e, a[5]), rp<const float>(e, a[6]), rp<const float>(e, a[7]),
+                            rp<float>(e, a[8]), rp<float>(e, a[9]), rp<float>(e, a[10]), resolve(e, a[11]), st);
+    case DK_OP_GAP_FWD:
+      return dk_gap_fwd(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], resolve(e, a[4]), st);
+    case DK_OP_GAP_BWD:
+      return dk_gap_bwd(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], resolve(e, a[4]), st);
     case DK_OP_TRANSPOSE:
       // src, rows, cols, lds, dst, ldd
       return dk_transpose_bf16(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], resolve(e, a[4]),
@@ -326,8 +355,7 @@ int dk_engine_run(void* h, int list, void* stream) {
   for (Op& op : e->lists[list]) {
     int r = run_op(e, op, stream);
     if (r != 0) return r;
-    if (op.kind == DK_OP_FORK || op.kind == DK_OP_JOIN) continue;
-    if (op.kind != DK_OP_MEMSET && op.kind != DK_OP_MEMCPY && op.kind != DK_OP_MEMCPY2D) e->launches += 1;
+    e->launches += kernels_in_op(op.kind);
   }
   return 0;
 }
@@ -344,9 +372,7 @@ int dk_engine_list_kernels(void* h, int list) {
   if (list < 0 || list >= (int)e->lists.size()) return -1;
   int n = 0;
   for (const Op& op : e->lists[list])
-    if (op.kind != DK_OP_MEMSET && op.kind != DK_OP_MEMCPY && op.kind != DK_OP_MEMCPY2D && op.kind != DK_OP_FORK &&
-        op.kind != DK_OP_JOIN)
-      ++n;
+    n += kernels_in_op(op.kind);
   return n;
 }
 

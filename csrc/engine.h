@@ -40,7 +40,12 @@ enum {
   DK_OP_MEMCPY2D = 28,
   DK_OP_FORK = 29,
   DK_OP_JOIN = 30,
-  DK_OP_GEMM_PULL = 31
+  DK_OP_GEMM_PULL = 31,
+  DK_OP_BN_FWD = 32,
+  DK_OP_BN_INF = 33,
+  DK_OP_BN_BWD = 34,
+  DK_OP_GAP_FWD = 35,
+  DK_OP_GAP_BWD = 36
 };
 
 #ifdef __cplusplus

@@ -59,6 +59,17 @@ int dk_col2im(const void* col, int ldcol, int B, int H, int W, int C, int KH, in
 int dk_maxpool_fwd(const void* x, int B, int H, int W, int C, int k, int stride, void* y, void* stream);
 int dk_maxpool_bwd(const void* x, const void* y, const void* dy, int B, int H, int W, int C, int k,
                    int stride, void* dx, void* stream);
+// BatchNormalization over the last axis of [rows, C] bf16 (C % 8 == 0) and global average pooling
+int dk_bn_forward(const void* x, long rows, int C, float* sums, float* saved_mean, float* saved_invstd,
+                  float* moving_mean, float* moving_var, const float* gamma, const float* beta, float eps,
+                  float momentum, int relu, void* y, void* stream);
+int dk_bn_inference(const void* x, long rows, int C, const float* moving_mean, const float* moving_var,
+                    const float* gamma, const float* beta, float eps, int relu, void* y, void* stream);
+int dk_bn_backward(const void* dy, const void* x, const void* y_relu, long rows, int C, const float* saved_mean,
+                   const float* saved_invstd, const float* gamma, float* sums, float* dgamma, float* dbeta, void* dx,
+                   void* stream);
+int dk_gap_fwd(const void* x, int B, int P, int C, void* y, void* stream);
+int dk_gap_bwd(const void* dy, int B, int P, int C, void* dx, void* stream);
 int dk_relu_mask_bf16(void* dy, const void* act, long n, void* stream);
 int dk_add_bf16(void* dst, const void* a, const void* b, long n, int relu, void* stream);
 

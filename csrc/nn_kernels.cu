@@ -448,6 +448,198 @@ add_bf16_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// BatchNormalization over the channel (last) axis of a [rows, C] bf16 matrix, training mode
+// (not in the reference's models; needed by ResNet-18, BASELINE config 5).
+//   stats    : per-channel sum / sum of squares (atomics into a zeroed [2, C] fp32 buffer)
+//   finalize : mean, invstd (saved for backward) + moving-average update in the fp32 master
+//   apply    : y = (x - mean) * invstd * gamma + beta  (+ ReLU)
+//   bwd_reduce: sum(dy'), sum(dy' * xhat) with dy' = dy masked by the ReLU output
+//   bwd_apply : dx = gamma * invstd * (dy' - sum(dy')/n - xhat * sum(dy' xhat)/n)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long rows, int C, float* __restrict__ sums,
+                int rows_per_block) {
+  DK_PDL_ENTER();
+  __shared__ float red[2][8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + lane * 2;
+  const long r0 = static_cast<long>(blockIdx.y) * rows_per_block;
+  const long r1 = min(rows, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  if (c + 1 < C) {
+    for (long r = r0 + warp; r < r1; r += 8) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + r * C + c));
+      s0 += f.x; s1 += f.y; q0 += f.x * f.x; q1 += f.y * f.y;
+    }
+  }
+  red[0][warp][lane * 2] = s0; red[0][warp][lane * 2 + 1] = s1;
+  red[1][warp][lane * 2] = q0; red[1][warp][lane * 2 + 1] = q1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[which][w][col];
+    if (blockIdx.x * 64 + col < C) atomicAdd(sums + which * C + blockIdx.x * 64 + col, t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ sums, long rows, int C, float eps, float momentum,
+                   float* __restrict__ saved_mean, float* __restrict__ saved_invstd,
+                   float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+  DK_PDL_ENTER();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float inv_n = 1.f / static_cast<float>(rows);
+  const float mean = sums[c] * inv_n;
+  const float var = fmaxf(sums[C + c] * inv_n - mean * mean, 0.f);
+  saved_mean[c] = mean;
+  saved_invstd[c] = rsqrtf(var + eps);
+  if (moving_mean != nullptr) {
+    moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * mean;
+    moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * var;
+  }
+}
+
+// mode 0: training (saved batch statistics); mode 1: inference (moving statistics, mean/var given)
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long rows, int C, const float* __restrict__ mean,
+                const float* __restrict__ invstd_or_var, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int relu, int inference, float eps,
+                __nv_bfloat16* __restrict__ y) {
+  DK_PDL_ENTER();
+  const int c8n = C >> 3;
+  const long total = rows * c8n;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c8n) << 3;
+    const uint4 q = *reinterpret_cast<const uint4*>(x + (i << 3));
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
+    float o[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float is = inference ? rsqrtf(invstd_or_var[c + u] + eps) : invstd_or_var[c + u];
+      float v = (__bfloat162float(h[u]) - mean[c + u]) * is * gamma[c + u] + beta[c + u];
+      o[u] = relu ? fmaxf(v, 0.f) : v;
+    }
+    uint4 w;
+    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+    w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(y + (i << 3)) = w;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                     const __nv_bfloat16* __restrict__ y_relu, long rows, int C,
+                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                     float* __restrict__ sums, int rows_per_block) {
+  DK_PDL_ENTER();
+  __shared__ float red[2][8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + lane * 2;
+  const long r0 = static_cast<long>(blockIdx.y) * rows_per_block;
+  const long r1 = min(rows, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  if (c + 1 < C) {
+    const float m0 = mean[c], m1 = mean[c + 1], i0 = invstd[c], i1 = invstd[c + 1];
+    for (long r = r0 + warp; r < r1; r += 8) {
+      float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + r * C + c));
+      if (y_relu != nullptr) {
+        const float2 yy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(y_relu + r * C + c));
+        if (!(yy.x > 0.f)) g.x = 0.f;
+        if (!(yy.y > 0.f)) g.y = 0.f;
+      }
+      const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + r * C + c));
+      s0 += g.x; s1 += g.y;
+      q0 += g.x * (xv.x - m0) * i0; q1 += g.y * (xv.y - m1) * i1;
+    }
+  }
+  red[0][warp][lane * 2] = s0; red[0][warp][lane * 2 + 1] = s1;
+  red[1][warp][lane * 2] = q0; red[1][warp][lane * 2 + 1] = q1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[which][w][col];
+    if (blockIdx.x * 64 + col < C) atomicAdd(sums + which * C + blockIdx.x * 64 + col, t);
+  }
+}
+
+// dx, and the parameter gradients dgamma = sum(dy' xhat), dbeta = sum(dy') (written by block 0)
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                    const __nv_bfloat16* __restrict__ y_relu, long rows, int C,
+                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ gamma, const float* __restrict__ sums,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx) {
+  DK_PDL_ENTER();
+  const int c8n = C >> 3;
+  const long total = rows * c8n;
+  const float inv_n = 1.f / static_cast<float>(rows);
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dbeta[c] = sums[c];
+      dgamma[c] = sums[C + c];
+    }
+  }
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c8n) << 3;
+    const uint4 qg = *reinterpret_cast<const uint4*>(dy + (i << 3));
+    const uint4 qx = *reinterpret_cast<const uint4*>(x + (i << 3));
+    uint4 qy = make_uint4(0, 0, 0, 0);
+    if (y_relu != nullptr) qy = *reinterpret_cast<const uint4*>(y_relu + (i << 3));
+    const __nv_bfloat16* hg = reinterpret_cast<const __nv_bfloat16*>(&qg);
+    const __nv_bfloat16* hx = reinterpret_cast<const __nv_bfloat16*>(&qx);
+    const __nv_bfloat16* hy = reinterpret_cast<const __nv_bfloat16*>(&qy);
+    float o[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float g = __bfloat162float(hg[u]);
+      if (y_relu != nullptr && !(__bfloat162float(hy[u]) > 0.f)) g = 0.f;
+      const float xhat = (__bfloat162float(hx[u]) - mean[c + u]) * invstd[c + u];
+      o[u] = gamma[c + u] * invstd[c + u] * (g - sums[c + u] * inv_n - xhat * sums[C + c + u] * inv_n);
+    }
+    uint4 w;
+    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+    w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(dx + (i << 3)) = w;
+  }
+}
+
+// global average pooling over the spatial positions: x [B, P, C] -> y [B, C] (and its backward)
+__global__ void __launch_bounds__(256)
+gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int P, int C, __nv_bfloat16* __restrict__ y) {
+  DK_PDL_ENTER();
+  const long total = static_cast<long>(B) * C;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long b = i / C;
+    float acc = 0.f;
+    for (int p = 0; p < P; ++p) acc += __bfloat162float(x[(b * P + p) * C + c]);
+    y[i] = __float2bfloat16_rn(acc / static_cast<float>(P));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gap_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int B, int P, int C, __nv_bfloat16* __restrict__ dx) {
+  DK_PDL_ENTER();
+  const long total = static_cast<long>(B) * P * C;
+  const float inv = 1.f / static_cast<float>(P);
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long b = i / (static_cast<long>(P) * C);
+    dx[i] = __float2bfloat16_rn(__bfloat162float(dy[b * C + c]) * inv);
+  }
+}
+
 static inline int ew_grid(long n) {
   long b = (n + 255) / 256;
   if (b < 1) b = 1;
@@ -594,6 +786,73 @@ int dk_maxpool_bwd(const void* x, const void* y, const void* dy, int B, int H, i
       reinterpret_cast<const __nv_bfloat16*>(dy), B, H, W, C, k, stride, OH, OW,
       reinterpret_cast<__nv_bfloat16*>(dx)));
   DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+
+static inline void stat_grid(long rows, int C, dim3* grid, int* rpb) {
+  const int colblocks = (C + 63) / 64;
+  long splits = (rows + 255) / 256;
+  long cap = (148 * 8) / colblocks;
+  if (cap < 64) cap = 64;
+  if (splits > cap) splits = cap;
+  if (splits < 1) splits = 1;
+  *rpb = static_cast<int>((rows + splits - 1) / splits);
+  *grid = dim3(colblocks, static_cast<unsigned>(splits));
+}
+
+// training forward: stats (sums must be zeroed) -> finalize -> apply, three launches
+int dk_bn_forward(const void* x, long rows, int C, float* sums, float* saved_mean, float* saved_invstd,
+                  float* moving_mean, float* moving_var, const float* gamma, const float* beta, float eps,
+                  float momentum, int relu, void* y, void* stream) {
+  if (C % 8 != 0) return -1;
+  dim3 grid; int rpb;
+  stat_grid(rows, C, &grid, &rpb);
+  DK_HOST_CHECK(DK_LAUNCH(bn_stats_kernel, grid, 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), rows, C,
+                          sums, rpb));
+  DK_HOST_CHECK(DK_LAUNCH(bn_finalize_kernel, (C + 255) / 256, 256, 0, stream, (const float*)sums, rows, C, eps,
+                          momentum, saved_mean, saved_invstd, moving_mean, moving_var));
+  DK_HOST_CHECK(DK_LAUNCH(bn_apply_kernel, ew_grid(rows * (C / 8)), 256, 0, stream,
+                          reinterpret_cast<const __nv_bfloat16*>(x), rows, C, (const float*)saved_mean,
+                          (const float*)saved_invstd, gamma, beta, relu, 0, eps, reinterpret_cast<__nv_bfloat16*>(y)));
+  return 0;
+}
+
+int dk_bn_inference(const void* x, long rows, int C, const float* moving_mean, const float* moving_var,
+                    const float* gamma, const float* beta, float eps, int relu, void* y, void* stream) {
+  if (C % 8 != 0) return -1;
+  DK_HOST_CHECK(DK_LAUNCH(bn_apply_kernel, ew_grid(rows * (C / 8)), 256, 0, stream,
+                          reinterpret_cast<const __nv_bfloat16*>(x), rows, C, moving_mean, moving_var, gamma, beta,
+                          relu, 1, eps, reinterpret_cast<__nv_bfloat16*>(y)));
+  return 0;
+}
+
+// backward: reduce (sums zeroed) -> apply; y_relu (optional) is the ReLU output used as mask
+int dk_bn_backward(const void* dy, const void* x, const void* y_relu, long rows, int C, const float* saved_mean,
+                   const float* saved_invstd, const float* gamma, float* sums, float* dgamma, float* dbeta, void* dx,
+                   void* stream) {
+  if (C % 8 != 0) return -1;
+  dim3 grid; int rpb;
+  stat_grid(rows, C, &grid, &rpb);
+  DK_HOST_CHECK(DK_LAUNCH(bn_bwd_reduce_kernel, grid, 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(dy),
+                          reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(y_relu),
+                          rows, C, saved_mean, saved_invstd, sums, rpb));
+  DK_HOST_CHECK(DK_LAUNCH(bn_bwd_apply_kernel, ew_grid(rows * (C / 8)), 256, 0, stream,
+                          reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
+                          reinterpret_cast<const __nv_bfloat16*>(y_relu), rows, C, saved_mean, saved_invstd, gamma,
+                          (const float*)sums, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dx)));
+  return 0;
+}
+
+int dk_gap_fwd(const void* x, int B, int P, int C, void* y, void* stream) {
+  DK_HOST_CHECK(DK_LAUNCH(gap_fwd_kernel, ew_grid(static_cast<long>(B) * C), 256, 0, stream,
+                          reinterpret_cast<const __nv_bfloat16*>(x), B, P, C, reinterpret_cast<__nv_bfloat16*>(y)));
+  return 0;
+}
+
+int dk_gap_bwd(const void* dy, int B, int P, int C, void* dx, void* stream) {
+  DK_HOST_CHECK(DK_LAUNCH(gap_bwd_kernel, ew_grid(static_cast<long>(B) * P * C), 256, 0, stream,
+                          reinterpret_cast<const __nv_bfloat16*>(dy), B, P, C, reinterpret_cast<__nv_bfloat16*>(dx)));
   return 0;
 }
 

@@ -37,6 +37,7 @@ OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_RELU_MASK, OP_ADD, OP_MEMSET = 8, 9, 10, 11, 
 OP_PS_COMMIT, OP_PS_PULL, OP_PS_EXCHANGE, OP_PS_ELASTIC, OP_PS_DAMPED, OP_PS_TICKET = 13, 14, 15, 16, 17, 18
 OP_LOCK_ACQUIRE, OP_LOCK_RELEASE, OP_EAMSGD_PRE, OP_EAMSGD_POST, OP_CAST, OP_ELOSS = 19, 20, 21, 22, 23, 24
 OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D, OP_FORK, OP_JOIN, OP_GEMM_PULL = 25, 26, 27, 28, 29, 30, 31
+OP_BN_FWD, OP_BN_INF, OP_BN_BWD, OP_GAP_FWD, OP_GAP_BWD = 32, 33, 34, 35, 36
 GEMM_TF32, GEMM_A_MN, GEMM_B_MN, GEMM_PERSISTENT = 1, 2, 4, 8
 
 OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6}
@@ -83,6 +84,11 @@ _SIGNATURES = {
     "dk_maxpool_fwd": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "dk_maxpool_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "dk_relu_mask_bf16": (i32, [vp, vp, i64, vp]),
+    "dk_bn_forward": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp]),
+    "dk_bn_inference": (i32, [vp, i64, i32, vp, vp, vp, vp, f32, i32, vp, vp]),
+    "dk_bn_backward": (i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "dk_gap_fwd": (i32, [vp, i32, i32, i32, vp, vp]),
+    "dk_gap_bwd": (i32, [vp, i32, i32, i32, vp, vp]),
     "dk_add_bf16": (i32, [vp, vp, vp, i64, i32, vp]),
     "dk_label_index": (i32, [vp, i32, i32, f32, i32, vp, vp, vp, vp]),
     # fabric

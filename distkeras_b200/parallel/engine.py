@@ -27,7 +27,8 @@ import numpy as np
 import torch
 
 from .. import _native as N
-from ..models.core import (Activation, Conv2D, Dense, Dropout, Flatten, MaxPooling2D, Sequential)
+from ..models.core import (Activation, BatchNormalization, Conv2D, Dense, Dropout, Flatten, GlobalAveragePooling2D,
+                           MaxPooling2D, ResidualBlock, Sequential)
 from ..ops.flat_optim import FlatOptimizer, OptimizerSpec
 from .replica import Replica
 
@@ -43,16 +44,45 @@ class UnsupportedByNativeEngine(Exception):
 
 
 class _Block:
-    """One lowered layer group."""
+    """One lowered layer group (a node of the native program)."""
 
     def __init__(self, kind: str):
-        self.kind = kind  # dense | conv | pool | flatten
+        self.kind = kind  # dense | conv | pool | flatten | bn | gap | res
         self.act: Optional[str] = None
         self.drop_p = 0.0
+        self.use_bias = True
+
+
+def _conv_block(layer_index, layer: Conv2D, in_shape, out_shape) -> _Block:
+    b = _Block("conv")
+    b.layer_index = layer_index
+    b.seg_prefix = ""
+    b.in_shape, b.out_shape = tuple(in_shape), tuple(out_shape)
+    b.kh, b.kw = layer.kernel_size
+    b.stride, b.pad = layer.strides[0], layer.pad_amount()
+    b.k_in = b.kh * b.kw * int(in_shape[-1])
+    b.n_out = layer.filters
+    b.act = layer.activation or "linear"
+    b.use_bias = layer.use_bias
+    if b.n_out % 8 != 0:
+        raise UnsupportedByNativeEngine("Conv2D filters must be a multiple of 8")
+    return b
+
+
+def _bn_block(layer_index, layer: BatchNormalization, shape, prefix="") -> _Block:
+    b = _Block("bn")
+    b.layer_index, b.seg_prefix = layer_index, prefix
+    b.shape = tuple(shape)
+    b.channels = int(shape[-1])
+    b.eps, b.momentum = layer.epsilon, layer.momentum
+    b.act = "linear"
+    if b.channels % 8 != 0:
+        raise UnsupportedByNativeEngine("BatchNormalization channels must be a multiple of 8")
+    return b
 
 
 def _group_layers(model: Sequential) -> List[_Block]:
-    """Fold Activation / Dropout layers into the preceding Dense / Conv block."""
+    """Fold Activation / Dropout layers into the preceding block; expand residual blocks."""
     blocks: List[_Block] = []
     model.build()
     for li, layer in enumerate(model.layers):
@@ -61,23 +91,12 @@ def _group_layers(model: Sequential) -> List[_Block]:
             if len(in_shape) != 1:
                 raise UnsupportedByNativeEngine("Dense on non-flat input")
             b = _Block("dense")
-            b.layer_index, b.k_in, b.n_out = li, int(in_shape[0]), layer.units
+            b.layer_index, b.k_in, b.n_out, b.seg_prefix = li, int(in_shape[0]), layer.units, ""
             b.act = layer.activation or "linear"
             b.use_bias = layer.use_bias
             blocks.append(b)
         elif isinstance(layer, Conv2D):
-            b = _Block("conv")
-            b.layer_index = li
-            b.in_shape, b.out_shape = tuple(in_shape), tuple(out_shape)
-            b.kh, b.kw = layer.kernel_size
-            b.stride, b.pad = layer.strides[0], layer.pad_amount()
-            b.k_in = b.kh * b.kw * int(in_shape[-1])
-            b.n_out = layer.filters
-            b.act = layer.activation or "linear"
-            b.use_bias = layer.use_bias
-            if b.n_out % 8 != 0:
-                raise UnsupportedByNativeEngine("Conv2D filters must be a multiple of 8")
-            blocks.append(b)
+            blocks.append(_conv_block(li, layer, in_shape, out_shape))
         elif isinstance(layer, MaxPooling2D):
             if layer.pool_size[0] != layer.pool_size[1] or layer.strides != layer.pool_size:
                 raise UnsupportedByNativeEngine("only square non-overlapping max-pooling")
@@ -85,10 +104,35 @@ def _group_layers(model: Sequential) -> List[_Block]:
             b.in_shape, b.out_shape, b.k = tuple(in_shape), tuple(out_shape), layer.pool_size[0]
             blocks.append(b)
         elif isinstance(layer, Flatten):
-            b = _Block("flatten")
+            blocks.append(_Block("flatten"))
+        elif isinstance(layer, BatchNormalization):
+            if len(in_shape) != 3:
+                raise UnsupportedByNativeEngine("BatchNormalization on non-image input")
+            blocks.append(_bn_block(li, layer, in_shape))
+        elif isinstance(layer, GlobalAveragePooling2D):
+            b = _Block("gap")
+            b.in_shape = tuple(in_shape)
+            blocks.append(b)
+        elif isinstance(layer, ResidualBlock):
+            b = _Block("res")
+            b.layer_index = li
+            b.in_shape, b.out_shape = tuple(in_shape), tuple(out_shape)
+            mid = layer.conv1.output_shape(in_shape)
+            b.conv1 = _conv_block(li, layer.conv1, in_shape, mid)
+            b.conv1.seg_prefix = "conv1."
+            b.bn1 = _bn_block(li, layer.bn1, mid, "bn1.")
+            b.bn1.act = "relu"
+            b.conv2 = _conv_block(li, layer.conv2, mid, mid)
+            b.conv2.seg_prefix = "conv2."
+            b.bn2 = _bn_block(li, layer.bn2, mid, "bn2.")
+            b.proj = None
+            if layer._needs_proj(in_shape):
+                b.proj = _conv_block(li, layer.proj, in_shape, mid)
+                b.proj.seg_prefix = "proj."
+                b.bnp = _bn_block(li, layer.bnp, mid, "bnp.")
             blocks.append(b)
         elif isinstance(layer, Activation):
-            if not blocks or blocks[-1].kind not in ("dense", "conv") or blocks[-1].act not in (None, "linear"):
+            if not blocks or blocks[-1].kind not in ("dense", "conv", "bn") or blocks[-1].act not in (None, "linear"):
                 raise UnsupportedByNativeEngine("free-standing Activation")
             blocks[-1].act = layer.activation
         elif isinstance(layer, Dropout):
@@ -98,13 +142,15 @@ def _group_layers(model: Sequential) -> List[_Block]:
         else:
             raise UnsupportedByNativeEngine(f"layer {layer.class_name}")
     for b in blocks[:-1]:
-        if b.kind in ("dense", "conv") and b.act not in ("relu", "linear"):
+        if b.kind in ("dense", "conv", "bn") and b.act not in ("relu", "linear"):
             raise UnsupportedByNativeEngine(f"hidden activation {b.act!r}")
     last = blocks[-1]
     if last.kind != "dense" or last.act not in ("softmax", "linear", "sigmoid"):
         raise UnsupportedByNativeEngine("the model must end in a Dense softmax / linear / sigmoid head")
     if last.drop_p:
         raise UnsupportedByNativeEngine("dropout on the output layer")
+    if blocks[0].kind not in ("dense", "conv"):
+        raise UnsupportedByNativeEngine("the model must start with a Dense or Conv2D layer")
     return blocks
 
 
@@ -209,119 +255,60 @@ class NativeReplica(Replica):
     # lowering
     # ------------------------------------------------------------------------------------------
     def _lower(self) -> None:
-        B, lib = self.B, self.lib
+        """Lower the block list into the forward lists (training / inference / fused-pull) and the
+        backward list.  Every block contributes a forward emission and a backward closure."""
+        B = self.B
         F = self._input_feats
         in_shape = tuple(self.model.input_shape)
-        # activation record: dict(ptr, rows, cols, ld, nhwc shape or None, tensor)
         x0 = self._buf(B, _r8(F))
         cur = dict(t=x0, rows=B, cols=F, ld=_r8(F), nhwc=in_shape if len(in_shape) == 3 else None)
-        if cur["nhwc"] is not None and F % 8 != 0 and False:
-            pass
         first = self.blocks[0]
+        x0f = None
         if self.pull_center_ptr and first.kind == "dense" and first.k_in % 8 == 0 and F % 8 == 0:
             self.L_step_pull = self.lib.dk_engine_new_list(self.engine)
             x0f = self._buf(B, F, dtype=torch.float32)
-        lists = [l for l in (self.L_step, self.L_fwd, self.L_step_pull) if l >= 0]
-        train_lists = (self.L_step, self.L_step_pull)
-        for lst in lists:
+        self._x0f = x0f
+        self._lists = [l for l in (self.L_step, self.L_fwd, self.L_step_pull) if l >= 0]
+        self._train_lists = (self.L_step, self.L_step_pull)
+        self._pad_refresh: list = []
+        # BatchNorm reduction scratch: zeroed once per step, sliced per BN (forward + backward sums)
+        nbn = sum(4 * c for c in self._bn_channels())
+        self._bn_scratch = self._buf(max(nbn, 1), dtype=torch.float32)
+        self._bn_used = 0
+        for lst in self._lists:
+            if nbn:
+                self._add(lst, N.OP_MEMSET, [self._bn_scratch.data_ptr(), 0, nbn * 4])
             self._add(lst, N.OP_INPUT,
                       [-(SLOT_X + 1), self.in_dtype, B, F, x0.data_ptr(), cur["ld"], 0, 0,
-                       self.step_counter.data_ptr() if lst in train_lists else 0,
+                       self.step_counter.data_ptr() if lst in self._train_lists else 0,
                        x0f.data_ptr() if lst == self.L_step_pull else 0, F],
                       [self.scale, self.shift])
-        # padded weight shadows are refreshed at the top of every program
-        self._pad_refresh: list = []
-        wptr_f32 = self.W.data_ptr()
-        wb_ptr = self.Wb.data_ptr()
-        fwd_records = []
         nblocks = len(self.blocks)
+        backward = []  # (block, closure(grad, premasked, need_dx, prev_block) -> (grad_in, premasked_in))
         for bi, b in enumerate(self.blocks):
             is_last = bi == nblocks - 1
             if b.kind in ("dense", "conv"):
-                kseg = self._seg(b.layer_index, "kernel")
-                bseg = self._seg(b.layer_index, "bias") if b.use_bias else None
-                K, Nout = b.k_in, b.n_out
-                # bf16 weight shadow [Nout, K] with a TMA-legal leading dimension
-                if K % 8 == 0:
-                    b.wb_ptr, b.wb_ld = wb_ptr + 2 * kseg.offset, K
-                else:
-                    pad = self._buf(Nout, _r8(K))
-                    b.wb_ptr, b.wb_ld = pad.data_ptr(), _r8(K)
-                    self._pad_refresh.append((pad.data_ptr(), _r8(K) * 2, wb_ptr + 2 * kseg.offset, K * 2, K * 2, Nout))
-                b.kseg, b.bseg = kseg, bseg
-                b.inp = cur
-                if b.kind == "conv":
-                    H, Wd, Cin = b.in_shape
-                    OH, OW, _ = b.out_shape
-                    rows = B * OH * OW
-                    col = self._buf(rows, _r8(K))
-                    b.col = dict(t=col, rows=rows, cols=K, ld=_r8(K), nhwc=None)
-                    for lst in lists:
-                        self._add(lst, N.OP_IM2COL, [cur["t"].data_ptr(), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad,
-                                                     OH, OW, col.data_ptr(), _r8(K)])
-                    a_in = b.col
-                else:
-                    rows = B
-                    a_in = cur
-                b.a_in = a_in
-                if is_last:
-                    ldl = _r8(Nout) if self.loss_kind == "xent" else Nout  # fp32 rows 16-byte aligned for TMA
-                    out = self._buf(rows, ldl, dtype=torch.float32)
-                    rec = dict(t=out, rows=rows, cols=Nout, ld=ldl, nhwc=None)
-                else:
-                    out = self._buf(rows, _r8(Nout))
-                    rec = dict(t=out, rows=rows, cols=Nout, ld=_r8(Nout),
-                               nhwc=b.out_shape if b.kind == "conv" else None)
-                for lst in lists:
-                    ep = N.GemmEpilogue()
-                    ep.bias = (wptr_f32 + 4 * bseg.offset) if bseg is not None else None
-                    ep.act = 1 if b.act == "relu" else 0
-                    ep.d, ep.ldd, ep.d_fp32 = out.data_ptr(), rec["ld"], 1 if is_last else 0
-                    ep.alpha = 1.0
-                    if lst in train_lists and b.drop_p > 0:
-                        ep.drop_p = b.drop_p
-                        ep.drop_seed = (self.seed * 7919 + bi * 104729) & 0xFFFFFFFF
-                        ep.step = self.step_counter.data_ptr()
-                    if lst == self.L_step_pull and bi == 0:
-                        # pull fused into the first GEMM: B operand = this layer's block of the center
-                        # variable in the PS GPU's HBM; the kernel refreshes W / W1 / Wb on the way
-                        off = kseg.offset
-                        self.pull_segment = (off, kseg.size)
-                        r = self.lib.dk_engine_add_gemm_pull(
-                            self.engine, lst, C.c_void_p(x0f.data_ptr()), F, C.c_void_p(self.pull_center_ptr + 4 * off),
-                            K, rows, Nout, K, C.c_void_p(self.W.data_ptr() + 4 * off),
-                            C.c_void_p(self.W1.data_ptr() + 4 * off), C.c_void_p(self.Wb.data_ptr() + 2 * off),
-                            C.byref(ep))
-                        if r < 0:
-                            raise RuntimeError(f"dk_engine_add_gemm_pull failed: {r}")
-                        continue
-                    self._gemm(lst, a_in["t"].data_ptr(), a_in["ld"], b.wb_ptr, b.wb_ld, rows, Nout, K, 0, ep)
-                b.out = rec
-                cur = rec
+                cur, bw = self._emit_matmul(b, cur, bi, is_last)
             elif b.kind == "pool":
-                H, Wd, Cc = b.in_shape
-                OH, OW, _ = b.out_shape
-                out = self._buf(B * OH * OW, Cc)
-                rec = dict(t=out, rows=B * OH * OW, cols=Cc, ld=Cc, nhwc=b.out_shape)
-                for lst in lists:
-                    self._add(lst, N.OP_MAXPOOL_FWD, [cur["t"].data_ptr(), B, H, Wd, Cc, b.k, b.k, out.data_ptr()])
-                b.inp, b.out = cur, rec
-                cur = rec
+                cur, bw = self._emit_pool(b, cur)
             elif b.kind == "flatten":
-                if cur["ld"] != cur["cols"]:
-                    raise UnsupportedByNativeEngine("flatten of a padded activation")
-                feat = cur["rows"] * cur["cols"] // B
-                if feat % 8 != 0:
-                    raise UnsupportedByNativeEngine("flattened feature count must be a multiple of 8")
-                rec = dict(t=cur["t"], rows=B, cols=feat, ld=feat, nhwc=None)
-                b.inp, b.out = cur, rec
-                cur = rec
+                cur, bw = self._emit_flatten(b, cur)
+            elif b.kind == "bn":
+                cur, bw = self._emit_bn(b, cur)
+            elif b.kind == "gap":
+                cur, bw = self._emit_gap(b, cur)
+            elif b.kind == "res":
+                cur, bw = self._emit_res(b, cur, bi)
+            else:  # pragma: no cover
+                raise UnsupportedByNativeEngine(b.kind)
+            b.out = cur
+            backward.append((b, bw))
         self.logits = cur["t"]
         Cn = self.num_classes
+        ldl = cur["ld"]
         self.probs = self._buf(B, Cn, dtype=torch.float32)
         self._zero_labels = self._buf(B, dtype=torch.int32)
-        # inference tail: probabilities
-        self._add(self.L_fwd, N.OP_XENT, [self.logits.data_ptr(), _r8(Cn), self._zero_labels.data_ptr(), 0, B, Cn, 0, 0,
+        self._add(self.L_fwd, N.OP_XENT, [self.logits.data_ptr(), ldl, self._zero_labels.data_ptr(), 0, B, Cn, 0, 0,
                                           0, 0, self.probs.data_ptr(), 0, 0, 0])
         self._prepend_pad_refresh(self.L_fwd)
         if not self.training:
@@ -331,7 +318,7 @@ class NativeReplica(Replica):
         ldz = _r8(Cn)
         dz = self._buf(B, ldz)
         if self.loss_kind == "xent":
-            self._add(lst, N.OP_XENT, [self.logits.data_ptr(), _r8(Cn),
+            self._add(lst, N.OP_XENT, [self.logits.data_ptr(), ldl,
                                        0 if self.dense_labels else -(SLOT_Y + 1),
                                        -(SLOT_Y + 1) if self.dense_labels else 0,
                                        B, Cn, dz.data_ptr(), ldz, 0, 0, 0, self.hist.data_ptr(),
@@ -341,76 +328,265 @@ class NativeReplica(Replica):
                                         0, 0, self.hist.data_ptr(), self.step_counter.data_ptr(), self.hist_slots])
         self._add(lst, N.OP_MEMSET, [self.G.data_ptr(), 0, self.P * 4])
         # ---- backward ----
-        g_ptr = self.G.data_ptr()
         grad = dict(t=dz, rows=B, cols=Cn, ld=ldz)
         premasked = True  # dZ of the head is already w.r.t. the logits
-        first_param_block = next(i for i, b in enumerate(self.blocks) if b.kind in ("dense", "conv"))
         for bi in range(nblocks - 1, -1, -1):
-            b = self.blocks[bi]
-            if b.kind in ("dense", "conv"):
-                rows, K, Nout = b.out["rows"], b.k_in, b.n_out
-                if b.act == "relu" and not premasked:
-                    self._add(lst, N.OP_RELU_MASK, [grad["t"].data_ptr(), b.out["t"].data_ptr(), rows * grad["ld"]])
-                # parameter gradients only feed the optimizer: they run on the engine's side stream
-                # (a parallel branch of the captured graph) while the dgrad chain continues
-                self._add(lst, N.OP_FORK, [0])
-                # the last block of the backward chain has no dgrad to overlap with: its bias
-                # gradient stays on the main stream so it runs concurrently with the wgrad
-                colsum_on_side = bi != first_param_block
-                self.lib.dk_engine_set_build_stream(self.engine, 1 if colsum_on_side else 0)
-                if b.bseg is not None:
-                    self._add(lst, N.OP_COLSUM, [grad["t"].data_ptr(), rows, Nout, grad["ld"],
-                                                 g_ptr + 4 * b.bseg.offset], [1.0])
-                self.lib.dk_engine_set_build_stream(self.engine, 1)
-                # wgrad: dW[Nout, K] = dZ^T[Nout, rows] * In[rows, K]  (both operands MN-major views)
-                ep = N.GemmEpilogue()
-                ep.d, ep.ldd, ep.d_fp32, ep.alpha = g_ptr + 4 * b.kseg.offset, K, 1, 1.0
-                self._gemm(lst, grad["t"].data_ptr(), grad["ld"], b.a_in["t"].data_ptr(), b.a_in["ld"], Nout, K,
-                           rows, N.GEMM_A_MN | N.GEMM_B_MN, ep)
-                self.lib.dk_engine_set_build_stream(self.engine, 0)
-                if bi == first_param_block:
-                    break
-                # dgrad: dIn[rows, K] = dZ[rows, Nout] * W[Nout, K]   (W read as an MN-major B operand)
-                prev = self.blocks[bi - 1]
-                din = self._buf(rows, _r8(K))
-                ep = N.GemmEpilogue()
-                ep.d, ep.ldd, ep.alpha = din.data_ptr(), _r8(K), 1.0
-                fuse_mask = b.kind == "dense" and prev.kind == "dense" and prev.act == "relu"
-                if fuse_mask:
-                    ep.mask, ep.ld_mask = prev.out["t"].data_ptr(), prev.out["ld"]
-                    if prev.drop_p > 0:
-                        ep.alpha = 1.0 / (1.0 - prev.drop_p)
-                elif b.kind == "dense" and prev.kind == "dense" and prev.drop_p > 0:
-                    raise UnsupportedByNativeEngine("dropout after a non-ReLU dense layer")
-                self._gemm(lst, grad["t"].data_ptr(), grad["ld"], b.wb_ptr, b.wb_ld, rows, K, Nout, N.GEMM_B_MN, ep)
-                if b.kind == "conv":
-                    H, Wd, Cin = b.in_shape
-                    OH, OW, _ = b.out_shape
-                    dx = self._buf(B * H * Wd, Cin)
-                    self._add(lst, N.OP_COL2IM, [din.data_ptr(), _r8(K), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad,
-                                                 OH, OW, dx.data_ptr()])
-                    grad = dict(t=dx, rows=B * H * Wd, cols=Cin, ld=Cin)
-                    premasked = False
-                else:
-                    grad = dict(t=din, rows=rows, cols=K, ld=_r8(K))
-                    premasked = fuse_mask
-            elif b.kind == "pool":
-                H, Wd, Cc = b.in_shape
-                dx = self._buf(B * H * Wd, Cc)
-                self._add(lst, N.OP_MAXPOOL_BWD, [b.inp["t"].data_ptr(), b.out["t"].data_ptr(), grad["t"].data_ptr(),
-                                                  B, H, Wd, Cc, b.k, b.k, dx.data_ptr()])
-                grad = dict(t=dx, rows=B * H * Wd, cols=Cc, ld=Cc)
-                premasked = False
-            elif b.kind == "flatten":
-                inp = b.inp
-                grad = dict(t=grad["t"], rows=inp["rows"], cols=inp["cols"], ld=inp["ld"])
+            b, bw = backward[bi]
+            prev = self.blocks[bi - 1] if bi > 0 else None
+            grad, premasked = bw(grad, premasked, bi > 0, prev)
+            if bi == 0:
+                break
         # ---- optimizer (one fused launch over the flat buffer, emits the bf16 shadow) ----
         self._add(lst, N.OP_JOIN, [0])
         o = self.opt
-        self._add(lst, N.OP_OPTIM, [N.OPT_KINDS[o.kernel_kind], self.W.data_ptr(), g_ptr, N.ptr(o.s0), N.ptr(o.s1),
-                                    self.Wb.data_ptr(), self.P, int(o.nesterov), self.step_counter.data_ptr()],
+        self._add(lst, N.OP_OPTIM, [N.OPT_KINDS[o.kernel_kind], self.W.data_ptr(), self.G.data_ptr(), N.ptr(o.s0),
+                                    N.ptr(o.s1), self.Wb.data_ptr(), self.P, int(o.nesterov),
+                                    self.step_counter.data_ptr()],
                   [o.lr, o.p0, o.p1, o.eps, o.decay, 1.0])
         self._prepend_pad_refresh(lst)
+
+    def _bn_channels(self) -> List[int]:
+        out = []
+        for b in self.blocks:
+            if b.kind == "bn":
+                out.append(b.channels)
+            elif b.kind == "res":
+                out += [b.bn1.channels, b.bn2.channels] + ([b.bnp.channels] if b.proj is not None else [])
+        return out
+
+    def _bn_slice(self, floats: int) -> int:
+        ptr = self._bn_scratch.data_ptr() + 4 * self._bn_used
+        self._bn_used += floats
+        return ptr
+
+    # -- Dense / Conv2D -----------------------------------------------------------------------------
+    def _emit_matmul(self, b: _Block, cur: dict, bi: int, is_last: bool):
+        B, lists = self.B, self._lists
+        wptr_f32, wb_ptr, g_ptr = self.W.data_ptr(), self.Wb.data_ptr(), (self.G.data_ptr() if self.training else 0)
+        kseg = self._seg(b.layer_index, b.seg_prefix + "kernel")
+        bseg = self._seg(b.layer_index, b.seg_prefix + "bias") if b.use_bias else None
+        K, Nout = b.k_in, b.n_out
+        if K % 8 == 0:  # bf16 weight shadow [Nout, K] with a TMA-legal leading dimension
+            wbp, wbld = wb_ptr + 2 * kseg.offset, K
+        else:
+            pad = self._buf(Nout, _r8(K))
+            wbp, wbld = pad.data_ptr(), _r8(K)
+            self._pad_refresh.append((pad.data_ptr(), _r8(K) * 2, wb_ptr + 2 * kseg.offset, K * 2, K * 2, Nout))
+        inp = cur
+        if b.kind == "conv":
+            H, Wd, Cin = b.in_shape
+            OH, OW, _ = b.out_shape
+            rows = B * OH * OW
+            col = self._buf(rows, _r8(K))
+            a_in = dict(t=col, rows=rows, cols=K, ld=_r8(K), nhwc=None)
+            for lst in lists:
+                self._add(lst, N.OP_IM2COL, [cur["t"].data_ptr(), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad,
+                                             OH, OW, col.data_ptr(), _r8(K)])
+        else:
+            rows = cur["rows"]
+            a_in = cur
+        if is_last:
+            ldl = _r8(Nout) if self.loss_kind == "xent" else Nout  # fp32 rows 16-byte aligned for TMA
+            out = self._buf(rows, ldl, dtype=torch.float32)
+            rec = dict(t=out, rows=rows, cols=Nout, ld=ldl, nhwc=None)
+        else:
+            out = self._buf(rows, _r8(Nout))
+            rec = dict(t=out, rows=rows, cols=Nout, ld=_r8(Nout), nhwc=b.out_shape if b.kind == "conv" else None)
+        for lst in lists:
+            ep = N.GemmEpilogue()
+            ep.bias = (wptr_f32 + 4 * bseg.offset) if bseg is not None else None
+            ep.act = 1 if b.act == "relu" else 0
+            ep.d, ep.ldd, ep.d_fp32 = out.data_ptr(), rec["ld"], 1 if is_last else 0
+            ep.alpha = 1.0
+            if lst in self._train_lists and b.drop_p > 0:
+                ep.drop_p = b.drop_p
+                ep.drop_seed = (self.seed * 7919 + bi * 104729) & 0xFFFFFFFF
+                ep.step = self.step_counter.data_ptr()
+            if lst == self.L_step_pull and bi == 0:
+                # pull fused into the first GEMM: B operand = this layer's block of the center
+                # variable in the PS GPU's HBM; the kernel refreshes W / W1 / Wb on the way
+                off = kseg.offset
+                self.pull_segment = (off, kseg.size)
+                r = self.lib.dk_engine_add_gemm_pull(
+                    self.engine, lst, C.c_void_p(self._x0f.data_ptr()), K, C.c_void_p(self.pull_center_ptr + 4 * off),
+                    K, rows, Nout, K, C.c_void_p(self.W.data_ptr() + 4 * off),
+                    C.c_void_p(self.W1.data_ptr() + 4 * off), C.c_void_p(self.Wb.data_ptr() + 2 * off), C.byref(ep))
+                if r < 0:
+                    raise RuntimeError(f"dk_engine_add_gemm_pull failed: {r}")
+                continue
+            self._gemm(lst, a_in["t"].data_ptr(), a_in["ld"], wbp, wbld, rows, Nout, K, 0, ep)
+        b.out_rec = rec
+
+        def backward(grad, premasked, need_dx, prev):
+            lst = self.L_bwd
+            if b.act == "relu" and not premasked:
+                self._add(lst, N.OP_RELU_MASK, [grad["t"].data_ptr(), rec["t"].data_ptr(), rows * grad["ld"]])
+            # parameter gradients only feed the optimizer: they run on the engine's side stream
+            # (a parallel branch of the captured graph) while the dgrad chain continues
+            self._add(lst, N.OP_FORK, [0])
+            self.lib.dk_engine_set_build_stream(self.engine, 1 if need_dx else 0)
+            if bseg is not None:
+                self._add(lst, N.OP_COLSUM, [grad["t"].data_ptr(), rows, Nout, grad["ld"], g_ptr + 4 * bseg.offset],
+                          [1.0])
+            self.lib.dk_engine_set_build_stream(self.engine, 1)
+            # wgrad: dW[Nout, K] = dZ^T[Nout, rows] * In[rows, K]  (both operands MN-major views)
+            ep = N.GemmEpilogue()
+            ep.d, ep.ldd, ep.d_fp32, ep.alpha = g_ptr + 4 * kseg.offset, K, 1, 1.0
+            self._gemm(lst, grad["t"].data_ptr(), grad["ld"], a_in["t"].data_ptr(), a_in["ld"], Nout, K, rows,
+                       N.GEMM_A_MN | N.GEMM_B_MN, ep)
+            self.lib.dk_engine_set_build_stream(self.engine, 0)
+            if not need_dx:
+                return None, True
+            # dgrad: dIn[rows, K] = dZ[rows, Nout] * W[Nout, K]   (W read as an MN-major B operand)
+            din = self._buf(rows, _r8(K))
+            ep = N.GemmEpilogue()
+            ep.d, ep.ldd, ep.alpha = din.data_ptr(), _r8(K), 1.0
+            fuse_mask = (b.kind == "dense" and prev is not None and prev.kind == "dense" and prev.act == "relu")
+            if fuse_mask:
+                ep.mask, ep.ld_mask = prev.out_rec["t"].data_ptr(), prev.out_rec["ld"]
+                if prev.drop_p > 0:
+                    ep.alpha = 1.0 / (1.0 - prev.drop_p)
+            elif b.kind == "dense" and prev is not None and prev.kind == "dense" and prev.drop_p > 0:
+                raise UnsupportedByNativeEngine("dropout after a non-ReLU dense layer")
+            self._gemm(lst, grad["t"].data_ptr(), grad["ld"], wbp, wbld, rows, K, Nout, N.GEMM_B_MN, ep)
+            if b.kind == "conv":
+                H, Wd, Cin = b.in_shape
+                OH, OW, _ = b.out_shape
+                dx = self._buf(B * H * Wd, Cin)
+                self._add(lst, N.OP_COL2IM, [din.data_ptr(), _r8(K), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad, OH, OW,
+                                             dx.data_ptr()])
+                return dict(t=dx, rows=B * H * Wd, cols=Cin, ld=Cin), False
+            return dict(t=din, rows=rows, cols=K, ld=_r8(K)), fuse_mask
+
+        return rec, backward
+
+    # -- pooling / reshapes ---------------------------------------------------------------------------
+    def _emit_pool(self, b: _Block, cur: dict):
+        B = self.B
+        H, Wd, Cc = b.in_shape
+        OH, OW, _ = b.out_shape
+        out = self._buf(B * OH * OW, Cc)
+        rec = dict(t=out, rows=B * OH * OW, cols=Cc, ld=Cc, nhwc=b.out_shape)
+        for lst in self._lists:
+            self._add(lst, N.OP_MAXPOOL_FWD, [cur["t"].data_ptr(), B, H, Wd, Cc, b.k, b.k, out.data_ptr()])
+        inp = cur
+
+        def backward(grad, premasked, need_dx, prev):
+            dx = self._buf(B * H * Wd, Cc)
+            self._add(self.L_bwd, N.OP_MAXPOOL_BWD, [inp["t"].data_ptr(), out.data_ptr(), grad["t"].data_ptr(), B, H,
+                                                     Wd, Cc, b.k, b.k, dx.data_ptr()])
+            return dict(t=dx, rows=B * H * Wd, cols=Cc, ld=Cc), False
+
+        return rec, backward
+
+    def _emit_flatten(self, b: _Block, cur: dict):
+        if cur["ld"] != cur["cols"]:
+            raise UnsupportedByNativeEngine("flatten of a padded activation")
+        feat = cur["rows"] * cur["cols"] // self.B
+        if feat % 8 != 0:
+            raise UnsupportedByNativeEngine("flattened feature count must be a multiple of 8")
+        rec = dict(t=cur["t"], rows=self.B, cols=feat, ld=feat, nhwc=None)
+        inp = cur
+
+        def backward(grad, premasked, need_dx, prev):
+            return dict(t=grad["t"], rows=inp["rows"], cols=inp["cols"], ld=inp["ld"]), premasked
+
+        return rec, backward
+
+    def _emit_gap(self, b: _Block, cur: dict):
+        B = self.B
+        H, Wd, Cc = b.in_shape
+        P = H * Wd
+        out = self._buf(B, Cc)
+        rec = dict(t=out, rows=B, cols=Cc, ld=Cc, nhwc=None)
+        for lst in self._lists:
+            self._add(lst, N.OP_GAP_FWD, [cur["t"].data_ptr(), B, P, Cc, out.data_ptr()])
+
+        def backward(grad, premasked, need_dx, prev):
+            dx = self._buf(B * P, Cc)
+            self._add(self.L_bwd, N.OP_GAP_BWD, [grad["t"].data_ptr(), B, P, Cc, dx.data_ptr()])
+            return dict(t=dx, rows=B * P, cols=Cc, ld=Cc), False
+
+        return rec, backward
+
+    # -- BatchNormalization (+ ReLU) ------------------------------------------------------------------
+    def _emit_bn(self, b: _Block, cur: dict):
+        if cur["ld"] != cur["cols"] or cur["cols"] != b.channels:
+            raise UnsupportedByNativeEngine("BatchNormalization on a padded activation")
+        rows, Cc = cur["rows"], b.channels
+        wf, g_ptr = self.W.data_ptr(), (self.G.data_ptr() if self.training else 0)
+        seg = {n: self._seg(b.layer_index, b.seg_prefix + n) for n in ("gamma", "beta", "moving_mean", "moving_variance")}
+        gamma, beta = wf + 4 * seg["gamma"].offset, wf + 4 * seg["beta"].offset
+        mm, mv = wf + 4 * seg["moving_mean"].offset, wf + 4 * seg["moving_variance"].offset
+        out = self._buf(rows, Cc)
+        rec = dict(t=out, rows=rows, cols=Cc, ld=Cc, nhwc=cur["nhwc"])
+        saved_mean, saved_invstd = self._buf(Cc, dtype=torch.float32), self._buf(Cc, dtype=torch.float32)
+        relu = 1 if b.act == "relu" else 0
+        fsum, bsum = self._bn_slice(2 * Cc), self._bn_slice(2 * Cc)
+        for lst in self._lists:
+            if lst in self._train_lists:
+                self._add(lst, N.OP_BN_FWD, [cur["t"].data_ptr(), rows, Cc, fsum, saved_mean.data_ptr(),
+                                             saved_invstd.data_ptr(), mm, mv, gamma, beta, relu, out.data_ptr()],
+                          [b.eps, b.momentum])
+            else:
+                self._add(lst, N.OP_BN_INF, [cur["t"].data_ptr(), rows, Cc, mm, mv, gamma, beta, relu, out.data_ptr()],
+                          [b.eps])
+        inp = cur
+        b.out_rec = rec
+
+        def backward(grad, premasked, need_dx, prev):
+            dx = self._buf(rows, Cc)
+            mask = out.data_ptr() if (relu and not premasked) else 0
+            self._add(self.L_bwd, N.OP_BN_BWD, [grad["t"].data_ptr(), inp["t"].data_ptr(), mask, rows, Cc,
+                                                saved_mean.data_ptr(), saved_invstd.data_ptr(), gamma, bsum,
+                                                g_ptr + 4 * seg["gamma"].offset, g_ptr + 4 * seg["beta"].offset,
+                                                dx.data_ptr()])
+            return dict(t=dx, rows=rows, cols=Cc, ld=Cc), True
+
+        return rec, backward
+
+    # -- residual block: conv-BN-ReLU-conv-BN (+ projection) , add, ReLU ---------------------------------
+    def _emit_res(self, b: _Block, cur: dict, bi: int):
+        x = cur
+        y1, bw_c1 = self._emit_matmul(b.conv1, x, bi, False)
+        a1, bw_b1 = self._emit_bn(b.bn1, y1)
+        y2, bw_c2 = self._emit_matmul(b.conv2, a1, bi, False)
+        z2, bw_b2 = self._emit_bn(b.bn2, y2)
+        if b.proj is not None:
+            yp, bw_cp = self._emit_matmul(b.proj, x, bi, False)
+            sc, bw_bp = self._emit_bn(b.bnp, yp)
+        else:
+            sc = x
+            if sc["ld"] != sc["cols"]:
+                raise UnsupportedByNativeEngine("identity shortcut on a padded activation")
+        rows, Cc = z2["rows"], z2["cols"]
+        out = self._buf(rows, Cc)
+        rec = dict(t=out, rows=rows, cols=Cc, ld=Cc, nhwc=b.out_shape)
+        for lst in self._lists:
+            self._add(lst, N.OP_ADD, [out.data_ptr(), z2["t"].data_ptr(), sc["t"].data_ptr(), rows * Cc, 1])
+        b.out_rec = rec
+
+        def backward(grad, premasked, need_dx, prev):
+            lst = self.L_bwd
+            if not premasked:
+                self._add(lst, N.OP_RELU_MASK, [grad["t"].data_ptr(), out.data_ptr(), rows * Cc])
+            g2, _ = bw_b2(grad, True, True, None)
+            ga1, _ = bw_c2(g2, True, True, None)
+            gy1, _ = bw_b1(ga1, False, True, None)       # ReLU of bn1 masked inside the BN backward
+            gx1, _ = bw_c1(gy1, True, need_dx, None)
+            if b.proj is not None:
+                gp, _ = bw_bp(grad, True, True, None)
+                gx2, _ = bw_cp(gp, True, need_dx, None)
+            else:
+                gx2 = grad
+            if not need_dx:
+                return None, True
+            n = gx1["rows"] * gx1["ld"]
+            dx = self._buf(gx1["rows"], gx1["ld"])
+            self._add(lst, N.OP_ADD, [dx.data_ptr(), gx1["t"].data_ptr(), gx2["t"].data_ptr(), n, 0])
+            return dict(t=dx, rows=gx1["rows"], cols=gx1["cols"], ld=gx1["ld"]), False
+
+        return rec, backward
 
     def pull_rest_ranges(self):
         """Flat ranges NOT covered by the fused-pull GEMM (pulled by the plain pull kernel)."""

@@ -24,7 +24,16 @@ def _cnn(seed=0):
                        Dense(32, activation="relu"), Dense(10, activation="softmax")], seed=seed)
 
 
-@pytest.mark.parametrize("maker,in_shape", [(_mlp, (64,)), (_cnn, (12, 12, 1))])
+def _resnet(seed=0):
+    from distkeras_b200.models import (Activation, BatchNormalization, Conv2D, Dense, GlobalAveragePooling2D,
+                                       MaxPooling2D, ResidualBlock, Sequential)
+
+    return Sequential([Conv2D(8, 3, padding="same", use_bias=False, input_shape=(16, 16, 3)), BatchNormalization(),
+                       Activation("relu"), MaxPooling2D(2), ResidualBlock(8), ResidualBlock(16, strides=2),
+                       GlobalAveragePooling2D(), Dense(10, activation="softmax")], seed=seed)
+
+
+@pytest.mark.parametrize("maker,in_shape", [(_mlp, (64,)), (_cnn, (12, 12, 1)), (_resnet, (16, 16, 3))])
 def test_native_gradients_match_autograd(maker, in_shape):
     from distkeras_b200.parallel.engine import NativeReplica
     from distkeras_b200.parallel.replica import TorchReplica
@@ -46,8 +55,10 @@ def test_native_gradients_match_autograd(maker, in_shape):
     g = nat.G.cpu()
     for seg in model.segments:
         a, b = g[seg.offset:seg.offset + seg.size], gref[seg.offset:seg.offset + seg.size]
+        if not seg.trainable:
+            continue
         err = float((a - b).norm() / (b.norm() + 1e-12))
-        assert err < 0.05, (seg.layer_index, seg.name, err)
+        assert err < (0.12 if maker is _resnet else 0.05), (seg.layer_index, seg.name, err)
     probs = nat.predict(x).cpu()
     want = torch.softmax(model.forward(x, logits=True), 1)
     assert torch.allclose(probs, want, atol=0.03)
@@ -179,16 +190,20 @@ def test_native_predictor_matches_autograd():
     assert torch.allclose(pred, torch.as_tensor(m.predict(x)), atol=0.02)
 
 
-def test_fabric_eager_worker_for_batchnorm_models():
-    """Models the native planner cannot lower (BatchNorm / residual) still train on the fabric:
-    autograd executor + in-kernel commit / pull (BN statistics travel through the PS)."""
+@pytest.mark.parametrize("native", [True, False])
+def test_fabric_residual_batchnorm_models(native):
+    """Residual / BatchNorm models train on the fabric (BN statistics travel through the PS, SURVEY
+    2.6): natively when every layer is lowerable, otherwise on the autograd executor with the same
+    in-kernel commit / pull."""
     from distkeras_b200.data import Dataset
-    from distkeras_b200.models import BatchNormalization, Conv2D, Dense, GlobalAveragePooling2D, ResidualBlock, Sequential
+    from distkeras_b200.models import (Activation, BatchNormalization, Conv2D, Dense, GlobalAveragePooling2D,
+                                       ResidualBlock, Sequential)
     from distkeras_b200.trainers import DynSGD
 
+    head = [Dense(4, activation="softmax")] if native else [Dense(8, activation="tanh"), Dense(4, activation="softmax")]
     m = Sequential([Conv2D(8, 3, padding="same", use_bias=False, input_shape=(8, 8, 3)), BatchNormalization(),
-                    ResidualBlock(8), ResidualBlock(16, strides=2), GlobalAveragePooling2D(),
-                    Dense(4, activation="softmax")], seed=0)
+                    Activation("relu"), ResidualBlock(8), ResidualBlock(16, strides=2), GlobalAveragePooling2D()]
+                   + head, seed=0)
     g = torch.Generator().manual_seed(0)
     y = torch.randint(0, 4, (512,), generator=g)
     x = torch.rand(512, 8, 8, 3, generator=g) + y.view(-1, 1, 1, 1).float() * 0.5
@@ -198,7 +213,7 @@ def test_fabric_eager_worker_for_batchnorm_models():
     t.backend = "fabric"
     model = t.train(ds)
     h = t.get_history()
-    assert t.fabric_stats[0]["executor"] == "FabricEagerWorker"
+    assert t.fabric_stats[0]["executor"] == ("FabricWorker" if native else "FabricEagerWorker")
     assert np.mean([r["history"][0] for r in h[-4:]]) < np.mean([r["history"][0] for r in h[:4]])
     assert t.num_updates() == 1 + len(h) // 2
     assert sum(t.staleness_histogram) == len(h) // 2

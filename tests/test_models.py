@@ -83,3 +83,17 @@ def test_uniform_weights():
     uniform_weights(m, (-0.5, 0.5))
     f = m.get_flat_weights()
     assert float(f.min()) >= -0.5 and float(f.max()) <= 0.5 and float(f.std()) > 0.2
+
+
+def test_native_planner_grouping_cpu():
+    """The native planner's block grouping is pure Python: check it without a GPU."""
+    from distkeras_b200.parallel.engine import UnsupportedByNativeEngine, _group_layers
+
+    assert [b.kind for b in _group_layers(mnist_mlp())] == ["dense"] * 3
+    assert [b.drop_p for b in _group_layers(mnist_mlp())] == [0.2, 0.2, 0.0]
+    kinds = [b.kind for b in _group_layers(resnet18((32, 32, 3), 10))]
+    assert kinds == ["conv", "bn", "pool"] + ["res"] * 8 + ["gap", "dense"]
+    res = [b for b in _group_layers(resnet18((32, 32, 3), 10)) if b.kind == "res"]
+    assert [r.proj is not None for r in res] == [False, False, True, False, True, False, True, False]
+    with pytest.raises(UnsupportedByNativeEngine):
+        _group_layers(Sequential([Dense(8, activation="tanh", input_shape=(4,)), Dense(2, activation="softmax")]))
