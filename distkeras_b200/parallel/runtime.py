@@ -55,6 +55,10 @@ class FabricWorker:
         self.alg = dict(algorithm)
         self.tau = int(self.alg["window"])
         self.region = region
+        # sharded parameter server: [(lo, hi, center_ptr)] slices of the flat center living on
+        # different GPUs' HBM (lifts the single-GPU NVLink ingress ceiling; README TODO of the
+        # reference: "multiple parameter servers").  None = the whole center is in `region`.
+        self.shards = None
         self.worker_id = int(worker_id)
         self.B = int(batch_size)
         self.comm = "commit_pull" if strict else comm
@@ -109,43 +113,57 @@ class FabricWorker:
     def _stream(self):
         return C.c_void_p(N.current_stream())
 
+    def set_shards(self, shards) -> None:
+        self.shards = list(shards)
+
     def _comm_ops(self) -> None:
         """Enqueue the window-boundary communication of the algorithm on the current stream."""
-        rep, reg, lib, k = self.rep, self.region, self.lib, self.alg["kind"]
-        c, ctrl = C.c_void_p(reg.center_ptr), C.c_void_p(reg.ctrl_ptr)
-        W, W1, Wb = rep.W.data_ptr(), rep.W1.data_ptr(), rep.Wb.data_ptr()
+        reg, lib = self.region, self.lib
+        ctrl = C.c_void_p(reg.ctrl_ptr)
         st = self._stream()
-        it = 0  # heartbeat value is informational; the window index is added host-side
         if self.strict:
             N.check(lib.dk_ps_lock_acquire(ctrl, self.ticket.data_ptr(), st), "lock_acquire")
-        if k in ("adag", "downpour", "dynsgd"):
-            scale = 1.0 / self.tau if k == "adag" else 1.0
-            sdev = None
-            if k == "dynsgd":
-                N.check(lib.dk_ps_ticket(ctrl, self.last_update.data_ptr(), self.scale_dev.data_ptr(), st), "ticket")
-                sdev = self.scale_dev.data_ptr()
-            if self.fused_pull:
-                # commit only: the pull happens inside the next window's first forward GEMM
-                N.check(lib.dk_ps_commit(c, W, W1, rep.P, scale, sdev, ctrl, self.worker_id, it, st), "commit")
-            elif self.comm == "exchange":
-                N.check(lib.dk_ps_exchange(c, W, W1, Wb, rep.P, scale, sdev, ctrl, self.worker_id, it,
-                                           self.last_update.data_ptr(), st), "exchange")
-            else:
-                N.check(lib.dk_ps_commit(c, W, W1, rep.P, scale, sdev, ctrl, self.worker_id, it, st), "commit")
-                N.check(lib.dk_ps_pull(c, W, W1, Wb, rep.P, ctrl, self.last_update.data_ptr(), st), "pull")
-        elif k in ("aeasgd", "eamsgd"):
-            N.check(lib.dk_ps_elastic(c, W, Wb, rep.P, float(self.alg["alpha"]), ctrl, self.worker_id, it, st),
-                    "elastic")
-        elif k == "experimental":
-            N.check(lib.dk_ps_damped_exchange(c, W, W1, Wb, rep.P, 1.0 / self.tau, float(self.alg["inv_lr"]), ctrl,
-                                              self.worker_id, it, st), "damped_exchange")
-        else:
-            raise ValueError(f"unknown algorithm {k!r}")
+        if self.alg["kind"] == "dynsgd":
+            N.check(lib.dk_ps_ticket(ctrl, self.last_update.data_ptr(), self.scale_dev.data_ptr(), st), "ticket")
+        shards = self.shards or [(0, self.rep.P, reg.center_ptr)]
+        for i, (lo, hi, cptr) in enumerate(shards):
+            # the control block (update counter, heartbeat) is bumped once per commit: by shard 0
+            self._comm_range(lo, hi, cptr, ctrl if i == 0 else None, st)
         if self.strict:
             N.check(lib.dk_ps_lock_release(ctrl, self.ticket.data_ptr(), st), "lock_release")
 
+    def _comm_range(self, lo: int, hi: int, center_ptr: int, ctrl, st) -> None:
+        rep, lib, k = self.rep, self.lib, self.alg["kind"]
+        n = hi - lo
+        c = C.c_void_p(center_ptr)
+        W, W1, Wb = rep.W.data_ptr() + 4 * lo, rep.W1.data_ptr() + 4 * lo, rep.Wb.data_ptr() + 2 * lo
+        it = 0
+        lu = self.last_update.data_ptr() if ctrl is not None else None
+        if k in ("adag", "downpour", "dynsgd"):
+            scale = 1.0 / self.tau if k == "adag" else 1.0
+            sdev = self.scale_dev.data_ptr() if k == "dynsgd" else None
+            if self.fused_pull:
+                # commit only: the pull happens inside the next window's first forward GEMM
+                N.check(lib.dk_ps_commit(c, W, W1, n, scale, sdev, ctrl, self.worker_id, it, st), "commit")
+            elif self.comm == "exchange":
+                N.check(lib.dk_ps_exchange(c, W, W1, Wb, n, scale, sdev, ctrl, self.worker_id, it, lu, st), "exchange")
+            else:
+                N.check(lib.dk_ps_commit(c, W, W1, n, scale, sdev, ctrl, self.worker_id, it, st), "commit")
+                N.check(lib.dk_ps_pull(c, W, W1, Wb, n, ctrl, lu, st), "pull")
+        elif k in ("aeasgd", "eamsgd"):
+            N.check(lib.dk_ps_elastic(c, W, Wb, n, float(self.alg["alpha"]), ctrl, self.worker_id, it, st), "elastic")
+        elif k == "experimental":
+            N.check(lib.dk_ps_damped_exchange(c, W, W1, Wb, n, 1.0 / self.tau, float(self.alg["inv_lr"]), ctrl,
+                                              self.worker_id, it, st), "damped_exchange")
+        else:
+            raise ValueError(f"unknown algorithm {k!r}")
+
     def comm_kernels(self) -> int:
         k = self.alg["kind"]
+        nshards = len(self.shards) if self.shards else 1
+        if nshards > 1:
+            per = 1 if (self.comm == "exchange" or k in ("aeasgd", "eamsgd", "experimental")) else 2
+            return nshards * per + (1 if k == "dynsgd" else 0) + (2 if self.strict else 0)
         if self.fused_pull:
             return 1 + len(self.rep.pull_rest_ranges()) + (1 if k == "dynsgd" else 0)
         n = 1 if (self.comm == "exchange" or k in ("aeasgd", "eamsgd", "experimental")) else 2
@@ -198,10 +216,12 @@ class FabricWorker:
     def initial_pull(self) -> None:
         """``pull(); set_weights(center)`` before the first batch (``workers.py:286-288``)."""
         rep, reg = self.rep, self.region
+        shards = self.shards or [(0, rep.P, reg.center_ptr)]
         with torch.cuda.stream(self.compute):
-            N.check(self.lib.dk_ps_pull(C.c_void_p(reg.center_ptr), rep.W.data_ptr(), rep.W1.data_ptr(),
-                                        rep.Wb.data_ptr(), rep.P, C.c_void_p(reg.ctrl_ptr),
-                                        self.last_update.data_ptr(), self._stream()), "pull")
+            for lo, hi, cptr in shards:
+                N.check(self.lib.dk_ps_pull(C.c_void_p(cptr), rep.W.data_ptr() + 4 * lo, rep.W1.data_ptr() + 4 * lo,
+                                            rep.Wb.data_ptr() + 2 * lo, hi - lo, C.c_void_p(reg.ctrl_ptr),
+                                            self.last_update.data_ptr(), self._stream()), "pull")
         self.compute.synchronize()
 
     def capture(self) -> None:
@@ -453,6 +473,26 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         info = None
     info = exchange_obj(info, 0)
     region = ps.region if rank == 0 else FabricRegion.open(info, local)
+    # optional sharded parameter server: slice r of the flat center lives in rank r's HBM
+    shard_regions, shards = [], None
+    native_supported = True
+    try:
+        from .engine import _group_layers
+
+        _group_layers(model)
+    except UnsupportedByNativeEngine:
+        native_supported = False  # same answer on every rank: the eager worker uses the unsharded center
+    if getattr(trainer, "sharded_ps", False) and world > 1 and native_supported:
+        P_total = model.num_params
+        per = ((P_total + world - 1) // world + 7) // 8 * 8
+        bounds = [(min(r * per, P_total), min((r + 1) * per, P_total)) for r in range(world)]
+        init_flat = model.get_flat_weights()
+        lo, hi = bounds[rank]
+        mine = FabricRegion.create(init_flat[lo:hi] if hi > lo else torch.zeros(8), local)
+        infos = [exchange_obj(mine.export() if r == rank else None, r) for r in range(world)]
+        shard_regions = [mine if r == rank else FabricRegion.open(infos[r], local) for r in range(world)]
+        shards = [(bounds[r][0], bounds[r][1], shard_regions[r].center_ptr) for r in range(world)
+                  if bounds[r][1] > bounds[r][0]]
     num_workers = min(trainer.num_workers, world)
     dedicated = bool(getattr(trainer, "dedicated_ps", False)) and world > 1
     worker_ranks = list(range(1, world)) if dedicated else list(range(world))
@@ -472,6 +512,8 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         except UnsupportedByNativeEngine:
             worker = FabricEagerWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid,
                                        trainer.batch_size, local, in_dtype, affine, **wkw)
+        if shards and isinstance(worker, FabricWorker):
+            worker.set_shards(shards)
         worker.initial_pull()
         worker.capture()
         static = getattr(trainer, "shard_mode", "dynamic" if trainer.parallelism_factor > 1 else "static") == "static"
@@ -534,8 +576,20 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         result["num_updates"] = ps.get_num_updates()
         result["staleness_hist"] = ps.staleness_histogram().tolist()
         ps.finalize()
+        if shards:  # assemble the center from the shards (rank 0 maps every shard)
+            flat = ps.get_model().get_flat_weights().clone()
+            for (lo, hi, _), reg_r in zip([(b[0], b[1], 0) for b in bounds if b[1] > b[0]],
+                                          [shard_regions[r] for r in range(world) if bounds[r][1] > bounds[r][0]]):
+                flat[lo:hi] = reg_r.read_center()[:hi - lo]
+            ps.get_model().set_flat_weights(flat)
         result["model"] = serialize_keras_model(ps.get_model())
     barrier()
+    for r, reg_r in enumerate(shard_regions):
+        if r != rank:
+            reg_r.close()
+    barrier()
+    if shard_regions:
+        shard_regions[rank].close()
     if rank != 0:
         region.close()
     else:
