@@ -568,6 +568,16 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
                  "h2d_bytes": worker.h2d_bytes, "d2h_bytes": worker.d2h_bytes, "seconds": time.time() - t0,
                  "device_ms": ev0.elapsed_time(ev1), "executor": type(worker).__name__}
         history = worker.history
+        # release the replica's device buffers / graphs before the next job in this process
+        try:
+            worker.rep.close()
+        except Exception:
+            pass
+        del worker
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
     else:
         barrier()
     barrier()
