@@ -81,7 +81,6 @@ __device__ __forceinline__ void gemm_epilogue(const CUtensorMap& tmap_d, const C
   constexpr int kChunk = BN < 32 ? 16 : 32;
   const bool tma_out = ep.tma_store != 0;
   const int esize = ep.d_fp32 ? 4 : 2;
-  const int group_cols = 128 / esize;                        // columns per 128-byte staging row
   // staging regions inside the (idle after the main loop) pipeline buffers
   const uint32_t out_region = smem_u32(smem) + quarter * (32 * BN * esize);
   const uint32_t mask_region = smem_u32(smem) + 4 * (32 * BN * esize) + quarter * (32 * BN * 2);

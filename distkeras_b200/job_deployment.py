@@ -17,7 +17,6 @@ from __future__ import annotations
 import binascii
 import json
 import multiprocessing as mp
-import os
 import threading
 import time
 import urllib.error

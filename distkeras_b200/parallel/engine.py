@@ -29,7 +29,7 @@ import torch
 from .. import _native as N
 from ..models.core import (Activation, BatchNormalization, Conv2D, Dense, Dropout, Flatten, GlobalAveragePooling2D,
                            MaxPooling2D, ResidualBlock, Sequential)
-from ..ops.flat_optim import FlatOptimizer, OptimizerSpec
+from ..ops.flat_optim import FlatOptimizer
 from .replica import Replica
 
 SLOT_X, SLOT_Y = 0, 1

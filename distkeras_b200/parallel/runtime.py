@@ -25,7 +25,6 @@ import tempfile
 import time
 from typing import List, Optional
 
-import numpy as np
 import torch
 
 from .. import _native as N
@@ -835,8 +834,6 @@ def train_ensemble_native(trainer, dataset: Dataset):
             torch.cuda.set_device(dev)
             m = master.copy()
             m.seed = (master.seed or 0) + 1 + i
-            from ..utils import uniform_weights  # noqa: F401  (ensembles differ by data shard + dropout stream)
-
             with torch.cuda.stream(torch.cuda.Stream(device=dev)):
                 try:
                     models[i], hists[i] = _sequential_native(trainer, parts[i], m, dev, i, trainer.num_epoch)

@@ -28,7 +28,7 @@ import torch
 
 from . import networking
 from .models.core import Sequential
-from .utils import deserialize_keras_model, serialize_keras_model
+from .utils import deserialize_keras_model
 
 
 def _to_flat_tensor(x, like: torch.Tensor) -> torch.Tensor:

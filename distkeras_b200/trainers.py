@@ -25,7 +25,6 @@ import threading
 import time
 from typing import List, Optional
 
-import numpy as np
 import torch
 
 from . import utils
@@ -149,9 +148,6 @@ class Trainer:
 
     def _maybe_shuffle(self, dataframe: Dataset, shuffle: bool) -> Dataset:
         return utils.shuffle(dataframe) if shuffle else dataframe
-
-    def _cpu_device(self, tid: int):
-        return "cpu"
 
     def _thread_device(self, tid: int):
         if self.backend != "thread" and torch.cuda.is_available():

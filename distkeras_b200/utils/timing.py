@@ -8,7 +8,7 @@ import json
 import logging
 import os
 import time
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 

@@ -26,7 +26,6 @@ import torch
 
 from . import networking
 from .data import Partition
-from .models.core import Sequential
 from .ops.flat_optim import OptimizerSpec
 from .utils import deserialize_keras_model, serialize_keras_model
 
