@@ -10,7 +10,7 @@ typedef uint16_t dk_bf16;
 #endif
 
 enum { DK_BF16 = 0, DK_F32 = 1 };
-enum { DK_GEMM_TF32 = 1, DK_GEMM_A_MN = 2, DK_GEMM_B_MN = 4, DK_GEMM_PERSISTENT = 8 };
+enum { DK_GEMM_TF32 = 1, DK_GEMM_A_MN = 2, DK_GEMM_B_MN = 4, DK_GEMM_PERSISTENT = 8, DK_GEMM_PAIR = 16 };
 
 // Fused epilogue description: out = mask( act( alpha * acc + bias ) )
 typedef struct DkGemmEpilogue {

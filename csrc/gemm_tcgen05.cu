@@ -944,6 +944,154 @@ static int launch_persistent(const GemmLaunch& L) {
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs on the SMs of one TPC compute a 256 x BN tile with ONE
+// tcgen05.mma stream issued by the leader.  Each CTA stages its own 128 rows of A and only HALF of
+// the B tile (BN/2 rows), so the shared-memory traffic per CTA (TMA writes + UMMA operand reads)
+// drops from 16+32 KB to 16+16 KB per k-block at BN = 256 and the L2 -> SM traffic for B halves.
+// TMA loads of both CTAs credit the leader's full barrier; tcgen05.commit multicasts the
+// "slot free" / "accumulator ready" arrivals to both CTAs.  K-major bf16 operands.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct PairSmem {
+  static constexpr int kABytes = kBlockM * 128;
+  static constexpr int kBBytes = (BN / 2) * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
+                 const GemmEpilogue ep, const int M, const int N, const int K) {
+  using S = PairSmem<BN, STAGES>;
+  constexpr int kBlockK = 64, kUmmaK = 16;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kIdesc = make_idesc(1u, 2 * kBlockM, BN);  // M = 256 across the pair
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* mask_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int n0 = blockIdx.y * BN;
+  const int m0 = pair * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
+  const int nb0 = n0 + static_cast<int>(rank) * (BN / 2);  // this CTA's half of the B tile
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    if (ep.tma_store) tma_prefetch_desc(&tmap_d);
+    if (ep.tma_mask) tma_prefetch_desc(&tmap_m);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(&mask_bar[q], 1);
+    fence_barrier_init();
+  }
+  cluster_sync_all();  // both CTAs' barriers exist before any remote arrival
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  DK_PDL_WAIT();
+  DK_PDL_TRIGGER();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);  // bytes of BOTH CTAs
+        tma_load_2d_2cta(sa, &tmap_a, kb * kBlockK, m0, &full_bar[stage]);
+        tma_load_2d_2cta(sb, &tmap_b, kb * kBlockK, nb0, &full_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_f16_2cta(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+          umma_commit_2cta(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit_2cta(tmem_full_bar);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    gemm_epilogue<BN>(tmap_d, tmap_m, ep, M, N, m0, n0, warp, lane, tmem_base, smem, tmem_full_bar, mask_bar);
+    tcgen05_fence_before();
+  }
+
+  cluster_sync_all();  // neither CTA may free TMEM / exit while the pair's MMAs or arrivals are in flight
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_pair(const GemmLaunch& L) {
+  using S = PairSmem<BN, STAGES>;
+  auto kern = gemm_pair_kernel<BN, STAGES>;
+  static bool configured[64] = {};
+  int dev = 0;
+  DK_HOST_CHECK(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    DK_HOST_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured[dev & 63] = true;
+  }
+  GemmEpilogue ep = L.ep;
+  const int esize = ep.d_fp32 ? 4 : 2;
+  const bool fits = 4 * 32 * BN * esize + (L.tm != nullptr ? 4 * 32 * BN * 2 : 0) <= STAGES * S::kStageBytes;
+  ep.tma_store = (L.td != nullptr && fits && ep.dt == nullptr) ? 1 : 0;
+  ep.tma_mask = (L.tm != nullptr && ep.tma_store) ? 1 : 0;
+  const int pairs = (L.M + 2 * kBlockM - 1) / (2 * kBlockM);
+  dim3 grid(2 * pairs, (L.N + BN - 1) / BN, 1);
+  DK_HOST_CHECK(launch_kernel_cluster(kern, grid, dim3(kGemmThreads), S::kTotal, L.stream, 2u, *L.ta, *L.tb,
+                                      ep.tma_store ? *L.td : *L.ta, ep.tma_mask ? *L.tm : *L.ta, ep, L.M, L.N, L.K));
+  return 0;
+}
+
 }  // namespace dk
 
 extern "C" {
@@ -1008,6 +1156,12 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
   L.stream = reinterpret_cast<cudaStream_t>(stream);
   if (M <= 0 || N <= 0 || K <= 0) return -3;
   const bool tf32 = flags & DK_GEMM_TF32, amn = flags & DK_GEMM_A_MN, bmn = flags & DK_GEMM_B_MN;
+  if ((flags & DK_GEMM_PAIR) && !tf32 && !amn && !bmn && splits <= 1) {
+    // B tensor map must have been encoded with box_rows = bn / 2 (each CTA loads half of the tile)
+    if (bn == 256) return dk::launch_pair<256, 6>(L);
+    if (bn == 128) return dk::launch_pair<128, 8>(L);
+    return -4;
+  }
   if ((flags & DK_GEMM_PERSISTENT) && !tf32 && !amn && L.td != nullptr && !ep->d_fp32 && ep->dt == nullptr &&
       splits <= 1 && (ep->mask == nullptr || L.tm != nullptr) && !ep->bias_along_m) {
     if (bn == 256) return bmn ? dk::launch_persistent<256, 3, true>(L) : dk::launch_persistent<256, 3, false>(L);
@@ -1089,7 +1243,7 @@ int dk_gemm_encode_operands(void* tmap_a, void* tmap_b, const void* A, long lda,
                                  : dk_tmap_encode_2d(tmap_a, A, dt, M, K, lda, dk::kBlockM);
   if (r != 0) return r;
   return (flags & DK_GEMM_B_MN) ? dk_tmap_encode_2d(tmap_b, B, dt, K, N, ldb, 64)
-                                : dk_tmap_encode_2d(tmap_b, B, dt, N, K, ldb, bn);
+                                : dk_tmap_encode_2d(tmap_b, B, dt, N, K, ldb, (flags & DK_GEMM_PAIR) ? bn / 2 : bn);
 }
 
 

@@ -182,7 +182,15 @@ int main(int argc, char** argv) {
   // tf32
   fails += run_case(128, 128, 64, DK_GEMM_TF32, 2, 128, false);
   fails += run_case(1000, 256, 784, DK_GEMM_TF32, 3, 128, true);
+  // cta_group::2 CTA-pair kernel
+  fails += run_case(256, 256, 64, DK_GEMM_PAIR, 0, 256, false);
+  fails += run_case(256, 256, 512, DK_GEMM_PAIR, 0, 256, false);
+  fails += run_case(512, 384, 320, DK_GEMM_PAIR, 0, 128, false);
+  fails += run_case(1000, 1000, 784, DK_GEMM_PAIR, 0, 256, true);
+  fails += run_case(300, 200, 136, DK_GEMM_PAIR, 2, 256, false);
   if (!quick) {
+    fails += run_case(8192, 8192, 8192, DK_GEMM_PAIR, 0, 256, true);
+    fails += run_case(16384, 1000, 784, DK_GEMM_PAIR, 0, 256, true);
     fails += run_case(8192, 8192, 8192, 0, 0, 256, true);
     fails += run_case(8192, 1000, 784, 0, 1, 128, true);
     fails += run_case(8192, 1000, 784, 0, 0, 128, true);

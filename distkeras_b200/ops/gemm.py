@@ -11,7 +11,8 @@ from .. import _native as N
 
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
             bias_along_m: bool = False, relu: bool = False, mask: Optional[torch.Tensor] = None, out_fp32: bool = False,
-            alpha: float = 1.0, bn: int = 0, tf32: bool = False, splits: int = 1, persistent: bool = False) -> torch.Tensor:
+            alpha: float = 1.0, bn: int = 0, tf32: bool = False, splits: int = 1, persistent: bool = False,
+            pair: bool = False) -> torch.Tensor:
     """``D[M, N] = epilogue(A B^T)``.
 
     ``a`` is ``[M, K]`` (K-major) or, with ``a_mn``, the MN-major storage ``[K, M]``; same for ``b``
@@ -30,6 +31,9 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool 
         ep.mask, ep.ld_mask = mask.data_ptr(), mask.stride(0)
     ep.d, ep.ldd, ep.d_fp32, ep.alpha = out.data_ptr(), Nn, int(out_fp32), alpha
     flags = (N.GEMM_TF32 if tf32 else 0) | (N.GEMM_A_MN if a_mn else 0) | (N.GEMM_B_MN if b_mn else 0)
+    if pair:  # cta_group::2: two CTAs share one 256 x bn tile
+        flags |= N.GEMM_PAIR
+        bn = bn or (256 if Nn > 128 else 128)
     if persistent:
         flags |= N.GEMM_PERSISTENT
         bn = bn or (256 if Nn > 128 else (128 if Nn > 64 else 64))

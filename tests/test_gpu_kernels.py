@@ -278,3 +278,16 @@ def test_gemm_persistent(N, M, Nn, K, bn):
         got = gemm_tn(a, b.t().contiguous(), b_mn=True, mask=mask, alpha=1.5, persistent=True, bn=bn)
         want = torch.where(mask.float() > 0, 1.5 * (a.float() @ b.float().t()), torch.zeros_like(ref))
         assert torch.allclose(got.float(), want, atol=0.05 * K ** 0.5, rtol=2e-2)
+
+
+@pytest.mark.parametrize("M,Nn,K,bn", [(256, 256, 64, 256), (1000, 1000, 784, 256), (512, 384, 320, 128), (4096, 2048, 1024, 256)])
+def test_gemm_cta_pair(N, M, Nn, K, bn):
+    """cta_group::2 kernel: a CTA pair computes one 256 x bn tile (each CTA stages half of B)."""
+    from distkeras_b200.ops.gemm import gemm_tn
+
+    torch.manual_seed(13)
+    a, b = bf(torch.randn(M, K, device="cuda")), bf(torch.randn(Nn, K, device="cuda"))
+    bias = torch.randn(Nn, device="cuda")
+    out = gemm_tn(a, b, bias=bias, relu=True, pair=True, bn=bn, out_fp32=True)
+    ref = torch.relu(a.float() @ b.float().t() + bias)
+    assert torch.allclose(out, ref, atol=2e-3 * K ** 0.5, rtol=1e-3)
