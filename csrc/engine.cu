@@ -311,6 +311,20 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
   }
   if (bn <= 0) bn = (splits == 0 && splitk_ok) ? dk_gemm_pick_bn_splitk(M, N, K) : dk_gemm_pick_bn2(M, N);
   if ((flags & DK_GEMM_B_MN) && bn < 64) bn = 64;
+  // large wgrad GEMMs (both operands MN-major, split-K fp32 accumulation) run on CTA pairs
+  // (cta_group::2: each CTA stages half of the B tile, one 256-row MMA per pair); DK_PAIR=0 disables
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* pe = getenv("DK_PAIR");
+    pair_env = (pe != nullptr && pe[0] == '0') ? 0 : 1;
+  }
+  const bool pair = pair_env && splits == 0 && splitk_ok && bn == 256 && M >= 512 &&
+                    (flags & (DK_GEMM_A_MN | DK_GEMM_B_MN)) == (DK_GEMM_A_MN | DK_GEMM_B_MN) &&
+                    !(flags & (DK_GEMM_TF32 | DK_GEMM_PERSISTENT));
+  if (pair) {
+    flags |= DK_GEMM_PAIR;
+    splits = dk_gemm_pick_splits_pair(M, N, K, bn);
+  }
   int r = dk_gemm_encode_operands(&op.ta, &op.tb, A, lda, B, ldb, M, N, K, bn, flags);
   if (r != 0) return r;
   op.ep = *ep;

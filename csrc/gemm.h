@@ -53,6 +53,7 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
                        const DkGemmEpilogue* ep, int M, int N, int K, int bn, int flags, int splits, void* stream);
 int dk_gemm_encode_output(void* tmap_d, const void* D, long ldd, int M, int N, int d_fp32);
 int dk_gemm_pick_splits(int M, int N, int K, int bn, int tf32);
+int dk_gemm_pick_splits_pair(int M, int N, int K, int bn);
 int dk_gemm_tn_ex(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M, int N,
                   int K, int flags, int bn, int splits, void* stream);
 int dk_gemm_pull_launch(const void* tmap_a, const void* tmap_b, const void* tmap_d, const DkGemmEpilogue* ep, int M,

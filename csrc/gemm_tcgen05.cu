@@ -962,15 +962,17 @@ struct PairSmem {
   static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool AMN, bool BMN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
-                 const GemmEpilogue ep, const int M, const int N, const int K) {
+                 const GemmEpilogue ep, const int M, const int N, const int K, const int kb_per_split) {
   using S = PairSmem<BN, STAGES>;
   constexpr int kBlockK = 64, kUmmaK = 16;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
-  constexpr uint32_t kIdesc = make_idesc(1u, 2 * kBlockM, BN);  // M = 256 across the pair
+  constexpr uint32_t kIdesc = make_idesc(1u, 2 * kBlockM, BN) | (AMN ? (1u << 15) : 0u) |
+                              (BMN ? (1u << 16) : 0u);  // M = 256 across the pair
+  static_assert(!BMN || BN >= 128, "MN-major B halves need BN / 2 >= 64");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -988,7 +990,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int n0 = blockIdx.y * BN;
   const int m0 = pair * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
   const int nb0 = n0 + static_cast<int>(rank) * (BN / 2);  // this CTA's half of the B tile
-  const int num_kb = (K + kBlockK - 1) / kBlockK;
+  const int total_kb = (K + kBlockK - 1) / kBlockK;
+  const int kb_begin = blockIdx.z * kb_per_split;            // split-K slice (uniform for the pair)
+  const int kb_end = min(total_kb, kb_begin + kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+  if (num_kb <= 0) return;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -1019,13 +1025,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
         if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);  // bytes of BOTH CTAs
-        tma_load_2d_2cta(sa, &tmap_a, kb * kBlockK, m0, &full_bar[stage]);
-        tma_load_2d_2cta(sb, &tmap_b, kb * kBlockK, nb0, &full_bar[stage]);
+        if constexpr (AMN) {
+#pragma unroll
+          for (int c = 0; c < kBlockM / 64; ++c)
+            tma_load_2d_2cta(sa + c * 8192, &tmap_a, m0 + c * 64, kb * kBlockK, &full_bar[stage]);
+        } else {
+          tma_load_2d_2cta(sa, &tmap_a, kb * kBlockK, m0, &full_bar[stage]);
+        }
+        if constexpr (BMN) {
+#pragma unroll
+          for (int c = 0; c < BN / 2 / 64; ++c)
+            tma_load_2d_2cta(sb + c * 8192, &tmap_b, nb0 + c * 64, kb * kBlockK, &full_bar[stage]);
+        } else {
+          tma_load_2d_2cta(sb, &tmap_b, kb * kBlockK, nb0, &full_bar[stage]);
+        }
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -1042,11 +1060,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
-          const uint64_t adesc = make_smem_desc_sw128(sa);
-          const uint64_t bdesc = make_smem_desc_sw128(sb);
+          const uint64_t adesc = AMN ? make_smem_desc_sw128_mn(sa) : make_smem_desc_sw128(sa);
+          const uint64_t bdesc = BMN ? make_smem_desc_sw128_mn(sb) : make_smem_desc_sw128(sb);
+          constexpr uint32_t kAStep = AMN ? (2048 >> 4) : 2;
+          constexpr uint32_t kBStep = BMN ? (2048 >> 4) : 2;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_f16_2cta(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+            umma_f16_2cta(tmem_base, adesc + kAStep * k, bdesc + kBStep * k, kIdesc, (kb | k) != 0);
           umma_commit_2cta(&empty_bar[stage]);
           if (kb == num_kb - 1) umma_commit_2cta(tmem_full_bar);
         }
@@ -1069,10 +1089,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool AMN = false, bool BMN = false>
 static int launch_pair(const GemmLaunch& L) {
   using S = PairSmem<BN, STAGES>;
-  auto kern = gemm_pair_kernel<BN, STAGES>;
+  auto kern = gemm_pair_kernel<BN, STAGES, AMN, BMN>;
   static bool configured[64] = {};
   int dev = 0;
   DK_HOST_CHECK(cudaGetDevice(&dev));
@@ -1086,9 +1106,16 @@ static int launch_pair(const GemmLaunch& L) {
   ep.tma_store = (L.td != nullptr && fits && ep.dt == nullptr) ? 1 : 0;
   ep.tma_mask = (L.tm != nullptr && ep.tma_store) ? 1 : 0;
   const int pairs = (L.M + 2 * kBlockM - 1) / (2 * kBlockM);
-  dim3 grid(2 * pairs, (L.N + BN - 1) / BN, 1);
+  const int total_kb = (L.K + 63) / 64;
+  int splits = L.splits < 1 ? 1 : L.splits;
+  if (splits > total_kb) splits = total_kb;
+  const int kb_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + kb_per_split - 1) / kb_per_split;
+  if (splits > 1 && !ep.d_fp32) return -6;
+  dim3 grid(2 * pairs, (L.N + BN - 1) / BN, splits);
   DK_HOST_CHECK(launch_kernel_cluster(kern, grid, dim3(kGemmThreads), S::kTotal, L.stream, 2u, *L.ta, *L.tb,
-                                      ep.tma_store ? *L.td : *L.ta, ep.tma_mask ? *L.tm : *L.ta, ep, L.M, L.N, L.K));
+                                      ep.tma_store ? *L.td : *L.ta, ep.tma_mask ? *L.tm : *L.ta, ep, L.M, L.N, L.K,
+                                      kb_per_split));
   return 0;
 }
 
@@ -1156,10 +1183,18 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
   L.stream = reinterpret_cast<cudaStream_t>(stream);
   if (M <= 0 || N <= 0 || K <= 0) return -3;
   const bool tf32 = flags & DK_GEMM_TF32, amn = flags & DK_GEMM_A_MN, bmn = flags & DK_GEMM_B_MN;
-  if ((flags & DK_GEMM_PAIR) && !tf32 && !amn && !bmn && splits <= 1) {
-    // B tensor map must have been encoded with box_rows = bn / 2 (each CTA loads half of the tile)
-    if (bn == 256) return dk::launch_pair<256, 6>(L);
-    if (bn == 128) return dk::launch_pair<128, 8>(L);
+  if ((flags & DK_GEMM_PAIR) && !tf32) {
+    // K-major B tensor maps must have been encoded with box_rows = bn / 2 (each CTA loads half the tile)
+    if (!amn && !bmn) {
+      if (bn == 256) return dk::launch_pair<256, 6>(L);
+      if (bn == 128) return dk::launch_pair<128, 8>(L);
+    } else if (amn && bmn) {
+      if (bn == 256) return dk::launch_pair<256, 6, true, true>(L);
+      if (bn == 128) return dk::launch_pair<128, 8, true, true>(L);
+    } else if (!amn && bmn) {
+      if (bn == 256) return dk::launch_pair<256, 6, false, true>(L);
+      if (bn == 128) return dk::launch_pair<128, 8, false, true>(L);
+    }
     return -4;
   }
   if ((flags & DK_GEMM_PERSISTENT) && !tf32 && !amn && L.td != nullptr && !ep->d_fp32 && ep->dt == nullptr &&
@@ -1225,6 +1260,17 @@ int dk_gemm_encode_output(void* tmap_d, const void* D, long ldd, int M, int N, i
 }
 
 // Split-K factor that fills the GPU (2 CTAs / SM) without making the slices too short.
+// split factor for the CTA-pair kernel: 74 pairs fill the 148 SMs
+int dk_gemm_pick_splits_pair(int M, int N, int K, int bn) {
+  const int tiles = ((M + 255) / 256) * ((N + bn - 1) / bn);
+  const int total_kb = (K + 63) / 64;
+  int splits = 74 / tiles;
+  if (splits > total_kb / 4) splits = total_kb / 4;
+  if (splits < 1) splits = 1;
+  if (splits > 32) splits = 32;
+  return splits;
+}
+
 int dk_gemm_pick_splits(int M, int N, int K, int bn, int tf32) {
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
   const int total_kb = (K + (tf32 ? 32 : 64) - 1) / (tf32 ? 32 : 64);

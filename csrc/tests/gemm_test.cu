@@ -188,6 +188,13 @@ int main(int argc, char** argv) {
   fails += run_case(512, 384, 320, DK_GEMM_PAIR, 0, 128, false);
   fails += run_case(1000, 1000, 784, DK_GEMM_PAIR, 0, 256, true);
   fails += run_case(300, 200, 136, DK_GEMM_PAIR, 2, 256, false);
+  fails += run_case(256, 256, 128, DK_GEMM_PAIR | DK_GEMM_A_MN | DK_GEMM_B_MN, 4, 256, false);
+  fails += run_case(256, 256, 128, DK_GEMM_PAIR | DK_GEMM_B_MN, 4, 256, false);
+  fails += run_case(1000, 784, 4096, DK_GEMM_PAIR | DK_GEMM_A_MN | DK_GEMM_B_MN, 4, 256, true, 4);
+  fails += run_case(1000, 784, 16384, DK_GEMM_PAIR | DK_GEMM_A_MN | DK_GEMM_B_MN, 4, 256, true, 4);
+  fails += run_case(1000, 784, 16384, DK_GEMM_A_MN | DK_GEMM_B_MN, 4, 256, true, 4);
+  fails += run_case(200, 1000, 16384, DK_GEMM_PAIR | DK_GEMM_A_MN | DK_GEMM_B_MN, 4, 256, true, 18);
+  fails += run_case(200, 1000, 16384, DK_GEMM_A_MN | DK_GEMM_B_MN, 4, 256, true, 18);
   if (!quick) {
     fails += run_case(8192, 8192, 8192, DK_GEMM_PAIR, 0, 256, true);
     fails += run_case(16384, 1000, 784, DK_GEMM_PAIR, 0, 256, true);

@@ -291,3 +291,15 @@ def test_gemm_cta_pair(N, M, Nn, K, bn):
     out = gemm_tn(a, b, bias=bias, relu=True, pair=True, bn=bn, out_fp32=True)
     ref = torch.relu(a.float() @ b.float().t() + bias)
     assert torch.allclose(out, ref, atol=2e-3 * K ** 0.5, rtol=1e-3)
+
+
+@pytest.mark.parametrize("M,Nn,K,bn,splits", [(1000, 784, 4096, 256, 4), (512, 256, 1024, 128, 2), (300, 520, 2048, 256, 1)])
+def test_gemm_cta_pair_wgrad_form(N, M, Nn, K, bn, splits):
+    """cta_group::2 with both operands MN-major and split-K (the weight-gradient GEMM of wide layers)."""
+    from distkeras_b200.ops.gemm import gemm_tn
+
+    torch.manual_seed(14)
+    at, bt = bf(torch.randn(K, M, device="cuda")), bf(torch.randn(K, Nn, device="cuda"))  # dZ [B, out], X [B, in]
+    out = gemm_tn(at, bt, a_mn=True, b_mn=True, pair=True, bn=bn, out_fp32=True, splits=splits)
+    ref = at.float().t() @ bt.float()
+    assert torch.allclose(out, ref, atol=2e-3 * K ** 0.5, rtol=1e-3)
