@@ -390,9 +390,19 @@ class FabricEagerWorker:
         elif k == "experimental":
             N.check(lib.dk_ps_damped_exchange(c, W, W1, None, self.P, 1.0 / self.tau, float(self.alg["inv_lr"]), ctrl,
                                               self.worker_id, self.iteration, st), "damped_exchange")
+        elif k == "custom":
+            # user-defined push / pull rule (the reference's "write your own optimizer" extension
+            # point, docs/optimizers.md:80-94, at the fabric level)
+            if self._exchange_ctx is None:
+                self._exchange_ctx = FabricExchange(self)
+            self.alg["exchange"](self._exchange_ctx)
+        else:
+            raise ValueError(f"unknown algorithm kind {k!r}")
         if self.strict:
             N.check(lib.dk_ps_lock_release(ctrl, self.ticket.data_ptr(), st), "lock_release")
         self.windows_run += 1
+
+    _exchange_ctx = None
 
     def initial_pull(self) -> None:
         reg = self.region
@@ -433,6 +443,107 @@ class FabricEagerWorker:
                 if not pre_batch and self.iteration % self.tau == 0:
                     self._comm_ops()
         self.drain()
+
+
+class FabricExchange:
+    """What a custom exchange rule sees at every communication-window boundary.
+
+    A trainer whose ``algorithm()`` returns ``{"kind": "custom", "window": tau, "exchange": fn}``
+    (``fn`` a picklable module-level callable) gets ``fn(ctx)`` called on the worker's stream every
+    ``tau`` mini-batches.  ``ctx.W`` is the worker's flat fp32 parameter vector (edit it in place),
+    ``ctx.W1`` the snapshot taken at the last ``pull()``; the center variable lives in the parameter
+    server's HBM and is reached through the helpers below, each ONE kernel over NVLink peer memory.
+    """
+
+    def __init__(self, worker: "FabricEagerWorker"):
+        self._w = worker
+        self.W, self.W1 = worker.W, worker.W1
+        self.worker_id, self.window = worker.worker_id, worker.tau
+        self._zeros: Optional[torch.Tensor] = None
+
+    @property
+    def iteration(self) -> int:
+        return self._w.iteration
+
+    def pull(self) -> None:
+        """``W <- center`` and ``W1 <- center`` (relaxed system-scope vector loads)."""
+        w = self._w
+        N.check(w.lib.dk_ps_pull(C.c_void_p(w.region.center_ptr), self.W.data_ptr(), self.W1.data_ptr(), None, w.P,
+                                 C.c_void_p(w.region.ctrl_ptr), w.last_update.data_ptr(), w._stream()), "pull")
+
+    def read_center(self) -> torch.Tensor:
+        """A local fp32 copy of the center variable (does not touch ``W`` / ``W1``)."""
+        w = self._w
+        out = torch.empty_like(self.W)
+        N.check(w.lib.dk_ps_copy(out.data_ptr(), C.c_void_p(w.region.center_ptr), w.P, w._stream()), "copy")
+        return out
+
+    def add_to_center(self, t: torch.Tensor, alpha: float = 1.0) -> None:
+        """``center += alpha * t`` with system-scope vector atomics; counts as one PS update."""
+        w = self._w
+        assert t.is_cuda and t.dtype == torch.float32 and t.numel() == w.P and t.is_contiguous()
+        if self._zeros is None:
+            self._zeros = torch.zeros_like(self.W)
+        N.check(w.lib.dk_ps_commit(C.c_void_p(w.region.center_ptr), t.data_ptr(), self._zeros.data_ptr(), w.P,
+                                   float(alpha), None, C.c_void_p(w.region.ctrl_ptr), w.worker_id, w.iteration,
+                                   w._stream()), "commit")
+
+    def commit_delta(self, scale: float = 1.0) -> None:
+        """``center += scale * (W - W1)`` -- the DOWNPOUR / ADAG commit."""
+        w = self._w
+        N.check(w.lib.dk_ps_commit(C.c_void_p(w.region.center_ptr), self.W.data_ptr(), self.W1.data_ptr(), w.P,
+                                   float(scale), None, C.c_void_p(w.region.ctrl_ptr), w.worker_id, w.iteration,
+                                   w._stream()), "commit")
+
+
+class CenterCheckpointer:
+    """Periodic snapshots of the center variable while the workers train.
+
+    The fabric parameter server is memory, so a checkpoint is just one more reader: a thread on the
+    owning rank copies the center (or its shards) and the control block to pinned host memory on its
+    own stream -- never synchronising the workers' streams -- and writes an atomic checkpoint file.
+    A snapshot taken mid-run is hogwild-consistent (it may interleave with commits at 16-byte
+    granularity), exactly like a worker's pull.
+    """
+
+    def __init__(self, model, region: FabricRegion, path: str, every_s: float, device_index: int, shards=None):
+        import threading
+
+        self.model, self.region, self.path = model.copy(), region, path
+        self.every_s, self.device_index = float(every_s), int(device_index)
+        self.shards = shards  # [(lo, hi, ptr)] or None
+        self.snapshots = 0
+        self._halt = threading.Event()
+        self._thread = threading.Thread(target=self._loop, daemon=True, name="dk-checkpointer")
+
+    def start(self) -> None:
+        self._thread.start()
+
+    def stop(self) -> None:
+        self._halt.set()
+        self._thread.join(timeout=60)
+
+    def _loop(self) -> None:
+        torch.cuda.set_device(self.device_index)
+        stream = torch.cuda.Stream(self.device_index)
+        P = self.model.num_params
+        host = torch.empty(P, dtype=torch.float32).pin_memory()
+        ctrl = torch.zeros(N.CTRL_WORDS, dtype=torch.int32).pin_memory()
+        lib, st = N.lib(), C.c_void_p(stream.cuda_stream)
+        while not self._halt.wait(self.every_s):
+            pieces = self.shards or [(0, P, self.region.center_ptr)]
+            for lo, hi, ptr in pieces:
+                N.check(lib.dk_memcpy_async(C.c_void_p(host.data_ptr() + 4 * lo), C.c_void_p(ptr), 4 * (hi - lo), 2, st),
+                        "checkpoint D2H")
+            N.check(lib.dk_memcpy_async(C.c_void_p(ctrl.data_ptr()), C.c_void_p(self.region.ctrl_ptr), 4 * N.CTRL_WORDS, 2,
+                                        st), "checkpoint ctrl D2H")
+            stream.synchronize()
+            from ..utils.checkpoint import save_checkpoint
+
+            self.model.set_flat_weights(host.clone())
+            save_checkpoint(self.path, self.model, num_updates=int(ctrl[N.CTRL_NUM_UPDATES]) + 1,
+                            extra={"partial": True, "snapshot": self.snapshots})
+            self.snapshots += 1
 
 
 # ================================================================================================
@@ -492,6 +603,11 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         shard_regions = [mine if r == rank else FabricRegion.open(infos[r], local) for r in range(world)]
         shards = [(bounds[r][0], bounds[r][1], shard_regions[r].center_ptr) for r in range(world)
                   if bounds[r][1] > bounds[r][0]]
+    checkpointer = None
+    if rank == 0 and getattr(trainer, "checkpoint_path", None) and getattr(trainer, "checkpoint_interval", None):
+        checkpointer = CenterCheckpointer(model, region, trainer.checkpoint_path, trainer.checkpoint_interval, local,
+                                          shards=shards)
+        checkpointer.start()
     num_workers = min(trainer.num_workers, world)
     dedicated = bool(getattr(trainer, "dedicated_ps", False)) and world > 1
     worker_ranks = list(range(1, world)) if dedicated else list(range(world))
@@ -506,6 +622,8 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         wid = worker_ranks.index(rank)
         wkw = dict(comm=getattr(trainer, "comm", "exchange"), strict=trainer.strict, seed=getattr(trainer, "seed", 0))
         try:
+            if alg["kind"] == "custom":  # python exchange rule: cannot live inside a captured graph
+                raise UnsupportedByNativeEngine("custom exchange rule")
             worker = FabricWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid, trainer.batch_size,
                                   local, in_dtype, affine, **wkw)
         except UnsupportedByNativeEngine:
@@ -581,6 +699,9 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         barrier()
     barrier()
     result = {"history": history, "stats": stats}
+    if checkpointer is not None:
+        checkpointer.stop()
+        stats["checkpoint_snapshots"] = checkpointer.snapshots
     if rank == 0:
         result["num_updates"] = ps.get_num_updates()
         result["staleness_hist"] = ps.staleness_histogram().tolist()

@@ -304,7 +304,8 @@ class DistributedTrainer(Trainer):
         self.parallelism_factor = 1
         self.communication_window = 1
         self.strict = bool(int(os.environ.get("DK_STRICT", "0")))
-        self.checkpoint_path: Optional[str] = None
+        self.checkpoint_path: Optional[str] = None       # final checkpoint (all backends)
+        self.checkpoint_interval: Optional[float] = None  # seconds between mid-run snapshots (fabric backend)
         self.tolerate_worker_failures = False
         self.worker_failures: list = []
 
@@ -387,6 +388,14 @@ class DistributedTrainer(Trainer):
     def train(self, dataframe: Dataset, shuffle: bool = False) -> Sequential:
         dataframe = self._maybe_shuffle(dataframe, shuffle)
         backend = self.backend
+        if backend == "fabric" and type(self).algorithm is DistributedTrainer.algorithm:
+            # user subclass that only overrides allocate_worker / allocate_parameter_server (the
+            # reference's two-class extension story): no device program to run, so the Python worker
+            # and parameter-server classes execute over the socket protocol, replicas still on the GPUs
+            import warnings
+
+            warnings.warn(f"{type(self).__name__} does not define algorithm(); falling back to backend='socket'")
+            backend = "socket"
         if backend == "fabric":
             if not torch.cuda.is_available():
                 raise RuntimeError("backend='fabric' needs CUDA; use backend='thread' or 'socket' on CPU")
@@ -395,6 +404,7 @@ class DistributedTrainer(Trainer):
             self.record_training_start()
             model, self.history = train_distributed_fabric(self, dataframe)
             self.record_training_end()
+            self._save_final_checkpoint(model, self.num_updates())
             return model
         if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1 and backend in ("socket", "spmd"):
             from .parallel.runtime import train_distributed_spmd_socket
@@ -433,12 +443,16 @@ class DistributedTrainer(Trainer):
                 self.parameter_server.finalize()
         self.history = [h for r in results for h in (r or [])]
         model = self.parameter_server.get_model()
-        if self.checkpoint_path:
-            from .utils.checkpoint import save_checkpoint
-
-            save_checkpoint(self.checkpoint_path, model, self.parameter_server.get_num_updates(),
-                            max([h["iteration"] for h in self.history], default=0), history=None)
+        self._save_final_checkpoint(model, self.parameter_server.get_num_updates())
         return model
+
+    def _save_final_checkpoint(self, model, num_updates: int) -> None:
+        if not self.checkpoint_path or int(os.environ.get("RANK", "0")) != 0:
+            return
+        from .utils.checkpoint import save_checkpoint
+
+        save_checkpoint(self.checkpoint_path, model, num_updates,
+                        max([h["iteration"] for h in self.history], default=0), history=None)
 
 
 class AsynchronousDistributedTrainer(DistributedTrainer):

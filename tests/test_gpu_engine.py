@@ -296,3 +296,32 @@ def test_smoke_entry():
     import __graft_entry__
 
     __graft_entry__.smoke()
+
+
+def test_fabric_periodic_and_final_checkpoint(tmp_path):
+    """Mid-run snapshots come from a reader thread on its own stream; the final file holds the result."""
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.trainers import ADAG
+    from distkeras_b200.utils.checkpoint import load_checkpoint, resume_trainer
+
+    g = torch.Generator().manual_seed(0)
+    n, B = 32768, 128
+    x = torch.randint(0, 255, (n, 64), generator=g).to(torch.uint8)
+    y = torch.randint(0, 10, (n,), generator=g).to(torch.int32)
+    ds = Dataset({"features": x, "label": y})
+    t = ADAG(_mlp(0), "adam", "categorical_crossentropy", num_workers=1, batch_size=B, num_epoch=4,
+             communication_window=4)
+    t.backend = "fabric"
+    t.checkpoint_path = str(tmp_path / "center.ckpt")
+    t.checkpoint_interval = 0.02
+    model = t.train(ds)
+    assert t.fabric_stats[0]["checkpoint_snapshots"] >= 1
+    ck = load_checkpoint(t.checkpoint_path)
+    assert not ck["extra"].get("partial")  # the final checkpoint replaced the snapshots
+    assert torch.equal(ck["model"].get_flat_weights(), model.get_flat_weights())
+    assert ck["num_updates"] == t.num_updates() == 1 + 4 * (n // B) // 4
+    t2 = ADAG(_mlp(1), "adam", "categorical_crossentropy", num_workers=1, batch_size=B, communication_window=4)
+    resume_trainer(t2, t.checkpoint_path)
+    from distkeras_b200.utils import deserialize_keras_model
+
+    assert torch.equal(deserialize_keras_model(t2.master_model).get_flat_weights(), model.get_flat_weights())

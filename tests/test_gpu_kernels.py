@@ -293,7 +293,7 @@ def test_gemm_cta_pair(N, M, Nn, K, bn):
     assert torch.allclose(out, ref, atol=2e-3 * K ** 0.5, rtol=1e-3)
 
 
-@pytest.mark.parametrize("M,Nn,K,bn,splits", [(1000, 784, 4096, 256, 4), (512, 256, 1024, 128, 2), (300, 520, 2048, 256, 1)])
+@pytest.mark.parametrize("M,Nn,K,bn,splits", [(1000, 784, 4096, 256, 4), (512, 256, 1024, 128, 2), (304, 520, 2048, 256, 1)])
 def test_gemm_cta_pair_wgrad_form(N, M, Nn, K, bn, splits):
     """cta_group::2 with both operands MN-major and split-K (the weight-gradient GEMM of wide layers)."""
     from distkeras_b200.ops.gemm import gemm_tn
