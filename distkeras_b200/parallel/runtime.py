@@ -30,8 +30,12 @@ import torch
 from .. import _native as N
 from ..data import Dataset, Partition
 from ..utils import deserialize_keras_model, serialize_keras_model
+from ..utils.timing import log_event
 from .engine import NativeReplica, UnsupportedByNativeEngine
 from .fabric import FabricRegion
+
+
+_NVTX = os.environ.get("DK_NVTX", "0") == "1"  # NVTX ranges around windows / exchanges (Nsight timelines)
 
 
 def _free_port() -> int:
@@ -271,6 +275,8 @@ class FabricWorker:
         """Train one window on ``tau * B`` rows of (pinned) host data.  Asynchronous: returns once the
         H2D copies and the graph replay are enqueued; at most two windows are in flight."""
         p = self.windows_run & 1
+        if _NVTX:
+            torch.cuda.nvtx.range_push(f"dk.window[{self.windows_run}] w{self.worker_id}")
         self._collect(p)  # window (n - 2) used this parity: wait for it, harvest its history
         with torch.cuda.stream(self.copy):
             self.x_stage[p].copy_(x_host.reshape(self.tau * self.B, -1), non_blocking=True)
@@ -285,6 +291,8 @@ class FabricWorker:
         self._pending[p] = self.iteration + 1
         self.iteration += self.tau
         self.windows_run += 1
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
 
     def drain(self) -> None:
         for p in ((self.windows_run & 1), ((self.windows_run + 1) & 1)):
@@ -543,6 +551,8 @@ class CenterCheckpointer:
             self.model.set_flat_weights(host.clone())
             save_checkpoint(self.path, self.model, num_updates=int(ctrl[N.CTRL_NUM_UPDATES]) + 1,
                             extra={"partial": True, "snapshot": self.snapshots})
+            log_event("fabric.checkpoint", path=self.path, snapshot=self.snapshots,
+                      num_updates=int(ctrl[N.CTRL_NUM_UPDATES]) + 1)
             self.snapshots += 1
 
 
@@ -569,6 +579,8 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
 
         bind_to_gpu_numa_node(local)  # pinned staging memory on the GPU's own socket
     alg = trainer.algorithm()
+    log_event("fabric.rank_start", rank=rank, world=world, device=local, algorithm=alg.get("kind"),
+              window=alg.get("window"), batch_size=trainer.batch_size, rows=len(dataset))
     model = deserialize_keras_model(trainer.master_model)
     in_dtype, affine = _affine_for(dataset, trainer.features_column)
     if getattr(trainer, "input_affine", None) is not None:
@@ -685,6 +697,7 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
                  "h2d_bytes": worker.h2d_bytes, "d2h_bytes": worker.d2h_bytes, "seconds": time.time() - t0,
                  "device_ms": ev0.elapsed_time(ev1), "executor": type(worker).__name__}
         history = worker.history
+        log_event("fabric.worker_done", rank=rank, worker_id=wid, **stats)
         # release the replica's device buffers / graphs before the next job in this process
         try:
             worker.rep.close()
