@@ -157,17 +157,18 @@ int run_op(Engine* e, Op& op, void* main_stream) {
       return dk_im2col(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], (int)a[6],
                        (int)a[7], (int)a[8], (int)a[9], (int)a[10], resolve(e, a[11]), (int)a[12], st);
     case DK_OP_COL2IM:
-      // col, ldcol, B, H, W, C, KH, KW, stride, pad, OH, OW, dx
-      return dk_col2im(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], (int)a[6],
-                       (int)a[7], (int)a[8], (int)a[9], (int)a[10], (int)a[11], resolve(e, a[12]), st);
+      // col, ldcol, B, H, W, C, KH, KW, stride, pad, OH, OW, dx, mask (0 = none)
+      return dk_col2im_ex(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], (int)a[6],
+                          (int)a[7], (int)a[8], (int)a[9], (int)a[10], (int)a[11], resolve(e, a[12]),
+                          resolve(e, a[13]), st);
     case DK_OP_MAXPOOL_FWD:
       // x, B, H, W, C, k, stride, y
       return dk_maxpool_fwd(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5],
                             (int)a[6], resolve(e, a[7]), st);
     case DK_OP_MAXPOOL_BWD:
-      // x, y, dy, B, H, W, C, k, stride, dx
-      return dk_maxpool_bwd(resolve(e, a[0]), resolve(e, a[1]), resolve(e, a[2]), (int)a[3], (int)a[4],
-                            (int)a[5], (int)a[6], (int)a[7], (int)a[8], resolve(e, a[9]), st);
+      // x, y, dy, B, H, W, C, k, stride, dx, relu
+      return dk_maxpool_bwd_ex(resolve(e, a[0]), resolve(e, a[1]), resolve(e, a[2]), (int)a[3], (int)a[4],
+                               (int)a[5], (int)a[6], (int)a[7], (int)a[8], resolve(e, a[9]), (int)a[10], st);
     case DK_OP_RELU_MASK:
       return dk_relu_mask_bf16(resolve(e, a[0]), resolve(e, a[1]), (long)a[2], st);
     case DK_OP_ADD:

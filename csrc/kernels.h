@@ -56,9 +56,13 @@ int dk_im2col(const void* x, int B, int H, int W, int C, int KH, int KW, int str
               int OW, void* col, int ldcol, void* stream);
 int dk_col2im(const void* col, int ldcol, int B, int H, int W, int C, int KH, int KW, int stride, int pad,
               int OH, int OW, void* dx, void* stream);
+int dk_col2im_ex(const void* col, int ldcol, int B, int H, int W, int C, int KH, int KW, int stride, int pad,
+                 int OH, int OW, void* dx, const void* mask, void* stream);
 int dk_maxpool_fwd(const void* x, int B, int H, int W, int C, int k, int stride, void* y, void* stream);
 int dk_maxpool_bwd(const void* x, const void* y, const void* dy, int B, int H, int W, int C, int k,
                    int stride, void* dx, void* stream);
+int dk_maxpool_bwd_ex(const void* x, const void* y, const void* dy, int B, int H, int W, int C, int k,
+                      int stride, void* dx, int relu, void* stream);
 // BatchNormalization over the last axis of [rows, C] bf16 (C % 8 == 0) and global average pooling
 int dk_bn_forward(const void* x, long rows, int C, float* sums, float* saved_mean, float* saved_invstd,
                   float* moving_mean, float* moving_var, const float* gamma, const float* beta, float eps,

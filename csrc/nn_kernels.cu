@@ -215,10 +215,52 @@ im2col_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, i
   }
 }
 
+// Small / odd channel counts (C = 1 or 3 in the first layer): one thread assembles 8 consecutive
+// elements of a col row (scalar gathers that hit L1) and writes them as ONE 16-byte store; the
+// padding columns K..ldcol-1 are written as zeros.  ldcol % 8 == 0.
+__global__ void __launch_bounds__(256)
+im2col_gather8_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int KH, int KW,
+                      int stride, int pad, int OH, int OW, __nv_bfloat16* __restrict__ col, int ldcol) {
+  DK_PDL_ENTER();
+  const int K = KH * KW * C;
+  const int chunks = ldcol >> 3;
+  const long total = static_cast<long>(B) * OH * OW * chunks;
+  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % chunks);
+    const long row = i / chunks;
+    long t = row;
+    const int ow = static_cast<int>(t % OW); t /= OW;
+    const int oh = static_cast<int>(t % OH); t /= OH;
+    const int b = static_cast<int>(t);
+    const int ih0 = oh * stride - pad, iw0 = ow * stride - pad;
+    int k = ch << 3;
+    int c = k % C, tap = k / C;
+    int kw = tap % KW, kh = tap / KW;
+    unsigned short v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ih = ih0 + kh, iw = iw0 + kw;
+      const bool ok = (k + e) < K && ih >= 0 && ih < H && iw >= 0 && iw < W;
+      v[e] = ok ? __ldg(xs + ((static_cast<long>(b) * H + ih) * W + iw) * C + c) : static_cast<unsigned short>(0);
+      if (++c == C) {
+        c = 0;
+        if (++kw == KW) { kw = 0; ++kh; }
+      }
+    }
+    uint4 o;
+    o.x = v[0] | (static_cast<uint32_t>(v[1]) << 16); o.y = v[2] | (static_cast<uint32_t>(v[3]) << 16);
+    o.z = v[4] | (static_cast<uint32_t>(v[5]) << 16); o.w = v[6] | (static_cast<uint32_t>(v[7]) << 16);
+    *reinterpret_cast<uint4*>(col + row * ldcol + (ch << 3)) = o;
+  }
+}
+
 // dx[b, ih, iw, c] = sum over the (kh, kw) windows that cover it (gather form: no atomics)
 __global__ void __launch_bounds__(256)
 col2im_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int H, int W, int C, int KH,
-              int KW, int stride, int pad, int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+              int KW, int stride, int pad, int OH, int OW, __nv_bfloat16* __restrict__ dx,
+              const __nv_bfloat16* __restrict__ mask) {
   DK_PDL_ENTER();
   const long total = static_cast<long>(B) * H * W * C;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -243,6 +285,7 @@ col2im_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int H, in
         acc += __bfloat162float(col[row * ldcol + (kh * KW + kw) * C + c]);
       }
     }
+    if (mask != nullptr && !(__bfloat162float(mask[i]) > 0.f)) acc = 0.f;  // fused dReLU of the producer
     dx[i] = __float2bfloat16_rn(acc);
   }
 }
@@ -250,7 +293,8 @@ col2im_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int H, in
 // 8-channel vector form of the gather (C % 8 == 0): one 16-byte load per covering window
 __global__ void __launch_bounds__(256)
 col2im_vec8_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int H, int W, int C, int KH,
-                   int KW, int stride, int pad, int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+                   int KW, int stride, int pad, int OH, int OW, __nv_bfloat16* __restrict__ dx,
+                   const __nv_bfloat16* __restrict__ mask) {
   DK_PDL_ENTER();
   const int c8n = C >> 3;
   const long total = static_cast<long>(B) * H * W * c8n;
@@ -282,6 +326,13 @@ col2im_vec8_kernel(const __nv_bfloat16* __restrict__ col, int ldcol, int B, int 
           acc[2 * u + 1] += f.y;
         }
       }
+    }
+    if (mask != nullptr) {  // fused dReLU of the layer that produced this activation
+      const uint4 mq = *reinterpret_cast<const uint4*>(mask + (i << 3));
+      const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mq);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (!(__bfloat162float(mh[u]) > 0.f)) acc[u] = 0.f;
     }
     uint4 o;
     o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
@@ -328,7 +379,7 @@ maxpool_fwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W
 // (non-overlapping windows), first-max position receives the gradient
 __global__ void __launch_bounds__(256)
 maxpool_bwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int B, int H,
-                        int W, int C, int k, int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+                        int W, int C, int k, int OH, int OW, __nv_bfloat16* __restrict__ dx, int relu) {
   DK_PDL_ENTER();
   const int c8n = C >> 3;
   const long total = static_cast<long>(B) * OH * OW * c8n;
@@ -356,6 +407,13 @@ maxpool_bwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
       }
     const uint4 gq = *reinterpret_cast<const uint4*>(dy + (i << 3));
     const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&gq);
+    // relu: x is a post-ReLU activation and dx feeds that ReLU's backward -> the mask (x > 0) is
+    // applied here (the window max decides: a zero max means every input of the window was clipped)
+    if (relu) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (!(m[u] > 0.f)) arg[u] = -1;
+    }
     for (int kh = 0; kh < k; ++kh)
       for (int kw = 0; kw < k; ++kw) {
         __nv_bfloat16 o[8];
@@ -364,6 +422,21 @@ maxpool_bwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
         *reinterpret_cast<uint4*>(dx + ((static_cast<long>(b) * H + oh * k + kh) * W + ow * k + kw) * C + c) =
             *reinterpret_cast<const uint4*>(o);
       }
+    // rows / columns past the last full window (H or W not a multiple of k) receive no gradient
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const bool tail_w = ow == OW - 1 && OW * k < W, tail_h = oh == OH - 1 && OH * k < H;
+    if (tail_w)
+      for (int kh = 0; kh < k; ++kh)
+        for (int jw = OW * k; jw < W; ++jw)
+          *reinterpret_cast<uint4*>(dx + ((static_cast<long>(b) * H + oh * k + kh) * W + jw) * C + c) = z;
+    if (tail_h)
+      for (int jh = OH * k; jh < H; ++jh)
+        for (int kw = 0; kw < k; ++kw)
+          *reinterpret_cast<uint4*>(dx + ((static_cast<long>(b) * H + jh) * W + ow * k + kw) * C + c) = z;
+    if (tail_w && tail_h)
+      for (int jh = OH * k; jh < H; ++jh)
+        for (int jw = OW * k; jw < W; ++jw)
+          *reinterpret_cast<uint4*>(dx + ((static_cast<long>(b) * H + jh) * W + jw) * C + c) = z;
   }
 }
 
@@ -394,7 +467,7 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
                    const __nv_bfloat16* __restrict__ dy, int B, int H, int W, int C, int k, int stride,
-                   int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+                   int OH, int OW, __nv_bfloat16* __restrict__ dx, int relu) {
   DK_PDL_ENTER();
   const long total = static_cast<long>(B) * H * W * C;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -421,7 +494,7 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
               fw = jw;
             }
           }
-        if (fh == ih && fw == iw) g = __bfloat162float(dy[o]);
+        if (fh == ih && fw == iw && (!relu || yv > 0.f)) g = __bfloat162float(dy[o]);
       }
     }
     dx[i] = __float2bfloat16_rn(g);
@@ -725,6 +798,14 @@ int dk_colsum_bf16(const void* src, int rows, int cols, int lds, float* out, flo
 
 int dk_im2col(const void* x, int B, int H, int W, int C, int KH, int KW, int stride, int pad, int OH,
               int OW, void* col, int ldcol, void* stream) {
+  if (C % 8 != 0 && ldcol % 8 == 0 && (reinterpret_cast<uintptr_t>(col) & 15) == 0) {
+    const long total8 = static_cast<long>(B) * OH * OW * (ldcol / 8);
+    DK_HOST_CHECK(DK_LAUNCH(im2col_gather8_kernel, ew_grid(total8), 256, 0, (cudaStream_t)stream,
+        reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, KH, KW, stride, pad, OH, OW,
+        reinterpret_cast<__nv_bfloat16*>(col), ldcol));
+    DK_HOST_CHECK(cudaGetLastError());
+    return 0;
+  }
   const int cvec = (C % 8 == 0) ? 8 : 1;
   const long total = static_cast<long>(B) * OH * OW * KH * KW * (C / cvec);
   DK_HOST_CHECK(DK_LAUNCH(im2col_kernel, ew_grid(total), 256, 0, (cudaStream_t)stream, 
@@ -736,18 +817,24 @@ int dk_im2col(const void* x, int B, int H, int W, int C, int KH, int KW, int str
 
 int dk_col2im(const void* col, int ldcol, int B, int H, int W, int C, int KH, int KW, int stride, int pad,
               int OH, int OW, void* dx, void* stream) {
+  return dk_col2im_ex(col, ldcol, B, H, W, C, KH, KW, stride, pad, OH, OW, dx, nullptr, stream);
+}
+
+// mask (optional, [B*H*W, C] bf16): dx is zeroed where mask <= 0 (dReLU of the producing layer)
+int dk_col2im_ex(const void* col, int ldcol, int B, int H, int W, int C, int KH, int KW, int stride, int pad,
+                 int OH, int OW, void* dx, const void* mask, void* stream) {
   if (C % 8 == 0 && ldcol % 8 == 0) {
     const long total8 = static_cast<long>(B) * H * W * (C / 8);
     DK_HOST_CHECK(DK_LAUNCH(col2im_vec8_kernel, ew_grid(total8), 256, 0, (cudaStream_t)stream, 
         reinterpret_cast<const __nv_bfloat16*>(col), ldcol, B, H, W, C, KH, KW, stride, pad, OH, OW,
-        reinterpret_cast<__nv_bfloat16*>(dx)));
+        reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(mask)));
     DK_HOST_CHECK(cudaGetLastError());
     return 0;
   }
   const long total = static_cast<long>(B) * H * W * C;
   DK_HOST_CHECK(DK_LAUNCH(col2im_kernel, ew_grid(total), 256, 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(col), ldcol, B, H, W, C, KH, KW, stride, pad, OH, OW,
-      reinterpret_cast<__nv_bfloat16*>(dx)));
+      reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(mask)));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -771,12 +858,18 @@ int dk_maxpool_fwd(const void* x, int B, int H, int W, int C, int k, int stride,
 
 int dk_maxpool_bwd(const void* x, const void* y, const void* dy, int B, int H, int W, int C, int k,
                    int stride, void* dx, void* stream) {
+  return dk_maxpool_bwd_ex(x, y, dy, B, H, W, C, k, stride, dx, 0, stream);
+}
+
+// relu != 0: additionally apply the (x > 0) mask of the ReLU that produced x (fused dReLU)
+int dk_maxpool_bwd_ex(const void* x, const void* y, const void* dy, int B, int H, int W, int C, int k,
+                      int stride, void* dx, int relu, void* stream) {
   const int OH = (H - k) / stride + 1, OW = (W - k) / stride + 1;
-  if (C % 8 == 0 && k == stride && H % k == 0 && W % k == 0) {
+  if (C % 8 == 0 && k == stride) {
     const long total8 = static_cast<long>(B) * OH * OW * (C / 8);
     DK_HOST_CHECK(DK_LAUNCH(maxpool_bwd_vec8_kernel, ew_grid(total8), 256, 0, (cudaStream_t)stream, 
         reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), B, H, W, C, k, OH, OW,
-        reinterpret_cast<__nv_bfloat16*>(dx)));
+        reinterpret_cast<__nv_bfloat16*>(dx), relu));
     DK_HOST_CHECK(cudaGetLastError());
     return 0;
   }
@@ -784,7 +877,7 @@ int dk_maxpool_bwd(const void* x, const void* y, const void* dy, int B, int H, i
   DK_HOST_CHECK(DK_LAUNCH(maxpool_bwd_kernel, ew_grid(total), 256, 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(y),
       reinterpret_cast<const __nv_bfloat16*>(dy), B, H, W, C, k, stride, OH, OW,
-      reinterpret_cast<__nv_bfloat16*>(dx)));
+      reinterpret_cast<__nv_bfloat16*>(dx), relu));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }

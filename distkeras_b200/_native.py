@@ -83,6 +83,8 @@ _SIGNATURES = {
     "dk_col2im": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "dk_maxpool_fwd": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "dk_maxpool_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "dk_maxpool_bwd_ex": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "dk_col2im_ex": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "dk_relu_mask_bf16": (i32, [vp, vp, i64, vp]),
     "dk_bn_forward": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp]),
     "dk_bn_inference": (i32, [vp, i64, i32, vp, vp, vp, vp, f32, i32, vp, vp]),

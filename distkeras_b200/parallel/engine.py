@@ -154,6 +154,15 @@ def _group_layers(model: Sequential) -> List[_Block]:
     return blocks
 
 
+def _relu_mask_fusable(prev, rows: int, cols: int) -> bool:
+    """True when ``prev`` (the block whose output gradient is being produced) ends in a plain ReLU
+    whose saved output has exactly the gradient's layout, so the consumer can apply ``out > 0``."""
+    if prev is None or prev.kind not in ("conv", "bn") or prev.act != "relu" or getattr(prev, "drop_p", 0) > 0:
+        return False
+    rec = getattr(prev, "out_rec", None)
+    return rec is not None and rec["rows"] == rows and rec["cols"] == cols and rec["ld"] == cols
+
+
 class NativeReplica(Replica):
     """A model replica executed by the native sm_100a engine on one GPU."""
 
@@ -453,9 +462,11 @@ class NativeReplica(Replica):
                 H, Wd, Cin = b.in_shape
                 OH, OW, _ = b.out_shape
                 dx = self._buf(B * H * Wd, Cin)
+                # dReLU of the producing conv / BN block is applied while the gradient image is assembled
+                fuse_relu = _relu_mask_fusable(prev, B * H * Wd, Cin)
                 self._add(lst, N.OP_COL2IM, [din.data_ptr(), _r8(K), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad, OH, OW,
-                                             dx.data_ptr()])
-                return dict(t=dx, rows=B * H * Wd, cols=Cin, ld=Cin), False
+                                             dx.data_ptr(), prev.out_rec["t"].data_ptr() if fuse_relu else 0])
+                return dict(t=dx, rows=B * H * Wd, cols=Cin, ld=Cin), fuse_relu
             return dict(t=din, rows=rows, cols=K, ld=_r8(K)), fuse_mask
 
         return rec, backward
@@ -473,9 +484,12 @@ class NativeReplica(Replica):
 
         def backward(grad, premasked, need_dx, prev):
             dx = self._buf(B * H * Wd, Cc)
+            # the pool's input is the previous block's post-ReLU output: its dReLU mask is (x > 0),
+            # which the pooling backward already has in registers -> no separate mask pass
+            fuse_relu = _relu_mask_fusable(prev, B * H * Wd, Cc)
             self._add(self.L_bwd, N.OP_MAXPOOL_BWD, [inp["t"].data_ptr(), out.data_ptr(), grad["t"].data_ptr(), B, H,
-                                                     Wd, Cc, b.k, b.k, dx.data_ptr()])
-            return dict(t=dx, rows=B * H * Wd, cols=Cc, ld=Cc), False
+                                                     Wd, Cc, b.k, b.k, dx.data_ptr(), 1 if fuse_relu else 0])
+            return dict(t=dx, rows=B * H * Wd, cols=Cc, ld=Cc), fuse_relu
 
         return rec, backward
 

@@ -303,3 +303,38 @@ def test_gemm_cta_pair_wgrad_form(N, M, Nn, K, bn, splits):
     out = gemm_tn(at, bt, a_mn=True, b_mn=True, pair=True, bn=bn, out_fp32=True, splits=splits)
     ref = at.float().t() @ bt.float()
     assert torch.allclose(out, ref, atol=2e-3 * K ** 0.5, rtol=1e-3)
+
+
+@pytest.mark.parametrize("H,Cc", [(13, 64), (7, 8), (13, 3)])
+def test_maxpool_bwd_odd_size_and_fused_relu(N, H, Cc):
+    """Floor-mode pooling of an odd image (uncovered last row / column gets zero gradient) with the
+    producer's dReLU fused in (x is a post-ReLU activation)."""
+    torch.manual_seed(15)
+    B = 3
+    x = bf(torch.relu(torch.randn(B, H, H, Cc, device="cuda")))
+    OH = H // 2
+    y = torch.zeros(B, OH, OH, Cc, dtype=torch.bfloat16, device="cuda")
+    N.check(N.lib().dk_maxpool_fwd(x.data_ptr(), B, H, H, Cc, 2, 2, y.data_ptr(), st()))
+    dy = bf(torch.randn(B, OH, OH, Cc, device="cuda"))
+    dx = torch.full_like(x, 7.0)  # poison: every element must be written
+    N.check(N.lib().dk_maxpool_bwd_ex(x.data_ptr(), y.data_ptr(), dy.data_ptr(), B, H, H, Cc, 2, 2, dx.data_ptr(), 1, st()))
+    pre = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    F.max_pool2d(torch.relu(pre), 2).backward(dy.float().permute(0, 3, 1, 2))
+    ref = pre.grad.permute(0, 2, 3, 1)
+    # ties inside a window (several zeros) route differently in torch; compare where the max is unique / positive
+    assert torch.allclose(dx.float() * (x.float() > 0), ref * (x.float() > 0), atol=1e-6)
+    assert float((dx.float() * (x.float() <= 0)).abs().max()) == 0.0
+
+
+def test_col2im_fused_mask(N):
+    torch.manual_seed(16)
+    B, H, Cin, k = 2, 12, 16, 3
+    OH = H - k + 1
+    K = k * k * Cin
+    dcol = bf(torch.randn(B * OH * OH, K, device="cuda"))
+    mask = bf(torch.randn(B, H, H, Cin, device="cuda"))
+    plain, masked = torch.zeros(B, H, H, Cin, dtype=torch.bfloat16, device="cuda"), torch.zeros(
+        B, H, H, Cin, dtype=torch.bfloat16, device="cuda")
+    N.check(N.lib().dk_col2im(dcol.data_ptr(), K, B, H, H, Cin, k, k, 1, 0, OH, OH, plain.data_ptr(), st()))
+    N.check(N.lib().dk_col2im_ex(dcol.data_ptr(), K, B, H, H, Cin, k, k, 1, 0, OH, OH, masked.data_ptr(), mask.data_ptr(), st()))
+    assert torch.equal(masked, torch.where(mask.float() > 0, plain, torch.zeros_like(plain)))
