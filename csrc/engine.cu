@@ -21,7 +21,7 @@ namespace {
 
 struct Op {
   int kind;
-  int stream_id;  // 0 = caller's stream, 1 = engine side stream (parallel graph branch)
+  int stream_id;  // 0 = caller's stream, 1.. = engine side streams (parallel graph branches)
   int64_t i[DK_OP_MAX_I];
   double f[DK_OP_MAX_F];
   // GEMM only
@@ -38,7 +38,7 @@ struct Engine {
   void* slots[DK_ENGINE_SLOTS];
   long launches;  // kernels enqueued so far (bench "gpu_launches" accounting)
   int build_stream;            // stream id given to ops added from now on
-  cudaStream_t side;           // side stream: independent work (wgrad / bias-grad) overlaps the dgrad chain
+  cudaStream_t side[DK_ENGINE_SIDE_STREAMS];  // independent work (wgrad / bias-grad branches) overlaps the dgrad chain
   std::vector<cudaEvent_t> events;
   size_t next_event;
 };
@@ -78,14 +78,17 @@ int run_op(Engine* e, Op& op, void* main_stream) {
   if (op.kind == DK_OP_FORK || op.kind == DK_OP_JOIN) {
     // FORK: side stream waits for everything enqueued so far on the main stream.
     // JOIN: main stream waits for everything enqueued so far on the side stream.
-    cudaStream_t from = op.kind == DK_OP_FORK ? (cudaStream_t)main_stream : e->side;
-    cudaStream_t to = op.kind == DK_OP_FORK ? e->side : (cudaStream_t)main_stream;
+    // a[0] = side stream id (1-based; 0 is accepted as 1)
+    const int sid = a[0] <= 0 ? 0 : (int)a[0] - 1;
+    if (sid >= DK_ENGINE_SIDE_STREAMS) return -1;
+    cudaStream_t from = op.kind == DK_OP_FORK ? (cudaStream_t)main_stream : e->side[sid];
+    cudaStream_t to = op.kind == DK_OP_FORK ? e->side[sid] : (cudaStream_t)main_stream;
     cudaEvent_t ev = next_event(e);
     DK_HOST_CHECK(cudaEventRecord(ev, from));
     DK_HOST_CHECK(cudaStreamWaitEvent(to, ev, 0));
     return 0;
   }
-  void* st = op.stream_id == 1 ? (void*)e->side : main_stream;
+  void* st = op.stream_id >= 1 ? (void*)e->side[op.stream_id - 1] : main_stream;
   switch (op.kind) {
     case DK_OP_INPUT:
       // x, in_dtype, B, F, xb, ldx, xt, ldxt, step_counter, xf, ldxf | scale, shift
@@ -235,20 +238,24 @@ void* dk_engine_create() {
   e->launches = 0;
   e->build_stream = 0;
   e->next_event = 0;
-  e->side = nullptr;
-  cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
+  for (int k = 0; k < DK_ENGINE_SIDE_STREAMS; ++k) {
+    e->side[k] = nullptr;
+    cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking);
+  }
   return e;
 }
 
 void dk_engine_destroy(void* h) {
   Engine* e = reinterpret_cast<Engine*>(h);
   for (cudaEvent_t ev : e->events) cudaEventDestroy(ev);
-  if (e->side != nullptr) cudaStreamDestroy(e->side);
+  for (int k = 0; k < DK_ENGINE_SIDE_STREAMS; ++k)
+    if (e->side[k] != nullptr) cudaStreamDestroy(e->side[k]);
   delete e;
 }
 
 // ops added after this call run on stream `id` (0 = caller's stream, 1 = engine side stream)
 int dk_engine_set_build_stream(void* h, int id) {
+  if (id < 0 || id > DK_ENGINE_SIDE_STREAMS) return -1;
   reinterpret_cast<Engine*>(h)->build_stream = id;
   return 0;
 }

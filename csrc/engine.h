@@ -6,6 +6,7 @@
 
 #define DK_OP_MAX_I 16
 #define DK_OP_MAX_F 8
+#define DK_ENGINE_SIDE_STREAMS 3
 #define DK_ENGINE_SLOTS 16
 
 enum {

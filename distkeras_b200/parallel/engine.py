@@ -21,6 +21,7 @@ parameter-server kernels operate on.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -293,6 +294,8 @@ class NativeReplica(Replica):
                        x0f.data_ptr() if lst == self.L_step_pull else 0, F],
                       [self.scale, self.shift])
         nblocks = len(self.blocks)
+        self._forked = set()
+        self._side_streams = int(os.environ.get("DK_SIDE_STREAMS", "2"))
         backward = []  # (block, closure(grad, premasked, need_dx, prev_block) -> (grad_in, premasked_in))
         for bi, b in enumerate(self.blocks):
             is_last = bi == nblocks - 1
@@ -346,7 +349,8 @@ class NativeReplica(Replica):
             if bi == 0:
                 break
         # ---- optimizer (one fused launch over the flat buffer, emits the bf16 shadow) ----
-        self._add(lst, N.OP_JOIN, [0])
+        for sid in sorted(self._forked):
+            self._add(lst, N.OP_JOIN, [sid])
         o = self.opt
         self._add(lst, N.OP_OPTIM, [N.OPT_KINDS[o.kernel_kind], self.W.data_ptr(), self.G.data_ptr(), N.ptr(o.s0),
                                     N.ptr(o.s1), self.Wb.data_ptr(), self.P, int(o.nesterov),
@@ -432,12 +436,20 @@ class NativeReplica(Replica):
                 self._add(lst, N.OP_RELU_MASK, [grad["t"].data_ptr(), rec["t"].data_ptr(), rows * grad["ld"]])
             # parameter gradients only feed the optimizer: they run on the engine's side stream
             # (a parallel branch of the captured graph) while the dgrad chain continues
-            self._add(lst, N.OP_FORK, [0])
-            self.lib.dk_engine_set_build_stream(self.engine, 1 if need_dx else 0)
+            # (graph branches).  DK_SIDE_STREAMS=2 (default): wgrads on branch 1, bias column sums on
+            # branch 2, and the first layer's wgrad -- nothing is left to overlap it with -- on the main
+            # stream; DK_SIDE_STREAMS=1: one branch carries both.
+            two = self._side_streams >= 2
+            s_bias = 2 if two else (1 if need_dx else 0)
+            s_wgrad = (1 if need_dx else 0) if two else 1
+            for sid in {s_bias, s_wgrad} - {0}:
+                self._add(lst, N.OP_FORK, [sid])
+                self._forked.add(sid)
+            self.lib.dk_engine_set_build_stream(self.engine, s_bias)
             if bseg is not None:
                 self._add(lst, N.OP_COLSUM, [grad["t"].data_ptr(), rows, Nout, grad["ld"], g_ptr + 4 * bseg.offset],
                           [1.0])
-            self.lib.dk_engine_set_build_stream(self.engine, 1)
+            self.lib.dk_engine_set_build_stream(self.engine, s_wgrad)
             # wgrad: dW[Nout, K] = dZ^T[Nout, rows] * In[rows, K]  (both operands MN-major views)
             ep = N.GemmEpilogue()
             ep.d, ep.ldd, ep.d_fp32, ep.alpha = g_ptr + 4 * kseg.offset, K, 1, 1.0
