@@ -109,6 +109,12 @@ int run_op(Engine* e, Op& op, void* main_stream) {
                              rp<const float>(e, a[3]), (int)a[4], (int)a[5], resolve(e, a[6]), (int)a[7],
                              resolve(e, a[8]), (int)a[9], rp<float>(e, a[10]), rp<float>(e, a[11]),
                              rp<const int>(e, a[12]), (int)a[13], st);
+    case DK_OP_HEAD:
+      // H, ldh, Wb, ldw, bias, labels, labels_dense, B, C, K, dz, ldz, dH, lddh, use_mask, hist, step, hist_slots | alpha
+      return dk_dense_softmax_head(resolve(e, a[0]), (int)a[1], resolve(e, a[2]), (int)a[3], rp<const float>(e, a[4]),
+                                   rp<const int>(e, a[5]), rp<const float>(e, a[6]), (int)a[7], (int)a[8], (int)a[9],
+                                   resolve(e, a[10]), (int)a[11], resolve(e, a[12]), (int)a[13], (float)f[0],
+                                   (int)a[14], rp<float>(e, a[15]), rp<const int>(e, a[16]), (int)a[17], st);
     case DK_OP_ELOSS:
       // kind, out, target, B, C, dz, ldz, dzt, ldzt, hist, step, hist_slots
       return dk_elementwise_loss((int)a[0], rp<const float>(e, a[1]), rp<const float>(e, a[2]), (int)a[3],

@@ -4,7 +4,7 @@
 
 #include "gemm.h"
 
-#define DK_OP_MAX_I 16
+#define DK_OP_MAX_I 20
 #define DK_OP_MAX_F 8
 #define DK_ENGINE_SIDE_STREAMS 3
 #define DK_ENGINE_SLOTS 16
@@ -46,7 +46,8 @@ enum {
   DK_OP_BN_INF = 33,
   DK_OP_BN_BWD = 34,
   DK_OP_GAP_FWD = 35,
-  DK_OP_GAP_BWD = 36
+  DK_OP_GAP_BWD = 36,
+  DK_OP_HEAD = 37
 };
 
 #ifdef __cplusplus

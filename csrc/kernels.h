@@ -34,6 +34,9 @@ int dk_cast_bf16(const float* src, void* dst, long n, void* stream);
 int dk_softmax_xent(const float* logits, int ldl, const int* labels, const float* labels_dense, int B,
                     int C, void* dz, int ldz, void* dzt, int ldzt, float* probs, float* hist,
                     const int* step, int hist_slots, void* stream);
+int dk_dense_softmax_head(const void* H, int ldh, const void* Wb, int ldw, const float* bias, const int* labels,
+                          const float* labels_dense, int B, int C, int K, void* dz, int ldz, void* dH, int lddh,
+                          float alpha, int use_mask, float* hist, const int* step, int hist_slots, void* stream);
 // generic elementwise losses on fp32 outputs (mse / binary cross-entropy on sigmoid outputs)
 int dk_elementwise_loss(int kind, const float* out, const float* target, int B, int C, void* dz, int ldz,
                         void* dzt, int ldzt, float* hist, const int* step, int hist_slots, void* stream);

@@ -37,7 +37,7 @@ OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_RELU_MASK, OP_ADD, OP_MEMSET = 8, 9, 10, 11, 
 OP_PS_COMMIT, OP_PS_PULL, OP_PS_EXCHANGE, OP_PS_ELASTIC, OP_PS_DAMPED, OP_PS_TICKET = 13, 14, 15, 16, 17, 18
 OP_LOCK_ACQUIRE, OP_LOCK_RELEASE, OP_EAMSGD_PRE, OP_EAMSGD_POST, OP_CAST, OP_ELOSS = 19, 20, 21, 22, 23, 24
 OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D, OP_FORK, OP_JOIN, OP_GEMM_PULL = 25, 26, 27, 28, 29, 30, 31
-OP_BN_FWD, OP_BN_INF, OP_BN_BWD, OP_GAP_FWD, OP_GAP_BWD = 32, 33, 34, 35, 36
+OP_BN_FWD, OP_BN_INF, OP_BN_BWD, OP_GAP_FWD, OP_GAP_BWD, OP_HEAD = 32, 33, 34, 35, 36, 37
 GEMM_TF32, GEMM_A_MN, GEMM_B_MN, GEMM_PERSISTENT, GEMM_PAIR = 1, 2, 4, 8, 16
 
 OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6}
@@ -73,6 +73,8 @@ _SIGNATURES = {
     "dk_eamsgd_post": (i32, [vp, vp, vp, vp, i64, f32, vp]),
     "dk_cast_bf16": (i32, [vp, vp, i64, vp]),
     "dk_softmax_xent": (i32, [vp, i32, vp, vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, i32, vp]),
+    "dk_dense_softmax_head": (i32, [vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, vp, i32, vp, i32, f32, i32, vp, vp, i32,
+                                    vp]),
     "dk_elementwise_loss": (i32, [i32, vp, vp, i32, i32, vp, i32, vp, i32, vp, vp, i32, vp]),
     "dk_input_stage": (i32, [vp, i32, i32, i32, f32, f32, vp, i32, vp, i32, vp, vp, i32, vp]),
     "dk_gemm_pull": (i32, [vp, i64, vp, i64, C.POINTER(GemmEpilogue), i32, i32, i32, vp, vp, vp, vp]),

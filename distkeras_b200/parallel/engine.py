@@ -329,7 +329,9 @@ class NativeReplica(Replica):
         # ---- loss ----
         ldz = _r8(Cn)
         dz = self._buf(B, ldz)
-        if self.loss_kind == "xent":
+        if self.loss_kind == "xent" and getattr(self, "head_fused", False):
+            pass  # loss + dZ come out of the fused head op emitted by the last block's backward
+        elif self.loss_kind == "xent":
             self._add(lst, N.OP_XENT, [self.logits.data_ptr(), ldl,
                                        0 if self.dense_labels else -(SLOT_Y + 1),
                                        -(SLOT_Y + 1) if self.dense_labels else 0,
@@ -398,6 +400,12 @@ class NativeReplica(Replica):
         else:
             rows = cur["rows"]
             a_in = cur
+        # classifier head (<= 16 classes, softmax cross-entropy): in the training lists the forward
+        # GEMM, the loss and the dgrad GEMM collapse into ONE kernel (dk_dense_softmax_head)
+        head_fused = (is_last and self.training and b.kind == "dense" and self.loss_kind == "xent" and Nout <= 16
+                      and K % 8 == 0 and a_in["ld"] % 8 == 0 and wbld == K and Nout * (K + 4) * 4 <= 48 * 1024
+                      and b.act != "relu" and os.environ.get("DK_FUSED_HEAD", "1") != "0")
+        self.head_fused = head_fused if is_last else getattr(self, "head_fused", False)
         if is_last:
             ldl = _r8(Nout) if self.loss_kind == "xent" else Nout  # fp32 rows 16-byte aligned for TMA
             out = self._buf(rows, ldl, dtype=torch.float32)
@@ -406,6 +414,8 @@ class NativeReplica(Replica):
             out = self._buf(rows, _r8(Nout))
             rec = dict(t=out, rows=rows, cols=Nout, ld=_r8(Nout), nhwc=b.out_shape if b.kind == "conv" else None)
         for lst in lists:
+            if head_fused and lst in self._train_lists:
+                continue  # logits are produced (and consumed) inside the fused head kernel
             ep = N.GemmEpilogue()
             ep.bias = (wptr_f32 + 4 * bseg.offset) if bseg is not None else None
             ep.act = 1 if b.act == "relu" else 0
@@ -432,6 +442,19 @@ class NativeReplica(Replica):
 
         def backward(grad, premasked, need_dx, prev):
             lst = self.L_bwd
+            head_din = None
+            if head_fused:
+                fuse_mask = prev is not None and prev.kind == "dense" and prev.act == "relu"
+                if prev is not None and prev.kind == "dense" and prev.drop_p > 0 and not fuse_mask:
+                    raise UnsupportedByNativeEngine("dropout after a non-ReLU dense layer")
+                alpha = 1.0 / (1.0 - prev.drop_p) if (fuse_mask and prev.drop_p > 0) else 1.0
+                head_din = self._buf(rows, K) if need_dx else None
+                self._add(lst, N.OP_HEAD,
+                          [a_in["t"].data_ptr(), a_in["ld"], wbp, wbld, (wptr_f32 + 4 * bseg.offset) if bseg is not None else 0,
+                           0 if self.dense_labels else -(SLOT_Y + 1), -(SLOT_Y + 1) if self.dense_labels else 0,
+                           rows, Nout, K, grad["t"].data_ptr(), grad["ld"], head_din.data_ptr() if need_dx else 0, K,
+                           1 if fuse_mask else 0, self.hist.data_ptr(), self.step_counter.data_ptr(), self.hist_slots],
+                          [alpha])
             if b.act == "relu" and not premasked:
                 self._add(lst, N.OP_RELU_MASK, [grad["t"].data_ptr(), rec["t"].data_ptr(), rows * grad["ld"]])
             # parameter gradients only feed the optimizer: they run on the engine's side stream
@@ -458,6 +481,8 @@ class NativeReplica(Replica):
             self.lib.dk_engine_set_build_stream(self.engine, 0)
             if not need_dx:
                 return None, True
+            if head_din is not None:  # the fused head already produced the (masked) input gradient
+                return dict(t=head_din, rows=rows, cols=K, ld=K), fuse_mask
             # dgrad: dIn[rows, K] = dZ[rows, Nout] * W[Nout, K]   (W read as an MN-major B operand)
             din = self._buf(rows, _r8(K))
             ep = N.GemmEpilogue()

@@ -338,3 +338,37 @@ def test_col2im_fused_mask(N):
     N.check(N.lib().dk_col2im(dcol.data_ptr(), K, B, H, H, Cin, k, k, 1, 0, OH, OH, plain.data_ptr(), st()))
     N.check(N.lib().dk_col2im_ex(dcol.data_ptr(), K, B, H, H, Cin, k, k, 1, 0, OH, OH, masked.data_ptr(), mask.data_ptr(), st()))
     assert torch.equal(masked, torch.where(mask.float() > 0, plain, torch.zeros_like(plain)))
+
+
+@pytest.mark.parametrize("B,Cc,K,dense,use_mask", [(256, 10, 200, False, True), (100, 2, 504, True, False),
+                                                  (33, 16, 64, False, True), (4096, 10, 1024, False, True)])
+def test_fused_classifier_head(N, B, Cc, K, dense, use_mask):
+    """logits GEMM + softmax cross-entropy + dgrad (+ dReLU mask) in one kernel vs PyTorch fp32."""
+    torch.manual_seed(17)
+    h = bf(torch.relu(torch.randn(B, K, device="cuda")) if use_mask else torch.randn(B, K, device="cuda"))
+    w = bf(torch.randn(Cc, K, device="cuda") * 0.1)
+    bias = torch.randn(Cc, device="cuda")
+    labels = torch.randint(0, Cc, (B,), device="cuda")
+    y = F.one_hot(labels, Cc).float()
+    ldz = (Cc + 7) // 8 * 8
+    dz = torch.full((B, ldz), 9.0, dtype=torch.bfloat16, device="cuda")
+    dh = torch.full((B, K), 9.0, dtype=torch.bfloat16, device="cuda")
+    hist = torch.zeros(4, 2, device="cuda")
+    step = torch.tensor([2], dtype=torch.int32, device="cuda")
+    li = labels.to(torch.int32)
+    alpha = 1.25
+    N.check(N.lib().dk_dense_softmax_head(h.data_ptr(), K, w.data_ptr(), K, bias.data_ptr(),
+                                          None if dense else li.data_ptr(), y.data_ptr() if dense else None, B, Cc, K,
+                                          dz.data_ptr(), ldz, dh.data_ptr(), K, alpha, int(use_mask), hist.data_ptr(),
+                                          step.data_ptr(), 4, st()))
+    z = h.float() @ w.float().t() + bias
+    p = torch.softmax(z, 1)
+    assert abs(float(hist[1, 0]) - float(F.cross_entropy(z, labels))) < 2e-3
+    assert abs(float(hist[1, 1]) - float((z.argmax(1) == labels).float().mean())) < 1e-6
+    g = (p - y) / B
+    assert torch.allclose(dz[:, :Cc].float(), g, atol=2e-3 / B + 1e-6, rtol=1e-2)
+    assert float(dz[:, Cc:].float().abs().max()) == 0.0 if ldz > Cc else True
+    ref = alpha * (dz[:, :Cc].float() @ w.float())
+    if use_mask:
+        ref = torch.where(h.float() > 0, ref, torch.zeros_like(ref))
+    assert torch.allclose(dh.float(), ref, atol=1e-2 * float(ref.abs().max()) + 1e-8, rtol=2e-2)
