@@ -178,8 +178,11 @@ softmax_xent_small_kernel(const float* __restrict__ logits, int ldl, const int* 
 //     dH = alpha * (dZ W), zeroed where H <= 0 when `use_mask` (dReLU / dropout of the producer).
 // It replaces a skinny forward GEMM (N = 10), the loss kernel and a skinny dgrad GEMM (K = 16): ~130
 // MFLOP at batch 16384, i.e. nothing for the tensor cores and three launch latencies on the critical
-// path.  Eight lanes share a row (each owns every 8th 16-byte chunk of it); W lives in shared memory
-// as fp32; per-row reductions are three xor-shuffles per class.
+// path.  Layout of the work: a warp owns 8 rows per pass; 8 lanes share a row (lane `sub` owns the
+// 16-byte chunks sub, sub + 8, ... of it) and every lane works on TWO rows (r and r + 4) so each
+// shared-memory read of W feeds 16 FMAs.  W is staged once per block as fp32 in a chunk-major layout
+// [chunk][class][8] whose chunk stride (8 C + 4 words) makes the 8 lanes of an LDS.128 phase hit
+// disjoint banks (measured: the naive [class][K] layout ran 6.5-way conflicted and smem-bound).
 // ------------------------------------------------------------------------------------------
 constexpr int kHeadMaxC = 16;
 
@@ -192,7 +195,11 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
   }
 }
 
-__global__ void __launch_bounds__(256)
+// MAXC: compile-time bound on the class count (2 / 10 / 16); NCH > 0: every lane keeps its (at most
+// NCH) chunks of both rows in registers -- all loads are issued back to back and the dReLU mask needs
+// no second read; NCH == 0 is the generic loop for K > 256.
+template <int MAXC, int NCH>
+__global__ void __launch_bounds__(128)
 dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __nv_bfloat16* __restrict__ Wb, int ldw,
                           const float* __restrict__ bias, const int* __restrict__ labels,
                           const float* __restrict__ labels_dense, int B, int C, int K,
@@ -200,121 +207,175 @@ dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __
                           float alpha, int use_mask, float* __restrict__ hist, const int* __restrict__ step,
                           int hist_slots) {
   DK_PDL_ENTER();
-  extern __shared__ float s_w[];  // [C][Kp] fp32
-  const int chunks = K >> 3;      // K % 8 == 0
-  const int Kp = K + 4;           // +4 floats: rows of W start on different banks
-  for (int i = threadIdx.x; i < C * K; i += blockDim.x) {
-    const int c = i / K, k = i - c * K;
-    s_w[c * Kp + k] = __bfloat162float(Wb[static_cast<size_t>(c) * ldw + k]);
+  extern __shared__ __align__(16) float s_w[];  // [chunks][C * 8 + 4]
+  const int chunks = K >> 3;                    // K % 8 == 0
+  const int SC = C * 8 + 4;
+  for (int i = threadIdx.x; i < C * chunks; i += blockDim.x) {  // one 16-byte load per 8 weights
+    const int c = i / chunks, ch = i - c * chunks;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(Wb + static_cast<size_t>(c) * ldw + (ch << 3)), f);
+    float* dst = s_w + ch * SC + c * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int sub = lane & 7, grp = lane >> 3;
   const float inv_b = 1.f / static_cast<float>(B);
   float loss_acc = 0.f, correct_acc = 0.f;
-  const int rows_per_iter = gridDim.x * (blockDim.x >> 5) * 4;
-  for (int row0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 4; row0 < B; row0 += rows_per_iter) {
-    const int row = row0 + grp;
-    const bool valid = row < B;
-    const __nv_bfloat16* hrow = H + static_cast<size_t>(valid ? row : 0) * ldh;
-    float acc[kHeadMaxC];
+  const int rows_per_pass = gridDim.x * nwarps * 8;
+  for (int row0 = (blockIdx.x * nwarps + warp) * 8; row0 < B; row0 += rows_per_pass) {
+    const int row[2] = {row0 + grp, row0 + 4 + grp};
+    const bool valid[2] = {row[0] < B, row[1] < B};
+    const __nv_bfloat16* hrow[2] = {H + static_cast<size_t>(valid[0] ? row[0] : 0) * ldh,
+                                    H + static_cast<size_t>(valid[1] ? row[1] : 0) * ldh};
+    float acc[2][MAXC];
 #pragma unroll
-    for (int c = 0; c < kHeadMaxC; ++c) acc[c] = 0.f;
-    for (int ch = sub; ch < chunks; ch += 8) {
-      float h[8];
-      unpack8(*reinterpret_cast<const uint4*>(hrow + (ch << 3)), h);
+    for (int c = 0; c < MAXC; ++c) acc[0][c] = acc[1][c] = 0.f;
+    uint4 hq[2][NCH > 0 ? NCH : 1];
+    if constexpr (NCH > 0) {
 #pragma unroll
-      for (int c = 0; c < kHeadMaxC; ++c) {
+      for (int j = 0; j < NCH; ++j) {
+        const int ch = sub + 8 * j;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+          hq[r][j] = ch < chunks ? *reinterpret_cast<const uint4*>(hrow[r] + (ch << 3)) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    auto fwd_chunk = [&](int ch, const uint4& qa, const uint4& qb) {
+      float ha[8], hb[8];
+      unpack8(qa, ha);
+      unpack8(qb, hb);
+      const float* wch = s_w + ch * SC;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
         if (c < C) {
-          const float* w = s_w + c * Kp + (ch << 3);
-          const float4 w0 = *reinterpret_cast<const float4*>(w), w1 = *reinterpret_cast<const float4*>(w + 4);
-          acc[c] += h[0] * w0.x + h[1] * w0.y + h[2] * w0.z + h[3] * w0.w + h[4] * w1.x + h[5] * w1.y + h[6] * w1.z +
-                    h[7] * w1.w;
+          const float4 w0 = *reinterpret_cast<const float4*>(wch + c * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wch + c * 8 + 4);
+          acc[0][c] += ha[0] * w0.x + ha[1] * w0.y + ha[2] * w0.z + ha[3] * w0.w + ha[4] * w1.x + ha[5] * w1.y +
+                       ha[6] * w1.z + ha[7] * w1.w;
+          acc[1][c] += hb[0] * w0.x + hb[1] * w0.y + hb[2] * w0.z + hb[3] * w0.w + hb[4] * w1.x + hb[5] * w1.y +
+                       hb[6] * w1.z + hb[7] * w1.w;
         }
       }
-    }
-    // reduce over the 8 lanes of the row (every lane ends up with the full logits)
+    };
+    if constexpr (NCH > 0) {
 #pragma unroll
-    for (int c = 0; c < kHeadMaxC; ++c) {
-      if (c < C) {
-        float v = acc[c];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        acc[c] = v + (bias != nullptr ? bias[c] : 0.f);
+      for (int j = 0; j < NCH; ++j)
+        if (sub + 8 * j < chunks) fwd_chunk(sub + 8 * j, hq[0][j], hq[1][j]);
+    } else {
+      for (int ch = sub; ch < chunks; ch += 8)
+        fwd_chunk(ch, *reinterpret_cast<const uint4*>(hrow[0] + (ch << 3)),
+                  *reinterpret_cast<const uint4*>(hrow[1] + (ch << 3)));
+    }
+    // reduce over the 8 lanes of a row (every lane ends up with the full logits), then softmax / loss
+    float g[2][MAXC];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float mx = -INFINITY;
+      int amax = 0;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+          float v = acc[r][c];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += bias != nullptr ? bias[c] : 0.f;
+          acc[r][c] = v;
+          if (v > mx) { mx = v; amax = c; }
+        }
+      }
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        g[r][c] = c < C ? __expf(acc[r][c] - mx) : 0.f;
+        se += g[r][c];
+      }
+      const float lse = __logf(se) + mx, inv_se = 1.f / se;
+      int label = 0;
+      float ysum = 1.f;
+      const float* y = nullptr;
+      if (valid[r]) {
+        if (labels_dense == nullptr) {
+          label = labels[row[r]];
+        } else {
+          y = labels_dense + static_cast<size_t>(row[r]) * C;
+          float ym = -INFINITY;
+          ysum = 0.f;
+          for (int c = 0; c < C; ++c) { const float t = y[c]; ysum += t; if (t > ym) { ym = t; label = c; } }
+        }
+      }
+      float row_loss = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+          const float t = y != nullptr ? y[c] : (c == label ? 1.f : 0.f);
+          row_loss += t * (lse - acc[r][c]);
+          // the bf16-rounded gradient is what the wgrad GEMM sees: use the same value for dH
+          g[r][c] = __bfloat162float(__float2bfloat16_rn((g[r][c] * inv_se * ysum - t) * inv_b));
+        }
+      }
+      if (valid[r] && sub == 0) {
+        loss_acc += row_loss;
+        correct_acc += (amax == label) ? 1.f : 0.f;
+      }
+      if (valid[r] && dz != nullptr) {
+        // lane `sub` stores the column pair (2 sub, 2 sub + 1) as one 4-byte word: the 8 lanes of a
+        // row write 32 contiguous bytes (pad columns up to ldz are zeros); ldz is even
+        uint32_t word = 0;
+#pragma unroll
+        for (int c = 0; c < MAXC; c += 2)
+          if ((c >> 1) == sub) word = pack_bf16x2(g[r][c], c + 1 < MAXC ? g[r][c + 1] : 0.f);
+        if (2 * sub < ldz) *reinterpret_cast<uint32_t*>(dz + static_cast<size_t>(row[r]) * ldz + 2 * sub) = word;
       }
     }
-    float mx = -INFINITY;
-    int amax = 0;
+    auto bwd_chunk = [&](int ch, const uint4& qa, const uint4& qb) {
+      float d[2][8];
 #pragma unroll
-    for (int c = 0; c < kHeadMaxC; ++c)
-      if (c < C && acc[c] > mx) { mx = acc[c]; amax = c; }
-    float e[kHeadMaxC], se = 0.f;
+      for (int u = 0; u < 8; ++u) d[0][u] = d[1][u] = 0.f;
+      const float* wch = s_w + ch * SC;
 #pragma unroll
-    for (int c = 0; c < kHeadMaxC; ++c) {
-      e[c] = c < C ? __expf(acc[c] - mx) : 0.f;
-      se += e[c];
-    }
-    const float lse = __logf(se) + mx, inv_se = 1.f / se;
-    int label = 0;
-    float ysum = 1.f;
-    const float* y = nullptr;
-    if (valid) {
-      if (labels_dense == nullptr) {
-        label = labels[row];
-      } else {
-        y = labels_dense + static_cast<size_t>(row) * C;
-        float ym = -INFINITY;
-        ysum = 0.f;
-        for (int c = 0; c < C; ++c) { const float t = y[c]; ysum += t; if (t > ym) { ym = t; label = c; } }
-      }
-    }
-    float g[kHeadMaxC], row_loss = 0.f;
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wch + c * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wch + c * 8 + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-    for (int c = 0; c < kHeadMaxC; ++c) {
-      g[c] = 0.f;
-      if (c < C) {
-        const float t = y != nullptr ? y[c] : (c == label ? 1.f : 0.f);
-        row_loss += t * (lse - acc[c]);
-        // the bf16-rounded gradient is what the wgrad GEMM sees: use the same value for dH
-        g[c] = __bfloat162float(__float2bfloat16_rn((e[c] * inv_se * ysum - t) * inv_b));
-      }
-    }
-    if (valid && sub == 0) {
-      loss_acc += row_loss;
-      correct_acc += (amax == label) ? 1.f : 0.f;
-    }
-    if (valid && dz != nullptr) {
-      // lane `sub` stores columns sub and sub + 8 (pad columns up to ldz are written as zeros)
-#pragma unroll
-      for (int c = 0; c < kHeadMaxC; ++c)
-        if ((c & 7) == sub && c < ldz) dz[static_cast<size_t>(row) * ldz + c] = __float2bfloat16_rn(g[c]);
-    }
-    if (valid && dH != nullptr) {
-      for (int ch = sub; ch < chunks; ch += 8) {
-        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < kHeadMaxC; ++c) {
-          if (c < C) {
-            const float* w = s_w + c * Kp + (ch << 3);
-            const float4 w0 = *reinterpret_cast<const float4*>(w), w1 = *reinterpret_cast<const float4*>(w + 4);
-            d[0] += g[c] * w0.x; d[1] += g[c] * w0.y; d[2] += g[c] * w0.z; d[3] += g[c] * w0.w;
-            d[4] += g[c] * w1.x; d[5] += g[c] * w1.y; d[6] += g[c] * w1.z; d[7] += g[c] * w1.w;
+          for (int u = 0; u < 8; ++u) {
+            d[0][u] += g[0][c] * wv[u];
+            d[1][u] += g[1][c] * wv[u];
           }
         }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
         if (use_mask) {
           float h[8];
-          unpack8(*reinterpret_cast<const uint4*>(hrow + (ch << 3)), h);
+          unpack8(r == 0 ? qa : qb, h);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) d[u] = h[u] > 0.f ? d[u] * alpha : 0.f;
+          for (int u = 0; u < 8; ++u) d[r][u] = h[u] > 0.f ? d[r][u] * alpha : 0.f;
         } else {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) d[u] *= alpha;
+          for (int u = 0; u < 8; ++u) d[r][u] *= alpha;
         }
-        uint4 o;
-        o.x = pack_bf16x2(d[0], d[1]); o.y = pack_bf16x2(d[2], d[3]);
-        o.z = pack_bf16x2(d[4], d[5]); o.w = pack_bf16x2(d[6], d[7]);
-        *reinterpret_cast<uint4*>(dH + static_cast<size_t>(row) * lddh + (ch << 3)) = o;
+        if (valid[r]) {
+          uint4 o;
+          o.x = pack_bf16x2(d[r][0], d[r][1]); o.y = pack_bf16x2(d[r][2], d[r][3]);
+          o.z = pack_bf16x2(d[r][4], d[r][5]); o.w = pack_bf16x2(d[r][6], d[r][7]);
+          *reinterpret_cast<uint4*>(dH + static_cast<size_t>(row[r]) * lddh + (ch << 3)) = o;
+        }
+      }
+    };
+    if (dH != nullptr) {
+      if constexpr (NCH > 0) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+          if (sub + 8 * j < chunks) bwd_chunk(sub + 8 * j, hq[0][j], hq[1][j]);
+      } else {
+        for (int ch = sub; ch < chunks; ch += 8)
+          bwd_chunk(ch, *reinterpret_cast<const uint4*>(hrow[0] + (ch << 3)),
+                    *reinterpret_cast<const uint4*>(hrow[1] + (ch << 3)));
       }
     }
   }
@@ -325,13 +386,35 @@ dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __
   __syncthreads();
   if (threadIdx.x == 0 && hist != nullptr) {
     float l = 0.f, c = 0.f;
-    for (int i = 0; i < (blockDim.x >> 5); ++i) { l += s_loss[i]; c += s_corr[i]; }
+    for (int i = 0; i < nwarps; ++i) { l += s_loss[i]; c += s_corr[i]; }
     int slot = step != nullptr ? (*step - 1) : 0;
     if (slot < 0) slot = 0;
     if (hist_slots > 0) slot %= hist_slots;
     atomicAdd(hist + 2 * slot, l * inv_b);
     atomicAdd(hist + 2 * slot + 1, c * inv_b);
   }
+}
+
+// host-side dispatch of the fused head (class-count / chunk-count specialisations)
+template <int MAXC>
+static int launch_head(const void* H, int ldh, const void* Wb, int ldw, const float* bias, const int* labels,
+                       const float* labels_dense, int B, int C, int K, void* dz, int ldz, void* dH, int lddh,
+                       float alpha, int use_mask, float* hist, const int* step, int hist_slots, void* stream,
+                       size_t smem) {
+  int blocks = (B + 31) / 32;                // 4 warps x 8 rows per pass
+  if (blocks > 148 * 4) blocks = 148 * 4;    // resident blocks stage W once and walk their rows
+  const int per_lane = (K / 8 + 7) / 8;      // 16-byte chunks each of the 8 lanes of a row owns
+#define DK_HEAD_LAUNCH(NCH)                                                                                          \
+  DK_HOST_CHECK(DK_LAUNCH((dense_softmax_head_kernel<MAXC, NCH>), blocks, 128, smem, (cudaStream_t)stream,           \
+      reinterpret_cast<const __nv_bfloat16*>(H), ldh, reinterpret_cast<const __nv_bfloat16*>(Wb), ldw, bias, labels, \
+      labels_dense, B, C, K, reinterpret_cast<__nv_bfloat16*>(dz), ldz, reinterpret_cast<__nv_bfloat16*>(dH), lddh,  \
+      alpha, use_mask, hist, step, hist_slots))
+  if (per_lane <= 2) { DK_HEAD_LAUNCH(2); }
+  else if (per_lane <= 4) { DK_HEAD_LAUNCH(4); }
+  else { DK_HEAD_LAUNCH(0); }
+#undef DK_HEAD_LAUNCH
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
 }
 
 // mean-squared-error / binary cross-entropy (on probabilities) for non-softmax heads
@@ -432,22 +515,22 @@ int dk_softmax_xent(const float* logits, int ldl, const int* labels, const float
 }
 
 // Fused classifier head; returns -7 when the shape is outside what the kernel covers (the caller
-// then uses GEMM + dk_softmax_xent + GEMM): C <= 16, K % 8 == 0, ldh / lddh % 8 == 0, W in <= 48 KB smem.
+// then uses GEMM + dk_softmax_xent + GEMM): C <= 16, K % 8 == 0, ld % 8 == 0, W in <= 48 KB smem.
 int dk_dense_softmax_head(const void* H, int ldh, const void* Wb, int ldw, const float* bias, const int* labels,
                           const float* labels_dense, int B, int C, int K, void* dz, int ldz, void* dH, int lddh,
                           float alpha, int use_mask, float* hist, const int* step, int hist_slots, void* stream) {
-  const size_t smem = static_cast<size_t>(C) * (K + 4) * sizeof(float);
+  const size_t smem = static_cast<size_t>(K / 8) * (C * 8 + 4) * sizeof(float);
   if (C < 1 || C > kHeadMaxC || K % 8 != 0 || ldh % 8 != 0 || (dH != nullptr && lddh % 8 != 0) || ldz > kHeadMaxC ||
-      ldz < C || smem > 48 * 1024)
+      ldz < C || ldz % 2 != 0 || ldw % 8 != 0 || smem > 48 * 1024)
     return -7;
-  int blocks = (B + 31) / 32;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  DK_HOST_CHECK(DK_LAUNCH(dense_softmax_head_kernel, blocks, 256, smem, (cudaStream_t)stream,
-      reinterpret_cast<const __nv_bfloat16*>(H), ldh, reinterpret_cast<const __nv_bfloat16*>(Wb), ldw, bias, labels,
-      labels_dense, B, C, K, reinterpret_cast<__nv_bfloat16*>(dz), ldz, reinterpret_cast<__nv_bfloat16*>(dH), lddh,
-      alpha, use_mask, hist, step, hist_slots));
-  DK_HOST_CHECK(cudaGetLastError());
-  return 0;
+  if (C <= 2)
+    return launch_head<2>(H, ldh, Wb, ldw, bias, labels, labels_dense, B, C, K, dz, ldz, dH, lddh, alpha, use_mask, hist,
+                          step, hist_slots, stream, smem);
+  if (C <= 10)
+    return launch_head<10>(H, ldh, Wb, ldw, bias, labels, labels_dense, B, C, K, dz, ldz, dH, lddh, alpha, use_mask,
+                           hist, step, hist_slots, stream, smem);
+  return launch_head<16>(H, ldh, Wb, ldw, bias, labels, labels_dense, B, C, K, dz, ldz, dH, lddh, alpha, use_mask, hist,
+                         step, hist_slots, stream, smem);
 }
 
 int dk_elementwise_loss(int kind, const float* out, const float* target, int B, int C, void* dz, int ldz,

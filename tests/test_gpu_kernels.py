@@ -1,7 +1,6 @@
 """Numerics of every native sm_100a kernel against a plain PyTorch fp32 reference (needs a B200)."""
 import ctypes as C
 
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F

@@ -2,7 +2,7 @@ import numpy as np
 import pytest
 import torch
 
-from distkeras_b200.models import (Conv2D, Dense, Dropout, Flatten, MaxPooling2D, Sequential, cifar10_cnn, higgs_mlp,
+from distkeras_b200.models import (Dense, Sequential, cifar10_cnn, higgs_mlp,
                                    mnist_convnet, mnist_mlp, model_from_json, resnet18)
 from distkeras_b200.utils import deserialize_keras_model, serialize_keras_model, uniform_weights
 

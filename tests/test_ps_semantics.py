@@ -7,15 +7,15 @@ import pytest
 import torch
 
 from distkeras_b200 import networking
-from distkeras_b200.data import Dataset, synthetic_mnist
-from distkeras_b200.models import Dense, Sequential, mnist_mlp
+from distkeras_b200.data import Dataset
+from distkeras_b200.models import Dense, Sequential
 from distkeras_b200.ops.flat_optim import FlatOptimizer
 from distkeras_b200.parameter_servers import (ADAGParameterServer, DeltaParameterServer, DynSGDParameterServer,
                                               ExperimentalParameterServer)
 from distkeras_b200.schemes import Emperor
 from distkeras_b200.trainers import (ADAG, AEASGD, DOWNPOUR, EAMSGD, AveragingTrainer, DynSGD, EnsembleTrainer,
                                      Experimental, SingleTrainer)
-from distkeras_b200.workers import AEASGDWorker, InProcessClient
+from distkeras_b200.workers import AEASGDWorker
 
 
 def tiny_model(seed=0):
