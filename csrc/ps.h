@@ -10,7 +10,8 @@ enum {
   DK_CTRL_STOP = 3,             // stop flag (fault handling)
   DK_CTRL_SHARD_NEXT = 4,       // dynamic shard queue: next unclaimed data partition
   DK_CTRL_WORKERS_DONE = 5,     // workers that finished their shards
-  DK_CTRL_HEARTBEAT = 16,       // + worker id: number of commits by that worker (liveness counter)
+  DK_CTRL_HEARTBEAT = 16,       // + worker id (< 40): number of commits by that worker (liveness counter)
+  DK_CTRL_DONE_FLAGS = 56,      // + worker id (< 40): non-zero once that worker finished its shards
   DK_CTRL_STALENESS_HIST = 96,  // 32 buckets
   DK_CTRL_WORDS = 128
 };

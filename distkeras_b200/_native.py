@@ -46,7 +46,8 @@ LOSS_XENT, LOSS_MSE, LOSS_BCE = 0, 1, 2
 
 # control block words (csrc/ps.h)
 CTRL_NUM_UPDATES, CTRL_LOCK_NEXT, CTRL_LOCK_SERVING, CTRL_STOP, CTRL_SHARD_NEXT, CTRL_WORKERS_DONE = 0, 1, 2, 3, 4, 5
-CTRL_HEARTBEAT, CTRL_STALENESS_HIST, CTRL_WORDS = 16, 96, 128
+CTRL_HEARTBEAT, CTRL_DONE_FLAGS, CTRL_STALENESS_HIST, CTRL_WORDS = 16, 56, 96, 128
+CTRL_MAX_WORKERS = 40
 
 _SIGNATURES = {
     # gemm

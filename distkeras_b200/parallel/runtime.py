@@ -30,6 +30,7 @@ import torch
 from .. import _native as N
 from ..data import Dataset, Partition
 from ..utils import deserialize_keras_model, serialize_keras_model
+from ..utils.config import fault_injection_point
 from ..utils.timing import log_event
 from .engine import NativeReplica, UnsupportedByNativeEngine
 from .fabric import FabricRegion
@@ -275,6 +276,8 @@ class FabricWorker:
         """Train one window on ``tau * B`` rows of (pinned) host data.  Asynchronous: returns once the
         H2D copies and the graph replay are enqueued; at most two windows are in flight."""
         p = self.windows_run & 1
+        for it in range(self.iteration + 1, self.iteration + self.tau + 1):
+            fault_injection_point(self.worker_id, it)  # DK_FAULT test hook: fails BEFORE anything is enqueued
         if _NVTX:
             torch.cuda.nvtx.range_push(f"dk.window[{self.windows_run}] w{self.worker_id}")
         self._collect(p)  # window (n - 2) used this parity: wait for it, harvest its history
@@ -298,6 +301,18 @@ class FabricWorker:
         for p in ((self.windows_run & 1), ((self.windows_run + 1) & 1)):
             self._collect(p)
         self.compute.synchronize()
+
+    def recover(self) -> None:
+        """After a failed task: finish what is in flight, drop the uncommitted window and adopt the
+        CURRENT center -- what a re-run Spark task does when it reconnects and pulls
+        (``workers.py:286-288``).  Optimizer state is kept."""
+        try:
+            self.drain()
+        except Exception:
+            torch.cuda.synchronize(self.rep.device)
+            self._pending = [None, None]
+        self.initial_pull()
+        self.rep.step_counter.zero_().add_(self.windows_run * self.tau)
 
     def train_partition(self, part: Partition, features_col: str, label_col: str, num_epoch: int = 1) -> None:
         """Consume a data partition: full windows through the graphs; the uncommitted tail (fewer
@@ -424,6 +439,10 @@ class FabricEagerWorker:
     def drain(self) -> None:
         torch.cuda.synchronize(self.device)
 
+    def recover(self) -> None:
+        self.drain()
+        self.initial_pull()
+
     def train_partition(self, part: Partition, features_col: str, label_col: str, num_epoch: int = 1) -> None:
         x_all, y_all = part.column(features_col), part.column(label_col)
         pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd")
@@ -431,6 +450,7 @@ class FabricEagerWorker:
         for _ in range(num_epoch):
             for b in range(n):
                 self.iteration += 1
+                fault_injection_point(self.worker_id, self.iteration)
                 x = x_all[b * self.B:(b + 1) * self.B].to(self.device, non_blocking=True).float()
                 if self.scale != 1.0 or self.shift != 0.0:
                     x = x * self.scale + self.shift
@@ -504,6 +524,61 @@ class FabricExchange:
                                    w._stream()), "commit")
 
 
+class FabricWatchdog:
+    """Liveness monitor on the rank that owns the center.
+
+    Every commit kernel bumps its worker's heartbeat word in the control block and a worker raises its
+    done flag when it has consumed its shards, so liveness is observable without the parameter server
+    ever waiting on anybody: a worker whose heartbeat has not moved for ``timeout`` seconds and whose
+    done flag is still zero is reported as stalled (structured log + ``stats["watchdog"]``).
+    """
+
+    def __init__(self, region: FabricRegion, num_workers: int, device_index: int, interval: float = 0.5,
+                 timeout: float = 30.0):
+        import threading
+
+        self.region, self.n = region, min(int(num_workers), N.CTRL_MAX_WORKERS)
+        self.device_index, self.interval, self.timeout = int(device_index), float(interval), float(timeout)
+        self.stalled: dict = {}      # worker id -> seconds without progress when it was flagged
+        self.heartbeats: List[int] = [0] * self.n
+        self.polls = 0
+        self._halt = threading.Event()
+        self._thread = threading.Thread(target=self._loop, daemon=True, name="dk-watchdog")
+
+    def start(self) -> None:
+        self._thread.start()
+
+    def stop(self) -> dict:
+        self._halt.set()
+        self._thread.join(timeout=30)
+        return {"stalled": dict(self.stalled), "heartbeats": list(self.heartbeats), "polls": self.polls}
+
+    def poll(self, ctrl, now: float, last_change: List[float]) -> None:
+        for w in range(self.n):
+            hb, done = int(ctrl[N.CTRL_HEARTBEAT + w]), int(ctrl[N.CTRL_DONE_FLAGS + w])
+            if hb != self.heartbeats[w] or done:
+                self.heartbeats[w] = hb
+                last_change[w] = now
+                continue
+            idle = now - last_change[w]
+            if idle > self.timeout and w not in self.stalled:
+                self.stalled[w] = idle
+                log_event("fabric.worker_stalled", worker_id=w, idle_seconds=round(idle, 3), heartbeat=hb)
+        self.polls += 1
+
+    def _loop(self) -> None:
+        torch.cuda.set_device(self.device_index)
+        stream = torch.cuda.Stream(self.device_index)
+        ctrl = torch.zeros(N.CTRL_WORDS, dtype=torch.int32).pin_memory()
+        lib, st = N.lib(), C.c_void_p(stream.cuda_stream)
+        last_change = [time.time()] * self.n
+        while not self._halt.wait(self.interval):
+            N.check(lib.dk_memcpy_async(C.c_void_p(ctrl.data_ptr()), C.c_void_p(self.region.ctrl_ptr), 4 * N.CTRL_WORDS, 2,
+                                        st), "watchdog ctrl D2H")
+            stream.synchronize()
+            self.poll(ctrl, time.time(), last_change)
+
+
 class CenterCheckpointer:
     """Periodic snapshots of the center variable while the workers train.
 
@@ -559,6 +634,12 @@ class CenterCheckpointer:
 # ================================================================================================
 # orchestration
 # ================================================================================================
+def _scratch_i32(worker) -> torch.Tensor:
+    if getattr(worker, "_scratch", None) is None:
+        worker._scratch = torch.zeros(1, dtype=torch.int32, device=worker.rep.device)
+    return worker._scratch
+
+
 def _affine_for(dataset: Dataset, features_col: str):
     """uint8 features are shipped raw and normalised to [0, 1] on the device (fused MinMax)."""
     x = dataset[features_col]
@@ -620,6 +701,11 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         checkpointer = CenterCheckpointer(model, region, trainer.checkpoint_path, trainer.checkpoint_interval, local,
                                           shards=shards)
         checkpointer.start()
+    watchdog = None
+    if rank == 0 and getattr(trainer, "watchdog_timeout", None):
+        watchdog = FabricWatchdog(region, trainer.num_workers, local, interval=getattr(trainer, "watchdog_interval", 0.5),
+                                  timeout=trainer.watchdog_timeout)
+        watchdog.start()
     num_workers = min(trainer.num_workers, world)
     dedicated = bool(getattr(trainer, "dedicated_ps", False)) and world > 1
     worker_ranks = list(range(1, world)) if dedicated else list(range(world))
@@ -671,9 +757,30 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         t0 = time.time()
         with torch.cuda.stream(worker.compute):
             ev0.record(worker.compute)
+        failures: List[dict] = []
+        tolerate = bool(getattr(trainer, "tolerate_worker_failures", False))
+
+        def run_task(part) -> None:
+            """One data partition = one task.  With ``tolerate_worker_failures`` a failed task is re-run
+            (at most twice) after the worker re-pulled the current center; the failed attempt's history
+            is discarded, like the result of a failed Spark task."""
+            for attempt in range(3):
+                mark = len(worker.history)
+                try:
+                    worker.train_partition(part, trainer.features_column, trainer.label_column, trainer.num_epoch)
+                    return
+                except Exception as exc:
+                    if not tolerate or attempt == 2:
+                        raise
+                    failures.append({"worker_id": wid, "partition": part.index, "attempt": attempt,
+                                     "iteration": worker.iteration, "error": repr(exc)})
+                    log_event("fabric.task_failed", **failures[-1])
+                    worker.recover()
+                    del worker.history[mark:]
+
         if static:
             for part in my_parts:
-                worker.train_partition(part, trainer.features_column, trainer.label_column, trainer.num_epoch)
+                run_task(part)
         else:
             # dynamic shard queue: claim partitions with a fetch-add on the PS control block
             claim = torch.zeros(1, dtype=torch.int32, device=worker.rep.device)
@@ -684,9 +791,13 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
                 idx = int(claim.item())
                 if idx >= n_parts:
                     break
-                worker.train_partition(parts[idx], trainer.features_column, trainer.label_column, trainer.num_epoch)
+                run_task(parts[idx])
         with torch.cuda.stream(worker.compute):
             ev1.record(worker.compute)
+            if wid < N.CTRL_MAX_WORKERS:  # raise this worker's done flag for the watchdog
+                N.check(worker.lib.dk_ps_fetch_add(C.c_void_p(region.ctrl_ptr + 4 * (N.CTRL_DONE_FLAGS + wid)), 1,
+                                                   _scratch_i32(worker).data_ptr(),
+                                                   C.c_void_p(N.current_stream())), "done flag")
         torch.cuda.synchronize()
         steps_done = worker.iteration - it0
         windows_done = worker.windows_run - w0
@@ -695,7 +806,7 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         stats = {"kernels_per_window": worker.kernels_per_window, "windows": windows_done, "steps": steps_done,
                  "gpu_launches": windows_done * worker.kernels_per_window + tail_steps * per_step,
                  "h2d_bytes": worker.h2d_bytes, "d2h_bytes": worker.d2h_bytes, "seconds": time.time() - t0,
-                 "device_ms": ev0.elapsed_time(ev1), "executor": type(worker).__name__}
+                 "device_ms": ev0.elapsed_time(ev1), "executor": type(worker).__name__, "failures": failures}
         history = worker.history
         log_event("fabric.worker_done", rank=rank, worker_id=wid, **stats)
         # release the replica's device buffers / graphs before the next job in this process
@@ -715,6 +826,8 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
     if checkpointer is not None:
         checkpointer.stop()
         stats["checkpoint_snapshots"] = checkpointer.snapshots
+    if watchdog is not None:
+        stats["watchdog"] = watchdog.stop()
     if rank == 0:
         result["num_updates"] = ps.get_num_updates()
         result["staleness_hist"] = ps.staleness_histogram().tolist()

@@ -306,7 +306,8 @@ class DistributedTrainer(Trainer):
         self.strict = bool(int(os.environ.get("DK_STRICT", "0")))
         self.checkpoint_path: Optional[str] = None       # final checkpoint (all backends)
         self.checkpoint_interval: Optional[float] = None  # seconds between mid-run snapshots (fabric backend)
-        self.tolerate_worker_failures = False
+        self.tolerate_worker_failures = False            # re-run a failed task instead of failing the job
+        self.watchdog_timeout: Optional[float] = None     # seconds without a heartbeat before a worker is flagged
         self.worker_failures: list = []
 
     # -- accessors (``trainers.py:389-460``) ---------------------------------------------------
@@ -404,6 +405,8 @@ class DistributedTrainer(Trainer):
             self.record_training_start()
             model, self.history = train_distributed_fabric(self, dataframe)
             self.record_training_end()
+            self.worker_failures = [f for st in (getattr(self, "fabric_stats", None) or [])
+                                    for f in (st or {}).get("failures", [])]
             self._save_final_checkpoint(model, self.num_updates())
             return model
         if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1 and backend in ("socket", "spmd"):

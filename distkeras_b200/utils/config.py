@@ -29,11 +29,16 @@ class RuntimeConfig:
         trainer.dedicated_ps = self.dedicated_ps
 
 
+_FIRED: set = set()
+
+
 def fault_injection_point(worker_id: int, iteration: int) -> None:
-    """Test hook: ``DK_FAULT=<worker>:<iteration>`` makes that worker fail there."""
+    """Test hook: ``DK_FAULT=<worker>:<iteration>`` makes that worker fail there.  Like
+    a real crash the fault fires ONCE per process and spec, so a retried task gets past it."""
     spec = os.environ.get("DK_FAULT")
-    if not spec:
+    if not spec or spec in _FIRED:
         return
     w, it = spec.split(":")
     if int(w) == int(worker_id) and int(it) == int(iteration):
+        _FIRED.add(spec)
         raise RuntimeError(f"injected fault: worker {worker_id} at iteration {iteration}")

@@ -325,3 +325,54 @@ def test_fabric_periodic_and_final_checkpoint(tmp_path):
     from distkeras_b200.utils import deserialize_keras_model
 
     assert torch.equal(deserialize_keras_model(t2.master_model).get_flat_weights(), model.get_flat_weights())
+
+
+def test_fabric_task_failure_is_retried(monkeypatch):
+    """DK_FAULT kills worker 0 at iteration 9; with tolerate_worker_failures the task is re-run after the
+    worker re-pulled the center (Spark task-retry semantics) and the job completes."""
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.trainers import ADAG
+
+    g = torch.Generator().manual_seed(0)
+    n, B = 4096, 128
+    proto = torch.randint(0, 200, (10, 64), generator=g)
+    y = torch.randint(0, 10, (n,), generator=g)
+    x = (proto[y] + torch.randint(0, 56, (n, 64), generator=g)).clamp(0, 255).to(torch.uint8)
+    ds = Dataset({"features": x, "label": y.to(torch.int32)})
+    monkeypatch.setenv("DK_FAULT", "0:9")
+    t = ADAG(_mlp(0), {"class_name": "adam", "config": {"lr": 0.003}}, "categorical_crossentropy", num_workers=1,
+             batch_size=B, num_epoch=1, communication_window=4)
+    t.backend = "fabric"
+    with pytest.raises(RuntimeError, match="injected fault"):
+        t.train(ds)  # default: failures surface
+    monkeypatch.setenv("DK_FAULT", "0:10")  # a fault fires once per spec: arm a new one
+    t.tolerate_worker_failures = True
+    model = t.train(ds)
+    assert len(t.worker_failures) == 1 and t.worker_failures[0]["worker_id"] == 0
+    assert len(t.get_history()) == n // B  # the failed attempt's records were discarded
+    model.compile("categorical_crossentropy")
+    assert model.evaluate(x.float() / 255.0, y)[1] > 0.7
+
+
+def test_fabric_watchdog_flags_silent_workers():
+    from distkeras_b200 import _native as N
+    from distkeras_b200.parallel.runtime import FabricWatchdog
+    from distkeras_b200.parameter_servers import FabricParameterServer
+    import ctypes as C
+    import time
+
+    ps = FabricParameterServer(_mlp(0), device_index=0)
+    ps.initialize()
+    try:
+        # worker 1 "finished" (done flag raised), workers 0 and 2 never commit
+        out = torch.zeros(1, dtype=torch.int32, device="cuda")
+        N.check(N.lib().dk_ps_fetch_add(C.c_void_p(ps.region.ctrl_ptr + 4 * (N.CTRL_DONE_FLAGS + 1)), 1, out.data_ptr(),
+                                        C.c_void_p(N.current_stream())), "fetch_add")
+        torch.cuda.synchronize()
+        wd = FabricWatchdog(ps.region, 3, 0, interval=0.02, timeout=0.1)
+        wd.start()
+        time.sleep(0.6)
+        report = wd.stop()
+        assert sorted(report["stalled"]) == [0, 2] and report["polls"] >= 3
+    finally:
+        ps.stop()

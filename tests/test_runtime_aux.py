@@ -53,6 +53,7 @@ def test_fault_injection_is_survivable(monkeypatch):
     t.backend = "thread"
     with pytest.raises(RuntimeError, match="injected fault"):
         t.train(tiny_data())  # default: failures surface (the reference prints and swallows them)
+    monkeypatch.setenv("DK_FAULT", "1:4")  # a fault fires once per spec: arm a new one for the second run
     t2 = ADAG(tiny_model(0), "sgd", "categorical_crossentropy", num_workers=2, batch_size=16, communication_window=2)
     t2.backend = "thread"
     t2.tolerate_worker_failures = True
