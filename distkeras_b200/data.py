@@ -245,6 +245,23 @@ class Dataset:
     def collect(self) -> List[Row]:
         return list(Partition(self, 0, 0, self._n))
 
+    def limit(self, n: int) -> "Dataset":
+        return Dataset({k: v[:n] for k, v in self.columns_data.items()}, self.num_partitions)
+
+    def show(self, n: int = 20) -> None:
+        """Print the first ``n`` rows (vectors abbreviated), like ``DataFrame.show``."""
+        names = self.columns
+        print(" | ".join(names))
+        for row in self.take(n):
+            cells = []
+            for k in names:
+                v = np.asarray(row[k].cpu() if torch.is_tensor(row[k]) else row[k]).reshape(-1)
+                if v.size > 6:
+                    cells.append(f"[{', '.join(f'{float(t):.3g}' for t in v[:3])}, ... x{v.size}]")
+                else:
+                    cells.append(str(v.tolist() if v.size > 1 else v.item()))
+            print(" | ".join(cells))
+
     def printSchema(self) -> None:
         for k, v in self.columns_data.items():
             print(f" |-- {k}: {str(v.dtype).replace('torch.', '')}{list(v.shape[1:])}")
@@ -284,6 +301,8 @@ class Dataset:
             bounds.append(int(round(acc * self._n)))
         bounds[-1] = self._n
         return [self.take_rows(perm[bounds[i]:bounds[i + 1]]) for i in range(len(weights))]
+
+    split = randomSplit
 
     def sample(self, fraction: float, seed: Optional[int] = None) -> "Dataset":
         return self.randomSplit([fraction, 1.0 - fraction], seed)[0]
