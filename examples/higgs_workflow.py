@@ -2,6 +2,7 @@
 """The reference's ``examples/workflow.ipynb`` / ``example_1_analysis.ipynb``: ATLAS-Higgs-shaped
 data, StandardTransformer-normalised features, a 30-500-500-500-2 MLP, SingleTrainer vs the
 asynchronous trainers, accuracy / F1 / training time side by side."""
+import argparse
 import os
 import sys
 
@@ -17,7 +18,11 @@ from distkeras_b200.trainers import AEASGD, DOWNPOUR, EAMSGD, SingleTrainer
 from distkeras_b200.transformers import LabelIndexTransformer, OneHotTransformer
 from distkeras_b200.utils import shuffle
 
-raw = shuffle(synthetic_higgs(200_000), seed=0)
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=int, default=200_000)
+args = ap.parse_args()
+
+raw = shuffle(synthetic_higgs(args.rows), seed=0)
 x = raw["features"]
 raw = raw.with_column("features_normalized", (x - x.mean(0)) / x.std(0, unbiased=False))  # StandardScaler step
 raw = OneHotTransformer(2, "label", "label_encoded").transform(raw)
