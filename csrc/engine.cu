@@ -99,6 +99,15 @@ int run_op(Engine* e, Op& op, void* main_stream) {
       // M, N, K, w_local, w1_local, wb_local, ldw (tensor maps + epilogue pre-encoded)
       return dk_gemm_pull_launch(&op.ta, &op.tb, op.has_td ? &op.td : nullptr, &op.ep, (int)a[0], (int)a[1], (int)a[2],
                                  rp<float>(e, a[3]), rp<float>(e, a[4]), resolve(e, a[5]), (int)a[6], st);
+    case DK_OP_CONV_GEMM:
+      // src, SH, SW, C, GH, GW, KH, KW, mul, off, div, M, N, K, bn (weight / output / mask maps + epilogue pre-encoded)
+      return dk_conv_gemm_launch(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], (int)a[6],
+                                 (int)a[7], (int)a[8], (int)a[9], (int)a[10], &op.tb, op.has_td ? &op.td : nullptr,
+                                 op.has_tm ? &op.tm : nullptr, &op.ep, (int)a[11], (int)a[12], (int)a[13], (int)a[14], st);
+    case DK_OP_WFLIP:
+      // w, ldw, wd, ldwd, Cout, Cin, KH, KW
+      return dk_conv_weight_flip(resolve(e, a[0]), (int)a[1], resolve(e, a[2]), (int)a[3], (int)a[4], (int)a[5], (int)a[6],
+                                 (int)a[7], st);
     case DK_OP_GEMM:
       // M, N, K, bn, flags (tensor maps + epilogue pre-encoded)
       return dk_gemm_tn_launch2(&op.ta, &op.tb, op.has_td ? &op.td : nullptr, op.has_tm ? &op.tm : nullptr, &op.ep,
@@ -349,6 +358,28 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
                  ? dk_gemm_pick_splits(M, N, K, bn, flags & DK_GEMM_TF32)
                  : 1;
   op.i[0] = M; op.i[1] = N; op.i[2] = K; op.i[3] = bn; op.i[4] = flags; op.i[5] = splits;
+  e->lists[list].push_back(op);
+  return static_cast<int>(e->lists[list].size()) - 1;
+}
+
+int dk_engine_add_conv_gemm(void* h, int list, const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW,
+                            int mul, int off, int div, const void* Bmat, long ldb, int M, int N, int K,
+                            const DkGemmEpilogue* ep) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (list < 0 || list >= (int)e->lists.size()) return -1;
+  Op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = DK_OP_CONV_GEMM;
+  op.stream_id = e->build_stream;
+  const int bn = dk_conv_pick_bn(N);
+  int r = dk_tmap_encode_2d(&op.tb, Bmat, DK_BF16, N, K, ldb, bn);
+  if (r != 0) return r;
+  op.ep = *ep;
+  op.has_td = ep->d != nullptr && dk_gemm_encode_output(&op.td, ep->d, ep->ldd, M, N, ep->d_fp32) == 0;
+  op.has_tm = ep->mask != nullptr && dk_gemm_encode_output(&op.tm, ep->mask, ep->ld_mask, M, N, 0) == 0;
+  op.i[0] = (int64_t)(uintptr_t)src;
+  op.i[1] = SH; op.i[2] = SW; op.i[3] = C; op.i[4] = GH; op.i[5] = GW; op.i[6] = KH; op.i[7] = KW;
+  op.i[8] = mul; op.i[9] = off; op.i[10] = div; op.i[11] = M; op.i[12] = N; op.i[13] = K; op.i[14] = bn;
   e->lists[list].push_back(op);
   return static_cast<int>(e->lists[list].size()) - 1;
 }

@@ -47,7 +47,9 @@ enum {
   DK_OP_BN_BWD = 34,
   DK_OP_GAP_FWD = 35,
   DK_OP_GAP_BWD = 36,
-  DK_OP_HEAD = 37
+  DK_OP_HEAD = 37,
+  DK_OP_CONV_GEMM = 38,
+  DK_OP_WFLIP = 39
 };
 
 #ifdef __cplusplus
@@ -67,6 +69,10 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
                        int K, int flags, int bn, int splits, const DkGemmEpilogue* ep);
 int dk_engine_add_gemm_pull(void* h, int list, const void* X, long ldx, const void* center_w, long ldc, int M, int N,
                             int K, void* w_local, void* w1_local, void* wb_local, const DkGemmEpilogue* ep);
+// implicit-GEMM convolution (forward or dgrad form; see conv_gemm_kernel in gemm_tcgen05.cu)
+int dk_engine_add_conv_gemm(void* h, int list, const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW,
+                            int mul, int off, int div, const void* Bmat, long ldb, int M, int N, int K,
+                            const DkGemmEpilogue* ep);
 int dk_engine_run(void* h, int list, void* stream);
 int dk_engine_list_size(void* h, int list);
 int dk_engine_list_kernels(void* h, int list);

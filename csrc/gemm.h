@@ -54,6 +54,14 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
 int dk_gemm_encode_output(void* tmap_d, const void* D, long ldd, int M, int N, int d_fp32);
 int dk_gemm_pick_splits(int M, int N, int K, int bn, int tf32);
 int dk_gemm_pick_splits_pair(int M, int N, int K, int bn);
+// implicit-GEMM convolution (A gathered from an NHWC activation; see conv_gemm_kernel)
+int dk_conv_gemm_launch(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int mul, int off,
+                        int div, const void* tmap_b, const void* tmap_d, const void* tmap_m, const DkGemmEpilogue* ep,
+                        int M, int N, int K, int bn, void* stream);
+int dk_conv_pick_bn(int N);
+int dk_conv_gemm(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int mul, int off, int div,
+                 const void* Bmat, long ldb, const DkGemmEpilogue* ep, int M, int N, int K, void* stream);
+int dk_conv_weight_flip(const void* w, int ldw, void* wd, int ldwd, int Cout, int Cin, int KH, int KW, void* stream);
 int dk_gemm_tn_ex(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M, int N,
                   int K, int flags, int bn, int splits, void* stream);
 int dk_gemm_pull_launch(const void* tmap_a, const void* tmap_b, const void* tmap_d, const DkGemmEpilogue* ep, int M,

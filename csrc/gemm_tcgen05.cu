@@ -427,6 +427,231 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 
 // ---------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution: D[M, N] = epilogue(A_gather[M, K] * B[N, K]^T) where the A operand is
+// never materialised -- row m = (b, y, x) of a (GH x GW) position grid, column k = (kh, kw, c), and
+//     A[m, k] = S[b, (y * mul - off + kh) / div, (x * mul - off + kw) / div, c]      (0 outside / if not divisible)
+// is gathered from the NHWC activation S straight into the 128-byte-swizzled shared-memory tile the
+// UMMA descriptor expects (16-byte chunks of 8 channels; C % 8 == 0).  The four epilogue warps are
+// idle during the main loop of the non-persistent kernel, so they ARE the gather producers: each
+// thread owns one of the 128 tile rows, issues the eight 16-byte loads of k-block i + 1 before it
+// stores k-block i (software pipelining over registers), then fence.proxy.async + one mbarrier
+// arrive per warp.  B (the weights, K-major) still arrives by TMA.
+//   forward:  S = X [B, H, W, Cin],   grid = OH x OW, mul = stride, off = pad,          div = 1
+//   dgrad:    S = dZ [B, OH, OW, Cout], grid = H x W,  mul = 1,      off = KH - 1 - pad, div = stride,
+//             B = the weights flipped / transposed to [Cin, (kh', kw', cout)]
+// This replaces im2col + GEMM (forward reads the activation instead of a 9x larger column matrix)
+// and GEMM + col2im (dgrad writes the input gradient once, with the producer's dReLU mask fused).
+// ---------------------------------------------------------------------------------------------
+struct ConvGather {
+  const __nv_bfloat16* src;
+  int SH, SW, C;      // source image
+  int GH, GW;         // position grid of the GEMM rows
+  int KH, KW;
+  int mul, off, div;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+conv_gemm_kernel(const ConvGather g, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
+                 const GemmEpilogue ep, const int M, const int N, const int K) {
+  using S = GemmSmem<BN, STAGES, false>;
+  constexpr int kBlockK = 64, kUmmaK = 16;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kIdesc = make_idesc(1u, kBlockM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* mask_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * kBlockM;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_b);
+    if (ep.tma_store) tma_prefetch_desc(&tmap_d);
+    if (ep.tma_mask) tma_prefetch_desc(&tmap_m);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1 + 128);  // TMA (expect_tx arrive) + every gather thread
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(&mask_bar[q], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  DK_PDL_WAIT();
+  DK_PDL_TRIGGER();
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (weights) ------------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sb = smem + stage * S::kStageBytes + S::kABytes;
+        mbar_expect_tx(&full_bar[stage], S::kBBytes);
+        tma_load_2d(sb, &tmap_b, kb * kBlockK, n0, &full_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+        const uint32_t sb = sa + S::kABytes;
+        const uint64_t adesc = make_smem_desc_sw128(sa);
+        const uint64_t bdesc = make_smem_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------ gather producers, then epilogue ----------------------------
+    const int r = (warp - 2) * 32 + lane;  // tile row owned by this thread
+    const int m = m0 + r;
+    const bool row_ok = m < M;
+    int b = 0, y = 0, x = 0;
+    if (row_ok) {
+      b = m / (g.GH * g.GW);
+      const int rem = m - b * g.GH * g.GW;
+      y = rem / g.GW;
+      x = rem - y * g.GW;
+    }
+    const int ty0 = y * g.mul - g.off, tx0 = x * g.mul - g.off;
+    const __nv_bfloat16* img = g.src + static_cast<size_t>(b) * g.SH * g.SW * g.C;
+    auto gather = [&](int kb, uint4* v) {
+      int k = kb * kBlockK;
+      int tap = k / g.C;
+      int c = k - tap * g.C;
+      int kh = tap / g.KW;
+      int kw = tap - kh * g.KW;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = make_uint4(0, 0, 0, 0);
+        if (row_ok && k < K) {
+          int ty = ty0 + kh, tx = tx0 + kw;
+          bool ok = ty >= 0 && tx >= 0;
+          if (g.div > 1) {
+            ok = ok && (ty % g.div == 0) && (tx % g.div == 0);
+            ty /= g.div;
+            tx /= g.div;
+          }
+          if (ok && ty < g.SH && tx < g.SW)
+            v[j] = __ldg(reinterpret_cast<const uint4*>(img + (static_cast<size_t>(ty) * g.SW + tx) * g.C + c));
+        }
+        k += 8;
+        c += 8;
+        if (c >= g.C) {
+          c = 0;
+          if (++kw == g.KW) { kw = 0; ++kh; }
+        }
+      }
+    };
+    uint4 cur[8], nxt[8];
+    gather(0, cur);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (kb + 1 < num_kb) gather(kb + 1, nxt);  // loads in flight while we wait for the slot
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) st_shared_v4(sa + sw128_off(r, j), cur[j].x, cur[j].y, cur[j].z, cur[j].w);
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(&full_bar[stage]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    gemm_epilogue<BN>(tmap_d, tmap_m, ep, M, N, m0, n0, warp, lane, tmem_base, smem, tmem_full_bar, mask_bar);
+    tcgen05_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_conv_gemm(const ConvGather& g, const CUtensorMap* tb, const CUtensorMap* td, const CUtensorMap* tm,
+                            GemmEpilogue ep, int M, int N, int K, cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES, false>;
+  auto kern = conv_gemm_kernel<BN, STAGES>;
+  static bool configured[64] = {};
+  int dev = 0;
+  DK_HOST_CHECK(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    DK_HOST_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured[dev & 63] = true;
+  }
+  const int esize = ep.d_fp32 ? 4 : 2;
+  const bool fits = 4 * 32 * BN * esize + (tm != nullptr ? 4 * 32 * BN * 2 : 0) <= STAGES * S::kStageBytes;
+  ep.tma_store = (td != nullptr && fits && ep.dt == nullptr) ? 1 : 0;
+  ep.tma_mask = (tm != nullptr && ep.tma_store) ? 1 : 0;
+  dim3 grid((N + BN - 1) / BN, (M + kBlockM - 1) / kBlockM, 1);
+  DK_HOST_CHECK(DK_LAUNCH(kern, grid, kGemmThreads, S::kTotal, stream, g, *tb, ep.tma_store ? *td : *tb,
+                          ep.tma_mask ? *tm : *tb, ep, M, N, K));
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// dgrad weights: Wd[c, (kh', kw', co)] = W[co, (KH - 1 - kh', KW - 1 - kw', c)]   (both bf16, K-major)
+__global__ void __launch_bounds__(256)
+conv_weight_flip_kernel(const __nv_bfloat16* __restrict__ w, int ldw, __nv_bfloat16* __restrict__ wd, int ldwd, int Cout,
+                        int Cin, int KH, int KW) {
+  DK_PDL_ENTER();
+  const int total = Cin * KH * KW * Cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t = i;
+    const int co = t % Cout; t /= Cout;
+    const int kw = t % KW; t /= KW;
+    const int kh = t % KH; t /= KH;
+    const int c = t;
+    wd[static_cast<size_t>(c) * ldwd + (kh * KW + kw) * Cout + co] =
+        w[static_cast<size_t>(co) * ldw + ((KH - 1 - kh) * KW + (KW - 1 - kw)) * Cin + c];
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // Pull fused into the first GEMM (reference op K2): the forward GEMM of the first layer
 // whose B operand -- the layer's weights -- is read by TMA **straight from the parameter server's
 // HBM** (the peer-mapped center variable, fp32, consumed as tf32 by tcgen05.mma).  The CTAs of the
@@ -1353,4 +1578,49 @@ int dk_gemm_tn(const void* A, long lda, const void* B, long ldb, const DkGemmEpi
   return dk_gemm_tn_ex(A, lda, B, ldb, ep, M, N, K, flags, bn, 1, stream);
 }
 
+// Implicit-GEMM convolution launch (see conv_gemm_kernel).  tmap_b: weights [N, K] K-major encoded with
+// box_rows = bn; tmap_d / tmap_m: output / mask [M, N] (optional) as for dk_gemm_tn_launch2.
+int dk_conv_gemm_launch(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int mul, int off,
+                        int div, const void* tmap_b, const void* tmap_d, const void* tmap_m, const DkGemmEpilogue* ep,
+                        int M, int N, int K, int bn, void* stream) {
+  if (C % 8 != 0 || K != KH * KW * C || M <= 0 || N <= 0) return -3;
+  dk::ConvGather g;
+  g.src = reinterpret_cast<const __nv_bfloat16*>(src);
+  g.SH = SH; g.SW = SW; g.C = C; g.GH = GH; g.GW = GW; g.KH = KH; g.KW = KW; g.mul = mul; g.off = off; g.div = div;
+  const CUtensorMap* tb = reinterpret_cast<const CUtensorMap*>(tmap_b);
+  const CUtensorMap* td = reinterpret_cast<const CUtensorMap*>(tmap_d);
+  const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(tmap_m);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 64) return dk::launch_conv_gemm<64, 4>(g, tb, td, tm, *ep, M, N, K, st);
+  if (bn == 128) return dk::launch_conv_gemm<128, 3>(g, tb, td, tm, *ep, M, N, K, st);
+  return -4;
+}
+
+int dk_conv_pick_bn(int N) { return N <= 64 ? 64 : 128; }
+
+// one-shot variant (tests): encodes the tensor maps first
+int dk_conv_gemm(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int mul, int off, int div,
+                 const void* Bmat, long ldb, const DkGemmEpilogue* ep, int M, int N, int K, void* stream) {
+  alignas(64) CUtensorMap tb, td, tm;
+  const int bn = dk_conv_pick_bn(N);
+  int r = dk_tmap_encode_2d(&tb, Bmat, DK_BF16, N, K, ldb, bn);
+  if (r != 0) return r;
+  const bool has_d = ep->d != nullptr && dk_gemm_encode_output(&td, ep->d, ep->ldd, M, N, ep->d_fp32) == 0;
+  const bool has_m = ep->mask != nullptr && dk_gemm_encode_output(&tm, ep->mask, ep->ld_mask, M, N, 0) == 0;
+  return dk_conv_gemm_launch(src, SH, SW, C, GH, GW, KH, KW, mul, off, div, &tb, has_d ? &td : nullptr,
+                             has_m ? &tm : nullptr, ep, M, N, K, bn, stream);
+}
+
+int dk_conv_weight_flip(const void* w, int ldw, void* wd, int ldwd, int Cout, int Cin, int KH, int KW, void* stream) {
+  const int total = Cin * KH * KW * Cout;
+  int blocks = (total + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  DK_HOST_CHECK(DK_LAUNCH(dk::conv_weight_flip_kernel, blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream),
+                          reinterpret_cast<const __nv_bfloat16*>(w), ldw, reinterpret_cast<__nv_bfloat16*>(wd), ldwd, Cout,
+                          Cin, KH, KW));
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
 }  // extern "C"
+

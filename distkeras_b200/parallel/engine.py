@@ -388,15 +388,22 @@ class NativeReplica(Replica):
             wbp, wbld = pad.data_ptr(), _r8(K)
             self._pad_refresh.append((pad.data_ptr(), _r8(K) * 2, wb_ptr + 2 * kseg.offset, K * 2, K * 2, Nout))
         inp = cur
+        implicit = False
         if b.kind == "conv":
             H, Wd, Cin = b.in_shape
             OH, OW, _ = b.out_shape
             rows = B * OH * OW
             col = self._buf(rows, _r8(K))
             a_in = dict(t=col, rows=rows, cols=K, ld=_r8(K), nhwc=None)
-            for lst in lists:
-                self._add(lst, N.OP_IM2COL, [cur["t"].data_ptr(), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad,
-                                             OH, OW, col.data_ptr(), _r8(K)])
+            # implicit GEMM (DK_IMPLICIT_CONV=1): the forward and dgrad GEMMs gather their A operand from
+            # the NHWC activation inside the kernel; the column matrix is then only needed by the wgrad
+            # GEMM, so im2col moves off the critical path onto the wgrad branch of the backward list
+            implicit = (os.environ.get("DK_IMPLICIT_CONV", "0") == "1" and Cin % 8 == 0 and Nout % 8 == 0
+                        and cur["ld"] == Cin and wbld == K and b.kh == b.kw and not is_last)
+            im2col_args = [cur["t"].data_ptr(), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad, OH, OW, col.data_ptr(), _r8(K)]
+            if not implicit:
+                for lst in lists:
+                    self._add(lst, N.OP_IM2COL, im2col_args)
         else:
             rows = cur["rows"]
             a_in = cur
@@ -437,6 +444,13 @@ class NativeReplica(Replica):
                 if r < 0:
                     raise RuntimeError(f"dk_engine_add_gemm_pull failed: {r}")
                 continue
+            if implicit:
+                r = self.lib.dk_engine_add_conv_gemm(self.engine, lst, C.c_void_p(cur["t"].data_ptr()), H, Wd, Cin, OH, OW,
+                                                     b.kh, b.kw, b.stride, b.pad, 1, C.c_void_p(wbp), wbld, rows, Nout, K,
+                                                     C.byref(ep))
+                if r < 0:
+                    raise RuntimeError(f"dk_engine_add_conv_gemm(fwd) failed: {r}")
+                continue
             self._gemm(lst, a_in["t"].data_ptr(), a_in["ld"], wbp, wbld, rows, Nout, K, 0, ep)
         b.out_rec = rec
 
@@ -473,6 +487,8 @@ class NativeReplica(Replica):
                 self._add(lst, N.OP_COLSUM, [grad["t"].data_ptr(), rows, Nout, grad["ld"], g_ptr + 4 * bseg.offset],
                           [1.0])
             self.lib.dk_engine_set_build_stream(self.engine, s_wgrad)
+            if implicit:  # the column matrix is only consumed by the wgrad GEMM below
+                self._add(lst, N.OP_IM2COL, im2col_args)
             # wgrad: dW[Nout, K] = dZ^T[Nout, rows] * In[rows, K]  (both operands MN-major views)
             ep = N.GemmEpilogue()
             ep.d, ep.ldd, ep.d_fp32, ep.alpha = g_ptr + 4 * kseg.offset, K, 1, 1.0
@@ -483,6 +499,26 @@ class NativeReplica(Replica):
                 return None, True
             if head_din is not None:  # the fused head already produced the (masked) input gradient
                 return dict(t=head_din, rows=rows, cols=K, ld=K), fuse_mask
+            if implicit and grad["ld"] == Nout:
+                H, Wd, Cin = b.in_shape
+                OH, OW, _ = b.out_shape
+                # implicit dgrad: dX[(b, ih, iw), c] = sum_{kh', kw', co} dZ[b, (ih - off + kh') / s, ..., co] * Wd[c, (kh', kw', co)]
+                # (Wd = the weights flipped / transposed once per step); the producer's dReLU mask is fused
+                Kd = b.kh * b.kw * Nout
+                wd = self._buf(Cin, Kd)
+                self._add(lst, N.OP_WFLIP, [wbp, wbld, wd.data_ptr(), Kd, Nout, Cin, b.kh, b.kw])
+                dx = self._buf(B * H * Wd, Cin)
+                fuse_relu = _relu_mask_fusable(prev, B * H * Wd, Cin)
+                ep = N.GemmEpilogue()
+                ep.d, ep.ldd, ep.alpha = dx.data_ptr(), Cin, 1.0
+                if fuse_relu:
+                    ep.mask, ep.ld_mask = prev.out_rec["t"].data_ptr(), prev.out_rec["ld"]
+                r = self.lib.dk_engine_add_conv_gemm(self.engine, lst, C.c_void_p(grad["t"].data_ptr()), OH, OW, Nout, H, Wd,
+                                                     b.kh, b.kw, 1, b.kh - 1 - b.pad, b.stride, C.c_void_p(wd.data_ptr()), Kd,
+                                                     B * H * Wd, Cin, Kd, C.byref(ep))
+                if r < 0:
+                    raise RuntimeError(f"dk_engine_add_conv_gemm(dgrad) failed: {r}")
+                return dict(t=dx, rows=B * H * Wd, cols=Cin, ld=Cin), fuse_relu
             # dgrad: dIn[rows, K] = dZ[rows, Nout] * W[Nout, K]   (W read as an MN-major B operand)
             din = self._buf(rows, _r8(K))
             ep = N.GemmEpilogue()

@@ -33,9 +33,14 @@ def _resnet(seed=0):
                        GlobalAveragePooling2D(), Dense(10, activation="softmax")], seed=seed)
 
 
-@pytest.mark.parametrize("maker,in_shape", [(_mlp, (64,)), (_cnn, (12, 12, 1)), (_resnet, (16, 16, 3))])
-def test_native_gradients_match_autograd(maker, in_shape):
+@pytest.mark.parametrize("maker,in_shape,implicit", [(_mlp, (64,), False), (_cnn, (12, 12, 1), False),
+                                                     (_resnet, (16, 16, 3), False), (_cnn, (12, 12, 1), True),
+                                                     (_resnet, (16, 16, 3), True)])
+def test_native_gradients_match_autograd(maker, in_shape, implicit, monkeypatch):
+    """``implicit``: forward / dgrad convolutions on the implicit-GEMM kernel (DK_IMPLICIT_CONV=1)."""
     from distkeras_b200.parallel.engine import NativeReplica
+
+    monkeypatch.setenv("DK_IMPLICIT_CONV", "1" if implicit else "0")
     from distkeras_b200.parallel.replica import TorchReplica
 
     B = 128

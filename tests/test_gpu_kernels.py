@@ -371,3 +371,40 @@ def test_fused_classifier_head(N, B, Cc, K, dense, use_mask):
     if use_mask:
         ref = torch.where(h.float() > 0, ref, torch.zeros_like(ref))
     assert torch.allclose(dh.float(), ref, atol=1e-2 * float(ref.abs().max()) + 1e-8, rtol=2e-2)
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,k,stride,pad", [(4, 16, 32, 32, 3, 1, 1), (3, 14, 32, 64, 3, 1, 0),
+                                                       (2, 12, 64, 64, 3, 2, 1), (5, 9, 16, 24, 1, 1, 0)])
+def test_implicit_gemm_conv_forward_and_dgrad(N, B, H, Cin, Cout, k, stride, pad):
+    """conv_gemm_kernel (A operand gathered from the NHWC activation) vs torch conv2d and its input gradient."""
+    torch.manual_seed(18)
+    OH = (H + 2 * pad - k) // stride + 1
+    x = bf(torch.randn(B, H, H, Cin, device="cuda"))
+    w = bf(torch.randn(Cout, k, k, Cin, device="cuda") * 0.1)  # [Cout, (kh, kw, c)]
+    bias = torch.randn(Cout, device="cuda")
+    K = k * k * Cin
+    M = B * OH * OH
+    out = torch.zeros(M, Cout, dtype=torch.bfloat16, device="cuda")
+    ep = N.GemmEpilogue()
+    ep.bias, ep.act, ep.d, ep.ldd, ep.alpha = bias.data_ptr(), 1, out.data_ptr(), Cout, 1.0
+    N.check(N.lib().dk_conv_gemm(x.data_ptr(), H, H, Cin, OH, OH, k, k, stride, pad, 1, w.data_ptr(), K, C.byref(ep), M, Cout,
+                                 K, st()), "conv fwd")
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.float().permute(0, 3, 1, 2)
+    pre = F.conv2d(xr, wr, bias, stride=stride, padding=pad)
+    ref = torch.relu(pre).permute(0, 2, 3, 1).reshape(M, Cout)
+    assert torch.allclose(out.float(), ref, atol=0.03 * K ** 0.5 * 0.1 + 0.02, rtol=2e-2)
+    # dgrad: dX = gather(dZ) x flipped weights, with a dReLU-style mask fused
+    dz = bf(torch.randn(B, OH, OH, Cout, device="cuda"))
+    wd = torch.zeros(Cin, k * k * Cout, dtype=torch.bfloat16, device="cuda")
+    N.check(N.lib().dk_conv_weight_flip(w.data_ptr(), K, wd.data_ptr(), k * k * Cout, Cout, Cin, k, k, st()), "flip")
+    mask = bf(torch.randn(B * H * H, Cin, device="cuda"))
+    dx = torch.zeros(B * H * H, Cin, dtype=torch.bfloat16, device="cuda")
+    ep2 = N.GemmEpilogue()
+    ep2.d, ep2.ldd, ep2.alpha, ep2.mask, ep2.ld_mask = dx.data_ptr(), Cin, 1.0, mask.data_ptr(), Cin
+    N.check(N.lib().dk_conv_gemm(dz.data_ptr(), OH, OH, Cout, H, H, k, k, 1, k - 1 - pad, stride, wd.data_ptr(), k * k * Cout,
+                                 C.byref(ep2), B * H * H, Cin, k * k * Cout, st()), "conv dgrad")
+    pre.backward(dz.float().permute(0, 3, 1, 2))
+    gref = xr.grad.permute(0, 2, 3, 1).reshape(B * H * H, Cin)
+    gref = torch.where(mask.float() > 0, gref, torch.zeros_like(gref))
+    assert torch.allclose(dx.float(), gref, atol=0.03 * float(gref.abs().max()) + 1e-3, rtol=3e-2)
