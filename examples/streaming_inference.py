@@ -34,7 +34,8 @@ def producer(n_batches=5, rows=2000):
     topic.put(None)
 
 
-threading.Thread(target=producer, daemon=True).start()
+feeder = threading.Thread(target=producer)
+feeder.start()
 predictor = ModelPredictor(higgs_mlp(seed=0), features_col="features")
 indexer = LabelIndexTransformer(output_dim=2)
 batch, done = [], False
@@ -55,3 +56,4 @@ while not done:
         signal = out.filter(lambda d: d["prediction_index"] == 1.0).count()
         print(f"micro-batch: {ds.count()} rows, {signal} predicted signal")
         batch = []
+feeder.join()
