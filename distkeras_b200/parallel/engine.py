@@ -401,9 +401,17 @@ class NativeReplica(Replica):
             implicit = (os.environ.get("DK_IMPLICIT_CONV", "0") == "1" and Cin % 8 == 0 and Nout % 8 == 0
                         and cur["ld"] == Cin and wbld == K and b.kh == b.kw and not is_last)
             im2col_args = [cur["t"].data_ptr(), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad, OH, OW, col.data_ptr(), _r8(K)]
-            if not implicit:
-                for lst in lists:
+            for lst in lists:
+                if not implicit:
                     self._add(lst, N.OP_IM2COL, im2col_args)
+                elif lst in self._train_lists:
+                    # only the wgrad GEMM (backward list) reads the column matrix: build it on side branch 3
+                    # while the forward chain continues; the backward list joins that branch before the wgrad
+                    self._add(lst, N.OP_FORK, [3])
+                    self.lib.dk_engine_set_build_stream(self.engine, 3)
+                    self._add(lst, N.OP_IM2COL, im2col_args)
+                    self.lib.dk_engine_set_build_stream(self.engine, 0)
+                    self._forked.add(3)
         else:
             rows = cur["rows"]
             a_in = cur
@@ -479,6 +487,8 @@ class NativeReplica(Replica):
             two = self._side_streams >= 2
             s_bias = 2 if two else (1 if need_dx else 0)
             s_wgrad = (1 if need_dx else 0) if two else 1
+            if implicit:  # the column matrix was built on branch 3 during the forward pass
+                self._add(lst, N.OP_JOIN, [3])
             for sid in {s_bias, s_wgrad} - {0}:
                 self._add(lst, N.OP_FORK, [sid])
                 self._forked.add(sid)
@@ -487,8 +497,6 @@ class NativeReplica(Replica):
                 self._add(lst, N.OP_COLSUM, [grad["t"].data_ptr(), rows, Nout, grad["ld"], g_ptr + 4 * bseg.offset],
                           [1.0])
             self.lib.dk_engine_set_build_stream(self.engine, s_wgrad)
-            if implicit:  # the column matrix is only consumed by the wgrad GEMM below
-                self._add(lst, N.OP_IM2COL, im2col_args)
             # wgrad: dW[Nout, K] = dZ^T[Nout, rows] * In[rows, K]  (both operands MN-major views)
             ep = N.GemmEpilogue()
             ep.d, ep.ldd, ep.d_fp32, ep.alpha = g_ptr + 4 * kseg.offset, K, 1, 1.0
