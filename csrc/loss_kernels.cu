@@ -264,6 +264,7 @@ dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __
       for (int j = 0; j < NCH; ++j)
         if (sub + 8 * j < chunks) fwd_chunk(sub + 8 * j, hq[0][j], hq[1][j]);
     } else {
+#pragma unroll 4  // independent loads of four chunks in flight per lane (the accumulation is the only dependency)
       for (int ch = sub; ch < chunks; ch += 8)
         fwd_chunk(ch, *reinterpret_cast<const uint4*>(hrow[0] + (ch << 3)),
                   *reinterpret_cast<const uint4*>(hrow[1] + (ch << 3)));
@@ -373,6 +374,7 @@ dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __
         for (int j = 0; j < NCH; ++j)
           if (sub + 8 * j < chunks) bwd_chunk(sub + 8 * j, hq[0][j], hq[1][j]);
       } else {
+#pragma unroll 4
         for (int ch = sub; ch < chunks; ch += 8)
           bwd_chunk(ch, *reinterpret_cast<const uint4*>(hrow[0] + (ch << 3)),
                     *reinterpret_cast<const uint4*>(hrow[1] + (ch << 3)));
