@@ -30,7 +30,8 @@ def main():
     exchange_obj, barrier = runtime._dist_helpers(d) if d else ((lambda o, s: o), (lambda: None))
     lib = N.lib()
     results = []
-    for n in (1_000_000, 12_000_000, 100_000_000):
+    sizes = [int(v) for v in os.environ.get("DK_PS_SIZES", "1000000,12000000,100000000").split(",")]
+    for n in sizes:
         region = FabricRegion.create(torch.zeros(n), local) if rank == 0 else None
         info = exchange_obj(region.export() if rank == 0 else None, 0)
         if rank != 0:
@@ -76,6 +77,61 @@ def main():
                                     "GBps_per_writer_per_dir": round(per_writer, 1),
                                     "GBps_ps_ingress_total": round(per_writer * (nw if world > 1 else 1), 1)})
                     print(json.dumps(results[-1]), flush=True)
+        # ---- NCCL baseline (BASELINE.json: "a path that only calls NCCL is the baseline"): the same
+        # commit / pull / exchange built from library calls -- elementwise kernels + ncclSend/ncclRecv
+        # between the writer (rank 1) and the server (rank 0), server-side add as its own kernel
+        if world > 1:
+            buf = torch.empty(n, device="cuda")
+            center_t = torch.zeros(n, device="cuda") if rank == 0 else None
+
+            def nccl_commit():
+                if rank == 1:
+                    torch.sub(w, w1, out=buf)
+                    buf.mul_(1e-6)
+                    dist.send(buf, 0)
+                elif rank == 0:
+                    dist.recv(buf, 1)
+                    center_t.add_(buf)
+
+            def nccl_pull():
+                if rank == 0:
+                    dist.send(center_t, 1)
+                elif rank == 1:
+                    dist.recv(buf, 0)
+                    w.copy_(buf)
+                    w1.copy_(buf)
+                    wb.copy_(buf)
+
+            def nccl_exchange():
+                nccl_commit()
+                nccl_pull()
+
+            for name, op in (("nccl:commit(sub+send|recv+add)", nccl_commit), ("nccl:pull(send|recv+3 copies)", nccl_pull),
+                             ("nccl:exchange(commit+pull)", nccl_exchange)):
+                active = rank in (0, 1)
+                iters = 20 if n <= 12_000_000 else 5
+                if active:
+                    for _ in range(3):
+                        op()
+                torch.cuda.synchronize()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if active:
+                    for _ in range(iters):
+                        op()
+                e1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / iters if active else 0.0], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t)
+                barrier()
+                if rank == 0:
+                    per_writer = 4.0 * n / (ms * 1e-3) / 1e9
+                    results.append({"op": name, "n": n, "writers": 1, "us": round(ms * 1e3, 2),
+                                    "GBps_per_writer_per_dir": round(per_writer, 1), "GBps_ps_ingress_total": round(per_writer, 1)})
+                    print(json.dumps(results[-1]), flush=True)
+            del buf, center_t
         barrier()
         region.close()
         del w, w1, wb
