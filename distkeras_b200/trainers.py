@@ -35,7 +35,7 @@ from .ops.flat_optim import OptimizerSpec
 from .parameter_servers import (ADAGParameterServer, DeltaParameterServer, DynSGDParameterServer,
                                 ExperimentalParameterServer)
 from .utils import deserialize_keras_model, history_executor, history_executors_average, serialize_keras_model
-from .workers import (ADAGWorker, AEASGDWorker, DOWNPOURWorker, DynSGDWorker, EAMSGDWorker, ExperimentalWorker,
+from .workers import (ADAGWorker, AEASGDWorker, DOWNPOURWorker, DynSGDWorker, EAMSGDWorker, EASGDWorker, ExperimentalWorker,
                       SequentialWorker)
 
 
@@ -474,6 +474,15 @@ class AsynchronousDistributedTrainer(DistributedTrainer):
         return self.parallelism_factor
 
 
+class SynchronousDistributedTrainer(DistributedTrainer):
+    """Base of the synchronous parameter-server trainers: one partition per worker, all workers alive at
+    the same time (the reference names it in ``docs/optimizers.md:22-31`` / ``workflow.ipynb:112`` but ships
+    no implementation).  Runs on the thread / socket backends."""
+
+    def _num_partitions(self) -> int:
+        return self.num_workers
+
+
 def _worker_kwargs(t: DistributedTrainer) -> dict:
     return dict(metrics=t.metrics, features_col=t.features_column, label_col=t.label_column,
                 batch_size=t.batch_size, num_epoch=t.num_epoch, master_host=t.master_host,
@@ -499,6 +508,27 @@ class AEASGD(AsynchronousDistributedTrainer):
 
     def algorithm(self) -> dict:
         return {"kind": "aeasgd", "window": self.communication_window, "alpha": self.rho * self.learning_rate}
+
+
+class EASGD(SynchronousDistributedTrainer):
+    """Synchronous Elastic Averaging SGD: ``C += sum_i alpha (W_i - C)``, ``W_i -= alpha (W_i - C)`` every
+    ``communication_window`` mini-batches, all workers in lock step (``alpha = rho * learning_rate``)."""
+
+    def __init__(self, keras_model, worker_optimizer, loss, metrics=("accuracy",), num_workers=2, batch_size=32,
+                 features_col="features", label_col="label", num_epoch=1, communication_window=32, rho=5.0,
+                 learning_rate=0.01, master_port=5000, loss_weights=None):
+        super().__init__(keras_model, worker_optimizer, loss, metrics, num_workers, batch_size, features_col,
+                         label_col, num_epoch, master_port, loss_weights)
+        self.communication_window = int(communication_window)
+        self.rho = float(rho)
+        self.learning_rate = float(learning_rate)
+
+    def allocate_worker(self):
+        w = EASGDWorker(self.master_model, self.worker_optimizer, self.loss, self.loss_weights,
+                        communication_window=self.communication_window, rho=self.rho,
+                        learning_rate=self.learning_rate, **_worker_kwargs(self))
+        w.barrier = threading.Barrier(self.num_workers)
+        return w
 
 
 class DOWNPOUR(AsynchronousDistributedTrainer):

@@ -372,6 +372,46 @@ class AEASGDWorker(NetworkWorker):
             self.iteration += 1
 
 
+class EASGDWorker(AEASGDWorker):
+    """Synchronous elastic averaging (Zhang et al.; the reference only documents it,
+    ``docs/optimizers.md:22-31``): every ``communication_window`` mini-batches ALL workers meet, read the
+    same center, move towards it by ``alpha`` and the center moves towards their mean.  Two rendezvous
+    per round: one so every worker reads the old center, one before anybody commits to it.  The
+    barrier is shared by the worker copies of one trainer (thread / socket backends); a worker that runs
+    out of data breaks the barrier and the others finish their shards asynchronously."""
+
+    barrier = None  # threading.Barrier installed by the trainer
+
+    def _meet(self) -> bool:
+        import threading
+
+        if self.barrier is None:
+            return True
+        try:
+            self.barrier.wait(timeout=60)
+            return True
+        except threading.BrokenBarrierError:
+            return False
+
+    def optimize(self) -> None:
+        try:
+            while True:
+                batch = self.get_next_minibatch()
+                if self.iteration % self.communication_window == 0 and self._meet():
+                    self.pull()
+                    W = self._W()
+                    E = self.alpha * (W - self.center_variable)
+                    W.sub_(E)
+                    self.replica.weights_changed()
+                    self._meet()  # everyone has read the old center
+                    self.commit(E)
+                self._train_batch(batch)
+                self.iteration += 1
+        finally:
+            if self.barrier is not None:
+                self.barrier.abort()  # out of data: release the peers
+
+
 class EAMSGDWorker(AEASGDWorker):
     """Algorithm D (``workers.py:413-458``): elastic averaging + Nesterov-style momentum."""
 

@@ -259,3 +259,22 @@ def test_multiple_feature_columns_are_concatenated():
     m = t.train(ds)
     m.compile("categorical_crossentropy")
     assert m.evaluate(torch.cat([a, b], 1), ds["label"])[1] > 0.6
+
+
+def test_synchronous_easgd_lockstep():
+    """Synchronous EASGD: every window all workers read the SAME center (two rendezvous per round), so the
+    center moves by exactly sum_i alpha (W_i - C_old); 2 workers x (32 batches / window 4) = 16 commits."""
+    from distkeras_b200.trainers import EASGD, SynchronousDistributedTrainer
+
+    ds = tiny_data(1024)
+    t = EASGD(tiny_model(0), {"class_name": "adam", "config": {"lr": 0.02}}, "categorical_crossentropy", num_workers=2,
+              batch_size=16, num_epoch=1, communication_window=4, rho=1.0, learning_rate=0.25)
+    assert isinstance(t, SynchronousDistributedTrainer)
+    t.backend = "thread"
+    model = t.train(ds)
+    assert t.num_updates() == 1 + 2 * (32 // 4)
+    model.compile("categorical_crossentropy")
+    assert model.evaluate(ds["features"], ds["label"])[1] > 0.6
+    # the commits of one round are interleaved pairwise: worker ids alternate in blocks of two
+    order = [wid for wid, _ in sorted(((h["worker_id"], h["iteration"]) for h in t.get_history()), key=lambda p: p[1])]
+    assert set(order) == {0, 1}
