@@ -278,3 +278,72 @@ def test_synchronous_easgd_lockstep():
     # the commits of one round are interleaved pairwise: worker ids alternate in blocks of two
     order = [wid for wid, _ in sorted(((h["worker_id"], h["iteration"]) for h in t.get_history()), key=lambda p: p[1])]
     assert set(order) == {0, 1}
+
+
+def _oracle_run(rule, n_batches=16, tau=4, **hp):
+    """Replay one worker's loop by hand and return the final center."""
+    ds = tiny_data(16 * n_batches)
+    ref = tiny_model(0)
+    ref.compile("categorical_crossentropy", "sgd")
+    C = ref.get_flat_weights().clone()   # center
+    W1 = C.clone()
+    x, y = ds["features"], ds["label"]
+    r = torch.zeros_like(C)
+    updates = 1  # the PS counter starts at 1
+    last_update = 1  # value returned by the initial pull
+    for it in range(1, n_batches + 1):
+        batch = (x[(it - 1) * 16:it * 16], y[(it - 1) * 16:it * 16])
+        if rule in ("downpour", "aeasgd", "eamsgd") and it % tau == 0:  # check BEFORE the batch
+            W = ref.get_flat_weights()
+            if rule == "downpour":
+                C = C + (W - W1)
+                ref.set_flat_weights(C)
+                W1 = C.clone()
+            else:
+                E = hp["rho"] * hp["lr"] * (W - C)
+                ref.set_flat_weights(W - E)
+                C = C + E
+        if rule == "eamsgd":
+            W = ref.get_flat_weights()
+            r_t = hp["momentum"] * r
+            W_copy = W.clone()
+            ref.set_flat_weights(W + r_t)
+            before = ref.get_flat_weights().clone()
+            ref.train_on_batch(*batch)
+            g = ref.get_flat_weights() - before
+            r = r_t - hp["lr"] * g
+            ref.set_flat_weights(W_copy - r)
+        else:
+            ref.train_on_batch(*batch)
+        if rule in ("dynsgd", "experimental") and it % tau == 0:  # check AFTER the batch
+            W = ref.get_flat_weights()
+            if rule == "dynsgd":
+                staleness = (updates - last_update) + 1
+                C = C + (W - W1) / staleness
+                updates += 1
+                last_update = updates
+            else:
+                res = (W - W1) / tau
+                d = 1.0 / ((1.0 / hp["lr"]) * (C - W1) ** 2 + 1.0)  # C_stale == W1 for a single worker
+                C = C + d * res
+            ref.set_flat_weights(C)
+            W1 = C.clone()
+    return ds, C
+
+
+@pytest.mark.parametrize("rule,cls,kw,hp", [
+    ("downpour", DOWNPOUR, dict(communication_window=4), {}),
+    ("aeasgd", AEASGD, dict(communication_window=4, rho=2.0, learning_rate=0.1), dict(rho=2.0, lr=0.1)),
+    ("eamsgd", EAMSGD, dict(communication_window=4, rho=2.0, learning_rate=0.1, momentum=0.5),
+     dict(rho=2.0, lr=0.1, momentum=0.5)),
+    ("dynsgd", DynSGD, dict(communication_window=4), {}),
+    ("experimental", Experimental, dict(communication_window=4, learning_rate=0.5), dict(lr=0.5)),
+])
+def test_single_worker_center_matches_hand_replay(rule, cls, kw, hp):
+    """One worker, plain SGD, deterministic: the trainer's final center equals the algorithm replayed by
+    hand from the formulas of SURVEY 2.6 (reference ``workers.py`` / ``parameter_servers.py``)."""
+    ds, want = _oracle_run(rule, **hp)
+    t = cls(tiny_model(0), "sgd", "categorical_crossentropy", num_workers=1, batch_size=16, **kw)
+    t.backend = "thread"
+    got = t.train(ds).get_flat_weights()
+    assert torch.allclose(got, want, atol=2e-5), (rule, float((got - want).abs().max()))
