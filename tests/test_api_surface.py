@@ -111,3 +111,16 @@ def test_alias_package_importable():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     assert os.path.realpath(os.path.join(root, "dist-keras_b200")) == os.path.realpath(
         os.path.join(root, "distkeras_b200"))
+
+
+def test_cli_info_reports_environment():
+    import json
+    import subprocess
+    import sys
+
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "distkeras_b200", "info"], cwd=root, capture_output=True, text=True,
+                       timeout=300, env=dict(__import__("os").environ, DK_STRICT="1"))
+    assert r.returncode == 0, r.stderr[-1000:]
+    d = json.loads(r.stdout)
+    assert "thread" in d["backends"] and d["switches"].get("DK_STRICT") == "1"
