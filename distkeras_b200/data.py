@@ -141,15 +141,32 @@ class Dataset:
 
     @classmethod
     def from_csv(cls, path: str, label_col: Optional[str] = None, features_col: str = "features",
-                 header: bool = True, dtype=np.float32, num_partitions: int = 1) -> "Dataset":
-        """Read a numeric CSV; all non-label columns are assembled into one vector column
-        (the VectorAssembler step of ``examples/mnist.py:99-107``)."""
+                 header: bool = True, dtype=np.float32, num_partitions: int = 1, drop_cols: Sequence[str] = (),
+                 label_map: Optional[Dict[str, int]] = None) -> "Dataset":
+        """Read a CSV; all non-label columns are assembled into one vector column (the VectorAssembler
+        step of ``examples/mnist.py:99-107``).  ``drop_cols`` removes bookkeeping columns (``EventId``,
+        ``Weight``); ``label_map`` indexes a string label (``{"b": 0, "s": 1}`` -- the StringIndexer step of
+        ``examples/workflow.ipynb``)."""
         with open(path, "r") as f:
             names = f.readline().strip().split(",") if header else None
+        if label_map is not None or drop_cols:
+            import pandas as pd
+
+            df = pd.read_csv(path, header=0 if header else None)
+            if names is None:
+                df.columns = names = [f"c{i}" for i in range(df.shape[1])]
+            df = df.drop(columns=[c for c in drop_cols if c in df.columns])
+            cols: Dict[str, object] = {}
+            if label_col is not None and label_col in df.columns:
+                lab = df.pop(label_col)
+                cols[label_col] = (lab.map(label_map).to_numpy(dtype=np.int64) if label_map is not None
+                                   else lab.to_numpy(dtype=dtype))
+            cols[features_col] = np.ascontiguousarray(df.to_numpy(dtype=dtype))
+            return cls(cols, num_partitions)
         arr = np.loadtxt(path, delimiter=",", skiprows=1 if header else 0, dtype=dtype, ndmin=2)
         if names is None:
             names = [f"c{i}" for i in range(arr.shape[1])]
-        cols: Dict[str, object] = {}
+        cols = {}
         if label_col is not None and label_col in names:
             li = names.index(label_col)
             cols[label_col] = arr[:, li].copy()

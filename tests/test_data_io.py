@@ -76,3 +76,11 @@ def test_model_serialisation_and_pickle_roundtrip(tmp_path):
     assert isinstance(get_os_username(), str) and len(get_os_username()) > 0
     base = set_keras_base_directory(str(tmp_path / "keras_home"))
     assert str(tmp_path) in base
+
+
+def test_csv_with_string_label_and_dropped_columns(tmp_path):
+    """ATLAS-Higgs layout: bookkeeping columns dropped, 's' / 'b' label indexed (the StringIndexer step)."""
+    p = tmp_path / "h.csv"
+    p.write_text("EventId,a,b,Weight,Label\n1,0.5,1.5,1.0,s\n2,3,4,2.0,b\n3,5,6,1.0,s\n")
+    ds = Dataset.from_csv(str(p), label_col="Label", drop_cols=("EventId", "Weight"), label_map={"b": 0, "s": 1})
+    assert ds["Label"].tolist() == [1, 0, 1] and ds["features"].tolist() == [[0.5, 1.5], [3.0, 4.0], [5.0, 6.0]]
