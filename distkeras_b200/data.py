@@ -159,9 +159,9 @@ class Dataset:
             cols: Dict[str, object] = {}
             if label_col is not None and label_col in df.columns:
                 lab = df.pop(label_col)
-                cols[label_col] = (lab.map(label_map).to_numpy(dtype=np.int64) if label_map is not None
-                                   else lab.to_numpy(dtype=dtype))
-            cols[features_col] = np.ascontiguousarray(df.to_numpy(dtype=dtype))
+                cols[label_col] = (np.array(lab.map(label_map), dtype=np.int64) if label_map is not None
+                                   else np.array(lab, dtype=dtype))
+            cols[features_col] = np.array(df.to_numpy(dtype=dtype), order="C")
             return cls(cols, num_partitions)
         arr = np.loadtxt(path, delimiter=",", skiprows=1 if header else 0, dtype=dtype, ndmin=2)
         if names is None:
