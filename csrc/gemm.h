@@ -59,6 +59,7 @@ int dk_conv_gemm_launch(const void* src, int SH, int SW, int C, int GH, int GW, 
                         int div, const void* tmap_b, const void* tmap_d, const void* tmap_m, const DkGemmEpilogue* ep,
                         int M, int N, int K, int bn, void* stream);
 int dk_conv_pick_bn(int N);
+int dk_conv_gather_mode(int mode);
 int dk_conv_gemm(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int mul, int off, int div,
                  const void* Bmat, long ldb, const DkGemmEpilogue* ep, int M, int N, int K, void* stream);
 int dk_conv_weight_flip(const void* w, int ldw, void* wd, int ldwd, int Cout, int Cin, int KH, int KW, void* stream);

@@ -450,7 +450,11 @@ struct ConvGather {
   int mul, off, div;
 };
 
-template <int BN, int STAGES>
+// LDGSTS = true: the gather is issued as cp.async (16 bytes, zero-fill for padding) straight into the
+// swizzled tile and completes on the stage's mbarrier (cp.async.mbarrier.arrive.noinc), so up to STAGES
+// k-blocks of loads are in flight per thread without holding them in registers; the MMA thread then
+// crosses to the async proxy with fence.proxy.async before issuing tcgen05.mma.
+template <int BN, int STAGES, bool LDGSTS>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 conv_gemm_kernel(const ConvGather g, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
@@ -522,6 +526,7 @@ conv_gemm_kernel(const ConvGather g, const __grid_constant__ CUtensorMap tmap_b,
       mbar_wait(&full_bar[stage], phase);
       tcgen05_fence_after();
       if (elect_one()) {
+        if constexpr (LDGSTS) fence_proxy_async_smem();  // cp.async wrote through the generic proxy
         const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
         const uint32_t sb = sa + S::kABytes;
         const uint64_t adesc = make_smem_desc_sw128(sa);
@@ -580,10 +585,53 @@ conv_gemm_kernel(const ConvGather g, const __grid_constant__ CUtensorMap tmap_b,
         }
       }
     };
-    uint4 cur[8], nxt[8];
-    gather(0, cur);
     int stage = 0;
     uint32_t phase = 0;
+    if constexpr (LDGSTS) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+        int k = kb * kBlockK;
+        int tap = k / g.C;
+        int c = k - tap * g.C;
+        int kh = tap / g.KW;
+        int kw = tap - kh * g.KW;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_bfloat16* src = g.src;  // any valid address when nothing is read (src-size 0 = zero fill)
+          uint32_t nbytes = 0;
+          if (row_ok && k < K) {
+            int ty = ty0 + kh, tx = tx0 + kw;
+            bool ok = ty >= 0 && tx >= 0;
+            if (g.div > 1) {
+              ok = ok && (ty % g.div == 0) && (tx % g.div == 0);
+              ty /= g.div;
+              tx /= g.div;
+            }
+            if (ok && ty < g.SH && tx < g.SW) {
+              src = img + (static_cast<size_t>(ty) * g.SW + tx) * g.C + c;
+              nbytes = 16;
+            }
+          }
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa + sw128_off(r, j)), "l"(src), "r"(nbytes)
+                       : "memory");
+          k += 8;
+          c += 8;
+          if (c >= g.C) {
+            c = 0;
+            if (++kw == g.KW) { kw = 0; ++kh; }
+          }
+        }
+        // arrive on the stage barrier when this thread's copies have landed (counted in the init value)
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage])) : "memory");
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    } else {
+    uint4 cur[8], nxt[8];
+    gather(0, cur);
     for (int kb = 0; kb < num_kb; ++kb) {
       if (kb + 1 < num_kb) gather(kb + 1, nxt);  // loads in flight while we wait for the slot
       mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -599,6 +647,7 @@ conv_gemm_kernel(const ConvGather g, const __grid_constant__ CUtensorMap tmap_b,
         phase ^= 1;
       }
     }
+    }
     gemm_epilogue<BN>(tmap_d, tmap_m, ep, M, N, m0, n0, warp, lane, tmem_base, smem, tmem_full_bar, mask_bar);
     tcgen05_fence_before();
   }
@@ -610,11 +659,11 @@ conv_gemm_kernel(const ConvGather g, const __grid_constant__ CUtensorMap tmap_b,
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool LDGSTS>
 static int launch_conv_gemm(const ConvGather& g, const CUtensorMap* tb, const CUtensorMap* td, const CUtensorMap* tm,
                             GemmEpilogue ep, int M, int N, int K, cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES, false>;
-  auto kern = conv_gemm_kernel<BN, STAGES>;
+  auto kern = conv_gemm_kernel<BN, STAGES, LDGSTS>;
   static bool configured[64] = {};
   int dev = 0;
   DK_HOST_CHECK(cudaGetDevice(&dev));
@@ -1580,6 +1629,19 @@ int dk_gemm_tn(const void* A, long lda, const void* B, long ldb, const DkGemmEpi
 
 // Implicit-GEMM convolution launch (see conv_gemm_kernel).  tmap_b: weights [N, K] K-major encoded with
 // box_rows = bn; tmap_d / tmap_m: output / mask [M, N] (optional) as for dk_gemm_tn_launch2.
+// A-gather implementation of the implicit-GEMM convolution: 0 = register-pipelined ld.global + st.shared
+// (default), 1 = cp.async ring completing on the stage mbarrier.  mode < 0 only queries; the initial value
+// comes from DK_CONV_LDGSTS.
+int dk_conv_gather_mode(int mode) {
+  static int current = -1;
+  if (current < 0) {
+    const char* e = getenv("DK_CONV_LDGSTS");
+    current = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  if (mode >= 0) current = mode ? 1 : 0;
+  return current;
+}
+
 int dk_conv_gemm_launch(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int mul, int off,
                         int div, const void* tmap_b, const void* tmap_d, const void* tmap_m, const DkGemmEpilogue* ep,
                         int M, int N, int K, int bn, void* stream) {
@@ -1591,8 +1653,13 @@ int dk_conv_gemm_launch(const void* src, int SH, int SW, int C, int GH, int GW, 
   const CUtensorMap* td = reinterpret_cast<const CUtensorMap*>(tmap_d);
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(tmap_m);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (bn == 64) return dk::launch_conv_gemm<64, 4>(g, tb, td, tm, *ep, M, N, K, st);
-  if (bn == 128) return dk::launch_conv_gemm<128, 3>(g, tb, td, tm, *ep, M, N, K, st);
+  if (dk_conv_gather_mode(-1) == 1) {
+    if (bn == 64) return dk::launch_conv_gemm<64, 4, true>(g, tb, td, tm, *ep, M, N, K, st);
+    if (bn == 128) return dk::launch_conv_gemm<128, 3, true>(g, tb, td, tm, *ep, M, N, K, st);
+    return -4;
+  }
+  if (bn == 64) return dk::launch_conv_gemm<64, 4, false>(g, tb, td, tm, *ep, M, N, K, st);
+  if (bn == 128) return dk::launch_conv_gemm<128, 3, false>(g, tb, td, tm, *ep, M, N, K, st);
   return -4;
 }
 

@@ -12,7 +12,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SWITCHES = ("DK_BACKEND", "DK_COMM", "DK_STRICT", "DK_DEDICATED_PS", "DK_LOG", "DK_NVTX", "DK_NUMA", "DK_FAULT",
+SWITCHES = ("DK_CONV_LDGSTS", "DK_BACKEND", "DK_COMM", "DK_STRICT", "DK_DEDICATED_PS", "DK_LOG", "DK_NVTX", "DK_NUMA", "DK_FAULT",
             "DK_PERSISTENT", "DK_PAIR", "DK_PDL", "DK_SIDE_STREAMS", "DK_FUSED_HEAD", "DK_IMPLICIT_CONV")
 
 

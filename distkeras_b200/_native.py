@@ -61,6 +61,7 @@ _SIGNATURES = {
                            i32, vp]),
     "dk_conv_weight_flip": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "dk_conv_pick_bn": (i32, [i32]),
+    "dk_conv_gather_mode": (i32, [i32]),
     # ps
     "dk_ps_commit": (i32, [vp, vp, vp, i64, f32, vp, vp, i32, u32, vp]),
     "dk_ps_pull": (i32, [vp, vp, vp, vp, i64, vp, vp, vp]),

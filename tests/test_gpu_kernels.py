@@ -373,9 +373,18 @@ def test_fused_classifier_head(N, B, Cc, K, dense, use_mask):
     assert torch.allclose(dh.float(), ref, atol=1e-2 * float(ref.abs().max()) + 1e-8, rtol=2e-2)
 
 
+@pytest.fixture
+def gather_mode(request, N):
+    """0 = register-pipelined gather, 1 = cp.async (LDGSTS) ring completing on the stage mbarrier."""
+    N.lib().dk_conv_gather_mode(request.param)
+    yield request.param
+    N.lib().dk_conv_gather_mode(0)
+
+
+@pytest.mark.parametrize("gather_mode", [0, 1], indirect=True)
 @pytest.mark.parametrize("B,H,Cin,Cout,k,stride,pad", [(4, 16, 32, 32, 3, 1, 1), (3, 14, 32, 64, 3, 1, 0),
                                                        (2, 12, 64, 64, 3, 2, 1), (5, 9, 16, 24, 1, 1, 0)])
-def test_implicit_gemm_conv_forward_and_dgrad(N, B, H, Cin, Cout, k, stride, pad):
+def test_implicit_gemm_conv_forward_and_dgrad(N, B, H, Cin, Cout, k, stride, pad, gather_mode):
     """conv_gemm_kernel (A operand gathered from the NHWC activation) vs torch conv2d and its input gradient."""
     torch.manual_seed(18)
     OH = (H + 2 * pad - k) // stride + 1
