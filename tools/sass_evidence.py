@@ -12,9 +12,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "distkeras_b200", "lib", "libdistkeras_b200.so")
-INTERESTING = re.compile(r"^(UTC|UTMA|LDTM|STTM|SYNCS|ACQBULK|UCGABAR|REDG|ATOMG|LDGSTS|UBLKCP|FENCE\.VIEW\.ASYNC)")
+INTERESTING = re.compile(r"^(UTC|UTMA|LDTM|STTM|SYNCS|ACQBULK|UCGABAR|REDG|ATOMG|LDGSTS|ARRIVES|UBLKCP|FENCE\.VIEW\.ASYNC)")
 PER_KERNEL = [("UTCHMMA", r"^UTCHMMA"), ("UTCHMMA.2CTA", r"^UTCHMMA.*2CTA"), ("LDTM", r"^LDTM"), ("UTMALDG", r"^UTMALDG"),
-              ("UTMASTG/REDG", r"^UTMA(STG|REDG)"), ("SYS-atomics", r"^(REDG|ATOMG).*\.SYS"), ("FENCE.ASYNC", r"^FENCE\.VIEW\.ASYNC")]
+              ("UTMASTG/REDG", r"^UTMA(STG|REDG)"), ("SYS-atomics", r"^(REDG|ATOMG).*\.SYS"), ("FENCE.ASYNC", r"^FENCE\.VIEW\.ASYNC"), ("LDGSTS", r"^LDGSTS"),
+              ("LDGSTSBAR", r"^ARRIVES\.LDGSTSBAR")]
 
 
 def main() -> None:
