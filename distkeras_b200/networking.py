@@ -51,9 +51,9 @@ def _encode(data: Any):
 
     def walk(obj):
         if isinstance(obj, np.ndarray):
-            arr = np.ascontiguousarray(obj)
-            buffers.append(memoryview(arr).cast("B"))
-            return {"__nd__": len(buffers) - 1, "dtype": arr.dtype.str, "shape": arr.shape}
+            flat = np.ascontiguousarray(obj).reshape(-1)  # (ascontiguousarray alone would turn 0-d into 1-d)
+            buffers.append(memoryview(flat.view(np.uint8)))
+            return {"__nd__": len(buffers) - 1, "dtype": flat.dtype.str, "shape": tuple(obj.shape)}
         if isinstance(obj, dict):
             return {k: walk(v) for k, v in obj.items()}
         if isinstance(obj, (list, tuple)):
