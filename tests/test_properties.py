@@ -27,7 +27,7 @@ payloads = st.recursive(st.one_of(arrays, st.integers(-2**31, 2**31), floats, st
 
 def _same(a, b) -> bool:
     if isinstance(a, np.ndarray):
-        return isinstance(b, np.ndarray) and a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+        return isinstance(b, np.ndarray) and a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
     if isinstance(a, dict):
         return isinstance(b, dict) and a.keys() == b.keys() and all(_same(a[k], b[k]) for k in a)
     if isinstance(a, (list, tuple)):
