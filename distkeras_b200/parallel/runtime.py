@@ -812,8 +812,8 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         # release the replica's device buffers / graphs before the next job in this process
         try:
             worker.rep.close()
-        except Exception:
-            pass
+        except Exception as exc:  # teardown only; the result is already collected
+            log_event("fabric.replica_close_failed", rank=rank, error=repr(exc))
         del worker
         import gc
 
