@@ -104,6 +104,11 @@ int run_op(Engine* e, Op& op, void* main_stream) {
       return dk_conv_gemm_launch(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], (int)a[6],
                                  (int)a[7], (int)a[8], (int)a[9], (int)a[10], &op.tb, op.has_td ? &op.td : nullptr,
                                  op.has_tm ? &op.tm : nullptr, &op.ep, (int)a[11], (int)a[12], (int)a[13], (int)a[14], st);
+    case DK_OP_CONV_WGRAD:
+      // src, SH, SW, C, GH, GW, KH, KW, stride, pad, Cout, rows, splits (dZ / dW maps pre-encoded)
+      return dk_conv_wgrad_launch(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], (int)a[6],
+                                  (int)a[7], (int)a[8], (int)a[9], &op.ta, &op.td, &op.ep, (int)a[10], (int)a[11],
+                                  (int)a[12], st);
     case DK_OP_WFLIP:
       // w, ldw, wd, ldwd, Cout, Cin, KH, KW
       return dk_conv_weight_flip(resolve(e, a[0]), (int)a[1], resolve(e, a[2]), (int)a[3], (int)a[4], (int)a[5], (int)a[6],
@@ -380,6 +385,33 @@ int dk_engine_add_conv_gemm(void* h, int list, const void* src, int SH, int SW, 
   op.i[0] = (int64_t)(uintptr_t)src;
   op.i[1] = SH; op.i[2] = SW; op.i[3] = C; op.i[4] = GH; op.i[5] = GW; op.i[6] = KH; op.i[7] = KW;
   op.i[8] = mul; op.i[9] = off; op.i[10] = div; op.i[11] = M; op.i[12] = N; op.i[13] = K; op.i[14] = bn;
+  e->lists[list].push_back(op);
+  return static_cast<int>(e->lists[list].size()) - 1;
+}
+
+int dk_engine_add_conv_wgrad(void* h, int list, const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW,
+                             int stride, int pad, const void* dz, long lddz, float* dw, long lddw, int Cout, int rows) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (list < 0 || list >= (int)e->lists.size()) return -1;
+  Op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = DK_OP_CONV_WGRAD;
+  op.stream_id = e->build_stream;
+  int r = dk_tmap_encode_2d(&op.ta, dz, DK_BF16, rows, Cout, lddz, 64);
+  if (r != 0) return r;
+  r = dk_gemm_encode_output(&op.td, dw, lddw, Cout, KH * KW * C, 1);
+  if (r != 0) return r;
+  op.has_td = 1;
+  op.ep.alpha = 1.f;
+  op.ep.d = dw;
+  op.ep.ldd = static_cast<int>(lddw);
+  op.ep.d_fp32 = 1;
+  const int tiles = (KH * KW * C + 127) / 128 * ((Cout + 127) / 128);
+  int splits = 148 / tiles;  // one 128-wide CTA per SM, single wave
+  if (splits < 1) splits = 1;
+  op.i[0] = (int64_t)(uintptr_t)src;
+  op.i[1] = SH; op.i[2] = SW; op.i[3] = C; op.i[4] = GH; op.i[5] = GW; op.i[6] = KH; op.i[7] = KW;
+  op.i[8] = stride; op.i[9] = pad; op.i[10] = Cout; op.i[11] = rows; op.i[12] = splits;
   e->lists[list].push_back(op);
   return static_cast<int>(e->lists[list].size()) - 1;
 }

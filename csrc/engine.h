@@ -49,7 +49,8 @@ enum {
   DK_OP_GAP_BWD = 36,
   DK_OP_HEAD = 37,
   DK_OP_CONV_GEMM = 38,
-  DK_OP_WFLIP = 39
+  DK_OP_WFLIP = 39,
+  DK_OP_CONV_WGRAD = 40  // experimental
 };
 
 #ifdef __cplusplus
@@ -73,6 +74,9 @@ int dk_engine_add_gemm_pull(void* h, int list, const void* X, long ldx, const vo
 int dk_engine_add_conv_gemm(void* h, int list, const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW,
                             int mul, int off, int div, const void* Bmat, long ldb, int M, int N, int K,
                             const DkGemmEpilogue* ep);
+// EXPERIMENTAL implicit wgrad (conv_wgrad_kernel): dW [Cout, KH KW C] fp32 (zeroed) += dZ^T [rows, Cout] * gather(src)
+int dk_engine_add_conv_wgrad(void* h, int list, const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW,
+                             int stride, int pad, const void* dz, long lddz, float* dw, long lddw, int Cout, int rows);
 int dk_engine_run(void* h, int list, void* stream);
 int dk_engine_list_size(void* h, int list);
 int dk_engine_list_kernels(void* h, int list);

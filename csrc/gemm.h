@@ -62,6 +62,12 @@ int dk_conv_pick_bn(int N);
 int dk_conv_gather_mode(int mode);
 int dk_conv_gemm(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int mul, int off, int div,
                  const void* Bmat, long ldb, const DkGemmEpilogue* ep, int M, int N, int K, void* stream);
+// EXPERIMENTAL implicit wgrad (not yet validated on hardware)
+int dk_conv_wgrad_launch(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int stride, int pad,
+                         const void* tmap_a, const void* tmap_d, const DkGemmEpilogue* ep, int Cout, int rows, int splits,
+                         void* stream);
+int dk_conv_wgrad(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int stride, int pad,
+                  const void* dz, long lddz, float* dw, long lddw, int Cout, int rows, int splits, void* stream);
 int dk_conv_weight_flip(const void* w, int ldw, void* wd, int ldwd, int Cout, int Cin, int KH, int KW, void* stream);
 int dk_gemm_tn_ex(const void* A, long lda, const void* B, long ldb, const DkGemmEpilogue* ep, int M, int N,
                   int K, int flags, int bn, int splits, void* stream);

@@ -682,6 +682,202 @@ static int launch_conv_gemm(const ConvGather& g, const CUtensorMap* tb, const CU
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// EXPERIMENTAL (compiled, reachable only with DK_IMPLICIT_WGRAD=1; not yet validated on hardware --
+// the round's GPU budget ended before its first run): implicit-GEMM weight gradient
+//     dW[co, (kh, kw, c)] += sum_m dZ[m, co] * X[b(m), y(m) * s - p + kh, x(m) * s - p + kw, c]
+// i.e. D[M = Cout, N = KH KW Cin] = A^T B with both operands MN-major and the GEMM-K dimension = the
+// B OH OW output positions (split-K over gridDim.z, fp32 TMA add-reduction like the dense wgrad).
+// A = dZ [rows, Cout] arrives by TMA ([64 co x 64 rows] boxes); the B tile -- 64 positions x BN
+// columns of the never-materialised column matrix -- is gathered with the validated cp.async zero-fill
+// pattern of conv_gemm_kernel into the MN-major swizzled layout ([64 k-rows][128 B] per 64-column chunk,
+// chunks 8192 B apart).  With it the column matrix (and im2col) disappears from training entirely.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_wgrad_kernel(const ConvGather g, const __grid_constant__ CUtensorMap tmap_a,
+                  const __grid_constant__ CUtensorMap tmap_d, const GemmEpilogue ep, const int M, const int N,
+                  const int K, const int kb_per_split) {
+  using S = GemmSmem<BN, STAGES, false>;
+  constexpr int kBlockK = 64, kUmmaK = 16;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kIdesc = make_idesc(1u, kBlockM, BN) | (1u << 15) | (1u << 16);  // A and B MN-major
+  static_assert(BN % 64 == 0, "MN-major B tiles come in 64-column chunks");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* mask_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * kBlockM;
+  const int total_kb = (K + kBlockK - 1) / kBlockK;  // K = number of output positions
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(total_kb, kb_begin + kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+  if (num_kb <= 0) return;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    if (ep.tma_store) tma_prefetch_desc(&tmap_d);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1 + 128);  // TMA (expect_tx arrive) + every gather thread
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(&mask_bar[q], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  DK_PDL_WAIT();
+  DK_PDL_TRIGGER();
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (dZ, MN-major A) ------------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * S::kStageBytes;
+        mbar_expect_tx(&full_bar[stage], S::kABytes);
+#pragma unroll
+        for (int c = 0; c < kBlockM / 64; ++c)
+          tma_load_2d(sa + c * 8192, &tmap_a, m0 + c * 64, kb * kBlockK, &full_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        fence_proxy_async_smem();  // the gathered tile was written through the generic proxy (cp.async)
+        const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+        const uint32_t sb = sa + S::kABytes;
+        const uint64_t adesc = make_smem_desc_sw128_mn(sa);
+        const uint64_t bdesc = make_smem_desc_sw128_mn(sb);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_f16(tmem_base, adesc + (2048 >> 4) * k, bdesc + (2048 >> 4) * k, kIdesc, (kb | k) != 0);
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------ gather producers (B), then epilogue ----------------------------
+    const int t = (warp - 2) * 32 + lane;   // 0..127
+    const int kr = t & 63;                  // GEMM-k row (output position) inside the k-block
+    constexpr int kUnits = BN / 8;          // 16-byte units per row
+    const int u_begin = (t >> 6) * (kUnits / 2), u_end = u_begin + kUnits / 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      const uint32_t sb = smem_u32(smem + stage * S::kStageBytes + S::kABytes);
+      const int m = kb * kBlockK + kr;      // output position
+      const bool row_ok = m < K;
+      int b = 0, y = 0, x = 0;
+      if (row_ok) {
+        b = m / (g.GH * g.GW);
+        const int rem = m - b * g.GH * g.GW;
+        y = rem / g.GW;
+        x = rem - y * g.GW;
+      }
+      const int ty0 = y * g.mul - g.off, tx0 = x * g.mul - g.off;
+      const __nv_bfloat16* img = g.src + static_cast<size_t>(b) * g.SH * g.SW * g.C;
+      int n = n0 + u_begin * 8;             // column of the (virtual) column matrix = (tap, c)
+      int tap = n / g.C;
+      int c = n - tap * g.C;
+      int kh = tap / g.KW;
+      int kw = tap - kh * g.KW;
+      for (int u = u_begin; u < u_end; ++u) {
+        const __nv_bfloat16* src = g.src;
+        uint32_t nbytes = 0;
+        if (row_ok && n < N) {
+          const int ty = ty0 + kh, tx = tx0 + kw;
+          if (ty >= 0 && tx >= 0 && ty < g.SH && tx < g.SW) {
+            src = img + (static_cast<size_t>(ty) * g.SW + tx) * g.C + c;
+            nbytes = 16;
+          }
+        }
+        // unit u -> 64-column chunk u / 8 (8192 B apart), 16-byte slot (u % 8) of row kr, 128-byte swizzle
+        const uint32_t dst = sb + (u >> 3) * 8192 + kr * 128 + (((u & 7) ^ (kr & 7)) << 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+        n += 8;
+        c += 8;
+        if (c >= g.C) {
+          c = 0;
+          if (++kw == g.KW) { kw = 0; ++kh; }
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage])) : "memory");
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    gemm_epilogue<BN>(tmap_d, tmap_d, ep, M, N, m0, n0, warp, lane, tmem_base, smem, tmem_full_bar, mask_bar);
+    tcgen05_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_conv_wgrad(const ConvGather& g, const CUtensorMap* ta, const CUtensorMap* td, GemmEpilogue ep, int M,
+                             int N, int K, int splits, cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES, false>;
+  auto kern = conv_wgrad_kernel<BN, STAGES>;
+  static bool configured[64] = {};
+  int dev = 0;
+  DK_HOST_CHECK(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    DK_HOST_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured[dev & 63] = true;
+  }
+  const int total_kb = (K + 63) / 64;
+  if (splits < 1) splits = 1;
+  if (splits > total_kb) splits = total_kb;
+  const int kb_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + kb_per_split - 1) / kb_per_split;
+  if (!ep.d_fp32 || td == nullptr) return -6;  // split-K accumulates with the fp32 TMA add-reduction
+  ep.tma_store = 1;
+  ep.tma_mask = 0;
+  dim3 grid((N + BN - 1) / BN, (M + kBlockM - 1) / kBlockM, splits);
+  DK_HOST_CHECK(DK_LAUNCH(kern, grid, kGemmThreads, S::kTotal, stream, g, *ta, *td, ep, M, N, K, kb_per_split));
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // dgrad weights: Wd[c, (kh', kw', co)] = W[co, (KH - 1 - kh', KW - 1 - kw', c)]   (both bf16, K-major)
 __global__ void __launch_bounds__(256)
 conv_weight_flip_kernel(const __nv_bfloat16* __restrict__ w, int ldw, __nv_bfloat16* __restrict__ wd, int ldwd, int Cout,
@@ -1676,6 +1872,37 @@ int dk_conv_gemm(const void* src, int SH, int SW, int C, int GH, int GW, int KH,
   const bool has_m = ep->mask != nullptr && dk_gemm_encode_output(&tm, ep->mask, ep->ld_mask, M, N, 0) == 0;
   return dk_conv_gemm_launch(src, SH, SW, C, GH, GW, KH, KW, mul, off, div, &tb, has_d ? &td : nullptr,
                              has_m ? &tm : nullptr, ep, M, N, K, bn, stream);
+}
+
+// EXPERIMENTAL implicit wgrad (see conv_wgrad_kernel): dW [Cout, KH KW Cin] fp32 += dZ^T * gather(X).
+// tmap_a: dZ stored [rows, Cout] encoded as an MN-major A operand (dk_tmap_encode_2d(.., rows = K_gemm, cols = Cout, box 64));
+// tmap_d: the fp32 gradient matrix [Cout, KH KW Cin] (must be zeroed by the caller: split-K adds into it).
+int dk_conv_wgrad_launch(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int stride, int pad,
+                         const void* tmap_a, const void* tmap_d, const DkGemmEpilogue* ep, int Cout, int rows, int splits,
+                         void* stream) {
+  if (C % 8 != 0 || Cout <= 0 || rows <= 0) return -3;
+  dk::ConvGather g;
+  g.src = reinterpret_cast<const __nv_bfloat16*>(src);
+  g.SH = SH; g.SW = SW; g.C = C; g.GH = GH; g.GW = GW; g.KH = KH; g.KW = KW; g.mul = stride; g.off = pad; g.div = 1;
+  return dk::launch_conv_wgrad<128, 4>(g, reinterpret_cast<const CUtensorMap*>(tmap_a),
+                                       reinterpret_cast<const CUtensorMap*>(tmap_d), *ep, Cout, KH * KW * C, rows, splits,
+                                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+// one-shot variant (tests)
+int dk_conv_wgrad(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int stride, int pad,
+                  const void* dz, long lddz, float* dw, long lddw, int Cout, int rows, int splits, void* stream) {
+  alignas(64) CUtensorMap ta, td;
+  int r = dk_tmap_encode_2d(&ta, dz, DK_BF16, rows, Cout, lddz, 64);
+  if (r != 0) return r;
+  r = dk_gemm_encode_output(&td, dw, lddw, Cout, KH * KW * C, 1);
+  if (r != 0) return r;
+  DkGemmEpilogue ep = {};
+  ep.alpha = 1.f;
+  ep.d = dw;
+  ep.ldd = static_cast<int>(lddw);
+  ep.d_fp32 = 1;
+  return dk_conv_wgrad_launch(src, SH, SW, C, GH, GW, KH, KW, stride, pad, &ta, &td, &ep, Cout, rows, splits, stream);
 }
 
 int dk_conv_weight_flip(const void* w, int ldw, void* wd, int ldwd, int Cout, int Cin, int KH, int KW, void* stream) {

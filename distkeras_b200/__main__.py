@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SWITCHES = ("DK_CONV_LDGSTS", "DK_BACKEND", "DK_COMM", "DK_STRICT", "DK_DEDICATED_PS", "DK_LOG", "DK_NVTX", "DK_NUMA", "DK_FAULT",
-            "DK_PERSISTENT", "DK_PAIR", "DK_PDL", "DK_SIDE_STREAMS", "DK_FUSED_HEAD", "DK_IMPLICIT_CONV")
+            "DK_PERSISTENT", "DK_PAIR", "DK_PDL", "DK_SIDE_STREAMS", "DK_FUSED_HEAD", "DK_IMPLICIT_CONV", "DK_IMPLICIT_WGRAD", "DK_EXPERIMENTAL")
 
 
 def info() -> dict:

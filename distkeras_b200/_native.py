@@ -38,7 +38,7 @@ OP_PS_COMMIT, OP_PS_PULL, OP_PS_EXCHANGE, OP_PS_ELASTIC, OP_PS_DAMPED, OP_PS_TIC
 OP_LOCK_ACQUIRE, OP_LOCK_RELEASE, OP_EAMSGD_PRE, OP_EAMSGD_POST, OP_CAST, OP_ELOSS = 19, 20, 21, 22, 23, 24
 OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D, OP_FORK, OP_JOIN, OP_GEMM_PULL = 25, 26, 27, 28, 29, 30, 31
 OP_BN_FWD, OP_BN_INF, OP_BN_BWD, OP_GAP_FWD, OP_GAP_BWD, OP_HEAD = 32, 33, 34, 35, 36, 37
-OP_CONV_GEMM, OP_WFLIP = 38, 39
+OP_CONV_GEMM, OP_WFLIP, OP_CONV_WGRAD = 38, 39, 40
 GEMM_TF32, GEMM_A_MN, GEMM_B_MN, GEMM_PERSISTENT, GEMM_PAIR = 1, 2, 4, 8, 16
 
 OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6}
@@ -62,6 +62,8 @@ _SIGNATURES = {
     "dk_conv_weight_flip": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "dk_conv_pick_bn": (i32, [i32]),
     "dk_conv_gather_mode": (i32, [i32]),
+    "dk_conv_wgrad": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, i64, i32, i32, i32, vp]),
+    "dk_engine_add_conv_wgrad": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, i64, i32, i32]),
     # ps
     "dk_ps_commit": (i32, [vp, vp, vp, i64, f32, vp, vp, i32, u32, vp]),
     "dk_ps_pull": (i32, [vp, vp, vp, vp, i64, vp, vp, vp]),

@@ -401,10 +401,13 @@ class NativeReplica(Replica):
             implicit = (os.environ.get("DK_IMPLICIT_CONV", "0") == "1" and Cin % 8 == 0 and Nout % 8 == 0
                         and cur["ld"] == Cin and wbld == K and b.kh == b.kw and not is_last)
             im2col_args = [cur["t"].data_ptr(), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad, OH, OW, col.data_ptr(), _r8(K)]
+            # EXPERIMENTAL (DK_IMPLICIT_WGRAD=1, needs DK_IMPLICIT_CONV=1): the wgrad gathers too, so no column
+            # matrix is built at all for this layer
+            implicit_wgrad = implicit and os.environ.get("DK_IMPLICIT_WGRAD", "0") == "1" and Nout <= 128
             for lst in lists:
                 if not implicit:
                     self._add(lst, N.OP_IM2COL, im2col_args)
-                elif lst in self._train_lists:
+                elif lst in self._train_lists and not implicit_wgrad:
                     # only the wgrad GEMM (backward list) reads the column matrix: build it on side branch 3
                     # while the forward chain continues; the backward list joins that branch before the wgrad
                     self._add(lst, N.OP_FORK, [3])
@@ -487,7 +490,7 @@ class NativeReplica(Replica):
             two = self._side_streams >= 2
             s_bias = 2 if two else (1 if need_dx else 0)
             s_wgrad = (1 if need_dx else 0) if two else 1
-            if implicit:  # the column matrix was built on branch 3 during the forward pass
+            if implicit and not implicit_wgrad:  # the column matrix was built on branch 3 during the forward pass
                 self._add(lst, N.OP_JOIN, [3])
             for sid in {s_bias, s_wgrad} - {0}:
                 self._add(lst, N.OP_FORK, [sid])
@@ -498,10 +501,21 @@ class NativeReplica(Replica):
                           [1.0])
             self.lib.dk_engine_set_build_stream(self.engine, s_wgrad)
             # wgrad: dW[Nout, K] = dZ^T[Nout, rows] * In[rows, K]  (both operands MN-major views)
-            ep = N.GemmEpilogue()
-            ep.d, ep.ldd, ep.d_fp32, ep.alpha = g_ptr + 4 * kseg.offset, K, 1, 1.0
-            self._gemm(lst, grad["t"].data_ptr(), grad["ld"], a_in["t"].data_ptr(), a_in["ld"], Nout, K, rows,
-                       N.GEMM_A_MN | N.GEMM_B_MN, ep)
+            if implicit and implicit_wgrad:
+                if grad["ld"] != Nout:
+                    raise UnsupportedByNativeEngine("implicit wgrad needs an unpadded output gradient")
+                Hh, Ww, Ci = b.in_shape
+                Oh, Ow, _ = b.out_shape
+                r = self.lib.dk_engine_add_conv_wgrad(self.engine, lst, C.c_void_p(inp["t"].data_ptr()), Hh, Ww, Ci, Oh, Ow,
+                                                      b.kh, b.kw, b.stride, b.pad, C.c_void_p(grad["t"].data_ptr()),
+                                                      grad["ld"], C.c_void_p(g_ptr + 4 * kseg.offset), K, Nout, rows)
+                if r < 0:
+                    raise RuntimeError(f"dk_engine_add_conv_wgrad failed: {r}")
+            else:
+                ep = N.GemmEpilogue()
+                ep.d, ep.ldd, ep.d_fp32, ep.alpha = g_ptr + 4 * kseg.offset, K, 1, 1.0
+                self._gemm(lst, grad["t"].data_ptr(), grad["ld"], a_in["t"].data_ptr(), a_in["ld"], Nout, K, rows,
+                           N.GEMM_A_MN | N.GEMM_B_MN, ep)
             self.lib.dk_engine_set_build_stream(self.engine, 0)
             if not need_dx:
                 return None, True

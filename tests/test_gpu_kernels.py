@@ -417,3 +417,24 @@ def test_implicit_gemm_conv_forward_and_dgrad(N, B, H, Cin, Cout, k, stride, pad
     gref = xr.grad.permute(0, 2, 3, 1).reshape(B * H * H, Cin)
     gref = torch.where(mask.float() > 0, gref, torch.zeros_like(gref))
     assert torch.allclose(dx.float(), gref, atol=0.03 * float(gref.abs().max()) + 1e-3, rtol=3e-2)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DK_EXPERIMENTAL") != "1",
+                    reason="conv_wgrad_kernel has not been validated on hardware yet (set DK_EXPERIMENTAL=1 to run)")
+@pytest.mark.parametrize("B,H,Cin,Cout,k,stride,pad,splits", [(4, 16, 32, 32, 3, 1, 1, 4), (3, 14, 32, 64, 3, 1, 0, 1),
+                                                              (2, 12, 64, 64, 3, 2, 1, 3)])
+def test_implicit_gemm_conv_wgrad_experimental(N, B, H, Cin, Cout, k, stride, pad, splits):
+    """EXPERIMENTAL implicit weight gradient vs autograd (first thing to validate in the next GPU session)."""
+    torch.manual_seed(19)
+    OH = (H + 2 * pad - k) // stride + 1
+    x = bf(torch.randn(B, H, H, Cin, device="cuda"))
+    dz = bf(torch.randn(B, OH, OH, Cout, device="cuda"))
+    K = k * k * Cin
+    rows = B * OH * OH
+    dw = torch.zeros(Cout, K, dtype=torch.float32, device="cuda")
+    N.check(N.lib().dk_conv_wgrad(x.data_ptr(), H, H, Cin, OH, OH, k, k, stride, pad, dz.data_ptr(), Cout, dw.data_ptr(), K,
+                                  Cout, rows, splits, st()), "conv wgrad")
+    w = torch.zeros(Cout, Cin, k, k, device="cuda", requires_grad=True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), w, None, stride=stride, padding=pad).backward(dz.float().permute(0, 3, 1, 2))
+    ref = w.grad.permute(0, 2, 3, 1).reshape(Cout, K)  # [Cout, (kh, kw, c)]
+    assert torch.allclose(dw, ref, atol=2e-3 * rows ** 0.5, rtol=1e-3)
