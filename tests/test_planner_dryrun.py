@@ -1,0 +1,91 @@
+"""The native engine's planner (``parallel/engine.py``) normally only runs on a GPU box.  This dry run lowers
+every zoo model on CPU -- real host-side op lists in the C++ engine, a recording proxy in place of the calls that
+need a CUDA driver (tensor-map encoding) -- under every planner switch, so a Python-level mistake in a lowering
+branch cannot hide until the GPU tests run."""
+import collections
+from unittest import mock
+
+import pytest
+import torch
+
+from distkeras_b200 import _native as N
+from distkeras_b200.models import ZOO
+from distkeras_b200.parallel import engine as eng
+
+GPU_ONLY = ("dk_engine_add_gemm", "dk_engine_add_gemm_pull", "dk_engine_add_conv_gemm", "dk_engine_add_conv_wgrad")
+OP_NAMES = {v: k for k, v in vars(N).items() if k.startswith("OP_") and isinstance(v, int)}
+
+
+class RecordingLib:
+    """Delegates host-only engine calls to the real library and records the GPU-only ones."""
+
+    def __init__(self, real):
+        self._real = real
+        self.calls = collections.Counter()
+        self.ops = collections.Counter()
+
+    def __getattr__(self, name):
+        real = getattr(self._real, name)
+        if name in GPU_ONLY:
+            def fake(*args):
+                self.calls[name] += 1
+                return 0
+            return fake
+        if name == "dk_engine_add_op":
+            def add_op(h, lst, kind, *rest):
+                self.ops[OP_NAMES.get(int(kind), int(kind))] += 1
+                return real(h, lst, kind, *rest)
+            return add_op
+        return real
+
+
+def _lower(model_name, batch, monkeypatch, **env):
+    for k in ("DK_IMPLICIT_CONV", "DK_IMPLICIT_WGRAD", "DK_SIDE_STREAMS", "DK_FUSED_HEAD"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    lib = RecordingLib(N.lib())
+    cpu = torch.device("cpu")
+    with mock.patch.object(eng.N, "lib", lambda: lib), mock.patch.object(eng.torch, "device", lambda *a, **k: cpu), \
+            mock.patch.object(eng.torch.cuda, "set_device", lambda *a, **k: None), \
+            mock.patch.object(eng.NativeReplica, "refresh_shadow", lambda self: None):
+        rep = eng.NativeReplica(ZOO[model_name](seed=0), "adam", "categorical_crossentropy", batch, 0, in_dtype="u8",
+                                input_affine=(1 / 255.0, 0.0))
+        sizes = {n: lib.dk_engine_list_size(rep.engine, getattr(rep, n)) for n in ("L_step", "L_bwd", "L_fwd")}
+        rep.close()
+    return lib, sizes
+
+
+@pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 256), ("higgs_mlp", 128), ("mnist_convnet", 32),
+                                              ("cifar10_cnn", 32), ("resnet18", 4)])
+def test_default_lowering(model_name, batch, monkeypatch):
+    lib, sizes = _lower(model_name, batch, monkeypatch)
+    assert sizes["L_step"] > 0 and sizes["L_bwd"] > sizes["L_step"] // 2 and sizes["L_fwd"] > 0
+    assert lib.calls["dk_engine_add_gemm"] > 0 and lib.calls["dk_engine_add_conv_gemm"] == 0
+    assert lib.ops["OP_OPTIM"] == 1 and lib.ops["OP_FORK"] == lib.ops["OP_FORK"]  # one optimizer launch per step
+    if model_name in ("mnist_mlp", "cifar10_cnn"):  # head input width is a multiple of 8 (200 / 512)
+        assert lib.ops["OP_HEAD"] == 1 and lib.ops["OP_XENT"] == 1  # fused head in training, softmax kernel in inference
+    elif model_name in ("higgs_mlp", "mnist_convnet"):  # 500 / 225 inputs: the three-kernel head
+        assert lib.ops["OP_HEAD"] == 0 and lib.ops["OP_XENT"] == 2
+    if "cnn" in model_name or "convnet" in model_name:
+        assert lib.ops["OP_RELU_MASK"] == 0  # every conv dReLU is fused into col2im / pool backward
+
+
+@pytest.mark.parametrize("env", [dict(DK_FUSED_HEAD="0"), dict(DK_SIDE_STREAMS="1"), dict(DK_IMPLICIT_CONV="1"),
+                                 dict(DK_IMPLICIT_CONV="1", DK_IMPLICIT_WGRAD="1")],
+                         ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+@pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 256), ("cifar10_cnn", 32), ("resnet18", 4)])
+def test_lowering_under_every_switch(model_name, batch, env, monkeypatch):
+    lib, sizes = _lower(model_name, batch, monkeypatch, **env)
+    assert sizes["L_step"] > 0 and sizes["L_bwd"] > 0
+    conv_model = model_name != "mnist_mlp"
+    if env.get("DK_FUSED_HEAD") == "0":
+        assert lib.ops["OP_HEAD"] == 0 and lib.ops["OP_XENT"] == 2
+    if env.get("DK_IMPLICIT_CONV") == "1" and conv_model:
+        assert lib.calls["dk_engine_add_conv_gemm"] > 0 and lib.ops["OP_WFLIP"] > 0
+        if env.get("DK_IMPLICIT_WGRAD") == "1":
+            assert lib.calls["dk_engine_add_conv_wgrad"] > 0
+        else:
+            assert lib.calls["dk_engine_add_conv_wgrad"] == 0 and lib.ops["OP_IM2COL"] > 0
+    if env.get("DK_SIDE_STREAMS") == "1":
+        assert lib.ops["OP_JOIN"] == 1
