@@ -688,6 +688,47 @@ class Sequential:
                 n += b
         return [tot_l / max(n, 1), tot_a / max(n, 1)]
 
+    def fit(self, x, y, batch_size: int = 32, epochs: int = 1, shuffle: bool = True, seed: Optional[int] = None,
+            verbose: int = 0) -> dict:
+        """Keras-style single-process training loop over ``train_on_batch`` (partial last batch dropped, like
+        the reference's workers).  Returns ``{"loss": [...], "accuracy": [...]}`` with one entry per epoch."""
+        x = torch.as_tensor(np.asarray(x)) if not isinstance(x, torch.Tensor) else x
+        y = torch.as_tensor(np.asarray(y)) if not isinstance(y, torch.Tensor) else y
+        n = x.shape[0]
+        g = torch.Generator()
+        if seed is not None:
+            g.manual_seed(seed)
+        hist = {"loss": [], "accuracy": []}
+        for epoch in range(int(epochs)):
+            order = torch.randperm(n, generator=g) if shuffle else torch.arange(n)
+            tot_l = tot_a = 0.0
+            steps = n // batch_size
+            for i in range(steps):
+                idx = order[i * batch_size:(i + 1) * batch_size]
+                l, a = self.train_on_batch(x[idx], y[idx])
+                tot_l += l
+                tot_a += a
+            hist["loss"].append(tot_l / max(steps, 1))
+            hist["accuracy"].append(tot_a / max(steps, 1))
+            if verbose:
+                print(f"epoch {epoch + 1}/{epochs}: loss {hist['loss'][-1]:.4f} accuracy {hist['accuracy'][-1]:.4f}")
+        return hist
+
+    # -- persistence (README TODO of the reference: "Save/Load Keras model") ------------------------
+    def save_weights(self, path: str) -> None:
+        torch.save({"flat": self.get_flat_weights().detach().cpu()}, path)
+
+    def load_weights(self, path: str) -> None:
+        flat = torch.load(path, weights_only=True)["flat"]
+        if flat.numel() != self.num_params:
+            raise ValueError(f"weight file holds {flat.numel()} parameters, the model has {self.num_params}")
+        self.set_flat_weights(flat)
+
+    def save(self, path: str) -> None:
+        """Architecture (JSON) + weights in one file; see :func:`load_model`."""
+        torch.save({"model": self.to_json(), "flat": self.get_flat_weights().detach().cpu(), "loss": self.loss,
+                    "optimizer": self.optimizer if isinstance(self.optimizer, (str, dict, type(None))) else None}, path)
+
     def to(self, device) -> "Sequential":
         self.build()
         self.flat = self.flat.to(device)
@@ -724,3 +765,14 @@ def model_from_config(cfg: dict) -> Sequential:
 
 def model_from_json(text: str) -> Sequential:
     return model_from_config(json.loads(text))
+
+
+def load_model(path: str) -> Sequential:
+    """Inverse of :meth:`Sequential.save` (re-compiles with the stored loss / optimizer when present)."""
+    d = torch.load(path, weights_only=False)
+    m = model_from_json(d["model"])
+    m.build()
+    m.set_flat_weights(d["flat"])
+    if d.get("loss"):
+        m.compile(d["loss"], d.get("optimizer") or "sgd")
+    return m

@@ -97,3 +97,30 @@ def test_native_planner_grouping_cpu():
     assert [r.proj is not None for r in res] == [False, False, True, False, True, False, True, False]
     with pytest.raises(UnsupportedByNativeEngine):
         _group_layers(Sequential([Dense(8, activation="tanh", input_shape=(4,)), Dense(2, activation="softmax")]))
+
+
+def test_fit_save_and_load_roundtrip(tmp_path):
+    """Keras-style conveniences: ``fit`` (loss goes down), ``save`` / ``load_model``, ``save_weights`` / ``load_weights``."""
+    from distkeras_b200.models import load_model
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(512, 8, generator=g)
+    y = (x @ torch.randn(8, 3, generator=g)).argmax(1)
+    m = Sequential([Dense(16, activation="relu", input_shape=(8,)), Dense(3, activation="softmax")], seed=0)
+    m.compile("categorical_crossentropy", {"class_name": "adam", "config": {"lr": 0.02}})
+    h = m.fit(x, y, batch_size=32, epochs=4, seed=0)
+    assert len(h["loss"]) == 4 and h["loss"][-1] < 0.7 * h["loss"][0] and h["accuracy"][-1] > h["accuracy"][0]
+    path = str(tmp_path / "model.dk")
+    m.save(path)
+    m2 = load_model(path)
+    assert m2.to_json() == m.to_json() and torch.equal(m2.get_flat_weights(), m.get_flat_weights())
+    assert np.allclose(m2.predict(x[:16]), m.predict(x[:16]))
+    assert m2.evaluate(x, y) == m.evaluate(x, y)
+    wpath = str(tmp_path / "w.pt")
+    m.save_weights(wpath)
+    m3 = Sequential([Dense(16, activation="relu", input_shape=(8,)), Dense(3, activation="softmax")], seed=5)
+    m3.build()
+    m3.load_weights(wpath)
+    assert torch.equal(m3.get_flat_weights(), m.get_flat_weights())
+    with pytest.raises(ValueError):
+        Sequential([Dense(4, input_shape=(8,))], seed=0).load_weights(wpath)
