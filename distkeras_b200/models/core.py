@@ -428,6 +428,13 @@ LOSS_ALIASES = {
     "binary_crossentropy": "binary_crossentropy",
     "mse": "mse",
     "mean_squared_error": "mse",
+    # the remaining Keras-1 objectives (autograd executors; the native engine lowers cross-entropy and MSE)
+    "mae": "mae", "mean_absolute_error": "mae",
+    "mape": "mape", "mean_absolute_percentage_error": "mape",
+    "msle": "msle", "mean_squared_logarithmic_error": "msle",
+    "hinge": "hinge", "squared_hinge": "squared_hinge",
+    "kld": "kld", "kullback_leibler_divergence": "kld",
+    "poisson": "poisson", "cosine_proximity": "cosine_proximity",
 }
 
 
@@ -447,12 +454,33 @@ def compute_loss(loss: str, out: torch.Tensor, y: torch.Tensor, from_logits: boo
         if idx is not None:
             return F.nll_loss(logp, idx)
         return -(y.to(logp.dtype) * logp).sum(dim=-1).mean()
+    if from_logits:  # ``out`` are the pre-softmax scores: every other objective is defined on the probabilities
+        out = torch.softmax(out, dim=-1)
     if kind == "binary_crossentropy":
         p = out.clamp(1e-7, 1 - 1e-7)
         t = y.to(p.dtype).reshape(p.shape)
         return -(t * torch.log(p) + (1 - t) * torch.log(1 - p)).mean()
     t = y.to(out.dtype).reshape(out.shape)
-    return ((out - t) ** 2).mean()
+    if kind == "mse":
+        return ((out - t) ** 2).mean()
+    if kind == "mae":
+        return (out - t).abs().mean()
+    if kind == "mape":
+        return 100.0 * ((t - out).abs() / t.abs().clamp_min(1e-7)).mean()
+    if kind == "msle":
+        return ((torch.log1p(out.clamp_min(1e-7)) - torch.log1p(t.clamp_min(1e-7))) ** 2).mean()
+    if kind == "hinge":
+        return torch.clamp(1.0 - t * out, min=0.0).mean()
+    if kind == "squared_hinge":
+        return (torch.clamp(1.0 - t * out, min=0.0) ** 2).mean()
+    if kind == "kld":
+        tc, oc = t.clamp(1e-7, 1.0), out.clamp(1e-7, 1.0)
+        return (tc * torch.log(tc / oc)).sum(dim=-1).mean()
+    if kind == "poisson":
+        return (out - t * torch.log(out + 1e-7)).mean()
+    if kind == "cosine_proximity":
+        return -(F.normalize(t, dim=-1) * F.normalize(out, dim=-1)).sum(dim=-1).mean()
+    raise ValueError(f"unsupported loss {loss!r}")
 
 
 def compute_accuracy(out: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

@@ -124,3 +124,21 @@ def test_fit_save_and_load_roundtrip(tmp_path):
     assert torch.equal(m3.get_flat_weights(), m.get_flat_weights())
     with pytest.raises(ValueError):
         Sequential([Dense(4, input_shape=(8,))], seed=0).load_weights(wpath)
+
+
+@pytest.mark.parametrize("loss", ["mae", "mean_absolute_percentage_error", "msle", "hinge", "squared_hinge", "kld",
+                                  "poisson", "cosine_proximity", "binary_crossentropy", "mean_squared_error"])
+def test_keras_objectives_are_differentiable_and_train(loss):
+    """Every Keras-1 objective name is accepted and a few steps reduce it (autograd executor)."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(128, 6, generator=g)
+    target = torch.softmax(x @ torch.randn(6, 4, generator=g), dim=1)  # positive, rows sum to 1
+    if loss in ("hinge", "squared_hinge"):
+        target = torch.where(target > 0.25, torch.ones_like(target), -torch.ones_like(target))
+    head = "tanh" if loss in ("hinge", "squared_hinge") else "softmax"
+    m = Sequential([Dense(16, activation="relu", input_shape=(6,)), Dense(4, activation=head)], seed=0)
+    m.compile(loss, {"class_name": "adam", "config": {"lr": 0.02}})
+    first = m.train_on_batch(x, target)[0]
+    for _ in range(40):
+        last = m.train_on_batch(x, target)[0]
+    assert np.isfinite(first) and np.isfinite(last) and last < first
