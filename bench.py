@@ -49,8 +49,9 @@ def reference_arm() -> None:
         why = f"{type(exc).__name__}: {exc}"
     if why is None:
         why = "reference imported but needs a Spark cluster + Keras backend to train; none on this image"
-    print(json.dumps({"impl": "reference",
-                      "unavailable": ("cerndb/dist-keras cannot run here: " + why)[:300].replace("\n", " ")}))
+    if int(os.environ.get("RANK", "0")) == 0:  # one line per job, also when launched with torchrun
+        print(json.dumps({"impl": "reference",
+                          "unavailable": ("cerndb/dist-keras cannot run here: " + why)[:300].replace("\n", " ")}))
 
 
 class ClockSampler:
