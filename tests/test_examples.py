@@ -26,3 +26,29 @@ def test_example_runs(script, args, expect):
                        text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert expect in r.stdout, r.stdout[-2000:]
+
+
+NOTEBOOKS = [
+    ("mnist.ipynb", {"synthetic_mnist(60000": "synthetic_mnist(1024", "num_epoch=2": "num_epoch=1"}),
+    ("workflow.ipynb", {"synthetic_higgs(200000)": "synthetic_higgs(4096)", "num_epoch=2": "num_epoch=1"}),
+    ("data_preparation.ipynb", {"synthetic_cifar10(2000": "synthetic_cifar10(200", "reshape(2000, -1)": "reshape(200, -1)"}),
+    ("streaming_inference.ipynb", {"rows=1000": "rows=200"}),
+]
+
+
+@pytest.mark.parametrize("name,subst", NOTEBOOKS, ids=[n for n, _ in NOTEBOOKS])
+def test_notebook_code_cells_run(name, subst, tmp_path):
+    """The notebooks are shipped unexecuted; their code cells must run top to bottom (toy sizes, CPU)."""
+    import json
+
+    nb = json.load(open(os.path.join(ROOT, "examples", name)))
+    src = "\n".join("".join(c["source"]) for c in nb["cells"] if c["cell_type"] == "code")
+    for a, b in subst.items():
+        assert a in src, f"{name}: substitution target {a!r} not found"
+        src = src.replace(a, b)
+    script = tmp_path / "nb.py"
+    script.write_text(src)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", DK_BACKEND="thread")
+    r = subprocess.run([sys.executable, str(script)], cwd=os.path.join(ROOT, "examples"), env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
