@@ -39,12 +39,12 @@ class RecordingLib:
         return real
 
 
-def _lower(model_name, batch, monkeypatch, **env):
+def _lower(model_name, batch, monkeypatch, native_lib, **env):
     for k in ("DK_IMPLICIT_CONV", "DK_IMPLICIT_WGRAD", "DK_SIDE_STREAMS", "DK_FUSED_HEAD"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    lib = RecordingLib(N.lib())
+    lib = RecordingLib(native_lib)
     cpu = torch.device("cpu")
     with mock.patch.object(eng.N, "lib", lambda: lib), mock.patch.object(eng.torch, "device", lambda *a, **k: cpu), \
             mock.patch.object(eng.torch.cuda, "set_device", lambda *a, **k: None), \
@@ -58,8 +58,8 @@ def _lower(model_name, batch, monkeypatch, **env):
 
 @pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 256), ("higgs_mlp", 128), ("mnist_convnet", 32),
                                               ("cifar10_cnn", 32), ("resnet18", 4)])
-def test_default_lowering(model_name, batch, monkeypatch):
-    lib, sizes = _lower(model_name, batch, monkeypatch)
+def test_default_lowering(model_name, batch, monkeypatch, native_lib):
+    lib, sizes = _lower(model_name, batch, monkeypatch, native_lib)
     assert sizes["L_step"] > 0 and sizes["L_bwd"] > sizes["L_step"] // 2 and sizes["L_fwd"] > 0
     assert lib.calls["dk_engine_add_gemm"] > 0 and lib.calls["dk_engine_add_conv_gemm"] == 0
     assert lib.ops["OP_OPTIM"] == 1 and lib.ops["OP_FORK"] == lib.ops["OP_FORK"]  # one optimizer launch per step
@@ -75,8 +75,8 @@ def test_default_lowering(model_name, batch, monkeypatch):
                                  dict(DK_IMPLICIT_CONV="1", DK_IMPLICIT_WGRAD="1")],
                          ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 @pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 256), ("cifar10_cnn", 32), ("resnet18", 4)])
-def test_lowering_under_every_switch(model_name, batch, env, monkeypatch):
-    lib, sizes = _lower(model_name, batch, monkeypatch, **env)
+def test_lowering_under_every_switch(model_name, batch, env, monkeypatch, native_lib):
+    lib, sizes = _lower(model_name, batch, monkeypatch, native_lib, **env)
     assert sizes["L_step"] > 0 and sizes["L_bwd"] > 0
     conv_model = model_name != "mnist_mlp"
     if env.get("DK_FUSED_HEAD") == "0":
