@@ -54,6 +54,9 @@ _SIGNATURES = {
     # gemm
     "dk_tmap_encode_2d": (i32, [vp, vp, i32, i64, i64, i64, i32]),
     "dk_gemm_pick_bn": (i32, [i32]),
+    "dk_gemm_pick_bn2": (i32, [i32, i32]),
+    "dk_gemm_pick_bn_splitk": (i32, [i32, i32, i32]),
+    "dk_gemm_pick_splits_pair": (i32, [i32, i32, i32, i32]),
     "dk_gemm_tn": (i32, [vp, i64, vp, i64, C.POINTER(GemmEpilogue), i32, i32, i32, i32, i32, vp]),
     "dk_gemm_tn_ex": (i32, [vp, i64, vp, i64, C.POINTER(GemmEpilogue), i32, i32, i32, i32, i32, i32, vp]),
     "dk_gemm_pick_splits": (i32, [i32, i32, i32, i32, i32]),

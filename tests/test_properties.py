@@ -116,3 +116,33 @@ def test_dynsgd_scales_by_staleness(commits):
         ps.apply_commit({"worker_id": 0, "residual": r, "last_update": last})
         n += 1
     assert torch.allclose(ps.center_variable, want, atol=1e-4)
+
+
+@FAST
+@given(st.integers(1, 40000), st.integers(1, 5000), st.integers(1, 300000))
+def test_gemm_tile_and_split_heuristics_fill_one_wave(M, Nn, K):
+    """Host-side scheduling rules of the tcgen05 GEMM (csrc/gemm_tcgen05.cu): legal tile widths, and a split-K
+    factor whose tiles x splits never spill into a second, nearly empty wave."""
+    from distkeras_b200 import _native
+
+    try:
+        lib = _native.lib()
+    except RuntimeError:
+        import pytest
+
+        pytest.skip("native library not built")
+    bn = lib.dk_gemm_pick_bn(Nn)
+    assert bn in (16, 32, 64, 128, 256) and (bn >= min(Nn, 128) or bn == 128)
+    bn2 = lib.dk_gemm_pick_bn2(M, Nn)
+    assert bn2 in (16, 32, 64, 128)
+    bk = lib.dk_gemm_pick_bn_splitk(M, Nn, K)
+    assert bk in (64, 128, 256)
+    splits = lib.dk_gemm_pick_splits(M, Nn, K, bk, 0)
+    tiles = ((M + 127) // 128) * ((Nn + bk - 1) // bk)
+    slots = 148 if bk > 128 else 296
+    assert 1 <= splits <= 32
+    assert splits == 1 or tiles * splits <= slots          # single wave
+    assert splits == 1 or splits <= max(1, ((K + 63) // 64) // 4)  # at least 4 k-blocks per slice
+    ps = lib.dk_gemm_pick_splits_pair(M, Nn, K, 256)
+    pair_tiles = ((M + 255) // 256) * ((Nn + 255) // 256)
+    assert 1 <= ps <= 32 and (ps == 1 or pair_tiles * ps <= 74)
