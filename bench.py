@@ -1,28 +1,33 @@
 #!/usr/bin/env python
-"""Headline benchmark: ADAG / DOWNPOUR / AEASGD samples/s on the MNIST MLP (or CIFAR-10 CNN) on N B200s.
+"""Headline benchmark: ADAG / DOWNPOUR / AEASGD / DynSGD samples/s on the MNIST MLP (or a conv net) on N B200s.
 
-    python bench.py --gpus 1 --steps 1200 --warmup 48
+    python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-        --master-port 29511 bench.py --gpus 8 --steps 1200 --warmup 48
+        --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5
+    python bench.py --impl reference --gpus 1 --steps 20 --warmup 5      # the unmodified reference
 
-A *step* is one mini-batch of ``--batch`` samples on EVERY worker (weak scaling: per-GPU work is
-fixed), including that worker's share of the parameter-server traffic (one fused commit + pull
-every ``--window`` steps).  Two numbers are reported:
+A *step* is one mini-batch of ``--batch`` samples on EVERY worker (weak scaling: per-GPU work is fixed),
+including that worker's share of the parameter-server traffic (one fused commit + pull every
+``--window`` steps).  The timed quantity is a *region* of exactly ``--steps`` = K consecutive steps:
 
-* ``value``     device-timed (CUDA events on the worker's compute stream, max over ranks):
-                CUDA-graph windows with the mini-batches already resident in device staging.
-* ``e2e``       the same metric through the public API (``ADAG(...).train(dataset)``): every
-                step's inputs are DMA'd from pinned host memory (uint8 pixels + int32 label) and
-                every step's loss / accuracy record is read back to the host.
+* ``value``  device-timed, max over ranks.  Every region is ONE CUDA graph of K training steps with the
+             algorithm's exchanges at the iterations where they fall (K need not be a multiple of the
+             window: the graphs cycle through the window phases).  After >= W warm-up steps that replay
+             every graph once, R >= 50 regions run back to back, each bracketed by CUDA events on the
+             worker's stream; ``ms_per_step * steps`` is the MEAN region time of the slowest rank, so
+             every timed step is in steady state and every rank performs R*K/window exchanges.
+* ``e2e``    the same metric through the public API (``ADAG(...).train(dataset)``): every step's
+             inputs are DMA'd from pinned host memory (uint8 pixels + int32 label) and every step's
+             loss / accuracy record is read back to the host; timed on the device per graph replay.
 
-``--impl reference`` would run the unmodified reference from ``baseline/_ref``; it cannot be
-imported on this image (needs pyspark + keras, Python-2 syntax), so that arm reports
-``unavailable``.
+``--impl reference`` runs the UNMODIFIED reference (``baseline/_ref``) on shimmed Keras / Spark
+substrates for the same model / trainer / window / batch (``baseline/reference_arm.py``).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -32,26 +37,34 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BASELINE = {  # published reference numbers: samples/s derived from training time
-    "adag": 268.0,        # ADAG MNIST MLP, 30 workers (examples/mnist_analysis.ipynb:841-842)
-    "downpour": 19203.0,  # DOWNPOUR Higgs MLP, 16 workers (examples/example_1_analysis.ipynb:553-554)
-    "aeasgd": 16454.0,    # AEASGD Higgs MLP, 16 workers (examples/example_1_analysis.ipynb:501-502)
+# published reference numbers, other hardware (CPU Spark clusters): context only
+PUBLISHED = {
+    "adag": {"samples_per_s": 268.0, "what": "ADAG MNIST MLP, 30 CPU workers, batch 4, window 5 "
+                                             "(examples/mnist_analysis.ipynb:841-842)"},
+    "downpour": {"samples_per_s": 19203.0, "what": "DOWNPOUR Higgs MLP, 16 CPU workers (example_1_analysis.ipynb:553-554)"},
+    "aeasgd": {"samples_per_s": 16454.0, "what": "AEASGD Higgs MLP, 16 CPU workers (example_1_analysis.ipynb:501-502)"},
 }
+DEFAULT_BATCH = {"mnist_mlp": 64, "cifar10_cnn": 64, "mnist_convnet": 64, "higgs_mlp": 64}
+IN_SHAPE = {"mnist_mlp": (784,), "cifar10_cnn": (32, 32, 3), "mnist_convnet": (28, 28, 1), "higgs_mlp": (30,)}
+DEFAULT_WINDOW = {"adag": 12, "downpour": 5, "aeasgd": 32, "dynsgd": 5, "eamsgd": 32, "experimental": 5}
+L2_BYTES = 126 * 2**20
 
 
-def reference_arm() -> None:
-    why = None
+def reference_arm(args) -> None:
+    """The unmodified reference through its own public API (see baseline/reference_arm.py)."""
+    rec = None
     try:
-        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
-        import distkeras  # noqa: F401
-        from distkeras import trainers  # noqa: F401
-    except BaseException as exc:  # SyntaxError / ImportError
-        why = f"{type(exc).__name__}: {exc}"
-    if why is None:
-        why = "reference imported but needs a Spark cluster + Keras backend to train; none on this image"
-    if int(os.environ.get("RANK", "0")) == 0:  # one line per job, also when launched with torchrun
-        print(json.dumps({"impl": "reference",
-                          "unavailable": ("cerndb/dist-keras cannot run here: " + why)[:300].replace("\n", " ")}))
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import reference_arm as ra
+
+        rec = ra.run(args.algo, args.model, args.gpus, args.steps, args.warmup, args.batch or DEFAULT_BATCH[args.model],
+                     args.window or DEFAULT_WINDOW[args.algo], args.optimizer, args.dedicated_ps)
+        if rec is None:  # torchrun ranks > 0: the reference's launcher is its own (shimmed) Spark driver on rank 0
+            return
+    except BaseException as exc:  # SyntaxError / ImportError / runtime failure of the reference
+        rec = {"impl": "reference",
+               "unavailable": ("cerndb/dist-keras could not run here: %s: %s" % (type(exc).__name__, exc))[:300].replace("\n", " ")}
+    print(json.dumps(rec, default=lambda o: o.item() if hasattr(o, "item") else str(o)))
 
 
 class ClockSampler:
@@ -129,34 +142,40 @@ class ClockSampler:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
+def auto_steps_per_graph(tau: int, batch: int) -> int:
+    """Mirror of FabricWorker's default: ~8k rows per graph replay, whole windows."""
+    return max(1, min(64, -(-8192 // (tau * batch)))) * tau
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1200)
-    ap.add_argument("--warmup", type=int, default=48)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--algo", default="adag", choices=["adag", "downpour", "aeasgd", "dynsgd", "eamsgd", "experimental"])
     ap.add_argument("--model", default="mnist_mlp", choices=["mnist_mlp", "cifar10_cnn", "mnist_convnet", "higgs_mlp"])
     ap.add_argument("--batch", type=int, default=None, help="mini-batch per worker")
     ap.add_argument("--window", type=int, default=None, help="communication window (ADAG default 12)")
     ap.add_argument("--optimizer", default="adam")
-    ap.add_argument("--comm", default="exchange", choices=["exchange", "commit_pull", "fused_pull"])
+    ap.add_argument("--comm", default="default", choices=["default", "exchange", "commit_pull", "fused_pull"])
     ap.add_argument("--dedicated-ps", action="store_true", help="rank 0 hosts the center only (N-1 workers)")
+    ap.add_argument("--sharded-ps", action="store_true", help="slice r of the center lives in rank r's HBM")
+    ap.add_argument("--reps", type=int, default=0, help="timed K-step regions (0 = auto: >= 50, ~1 s)")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
 
     if args.impl == "reference":
-        reference_arm()
+        reference_arm(args)
         return
 
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.gpus != world:
-        if world == 1 and args.gpus > 1:
-            sys.exit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
-                     "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        sys.exit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                 "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
     from distkeras_b200 import trainers
     from distkeras_b200.data import Dataset
     from distkeras_b200.models import ZOO
@@ -169,48 +188,46 @@ def main() -> None:
     from distkeras_b200.utils.numa import bind_to_gpu_numa_node
 
     numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
-    dist = None
-    if world > 1:
-        dist = runtime._init_pg()
+    dist = runtime._init_pg() if world > 1 else None
     exchange_obj, barrier = runtime._dist_helpers(dist) if dist else ((lambda o, s: o), (lambda: None))
 
-    defaults = {"mnist_mlp": (16384, (784,)), "cifar10_cnn": (256, (32, 32, 3)), "mnist_convnet": (256, (28, 28, 1)),
-                "higgs_mlp": (4096, (30,))}
-    B = args.batch or defaults[args.model][0]
-    in_shape = defaults[args.model][1]
-    tau = args.window or {"adag": 12, "downpour": 5, "aeasgd": 32, "dynsgd": 5, "eamsgd": 32, "experimental": 5}[args.algo]
-    K, W = int(args.steps), max(3, int(args.warmup))
+    def gather(obj):
+        if not dist:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    B = args.batch or DEFAULT_BATCH[args.model]
+    in_shape = IN_SHAPE[args.model]
+    tau = args.window or DEFAULT_WINDOW[args.algo]
+    K, W = max(1, int(args.steps)), max(3, int(args.warmup))
     model = ZOO[args.model](seed=0)
     model.build()
     classes = model.output_shape[-1]
+    feat = 1
+    for s in in_shape:
+        feat *= s
 
     TrainerCls = {"adag": trainers.ADAG, "downpour": trainers.DOWNPOUR, "aeasgd": trainers.AEASGD,
                   "dynsgd": trainers.DynSGD, "eamsgd": trainers.EAMSGD, "experimental": trainers.Experimental}[args.algo]
-    kw = dict(num_workers=world - 1 if (args.dedicated_ps and world > 1) else world, batch_size=B,
-              communication_window=tau)
+    dedicated = args.dedicated_ps and world > 1
+    kw = dict(num_workers=world - 1 if dedicated else world, batch_size=B, communication_window=tau)
     if args.algo in ("aeasgd", "eamsgd"):
         kw.update(rho=0.1, learning_rate=0.1)  # BASELINE config: AEASGD rho=0.1
     trainer = TrainerCls(model, args.optimizer, "categorical_crossentropy", **kw)
     trainer.backend = "fabric"
-    trainer.dedicated_ps = args.dedicated_ps
-    trainer.comm = args.comm
+    trainer.dedicated_ps = dedicated
+    if args.comm != "default":
+        trainer.comm = args.comm
+    trainer.sharded_ps = bool(args.sharded_ps)
     trainer.shard_mode = "static"
     n_workers = trainer.num_workers
-
-    # synthetic data of the named shape: uint8 pixels + int32 labels, pinned host memory.
-    feat = 1
-    for s in in_shape:
-        feat *= s
+    comm = getattr(trainer, "comm", "exchange")
+    is_worker = (rank >= 1 or not dedicated) or world == 1
     g = torch.Generator().manual_seed(1234 + rank)
-    # e2e host dataset: W warm-up steps + `chunk` steps replayed K / chunk times (keeps the pinned
-    # footprint bounded for long runs; the timed region is still exactly K steps streamed from host)
-    chunk = K
-    for c in (480, 360, 240, 120):
-        if K > c and K % c == 0 and c % tau == 0:
-            chunk = c
-            break
-    rows = (W + chunk) * B
-    is_worker = (rank >= 1 or not args.dedicated_ps) or world == 1
+    in_dtype = "f32" if args.model == "higgs_mlp" else "u8"
+    row_bytes = feat * (4 if in_dtype == "f32" else 1) + 4
 
     # ---------------------------------------------------------------- kernel-only (device-timed)
     alg = trainer.algorithm()
@@ -224,16 +241,19 @@ def main() -> None:
         ps, info = None, None
     info = exchange_obj(info, 0)
     region = ps.region if rank == 0 else FabricRegion.open(info, local)
-    ms_dev, launches = 0.0, 0
     sampler = ClockSampler(world)
     if rank == 0:
         sampler.start()
+    period = tau // math.gcd(K, tau)          # distinct window phases a K-step region can start at
+    period = period * 2 // math.gcd(period, 2)  # ... times the two staging parities
+    staged_bytes = 2 * K * B * row_bytes
+    flush = staged_bytes < L2_BYTES
+    mine = {"rank": rank, "worker": is_worker}
     if is_worker:
-        wid = rank - 1 if (args.dedicated_ps and world > 1) else rank
-        in_dtype = "f32" if args.model == "higgs_mlp" else "u8"
+        wid = rank - 1 if dedicated else rank
         affine = (1.0, 0.0) if in_dtype == "f32" else (1.0 / 255.0, 0.0)
         worker = FabricWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid, B, local, in_dtype,
-                              affine, comm=args.comm)
+                              affine, comm=comm, steps_per_graph=K)
         # resident inputs for the kernel-only number: both staging parities hold distinct random batches
         for p in (0, 1):
             if in_dtype == "u8":
@@ -242,47 +262,69 @@ def main() -> None:
                 worker.x_stage[p].copy_(torch.randn(worker.x_stage[p].shape, generator=g))
             worker.y_stage[p].copy_(torch.randint(0, classes, worker.y_stage[p].shape, generator=g).to(torch.int32))
         worker.initial_pull()
-        worker.capture()
+        for r in range(period):                       # capture every (parity, phase) graph
+            worker.graph(r & 1, K, (r * K) % tau)
+        scrub = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device="cuda") if flush else None
 
-        def run_steps(n):
-            done = 0
-            nwin = 0
-            while n - done >= tau:
-                worker.graphs[nwin & 1].replay()
-                done += tau
-                nwin += 1
-            for j in range(n - done):  # tail: eager steps, no commit (reference semantics)
-                worker._step(0, j)
-            return nwin, n - done
+        def run_regions(first: int, count: int, events=None):
+            """Replay regions first .. first+count-1; with `events`, bracket each by a CUDA event pair
+            (after the L2 flush when the staged inputs do not exceed L2)."""
+            for r in range(first, first + count):
+                if flush:
+                    scrub.fill_(r & 0xFF)
+                if events is not None:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e0.record(worker.compute)
+                worker.replay(r & 1, K, (r * K) % tau)
+                if events is not None:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record(worker.compute)
+                    events.append((e0, e1))
 
+        warm_regions = max(period, -(-W // K))
+        warm_regions += (-warm_regions) % period
         with torch.cuda.stream(worker.compute):
-            run_steps(W)
+            cal = []
+            run_regions(0, warm_regions, cal)
         torch.cuda.synchronize()
+        cal_ms = statistics.median(a.elapsed_time(b) for a, b in cal)
+        R = args.reps if args.reps > 0 else int(min(4000, max(50, 1000.0 / max(cal_ms, 1e-3))))
+        R += (-R) % period
+        worker.launched = worker.exchanges = 0
         barrier()
         sampler.mark_start()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        events = []
         with torch.cuda.stream(worker.compute):
-            ev0.record(worker.compute)
-            nwin, ntail = run_steps(K)
-            ev1.record(worker.compute)
+            run_regions(warm_regions, R, events)
         torch.cuda.synchronize()
         sampler.mark_end()
         barrier()
-        ms_dev = ev0.elapsed_time(ev1)
-        per_step = (worker.kernels_per_window - worker.comm_kernels()) // tau
-        launches = nwin * worker.kernels_per_window + ntail * per_step
+        rep_ms = [a.elapsed_time(b) for a, b in events]
+        # the exchange alone, all ranks at once (PS ingress / egress contention included)
+        xev = []
+        with torch.cuda.stream(worker.compute):
+            for i in range(30):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                if flush:
+                    scrub.fill_(i)
+                e0.record(worker.compute)
+                xk = worker._comm_ops()
+                e1.record(worker.compute)
+                xev.append((e0, e1))
+        torch.cuda.synchronize()
+        x_us = 1e3 * statistics.median(a.elapsed_time(b) for a, b in xev[5:])
+        mine.update({"rep_ms": rep_ms, "launches": worker.launched, "exchanges": worker.exchanges, "exchange_us": x_us,
+                     "exchange_kernels": xk, "kernels_per_step": worker.kernels_per_step, "params": worker.rep.P,
+                     "R": R})
+        barrier()
+        worker.rep.close()
+        del worker, scrub
     else:
         barrier()
         barrier()
+        barrier()
     clocks = sampler.stop() if rank == 0 else None
-    if dist:
-        t = torch.tensor([ms_dev, float(launches)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t[0:1], op=dist.ReduceOp.MAX)
-        dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM)
-        ms_dev, launches = float(t[0]), int(t[1])
-    if is_worker:
-        worker.rep.close()
-        del worker
+    allr = gather(mine)
     barrier()
     if rank != 0:
         region.close()
@@ -292,50 +334,86 @@ def main() -> None:
 
     # ---------------------------------------------------------------- end to end (public API)
     e2e = None
+    wk = [r for r in allr if r.get("worker")]
+    dev_ms_per_step = max(sum(r["rep_ms"]) / (len(r["rep_ms"]) * K) for r in wk)
     if not args.skip_e2e:
+        n_g = auto_steps_per_graph(tau, B)
+        chunk = n_g * max(1, min(int(1.0e9 // (n_g * B * row_bytes)), 64))
+        total = max(6 * n_g, int(1.2e3 / max(2.5 * dev_ms_per_step, 1e-3)))   # ~1.2 s at 2.5x the device time
+        total = min(total, 200000)
+        epochs = max(1, -(-total // chunk))
+        if epochs == 1:
+            chunk = -(-total // n_g) * n_g
+        rows = chunk * B
         if args.model == "higgs_mlp":
             x = torch.randn(rows, feat, generator=g)
         else:
             x = torch.randint(0, 256, (rows,) + tuple(in_shape), dtype=torch.uint8, generator=g)
         y = torch.randint(0, classes, (rows,), generator=g).to(torch.int32)
-        # SPMD data loading: every rank holds its own shard in pinned host memory
         ds = Dataset({"features": x, "label": y})
-        trainer.data_is_local_shard = True
-        trainer.bench_warmup_steps = W
-        trainer.set_num_epoch(K // chunk)
+        trainer.data_is_local_shard = True      # SPMD data loading: every rank holds its own shard (pinned host memory)
+        trainer.trace_windows = True            # per-replay device-time trace
+        trainer.set_num_epoch(epochs)
         trainer.train(ds)
-        stats = [s for s in trainer.fabric_stats if s.get("steps")]
-        e2e_ms = max(s["device_ms"] for s in stats)
-        steps = min(s["steps"] for s in stats)
-        e2e = {"value": n_workers * B * steps / (e2e_ms * 1e-3), "unit": "samples/s",
-               "ms_per_step": e2e_ms / steps, "steps": steps,
-               "h2d_bytes_per_step": int(sum(s["h2d_bytes"] for s in stats) / steps),
-               "d2h_bytes_per_step": int(sum(s["d2h_bytes"] for s in stats) / steps),
+        per_rank = []
+        for st in trainer.fabric_stats:
+            tr = st.get("trace_ms") if st else None
+            if not tr:
+                continue
+            skip, seen = 0, 0
+            while skip < len(tr) - 1 and (seen < W or skip < 2):   # warm-up: >= W steps and both staging parities
+                seen += tr[skip][1]
+                skip += 1
+            ms = sum(t for t, _ in tr[skip:])
+            steps = sum(n for _, n in tr[skip:])
+            per_rank.append((ms / steps, steps, st["h2d_bytes"] / st["steps"], st["d2h_bytes"] / st["steps"]))
+        e2e_ms = max(p[0] for p in per_rank)
+        e2e = {"value": n_workers * B / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+               "steps": K, "timed_steps_per_rank": min(p[1] for p in per_rank),
+               "per_rank_ms_per_step": [round(p[0], 6) for p in per_rank],
+               "h2d_bytes_per_step": int(sum(p[2] for p in per_rank)), "d2h_bytes_per_step": int(sum(p[3] for p in per_rank)),
+               "steps_per_graph_replay": n_g,
                "api": f"distkeras_b200.trainers.{TrainerCls.__name__}(...).train(dataset)",
                "num_updates": int(trainer.fabric_num_updates)}
 
-    staged_mib = 2 * tau * B * feat * (4 if args.model == "higgs_mlp" else 1) / 2**20
-    l2_policy = (f"kernel-only: inputs larger than L2 -- every step reads a different mini-batch out of {staged_mib:.0f} MiB "
-                 "of device staging (2 x window of distinct batches, cycled; L2 is 126 MB), no explicit flush; weights "
-                 "stay L2-resident as in real training" if staged_mib > 126 else
-                 f"kernel-only: staged inputs are only {staged_mib:.0f} MiB (< 126 MB L2) for this model/batch -- "
-                 "L2-resident inputs, no flush") + "; e2e: inputs streamed from pinned host memory every step"
     if rank == 0:
-        value = n_workers * B * K / (ms_dev * 1e-3)
+        per_rank_ms = [sum(r["rep_ms"]) / (len(r["rep_ms"]) * K) for r in wk]
+        slow = max(wk, key=lambda r: sum(r["rep_ms"]))
+        ms_per_step = sum(slow["rep_ms"]) / (len(slow["rep_ms"]) * K)
+        value = n_workers * B / (ms_per_step * 1e-3)
+        x_us = max(r["exchange_us"] for r in wk)
+        P = wk[0]["params"]
+        ex_per_rep = slow["exchanges"] / max(1, len(slow["rep_ms"]))
+        gbs = 4.0 * P / (x_us * 1e-6) / 1e9
+        l2_policy = ("inputs L2-sized or smaller (%.1f MiB staged): L2 flushed (252 MiB scrub write) before every timed "
+                     "K-step region, each region timed by its own event pair" % (staged_bytes / 2**20)) if flush else (
+                     "inputs larger than L2 (%.0f MiB staged, cycled): every step reads a different mini-batch, no explicit "
+                     "flush; weights stay L2-resident as in real training" % (staged_bytes / 2**20))
         out = {
             "metric": f"{args.model} {args.algo.upper()} training throughput (samples/s, whole job)",
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": value / BASELINE[args.algo] if args.algo in BASELINE else None,
-            "dtype": "bf16", "data": "synthetic", "impl": "native",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "native",
             "config": {"model": args.model, "trainer": TrainerCls.__name__, "global_batch": n_workers * B,
                        "batch_per_worker": B, "seq_len": None, "num_workers": n_workers,
                        "communication_window": tau, "worker_optimizer": args.optimizer,
-                       "parallelism": f"async-ps(center on gpu0, {'dedicated' if args.dedicated_ps and world > 1 else 'colocated'})"
-                                      f"+dp{n_workers}",
-                       "ps_transport": f"in-kernel NVLink P2P atomics ({args.comm})",
-                       "l2_policy": l2_policy},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "numa_node_rank0": numa_node,
+                       "parallelism": f"async-ps(center on gpu0, {'dedicated' if dedicated else 'colocated'}"
+                                      f"{', sharded' if args.sharded_ps else ''})+dp{n_workers}",
+                       "ps_transport": f"in-kernel NVLink P2P atomics ({comm})",
+                       "l2_policy": l2_policy + "; e2e: inputs streamed from pinned host memory every step"},
+            "timing": {"regions": slow["R"], "steps_per_region": K, "region_ms_mean": ms_per_step * K,
+                       "region_ms_median": statistics.median(slow["rep_ms"]), "region_ms_min": min(slow["rep_ms"]),
+                       "region_ms_max": max(slow["rep_ms"]), "exchanges_per_rank": slow["exchanges"],
+                       "exchanges_per_region": ex_per_rep, "graphs": period},
+            "per_rank_ms_per_step": [round(v, 6) for v in per_rank_ms],
+            "exchange_us": x_us, "exchange_kernels": wk[0]["exchange_kernels"],
+            "ps_gbs": {"push": gbs, "pull": gbs, "bytes_each_way": 4 * P, "vs_900": gbs / 900.0, "vs_measured_770": gbs / 770.0,
+                       "note": "per worker, all ranks exchanging at once; one fused kernel moves 4P bytes each way"},
+            "comm_fraction": ex_per_rep * x_us * 1e-3 / (ms_per_step * K),
+            "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(sum(r["launches"] for r in wk)),
+            "kernels_per_step": wk[0]["kernels_per_step"],
+            "published_reference": PUBLISHED.get(args.algo), "numa_node_rank0": numa_node,
         }
         print(json.dumps(out, default=lambda o: o.item() if hasattr(o, 'item') else str(o)))
     if dist:

@@ -70,22 +70,51 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = o;
 }
 
-// Generic flat traversal: each thread handles kPsUnroll float4 per grid-stride step (all loads
-// issued before any use so several 16-byte NVLink requests are in flight per thread), then a
-// scalar tail.  F has: float4 load phase / compute+store phase expressed through two functors.
-template <typename VecOp, typename ScalarOp>
-__device__ __forceinline__ void flat_for_each(long n, VecOp vec_op, ScalarOp scalar_op) {
+// Flat traversal in three phases per thread: kPsUnroll float4 slots each.  Phase 0 issues every local
+// load (prep), phase 1 issues every remote operation (NVLink load / atomic) and only phase 2 consumes
+// the results, so a thread keeps kPsUnroll independent 16-byte NVLink requests in flight instead of
+// serialising kPsUnroll round trips (a 1 M-parameter exchange is latency-bound: 4 MB is ~4.4 us at link
+// rate, one round trip is ~2 us).  A scalar tail covers n % 4.
+struct NoRegs {};
+
+template <typename Prep, typename Issue, typename Finish, typename ScalarOp>
+__device__ __forceinline__ void flat_pipeline(long n, Prep prep, Issue issue, Finish finish, ScalarOp scalar_op) {
   const long n4 = n >> 2;
-  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
-  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride)
-    vec_op(i << 2);
+  const long tile = static_cast<long>(blockDim.x) * kPsUnroll;
+  for (long base = static_cast<long>(blockIdx.x) * tile + threadIdx.x; base < n4;
+       base += static_cast<long>(gridDim.x) * tile) {
+    decltype(prep(0L)) a[kPsUnroll];
+    decltype(issue(0L, a[0])) b[kPsUnroll];
+#pragma unroll
+    for (int u = 0; u < kPsUnroll; ++u) {
+      const long i = base + static_cast<long>(u) * blockDim.x;
+      if (i < n4) a[u] = prep(i << 2);
+    }
+#pragma unroll
+    for (int u = 0; u < kPsUnroll; ++u) {
+      const long i = base + static_cast<long>(u) * blockDim.x;
+      if (i < n4) b[u] = issue(i << 2, a[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kPsUnroll; ++u) {
+      const long i = base + static_cast<long>(u) * blockDim.x;
+      if (i < n4) finish(i << 2, a[u], b[u]);
+    }
+  }
   const long tail0 = n4 << 2;
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
   for (long i = tail0 + static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     scalar_op(i);
 }
 
 __device__ __forceinline__ float load_scale(const float* scale_dev, float scale) {
   return scale_dev != nullptr ? scale * __ldg(scale_dev) : scale;
+}
+
+__device__ __forceinline__ float4 residual4(const float* w, const float* w1, long i, float s) {
+  const float4 a = *reinterpret_cast<const float4*>(w + i);
+  const float4 b = *reinterpret_cast<const float4*>(w1 + i);
+  return make_float4((a.x - b.x) * s, (a.y - b.y) * s, (a.z - b.z) * s, (a.w - b.w) * s);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -95,14 +124,13 @@ ps_commit_kernel(float* __restrict__ center, const float* __restrict__ w, const 
                  unsigned iteration) {
   DK_PDL_ENTER();
   const float s = load_scale(scale_dev, scale);
-  flat_for_each(
-      n,
-      [&](long i) {
-        const float4 a = *reinterpret_cast<const float4*>(w + i);
-        const float4 b = *reinterpret_cast<const float4*>(w1 + i);
-        red_add_v4_sys(center + i,
-                       make_float4((a.x - b.x) * s, (a.y - b.y) * s, (a.z - b.z) * s, (a.w - b.w) * s));
+  flat_pipeline(
+      n, [&](long i) { return residual4(w, w1, i, s); },
+      [&](long i, const float4& r) {
+        red_add_v4_sys(center + i, r);
+        return NoRegs{};
       },
+      [&](long, const float4&, const NoRegs&) {},
       [&](long i) { red_add_sys(center + i, (w[i] - w1[i]) * s); });
   if (ctrl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
     if (scale_dev == nullptr)  // DynSGD already bumped the counter in its ticket kernel
@@ -115,10 +143,9 @@ __global__ void __launch_bounds__(kPsThreads)
 ps_pull_kernel(const float* __restrict__ center, float* __restrict__ w, float* __restrict__ w1,
                __nv_bfloat16* __restrict__ wb, long n, const unsigned* ctrl, unsigned* last_update) {
   DK_PDL_ENTER();
-  flat_for_each(
-      n,
-      [&](long i) {
-        const float4 c = ld_sys_v4(center + i);
+  flat_pipeline(
+      n, [&](long) { return NoRegs{}; }, [&](long i, const NoRegs&) { return ld_sys_v4(center + i); },
+      [&](long i, const NoRegs&, const float4& c) {
         *reinterpret_cast<float4*>(w + i) = c;
         if (w1 != nullptr) *reinterpret_cast<float4*>(w1 + i) = c;
         if (wb != nullptr) st_bf16x4(wb + i, c);
@@ -144,13 +171,10 @@ ps_exchange_kernel(float* __restrict__ center, float* __restrict__ w, float* __r
                    unsigned iteration, unsigned* last_update) {
   DK_PDL_ENTER();
   const float s = load_scale(scale_dev, scale);
-  flat_for_each(
-      n,
-      [&](long i) {
-        const float4 a = *reinterpret_cast<const float4*>(w + i);
-        const float4 b = *reinterpret_cast<const float4*>(w1 + i);
-        const float4 r = make_float4((a.x - b.x) * s, (a.y - b.y) * s, (a.z - b.z) * s, (a.w - b.w) * s);
-        const float4 o = atom_add_v4_sys(center + i, r);
+  flat_pipeline(
+      n, [&](long i) { return residual4(w, w1, i, s); },
+      [&](long i, const float4& r) { return atom_add_v4_sys(center + i, r); },
+      [&](long i, const float4& r, const float4& o) {
         const float4 c = make_float4(o.x + r.x, o.y + r.y, o.z + r.z, o.w + r.w);
         *reinterpret_cast<float4*>(w + i) = c;
         *reinterpret_cast<float4*>(w1 + i) = c;
@@ -179,11 +203,11 @@ __global__ void __launch_bounds__(kPsThreads)
 ps_elastic_kernel(float* __restrict__ center, float* __restrict__ w, __nv_bfloat16* __restrict__ wb,
                   long n, float alpha, unsigned* ctrl, int worker, unsigned iteration) {
   DK_PDL_ENTER();
-  flat_for_each(
-      n,
-      [&](long i) {
-        const float4 c = ld_sys_v4(center + i);
-        float4 x = *reinterpret_cast<const float4*>(w + i);
+  flat_pipeline(
+      n, [&](long i) { return *reinterpret_cast<const float4*>(w + i); },
+      [&](long i, const float4&) { return ld_sys_v4(center + i); },
+      [&](long i, const float4& x0, const float4& c) {
+        float4 x = x0;
         const float4 e = make_float4(alpha * (x.x - c.x), alpha * (x.y - c.y), alpha * (x.z - c.z),
                                      alpha * (x.w - c.w));
         x.x -= e.x; x.y -= e.y; x.z -= e.z; x.w -= e.w;
@@ -206,18 +230,29 @@ ps_elastic_kernel(float* __restrict__ center, float* __restrict__ w, __nv_bfloat
 }
 
 // Experimental PS: per-element staleness damping, then the worker adopts the new center.
+struct Float4x2 {
+  float4 a, b;
+};
+
 __global__ void __launch_bounds__(kPsThreads)
 ps_damped_exchange_kernel(float* __restrict__ center, float* __restrict__ w, float* __restrict__ w1,
                           __nv_bfloat16* __restrict__ wb, long n, float scale, float inv_lr,
                           unsigned* ctrl, int worker, unsigned iteration) {
   DK_PDL_ENTER();
   // w1 doubles as the stale center variable (the worker's last pulled copy, workers.py:553-563).
-  flat_for_each(
+  // Two NVLink round trips per element are inherent here (the damping needs the CURRENT center before
+  // the update can be formed); the kPsUnroll slots of a thread overlap theirs.
+  flat_pipeline(
       n,
       [&](long i) {
-        const float4 c = ld_sys_v4(center + i);
-        const float4 a = *reinterpret_cast<const float4*>(w + i);
-        const float4 b = *reinterpret_cast<const float4*>(w1 + i);
+        Float4x2 t;
+        t.a = *reinterpret_cast<const float4*>(w + i);
+        t.b = *reinterpret_cast<const float4*>(w1 + i);
+        return t;
+      },
+      [&](long i, const Float4x2&) { return ld_sys_v4(center + i); },
+      [&](long i, const Float4x2& t, const float4& c) {
+        const float4 a = t.a, b = t.b;
         float4 r = make_float4((a.x - b.x) * scale, (a.y - b.y) * scale, (a.z - b.z) * scale,
                                (a.w - b.w) * scale);
         const float dx = c.x - b.x, dy = c.y - b.y, dz = c.z - b.z, dw = c.w - b.w;
@@ -302,17 +337,20 @@ __global__ void __launch_bounds__(kPsThreads)
 ps_average_kernel(PeerPtrs peers, int num_peers, long lo, long hi, float inv) {
   DK_PDL_ENTER();
   const long n = hi - lo;
-  flat_for_each(
-      n,
-      [&](long i) {
+  flat_pipeline(
+      n, [&](long) { return NoRegs{}; },
+      [&](long i, const NoRegs&) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
+#pragma unroll 4
         for (int r = 0; r < num_peers; ++r) {
           const float4 v = ld_sys_v4(peers.p[r] + lo + i);
           acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-#pragma unroll 1
+        return acc;
+      },
+      [&](long i, const NoRegs&, const float4& sum) {
+        const float4 acc = make_float4(sum.x * inv, sum.y * inv, sum.z * inv, sum.w * inv);
+#pragma unroll 4
         for (int r = 0; r < num_peers; ++r) *reinterpret_cast<float4*>(peers.p[r] + lo + i) = acc;
       },
       [&](long i) {
@@ -327,8 +365,9 @@ ps_average_kernel(PeerPtrs peers, int num_peers, long lo, long hi, float inv) {
 __global__ void __launch_bounds__(kPsThreads)
 ps_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, long n) {
   DK_PDL_ENTER();
-  flat_for_each(
-      n, [&](long i) { *reinterpret_cast<float4*>(dst + i) = ld_sys_v4(src + i); },
+  flat_pipeline(
+      n, [&](long) { return NoRegs{}; }, [&](long i, const NoRegs&) { return ld_sys_v4(src + i); },
+      [&](long i, const NoRegs&, const float4& v) { *reinterpret_cast<float4*>(dst + i) = v; },
       [&](long i) { dst[i] = ld_sys(src + i); });
 }
 

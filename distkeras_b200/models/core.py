@@ -797,7 +797,7 @@ def model_from_json(text: str) -> Sequential:
 
 def load_model(path: str) -> Sequential:
     """Inverse of :meth:`Sequential.save` (re-compiles with the stored loss / optimizer when present)."""
-    d = torch.load(path, weights_only=False)
+    d = torch.load(path, weights_only=True)  # str / dict / tensor payload only: no arbitrary unpickling
     m = model_from_json(d["model"])
     m.build()
     m.set_flat_weights(d["flat"])

@@ -4,15 +4,16 @@ Capability parity with ``distkeras/networking.py``: ``determine_host_address``, 
 ``recv_data``, ``send_data``, ``connect``.  The reference frames every message as a 20-byte
 zero-padded ASCII length + a pickle (``networking.py:42-86``) and re-allocates the receive
 buffer on every chunk.  Here a message is an 16-byte binary header (magic, payload length) followed
-by a msgpack-free, copy-free encoding: a small pickled metadata dict plus the raw bytes of every
-tensor, received straight into a preallocated ``bytearray`` with ``recv_into``.
+by a copy-free encoding: a small JSON metadata document plus the raw bytes of every
+tensor, received straight into a preallocated ``bytearray`` with ``recv_into``.  The metadata is JSON (dtype /
+shape / scalars only), never a pickle: a peer that can reach the port cannot make the server execute code.
 
 On the GPU path none of this is used: commits and pulls are loads / atomics issued from CUDA
 kernels over NVLink (``csrc/ps_kernels.cu``).
 """
 from __future__ import annotations
 
-import pickle
+import json
 import socket
 import struct
 from typing import Any
@@ -53,9 +54,15 @@ def _encode(data: Any):
         if isinstance(obj, np.ndarray):
             flat = np.ascontiguousarray(obj).reshape(-1)  # (ascontiguousarray alone would turn 0-d into 1-d)
             buffers.append(memoryview(flat.view(np.uint8)))
-            return {"__nd__": len(buffers) - 1, "dtype": flat.dtype.str, "shape": tuple(obj.shape)}
+            return {"__nd__": len(buffers) - 1, "dtype": flat.dtype.str, "shape": list(obj.shape)}
         if isinstance(obj, dict):
-            return {k: walk(v) for k, v in obj.items()}
+            return {"__map__": [[walk(k), walk(v)] for k, v in obj.items()]}
+        if isinstance(obj, tuple):
+            return {"__tuple__": [walk(v) for v in obj]}
+        if isinstance(obj, (np.integer, np.floating, np.bool_)):
+            return obj.item()
+        if isinstance(obj, bytes):
+            return {"__bytes__": obj.hex()}
         if isinstance(obj, (list, tuple)):
             return [walk(v) for v in obj]
         try:
@@ -70,13 +77,26 @@ def _encode(data: Any):
     return walk(data), buffers
 
 
+def _hashable(k):
+    return tuple(_hashable(x) for x in k) if isinstance(k, list) else k
+
+
 def _decode(meta: Any, raw: memoryview, offsets):
     def walk(obj):
         if isinstance(obj, dict):
             if "__nd__" in obj:
                 lo, hi = offsets[obj["__nd__"]]
-                return np.frombuffer(raw[lo:hi], dtype=np.dtype(obj["dtype"])).reshape(obj["shape"])
-            return {k: walk(v) for k, v in obj.items()}
+                dt = np.dtype(obj["dtype"])
+                if dt.hasobject:
+                    raise ConnectionError("object arrays are not accepted on the wire")
+                return np.frombuffer(raw[lo:hi], dtype=dt).reshape(tuple(obj["shape"]))
+            if "__map__" in obj:
+                return {_hashable(walk(k)): walk(v) for k, v in obj["__map__"]}
+            if "__tuple__" in obj:
+                return tuple(walk(v) for v in obj["__tuple__"])
+            if "__bytes__" in obj:
+                return bytes.fromhex(obj["__bytes__"])
+            raise ConnectionError("malformed frame metadata")
         if isinstance(obj, list):
             return [walk(v) for v in obj]
         return obj
@@ -88,7 +108,7 @@ def send_data(connection: socket.socket, data: Any) -> None:
     """Send one framed message (``networking.py:65-86``)."""
     meta, buffers = _encode(data)
     sizes = [len(b) for b in buffers]
-    meta_bytes = pickle.dumps({"meta": meta, "sizes": sizes}, -1)
+    meta_bytes = json.dumps({"meta": meta, "sizes": sizes}, allow_nan=True).encode("utf-8")
     connection.sendall(_HEADER.pack(_MAGIC, len(meta_bytes), sum(sizes)))
     connection.sendall(meta_bytes)
     for b in buffers:
@@ -100,7 +120,7 @@ def recv_data(connection: socket.socket) -> Any:
     magic, meta_len, raw_len = _HEADER.unpack(bytes(recvall(connection, _HEADER.size)))
     if magic != _MAGIC:
         raise ConnectionError("bad frame magic")
-    info = pickle.loads(bytes(recvall(connection, meta_len)))
+    info = json.loads(bytes(recvall(connection, meta_len)).decode("utf-8"))
     raw = memoryview(recvall(connection, raw_len)) if raw_len else memoryview(b"")
     offsets, pos = [], 0
     for s in info["sizes"]:

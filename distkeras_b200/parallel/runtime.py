@@ -51,11 +51,22 @@ def _free_port() -> int:
 # fabric worker
 # ================================================================================================
 class FabricWorker:
-    """One worker replica driven by per-window CUDA graphs."""
+    """One worker replica driven by CUDA graphs of whole training *regions*.
+
+    A graph holds ``n`` consecutive training steps (``n`` = ``windows_per_graph * tau`` for training; any
+    ``n`` for benchmarking) together with every window-boundary exchange that falls inside them, so
+    the host touches the device once per ``n`` steps: one DMA of ``n`` mini-batches from pinned memory,
+    one graph replay, one D2H node with the region's loss / accuracy records.  Small mini-batches (the
+    reference trains at 4-64 rows, ``examples/mnist_analysis.ipynb:387``) pack several communication
+    windows into one graph so the per-replay host cost is amortised.  Graphs are cached by
+    ``(parity, n, phase)``: ``parity`` selects the staging buffers, ``phase`` is the position of the
+    region's first step inside its communication window.
+    """
 
     def __init__(self, model, optimizer, loss: str, algorithm: dict, region: FabricRegion, worker_id: int,
                  batch_size: int, device_index: int, in_dtype: str, input_affine=(1.0, 0.0), comm: str = "exchange",
-                 strict: bool = False, dense_labels: bool = False, seed: int = 0):
+                 strict: bool = False, dense_labels: bool = False, seed: int = 0, steps_per_graph: Optional[int] = None,
+                 trace: bool = False):
         self.alg = dict(algorithm)
         self.tau = int(self.alg["window"])
         self.region = region
@@ -68,13 +79,14 @@ class FabricWorker:
         self.comm = "commit_pull" if strict else comm
         self.strict = strict
         self.device_index = device_index
-        # Fused pull: every M-tile row of the first GEMM fetches the weight tiles itself (peer memory
-        # bypasses the local L2), so it pays off while the batch spans few 128-row tiles; larger
-        # batches use the fused exchange kernel (cluster-multicast of the weight tile is the next step).
-        self.fused_pull = (comm == "fused_pull" and not strict and self.alg["kind"] in ("adag", "dynsgd")
-                           and int(batch_size) <= 512)
+        if steps_per_graph is None:
+            # ~8k rows per replay: 1 window per graph at large batches, several at the reference's
+            g = max(1, min(64, -(-8192 // (self.tau * self.B))))
+            steps_per_graph = g * self.tau
+        self.n_max = int(steps_per_graph)
+        self.fused_pull = (comm == "fused_pull" and not strict and self.alg["kind"] in ("adag", "dynsgd"))
         self.rep = NativeReplica(model, optimizer, loss, batch_size, device_index, in_dtype=in_dtype,
-                                 input_affine=input_affine, hist_slots=2 * self.tau, dense_labels=dense_labels,
+                                 input_affine=input_affine, hist_slots=2 * self.n_max, dense_labels=dense_labels,
                                  seed=seed + 7 * worker_id,
                                  pull_center_ptr=region.center_ptr if self.fused_pull else 0)
         if self.fused_pull and self.rep.L_step_pull < 0:
@@ -83,6 +95,7 @@ class FabricWorker:
             self.comm = "exchange"
         rep = self.rep
         dev = rep.device
+        dense_labels = rep.dense_labels  # the replica decides (mse on a linear head needs dense targets)
         self.lib = rep.lib
         self.F = rep._input_feats
         rep.ensure_snapshot()
@@ -92,26 +105,35 @@ class FabricWorker:
         if self.alg["kind"] == "eamsgd":
             self.mom = torch.zeros(rep.P, dtype=torch.float32, device=dev)
             self.wcopy = torch.zeros(rep.P, dtype=torch.float32, device=dev)
-        # double-buffered window staging
-        self.x_stage = [torch.zeros(self.tau * self.B, self.F, dtype=rep.in_torch_dtype, device=dev) for _ in (0, 1)]
+        # double-buffered region staging
+        n = self.n_max
+        self.x_stage = [torch.zeros(n * self.B, self.F, dtype=rep.in_torch_dtype, device=dev) for _ in (0, 1)]
         if dense_labels:
-            self.y_stage = [torch.zeros(self.tau * self.B, rep.num_classes, dtype=torch.float32, device=dev)
-                            for _ in (0, 1)]
+            self.y_stage = [torch.zeros(n * self.B, rep.num_classes, dtype=torch.float32, device=dev) for _ in (0, 1)]
         else:
-            self.y_stage = [torch.zeros(self.tau * self.B, dtype=torch.int32, device=dev) for _ in (0, 1)]
-        self.hist_host = [torch.zeros(self.tau, 2, dtype=torch.float32).pin_memory() for _ in (0, 1)]
+            self.y_stage = [torch.zeros(n * self.B, dtype=torch.int32, device=dev) for _ in (0, 1)]
+        self.hist_host = [torch.zeros(n, 2, dtype=torch.float32).pin_memory() for _ in (0, 1)]
         self.compute = torch.cuda.Stream(device=dev)
         self.copy = torch.cuda.Stream(device=dev)
         self.copied = [torch.cuda.Event() for _ in (0, 1)]
         self.done = [torch.cuda.Event() for _ in (0, 1)]
-        self.graphs: List[Optional[torch.cuda.CUDAGraph]] = [None, None]
-        self.kernels_per_window = 0
-        self.windows_run = 0
+        self._graphs: dict = {}          # (parity, n, phase) -> CUDAGraph
+        self._graph_kernels: dict = {}   # (parity, n, phase) -> kernel launches per replay
+        self._graph_exchanges: dict = {}
+        self.kernels_per_window = 0      # launches of one full window (tau steps + its exchange)
+        self.kernels_per_step = 0
+        self.launched = 0                # kernels launched through graph replays so far
+        self.exchanges = 0
+        self.windows_run = 0             # communication windows completed (graph replays * windows per graph)
+        self.replays = 0
         self.history: List[dict] = []
         self.iteration = 0
-        self._pending: List[Optional[int]] = [None, None]  # first iteration of the window in flight per parity
+        self._pending: List[Optional[tuple]] = [None, None]  # (first iteration, n) of the region in flight per parity
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.trace = bool(trace)
+        self.trace_events: List[tuple] = []   # (event after replay, steps in it) -- device-time trace
+        self._warm = False
 
     # -- device program pieces -------------------------------------------------------------------
     def _stream(self):
@@ -120,23 +142,29 @@ class FabricWorker:
     def set_shards(self, shards) -> None:
         self.shards = list(shards)
 
-    def _comm_ops(self) -> None:
-        """Enqueue the window-boundary communication of the algorithm on the current stream."""
+    def _comm_ops(self) -> int:
+        """Enqueue the window-boundary communication of the algorithm on the current stream; returns
+        the number of kernels launched."""
         reg, lib = self.region, self.lib
         ctrl = C.c_void_p(reg.ctrl_ptr)
         st = self._stream()
+        k = 0
         if self.strict:
             N.check(lib.dk_ps_lock_acquire(ctrl, self.ticket.data_ptr(), st), "lock_acquire")
+            k += 1
         if self.alg["kind"] == "dynsgd":
             N.check(lib.dk_ps_ticket(ctrl, self.last_update.data_ptr(), self.scale_dev.data_ptr(), st), "ticket")
+            k += 1
         shards = self.shards or [(0, self.rep.P, reg.center_ptr)]
         for i, (lo, hi, cptr) in enumerate(shards):
             # the control block (update counter, heartbeat) is bumped once per commit: by shard 0
-            self._comm_range(lo, hi, cptr, ctrl if i == 0 else None, st)
+            k += self._comm_range(lo, hi, cptr, ctrl if i == 0 else None, st)
         if self.strict:
             N.check(lib.dk_ps_lock_release(ctrl, self.ticket.data_ptr(), st), "lock_release")
+            k += 1
+        return k
 
-    def _comm_range(self, lo: int, hi: int, center_ptr: int, ctrl, st) -> None:
+    def _comm_range(self, lo: int, hi: int, center_ptr: int, ctrl, st) -> int:
         rep, lib, k = self.rep, self.lib, self.alg["kind"]
         n = hi - lo
         c = C.c_void_p(center_ptr)
@@ -149,73 +177,78 @@ class FabricWorker:
             if self.fused_pull:
                 # commit only: the pull happens inside the next window's first forward GEMM
                 N.check(lib.dk_ps_commit(c, W, W1, n, scale, sdev, ctrl, self.worker_id, it, st), "commit")
-            elif self.comm == "exchange":
+                return 1
+            if self.comm == "exchange":
                 N.check(lib.dk_ps_exchange(c, W, W1, Wb, n, scale, sdev, ctrl, self.worker_id, it, lu, st), "exchange")
-            else:
-                N.check(lib.dk_ps_commit(c, W, W1, n, scale, sdev, ctrl, self.worker_id, it, st), "commit")
-                N.check(lib.dk_ps_pull(c, W, W1, Wb, n, ctrl, lu, st), "pull")
-        elif k in ("aeasgd", "eamsgd"):
+                return 1
+            N.check(lib.dk_ps_commit(c, W, W1, n, scale, sdev, ctrl, self.worker_id, it, st), "commit")
+            N.check(lib.dk_ps_pull(c, W, W1, Wb, n, ctrl, lu, st), "pull")
+            return 2
+        if k in ("aeasgd", "eamsgd"):
             N.check(lib.dk_ps_elastic(c, W, Wb, n, float(self.alg["alpha"]), ctrl, self.worker_id, it, st), "elastic")
-        elif k == "experimental":
+            return 1
+        if k == "experimental":
             N.check(lib.dk_ps_damped_exchange(c, W, W1, Wb, n, 1.0 / self.tau, float(self.alg["inv_lr"]), ctrl,
                                               self.worker_id, it, st), "damped_exchange")
-        else:
-            raise ValueError(f"unknown algorithm {k!r}")
+            return 1
+        raise ValueError(f"unknown algorithm {k!r}")
 
-    def comm_kernels(self) -> int:
-        k = self.alg["kind"]
-        nshards = len(self.shards) if self.shards else 1
-        if nshards > 1:
-            per = 1 if (self.comm == "exchange" or k in ("aeasgd", "eamsgd", "experimental")) else 2
-            return nshards * per + (1 if k == "dynsgd" else 0) + (2 if self.strict else 0)
-        if self.fused_pull:
-            return 1 + len(self.rep.pull_rest_ranges()) + (1 if k == "dynsgd" else 0)
-        n = 1 if (self.comm == "exchange" or k in ("aeasgd", "eamsgd", "experimental")) else 2
-        if k == "dynsgd":
-            n += 1
-        if self.strict:
-            n += 2
-        return n
-
-    def _pull_rest(self) -> None:
+    def _pull_rest(self) -> int:
         """Pull every segment the fused-pull GEMM does not cover (biases, later layers)."""
         rep, reg = self.rep, self.region
-        for lo, hi in rep.pull_rest_ranges():
+        ranges = rep.pull_rest_ranges()
+        for lo, hi in ranges:
             N.check(self.lib.dk_ps_pull(C.c_void_p(reg.center_ptr + 4 * lo), rep.W.data_ptr() + 4 * lo,
                                         rep.W1.data_ptr() + 4 * lo, rep.Wb.data_ptr() + 2 * lo, hi - lo,
                                         C.c_void_p(reg.ctrl_ptr), self.last_update.data_ptr(), self._stream()),
                     "pull_rest")
+        return len(ranges)
 
-    def _step(self, parity: int, j: int, fused_pull: bool = False) -> None:
+    def _step(self, parity: int, j: int, fused_pull: bool = False) -> int:
         rep = self.rep
         xs, ys = self.x_stage[parity], self.y_stage[parity]
         x_ptr = xs.data_ptr() + j * self.B * self.F * xs.element_size()
         y_ptr = ys.data_ptr() + j * self.B * (ys.shape[1] if ys.dim() == 2 else 1) * ys.element_size()
+        before = rep.launches()
+        extra = 0
         if self.alg["kind"] == "eamsgd":
             N.check(self.lib.dk_eamsgd_pre(rep.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(),
                                            rep.Wb.data_ptr(), rep.P, float(self.alg["momentum"]), self._stream()),
                     "eamsgd_pre")
+            extra += 1
         rep.enqueue_step(x_ptr, y_ptr, fused_pull=fused_pull)
         if self.alg["kind"] == "eamsgd":
             N.check(self.lib.dk_eamsgd_post(rep.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(),
                                             rep.Wb.data_ptr(), rep.P, float(self.alg["eta"]), self._stream()),
                     "eamsgd_post")
+            extra += 1
+        return rep.launches() - before + extra
 
-    def _window_program(self, parity: int) -> None:
-        """tau steps + the algorithm's communication, in reference order."""
-        rep = self.rep
-        half = rep.hist[parity * self.tau:(parity + 1) * self.tau]
-        half.zero_()
-        pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd")  # check happens before the batch
-        if self.fused_pull:
-            self._pull_rest()
-        for j in range(self.tau):
-            if pre_batch and j == self.tau - 1:
-                self._comm_ops()
-            self._step(parity, j, fused_pull=self.fused_pull and j == 0)
-        if not pre_batch:
-            self._comm_ops()
-        self.hist_host[parity].copy_(half, non_blocking=True)
+    def _region_program(self, parity: int, n: int, phase: int) -> tuple:
+        """``n`` steps starting ``phase`` steps into a communication window, with the algorithm's
+        exchange wherever an iteration count hits a multiple of ``tau`` -- in reference order
+        (ADAG / DynSGD / Experimental check after the batch, DOWNPOUR / AEASGD / EAMSGD
+        before it).  Returns (kernel launches, exchanges)."""
+        rep, tau = self.rep, self.tau
+        seg = rep.hist[parity * self.n_max:parity * self.n_max + n]
+        seg.zero_()
+        pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd")
+        kernels = exchanges = 0
+        for j in range(n):
+            it = phase + j + 1                      # iteration number relative to the last window boundary
+            boundary = it % tau == 0
+            first_of_window = (phase + j) % tau == 0
+            if self.fused_pull and first_of_window:
+                kernels += self._pull_rest()
+            if pre_batch and boundary:
+                kernels += self._comm_ops()
+                exchanges += 1
+            kernels += self._step(parity, j, fused_pull=self.fused_pull and first_of_window)
+            if not pre_batch and boundary:
+                kernels += self._comm_ops()
+                exchanges += 1
+        self.hist_host[parity][:n].copy_(seg, non_blocking=True)
+        return kernels, exchanges
 
     def initial_pull(self) -> None:
         """``pull(); set_weights(center)`` before the first batch (``workers.py:286-288``)."""
@@ -228,20 +261,15 @@ class FabricWorker:
                                             self.last_update.data_ptr(), self._stream()), "pull")
         self.compute.synchronize()
 
-    def capture(self) -> None:
-        """Warm every kernel once (lazy module load) on scratch state, then capture both parities."""
+    def _warm_up(self) -> None:
+        """Run every kernel of a step once (lazy module load) on scratch state and restore it."""
         rep = self.rep
         torch.cuda.synchronize(rep.device)
         saved = (rep.W.clone(), rep.W1.clone(), rep.step_counter.clone(),
                  None if rep.opt.s0 is None else rep.opt.s0.clone(), None if rep.opt.s1 is None else rep.opt.s1.clone())
-        launches0 = rep.launches()
         with torch.cuda.stream(self.compute):
-            self._step(0, 0)
+            self.kernels_per_step = self._step(0, 0)
         self.compute.synchronize()
-        per_step = rep.launches() - launches0
-        extra = 2 if self.alg["kind"] == "eamsgd" else 0
-        self.kernels_per_window = self.tau * (per_step + extra) + self.comm_kernels()
-        # restore the state touched by the warm-up step
         rep.W.copy_(saved[0]); rep.W1.copy_(saved[1]); rep.step_counter.copy_(saved[2])
         if saved[3] is not None:
             rep.opt.s0.copy_(saved[3])
@@ -252,53 +280,117 @@ class FabricWorker:
         rep.refresh_shadow()
         rep.hist.zero_()
         torch.cuda.synchronize(rep.device)
-        for parity in (0, 1):
+        self._warm = True
+
+    def graph(self, parity: int, n: int, phase: int = 0) -> torch.cuda.CUDAGraph:
+        """The (cached) CUDA graph of an ``n``-step region; captured on first use."""
+        key = (parity, n, phase % self.tau)
+        g = self._graphs.get(key)
+        if g is None:
+            if not self._warm:
+                self._warm_up()
+            if n > self.n_max:
+                raise ValueError(f"region of {n} steps exceeds the staging capacity ({self.n_max})")
+            torch.cuda.synchronize(self.rep.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.compute):
-                self._window_program(parity)
-            self.graphs[parity] = g
-        torch.cuda.synchronize(rep.device)
+                self._graph_kernels[key], self._graph_exchanges[key] = self._region_program(parity, n, key[2])
+            torch.cuda.synchronize(self.rep.device)
+            self._graphs[key] = g
+        return g
+
+    def replay(self, parity: int, n: int, phase: int = 0) -> None:
+        """Replay a region graph on the current stream (bookkeeping included)."""
+        key = (parity, n, phase % self.tau)
+        self.graph(*key).replay()
+        self.launched += self._graph_kernels[key]
+        self.exchanges += self._graph_exchanges[key]
+
+    def capture(self) -> None:
+        """Capture both parities of the full-size training graph ahead of time."""
+        for parity in (0, 1):
+            self.graph(parity, self.n_max, 0)
+        key = (0, self.n_max, 0)
+        wins = max(1, self._graph_exchanges[key])
+        self.kernels_per_window = self._graph_kernels[key] // wins if self.n_max % self.tau == 0 else 0
+
+    def comm_kernels(self) -> int:
+        """Kernels of one window-boundary exchange."""
+        return max(0, self.kernels_per_window - self.tau * self.kernels_per_step) if self.kernels_per_window else 0
 
     # -- host loop ----------------------------------------------------------------------------------
     def _collect(self, parity: int) -> None:
-        first = self._pending[parity]
-        if first is None:
+        pend = self._pending[parity]
+        if pend is None:
             return
+        first, n = pend
         self.done[parity].synchronize()
-        recs = self.hist_host[parity].numpy()
+        recs = self.hist_host[parity][:n].tolist()
         now = time.time()
-        for j in range(self.tau):
-            self.history.append({"history": [float(recs[j, 0]), float(recs[j, 1])], "worker_id": self.worker_id,
-                                 "iteration": first + j, "timestamp": now})
+        wid = self.worker_id
+        self.history.extend({"history": recs[j], "worker_id": wid, "iteration": first + j, "timestamp": now}
+                            for j in range(n))
         self._pending[parity] = None
 
-    def run_window(self, x_host: torch.Tensor, y_host: torch.Tensor) -> None:
-        """Train one window on ``tau * B`` rows of (pinned) host data.  Asynchronous: returns once the
-        H2D copies and the graph replay are enqueued; at most two windows are in flight."""
-        p = self.windows_run & 1
-        for it in range(self.iteration + 1, self.iteration + self.tau + 1):
+    def run_region(self, x_host: torch.Tensor, y_host: torch.Tensor, n: Optional[int] = None) -> None:
+        """Train ``n`` steps (a multiple of ``tau``, at most ``n_max``) on ``n * B`` rows of (pinned) host
+        data.  Asynchronous: returns once the H2D copies and the graph replay are enqueued; at most two
+        regions are in flight."""
+        n = self.n_max if n is None else int(n)
+        p = self.replays & 1
+        for it in range(self.iteration + 1, self.iteration + n + 1):
             fault_injection_point(self.worker_id, it)  # DK_FAULT test hook: fails BEFORE anything is enqueued
         if _NVTX:
-            torch.cuda.nvtx.range_push(f"dk.window[{self.windows_run}] w{self.worker_id}")
-        self._collect(p)  # window (n - 2) used this parity: wait for it, harvest its history
+            torch.cuda.nvtx.range_push(f"dk.region[{self.replays}] w{self.worker_id}")
+        self._collect(p)  # region (r - 2) used this parity: wait for it, harvest its history
         with torch.cuda.stream(self.copy):
-            self.x_stage[p].copy_(x_host.reshape(self.tau * self.B, -1), non_blocking=True)
-            self.y_stage[p].copy_(y_host, non_blocking=True)
+            self.x_stage[p][:n * self.B].copy_(x_host.reshape(n * self.B, -1), non_blocking=True)
+            self.y_stage[p][:n * self.B].copy_(y_host, non_blocking=True)
             self.copied[p].record(self.copy)
         self.h2d_bytes += x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()
         self.compute.wait_event(self.copied[p])
         with torch.cuda.stream(self.compute):
-            self.graphs[p].replay()
+            if n != self.n_max or self._misaligned:
+                self._realign(p)
+            self.replay(p, n, 0)
             self.done[p].record(self.compute)
-        self.d2h_bytes += self.tau * 8
-        self._pending[p] = self.iteration + 1
-        self.iteration += self.tau
-        self.windows_run += 1
+            if self.trace:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(self.compute)
+                self.trace_events.append((ev, n))
+        self._misaligned = n != self.n_max
+        self.d2h_bytes += n * 8
+        self._pending[p] = (self.iteration + 1, n)
+        self.iteration += n
+        self.windows_run += n // self.tau
+        self.replays += 1
         if _NVTX:
             torch.cuda.nvtx.range_pop()
 
+    run_window = run_region  # one-window-per-graph name kept for callers of the round-1 API
+
+    _misaligned = False
+
+    def _realign(self, parity: int) -> None:
+        """Point the device step counter at the history slots of this parity (short regions and eager
+        tail steps advance it by less than ``n_max``); it stays monotonic (Adam bias correction)."""
+        self.rep.step_counter.fill_(self.replays * self.n_max)  # replays & 1 == parity
+
+    def trace_start(self) -> None:
+        """Mark the beginning of the device-time trace on the compute stream."""
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(self.compute)
+        self.trace_events.append((ev, 0))
+
+    def trace_ms(self) -> List[tuple]:
+        """[(device ms, steps)] per replay since ``trace_start`` (call after ``drain``)."""
+        out = []
+        for (a, _), (b, n) in zip(self.trace_events, self.trace_events[1:]):
+            out.append((a.elapsed_time(b), n))
+        return out
+
     def drain(self) -> None:
-        for p in ((self.windows_run & 1), ((self.windows_run + 1) & 1)):
+        for p in ((self.replays & 1), ((self.replays + 1) & 1)):
             self._collect(p)
         self.compute.synchronize()
 
@@ -312,36 +404,45 @@ class FabricWorker:
             torch.cuda.synchronize(self.rep.device)
             self._pending = [None, None]
         self.initial_pull()
-        self.rep.step_counter.zero_().add_(self.windows_run * self.tau)
+        self._misaligned = True
 
     def train_partition(self, part: Partition, features_col: str, label_col: str, num_epoch: int = 1) -> None:
-        """Consume a data partition: full windows through the graphs; the uncommitted tail (fewer
-        than ``tau`` batches) is trained eagerly and, like the reference, never committed."""
+        """Consume a data partition: whole windows through the graphs (``n_max`` steps per replay, then
+        one shorter replay for the remaining full windows); the uncommitted tail (fewer than ``tau``
+        batches) is trained eagerly and, like the reference, never committed."""
         x_all, y_all = part.column(features_col), part.column(label_col)
         if y_all.dim() == 2 and not self.rep.dense_labels:
             y_all = y_all.argmax(dim=1)
         if not self.rep.dense_labels and y_all.dtype != torch.int32:
             y_all = y_all.to(torch.int32)
-        rows_per_window = self.tau * self.B
-        n = x_all.shape[0]
+        if self.rep.dense_labels and y_all.dtype != torch.float32:
+            y_all = y_all.to(torch.float32)
+        if x_all.dtype != self.rep.in_torch_dtype:
+            x_all = x_all.to(self.rep.in_torch_dtype)
+        B, tau = self.B, self.tau
+        n_rows = x_all.shape[0]
         for _ in range(num_epoch):
-            full = n // rows_per_window
-            for w in range(full):
-                lo = w * rows_per_window
-                self.run_window(x_all[lo:lo + rows_per_window], y_all[lo:lo + rows_per_window])
-            tail_lo = full * rows_per_window
-            tail_batches = (n - tail_lo) // self.B
+            lo = 0
+            windows = n_rows // (tau * B)
+            while windows > 0:
+                n = min(self.n_max, windows * tau)
+                n -= n % tau
+                if n <= 0:
+                    break
+                self.run_region(x_all[lo:lo + n * B], y_all[lo:lo + n * B], n)
+                lo += n * B
+                windows -= n // tau
+            tail_batches = (n_rows - lo) // B
             if tail_batches:
                 self.drain()
                 with torch.cuda.stream(self.compute):
                     for j in range(tail_batches):
-                        lo = tail_lo + j * self.B
-                        loss, acc = self.rep.train_on_batch(x_all[lo:lo + self.B], y_all[lo:lo + self.B])
+                        a = lo + j * B
+                        loss, acc = self.rep.train_on_batch(x_all[a:a + B], y_all[a:a + B])
                         self.iteration += 1
                         self.history.append({"history": [loss, acc], "worker_id": self.worker_id,
                                              "iteration": self.iteration, "timestamp": time.time()})
-                # realign the history ring with the window boundary for the next epoch
-                self.rep.step_counter.zero_().add_(self.windows_run * self.tau)
+                self._misaligned = True
         self.drain()
 
 
@@ -461,7 +562,8 @@ class FabricEagerWorker:
                 if self.alg["kind"] == "eamsgd":
                     N.check(self.lib.dk_eamsgd_pre(self.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(), None,
                                                    self.P, float(self.alg["momentum"]), self._stream()), "eamsgd_pre")
-                loss, acc = self.rep.train_on_batch(x, y.long() if y.dim() == 1 else y)
+                loss, acc = self.rep.train_on_batch(
+                    x, y.long() if (y.dim() == 1 and "crossentropy" in str(self.rep.loss)) else y)
                 if self.alg["kind"] == "eamsgd":
                     N.check(self.lib.dk_eamsgd_post(self.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(), None,
                                                     self.P, float(self.alg["eta"]), self._stream()), "eamsgd_post")
@@ -719,12 +821,18 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         parts = dataset.repartition(n_parts).partitions(n_parts)
         wid = worker_ranks.index(rank)
         wkw = dict(comm=getattr(trainer, "comm", "exchange"), strict=trainer.strict, seed=getattr(trainer, "seed", 0))
+        trace = bool(getattr(trainer, "trace_windows", False))
         try:
             if alg["kind"] == "custom":  # python exchange rule: cannot live inside a captured graph
                 raise UnsupportedByNativeEngine("custom exchange rule")
             worker = FabricWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid, trainer.batch_size,
-                                  local, in_dtype, affine, **wkw)
-        except UnsupportedByNativeEngine:
+                                  local, in_dtype, affine, steps_per_graph=getattr(trainer, "steps_per_graph", None),
+                                  trace=trace, **wkw)
+        except UnsupportedByNativeEngine as exc:
+            import warnings
+
+            warnings.warn(f"the native sm_100a engine does not lower this model ({exc}); the replica runs on the "
+                          "autograd executor (cuBLAS / cuDNN), the parameter-server program stays in-kernel")
             worker = FabricEagerWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid,
                                        trainer.batch_size, local, in_dtype, affine, **wkw)
         if shards and isinstance(worker, FabricWorker):
@@ -734,21 +842,10 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         static = getattr(trainer, "shard_mode", "dynamic" if trainer.parallelism_factor > 1 else "static") == "static"
         my_parts = [parts[i] for i in range(wid, n_parts, len(worker_ranks))] if static else None
         if getattr(trainer, "data_is_local_shard", False):
-            # SPMD data loading: the dataset this rank was given IS its shard
+            # SPMD data loading (torchrun): the dataset this rank was given IS its shard
             static = True
             f = max(1, int(trainer.parallelism_factor))
             my_parts = dataset.repartition(f).partitions(f)
-        warm = int(getattr(trainer, "bench_warmup_steps", 0))
-        if warm and static and my_parts:
-            # untimed warm-up on the head of the first shard (bench contract: W warm-up steps)
-            head = my_parts[0]
-            rows = warm * trainer.batch_size
-            worker.train_partition(Partition(head.dataset, head.index, head.start, head.start + rows),
-                                   trainer.features_column, trainer.label_column, 1)
-            my_parts[0] = Partition(head.dataset, head.index, head.start + rows, head.stop)
-            worker.history = []
-            worker.h2d_bytes = worker.d2h_bytes = 0
-            worker.windows_run_at_start = worker.windows_run
         torch.cuda.synchronize()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -757,6 +854,8 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         t0 = time.time()
         with torch.cuda.stream(worker.compute):
             ev0.record(worker.compute)
+            if trace and isinstance(worker, FabricWorker):
+                worker.trace_start()
         failures: List[dict] = []
         tolerate = bool(getattr(trainer, "tolerate_worker_failures", False))
 
@@ -801,12 +900,18 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         torch.cuda.synchronize()
         steps_done = worker.iteration - it0
         windows_done = worker.windows_run - w0
-        tail_steps = steps_done - windows_done * worker.tau
-        per_step = max(0, worker.kernels_per_window - worker.comm_kernels()) // worker.tau
+        if isinstance(worker, FabricWorker):
+            graph_steps = sum(n for _, n in worker.trace_events) if trace else None
+            launches = worker.launched + max(0, steps_done - windows_done * worker.tau) * worker.kernels_per_step
+        else:
+            graph_steps, launches = None, 0
         stats = {"kernels_per_window": worker.kernels_per_window, "windows": windows_done, "steps": steps_done,
-                 "gpu_launches": windows_done * worker.kernels_per_window + tail_steps * per_step,
+                 "gpu_launches": launches, "exchanges": getattr(worker, "exchanges", windows_done),
+                 "steps_per_graph": getattr(worker, "n_max", None), "graph_steps": graph_steps,
                  "h2d_bytes": worker.h2d_bytes, "d2h_bytes": worker.d2h_bytes, "seconds": time.time() - t0,
                  "device_ms": ev0.elapsed_time(ev1), "executor": type(worker).__name__, "failures": failures}
+        if trace and isinstance(worker, FabricWorker):
+            stats["trace_ms"] = worker.trace_ms()
         history = worker.history
         log_event("fabric.worker_done", rank=rank, worker_id=wid, **stats)
         # release the replica's device buffers / graphs before the next job in this process
@@ -954,9 +1059,16 @@ def _sequential_native(trainer, part: Partition, model, device_index: int, worke
     rep = NativeReplica(model, trainer.worker_optimizer, trainer.loss, trainer.batch_size, device_index,
                         in_dtype=in_dtype, input_affine=affine, hist_slots=4096)
     x_all, y_all = part.column(trainer.features_column), part.column(trainer.label_column)
-    if y_all.dim() == 2:
-        y_all = y_all.argmax(dim=1)
-    y_all = y_all.to(torch.int32)
+    if rep.dense_labels:   # regression targets (mse on a linear head): fp32 [n, n_out], never argmax'd
+        y_all = y_all.to(torch.float32).reshape(y_all.shape[0], -1)
+        if y_all.shape[1] != rep.num_classes:
+            raise ValueError(f"label column has {y_all.shape[1]} values per row, the model outputs {rep.num_classes}")
+        y_stride = trainer.batch_size * rep.num_classes * 4
+    else:
+        if y_all.dim() == 2:
+            y_all = y_all.argmax(dim=1)
+        y_all = y_all.to(torch.int32)
+        y_stride = trainer.batch_size * 4
     dev = rep.device
     B = trainer.batch_size
     history, it = [], 0
@@ -965,12 +1077,13 @@ def _sequential_native(trainer, part: Partition, model, device_index: int, worke
     for _ in range(num_epoch):
         for c0 in range(0, n_batches, chunk):
             c1 = min(n_batches, c0 + chunk)
-            xd = x_all[c0 * B:c1 * B].to(dev, non_blocking=True).reshape((c1 - c0) * B, -1)
-            yd = y_all[c0 * B:c1 * B].to(dev, non_blocking=True)
+            # the replica was planned for rep.in_torch_dtype: cast here (the kernels read raw pointers)
+            xd = x_all[c0 * B:c1 * B].to(dev, non_blocking=True).reshape((c1 - c0) * B, -1).to(rep.in_torch_dtype).contiguous()
+            yd = y_all[c0 * B:c1 * B].to(dev, non_blocking=True).contiguous()
             rep.hist.zero_()
             base = int(rep.step_counter.item())
             for j in range(c1 - c0):
-                rep.enqueue_step(xd.data_ptr() + j * B * xd.shape[1] * xd.element_size(), yd.data_ptr() + j * B * 4)
+                rep.enqueue_step(xd.data_ptr() + j * B * xd.shape[1] * xd.element_size(), yd.data_ptr() + j * y_stride)
             steps = (torch.arange(c1 - c0, device=dev) + base) % rep.hist_slots
             recs = rep.hist[steps].cpu().numpy()
             now = time.time()
@@ -1018,8 +1131,16 @@ def train_averaging_native(trainer, dataset: Dataset):
                 dev = w % ndev
                 torch.cuda.set_device(dev)
                 with torch.cuda.stream(torch.cuda.Stream(device=dev)):
-                    m, h = _sequential_native(trainer, parts[w], master.copy(), dev, w, 1)
-                    flats[w] = m.get_flat_weights().to(f"cuda:{dev}").contiguous()
+                    try:
+                        m, h = _sequential_native(trainer, parts[w], master.copy(), dev, w, 1)
+                    except UnsupportedByNativeEngine:
+                        # models the planner does not lower (tanh hidden layers, Reshape, ...): the
+                        # autograd SequentialWorker trains this replica on the same GPU
+                        from ..trainers import _run_tasks
+
+                        res, ws = _run_tasks(trainer.allocate_worker(), [parts[w]], 1, lambda tid: f"cuda:{dev}")
+                        m, h = deserialize_keras_model(res[0][0]), ws[0].training_history
+                    flats[w] = m.get_flat_weights().to(f"cuda:{dev}", torch.float32).contiguous()
                     torch.cuda.current_stream().synchronize()
                 for rec in h:
                     rec["epoch"] = epoch
@@ -1112,10 +1233,16 @@ def train_distributed_spmd_socket(trainer, dataset: Dataset):
     rank, world = _spmd_env()
     dist = _init_pg("gloo")
     exchange_obj, barrier = _dist_helpers(dist)
+    if type(trainer).__name__ in ("EASGD", "SynchronousDistributedTrainer"):
+        raise RuntimeError("synchronous EASGD meets its workers on an in-process barrier; under torchrun use "
+                           "AEASGD (asynchronous) or run it with backend='thread'")
     if rank == 0:
         trainer.parameter_server = trainer.allocate_parameter_server()
         trainer.parameter_server.master_port = 0
-        trainer.master_host = "127.0.0.1"
+        # ranks may live on other hosts: advertise the rendezvous address, and only then leave loopback
+        trainer.master_host = os.environ.get("MASTER_ADDR", "127.0.0.1")
+        if trainer.master_host not in ("127.0.0.1", "localhost"):
+            trainer.parameter_server.bind_host = "0.0.0.0"
         trainer.start_service()
         addr = (trainer.master_host, trainer.master_port)
     else:

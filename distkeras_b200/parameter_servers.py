@@ -93,7 +93,9 @@ class SocketParameterServer(ParameterServer):
         fd = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
         fd.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
         fd.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
-        fd.bind(("0.0.0.0", int(self.master_port or 0)))
+        # loopback unless the trainer asked for a routable address (multi-host control path):
+        # bind_host = "0.0.0.0" is opt-in
+        fd.bind((getattr(self, "bind_host", None) or "127.0.0.1", int(self.master_port or 0)))
         self.master_port = fd.getsockname()[1]
         fd.listen(64)
         self.socket = fd

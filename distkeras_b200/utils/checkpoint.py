@@ -30,7 +30,10 @@ def save_checkpoint(path: str, model, num_updates: int = 0, iteration: int = 0, 
 
 
 def load_checkpoint(path: str) -> dict:
-    payload = torch.load(path, weights_only=False)
+    try:
+        payload = torch.load(path, weights_only=True)   # plain containers + tensors only
+    except Exception:  # checkpoints carrying user objects in `extra` / `history` (trusted, locally written)
+        payload = torch.load(path, weights_only=False)
     if payload.get("version") != FORMAT_VERSION:
         raise ValueError(f"unsupported checkpoint version {payload.get('version')}")
     payload["model"] = deserialize_keras_model(payload["model"])

@@ -381,6 +381,7 @@ class EASGDWorker(AEASGDWorker):
     out of data breaks the barrier and the others finish their shards asynchronously."""
 
     barrier = None  # threading.Barrier installed by the trainer
+    _alone = False  # set once the rendezvous is broken
 
     def _meet(self) -> bool:
         import threading
@@ -397,14 +398,20 @@ class EASGDWorker(AEASGDWorker):
         try:
             while True:
                 batch = self.get_next_minibatch()
-                if self.iteration % self.communication_window == 0 and self._meet():
-                    self.pull()
-                    W = self._W()
-                    E = self.alpha * (W - self.center_variable)
-                    W.sub_(E)
-                    self.replica.weights_changed()
-                    self._meet()  # everyone has read the old center
-                    self.commit(E)
+                if self.iteration % self.communication_window == 0:
+                    if self._alone or not self._meet():
+                        # a peer ran out of data (broken barrier): keep exchanging with the center
+                        # asynchronously, i.e. AEASGD's elastic step, for the rest of the shard
+                        self._alone = True
+                        self.elastic_step()
+                    else:
+                        self.pull()
+                        W = self._W()
+                        E = self.alpha * (W - self.center_variable)
+                        W.sub_(E)
+                        self.replica.weights_changed()
+                        self._meet()  # everyone has read the old center
+                        self.commit(E)
                 self._train_batch(batch)
                 self.iteration += 1
         finally:
