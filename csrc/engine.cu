@@ -31,6 +31,10 @@ struct Op {
   alignas(64) CUtensorMap tm;
   DkGemmEpilogue ep;
   int has_td, has_tm;
+  int dyn_a_slot;   // >= 0: A operand base comes from this slot (tensor map re-encoded when the list runs)
+  long dyn_lda;
+  void* rec;        // DK_OP_BWD_UPDATE: launch record (owned)
+  int bwd_slot[DK_BWD_MAX_LAYERS];
 };
 
 struct Engine {
@@ -113,8 +117,20 @@ int run_op(Engine* e, Op& op, void* main_stream) {
       // w, ldw, wd, ldwd, Cout, Cin, KH, KW
       return dk_conv_weight_flip(resolve(e, a[0]), (int)a[1], resolve(e, a[2]), (int)a[3], (int)a[4], (int)a[5], (int)a[6],
                                  (int)a[7], st);
+    case DK_OP_BWD_UPDATE: {
+      for (int l = 0; l < DK_BWD_MAX_LAYERS; ++l)
+        if (op.bwd_slot[l] >= 0) {
+          int r = dk_bwd_update_set_input(op.rec, l, e->slots[op.bwd_slot[l]]);
+          if (r != 0) return r;
+        }
+      return dk_bwd_update_launch(op.rec, st);
+    }
     case DK_OP_GEMM:
       // M, N, K, bn, flags (tensor maps + epilogue pre-encoded)
+      if (op.dyn_a_slot >= 0) {
+        int r = dk_tmap_encode_2d(&op.ta, e->slots[op.dyn_a_slot], DK_BF16, a[0], a[2], op.dyn_lda, 128);
+        if (r != 0) return r;
+      }
       return dk_gemm_tn_launch2(&op.ta, &op.tb, op.has_td ? &op.td : nullptr, op.has_tm ? &op.tm : nullptr, &op.ep,
                                 (int)a[0], (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], st);
     case DK_OP_XENT:
@@ -267,6 +283,9 @@ void* dk_engine_create() {
 
 void dk_engine_destroy(void* h) {
   Engine* e = reinterpret_cast<Engine*>(h);
+  for (auto& lst : e->lists)
+    for (Op& op : lst)
+      if (op.rec != nullptr) free(op.rec);
   for (cudaEvent_t ev : e->events) cudaEventDestroy(ev);
   for (int k = 0; k < DK_ENGINE_SIDE_STREAMS; ++k)
     if (e->side[k] != nullptr) cudaStreamDestroy(e->side[k]);
@@ -306,6 +325,7 @@ int dk_engine_add_op(void* h, int list, int kind, const int64_t* iargs, int ni, 
   if (list < 0 || list >= (int)e->lists.size() || ni > DK_OP_MAX_I || nf > DK_OP_MAX_F) return -1;
   Op op;
   memset(&op, 0, sizeof(op));
+  op.dyn_a_slot = -1;
   op.kind = kind;
   op.stream_id = e->build_stream;
   for (int k = 0; k < ni; ++k) op.i[k] = iargs[k];
@@ -321,6 +341,7 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
   if (list < 0 || list >= (int)e->lists.size()) return -1;
   Op op;
   memset(&op, 0, sizeof(op));
+  op.dyn_a_slot = -1;
   op.kind = DK_OP_GEMM;
   op.stream_id = e->build_stream;
   const bool splitk_ok = ep->d_fp32 && ep->bias == nullptr && ep->act == 0 && ep->mask == nullptr;
@@ -367,6 +388,45 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
   return static_cast<int>(e->lists[list].size()) - 1;
 }
 
+int dk_engine_add_gemm_slot(void* h, int list, int a_slot, long lda, const void* B, long ldb, int M, int N, int K,
+                            int flags, int bn, int splits, const DkGemmEpilogue* ep) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (a_slot < 0 || a_slot >= DK_ENGINE_SLOTS || (flags & (DK_GEMM_A_MN | DK_GEMM_TF32 | DK_GEMM_PAIR))) return -1;
+  // encode against a placeholder base (B is a valid, aligned device pointer); the real one is bound per run
+  int r = dk_engine_add_gemm(h, list, B, lda, B, ldb, M, N, K, flags, bn, splits, ep);
+  if (r < 0) return r;
+  Op& op = e->lists[list][r];
+  op.dyn_a_slot = a_slot;
+  op.dyn_lda = lda;
+  return r;
+}
+
+int dk_engine_add_bwd_update(void* h, int list, const DkBwdUpdateDesc* desc) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (list < 0 || list >= (int)e->lists.size()) return -1;
+  Op op;
+  memset(&op, 0, sizeof(op));
+  op.dyn_a_slot = -1;
+  op.kind = DK_OP_BWD_UPDATE;
+  op.stream_id = e->build_stream;
+  void* raw = nullptr;
+  if (posix_memalign(&raw, 128, dk_bwd_update_record_bytes()) != 0) return -2;
+  op.rec = raw;
+  // slot-fed layers are prepared against a placeholder input (their own dZ buffer) and re-pointed per run
+  DkBwdUpdateDesc d = *desc;
+  for (int l = 0; l < DK_BWD_MAX_LAYERS; ++l) {
+    op.bwd_slot[l] = (l < d.nlayers && d.layer[l].x_slot >= 0) ? d.layer[l].x_slot : -1;
+    if (op.bwd_slot[l] >= 0) d.layer[l].x = nullptr;
+  }
+  int r = dk_bwd_update_prepare(op.rec, &d);
+  if (r != 0) {
+    free(raw);
+    return r < 0 ? r : -r;
+  }
+  e->lists[list].push_back(op);
+  return static_cast<int>(e->lists[list].size()) - 1;
+}
+
 int dk_engine_add_conv_gemm(void* h, int list, const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW,
                             int mul, int off, int div, const void* Bmat, long ldb, int M, int N, int K,
                             const DkGemmEpilogue* ep) {
@@ -374,6 +434,7 @@ int dk_engine_add_conv_gemm(void* h, int list, const void* src, int SH, int SW, 
   if (list < 0 || list >= (int)e->lists.size()) return -1;
   Op op;
   memset(&op, 0, sizeof(op));
+  op.dyn_a_slot = -1;
   op.kind = DK_OP_CONV_GEMM;
   op.stream_id = e->build_stream;
   const int bn = dk_conv_pick_bn(N);
@@ -395,6 +456,7 @@ int dk_engine_add_conv_wgrad(void* h, int list, const void* src, int SH, int SW,
   if (list < 0 || list >= (int)e->lists.size()) return -1;
   Op op;
   memset(&op, 0, sizeof(op));
+  op.dyn_a_slot = -1;
   op.kind = DK_OP_CONV_WGRAD;
   op.stream_id = e->build_stream;
   int r = dk_tmap_encode_2d(&op.ta, dz, DK_BF16, rows, Cout, lddz, 64);
@@ -424,6 +486,7 @@ int dk_engine_add_gemm_pull(void* h, int list, const void* X, long ldx, const vo
   if (list < 0 || list >= (int)e->lists.size()) return -1;
   Op op;
   memset(&op, 0, sizeof(op));
+  op.dyn_a_slot = -1;
   op.kind = DK_OP_GEMM_PULL;
   op.stream_id = e->build_stream;
   int r = dk_tmap_encode_2d(&op.ta, X, DK_F32, M, K, ldx, 128);

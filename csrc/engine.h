@@ -2,6 +2,7 @@
 #pragma once
 #include <stdint.h>
 
+#include "dense_fused.h"
 #include "gemm.h"
 
 #define DK_OP_MAX_I 20
@@ -50,7 +51,8 @@ enum {
   DK_OP_HEAD = 37,
   DK_OP_CONV_GEMM = 38,
   DK_OP_WFLIP = 39,
-  DK_OP_CONV_WGRAD = 40  // experimental
+  DK_OP_CONV_WGRAD = 40,  // experimental
+  DK_OP_BWD_UPDATE = 41   // fused wgrad + bias-grad + optimizer (+ PS exchange) of every dense layer
 };
 
 #ifdef __cplusplus
@@ -68,6 +70,12 @@ int dk_engine_add_op(void* h, int list, int kind, const int64_t* iargs, int ni, 
                      int nf);
 int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B, long ldb, int M, int N,
                        int K, int flags, int bn, int splits, const DkGemmEpilogue* ep);
+// same, with the A operand base read from engine slot `a_slot` every time the list runs (the tensor map is
+// re-encoded at enqueue time; inside a captured graph that is capture time only)
+int dk_engine_add_gemm_slot(void* h, int list, int a_slot, long lda, const void* B, long ldb, int M, int N, int K,
+                            int flags, int bn, int splits, const DkGemmEpilogue* ep);
+// fused dense backward-update (dense_fused.cu); layers with x_slot >= 0 take their input from that slot
+int dk_engine_add_bwd_update(void* h, int list, const DkBwdUpdateDesc* desc);
 int dk_engine_add_gemm_pull(void* h, int list, const void* X, long ldx, const void* center_w, long ldc, int M, int N,
                             int K, void* w_local, void* w1_local, void* wb_local, const DkGemmEpilogue* ep);
 // implicit-GEMM convolution (forward or dgrad form; see conv_gemm_kernel in gemm_tcgen05.cu)

@@ -7,53 +7,9 @@
 // read from a device counter so the launch can be replayed from a CUDA graph.
 #include "common.cuh"
 #include "kernels.h"
+#include "optim.cuh"
 
 namespace dk {
-
-struct OptimArgs {
-  float* w;
-  const float* g;
-  float* s0;  // momentum / accumulator / adam m / adadelta acc
-  float* s1;  // adam v / adadelta delta_acc / adamax u
-  __nv_bfloat16* wb;
-  long n;
-  int kind;
-  float lr, p0, p1, eps, decay;
-  int nesterov;
-  const int* step;  // device step counter (>= 1)
-  float grad_scale;
-};
-
-template <int KIND>
-__device__ __forceinline__ void optim_update(float& w, float g, float& s0, float& s1, float lr,
-                                             const OptimArgs& a, float corr) {
-  if constexpr (KIND == DK_OPT_SGD) {
-    w -= lr * g;
-  } else if constexpr (KIND == DK_OPT_MOMENTUM) {
-    const float v = a.p0 * s0 - lr * g;
-    s0 = v;
-    w += a.nesterov ? a.p0 * v - lr * g : v;
-  } else if constexpr (KIND == DK_OPT_ADAGRAD) {
-    s0 += g * g;
-    w -= lr * g / (sqrtf(s0) + a.eps);
-  } else if constexpr (KIND == DK_OPT_RMSPROP) {
-    s0 = a.p0 * s0 + (1.f - a.p0) * g * g;
-    w -= lr * g / (sqrtf(s0) + a.eps);
-  } else if constexpr (KIND == DK_OPT_ADAM) {
-    s0 = a.p0 * s0 + (1.f - a.p0) * g;
-    s1 = a.p1 * s1 + (1.f - a.p1) * g * g;
-    w -= lr * corr * s0 / (sqrtf(s1) + a.eps);
-  } else if constexpr (KIND == DK_OPT_ADADELTA) {
-    s0 = a.p0 * s0 + (1.f - a.p0) * g * g;
-    const float upd = g * sqrtf(s1 + a.eps) / sqrtf(s0 + a.eps);
-    w -= lr * upd;
-    s1 = a.p0 * s1 + (1.f - a.p0) * upd * upd;
-  } else if constexpr (KIND == DK_OPT_ADAMAX) {
-    s0 = a.p0 * s0 + (1.f - a.p0) * g;
-    s1 = fmaxf(a.p1 * s1, fabsf(g));
-    w -= lr * corr * s0 / (s1 + a.eps);
-  }
-}
 
 template <int KIND>
 __global__ void __launch_bounds__(256) optim_kernel(const OptimArgs a) {

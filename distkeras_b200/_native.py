@@ -31,6 +31,29 @@ class GemmEpilogue(C.Structure):
     ]
 
 
+BWD_MAX_LAYERS, BWD_MAX_SHARDS = 6, 16
+COMM_NONE, COMM_EXCHANGE, COMM_ELASTIC = 0, 1, 2
+
+
+class BwdLayerDesc(C.Structure):
+    """Mirror of ``DkBwdLayerDesc`` (csrc/dense_fused.h)."""
+
+    _fields_ = [("dz", vp), ("lddz", i64), ("x", vp), ("ldx", i64), ("x_slot", i32), ("n_out", i32), ("k_in", i32),
+                ("w_off", i64), ("b_off", i64), ("wb_pad", vp), ("ldwb_pad", i64)]
+
+
+class BwdUpdateDesc(C.Structure):
+    """Mirror of ``DkBwdUpdateDesc`` (csrc/dense_fused.h)."""
+
+    _fields_ = [("nlayers", i32), ("batch", i32), ("layer", BwdLayerDesc * BWD_MAX_LAYERS),
+                ("w", vp), ("s0", vp), ("s1", vp), ("w1", vp), ("wb", vp),
+                ("opt_kind", i32), ("lr", f32), ("p0", f32), ("p1", f32), ("eps", f32), ("decay", f32), ("nesterov", i32),
+                ("step", vp), ("done_counter", vp), ("step_inc", i32),
+                ("comm_mode", i32), ("comm_scale", f32), ("scale_dev", vp), ("alpha", f32),
+                ("nshards", i32), ("shard_per", i64), ("shard_center", vp * BWD_MAX_SHARDS),
+                ("ctrl", vp), ("worker", i32), ("last_update", vp)]
+
+
 # op kinds (csrc/engine.h)
 OP_INPUT, OP_GEMM, OP_XENT, OP_ROWSUM, OP_TRANSPOSE, OP_OPTIM, OP_IM2COL, OP_COL2IM = range(8)
 OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_RELU_MASK, OP_ADD, OP_MEMSET = 8, 9, 10, 11, 12
@@ -38,7 +61,7 @@ OP_PS_COMMIT, OP_PS_PULL, OP_PS_EXCHANGE, OP_PS_ELASTIC, OP_PS_DAMPED, OP_PS_TIC
 OP_LOCK_ACQUIRE, OP_LOCK_RELEASE, OP_EAMSGD_PRE, OP_EAMSGD_POST, OP_CAST, OP_ELOSS = 19, 20, 21, 22, 23, 24
 OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D, OP_FORK, OP_JOIN, OP_GEMM_PULL = 25, 26, 27, 28, 29, 30, 31
 OP_BN_FWD, OP_BN_INF, OP_BN_BWD, OP_GAP_FWD, OP_GAP_BWD, OP_HEAD = 32, 33, 34, 35, 36, 37
-OP_CONV_GEMM, OP_WFLIP, OP_CONV_WGRAD = 38, 39, 40
+OP_CONV_GEMM, OP_WFLIP, OP_CONV_WGRAD, OP_BWD_UPDATE = 38, 39, 40, 41
 GEMM_TF32, GEMM_A_MN, GEMM_B_MN, GEMM_PERSISTENT, GEMM_PAIR = 1, 2, 4, 8, 16
 
 OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6}
@@ -138,6 +161,10 @@ _SIGNATURES = {
                                       C.POINTER(GemmEpilogue)]),
     "dk_engine_add_gemm": (i32, [vp, i32, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, C.POINTER(GemmEpilogue)]),
     "dk_engine_add_gemm_pull": (i32, [vp, i32, vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, C.POINTER(GemmEpilogue)]),
+    "dk_engine_add_gemm_slot": (i32, [vp, i32, i32, i64, vp, i64, i32, i32, i32, i32, i32, i32, C.POINTER(GemmEpilogue)]),
+    "dk_engine_add_bwd_update": (i32, [vp, i32, C.POINTER(BwdUpdateDesc)]),
+    "dk_bwd_update": (i32, [C.POINTER(BwdUpdateDesc), vp]),
+    "dk_bwd_update_desc_bytes": (i64, []),
     "dk_engine_run": (i32, [vp, i32, vp]),
     "dk_engine_list_size": (i32, [vp, i32]),
     "dk_engine_list_kernels": (i32, [vp, i32]),
@@ -166,6 +193,8 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        if handle.dk_bwd_update_desc_bytes() != C.sizeof(BwdUpdateDesc):
+            raise RuntimeError("ctypes mirror of DkBwdUpdateDesc is out of sync with csrc/dense_fused.h")
         _lib = handle
     return _lib
 

@@ -33,7 +33,7 @@ from ..models.core import (Activation, BatchNormalization, Conv2D, Dense, Dropou
 from ..ops.flat_optim import FlatOptimizer
 from .replica import Replica
 
-SLOT_X, SLOT_Y = 0, 1
+SLOT_X, SLOT_Y, SLOT_XB = 0, 1, 2
 
 
 def _r8(n: int) -> int:
@@ -170,7 +170,8 @@ class NativeReplica(Replica):
     def __init__(self, model: Sequential, optimizer, loss: str, batch_size: int, device_index: int = 0,
                  in_dtype: str = "u8", input_affine: Tuple[float, float] = (1.0, 0.0), hist_slots: int = 1024,
                  dense_labels: bool = False, seed: int = 1234, training: bool = True,
-                 pull_center_ptr: int = 0):
+                 pull_center_ptr: int = 0, region_steps: int = 1, comm_spec: Optional[dict] = None,
+                 compact: Optional[bool] = None):
         self.lib = N.lib()
         model.build()
         self.model = model
@@ -186,6 +187,9 @@ class NativeReplica(Replica):
         self.dense_labels = bool(dense_labels)
         self.seed = int(seed)
         self.blocks = _group_layers(model)
+        self.region_steps = max(1, int(region_steps))
+        self.comm_spec = dict(comm_spec) if comm_spec else None
+        self._compact_request = compact
         head = self.blocks[-1]
         self.num_classes = head.n_out
         if loss in ("categorical_crossentropy", "sparse_categorical_crossentropy"):
@@ -203,15 +207,23 @@ class NativeReplica(Replica):
         self.P = P
         self.W = model.get_flat_weights().detach().to(dev, torch.float32).clone().contiguous()
         self.Wb = torch.zeros(P, dtype=torch.bfloat16, device=dev)
-        self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.hist = torch.zeros(self.hist_slots, 2, dtype=torch.float32, device=dev)
         self.training = training
         self.pull_center_ptr = int(pull_center_ptr) if training else 0
+        # compact (small-batch) program: region-level input staging, narrow forward tiles, and ONE fused
+        # kernel for every weight gradient + bias gradient + optimizer update (+ the PS exchange)
+        self.compact = self._compact_eligible()
+        # device step counter: in the classic program the per-step input stage increments it before the
+        # step's kernels read it; in the compact program it holds the 1-based index of the step being
+        # executed and the fused backward-update kernel advances it when the step is complete
+        self.step_base = 1 if self.compact else 0
+        self.step_counter = torch.full((1,), self.step_base, dtype=torch.int32, device=dev)
+        self._done_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.W1 = None
         if training:
-            self.G = torch.zeros(P, dtype=torch.float32, device=dev)
+            self.G = None if self.compact else torch.zeros(P, dtype=torch.float32, device=dev)
             self.opt = FlatOptimizer(optimizer, P, dev)
-            if self.pull_center_ptr:
+            if self.pull_center_ptr or self.comm_spec:
                 self.W1 = self.W.clone()
         self._keep: list = []  # buffers referenced only by raw pointers
         self.engine = self.lib.dk_engine_create()
@@ -220,6 +232,8 @@ class NativeReplica(Replica):
         self.L_step = self.lib.dk_engine_new_list(self.engine) if training else -1
         self.L_bwd = self.lib.dk_engine_new_list(self.engine) if training else -1
         self.L_fwd = self.lib.dk_engine_new_list(self.engine)
+        self.L_bwd_comm = -1      # compact program: backward list whose fused update also exchanges with the PS
+        self.L_in_region = self.L_in_step = -1
         self.L_step_pull = -1
         self.pull_segment = None
         self._input_feats = int(np.prod(model.input_shape))
@@ -232,6 +246,29 @@ class NativeReplica(Replica):
             self._y_stage = torch.zeros(self.B, self.num_classes, dtype=torch.float32, device=dev)
         else:
             self._y_stage = torch.zeros(self.B, dtype=torch.int32, device=dev)
+
+    def _compact_eligible(self) -> bool:
+        """The compact program covers what the reference actually trains at its batch sizes: stacks of
+        Dense (+ReLU / Dropout) layers ending in a softmax head with <= 16 classes, cross-entropy."""
+        if self._compact_request is False or os.environ.get("DK_COMPACT", "1") == "0" or not self.training:
+            return False
+        if self.pull_center_ptr or self.loss_kind != "xent" or os.environ.get("DK_FUSED_HEAD", "1") == "0":
+            return False
+        limit = int(os.environ.get("DK_COMPACT_MAX_BATCH", "256"))
+        if self.B > limit and self._compact_request is not True:
+            return False
+        blocks = self.blocks
+        if any(b.kind != "dense" for b in blocks) or not (1 <= len(blocks) <= N.BWD_MAX_LAYERS):
+            return False
+        for b in blocks[:-1]:
+            if b.n_out % 8 != 0:
+                return False
+        for b in blocks[1:]:
+            if b.k_in % 8 != 0:
+                return False
+        head = blocks[-1]
+        return (head.n_out <= 16 and head.act == "softmax" and head.k_in % 8 == 0
+                and head.n_out * (head.k_in + 4) * 4 <= 48 * 1024)
 
     # ------------------------------------------------------------------------------------------
     # op-list helpers
@@ -270,8 +307,20 @@ class NativeReplica(Replica):
         B = self.B
         F = self._input_feats
         in_shape = tuple(self.model.input_shape)
-        x0 = self._buf(B, _r8(F))
-        cur = dict(t=x0, rows=B, cols=F, ld=_r8(F), nhwc=in_shape if len(in_shape) == 3 else None)
+        if self.compact:
+            # the whole region's mini-batches are staged (cast + MinMax affine) by ONE launch; step j reads
+            # rows [j B, (j + 1) B) through slot SLOT_XB (tensor maps re-encoded when the list is enqueued)
+            x0 = self._buf(self.region_steps * B, _r8(F))
+            self._xb_region = x0
+            self.L_in_region = self.lib.dk_engine_new_list(self.engine)
+            self.L_in_step = self.lib.dk_engine_new_list(self.engine)
+            for lst, rows in ((self.L_in_region, self.region_steps * B), (self.L_in_step, B)):
+                self._add(lst, N.OP_INPUT, [-(SLOT_X + 1), self.in_dtype, rows, F, x0.data_ptr(), _r8(F), 0, 0, 0, 0, F],
+                          [self.scale, self.shift])
+        else:
+            x0 = self._buf(B, _r8(F))
+        cur = dict(t=x0, rows=B, cols=F, ld=_r8(F), nhwc=in_shape if len(in_shape) == 3 else None,
+                   slot=SLOT_XB if self.compact else None)
         first = self.blocks[0]
         x0f = None
         if self.pull_center_ptr and first.kind == "dense" and first.k_in % 8 == 0 and F % 8 == 0:
@@ -285,7 +334,7 @@ class NativeReplica(Replica):
         nbn = sum(4 * c for c in self._bn_channels())
         self._bn_scratch = self._buf(max(nbn, 1), dtype=torch.float32)
         self._bn_used = 0
-        for lst in self._lists:
+        for lst in ([] if self.compact else self._lists):
             if nbn:
                 self._add(lst, N.OP_MEMSET, [self._bn_scratch.data_ptr(), 0, nbn * 4])
             self._add(lst, N.OP_INPUT,
@@ -325,40 +374,86 @@ class NativeReplica(Replica):
         self._prepend_pad_refresh(self.L_fwd)
         if not self.training:
             return
-        lst = self.L_bwd
-        # ---- loss ----
         ldz = _r8(Cn)
-        dz = self._buf(B, ldz)
-        if self.loss_kind == "xent" and getattr(self, "head_fused", False):
-            pass  # loss + dZ come out of the fused head op emitted by the last block's backward
-        elif self.loss_kind == "xent":
-            self._add(lst, N.OP_XENT, [self.logits.data_ptr(), ldl,
-                                       0 if self.dense_labels else -(SLOT_Y + 1),
-                                       -(SLOT_Y + 1) if self.dense_labels else 0,
-                                       B, Cn, dz.data_ptr(), ldz, 0, 0, 0, self.hist.data_ptr(),
-                                       self.step_counter.data_ptr(), self.hist_slots])
-        else:
-            self._add(lst, N.OP_ELOSS, [N.LOSS_MSE, self.logits.data_ptr(), -(SLOT_Y + 1), B, Cn, dz.data_ptr(), ldz,
-                                        0, 0, self.hist.data_ptr(), self.step_counter.data_ptr(), self.hist_slots])
-        self._add(lst, N.OP_MEMSET, [self.G.data_ptr(), 0, self.P * 4])
-        # ---- backward ----
-        grad = dict(t=dz, rows=B, cols=Cn, ld=ldz)
-        premasked = True  # dZ of the head is already w.r.t. the logits
-        for bi in range(nblocks - 1, -1, -1):
-            b, bw = backward[bi]
-            prev = self.blocks[bi - 1] if bi > 0 else None
-            grad, premasked = bw(grad, premasked, bi > 0, prev)
-            if bi == 0:
-                break
-        # ---- optimizer (one fused launch over the flat buffer, emits the bf16 shadow) ----
-        for sid in sorted(self._forked):
-            self._add(lst, N.OP_JOIN, [sid])
+        targets = [self.L_bwd]
+        if self.compact and self.comm_spec:
+            self.L_bwd_comm = self.lib.dk_engine_new_list(self.engine)
+            targets.append(self.L_bwd_comm)
+        for lst in targets:
+            self._bwd_list = lst
+            self._bwd_layers = []
+            # ---- loss ----
+            dz = self._buf(B, ldz)
+            if self.loss_kind == "xent" and getattr(self, "head_fused", False):
+                pass  # loss + dZ come out of the fused head op emitted by the last block's backward
+            elif self.loss_kind == "xent":
+                self._add(lst, N.OP_XENT, [self.logits.data_ptr(), ldl,
+                                           0 if self.dense_labels else -(SLOT_Y + 1),
+                                           -(SLOT_Y + 1) if self.dense_labels else 0,
+                                           B, Cn, dz.data_ptr(), ldz, 0, 0, 0, self.hist.data_ptr(),
+                                           self.step_counter.data_ptr(), self.hist_slots])
+            else:
+                self._add(lst, N.OP_ELOSS, [N.LOSS_MSE, self.logits.data_ptr(), -(SLOT_Y + 1), B, Cn, dz.data_ptr(), ldz,
+                                            0, 0, self.hist.data_ptr(), self.step_counter.data_ptr(), self.hist_slots])
+            if not self.compact:
+                self._add(lst, N.OP_MEMSET, [self.G.data_ptr(), 0, self.P * 4])
+            # ---- backward ----
+            grad = dict(t=dz, rows=B, cols=Cn, ld=ldz)
+            premasked = True  # dZ of the head is already w.r.t. the logits
+            for bi in range(nblocks - 1, -1, -1):
+                b, bw = backward[bi]
+                prev = self.blocks[bi - 1] if bi > 0 else None
+                grad, premasked = bw(grad, premasked, bi > 0, prev)
+                if bi == 0:
+                    break
+            for sid in sorted(self._forked):
+                self._add(lst, N.OP_JOIN, [sid])
+            o = self.opt
+            if self.compact:
+                # ---- every weight gradient, bias gradient and the optimizer rule: ONE kernel ----
+                self._emit_bwd_update(lst, with_comm=lst == self.L_bwd_comm)
+            else:
+                # ---- optimizer (one fused launch over the flat buffer, emits the bf16 shadow) ----
+                self._add(lst, N.OP_OPTIM, [N.OPT_KINDS[o.kernel_kind], self.W.data_ptr(), self.G.data_ptr(), N.ptr(o.s0),
+                                            N.ptr(o.s1), self.Wb.data_ptr(), self.P, int(o.nesterov),
+                                            self.step_counter.data_ptr()],
+                          [o.lr, o.p0, o.p1, o.eps, o.decay, 1.0])
+            self._prepend_pad_refresh(lst)
+
+    def _emit_bwd_update(self, lst: int, with_comm: bool) -> None:
         o = self.opt
-        self._add(lst, N.OP_OPTIM, [N.OPT_KINDS[o.kernel_kind], self.W.data_ptr(), self.G.data_ptr(), N.ptr(o.s0),
-                                    N.ptr(o.s1), self.Wb.data_ptr(), self.P, int(o.nesterov),
-                                    self.step_counter.data_ptr()],
-                  [o.lr, o.p0, o.p1, o.eps, o.decay, 1.0])
-        self._prepend_pad_refresh(lst)
+        d = N.BwdUpdateDesc()
+        layers = self._bwd_layers
+        d.nlayers, d.batch = len(layers), self.B
+        for i, l in enumerate(layers):
+            ld = d.layer[i]
+            ld.dz, ld.lddz, ld.x, ld.ldx, ld.x_slot = l["dz"], l["lddz"], l["x"], l["ldx"], l["x_slot"]
+            ld.n_out, ld.k_in, ld.w_off, ld.b_off = l["n_out"], l["k_in"], l["w_off"], l["b_off"]
+            ld.wb_pad, ld.ldwb_pad = l["wb_pad"], l["ldwb_pad"]
+        d.w, d.s0, d.s1, d.wb = self.W.data_ptr(), N.ptr(o.s0), N.ptr(o.s1), self.Wb.data_ptr()
+        d.w1 = N.ptr(self.W1)
+        d.opt_kind = N.OPT_KINDS[o.kernel_kind]
+        d.lr, d.p0, d.p1, d.eps, d.decay, d.nesterov = o.lr, o.p0, o.p1, o.eps, o.decay, int(o.nesterov)
+        d.step, d.done_counter, d.step_inc = self.step_counter.data_ptr(), self._done_counter.data_ptr(), 1
+        d.comm_mode, d.nshards, d.shard_per = N.COMM_NONE, 1, 1
+        if with_comm:
+            c = self.comm_spec
+            d.comm_mode = c["mode"]
+            d.comm_scale, d.alpha = float(c.get("scale", 1.0)), float(c.get("alpha", 0.0))
+            d.scale_dev = c.get("scale_dev") or None
+            shards = c["shards"]  # [(lo, hi, center_ptr)], equal-sized except the last
+            if len(shards) > N.BWD_MAX_SHARDS:
+                raise UnsupportedByNativeEngine("too many parameter-server shards for the fused exchange")
+            d.nshards = len(shards)
+            d.shard_per = max(1, shards[0][1] - shards[0][0])
+            for i, (lo, hi, ptr) in enumerate(shards):
+                if lo != i * d.shard_per:
+                    raise UnsupportedByNativeEngine("parameter-server shards must be equal-sized and contiguous")
+                d.shard_center[i] = ptr
+            d.ctrl, d.worker, d.last_update = c["ctrl"], int(c["worker"]), c.get("last_update") or None
+        r = self.lib.dk_engine_add_bwd_update(self.engine, lst, C.byref(d))
+        if r < 0:
+            raise RuntimeError(f"dk_engine_add_bwd_update failed: {r}")
 
     def _bn_channels(self) -> List[int]:
         out = []
@@ -369,6 +464,16 @@ class NativeReplica(Replica):
                 out += [b.bn1.channels, b.bn2.channels] + ([b.bnp.channels] if b.proj is not None else [])
         return out
 
+    @staticmethod
+    def _narrow_bn(M: int, Nn: int, floor: int) -> int:
+        """Tile width for the compact program: with one or two M tiles the grid is N / bn CTAs, so the
+        narrowest tile that keeps <= ~2 CTAs per SM spreads the weight stream over the most SMs."""
+        m_tiles = (M + 127) // 128
+        for bn in (16, 32, 64, 128):
+            if bn >= floor and m_tiles * ((Nn + bn - 1) // bn) <= 296:
+                return bn
+        return 128
+
     def _bn_slice(self, floats: int) -> int:
         ptr = self._bn_scratch.data_ptr() + 4 * self._bn_used
         self._bn_used += floats
@@ -377,7 +482,7 @@ class NativeReplica(Replica):
     # -- Dense / Conv2D -----------------------------------------------------------------------------
     def _emit_matmul(self, b: _Block, cur: dict, bi: int, is_last: bool):
         B, lists = self.B, self._lists
-        wptr_f32, wb_ptr, g_ptr = self.W.data_ptr(), self.Wb.data_ptr(), (self.G.data_ptr() if self.training else 0)
+        wptr_f32, wb_ptr, g_ptr = self.W.data_ptr(), self.Wb.data_ptr(), (N.ptr(self.G) if self.training else 0)
         kseg = self._seg(b.layer_index, b.seg_prefix + "kernel")
         bseg = self._seg(b.layer_index, b.seg_prefix + "bias") if b.use_bias else None
         K, Nout = b.k_in, b.n_out
@@ -462,11 +567,19 @@ class NativeReplica(Replica):
                 if r < 0:
                     raise RuntimeError(f"dk_engine_add_conv_gemm(fwd) failed: {r}")
                 continue
-            self._gemm(lst, a_in["t"].data_ptr(), a_in["ld"], wbp, wbld, rows, Nout, K, 0, ep)
+            bn = self._narrow_bn(rows, Nout, 16) if self.compact else 0
+            if a_in.get("slot") is not None:
+                r = self.lib.dk_engine_add_gemm_slot(self.engine, lst, a_in["slot"], a_in["ld"], C.c_void_p(wbp), wbld,
+                                                     rows, Nout, K, 0, bn, 1, C.byref(ep))
+                if r < 0:
+                    raise RuntimeError(f"dk_engine_add_gemm_slot(M={rows}, N={Nout}, K={K}) failed: {r}")
+                continue
+            self._gemm(lst, a_in["t"].data_ptr(), a_in["ld"], wbp, wbld, rows, Nout, K, 0, ep, bn=bn,
+                       splits=1 if bn else 0)
         b.out_rec = rec
 
         def backward(grad, premasked, need_dx, prev):
-            lst = self.L_bwd
+            lst = self._bwd_list
             head_din = None
             if head_fused:
                 fuse_mask = prev is not None and prev.kind == "dense" and prev.act == "relu"
@@ -475,7 +588,8 @@ class NativeReplica(Replica):
                 alpha = 1.0 / (1.0 - prev.drop_p) if (fuse_mask and prev.drop_p > 0) else 1.0
                 head_din = self._buf(rows, K) if need_dx else None
                 self._add(lst, N.OP_HEAD,
-                          [a_in["t"].data_ptr(), a_in["ld"], wbp, wbld, (wptr_f32 + 4 * bseg.offset) if bseg is not None else 0,
+                          [-(a_in["slot"] + 1) if a_in.get("slot") is not None else a_in["t"].data_ptr(), a_in["ld"], wbp,
+                           wbld, (wptr_f32 + 4 * bseg.offset) if bseg is not None else 0,
                            0 if self.dense_labels else -(SLOT_Y + 1), -(SLOT_Y + 1) if self.dense_labels else 0,
                            rows, Nout, K, grad["t"].data_ptr(), grad["ld"], head_din.data_ptr() if need_dx else 0, K,
                            1 if fuse_mask else 0, self.hist.data_ptr(), self.step_counter.data_ptr(), self.hist_slots],
@@ -487,6 +601,32 @@ class NativeReplica(Replica):
             # (graph branches).  DK_SIDE_STREAMS=2 (default): wgrads on branch 1, bias column sums on
             # branch 2, and the first layer's wgrad -- nothing is left to overlap it with -- on the main
             # stream; DK_SIDE_STREAMS=1: one branch carries both.
+            if self.compact:
+                # weight / bias gradient + optimizer of this layer are tiles of the fused update kernel
+                padded = wbld != K
+                self._bwd_layers.append(dict(
+                    dz=grad["t"].data_ptr(), lddz=grad["ld"],
+                    x=None if a_in.get("slot") is not None else a_in["t"].data_ptr(), ldx=a_in["ld"],
+                    x_slot=a_in["slot"] if a_in.get("slot") is not None else -1, n_out=Nout, k_in=K,
+                    w_off=kseg.offset, b_off=bseg.offset if bseg is not None else -1,
+                    wb_pad=wbp if padded else None, ldwb_pad=wbld if padded else 0))
+                if not need_dx:
+                    return None, True
+                if head_din is not None:
+                    return dict(t=head_din, rows=rows, cols=K, ld=K), fuse_mask
+                din = self._buf(rows, _r8(K))
+                ep = N.GemmEpilogue()
+                ep.d, ep.ldd, ep.alpha = din.data_ptr(), _r8(K), 1.0
+                fuse_mask = prev is not None and prev.kind == "dense" and prev.act == "relu"
+                if fuse_mask:
+                    ep.mask, ep.ld_mask = prev.out_rec["t"].data_ptr(), prev.out_rec["ld"]
+                    if prev.drop_p > 0:
+                        ep.alpha = 1.0 / (1.0 - prev.drop_p)
+                elif prev is not None and prev.kind == "dense" and prev.drop_p > 0:
+                    raise UnsupportedByNativeEngine("dropout after a non-ReLU dense layer")
+                self._gemm(lst, grad["t"].data_ptr(), grad["ld"], wbp, wbld, rows, K, Nout, N.GEMM_B_MN, ep,
+                           bn=self._narrow_bn(rows, K, 64), splits=1)
+                return dict(t=din, rows=rows, cols=K, ld=_r8(K)), fuse_mask
             two = self._side_streams >= 2
             s_bias = 2 if two else (1 if need_dx else 0)
             s_wgrad = (1 if need_dx else 0) if two else 1
@@ -582,7 +722,7 @@ class NativeReplica(Replica):
             # the pool's input is the previous block's post-ReLU output: its dReLU mask is (x > 0),
             # which the pooling backward already has in registers -> no separate mask pass
             fuse_relu = _relu_mask_fusable(prev, B * H * Wd, Cc)
-            self._add(self.L_bwd, N.OP_MAXPOOL_BWD, [inp["t"].data_ptr(), out.data_ptr(), grad["t"].data_ptr(), B, H,
+            self._add(self._bwd_list, N.OP_MAXPOOL_BWD, [inp["t"].data_ptr(), out.data_ptr(), grad["t"].data_ptr(), B, H,
                                                      Wd, Cc, b.k, b.k, dx.data_ptr(), 1 if fuse_relu else 0])
             return dict(t=dx, rows=B * H * Wd, cols=Cc, ld=Cc), fuse_relu
 
@@ -613,7 +753,7 @@ class NativeReplica(Replica):
 
         def backward(grad, premasked, need_dx, prev):
             dx = self._buf(B * P, Cc)
-            self._add(self.L_bwd, N.OP_GAP_BWD, [grad["t"].data_ptr(), B, P, Cc, dx.data_ptr()])
+            self._add(self._bwd_list, N.OP_GAP_BWD, [grad["t"].data_ptr(), B, P, Cc, dx.data_ptr()])
             return dict(t=dx, rows=B * P, cols=Cc, ld=Cc), False
 
         return rec, backward
@@ -623,7 +763,7 @@ class NativeReplica(Replica):
         if cur["ld"] != cur["cols"] or cur["cols"] != b.channels:
             raise UnsupportedByNativeEngine("BatchNormalization on a padded activation")
         rows, Cc = cur["rows"], b.channels
-        wf, g_ptr = self.W.data_ptr(), (self.G.data_ptr() if self.training else 0)
+        wf, g_ptr = self.W.data_ptr(), (N.ptr(self.G) if self.training else 0)
         seg = {n: self._seg(b.layer_index, b.seg_prefix + n) for n in ("gamma", "beta", "moving_mean", "moving_variance")}
         gamma, beta = wf + 4 * seg["gamma"].offset, wf + 4 * seg["beta"].offset
         mm, mv = wf + 4 * seg["moving_mean"].offset, wf + 4 * seg["moving_variance"].offset
@@ -646,7 +786,7 @@ class NativeReplica(Replica):
         def backward(grad, premasked, need_dx, prev):
             dx = self._buf(rows, Cc)
             mask = out.data_ptr() if (relu and not premasked) else 0
-            self._add(self.L_bwd, N.OP_BN_BWD, [grad["t"].data_ptr(), inp["t"].data_ptr(), mask, rows, Cc,
+            self._add(self._bwd_list, N.OP_BN_BWD, [grad["t"].data_ptr(), inp["t"].data_ptr(), mask, rows, Cc,
                                                 saved_mean.data_ptr(), saved_invstd.data_ptr(), gamma, bsum,
                                                 g_ptr + 4 * seg["gamma"].offset, g_ptr + 4 * seg["beta"].offset,
                                                 dx.data_ptr()])
@@ -676,7 +816,7 @@ class NativeReplica(Replica):
         b.out_rec = rec
 
         def backward(grad, premasked, need_dx, prev):
-            lst = self.L_bwd
+            lst = self._bwd_list
             if not premasked:
                 self._add(lst, N.OP_RELU_MASK, [grad["t"].data_ptr(), out.data_ptr(), rows * Cc])
             g2, _ = bw_b2(grad, True, True, None)
@@ -730,12 +870,35 @@ class NativeReplica(Replica):
 
     weights_changed = refresh_shadow
 
-    def enqueue_step(self, x_ptr: int, y_ptr: int, fused_pull: bool = False) -> None:
+    def enqueue_region_input(self, x_ptr: int) -> None:
+        """Compact program: stage (cast + affine) the mini-batches of a whole region -- ``region_steps * B``
+        rows starting at ``x_ptr`` -- with one launch; steps then run with ``staged_row = j * B``."""
+        self.lib.dk_engine_set_slot(self.engine, SLOT_X, C.c_void_p(x_ptr))
+        self._run(self.L_in_region)
+
+    def enqueue_step(self, x_ptr: int, y_ptr: int, fused_pull: bool = False, comm: bool = False,
+                     staged_row: Optional[int] = None) -> None:
         """Enqueue one training step reading its batch from device pointers (graph-capturable).
         With ``fused_pull`` the first layer's weights are pulled from the parameter server inside
-        its forward GEMM (the caller pulls every other segment beforehand)."""
-        self.lib.dk_engine_set_slot(self.engine, SLOT_X, C.c_void_p(x_ptr))
+        its forward GEMM (the caller pulls every other segment beforehand).  Compact program: with
+        ``staged_row`` the batch was already staged by :meth:`enqueue_region_input`; ``comm`` makes the
+        fused backward-update kernel also perform the window-boundary exchange with the PS."""
         self.lib.dk_engine_set_slot(self.engine, SLOT_Y, C.c_void_p(y_ptr))
+        if self.compact:
+            xr = self._xb_region
+            if staged_row is None:
+                self.lib.dk_engine_set_slot(self.engine, SLOT_X, C.c_void_p(x_ptr))
+                self._run(self.L_in_step)
+                staged_row = 0
+            self.lib.dk_engine_set_slot(self.engine, SLOT_XB, C.c_void_p(xr.data_ptr() + staged_row * xr.shape[1] * 2))
+            if hasattr(self, "L_pad"):
+                self._run(self.L_pad)
+            self._run(self.L_step)
+            if comm and self.L_bwd_comm < 0:
+                raise RuntimeError("the replica was planned without a comm_spec")
+            self._run(self.L_bwd_comm if comm else self.L_bwd)
+            return
+        self.lib.dk_engine_set_slot(self.engine, SLOT_X, C.c_void_p(x_ptr))
         if hasattr(self, "L_pad"):
             self._run(self.L_pad)
         if fused_pull:
@@ -748,6 +911,9 @@ class NativeReplica(Replica):
 
     def enqueue_forward(self, x_ptr: int) -> None:
         self.lib.dk_engine_set_slot(self.engine, SLOT_X, C.c_void_p(x_ptr))
+        if self.compact:
+            self._run(self.L_in_step)
+            self.lib.dk_engine_set_slot(self.engine, SLOT_XB, C.c_void_p(self._xb_region.data_ptr()))
         if hasattr(self, "L_pad"):
             self._run(self.L_pad)
         self._run(self.L_fwd)
@@ -776,7 +942,7 @@ class NativeReplica(Replica):
 
     def train_on_batch(self, x, y):
         self._stage_inputs(x, y)
-        slot = int(self.step_counter.item()) % self.hist_slots
+        slot = (int(self.step_counter.item()) - self.step_base) % self.hist_slots
         self.hist[slot].zero_()
         self.enqueue_step(self._x_stage.data_ptr(), self._y_stage.data_ptr())
         self.iteration += 1

@@ -66,14 +66,14 @@ class FabricWorker:
     def __init__(self, model, optimizer, loss: str, algorithm: dict, region: FabricRegion, worker_id: int,
                  batch_size: int, device_index: int, in_dtype: str, input_affine=(1.0, 0.0), comm: str = "exchange",
                  strict: bool = False, dense_labels: bool = False, seed: int = 0, steps_per_graph: Optional[int] = None,
-                 trace: bool = False):
+                 trace: bool = False, shards=None, fuse_comm: bool = True):
         self.alg = dict(algorithm)
         self.tau = int(self.alg["window"])
         self.region = region
         # sharded parameter server: [(lo, hi, center_ptr)] slices of the flat center living on
         # different GPUs' HBM (lifts the single-GPU NVLink ingress ceiling; README TODO of the
         # reference: "multiple parameter servers").  None = the whole center is in `region`.
-        self.shards = None
+        self.shards = list(shards) if shards else None
         self.worker_id = int(worker_id)
         self.B = int(batch_size)
         self.comm = "commit_pull" if strict else comm
@@ -85,10 +85,29 @@ class FabricWorker:
             steps_per_graph = g * self.tau
         self.n_max = int(steps_per_graph)
         self.fused_pull = (comm == "fused_pull" and not strict and self.alg["kind"] in ("adag", "dynsgd"))
+        dev0 = torch.device("cuda", device_index)
+        self.last_update = torch.zeros(1, dtype=torch.int32, device=dev0)
+        self.scale_dev = torch.ones(1, dtype=torch.float32, device=dev0)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev0)
+        # Exchange fused into the backward pass (compact program): the step that closes a window runs the
+        # variant of the fused weight-gradient + optimizer kernel whose epilogue also commits the window's
+        # displacement to the PS with system-scope atomics and adopts the returned center -- no separate
+        # communication launch (the flat kernels of _comm_ops remain for every other case).
+        kind = self.alg["kind"]
+        comm_spec = None
+        if fuse_comm and not strict and self.comm == "exchange" and kind in ("adag", "downpour", "dynsgd", "aeasgd"):
+            model.build()
+            comm_spec = dict(mode=N.COMM_ELASTIC if kind == "aeasgd" else N.COMM_EXCHANGE,
+                             scale=1.0 / self.tau if kind == "adag" else 1.0, alpha=float(self.alg.get("alpha", 0.0)),
+                             scale_dev=self.scale_dev.data_ptr() if kind == "dynsgd" else 0,
+                             shards=self.shards or [(0, model.num_params, region.center_ptr)], ctrl=region.ctrl_ptr,
+                             worker=self.worker_id, last_update=self.last_update.data_ptr())
         self.rep = NativeReplica(model, optimizer, loss, batch_size, device_index, in_dtype=in_dtype,
                                  input_affine=input_affine, hist_slots=2 * self.n_max, dense_labels=dense_labels,
                                  seed=seed + 7 * worker_id,
-                                 pull_center_ptr=region.center_ptr if self.fused_pull else 0)
+                                 pull_center_ptr=region.center_ptr if self.fused_pull else 0,
+                                 region_steps=self.n_max, comm_spec=comm_spec)
+        self.fused_comm = self.rep.compact and self.rep.L_bwd_comm >= 0
         if self.fused_pull and self.rep.L_step_pull < 0:
             self.fused_pull = False
         if comm == "fused_pull" and not self.fused_pull:
@@ -99,9 +118,6 @@ class FabricWorker:
         self.lib = rep.lib
         self.F = rep._input_feats
         rep.ensure_snapshot()
-        self.last_update = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.scale_dev = torch.ones(1, dtype=torch.float32, device=dev)
-        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         if self.alg["kind"] == "eamsgd":
             self.mom = torch.zeros(rep.P, dtype=torch.float32, device=dev)
             self.wcopy = torch.zeros(rep.P, dtype=torch.float32, device=dev)
@@ -140,6 +156,8 @@ class FabricWorker:
         return C.c_void_p(N.current_stream())
 
     def set_shards(self, shards) -> None:
+        if self.fused_comm:
+            raise RuntimeError("pass shards= to the constructor: the fused exchange is planned with them")
         self.shards = list(shards)
 
     def _comm_ops(self) -> int:
@@ -204,7 +222,7 @@ class FabricWorker:
                     "pull_rest")
         return len(ranges)
 
-    def _step(self, parity: int, j: int, fused_pull: bool = False) -> int:
+    def _step(self, parity: int, j: int, fused_pull: bool = False, comm: bool = False) -> int:
         rep = self.rep
         xs, ys = self.x_stage[parity], self.y_stage[parity]
         x_ptr = xs.data_ptr() + j * self.B * self.F * xs.element_size()
@@ -216,7 +234,10 @@ class FabricWorker:
                                            rep.Wb.data_ptr(), rep.P, float(self.alg["momentum"]), self._stream()),
                     "eamsgd_pre")
             extra += 1
-        rep.enqueue_step(x_ptr, y_ptr, fused_pull=fused_pull)
+        if rep.compact:   # the region's batches were staged by one launch (enqueue_region_input)
+            rep.enqueue_step(0, y_ptr, comm=comm, staged_row=j * self.B)
+        else:
+            rep.enqueue_step(x_ptr, y_ptr, fused_pull=fused_pull)
         if self.alg["kind"] == "eamsgd":
             N.check(self.lib.dk_eamsgd_post(rep.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(),
                                             rep.Wb.data_ptr(), rep.P, float(self.alg["eta"]), self._stream()),
@@ -234,17 +255,33 @@ class FabricWorker:
         seg.zero_()
         pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd")
         kernels = exchanges = 0
+        if rep.compact:
+            before = rep.launches()
+            rep.enqueue_region_input(self.x_stage[parity].data_ptr())
+            kernels += rep.launches() - before
+        fused_before = False   # the previous step's fused update already did this boundary's exchange
         for j in range(n):
             it = phase + j + 1                      # iteration number relative to the last window boundary
             boundary = it % tau == 0
             first_of_window = (phase + j) % tau == 0
             if self.fused_pull and first_of_window:
                 kernels += self._pull_rest()
-            if pre_batch and boundary:
+            if pre_batch and boundary and not fused_before:
                 kernels += self._comm_ops()
                 exchanges += 1
-            kernels += self._step(parity, j, fused_pull=self.fused_pull and first_of_window)
-            if not pre_batch and boundary:
+            # exchange fused into this step's backward-update kernel: the step that closes the window
+            # (ADAG / DynSGD: check after the batch) or the one before the boundary batch (DOWNPOUR / AEASGD:
+            # check before the batch, i.e. right after the previous step's update)
+            fuse = self.fused_comm and (((it + 1) % tau == 0 and j + 1 < n) if pre_batch else boundary)
+            if fuse and self.alg["kind"] == "dynsgd":
+                N.check(self.lib.dk_ps_ticket(C.c_void_p(self.region.ctrl_ptr), self.last_update.data_ptr(),
+                                              self.scale_dev.data_ptr(), self._stream()), "ticket")
+                kernels += 1
+            kernels += self._step(parity, j, fused_pull=self.fused_pull and first_of_window, comm=fuse)
+            if fuse:
+                exchanges += 1
+            fused_before = fuse and pre_batch
+            if not pre_batch and boundary and not fuse:
                 kernels += self._comm_ops()
                 exchanges += 1
         self.hist_host[parity][:n].copy_(seg, non_blocking=True)
@@ -268,6 +305,8 @@ class FabricWorker:
         saved = (rep.W.clone(), rep.W1.clone(), rep.step_counter.clone(),
                  None if rep.opt.s0 is None else rep.opt.s0.clone(), None if rep.opt.s1 is None else rep.opt.s1.clone())
         with torch.cuda.stream(self.compute):
+            if rep.compact:
+                rep.enqueue_region_input(self.x_stage[0].data_ptr())
             self.kernels_per_step = self._step(0, 0)
         self.compute.synchronize()
         rep.W.copy_(saved[0]); rep.W1.copy_(saved[1]); rep.step_counter.copy_(saved[2])
@@ -316,7 +355,10 @@ class FabricWorker:
 
     def comm_kernels(self) -> int:
         """Kernels of one window-boundary exchange."""
-        return max(0, self.kernels_per_window - self.tau * self.kernels_per_step) if self.kernels_per_window else 0
+        if not self.kernels_per_window:
+            return 0
+        staged = 1 if self.rep.compact else 0   # the region's input-stage launch is not a comm kernel
+        return max(0, self.kernels_per_window - self.tau * self.kernels_per_step - staged)
 
     # -- host loop ----------------------------------------------------------------------------------
     def _collect(self, parity: int) -> None:
@@ -374,7 +416,7 @@ class FabricWorker:
     def _realign(self, parity: int) -> None:
         """Point the device step counter at the history slots of this parity (short regions and eager
         tail steps advance it by less than ``n_max``); it stays monotonic (Adam bias correction)."""
-        self.rep.step_counter.fill_(self.replays * self.n_max)  # replays & 1 == parity
+        self.rep.step_counter.fill_(self.replays * self.n_max + self.rep.step_base)  # replays & 1 == parity
 
     def trace_start(self) -> None:
         """Mark the beginning of the device-time trace on the compute stream."""
@@ -827,7 +869,7 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
                 raise UnsupportedByNativeEngine("custom exchange rule")
             worker = FabricWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid, trainer.batch_size,
                                   local, in_dtype, affine, steps_per_graph=getattr(trainer, "steps_per_graph", None),
-                                  trace=trace, **wkw)
+                                  trace=trace, shards=shards, fuse_comm=getattr(trainer, "fuse_comm", True), **wkw)
         except UnsupportedByNativeEngine as exc:
             import warnings
 
@@ -835,8 +877,6 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
                           "autograd executor (cuBLAS / cuDNN), the parameter-server program stays in-kernel")
             worker = FabricEagerWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid,
                                        trainer.batch_size, local, in_dtype, affine, **wkw)
-        if shards and isinstance(worker, FabricWorker):
-            worker.set_shards(shards)
         worker.initial_pull()
         worker.capture()
         static = getattr(trainer, "shard_mode", "dynamic" if trainer.parallelism_factor > 1 else "static") == "static"

@@ -52,7 +52,7 @@ def test_native_gradients_match_autograd(maker, in_shape, implicit, monkeypatch)
     lref, aref = ref.train_on_batch(x, y)
     gref = ref.W.grad.clone()
     nat = NativeReplica(model, {"class_name": "sgd", "config": {"lr": 0.0}}, "categorical_crossentropy", B, 0,
-                        in_dtype="f32")
+                        in_dtype="f32", compact=False)  # the compact program keeps no gradient buffer to inspect
     lnat, anat = nat.train_on_batch(x, y.to(torch.int32))
     torch.cuda.synchronize()
     assert abs(lnat - lref) < 0.02 * max(1.0, abs(lref)), (lnat, lref)
@@ -245,7 +245,58 @@ def test_fused_pull_mode_matches_exchange():
         stats.append(t.fabric_stats[0])
     rel = float((outs[0] - outs[1]).norm() / outs[0].norm())
     assert rel < 0.01, rel  # tf32 first layer in the pull step vs bf16: tiny drift only
-    assert stats[1]["kernels_per_window"] == stats[0]["kernels_per_window"] + 1  # commit + pull_rest vs exchange
+    # exchange mode runs the compact program (exchange fused into the backward-update kernel: no comm launch)
+    assert stats[0]["kernels_per_window"] < stats[1]["kernels_per_window"]
+
+
+@pytest.mark.parametrize("B,optimizer", [(64, "adam"), (128, {"class_name": "sgd", "config": {"lr": 0.05, "momentum": 0.9}}),
+                                         (32, "adagrad"), (256, "rmsprop")])
+def test_compact_program_matches_classic_program(B, optimizer):
+    """Small-batch program (region input stage, narrow tiles, ONE fused wgrad + bias-grad + optimizer kernel)
+    against the wide-batch program (separate wgrad / colsum / optimizer kernels): same steps, same weights."""
+    from distkeras_b200.parallel.engine import NativeReplica
+
+    torch.manual_seed(0)
+    xs = torch.randint(0, 256, (6, B, 64), dtype=torch.uint8)
+    ys = torch.randint(0, 10, (6, B)).to(torch.int32)
+    out = {}
+    for compact in (False, True):
+        rep = NativeReplica(_mlp(3, dropout=True), optimizer, "categorical_crossentropy", B, 0, in_dtype="u8",
+                            input_affine=(1 / 255.0, 0.0), compact=compact, seed=11)
+        assert rep.compact == compact
+        hist = [rep.train_on_batch(xs[i], ys[i]) for i in range(6)]
+        torch.cuda.synchronize()
+        out[compact] = (rep.W.cpu().clone(), rep.Wb.float().cpu().clone(), hist, rep.opt.s0.cpu().clone())
+        rep.close()
+    w0, w1 = out[False][0], out[True][0]
+    assert float((w0 - w1).norm() / w0.norm()) < 2e-3
+    assert torch.allclose(out[True][1], w1, atol=1e-2, rtol=1e-2)          # bf16 shadow follows the master
+    assert float((out[False][3] - out[True][3]).norm() / (out[False][3].norm() + 1e-12)) < 2e-2
+    for (l0, a0), (l1, a1) in zip(out[False][2], out[True][2]):
+        assert abs(l0 - l1) < 0.02 * max(1.0, abs(l0)) and abs(a0 - a1) <= 4.0 / B
+
+
+@pytest.mark.parametrize("name,kw", [("ADAG", dict(communication_window=4)), ("DOWNPOUR", dict(communication_window=3)),
+                                     ("DynSGD", dict(communication_window=3)),
+                                     ("AEASGD", dict(communication_window=4, rho=1.0, learning_rate=0.1))])
+def test_exchange_fused_into_backward_matches_flat_kernels(name, kw):
+    """The window-boundary exchange done by the epilogue of the fused backward-update kernel (no comm launch)
+    gives the same center / history as the separate exchange kernels."""
+    from distkeras_b200 import trainers
+    from distkeras_b200.data import Dataset
+
+    torch.manual_seed(0)
+    ds = Dataset({"features": torch.rand(1536, 64), "label": torch.randint(0, 10, (1536,)).to(torch.int32)})
+    outs = []
+    for fuse in (False, True):
+        t = getattr(trainers, name)(_mlp(0), {"class_name": "sgd", "config": {"lr": 0.05}}, "categorical_crossentropy",
+                                    num_workers=1, batch_size=64, **kw)
+        t.backend, t.fuse_comm = "fabric", fuse
+        outs.append((t.train(ds).get_flat_weights().cpu(), t.num_updates(), t.fabric_stats[0], t.get_history()))
+    assert outs[0][1] == outs[1][1]                                   # same number of commits at the PS
+    assert float((outs[0][0] - outs[1][0]).norm() / outs[0][0].norm()) < 1e-3
+    assert outs[1][2]["kernels_per_window"] < outs[0][2]["kernels_per_window"]
+    assert abs(outs[0][3][-1]["history"][0] - outs[1][3][-1]["history"][0]) < 0.02
 
 
 def _needs_gpus(n):

@@ -438,3 +438,80 @@ def test_implicit_gemm_conv_wgrad_experimental(N, B, H, Cin, Cout, k, stride, pa
     F.conv2d(x.float().permute(0, 3, 1, 2), w, None, stride=stride, padding=pad).backward(dz.float().permute(0, 3, 1, 2))
     ref = w.grad.permute(0, 2, 3, 1).reshape(Cout, K)  # [Cout, (kh, kw, c)]
     assert torch.allclose(dw, ref, atol=2e-3 * rows ** 0.5, rtol=1e-3)
+
+
+@pytest.mark.parametrize("B,comm", [(64, 0), (96, 0), (16, 1), (128, 1), (64, 2)])
+@pytest.mark.parametrize("opt", ["adam", "sgd"])
+def test_fused_dense_backward_update_kernel(N, B, comm, opt):
+    """dk_bwd_update: dW = dZ^T X (tcgen05, MN-major operands), db via the ones-tile MMA, optimizer rule in the
+    epilogue, bf16 shadow, and (comm != 0) the PS exchange -- against plain fp32 PyTorch."""
+    torch.manual_seed(5)
+    dims = [(1000, 784), (200, 1000), (10, 200)]              # (n_out, k_in) of the MNIST MLP
+    P = sum(o * i + o for o, i in dims)
+    W = torch.randn(P, device="cuda") * 0.05
+    W1 = W - torch.randn(P, device="cuda") * 0.01            # last pulled center
+    center = W1 + torch.randn(P, device="cuda") * 0.02       # other workers moved it meanwhile
+    s0, s1 = torch.rand(P, device="cuda") * 0.01, torch.rand(P, device="cuda") * 0.01
+    Wb = torch.zeros(P, dtype=torch.bfloat16, device="cuda")
+    step = torch.tensor([3], dtype=torch.int32, device="cuda")
+    done = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ctrl = torch.zeros(N.CTRL_WORDS, dtype=torch.int32, device="cuda")
+    last = torch.zeros(1, dtype=torch.int32, device="cuda")
+    kind = N.OPT_KINDS[opt]
+    lr, p0, p1, eps = (0.001, 0.9, 0.999, 1e-7) if opt == "adam" else (0.05, 0.0, 0.0, 0.0)
+    d = N.BwdUpdateDesc()
+    d.nlayers, d.batch = len(dims), B
+    keep, off, ref = [], 0, {}
+    Wr, s0r, s1r = W.clone(), s0.clone(), s1.clone()
+    for i, (o, k) in enumerate(dims):
+        ldz = (o + 7) // 8 * 8
+        dz = torch.zeros(B, ldz, dtype=torch.bfloat16, device="cuda")
+        dz[:, :o] = bf(torch.randn(B, o, device="cuda") * 0.1)
+        x = bf(torch.randn(B, k, device="cuda"))
+        keep += [dz, x]
+        L = d.layer[i]
+        L.dz, L.lddz, L.x, L.ldx, L.x_slot = dz.data_ptr(), ldz, x.data_ptr(), k, -1
+        L.n_out, L.k_in, L.w_off, L.b_off, L.wb_pad, L.ldwb_pad = o, k, off, off + o * k, None, 0
+        ref[i] = (dz[:, :o].float().t() @ x.float(), dz[:, :o].float().sum(0), off, o, k)
+        off += o * k + o
+    d.w, d.s0, d.s1, d.w1, d.wb = W.data_ptr(), s0.data_ptr() if opt == "adam" else None, \
+        s1.data_ptr() if opt == "adam" else None, W1.data_ptr(), Wb.data_ptr()
+    d.opt_kind, d.lr, d.p0, d.p1, d.eps, d.decay, d.nesterov = kind, lr, p0, p1, eps, 0.0, 0
+    d.step, d.done_counter, d.step_inc = step.data_ptr(), done.data_ptr(), 1
+    d.comm_mode, d.comm_scale, d.alpha, d.nshards, d.shard_per = comm, 0.25, 0.3, 1, P
+    d.shard_center[0] = center.data_ptr()
+    d.ctrl, d.worker, d.last_update = ctrl.data_ptr(), 2, last.data_ptr()
+    W1_0, center_0 = W1.clone(), center.clone()
+    N.check(N.lib().dk_bwd_update(C.byref(d), st()), "dk_bwd_update")
+    torch.cuda.synchronize()
+    # reference: gradient, optimizer rule at t = 3, then the exchange
+    G = torch.zeros(P, device="cuda")
+    for i, (gw, gb, o_, o, k) in ref.items():
+        G[o_:o_ + o * k] = gw.reshape(-1)
+        G[o_ + o * k:o_ + o * k + o] = gb
+    if opt == "adam":
+        s0r = p0 * s0r + (1 - p0) * G
+        s1r = p1 * s1r + (1 - p1) * G * G
+        corr = (1 - p1 ** 3) ** 0.5 / (1 - p0 ** 3)
+        Wr = Wr - lr * corr * s0r / (s1r.sqrt() + eps)
+    else:
+        Wr = Wr - lr * G
+    if comm == 1:
+        r = (Wr - W1_0) * 0.25
+        center_r = center_0 + r
+        Wr = center_r.clone()
+        assert torch.allclose(center, center_r, atol=1e-5) and torch.allclose(W1, center_r, atol=1e-5)
+        assert int(ctrl[N.CTRL_NUM_UPDATES]) == 1 and int(ctrl[N.CTRL_HEARTBEAT + 2]) == 1 and int(last) == 1
+    elif comm == 2:
+        E = 0.3 * (Wr - center_0)
+        Wr = Wr - E
+        assert torch.allclose(center, center_0 + E, atol=1e-5)
+    else:
+        assert torch.equal(center, center_0)
+    # bf16 operands, fp32 accumulation over B <= 128 terms: tight tolerances
+    tol = 5e-3 if opt == "adam" else 2e-4    # Adam normalises tiny gradients: rounding of g shows in the step
+    assert torch.allclose(W, Wr, atol=tol, rtol=1e-3), float((W - Wr).abs().max())
+    if opt == "adam":
+        assert torch.allclose(s0, s0r, atol=1e-4, rtol=1e-3) and torch.allclose(s1, s1r, atol=1e-5, rtol=1e-2)
+    assert torch.allclose(Wb.float(), W, atol=1e-2, rtol=1e-2)
+    assert int(step) == 4 and int(done) == 0

@@ -12,7 +12,8 @@ from distkeras_b200 import _native as N
 from distkeras_b200.models import ZOO
 from distkeras_b200.parallel import engine as eng
 
-GPU_ONLY = ("dk_engine_add_gemm", "dk_engine_add_gemm_pull", "dk_engine_add_conv_gemm", "dk_engine_add_conv_wgrad")
+GPU_ONLY = ("dk_engine_add_gemm", "dk_engine_add_gemm_pull", "dk_engine_add_conv_gemm", "dk_engine_add_conv_wgrad",
+            "dk_engine_add_gemm_slot", "dk_engine_add_bwd_update")
 OP_NAMES = {v: k for k, v in vars(N).items() if k.startswith("OP_") and isinstance(v, int)}
 
 
@@ -40,7 +41,7 @@ class RecordingLib:
 
 
 def _lower(model_name, batch, monkeypatch, native_lib, **env):
-    for k in ("DK_IMPLICIT_CONV", "DK_IMPLICIT_WGRAD", "DK_SIDE_STREAMS", "DK_FUSED_HEAD"):
+    for k in ("DK_IMPLICIT_CONV", "DK_IMPLICIT_WGRAD", "DK_SIDE_STREAMS", "DK_FUSED_HEAD", "DK_COMPACT", "DK_COMPACT_MAX_BATCH"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -56,7 +57,17 @@ def _lower(model_name, batch, monkeypatch, native_lib, **env):
     return lib, sizes
 
 
-@pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 256), ("higgs_mlp", 128), ("mnist_convnet", 32),
+def test_compact_lowering_of_small_batch_mlp(monkeypatch, native_lib):
+    """Batch <= 256 dense stacks: region-level input stage, slot-fed first GEMM, ONE fused backward-update op."""
+    lib, sizes = _lower("mnist_mlp", 64, monkeypatch, native_lib)
+    assert lib.calls["dk_engine_add_bwd_update"] == 1 and lib.calls["dk_engine_add_gemm_slot"] == 2  # L_step + L_fwd
+    assert lib.ops["OP_OPTIM"] == 0 and lib.ops["OP_COLSUM"] == 0 and lib.ops["OP_MEMSET"] == 0
+    assert lib.ops["OP_INPUT"] == 2 and lib.ops["OP_HEAD"] == 1
+    # L_step: fwd1 (slot-fed), fwd2 | L_bwd: head, dgrad2, fused update | L_fwd: fwd1, fwd2, head GEMM, softmax
+    assert lib.calls["dk_engine_add_gemm"] == 4 and sizes["L_bwd"] == 1 and sizes["L_fwd"] == 1
+
+
+@pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 512), ("higgs_mlp", 128), ("mnist_convnet", 32),
                                               ("cifar10_cnn", 32), ("resnet18", 4)])
 def test_default_lowering(model_name, batch, monkeypatch, native_lib):
     lib, sizes = _lower(model_name, batch, monkeypatch, native_lib)
@@ -74,7 +85,7 @@ def test_default_lowering(model_name, batch, monkeypatch, native_lib):
 @pytest.mark.parametrize("env", [dict(DK_FUSED_HEAD="0"), dict(DK_SIDE_STREAMS="1"), dict(DK_IMPLICIT_CONV="1"),
                                  dict(DK_IMPLICIT_CONV="1", DK_IMPLICIT_WGRAD="1")],
                          ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
-@pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 256), ("cifar10_cnn", 32), ("resnet18", 4)])
+@pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 512), ("cifar10_cnn", 32), ("resnet18", 4)])
 def test_lowering_under_every_switch(model_name, batch, env, monkeypatch, native_lib):
     lib, sizes = _lower(model_name, batch, monkeypatch, native_lib, **env)
     assert sizes["L_step"] > 0 and sizes["L_bwd"] > 0
