@@ -38,12 +38,23 @@ namespace dk {
 
 constexpr int kBwdBlockM = 128;
 constexpr int kBwdBN = 64;
-constexpr int kBwdThreads = 192;
-constexpr int kBwdStages = 3;
+constexpr int kBwdThreads = 320;  // producer, MMA issuer, 8 epilogue warps
+constexpr int kBwdStages = 2;  // GEMM-K = the mini-batch: one or two 64-row k-blocks in the compact regime
+
+// TMA descriptors of a layer's parameter state (device memory, written once at plan time): the fp32 master,
+// optimizer state and last-pulled-center tiles are LOADED as [128 x 32] boxes while the MMA runs, and the
+// updated tiles (and the bf16 shadow) are STORED back as [32-row] boxes -- the optimizer never issues a
+// global load or store of its own.
+enum { kStW = 0, kStS0 = 1, kStS1 = 2, kStW1 = 3, kStWb = 4 };
+struct StateMaps {
+  alignas(64) CUtensorMap ld[4];  // W, s0, s1, W1: fp32 [n_out, k_in], box 32 cols x 128 rows, SWIZZLE_128B
+  alignas(64) CUtensorMap st[5];  // W, s0, s1, W1: box 32 x 32; Wb: bf16 box 64 cols x 32 rows
+};
 
 struct BwdLayerDev {
   alignas(64) CUtensorMap ta;  // dZ [batch, n_out] as an MN-major A operand (64 x 64 boxes)
   alignas(64) CUtensorMap tb;  // X  [batch, k_in]  as an MN-major B operand
+  const StateMaps* maps;       // nullptr for layers on the element-wise path
   long w_off, b_off;
   __nv_bfloat16* wb_pad;
   int ldwb_pad;
@@ -73,6 +84,7 @@ struct BwdRecord {
   BwdUpdateDev dev;
   const void* x[DK_BWD_MAX_LAYERS];
   long ldx[DK_BWD_MAX_LAYERS];
+  StateMaps* maps_dev;  // device array [nlayers]
   int total_tiles;
 };
 
@@ -123,12 +135,13 @@ __device__ __forceinline__ float ld_sys_f(const float* addr) {
 }
 
 // one parameter: optimizer rule (+ bf16 shadow when no exchange follows)
+template <int KIND>
 __device__ __forceinline__ void update_scalar(const BwdUpdateDev& p, long idx, float g, float lr, float corr,
                                               bool write_shadow) {
   float w = p.w[idx];
   float s0 = p.s0 != nullptr ? p.s0[idx] : 0.f;
   float s1 = p.s1 != nullptr ? p.s1[idx] : 0.f;
-  optim_update_rt(p.opt.kind, w, g, s0, s1, lr, p.opt, corr);
+  optim_update<KIND>(w, g, s0, s1, lr, p.opt, corr);
   p.w[idx] = w;
   if (p.s0 != nullptr) p.s0[idx] = s0;
   if (p.s1 != nullptr) p.s1[idx] = s1;
@@ -153,6 +166,200 @@ __device__ __forceinline__ float exchange_scalar(const BwdUpdateDev& p, long idx
   return w;
 }
 
+// Shared-memory plan (after the 1024-byte alignment):
+//   [0, kStagesBytes)        TMA <-> MMA pipeline (A 16 KB + B 8 KB per stage); idle once the accumulator is
+//                            complete, the first 32 KB are then reused as the 8 epilogue warps' 4 KB gradient slots
+//   ones (2 KB)              bf16 1.0 tile: B operand of the bias-gradient MMA
+//   state tiles              W, s0, s1, W1: two [128 rows x 128 B] swizzled half-tiles each (32 KB per array)
+//   Wb tile (16 KB)          [128 rows x 128 B] bf16
+constexpr int kBwdStagesBytes = kBwdStages * (kBwdBlockM * 128 + kBwdBN * 128);
+constexpr int kBwdTileBytes = 2 * kBwdBlockM * 128;  // one fp32 state array of a 128 x 64 tile
+constexpr int kBwdSmemUse = kBwdStagesBytes + 2048 + 4 * kBwdTileBytes + kBwdBlockM * 128 + 256;
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Epilogue of one (quarter, half) = 32 rows x 32 columns slice of the accumulator tile, executed by one warp
+// with lane = row (the TMEM-native mapping).  The parameter state of the slice is already in shared memory
+// (TMA, 128-byte swizzle: lane = row accesses are bank-conflict free); the loop over the slice's eight 16-byte
+// column groups is NOT unrolled -- these kernels run once per step, so straight-line code is paid for in
+// instruction-cache misses.  On a window boundary the slice is then exchanged with the parameter server with
+// lane = column-group (coalesced 128-byte runs per row over NVLink), all 8 requests of a lane in flight.
+template <int KIND>
+__device__ __forceinline__ void bwd_epilogue(const BwdUpdateDev& p, const BwdLayerDev& ly, const int m0, const int n0,
+                                             const int quarter, const int half, const int lane, const uint32_t tmem_base,
+                                             const uint32_t gslot, const uint32_t tiles, const uint32_t wb_tile,
+                                             uint64_t* state_bar, const bool has_bias) {
+  constexpr bool kS0 = KIND != DK_OPT_SGD;
+  constexpr bool kS1 = KIND == DK_OPT_ADAM || KIND == DK_OPT_ADADELTA || KIND == DK_OPT_ADAMAX;
+  const int t = max(*p.step, 1);
+  float lr = p.opt.lr, corr = 1.f;
+  if (p.opt.decay > 0.f) lr = __fdividef(lr, 1.f + p.opt.decay * static_cast<float>(t - 1));
+  if constexpr (KIND == DK_OPT_ADAM)
+    corr = __fdividef(sqrtf(1.f - __powf(p.opt.p1, static_cast<float>(t))), 1.f - __powf(p.opt.p0, static_cast<float>(t)));
+  if constexpr (KIND == DK_OPT_ADAMAX) corr = __fdividef(1.f, 1.f - __powf(p.opt.p0, static_cast<float>(t)));
+  const bool comm = p.comm_mode != DK_COMM_NONE;
+  const float cs = comm ? (p.scale_dev != nullptr ? p.comm_scale * __ldg(p.scale_dev) : p.comm_scale) : 0.f;
+  const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+  const int nbase = n0 + half * 32;                  // first column of this warp's slice
+  const int mbase = m0 + quarter * 32;               // first row
+  const bool slice_live = nbase < ly.k_in;
+  if (slice_live) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(trow + half * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4)                   // row `lane`, 16-byte chunk c4 -> swizzled slot
+      st_shared_v4(gslot + lane * 128 + ((c4 ^ (lane & 7)) << 4), r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
+    __syncwarp();
+  }
+  if (ly.maps != nullptr) {
+    // =============================== TMA-fed path (k_in % 4 == 0) ===============================
+    const uint32_t rowoff = (quarter * 32 + lane) * 128;          // this lane's row inside a half-tile
+    const uint32_t tW = tiles + half * (kBwdBlockM * 128);
+    const uint32_t tS0 = tW + kBwdTileBytes, tS1 = tW + 2 * kBwdTileBytes, tW1 = tW + 3 * kBwdTileBytes;
+    if (slice_live) {
+      mbar_wait(state_bar, 0);                                     // the state tiles have landed
+#pragma unroll 1
+      for (int jj = 0; jj < 4; ++jj) {                             // two 16-byte column groups per trip
+        uint32_t packed[4];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int j = 2 * jj + h2;
+          const uint32_t off = rowoff + ((j ^ (lane & 7)) << 4);
+          const uint4 gq = ld_shared_v4(gslot + lane * 128 + ((j ^ (lane & 7)) << 4));
+          uint4 wq = ld_shared_v4(tW + off);
+          uint4 aq = kS0 ? ld_shared_v4(tS0 + off) : make_uint4(0, 0, 0, 0);
+          uint4 bq = kS1 ? ld_shared_v4(tS1 + off) : make_uint4(0, 0, 0, 0);
+          float w[4] = {__uint_as_float(wq.x), __uint_as_float(wq.y), __uint_as_float(wq.z), __uint_as_float(wq.w)};
+          float a[4] = {__uint_as_float(aq.x), __uint_as_float(aq.y), __uint_as_float(aq.z), __uint_as_float(aq.w)};
+          float b[4] = {__uint_as_float(bq.x), __uint_as_float(bq.y), __uint_as_float(bq.z), __uint_as_float(bq.w)};
+          const float g[4] = {__uint_as_float(gq.x), __uint_as_float(gq.y), __uint_as_float(gq.z), __uint_as_float(gq.w)};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) optim_update<KIND>(w[e], g[e], a[e], b[e], lr, p.opt, corr);
+          st_shared_v4(tW + off, __float_as_uint(w[0]), __float_as_uint(w[1]), __float_as_uint(w[2]), __float_as_uint(w[3]));
+          if constexpr (kS0)
+            st_shared_v4(tS0 + off, __float_as_uint(a[0]), __float_as_uint(a[1]), __float_as_uint(a[2]), __float_as_uint(a[3]));
+          if constexpr (kS1)
+            st_shared_v4(tS1 + off, __float_as_uint(b[0]), __float_as_uint(b[1]), __float_as_uint(b[2]), __float_as_uint(b[3]));
+          packed[2 * h2] = pack_bf16x2(w[0], w[1]);
+          packed[2 * h2 + 1] = pack_bf16x2(w[2], w[3]);
+        }
+        // 8 bf16 = 16-byte chunk (4 half + jj) of this row of the shadow tile
+        st_shared_v4(wb_tile + rowoff + (((4 * half + jj) ^ (lane & 7)) << 4), packed[0], packed[1], packed[2], packed[3]);
+      }
+      if (comm) {
+        // ---- window boundary: push the window's displacement, adopt the center ----
+        __syncwarp();
+        const int sub = lane >> 3, c4 = lane & 7;     // lane = 16-byte column group, 4 rows per warp access
+        const int n = nbase + 4 * c4;
+        const bool col_ok = n < ly.k_in;
+        float4 x[8], y[8];
+        bool ok[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = quarter * 32 + 4 * i + sub;
+          ok[i] = col_ok && (m0 + row) < ly.n_out;
+          const uint32_t off = row * 128 + ((c4 ^ (row & 7)) << 4);
+          const uint4 q = ld_shared_v4(tW + off);     // updated W
+          x[i] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+          y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.comm_mode == DK_COMM_EXCHANGE) {
+            const uint4 b = ld_shared_v4(tW1 + off);  // last pulled center
+            x[i] = make_float4((x[i].x - __uint_as_float(b.x)) * cs, (x[i].y - __uint_as_float(b.y)) * cs,
+                               (x[i].z - __uint_as_float(b.z)) * cs, (x[i].w - __uint_as_float(b.w)) * cs);  // residual
+          }
+        }
+        if (p.comm_mode == DK_COMM_EXCHANGE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (ok[i]) y[i] = atom_add_v4_sys_f(center_of(p, ly.w_off + static_cast<long>(mbase + 4 * i + sub) * ly.k_in + n), x[i]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            y[i].x += x[i].x; y[i].y += x[i].y; y[i].z += x[i].z; y[i].w += x[i].w;   // new center = new W = new W1
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (ok[i]) y[i] = ld_sys_v4_f(center_of(p, ly.w_off + static_cast<long>(mbase + 4 * i + sub) * ly.k_in + n));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!ok[i]) continue;
+            const float4 e = make_float4(p.alpha * (x[i].x - y[i].x), p.alpha * (x[i].y - y[i].y), p.alpha * (x[i].z - y[i].z),
+                                         p.alpha * (x[i].w - y[i].w));
+            red_add_v4_sys_f(center_of(p, ly.w_off + static_cast<long>(mbase + 4 * i + sub) * ly.k_in + n), e);
+            y[i] = make_float4(x[i].x - e.x, x[i].y - e.y, x[i].z - e.z, x[i].w - e.w);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = quarter * 32 + 4 * i + sub;
+          const uint32_t off = row * 128 + ((c4 ^ (row & 7)) << 4);
+          st_shared_v4(tW + off, __float_as_uint(y[i].x), __float_as_uint(y[i].y), __float_as_uint(y[i].z), __float_as_uint(y[i].w));
+          if (p.comm_mode == DK_COMM_EXCHANGE)
+            st_shared_v4(tW1 + off, __float_as_uint(y[i].x), __float_as_uint(y[i].y), __float_as_uint(y[i].z),
+                         __float_as_uint(y[i].w));
+          // bf16 shadow: 4 values = 8 bytes at byte (64 half + 8 c4) of the row: chunk (4 half + c4 / 2), half (c4 & 1)
+          const uint32_t wboff = row * 128 + (((4 * half + (c4 >> 1)) ^ (row & 7)) << 4) + ((c4 & 1) << 3);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(wb_tile + wboff), "r"(pack_bf16x2(y[i].x, y[i].y)),
+                       "r"(pack_bf16x2(y[i].z, y[i].w))
+                       : "memory");
+        }
+      }
+      // ---- write the slice back: TMA stores out of the swizzled tiles (clipped at the matrix edge) ----
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t sub_off = quarter * 4096;
+        tma_store_2d_addr(&ly.maps->st[kStW], tW + sub_off, nbase, mbase);
+        if constexpr (kS0) tma_store_2d_addr(&ly.maps->st[kStS0], tS0 + sub_off, nbase, mbase);
+        if constexpr (kS1) tma_store_2d_addr(&ly.maps->st[kStS1], tS1 + sub_off, nbase, mbase);
+        if (p.comm_mode == DK_COMM_EXCHANGE) tma_store_2d_addr(&ly.maps->st[kStW1], tW1 + sub_off, nbase, mbase);
+      }
+    }
+    // the two halves of a quarter fill one [32 x 128 B] box of the bf16 shadow tile: pair barrier, one store
+    named_bar_sync(1 + quarter, 64);
+    if (half == 0 && lane == 0 && n0 < ly.k_in) tma_store_2d_addr(&ly.maps->st[kStWb], wb_tile + quarter * 4096, n0, mbase);
+    if (lane == 0) {
+      tma_store_commit();
+      tma_store_wait_read<0>();
+    }
+  } else if (slice_live) {
+    // ====== element-wise path (k_in % 4 != 0, e.g. the 30-feature Higgs input layer): lane = column group ======
+    const int sub = lane >> 3, c4 = lane & 7;
+    const int n = nbase + 4 * c4;
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      const int row = 4 * i + sub;
+      const int m = mbase + row;
+      if (m >= ly.n_out) continue;
+      const uint4 q = ld_shared_v4(gslot + row * 128 + ((c4 ^ (row & 7)) << 4));
+      const float gq[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        if (n + j >= ly.k_in) break;
+        const long idx = ly.w_off + static_cast<long>(m) * ly.k_in + n + j;
+        update_scalar<KIND>(p, idx, gq[j], lr, corr, !comm);
+        float wn = p.w[idx];
+        if (comm) wn = exchange_scalar(p, idx, cs);
+        if (ly.wb_pad != nullptr) ly.wb_pad[static_cast<long>(m) * ly.ldwb_pad + n + j] = __float2bfloat16_rn(wn);
+      }
+    }
+  }
+  // ---- bias: its gradient is column 0 of the ones-tile accumulator; lane = row, contiguous in memory ----
+  if (has_bias && half == 0) {
+    uint32_t r[16];
+    tmem_ld_32x32b_x16(trow + kBwdBN, r);
+    tmem_ld_wait();
+    const int m = mbase + lane;
+    if (m < ly.n_out) {
+      update_scalar<KIND>(p, ly.b_off + m, __uint_as_float(r[0]), lr, corr, !comm);
+      if (comm) exchange_scalar(p, ly.b_off + m, cs);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBwdThreads, 1)
 dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
   constexpr int BN = kBwdBN;
@@ -165,11 +372,14 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* ones = smem + kBwdStages * kStageBytes;  // 16 rows x 128 B of bf16 1.0 (layout-invariant)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + 2048);
+  uint8_t* ones = smem + kBwdStagesBytes;            // 16 rows x 128 B of bf16 1.0 (layout-invariant)
+  uint8_t* tiles = ones + 2048;                      // W, s0, s1, W1 state tiles
+  uint8_t* wb_tile = tiles + 4 * kBwdTileBytes;      // bf16 shadow tile
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(wb_tile + kBwdBlockM * 128);
   uint64_t* empty_bar = full_bar + kBwdStages;
   uint64_t* tmem_full_bar = empty_bar + kBwdStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* state_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(state_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,6 +391,10 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
   const int n0 = (local % ly.tiles_n) * BN;
   const bool has_bias = ly.b_off >= 0 && n0 == 0;
   const int num_kb = (p.batch + 63) / 64;
+  const int kind = p.opt.kind;
+  const bool use_s0 = kind != DK_OPT_SGD;
+  const bool use_s1 = kind == DK_OPT_ADAM || kind == DK_OPT_ADADELTA || kind == DK_OPT_ADAMAX;
+  const bool use_w1 = p.comm_mode == DK_COMM_EXCHANGE;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&ly.ta);
@@ -190,13 +404,14 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(state_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  if (warp >= 2) {  // 128 threads x 16 B = the ones tile
+  if (warp >= 2 && warp < 6) {  // 128 threads x 16 B = the ones tile
     const int t = threadIdx.x - 64;
     st_shared_v4(smem_u32(ones) + t * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
@@ -222,6 +437,19 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
         for (int c = 0; c < kBwdBlockM / 64; ++c) tma_load_2d(sa + c * 8192, &ly.ta, m0 + c * 64, kb * 64, &full_bar[stage]);
 #pragma unroll
         for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &ly.tb, n0 + c * 64, kb * 64, &full_bar[stage]);
+        if (kb == 0 && ly.maps != nullptr) {
+          // the parameter state of this tile: in flight while the gradient GEMM runs
+          const int narr = 1 + (use_s0 ? 1 : 0) + (use_s1 ? 1 : 0) + (use_w1 ? 1 : 0);
+          mbar_expect_tx(state_bar, narr * kBwdTileBytes);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const bool want = a == kStW || (a == kStS0 && use_s0) || (a == kStS1 && use_s1) || (a == kStW1 && use_w1);
+            if (!want) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              tma_load_2d(tiles + a * kBwdTileBytes + h * (kBwdBlockM * 128), &ly.maps->ld[a], n0 + 32 * h, m0, state_bar);
+          }
+        }
         if (++stage == kBwdStages) {
           stage = 0;
           phase ^= 1;
@@ -256,130 +484,21 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
     }
   } else {
     // ------------------------------ epilogue: optimizer (+ exchange) ------------------------------
-    const int quarter = warp & 3;
-    const int m = m0 + quarter * 32 + lane;  // output unit (row of the kernel) owned by this thread
-    const bool row_ok = m < ly.n_out;
-    const int t = max(*p.step, 1);
-    float lr, corr;
-    optim_prelude(p.opt, t, lr, corr);
-    const bool comm = p.comm_mode != DK_COMM_NONE;
-    const float cs = comm ? (p.scale_dev != nullptr ? p.comm_scale * __ldg(p.scale_dev) : p.comm_scale) : 0.f;
-    const bool has_s0 = p.s0 != nullptr, has_s1 = p.s1 != nullptr;
-    const long row_idx = ly.w_off + static_cast<long>(m) * ly.k_in;
+    const int e = warp - 2;            // 0..7
+    const int quarter = warp & 3;      // TMEM lane quarter this warp may read
+    const int half = e >> 2;           // which 32 of the 64 accumulator columns
+    const uint32_t gslot = smem_u32(smem) + e * 4096;   // pipeline buffers are idle once the accumulator is complete
+    const uint32_t tl = smem_u32(tiles), wbt = smem_u32(wb_tile);
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    // ---- pass 1: gradient (TMEM) -> optimizer rule -> W / state (/ shadow) ----
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      const int n = n0 + c;
-      if (n >= ly.k_in) break;  // warp-uniform
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(trow + c, r);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-      const long idx = row_idx + n;
-      if (ly.vec && n + 16 <= ly.k_in) {
-        float4 wv[4], av[4], bv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          wv[q] = *reinterpret_cast<const float4*>(p.w + idx + 4 * q);
-          av[q] = has_s0 ? *reinterpret_cast<const float4*>(p.s0 + idx + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-          bv[q] = has_s1 ? *reinterpret_cast<const float4*>(p.s1 + idx + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          optim_update_rt(p.opt.kind, wv[q].x, __uint_as_float(r[4 * q]), av[q].x, bv[q].x, lr, p.opt, corr);
-          optim_update_rt(p.opt.kind, wv[q].y, __uint_as_float(r[4 * q + 1]), av[q].y, bv[q].y, lr, p.opt, corr);
-          optim_update_rt(p.opt.kind, wv[q].z, __uint_as_float(r[4 * q + 2]), av[q].z, bv[q].z, lr, p.opt, corr);
-          optim_update_rt(p.opt.kind, wv[q].w, __uint_as_float(r[4 * q + 3]), av[q].w, bv[q].w, lr, p.opt, corr);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          *reinterpret_cast<float4*>(p.w + idx + 4 * q) = wv[q];
-          if (has_s0) *reinterpret_cast<float4*>(p.s0 + idx + 4 * q) = av[q];
-          if (has_s1) *reinterpret_cast<float4*>(p.s1 + idx + 4 * q) = bv[q];
-        }
-        if (!comm) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint2 o;
-            o.x = pack_bf16x2(wv[q].x, wv[q].y);
-            o.y = pack_bf16x2(wv[q].z, wv[q].w);
-            *reinterpret_cast<uint2*>(p.wb + idx + 4 * q) = o;
-            if (ly.wb_pad != nullptr)
-              *reinterpret_cast<uint2*>(ly.wb_pad + static_cast<long>(m) * ly.ldwb_pad + n + 4 * q) = o;
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int j = 0; j < 16; ++j) {
-          if (n + j >= ly.k_in) break;
-          update_scalar(p, idx + j, __uint_as_float(r[j]), lr, corr, !comm);
-          if (!comm && ly.wb_pad != nullptr)
-            ly.wb_pad[static_cast<long>(m) * ly.ldwb_pad + n + j] = __float2bfloat16_rn(p.w[idx + j]);
-        }
-      }
-    }
-    if (has_bias) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(trow + BN, r);
-      tmem_ld_wait();
-      if (row_ok) {
-        update_scalar(p, ly.b_off + m, __uint_as_float(r[0]), lr, corr, !comm);
-        if (comm) exchange_scalar(p, ly.b_off + m, cs);
-      }
-    }
-    // ---- pass 2 (window boundary): push the window's displacement, adopt the center ----
-    if (comm && row_ok) {
-      const int ncols = min(BN, ly.k_in - n0);
-      const long idx0 = row_idx + n0;
-      if (ly.vec && ncols == BN) {
-        // all 16 float4 of this row slice: every NVLink request is issued before the first result is used
-        float4 x[BN / 4], y[BN / 4];
-        if (p.comm_mode == DK_COMM_EXCHANGE) {
-#pragma unroll
-          for (int q = 0; q < BN / 4; ++q) {
-            const float4 a = *reinterpret_cast<const float4*>(p.w + idx0 + 4 * q);
-            const float4 b = *reinterpret_cast<const float4*>(p.w1 + idx0 + 4 * q);
-            x[q] = make_float4((a.x - b.x) * cs, (a.y - b.y) * cs, (a.z - b.z) * cs, (a.w - b.w) * cs);
-          }
-#pragma unroll
-          for (int q = 0; q < BN / 4; ++q) y[q] = atom_add_v4_sys_f(center_of(p, idx0 + 4 * q), x[q]);
-#pragma unroll
-          for (int q = 0; q < BN / 4; ++q) {
-            y[q].x += x[q].x; y[q].y += x[q].y; y[q].z += x[q].z; y[q].w += x[q].w;
-            *reinterpret_cast<float4*>(p.w1 + idx0 + 4 * q) = y[q];
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < BN / 4; ++q) x[q] = ld_sys_v4_f(center_of(p, idx0 + 4 * q));
-#pragma unroll
-          for (int q = 0; q < BN / 4; ++q) {
-            const float4 a = *reinterpret_cast<const float4*>(p.w + idx0 + 4 * q);
-            const float4 e = make_float4(p.alpha * (a.x - x[q].x), p.alpha * (a.y - x[q].y), p.alpha * (a.z - x[q].z),
-                                         p.alpha * (a.w - x[q].w));
-            y[q] = make_float4(a.x - e.x, a.y - e.y, a.z - e.z, a.w - e.w);
-            red_add_v4_sys_f(center_of(p, idx0 + 4 * q), e);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < BN / 4; ++q) {
-          *reinterpret_cast<float4*>(p.w + idx0 + 4 * q) = y[q];
-          uint2 o;
-          o.x = pack_bf16x2(y[q].x, y[q].y);
-          o.y = pack_bf16x2(y[q].z, y[q].w);
-          *reinterpret_cast<uint2*>(p.wb + idx0 + 4 * q) = o;
-          if (ly.wb_pad != nullptr)
-            *reinterpret_cast<uint2*>(ly.wb_pad + static_cast<long>(m) * ly.ldwb_pad + n0 + 4 * q) = o;
-        }
-      } else {
-#pragma unroll 1
-        for (int j = 0; j < ncols; ++j) {
-          const float wn = exchange_scalar(p, idx0 + j, cs);
-          if (ly.wb_pad != nullptr) ly.wb_pad[static_cast<long>(m) * ly.ldwb_pad + n0 + j] = __float2bfloat16_rn(wn);
-        }
-      }
+    switch (kind) {
+      case DK_OPT_SGD: bwd_epilogue<DK_OPT_SGD>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
+      case DK_OPT_MOMENTUM: bwd_epilogue<DK_OPT_MOMENTUM>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
+      case DK_OPT_ADAGRAD: bwd_epilogue<DK_OPT_ADAGRAD>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
+      case DK_OPT_RMSPROP: bwd_epilogue<DK_OPT_RMSPROP>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
+      case DK_OPT_ADAM: bwd_epilogue<DK_OPT_ADAM>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
+      case DK_OPT_ADADELTA: bwd_epilogue<DK_OPT_ADADELTA>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
+      default: bwd_epilogue<DK_OPT_ADAMAX>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
     }
     tcgen05_fence_before();
   }
@@ -414,7 +533,7 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
   }
 }
 
-constexpr int kBwdSmem = kBwdStages * (kBwdBlockM * 128 + kBwdBN * 128) + 2048 + 256 + 1024;
+constexpr int kBwdSmem = kBwdSmemUse + 1024;  // + alignment slack
 
 }  // namespace dk
 
@@ -445,6 +564,7 @@ int dk_bwd_update_prepare(void* record, const DkBwdUpdateDesc* d) {
       r = dk_tmap_encode_2d(&ly.tb, s.x, DK_BF16, d->batch, s.k_in, s.ldx, 64);
       if (r != 0) return r;
     }
+    ly.maps = nullptr;
     ly.w_off = s.w_off;
     ly.b_off = s.b_off;
     ly.wb_pad = reinterpret_cast<__nv_bfloat16*>(s.wb_pad);
@@ -457,6 +577,37 @@ int dk_bwd_update_prepare(void* record, const DkBwdUpdateDesc* d) {
     tiles += ((s.n_out + kBwdBlockM - 1) / kBwdBlockM) * ly.tiles_n;
   }
   rec->total_tiles = tiles;
+  // parameter-state tensor maps (device memory): layers whose rows are 16-byte aligned take the TMA-fed path
+  rec->maps_dev = nullptr;
+  {
+    StateMaps host[DK_BWD_MAX_LAYERS];
+    memset(host, 0, sizeof(host));
+    bool any = false;
+    for (int l = 0; l < d->nlayers; ++l) {
+      const DkBwdLayerDesc& sd = d->layer[l];
+      BwdLayerDev& ly = p.layer[l];
+      if (!ly.vec || sd.wb_pad != nullptr || sd.k_in % 8 != 0 || sd.w_off % 8 != 0) continue;  // bf16 rows 16-byte aligned too
+      float* arrs[4] = {d->w, d->s0, d->s1, d->w1};
+      bool ok = true;
+      for (int a = 0; a < 4 && ok; ++a) {
+        if (arrs[a] == nullptr) continue;
+        ok = dk_tmap_encode_2d(&host[l].ld[a], arrs[a] + sd.w_off, DK_F32, sd.n_out, sd.k_in, sd.k_in, kBwdBlockM) == 0 &&
+             dk_tmap_encode_2d(&host[l].st[a], arrs[a] + sd.w_off, DK_F32, sd.n_out, sd.k_in, sd.k_in, 32) == 0;
+      }
+      ok = ok && dk_tmap_encode_2d(&host[l].st[kStWb], reinterpret_cast<__nv_bfloat16*>(d->wb) + sd.w_off, DK_BF16, sd.n_out,
+                                   sd.k_in, sd.k_in, 32) == 0;
+      if (ok) {
+        any = true;
+        ly.maps = reinterpret_cast<const StateMaps*>(static_cast<uintptr_t>(l + 1));  // patched to the device address below
+      }
+    }
+    if (any) {
+      DK_HOST_CHECK(cudaMalloc(reinterpret_cast<void**>(&rec->maps_dev), sizeof(StateMaps) * DK_BWD_MAX_LAYERS));
+      DK_HOST_CHECK(cudaMemcpy(rec->maps_dev, host, sizeof(StateMaps) * DK_BWD_MAX_LAYERS, cudaMemcpyHostToDevice));
+      for (int l = 0; l < d->nlayers; ++l)
+        if (p.layer[l].maps != nullptr) p.layer[l].maps = rec->maps_dev + l;
+    }
+  }
   for (int s = 0; s < d->nshards; ++s) p.shard_center[s] = d->shard_center[s];
   p.w = d->w; p.s0 = d->s0; p.s1 = d->s1; p.w1 = d->w1;
   p.wb = reinterpret_cast<__nv_bfloat16*>(d->wb);
@@ -468,6 +619,12 @@ int dk_bwd_update_prepare(void* record, const DkBwdUpdateDesc* d) {
   p.nlayers = d->nlayers; p.batch = d->batch; p.step_inc = d->step_inc; p.comm_mode = d->comm_mode;
   p.nshards = d->nshards; p.worker = d->worker; p.comm_scale = d->comm_scale; p.alpha = d->alpha;
   return 0;
+}
+
+void dk_bwd_update_release(void* record) {
+  BwdRecord* rec = reinterpret_cast<BwdRecord*>(record);
+  if (rec->maps_dev != nullptr) cudaFree(rec->maps_dev);
+  rec->maps_dev = nullptr;
 }
 
 int dk_bwd_update_set_input(void* record, int layer, const void* x) {
@@ -500,7 +657,10 @@ int dk_bwd_update(const DkBwdUpdateDesc* desc, void* stream) {
   void* rec = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(storage) + 63) & ~static_cast<uintptr_t>(63));
   int r = dk_bwd_update_prepare(rec, desc);
   if (r != 0) return r;
-  return dk_bwd_update_launch(rec, stream);
+  r = dk_bwd_update_launch(rec, stream);
+  cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));  // one-shot helper: the maps die with this call
+  dk_bwd_update_release(rec);
+  return r;
 }
 
 }  // extern "C"

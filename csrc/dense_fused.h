@@ -56,6 +56,7 @@ extern "C" {
 long dk_bwd_update_record_bytes();
 long dk_bwd_update_desc_bytes();  // sizeof(DkBwdUpdateDesc): checked by the ctypes binding
 int dk_bwd_update_prepare(void* record, const DkBwdUpdateDesc* desc);
+void dk_bwd_update_release(void* record);  // frees the device-side tensor maps of a prepared record
 // Re-point layer `layer`'s input operand (slot-fed first layer) before a launch.
 int dk_bwd_update_set_input(void* record, int layer, const void* x);
 int dk_bwd_update_launch(const void* record, void* stream);

@@ -285,7 +285,10 @@ void dk_engine_destroy(void* h) {
   Engine* e = reinterpret_cast<Engine*>(h);
   for (auto& lst : e->lists)
     for (Op& op : lst)
-      if (op.rec != nullptr) free(op.rec);
+      if (op.rec != nullptr) {
+        dk_bwd_update_release(op.rec);
+        free(op.rec);
+      }
   for (cudaEvent_t ev : e->events) cudaEventDestroy(ev);
   for (int k = 0; k < DK_ENGINE_SIDE_STREAMS; ++k)
     if (e->side[k] != nullptr) cudaStreamDestroy(e->side[k]);

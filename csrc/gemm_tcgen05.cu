@@ -1649,6 +1649,12 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
     }
   }
   if (!amn && !bmn) {
+    // One M tile (the reference's batch sizes): the K loop is a chain of L2 round trips, so the ring is made
+    // deep enough to have (nearly) every k-block in flight at once; the CTA then owns the SM's shared memory.
+    if (M <= dk::kBlockM && K > 6 * 64) {
+      if (bn == 16) return dk::launch_gemm<16, 12, false>(L);
+      if (bn == 32) return dk::launch_gemm<32, 11, false>(L);
+    }
     switch (bn) {
       case 16: return dk::launch_gemm<16, 6, false>(L);
       case 32: return dk::launch_gemm<32, 6, false>(L);

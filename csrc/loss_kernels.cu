@@ -198,7 +198,9 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
 // MAXC: compile-time bound on the class count (2 / 10 / 16); NCH > 0: every lane keeps its (at most
 // NCH) chunks of both rows in registers -- all loads are issued back to back and the dReLU mask needs
 // no second read; NCH == 0 is the generic loop for K > 256.
-template <int MAXC, int NCH>
+// R: rows handled by each 8-lane group per pass (2 = a shared-memory read of W feeds 16 FMAs: best when the
+// batch is large; 1 = half the serial work per lane, twice the warps: best in the latency-bound small-batch regime).
+template <int MAXC, int NCH, int R>
 __global__ void __launch_bounds__(128)
 dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __nv_bfloat16* __restrict__ Wb, int ldw,
                           const float* __restrict__ bias, const int* __restrict__ labels,
@@ -210,6 +212,7 @@ dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __
   extern __shared__ __align__(16) float s_w[];  // [chunks][C * 8 + 4]
   const int chunks = K >> 3;                    // K % 8 == 0
   const int SC = C * 8 + 4;
+#pragma unroll 4
   for (int i = threadIdx.x; i < C * chunks; i += blockDim.x) {  // one 16-byte load per 8 weights
     const int c = i / chunks, ch = i - c * chunks;
     float f[8];
@@ -223,56 +226,69 @@ dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __
   const int sub = lane & 7, grp = lane >> 3;
   const float inv_b = 1.f / static_cast<float>(B);
   float loss_acc = 0.f, correct_acc = 0.f;
-  const int rows_per_pass = gridDim.x * nwarps * 8;
-  for (int row0 = (blockIdx.x * nwarps + warp) * 8; row0 < B; row0 += rows_per_pass) {
-    const int row[2] = {row0 + grp, row0 + 4 + grp};
-    const bool valid[2] = {row[0] < B, row[1] < B};
-    const __nv_bfloat16* hrow[2] = {H + static_cast<size_t>(valid[0] ? row[0] : 0) * ldh,
-                                    H + static_cast<size_t>(valid[1] ? row[1] : 0) * ldh};
-    float acc[2][MAXC];
+  const int rows_per_pass = gridDim.x * nwarps * 4 * R;
+  for (int row0 = (blockIdx.x * nwarps + warp) * 4 * R; row0 < B; row0 += rows_per_pass) {
+    int row[R];
+    bool valid[R];
+    const __nv_bfloat16* hrow[R];
+    float acc[R][MAXC];
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) acc[0][c] = acc[1][c] = 0.f;
-    uint4 hq[2][NCH > 0 ? NCH : 1];
+    for (int r = 0; r < R; ++r) {
+      row[r] = row0 + 4 * r + grp;
+      valid[r] = row[r] < B;
+      hrow[r] = H + static_cast<size_t>(valid[r] ? row[r] : 0) * ldh;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) acc[r][c] = 0.f;
+    }
+    uint4 hq[R][NCH > 0 ? NCH : 1];
     if constexpr (NCH > 0) {
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
         const int ch = sub + 8 * j;
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int r = 0; r < R; ++r)
           hq[r][j] = ch < chunks ? *reinterpret_cast<const uint4*>(hrow[r] + (ch << 3)) : make_uint4(0, 0, 0, 0);
       }
     }
-    auto fwd_chunk = [&](int ch, const uint4& qa, const uint4& qb) {
-      float ha[8], hb[8];
-      unpack8(qa, ha);
-      unpack8(qb, hb);
+    auto fwd_chunk = [&](int ch, const uint4* q) {
+      float hv[R][8];
+#pragma unroll
+      for (int r = 0; r < R; ++r) unpack8(q[r], hv[r]);
       const float* wch = s_w + ch * SC;
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         if (c < C) {
           const float4 w0 = *reinterpret_cast<const float4*>(wch + c * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(wch + c * 8 + 4);
-          acc[0][c] += ha[0] * w0.x + ha[1] * w0.y + ha[2] * w0.z + ha[3] * w0.w + ha[4] * w1.x + ha[5] * w1.y +
-                       ha[6] * w1.z + ha[7] * w1.w;
-          acc[1][c] += hb[0] * w0.x + hb[1] * w0.y + hb[2] * w0.z + hb[3] * w0.w + hb[4] * w1.x + hb[5] * w1.y +
-                       hb[6] * w1.z + hb[7] * w1.w;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            acc[r][c] += hv[r][0] * w0.x + hv[r][1] * w0.y + hv[r][2] * w0.z + hv[r][3] * w0.w + hv[r][4] * w1.x +
+                         hv[r][5] * w1.y + hv[r][6] * w1.z + hv[r][7] * w1.w;
         }
       }
     };
     if constexpr (NCH > 0) {
 #pragma unroll
       for (int j = 0; j < NCH; ++j)
-        if (sub + 8 * j < chunks) fwd_chunk(sub + 8 * j, hq[0][j], hq[1][j]);
+        if (sub + 8 * j < chunks) {
+          uint4 q[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) q[r] = hq[r][j];
+          fwd_chunk(sub + 8 * j, q);
+        }
     } else {
 #pragma unroll 4  // independent loads of four chunks in flight per lane (the accumulation is the only dependency)
-      for (int ch = sub; ch < chunks; ch += 8)
-        fwd_chunk(ch, *reinterpret_cast<const uint4*>(hrow[0] + (ch << 3)),
-                  *reinterpret_cast<const uint4*>(hrow[1] + (ch << 3)));
+      for (int ch = sub; ch < chunks; ch += 8) {
+        uint4 q[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) q[r] = *reinterpret_cast<const uint4*>(hrow[r] + (ch << 3));
+        fwd_chunk(ch, q);
+      }
     }
     // reduce over the 8 lanes of a row (every lane ends up with the full logits), then softmax / loss
-    float g[2][MAXC];
+    float g[R][MAXC];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < R; ++r) {
       float mx = -INFINITY;
       int amax = 0;
 #pragma unroll
@@ -331,10 +347,12 @@ dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __
         if (2 * sub < ldz) *reinterpret_cast<uint32_t*>(dz + static_cast<size_t>(row[r]) * ldz + 2 * sub) = word;
       }
     }
-    auto bwd_chunk = [&](int ch, const uint4& qa, const uint4& qb) {
-      float d[2][8];
+    auto bwd_chunk = [&](int ch, const uint4* q) {
+      float d[R][8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) d[0][u] = d[1][u] = 0.f;
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[r][u] = 0.f;
       const float* wch = s_w + ch * SC;
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
@@ -343,17 +361,16 @@ dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __
           const float4 w1 = *reinterpret_cast<const float4*>(wch + c * 8 + 4);
           const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            d[0][u] += g[0][c] * wv[u];
-            d[1][u] += g[1][c] * wv[u];
-          }
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int r = 0; r < R; ++r) d[r][u] += g[r][c] * wv[u];
         }
       }
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
+      for (int r = 0; r < R; ++r) {
         if (use_mask) {
           float h[8];
-          unpack8(r == 0 ? qa : qb, h);
+          unpack8(q[r], h);
 #pragma unroll
           for (int u = 0; u < 8; ++u) d[r][u] = h[u] > 0.f ? d[r][u] * alpha : 0.f;
         } else {
@@ -372,12 +389,20 @@ dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __
       if constexpr (NCH > 0) {
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
-          if (sub + 8 * j < chunks) bwd_chunk(sub + 8 * j, hq[0][j], hq[1][j]);
+          if (sub + 8 * j < chunks) {
+            uint4 q[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) q[r] = hq[r][j];
+            bwd_chunk(sub + 8 * j, q);
+          }
       } else {
 #pragma unroll 4
-        for (int ch = sub; ch < chunks; ch += 8)
-          bwd_chunk(ch, *reinterpret_cast<const uint4*>(hrow[0] + (ch << 3)),
-                    *reinterpret_cast<const uint4*>(hrow[1] + (ch << 3)));
+        for (int ch = sub; ch < chunks; ch += 8) {
+          uint4 q[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) q[r] = *reinterpret_cast<const uint4*>(hrow[r] + (ch << 3));
+          bwd_chunk(ch, q);
+        }
       }
     }
   }
@@ -403,17 +428,27 @@ static int launch_head(const void* H, int ldh, const void* Wb, int ldw, const fl
                        const float* labels_dense, int B, int C, int K, void* dz, int ldz, void* dH, int lddh,
                        float alpha, int use_mask, float* hist, const int* step, int hist_slots, void* stream,
                        size_t smem) {
-  int blocks = (B + 31) / 32;                // 4 warps x 8 rows per pass
+  // B > 512: 4 warps x 8 rows per pass and block (R = 2).  Small batches are latency-bound: one row per 8-lane
+  // group (R = 1) and one warp (4 rows) per block, so the few rows spread over up to B / 4 SMs.
+  const bool small = B <= 512;
+  const int threads = small ? 32 : 128;
+  int blocks = small ? (B + 3) / 4 : (B + 31) / 32;
   if (blocks > 148 * 4) blocks = 148 * 4;    // resident blocks stage W once and walk their rows
   const int per_lane = (K / 8 + 7) / 8;      // 16-byte chunks each of the 8 lanes of a row owns
-#define DK_HEAD_LAUNCH(NCH)                                                                                          \
-  DK_HOST_CHECK(DK_LAUNCH((dense_softmax_head_kernel<MAXC, NCH>), blocks, 128, smem, (cudaStream_t)stream,           \
+#define DK_HEAD_LAUNCH(NCH, RR)                                                                                      \
+  DK_HOST_CHECK(DK_LAUNCH((dense_softmax_head_kernel<MAXC, NCH, RR>), blocks, threads, smem, (cudaStream_t)stream,   \
       reinterpret_cast<const __nv_bfloat16*>(H), ldh, reinterpret_cast<const __nv_bfloat16*>(Wb), ldw, bias, labels, \
       labels_dense, B, C, K, reinterpret_cast<__nv_bfloat16*>(dz), ldz, reinterpret_cast<__nv_bfloat16*>(dH), lddh,  \
       alpha, use_mask, hist, step, hist_slots))
-  if (per_lane <= 2) { DK_HEAD_LAUNCH(2); }
-  else if (per_lane <= 4) { DK_HEAD_LAUNCH(4); }
-  else { DK_HEAD_LAUNCH(0); }
+  if (small) {
+    if (per_lane <= 2) { DK_HEAD_LAUNCH(2, 1); }
+    else if (per_lane <= 4) { DK_HEAD_LAUNCH(4, 1); }
+    else { DK_HEAD_LAUNCH(0, 1); }
+  } else {
+    if (per_lane <= 2) { DK_HEAD_LAUNCH(2, 2); }
+    else if (per_lane <= 4) { DK_HEAD_LAUNCH(4, 2); }
+    else { DK_HEAD_LAUNCH(0, 2); }
+  }
 #undef DK_HEAD_LAUNCH
   DK_HOST_CHECK(cudaGetLastError());
   return 0;

@@ -31,23 +31,23 @@ __device__ __forceinline__ void optim_update(float& w, float g, float& s0, float
     w += a.nesterov ? a.p0 * v - lr * g : v;
   } else if constexpr (KIND == DK_OPT_ADAGRAD) {
     s0 += g * g;
-    w -= lr * g / (sqrtf(s0) + a.eps);
+    w -= lr * __fdividef(g, sqrtf(s0) + a.eps);
   } else if constexpr (KIND == DK_OPT_RMSPROP) {
     s0 = a.p0 * s0 + (1.f - a.p0) * g * g;
-    w -= lr * g / (sqrtf(s0) + a.eps);
+    w -= lr * __fdividef(g, sqrtf(s0) + a.eps);
   } else if constexpr (KIND == DK_OPT_ADAM) {
     s0 = a.p0 * s0 + (1.f - a.p0) * g;
     s1 = a.p1 * s1 + (1.f - a.p1) * g * g;
-    w -= lr * corr * s0 / (sqrtf(s1) + a.eps);
+    w -= lr * corr * __fdividef(s0, sqrtf(s1) + a.eps);
   } else if constexpr (KIND == DK_OPT_ADADELTA) {
     s0 = a.p0 * s0 + (1.f - a.p0) * g * g;
-    const float upd = g * sqrtf(s1 + a.eps) / sqrtf(s0 + a.eps);
+    const float upd = g * sqrtf(__fdividef(s1 + a.eps, s0 + a.eps));
     w -= lr * upd;
     s1 = a.p0 * s1 + (1.f - a.p0) * upd * upd;
   } else if constexpr (KIND == DK_OPT_ADAMAX) {
     s0 = a.p0 * s0 + (1.f - a.p0) * g;
     s1 = fmaxf(a.p1 * s1, fabsf(g));
-    w -= lr * corr * s0 / (s1 + a.eps);
+    w -= lr * corr * __fdividef(s0, s1 + a.eps);
   }
 }
 
