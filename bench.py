@@ -162,6 +162,8 @@ def main() -> None:
     ap.add_argument("--dedicated-ps", action="store_true", help="rank 0 hosts the center only (N-1 workers)")
     ap.add_argument("--sharded-ps", action="store_true", help="slice r of the center lives in rank r's HBM")
     ap.add_argument("--reps", type=int, default=0, help="timed K-step regions (0 = auto: >= 50, ~1 s)")
+    ap.add_argument("--no-fuse-comm", action="store_true",
+                    help="A/B: window-boundary exchange as separate kernels instead of inside the backward-update kernel")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
 
@@ -221,6 +223,7 @@ def main() -> None:
     if args.comm != "default":
         trainer.comm = args.comm
     trainer.sharded_ps = bool(args.sharded_ps)
+    trainer.fuse_comm = not args.no_fuse_comm
     trainer.shard_mode = "static"
     n_workers = trainer.num_workers
     comm = getattr(trainer, "comm", "exchange")
@@ -241,6 +244,9 @@ def main() -> None:
         ps, info = None, None
     info = exchange_obj(info, 0)
     region = ps.region if rank == 0 else FabricRegion.open(info, local)
+    shard_regions, shards = [], None
+    if args.sharded_ps and world > 1:
+        shard_regions, shards, _ = runtime.setup_center_shards(model, rank, world, local, exchange_obj)
     sampler = ClockSampler(world)
     if rank == 0:
         sampler.start()
@@ -253,7 +259,7 @@ def main() -> None:
         wid = rank - 1 if dedicated else rank
         affine = (1.0, 0.0) if in_dtype == "f32" else (1.0 / 255.0, 0.0)
         worker = FabricWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid, B, local, in_dtype,
-                              affine, comm=comm, steps_per_graph=K)
+                              affine, comm=comm, steps_per_graph=K, shards=shards, fuse_comm=not args.no_fuse_comm)
         # resident inputs for the kernel-only number: both staging parities hold distinct random batches
         for p in (0, 1):
             if in_dtype == "u8":
@@ -314,6 +320,7 @@ def main() -> None:
         torch.cuda.synchronize()
         x_us = 1e3 * statistics.median(a.elapsed_time(b) for a, b in xev[5:])
         mine.update({"rep_ms": rep_ms, "launches": worker.launched, "exchanges": worker.exchanges, "exchange_us": x_us,
+                     "fused_comm": bool(worker.fused_comm), "compact": bool(worker.rep.compact),
                      "exchange_kernels": xk, "kernels_per_step": worker.kernels_per_step, "params": worker.rep.P,
                      "R": R})
         barrier()
@@ -326,6 +333,12 @@ def main() -> None:
     clocks = sampler.stop() if rank == 0 else None
     allr = gather(mine)
     barrier()
+    for r, reg_r in enumerate(shard_regions):
+        if r != rank:
+            reg_r.close()
+    barrier()
+    if shard_regions:
+        shard_regions[rank].close()
     if rank != 0:
         region.close()
     else:
@@ -399,7 +412,10 @@ def main() -> None:
                        "communication_window": tau, "worker_optimizer": args.optimizer,
                        "parallelism": f"async-ps(center on gpu0, {'dedicated' if dedicated else 'colocated'}"
                                       f"{', sharded' if args.sharded_ps else ''})+dp{n_workers}",
-                       "ps_transport": f"in-kernel NVLink P2P atomics ({comm})",
+                       "ps_transport": ("in-kernel NVLink P2P atomics, exchange fused into the backward-update GEMM epilogue"
+                                        if wk[0].get("fused_comm") else f"in-kernel NVLink P2P atomics ({comm} kernel)"),
+                       "program": "compact (region input stage, fused wgrad+bias-grad+optimizer kernel)"
+                                  if wk[0].get("compact") else "wide-batch (per-layer GEMMs, split-K wgrad, flat optimizer)",
                        "l2_policy": l2_policy + "; e2e: inputs streamed from pinned host memory every step"},
             "timing": {"regions": slow["R"], "steps_per_region": K, "region_ms_mean": ms_per_step * K,
                        "region_ms_median": statistics.median(slow["rep_ms"]), "region_ms_min": min(slow["rep_ms"]),
@@ -407,6 +423,8 @@ def main() -> None:
                        "exchanges_per_region": ex_per_rep, "graphs": period},
             "per_rank_ms_per_step": [round(v, 6) for v in per_rank_ms],
             "exchange_us": x_us, "exchange_kernels": wk[0]["exchange_kernels"],
+            "exchange_note": "the stand-alone exchange kernel, all ranks at once (what a window boundary costs when it is NOT "
+                             "fused into the backward pass)",
             "ps_gbs": {"push": gbs, "pull": gbs, "bytes_each_way": 4 * P, "vs_900": gbs / 900.0, "vs_measured_770": gbs / 770.0,
                        "note": "per worker, all ranks exchanging at once; one fused kernel moves 4P bytes each way"},
             "comm_fraction": ex_per_rep * x_us * 1e-3 / (ms_per_step * K),

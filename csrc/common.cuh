@@ -88,6 +88,18 @@ inline cudaError_t launch_kernel_cluster(void (*kern)(KArgs...), dim3 grid, dim3
   dk::launch_kernel((kern), dim3(grid), dim3(block), (smem), (cudaStream_t)(stream), __VA_ARGS__)
 
 // ---------------------------------------------------------------------------
+// in-kernel timeline (diagnostics): when a kernel is handed a trace buffer, designated threads of its first
+// CTA store the SM clock at fixed points (tools/kernel_timeline.py prints the phases).  nullptr = off.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void trace_stamp(unsigned long long* buf, int slot) {
+  if (buf != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    buf[slot] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // misc
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

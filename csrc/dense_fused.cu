@@ -74,6 +74,7 @@ struct BwdUpdateDev {
   const float* scale_dev;
   unsigned* ctrl;
   unsigned* last_update;
+  unsigned long long* trace;
   long shard_per;
   OptimArgs opt;
   int nlayers, batch, step_inc, comm_mode, nshards, worker;
@@ -190,17 +191,11 @@ template <int KIND>
 __device__ __forceinline__ void bwd_epilogue(const BwdUpdateDev& p, const BwdLayerDev& ly, const int m0, const int n0,
                                              const int quarter, const int half, const int lane, const uint32_t tmem_base,
                                              const uint32_t gslot, const uint32_t tiles, const uint32_t wb_tile,
-                                             uint64_t* state_bar, const bool has_bias) {
+                                             uint64_t* state_bar, const bool has_bias, const float lr, const float corr,
+                                             const float cs, float bw, float bs0, float bs1) {
   constexpr bool kS0 = KIND != DK_OPT_SGD;
   constexpr bool kS1 = KIND == DK_OPT_ADAM || KIND == DK_OPT_ADADELTA || KIND == DK_OPT_ADAMAX;
-  const int t = max(*p.step, 1);
-  float lr = p.opt.lr, corr = 1.f;
-  if (p.opt.decay > 0.f) lr = __fdividef(lr, 1.f + p.opt.decay * static_cast<float>(t - 1));
-  if constexpr (KIND == DK_OPT_ADAM)
-    corr = __fdividef(sqrtf(1.f - __powf(p.opt.p1, static_cast<float>(t))), 1.f - __powf(p.opt.p0, static_cast<float>(t)));
-  if constexpr (KIND == DK_OPT_ADAMAX) corr = __fdividef(1.f, 1.f - __powf(p.opt.p0, static_cast<float>(t)));
   const bool comm = p.comm_mode != DK_COMM_NONE;
-  const float cs = comm ? (p.scale_dev != nullptr ? p.comm_scale * __ldg(p.scale_dev) : p.comm_scale) : 0.f;
   const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
   const int nbase = n0 + half * 32;                  // first column of this warp's slice
   const int mbase = m0 + quarter * 32;               // first row
@@ -221,6 +216,7 @@ __device__ __forceinline__ void bwd_epilogue(const BwdUpdateDev& p, const BwdLay
     const uint32_t tS0 = tW + kBwdTileBytes, tS1 = tW + 2 * kBwdTileBytes, tW1 = tW + 3 * kBwdTileBytes;
     if (slice_live) {
       mbar_wait(state_bar, 0);                                     // the state tiles have landed
+      if (blockIdx.x == 0 && quarter == 2 && half == 0 && lane == 0) trace_stamp(p.trace, 5);
 #pragma unroll 1
       for (int jj = 0; jj < 4; ++jj) {                             // two 16-byte column groups per trip
         uint32_t packed[4];
@@ -354,8 +350,13 @@ __device__ __forceinline__ void bwd_epilogue(const BwdUpdateDev& p, const BwdLay
     tmem_ld_wait();
     const int m = mbase + lane;
     if (m < ly.n_out) {
-      update_scalar<KIND>(p, ly.b_off + m, __uint_as_float(r[0]), lr, corr, !comm);
-      if (comm) exchange_scalar(p, ly.b_off + m, cs);
+      const long idx = ly.b_off + m;                 // bw / bs0 / bs1 were loaded before the accumulator wait
+      optim_update<KIND>(bw, __uint_as_float(r[0]), bs0, bs1, lr, p.opt, corr);
+      p.w[idx] = bw;
+      if constexpr (kS0) p.s0[idx] = bs0;
+      if constexpr (kS1) p.s1[idx] = bs1;
+      if (comm) exchange_scalar(p, idx, cs);
+      else p.wb[idx] = __float2bfloat16_rn(bw);
     }
   }
 }
@@ -381,6 +382,8 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
   uint64_t* state_bar = tmem_full_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(state_bar + 1);
 
+  unsigned long long* const tr = blockIdx.x == 0 ? p.trace : nullptr;
+  if (threadIdx.x == 0) trace_stamp(tr, 0);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   int L = 0;
@@ -420,8 +423,10 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_stamp(tr, 1);
   DK_PDL_WAIT();
   DK_PDL_TRIGGER();
+  if (threadIdx.x == 0) trace_stamp(tr, 2);
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -463,6 +468,7 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tcgen05_fence_after();
+      if (kb == 0 && lane == 0) trace_stamp(tr, 3);
       if (elect_one()) {
         const uint32_t sa = smem_u32(smem + stage * kStageBytes);
         const uint64_t adesc = make_smem_desc_sw128_mn(sa);
@@ -489,18 +495,37 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
     const int half = e >> 2;           // which 32 of the 64 accumulator columns
     const uint32_t gslot = smem_u32(smem) + e * 4096;   // pipeline buffers are idle once the accumulator is complete
     const uint32_t tl = smem_u32(tiles), wbt = smem_u32(wb_tile);
+    // everything that only depends on the previous step is fetched while the operands / state tiles are in
+    // flight: step number -> learning rate and bias correction, DynSGD scale, this lane's bias parameter
+    const int t = max(*p.step, 1);
+    float lr = p.opt.lr, corr = 1.f;
+    if (p.opt.decay > 0.f) lr = __fdividef(lr, 1.f + p.opt.decay * static_cast<float>(t - 1));
+    if (kind == DK_OPT_ADAM)
+      corr = __fdividef(sqrtf(1.f - __powf(p.opt.p1, static_cast<float>(t))), 1.f - __powf(p.opt.p0, static_cast<float>(t)));
+    if (kind == DK_OPT_ADAMAX) corr = __fdividef(1.f, 1.f - __powf(p.opt.p0, static_cast<float>(t)));
+    const float cs = p.comm_mode != DK_COMM_NONE
+                         ? (p.scale_dev != nullptr ? p.comm_scale * __ldg(p.scale_dev) : p.comm_scale) : 0.f;
+    float bw = 0.f, bs0 = 0.f, bs1 = 0.f;
+    if (has_bias && half == 0 && m0 + quarter * 32 + lane < ly.n_out) {
+      const long idx = ly.b_off + m0 + quarter * 32 + lane;
+      bw = p.w[idx];
+      if (use_s0) bs0 = p.s0[idx];
+      if (use_s1) bs1 = p.s1[idx];
+    }
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
+    if (warp == 2 && lane == 0) trace_stamp(tr, 4);
     switch (kind) {
-      case DK_OPT_SGD: bwd_epilogue<DK_OPT_SGD>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
-      case DK_OPT_MOMENTUM: bwd_epilogue<DK_OPT_MOMENTUM>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
-      case DK_OPT_ADAGRAD: bwd_epilogue<DK_OPT_ADAGRAD>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
-      case DK_OPT_RMSPROP: bwd_epilogue<DK_OPT_RMSPROP>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
-      case DK_OPT_ADAM: bwd_epilogue<DK_OPT_ADAM>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
-      case DK_OPT_ADADELTA: bwd_epilogue<DK_OPT_ADADELTA>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
-      default: bwd_epilogue<DK_OPT_ADAMAX>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias); break;
+      case DK_OPT_SGD: bwd_epilogue<DK_OPT_SGD>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
+      case DK_OPT_MOMENTUM: bwd_epilogue<DK_OPT_MOMENTUM>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
+      case DK_OPT_ADAGRAD: bwd_epilogue<DK_OPT_ADAGRAD>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
+      case DK_OPT_RMSPROP: bwd_epilogue<DK_OPT_RMSPROP>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
+      case DK_OPT_ADAM: bwd_epilogue<DK_OPT_ADAM>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
+      case DK_OPT_ADADELTA: bwd_epilogue<DK_OPT_ADADELTA>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
+      default: bwd_epilogue<DK_OPT_ADAMAX>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
     }
     tcgen05_fence_before();
+    if (warp == 2 && lane == 0) trace_stamp(tr, 6);
   }
 
   __syncthreads();
@@ -508,6 +533,7 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (threadIdx.x == 0) trace_stamp(tr, 7);
   if (threadIdx.x == 0) {
     // last CTA of the grid: advance the step counter (every CTA read it before arriving here) and
     // publish the commit in the parameter server's control block
@@ -612,7 +638,7 @@ int dk_bwd_update_prepare(void* record, const DkBwdUpdateDesc* d) {
   p.w = d->w; p.s0 = d->s0; p.s1 = d->s1; p.w1 = d->w1;
   p.wb = reinterpret_cast<__nv_bfloat16*>(d->wb);
   p.step = d->step; p.done_counter = d->done_counter; p.scale_dev = d->scale_dev;
-  p.ctrl = d->ctrl; p.last_update = d->last_update; p.shard_per = d->shard_per > 0 ? d->shard_per : 1;
+  p.ctrl = d->ctrl; p.last_update = d->last_update; p.trace = d->trace; p.shard_per = d->shard_per > 0 ? d->shard_per : 1;
   memset(&p.opt, 0, sizeof(p.opt));
   p.opt.kind = d->opt_kind; p.opt.lr = d->lr; p.opt.p0 = d->p0; p.opt.p1 = d->p1; p.opt.eps = d->eps;
   p.opt.decay = d->decay; p.opt.nesterov = d->nesterov; p.opt.grad_scale = 1.f;

@@ -46,6 +46,7 @@ typedef struct DkBwdUpdateDesc {
   unsigned* ctrl;          // PS control block (peer-mapped)
   int worker;
   unsigned* last_update;
+  unsigned long long* trace;  // diagnostics: clock stamps of CTA 0 (nullptr = off)
 } DkBwdUpdateDesc;
 
 #ifdef __cplusplus

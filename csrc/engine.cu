@@ -128,7 +128,8 @@ int run_op(Engine* e, Op& op, void* main_stream) {
     case DK_OP_GEMM:
       // M, N, K, bn, flags (tensor maps + epilogue pre-encoded)
       if (op.dyn_a_slot >= 0) {
-        int r = dk_tmap_encode_2d(&op.ta, e->slots[op.dyn_a_slot], DK_BF16, a[0], a[2], op.dyn_lda, 128);
+        int r = dk_tmap_encode_2d(&op.ta, e->slots[op.dyn_a_slot], DK_BF16, a[0], a[2], op.dyn_lda,
+                                  (a[4] & DK_GEMM_SHORT_A) ? dk_gemm_a_box_rows((int)a[0]) : 128);
         if (r != 0) return r;
       }
       return dk_gemm_tn_launch2(&op.ta, &op.tb, op.has_td ? &op.td : nullptr, op.has_tm ? &op.tm : nullptr, &op.ep,
@@ -356,7 +357,7 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
     persistent_env = (pe != nullptr && pe[0] == '0') ? 0 : 1;
   }
   if (bn <= 0 && persistent_env && !ep->d_fp32 && ep->d != nullptr && ep->dt == nullptr && !ep->bias_along_m &&
-      !(flags & (DK_GEMM_A_MN | DK_GEMM_TF32)) && N >= 16 && (ep->ldd % 8) == 0 &&
+      !(flags & (DK_GEMM_A_MN | DK_GEMM_TF32 | DK_GEMM_SHORT_A)) && N >= 16 && (ep->ldd % 8) == 0 &&
       (ep->mask == nullptr || (ep->ld_mask % 8) == 0)) {
     bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
     flags |= DK_GEMM_PERSISTENT;
@@ -395,6 +396,7 @@ int dk_engine_add_gemm_slot(void* h, int list, int a_slot, long lda, const void*
                             int flags, int bn, int splits, const DkGemmEpilogue* ep) {
   Engine* e = reinterpret_cast<Engine*>(h);
   if (a_slot < 0 || a_slot >= DK_ENGINE_SLOTS || (flags & (DK_GEMM_A_MN | DK_GEMM_TF32 | DK_GEMM_PAIR))) return -1;
+  if (bn <= 0 && !(flags & DK_GEMM_SHORT_A)) return -1;  // slot-fed operands run on the plain kernel: explicit tile width
   // encode against a placeholder base (B is a valid, aligned device pointer); the real one is bound per run
   int r = dk_engine_add_gemm(h, list, B, lda, B, ldb, M, N, K, flags, bn, splits, ep);
   if (r < 0) return r;

@@ -10,7 +10,8 @@ typedef uint16_t dk_bf16;
 #endif
 
 enum { DK_BF16 = 0, DK_F32 = 1 };
-enum { DK_GEMM_TF32 = 1, DK_GEMM_A_MN = 2, DK_GEMM_B_MN = 4, DK_GEMM_PERSISTENT = 8, DK_GEMM_PAIR = 16 };
+enum { DK_GEMM_TF32 = 1, DK_GEMM_A_MN = 2, DK_GEMM_B_MN = 4, DK_GEMM_PERSISTENT = 8, DK_GEMM_PAIR = 16,
+       DK_GEMM_SHORT_A = 32 /* K-major A of one short M tile: TMA box of ceil8(M) rows (plain kernel only) */ };
 
 // Fused epilogue description: out = mask( act( alpha * acc + bias ) )
 typedef struct DkGemmEpilogue {
@@ -31,6 +32,7 @@ typedef struct DkGemmEpilogue {
   const int* step;       // device step counter mixed into the dropout hash (graph-replay safe)
   int tma_store;         // set by the launcher: output goes through smem staging + TMA store
   int tma_mask;          // set by the launcher: mask tile is fetched with TMA
+  unsigned long long* trace;  // diagnostics: 8 clock stamps of CTA (0, 0) (nullptr = off)
 } DkGemmEpilogue;
 
 #ifdef __cplusplus
@@ -45,6 +47,7 @@ extern "C" {
 int dk_tmap_encode_2d(void* out_tmap, const void* base, int dtype, long rows, long cols, long ld,
                       int box_rows);
 int dk_gemm_pick_bn(int N);
+int dk_gemm_a_box_rows(int M);
 int dk_gemm_pick_bn2(int M, int N);
 int dk_gemm_pick_bn_splitk(int M, int N, int K);
 int dk_gemm_tn_launch(const void* tmap_a, const void* tmap_b, const DkGemmEpilogue* ep, int M, int N,

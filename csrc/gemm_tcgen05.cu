@@ -260,8 +260,11 @@ template <int BN, int STAGES, bool TF32, bool AMN, bool BMN>
 __global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 2 : 1))
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
-               const GemmEpilogue ep, const int M, const int N, const int K, const int kb_per_split) {
+               const GemmEpilogue ep, const int M, const int N, const int K, const int kb_per_split,
+               const int a_box_rows) {
   using S = GemmSmem<BN, STAGES, TF32>;
+  // bytes one k-block of the A operand brings in (DK_GEMM_SHORT_A: a short single M tile uses a short box)
+  const int a_stage_bytes = AMN ? S::kABytes : a_box_rows * 128;
   constexpr int kBlockK = TF32 ? 32 : 64;   // elements per 128-byte swizzle row
   constexpr int kUmmaK = TF32 ? 8 : 16;     // 32 bytes of K per tcgen05.mma
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
@@ -279,6 +282,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* mask_bar = tmem_full_bar + 1;  // [4], one per epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 4);
 
+  unsigned long long* const tr = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? ep.trace : nullptr;
+  if (threadIdx.x == 0) trace_stamp(tr, 0);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
@@ -310,10 +315,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_stamp(tr, 1);
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail
   // of the previous kernel; operands / bias / mask produced by it are only touched after this point
   DK_PDL_WAIT();
   DK_PDL_TRIGGER();
+  if (threadIdx.x == 0) trace_stamp(tr, 2);
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -324,7 +331,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
-        mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+        mbar_expect_tx(&full_bar[stage], a_stage_bytes + S::kBBytes);
         if constexpr (AMN) {
 #pragma unroll
           for (int c = 0; c < kBlockM / 64; ++c)
@@ -352,6 +359,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tcgen05_fence_after();
+      if (kb == 0 && lane == 0) trace_stamp(tr, 3);
+      if (kb == num_kb - 1 && lane == 0) trace_stamp(tr, 4);
       if (elect_one()) {
         const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
         const uint32_t sb = sa + S::kABytes;
@@ -379,14 +388,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
+    if (warp == 2 && lane == 0) {
+      mbar_wait(tmem_full_bar, 0);
+      trace_stamp(tr, 5);
+    }
     gemm_epilogue<BN>(tmap_d, tmap_m, ep, M, N, m0, n0, warp, lane, tmem_base, smem, tmem_full_bar, mask_bar);
     tcgen05_fence_before();
+    if (warp == 2 && lane == 0) trace_stamp(tr, 6);
   }
 
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+    if (lane == 0) trace_stamp(tr, 7);
   }
 }
 
@@ -1037,6 +1052,7 @@ struct GemmLaunch {
   const CUtensorMap* tm;  // may be nullptr
   GemmEpilogue ep;
   int M, N, K, splits;
+  int a_box_rows = kBlockM;
   cudaStream_t stream;
 };
 
@@ -1071,7 +1087,7 @@ static int launch_gemm(const GemmLaunch& L) {
   if (splits > 1 && !ep.d_fp32) return -6;
   dim3 grid((N + BN - 1) / BN, (M + kBlockM - 1) / kBlockM, splits);
   DK_HOST_CHECK(DK_LAUNCH(kern, grid, kGemmThreads, S::kTotal, stream, ta, tb, ep.tma_store ? *L.td : ta, ep.tma_mask ? *L.tm : ta, ep, M,
-                                                  N, K, kb_per_split));
+                                                  N, K, kb_per_split, L.a_box_rows));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1577,6 +1593,14 @@ int dk_tmap_encode_2d(void* out_tmap, const void* base, int dtype, long rows, lo
   return r == CUDA_SUCCESS ? 0 : -100 - static_cast<int>(r);
 }
 
+// Rows of the TMA box of a K-major A operand: a single short M tile (M < 128, the small-batch regime) is
+// loaded with a box of just ceil8(M) rows -- half the shared-memory fill of a 128-row box whose rows past M
+// would only be zero-filled; the accumulator rows past M are never stored.
+int dk_gemm_a_box_rows(int M) {
+  if (M >= dk::kBlockM) return dk::kBlockM;
+  return (M + 7) / 8 * 8;
+}
+
 int dk_gemm_pick_bn(int N) {
   if (N <= 16) return 16;
   if (N <= 32) return 32;
@@ -1618,6 +1642,10 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
   L.stream = reinterpret_cast<cudaStream_t>(stream);
   if (M <= 0 || N <= 0 || K <= 0) return -3;
   const bool tf32 = flags & DK_GEMM_TF32, amn = flags & DK_GEMM_A_MN, bmn = flags & DK_GEMM_B_MN;
+  if (flags & DK_GEMM_SHORT_A) {
+    if ((flags & (DK_GEMM_PAIR | DK_GEMM_PERSISTENT | DK_GEMM_A_MN)) || M > dk::kBlockM) return -8;  // plain kernel, one M tile
+    L.a_box_rows = dk_gemm_a_box_rows(M);
+  }
   if ((flags & DK_GEMM_PAIR) && !tf32) {
     // K-major B tensor maps must have been encoded with box_rows = bn / 2 (each CTA loads half the tile)
     if (!amn && !bmn) {
@@ -1727,7 +1755,7 @@ int dk_gemm_encode_operands(void* tmap_a, void* tmap_b, const void* A, long lda,
                             int M, int N, int K, int bn, int flags) {
   const int dt = (flags & DK_GEMM_TF32) ? DK_F32 : DK_BF16;
   int r = (flags & DK_GEMM_A_MN) ? dk_tmap_encode_2d(tmap_a, A, dt, K, M, lda, 64)
-                                 : dk_tmap_encode_2d(tmap_a, A, dt, M, K, lda, dk::kBlockM);
+                                 : dk_tmap_encode_2d(tmap_a, A, dt, M, K, lda, (flags & DK_GEMM_SHORT_A) ? dk_gemm_a_box_rows(M) : dk::kBlockM);
   if (r != 0) return r;
   return (flags & DK_GEMM_B_MN) ? dk_tmap_encode_2d(tmap_b, B, dt, K, N, ldb, 64)
                                 : dk_tmap_encode_2d(tmap_b, B, dt, N, K, ldb, (flags & DK_GEMM_PAIR) ? bn / 2 : bn);

@@ -422,33 +422,194 @@ dense_softmax_head_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Small-batch variant of the fused head (B <= 512, the reference's batch sizes): the step is a chain of
+// dependent kernels there, so this one is built for latency, not throughput.  A block owns 8 rows, 16
+// lanes per row.  ONE round of global loads brings the whole weight matrix (bf16, C x K), the block's 8
+// activation rows, bias and labels into shared memory; every lane then owns the bf16 pairs lr, lr + 16,
+// ... of its row: logits by 10 short FMA chains + a 4-step half-warp reduction, softmax / loss /
+// accuracy redundantly per lane, dZ as packed pairs, and dH = alpha (dZ W) * (H > 0) for the lane's own
+// pairs (coalesced 4-byte stores).  No loop is unrolled more than NW (<= 8) times: the kernel runs once
+// per step and straight-line code is paid for in instruction-cache misses.
+// ------------------------------------------------------------------------------------------
+template <int MAXC>
+__global__ void __launch_bounds__(128)
+dense_softmax_head_small_kernel(const __nv_bfloat16* __restrict__ H, int ldh, const __nv_bfloat16* __restrict__ Wb, int ldw,
+                                const float* __restrict__ bias, const int* __restrict__ labels,
+                                const float* __restrict__ labels_dense, int B, int C, int K,
+                                __nv_bfloat16* __restrict__ dz, int ldz, __nv_bfloat16* __restrict__ dH, int lddh,
+                                float alpha, int use_mask, float* __restrict__ hist, const int* __restrict__ step,
+                                int hist_slots) {
+  DK_PDL_ENTER();
+  extern __shared__ __align__(16) uint32_t s_head[];
+  const int kw = K >> 1;                      // bf16 pairs per row (K % 8 == 0)
+  uint32_t* sW = s_head;                      // [C][kw]
+  uint32_t* sH = sW + C * kw;                 // [8][kw]
+  float* sB = reinterpret_cast<float*>(sH + 8 * kw);  // [MAXC] bias, then [8] labels
+  int* sL = reinterpret_cast<int*>(sB + MAXC);
+  __shared__ float s_loss[4], s_corr[4];
+  const int tid = threadIdx.x;
+  const int row_in = tid >> 4, lr = tid & 15;
+  const int row0 = blockIdx.x * 8;
+  const int chunks = K >> 3;                  // 16-byte chunks per row
+  // ---- one round of global loads ----
+  for (int i = tid; i < C * chunks; i += 128) {
+    const int c = i / chunks, ch = i - c * chunks;
+    reinterpret_cast<uint4*>(sW + c * kw)[ch] = *reinterpret_cast<const uint4*>(Wb + static_cast<size_t>(c) * ldw + (ch << 3));
+  }
+  for (int i = tid; i < 8 * chunks; i += 128) {
+    const int r = i / chunks, ch = i - r * chunks;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (row0 + r < B) q = *reinterpret_cast<const uint4*>(H + static_cast<size_t>(row0 + r) * ldh + (ch << 3));
+    reinterpret_cast<uint4*>(sH + r * kw)[ch] = q;
+  }
+  if (tid < MAXC) sB[tid] = (bias != nullptr && tid < C) ? bias[tid] : 0.f;
+  if (tid >= 64 && tid < 72) {
+    const int r = tid - 64;
+    int lab = 0;
+    if (row0 + r < B && labels_dense == nullptr) lab = labels[row0 + r];
+    sL[r] = lab;
+  }
+  __syncthreads();
+  const int row = row0 + row_in;
+  const bool valid = row < B;
+  const uint32_t* hrow = sH + row_in * kw;
+  // ---- logits: the lane's pairs against every class ----
+  float acc[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) acc[c] = 0.f;
+#pragma unroll 2
+  for (int w = lr; w < kw; w += 16) {
+    const uint32_t hp = hrow[w];
+    const float h0 = __uint_as_float(hp << 16), h1 = __uint_as_float(hp & 0xffff0000u);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c < C) {
+        const uint32_t wp = sW[c * kw + w];
+        acc[c] = fmaf(h0, __uint_as_float(wp << 16), fmaf(h1, __uint_as_float(wp & 0xffff0000u), acc[c]));
+      }
+    }
+  }
+  float mx = -INFINITY;
+  int amax = 0;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    if (c < C) {
+      float v = acc[c];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += sB[c];
+      acc[c] = v;
+      if (v > mx) { mx = v; amax = c; }
+    }
+  }
+  // ---- softmax, loss, accuracy, dZ ----
+  float g[MAXC];
+  float se = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    g[c] = c < C ? __expf(acc[c] - mx) : 0.f;
+    se += g[c];
+  }
+  const float lse = __logf(se) + mx, inv_se = __fdividef(1.f, se), inv_b = 1.f / static_cast<float>(B);
+  int label = sL[row_in];
+  float ysum = 1.f;
+  const float* y = nullptr;
+  if (valid && labels_dense != nullptr) {
+    y = labels_dense + static_cast<size_t>(row) * C;
+    float ym = -INFINITY;
+    ysum = 0.f;
+    for (int c = 0; c < C; ++c) { const float t = y[c]; ysum += t; if (t > ym) { ym = t; label = c; } }
+  }
+  float row_loss = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    if (c < C) {
+      const float t = y != nullptr ? y[c] : (c == label ? 1.f : 0.f);
+      row_loss += t * (lse - acc[c]);
+      // the bf16-rounded gradient is what the weight-gradient GEMM sees: use the same value for dH
+      g[c] = __bfloat162float(__float2bfloat16_rn((g[c] * inv_se * ysum - t) * inv_b));
+    }
+  }
+  if (valid && dz != nullptr && 2 * lr < ldz) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int c = 0; c < MAXC; c += 2)
+      if ((c >> 1) == lr) word = pack_bf16x2(g[c], c + 1 < MAXC ? g[c + 1] : 0.f);
+    *reinterpret_cast<uint32_t*>(dz + static_cast<size_t>(row) * ldz + 2 * lr) = word;
+  }
+  // ---- dH = alpha (dZ W) * (H > 0): the lane's own pairs ----
+  if (dH != nullptr && valid) {
+#pragma unroll 2
+    for (int w = lr; w < kw; w += 16) {
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+          const uint32_t wp = sW[c * kw + w];
+          d0 = fmaf(g[c], __uint_as_float(wp << 16), d0);
+          d1 = fmaf(g[c], __uint_as_float(wp & 0xffff0000u), d1);
+        }
+      }
+      if (use_mask) {
+        const uint32_t hp = hrow[w];
+        d0 = __uint_as_float(hp << 16) > 0.f ? d0 * alpha : 0.f;
+        d1 = __uint_as_float(hp & 0xffff0000u) > 0.f ? d1 * alpha : 0.f;
+      } else {
+        d0 *= alpha;
+        d1 *= alpha;
+      }
+      *reinterpret_cast<uint32_t*>(dH + static_cast<size_t>(row) * lddh + 2 * w) = pack_bf16x2(d0, d1);
+    }
+  }
+  // ---- history record: one atomic pair per block ----
+  float l = (valid && lr == 0) ? row_loss : 0.f, cr = (valid && lr == 0 && amax == label) ? 1.f : 0.f;
+  l = warp_sum(l);
+  cr = warp_sum(cr);
+  if ((tid & 31) == 0) { s_loss[tid >> 5] = l; s_corr[tid >> 5] = cr; }
+  __syncthreads();
+  if (tid == 0 && hist != nullptr) {
+    int slot = step != nullptr ? (*step - 1) : 0;
+    if (slot < 0) slot = 0;
+    if (hist_slots > 0) slot %= hist_slots;
+    atomicAdd(hist + 2 * slot, (s_loss[0] + s_loss[1] + s_loss[2] + s_loss[3]) * inv_b);
+    atomicAdd(hist + 2 * slot + 1, (s_corr[0] + s_corr[1] + s_corr[2] + s_corr[3]) * inv_b);
+  }
+}
+
+template <int MAXC>
+static int launch_head_small(const void* H, int ldh, const void* Wb, int ldw, const float* bias, const int* labels,
+                             const float* labels_dense, int B, int C, int K, void* dz, int ldz, void* dH, int lddh,
+                             float alpha, int use_mask, float* hist, const int* step, int hist_slots, void* stream) {
+  const size_t smem = static_cast<size_t>(C + 8) * (K / 2) * 4 + MAXC * 4 + 8 * 4;
+  DK_HOST_CHECK(DK_LAUNCH((dense_softmax_head_small_kernel<MAXC>), (B + 7) / 8, 128, smem, (cudaStream_t)stream,
+      reinterpret_cast<const __nv_bfloat16*>(H), ldh, reinterpret_cast<const __nv_bfloat16*>(Wb), ldw, bias, labels,
+      labels_dense, B, C, K, reinterpret_cast<__nv_bfloat16*>(dz), ldz, reinterpret_cast<__nv_bfloat16*>(dH), lddh,
+      alpha, use_mask, hist, step, hist_slots));
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // host-side dispatch of the fused head (class-count / chunk-count specialisations)
 template <int MAXC>
 static int launch_head(const void* H, int ldh, const void* Wb, int ldw, const float* bias, const int* labels,
                        const float* labels_dense, int B, int C, int K, void* dz, int ldz, void* dH, int lddh,
                        float alpha, int use_mask, float* hist, const int* step, int hist_slots, void* stream,
                        size_t smem) {
-  // B > 512: 4 warps x 8 rows per pass and block (R = 2).  Small batches are latency-bound: one row per 8-lane
-  // group (R = 1) and one warp (4 rows) per block, so the few rows spread over up to B / 4 SMs.
-  const bool small = B <= 512;
-  const int threads = small ? 32 : 128;
-  int blocks = small ? (B + 3) / 4 : (B + 31) / 32;
+  int blocks = (B + 31) / 32;                // 4 warps x 8 rows per pass
   if (blocks > 148 * 4) blocks = 148 * 4;    // resident blocks stage W once and walk their rows
   const int per_lane = (K / 8 + 7) / 8;      // 16-byte chunks each of the 8 lanes of a row owns
-#define DK_HEAD_LAUNCH(NCH, RR)                                                                                      \
-  DK_HOST_CHECK(DK_LAUNCH((dense_softmax_head_kernel<MAXC, NCH, RR>), blocks, threads, smem, (cudaStream_t)stream,   \
+#define DK_HEAD_LAUNCH(NCH)                                                                                          \
+  DK_HOST_CHECK(DK_LAUNCH((dense_softmax_head_kernel<MAXC, NCH, 2>), blocks, 128, smem, (cudaStream_t)stream,        \
       reinterpret_cast<const __nv_bfloat16*>(H), ldh, reinterpret_cast<const __nv_bfloat16*>(Wb), ldw, bias, labels, \
       labels_dense, B, C, K, reinterpret_cast<__nv_bfloat16*>(dz), ldz, reinterpret_cast<__nv_bfloat16*>(dH), lddh,  \
       alpha, use_mask, hist, step, hist_slots))
-  if (small) {
-    if (per_lane <= 2) { DK_HEAD_LAUNCH(2, 1); }
-    else if (per_lane <= 4) { DK_HEAD_LAUNCH(4, 1); }
-    else { DK_HEAD_LAUNCH(0, 1); }
-  } else {
-    if (per_lane <= 2) { DK_HEAD_LAUNCH(2, 2); }
-    else if (per_lane <= 4) { DK_HEAD_LAUNCH(4, 2); }
-    else { DK_HEAD_LAUNCH(0, 2); }
-  }
+  if (per_lane <= 2) { DK_HEAD_LAUNCH(2); }
+  else if (per_lane <= 4) { DK_HEAD_LAUNCH(4); }
+  else { DK_HEAD_LAUNCH(0); }
 #undef DK_HEAD_LAUNCH
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
@@ -560,6 +721,16 @@ int dk_dense_softmax_head(const void* H, int ldh, const void* Wb, int ldw, const
   if (C < 1 || C > kHeadMaxC || K % 8 != 0 || ldh % 8 != 0 || (dH != nullptr && lddh % 8 != 0) || ldz > kHeadMaxC ||
       ldz < C || ldz % 2 != 0 || ldw % 8 != 0 || smem > 48 * 1024)
     return -7;
+  if (B <= 512 && static_cast<size_t>(C + 8) * (K / 2) * 4 <= 40 * 1024) {  // latency-bound regime
+    if (C <= 2)
+      return launch_head_small<2>(H, ldh, Wb, ldw, bias, labels, labels_dense, B, C, K, dz, ldz, dH, lddh, alpha, use_mask,
+                                  hist, step, hist_slots, stream);
+    if (C <= 10)
+      return launch_head_small<10>(H, ldh, Wb, ldw, bias, labels, labels_dense, B, C, K, dz, ldz, dH, lddh, alpha, use_mask,
+                                   hist, step, hist_slots, stream);
+    return launch_head_small<16>(H, ldh, Wb, ldw, bias, labels, labels_dense, B, C, K, dz, ldz, dH, lddh, alpha, use_mask,
+                                 hist, step, hist_slots, stream);
+  }
   if (C <= 2)
     return launch_head<2>(H, ldh, Wb, ldw, bias, labels, labels_dense, B, C, K, dz, ldz, dH, lddh, alpha, use_mask, hist,
                           step, hist_slots, stream, smem);

@@ -28,6 +28,7 @@ class GemmEpilogue(C.Structure):
         ("bias", vp), ("bias_along_m", i32), ("act", i32), ("mask", vp), ("ld_mask", i32),
         ("d", vp), ("ldd", i32), ("d_fp32", i32), ("accumulate", i32), ("dt", vp), ("lddt", i32),
         ("alpha", f32), ("drop_p", f32), ("drop_seed", u32), ("step", vp), ("tma_store", i32), ("tma_mask", i32),
+        ("trace", vp),
     ]
 
 
@@ -51,7 +52,7 @@ class BwdUpdateDesc(C.Structure):
                 ("step", vp), ("done_counter", vp), ("step_inc", i32),
                 ("comm_mode", i32), ("comm_scale", f32), ("scale_dev", vp), ("alpha", f32),
                 ("nshards", i32), ("shard_per", i64), ("shard_center", vp * BWD_MAX_SHARDS),
-                ("ctrl", vp), ("worker", i32), ("last_update", vp)]
+                ("ctrl", vp), ("worker", i32), ("last_update", vp), ("trace", vp)]
 
 
 # op kinds (csrc/engine.h)
@@ -62,7 +63,7 @@ OP_LOCK_ACQUIRE, OP_LOCK_RELEASE, OP_EAMSGD_PRE, OP_EAMSGD_POST, OP_CAST, OP_ELO
 OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D, OP_FORK, OP_JOIN, OP_GEMM_PULL = 25, 26, 27, 28, 29, 30, 31
 OP_BN_FWD, OP_BN_INF, OP_BN_BWD, OP_GAP_FWD, OP_GAP_BWD, OP_HEAD = 32, 33, 34, 35, 36, 37
 OP_CONV_GEMM, OP_WFLIP, OP_CONV_WGRAD, OP_BWD_UPDATE = 38, 39, 40, 41
-GEMM_TF32, GEMM_A_MN, GEMM_B_MN, GEMM_PERSISTENT, GEMM_PAIR = 1, 2, 4, 8, 16
+GEMM_TF32, GEMM_A_MN, GEMM_B_MN, GEMM_PERSISTENT, GEMM_PAIR, GEMM_SHORT_A = 1, 2, 4, 8, 16, 32
 
 OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6}
 IN_U8, IN_F32, IN_BF16 = 0, 1, 2

@@ -226,6 +226,10 @@ class NativeReplica(Replica):
             if self.pull_center_ptr or self.comm_spec:
                 self.W1 = self.W.clone()
         self._keep: list = []  # buffers referenced only by raw pointers
+        # DK_TRACE=1: every GEMM / fused-update op of the training lists stamps the SM clock of its first CTA
+        # at fixed points into a row of this buffer (tools/kernel_timeline.py)
+        self._trace = torch.zeros(64, 8, dtype=torch.int64, device=dev) if os.environ.get("DK_TRACE") == "1" else None
+        self._trace_names: list = []
         self.engine = self.lib.dk_engine_create()
         # L_step: training forward; L_bwd: loss + backward + optimizer; L_fwd: inference forward;
         # L_step_pull: training forward whose first GEMM pulls its weights from the PS (fused pull)
@@ -285,8 +289,16 @@ class NativeReplica(Replica):
         if r < 0:
             raise RuntimeError(f"dk_engine_add_op({kind}) failed: {r}")
 
+    def _trace_row(self, name: str) -> int:
+        """Device address of the next trace row (0 when tracing is off)."""
+        if self._trace is None or len(self._trace_names) >= self._trace.shape[0]:
+            return 0
+        self._trace_names.append(name)
+        return self._trace.data_ptr() + 64 * (len(self._trace_names) - 1)
+
     def _gemm(self, lst: int, A: int, lda: int, Bp: int, ldb: int, M: int, Nn: int, K: int, flags: int,
               ep: N.GemmEpilogue, bn: int = 0, splits: int = 0) -> None:
+        ep.trace = self._trace_row(f"list{lst} gemm M={M} N={Nn} K={K} flags={flags} bn={bn}") or None
         r = self.lib.dk_engine_add_gemm(self.engine, lst, C.c_void_p(A), lda, C.c_void_p(Bp), ldb, M, Nn, K,
                                         flags, bn, splits, C.byref(ep))
         if r < 0:
@@ -451,6 +463,7 @@ class NativeReplica(Replica):
                     raise UnsupportedByNativeEngine("parameter-server shards must be equal-sized and contiguous")
                 d.shard_center[i] = ptr
             d.ctrl, d.worker, d.last_update = c["ctrl"], int(c["worker"]), c.get("last_update") or None
+        d.trace = self._trace_row(f"list{lst} bwd_update comm={int(with_comm)}") or None
         r = self.lib.dk_engine_add_bwd_update(self.engine, lst, C.byref(d))
         if r < 0:
             raise RuntimeError(f"dk_engine_add_bwd_update failed: {r}")
@@ -568,13 +581,15 @@ class NativeReplica(Replica):
                     raise RuntimeError(f"dk_engine_add_conv_gemm(fwd) failed: {r}")
                 continue
             bn = self._narrow_bn(rows, Nout, 16) if self.compact else 0
+            fl = N.GEMM_SHORT_A if (self.compact and rows < 128) else 0   # one short M tile: short TMA box
             if a_in.get("slot") is not None:
+                ep.trace = self._trace_row(f"list{lst} gemm(slot) M={rows} N={Nout} K={K} bn={bn}") or None
                 r = self.lib.dk_engine_add_gemm_slot(self.engine, lst, a_in["slot"], a_in["ld"], C.c_void_p(wbp), wbld,
-                                                     rows, Nout, K, 0, bn, 1, C.byref(ep))
+                                                     rows, Nout, K, fl, bn, 1, C.byref(ep))
                 if r < 0:
                     raise RuntimeError(f"dk_engine_add_gemm_slot(M={rows}, N={Nout}, K={K}) failed: {r}")
                 continue
-            self._gemm(lst, a_in["t"].data_ptr(), a_in["ld"], wbp, wbld, rows, Nout, K, 0, ep, bn=bn,
+            self._gemm(lst, a_in["t"].data_ptr(), a_in["ld"], wbp, wbld, rows, Nout, K, fl, ep, bn=bn,
                        splits=1 if bn else 0)
         b.out_rec = rec
 
@@ -624,8 +639,8 @@ class NativeReplica(Replica):
                         ep.alpha = 1.0 / (1.0 - prev.drop_p)
                 elif prev is not None and prev.kind == "dense" and prev.drop_p > 0:
                     raise UnsupportedByNativeEngine("dropout after a non-ReLU dense layer")
-                self._gemm(lst, grad["t"].data_ptr(), grad["ld"], wbp, wbld, rows, K, Nout, N.GEMM_B_MN, ep,
-                           bn=self._narrow_bn(rows, K, 64), splits=1)
+                self._gemm(lst, grad["t"].data_ptr(), grad["ld"], wbp, wbld, rows, K, Nout,
+                           N.GEMM_B_MN | (N.GEMM_SHORT_A if rows < 128 else 0), ep, bn=self._narrow_bn(rows, K, 64), splits=1)
                 return dict(t=din, rows=rows, cols=K, ld=_r8(K)), fuse_mask
             two = self._side_streams >= 2
             s_bias = 2 if two else (1 if need_dx else 0)

@@ -792,6 +792,23 @@ def _affine_for(dataset: Dataset, features_col: str):
     return "f32", (1.0, 0.0)
 
 
+def setup_center_shards(model, rank: int, world: int, local: int, exchange_obj):
+    """Sharded parameter server: slice r of the flat center variable lives in rank r's HBM (the reference's
+    "multiple parameter servers" TODO, ``README.md:218``).  Every rank allocates its slice, exports it over CUDA
+    IPC and maps all the others.  Returns (regions, [(lo, hi, center_ptr)], bounds); slices are equal-sized
+    (a multiple of 8 elements) so a kernel finds the owner of element ``i`` as ``i // per``."""
+    P_total = model.num_params
+    per = ((P_total + world - 1) // world + 7) // 8 * 8
+    bounds = [(min(r * per, P_total), min((r + 1) * per, P_total)) for r in range(world)]
+    init_flat = model.get_flat_weights()
+    lo, hi = bounds[rank]
+    mine = FabricRegion.create(init_flat[lo:hi] if hi > lo else torch.zeros(8), local)
+    infos = [exchange_obj(mine.export() if r == rank else None, r) for r in range(world)]
+    regions = [mine if r == rank else FabricRegion.open(infos[r], local) for r in range(world)]
+    shards = [(bounds[r][0], bounds[r][1], regions[r].center_ptr) for r in range(world) if bounds[r][1] > bounds[r][0]]
+    return regions, shards, bounds
+
+
 def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, barrier) -> dict:
     """Body shared by the SPMD (torchrun) and the spawned modes.  ``exchange_obj(obj, src)``
     broadcasts a picklable object from rank ``src``; ``barrier()`` synchronises all ranks."""
@@ -829,17 +846,9 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
         _group_layers(model)
     except UnsupportedByNativeEngine:
         native_supported = False  # same answer on every rank: the eager worker uses the unsharded center
+    bounds = []
     if getattr(trainer, "sharded_ps", False) and world > 1 and native_supported:
-        P_total = model.num_params
-        per = ((P_total + world - 1) // world + 7) // 8 * 8
-        bounds = [(min(r * per, P_total), min((r + 1) * per, P_total)) for r in range(world)]
-        init_flat = model.get_flat_weights()
-        lo, hi = bounds[rank]
-        mine = FabricRegion.create(init_flat[lo:hi] if hi > lo else torch.zeros(8), local)
-        infos = [exchange_obj(mine.export() if r == rank else None, r) for r in range(world)]
-        shard_regions = [mine if r == rank else FabricRegion.open(infos[r], local) for r in range(world)]
-        shards = [(bounds[r][0], bounds[r][1], shard_regions[r].center_ptr) for r in range(world)
-                  if bounds[r][1] > bounds[r][0]]
+        shard_regions, shards, bounds = setup_center_shards(model, rank, world, local, exchange_obj)
     checkpointer = None
     if rank == 0 and getattr(trainer, "checkpoint_path", None) and getattr(trainer, "checkpoint_interval", None):
         checkpointer = CenterCheckpointer(model, region, trainer.checkpoint_path, trainer.checkpoint_interval, local,

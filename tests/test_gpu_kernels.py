@@ -339,7 +339,7 @@ def test_col2im_fused_mask(N):
     assert torch.equal(masked, torch.where(mask.float() > 0, plain, torch.zeros_like(plain)))
 
 
-@pytest.mark.parametrize("B,Cc,K,dense,use_mask", [(256, 10, 200, False, True), (100, 2, 504, True, False),
+@pytest.mark.parametrize("B,Cc,K,dense,use_mask", [(256, 10, 200, False, True), (100, 2, 504, True, False), (64, 10, 200, False, True),
                                                   (33, 16, 64, False, True), (4096, 10, 1024, False, True)])
 def test_fused_classifier_head(N, B, Cc, K, dense, use_mask):
     """logits GEMM + softmax cross-entropy + dgrad (+ dReLU mask) in one kernel vs PyTorch fp32."""
