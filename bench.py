@@ -296,6 +296,10 @@ def main() -> None:
         cal_ms = statistics.median(a.elapsed_time(b) for a, b in cal)
         R = args.reps if args.reps > 0 else int(min(4000, max(50, 1000.0 / max(cal_ms, 1e-3))))
         R += (-R) % period
+    else:
+        R = 0
+    R = max(gather(R))        # every rank times the same number of regions
+    if is_worker:
         worker.launched = worker.exchanges = 0
         barrier()
         sampler.mark_start()
@@ -391,7 +395,7 @@ def main() -> None:
 
     if rank == 0:
         per_rank_ms = [sum(r["rep_ms"]) / (len(r["rep_ms"]) * K) for r in wk]
-        slow = max(wk, key=lambda r: sum(r["rep_ms"]))
+        slow = max(wk, key=lambda r: sum(r["rep_ms"]) / len(r["rep_ms"]))
         ms_per_step = sum(slow["rep_ms"]) / (len(slow["rep_ms"]) * K)
         value = n_workers * B / (ms_per_step * 1e-3)
         x_us = max(r["exchange_us"] for r in wk)
