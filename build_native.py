@@ -26,7 +26,7 @@ NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "--extended-lambda", "-Xc
                      "-Xcompiler", "-fvisibility=default"]
 
 SOURCES = ["gemm_tcgen05.cu", "ps_kernels.cu", "optim_kernels.cu", "loss_kernels.cu", "nn_kernels.cu",
-           "fabric.cu", "dense_fused.cu", "engine.cu"]
+           "fabric.cu", "dense_fused.cu", "conv_tma.cu", "engine.cu"]
 
 
 def nvcc() -> str:

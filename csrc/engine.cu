@@ -105,6 +105,9 @@ int run_op(Engine* e, Op& op, void* main_stream) {
                                  rp<float>(e, a[3]), rp<float>(e, a[4]), resolve(e, a[5]), (int)a[6], st);
     case DK_OP_CONV_GEMM:
       // src, SH, SW, C, GH, GW, KH, KW, mul, off, div, M, N, K, bn (weight / output / mask maps + epilogue pre-encoded)
+      if (a[15])
+        return dk_conv_tma_launch(&op.ta, &op.tb, op.has_td ? &op.td : nullptr, op.has_tm ? &op.tm : nullptr, &op.ep, (int)a[3],
+                                  (int)a[4], (int)a[5], (int)a[6], (int)a[7], (int)a[8], (int)a[9], (int)a[11], (int)a[12], st);
       return dk_conv_gemm_launch(resolve(e, a[0]), (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], (int)a[6],
                                  (int)a[7], (int)a[8], (int)a[9], (int)a[10], &op.tb, op.has_td ? &op.td : nullptr,
                                  op.has_tm ? &op.tm : nullptr, &op.ep, (int)a[11], (int)a[12], (int)a[13], (int)a[14], st);
@@ -442,9 +445,27 @@ int dk_engine_add_conv_gemm(void* h, int list, const void* src, int SH, int SW, 
   op.dyn_a_slot = -1;
   op.kind = DK_OP_CONV_GEMM;
   op.stream_id = e->build_stream;
-  const int bn = dk_conv_pick_bn(N);
-  int r = dk_tmap_encode_2d(&op.tb, Bmat, DK_BF16, N, K, ldb, bn);
+  // TMA-im2col persistent kernel when the geometry allows it (C a multiple of 64 or exactly 32, undilated);
+  // the thread-gather kernel otherwise.  DK_CONV_TMA=0 forces the gather kernel (A/B runs).
+  static int tma_env = -1;
+  if (tma_env < 0) {
+    const char* te = getenv("DK_CONV_TMA");
+    tma_env = (te != nullptr && te[0] == '0') ? 0 : 1;
+  }
+  const bool use_tma = tma_env && dk_conv_tma_supported(C, div, N, ep->ldd, ep->d_fp32) && ep->d != nullptr && ep->dt == nullptr &&
+                       (ep->mask == nullptr || (ep->ld_mask % 8) == 0) && M % (GH * GW) == 0;
+  const int bn = use_tma ? dk_conv_tma_bn(N) : dk_conv_pick_bn(N);
+  int r;
+  if (use_tma) {
+    const int chan = C % 64 == 0 ? 64 : 32;
+    r = dk_conv_tma_encode_a(&op.ta, src, M / (GH * GW), SH, SW, C, GH, GW, mul, off, chan);
+    if (r != 0) return r;
+    r = dk_conv_tma_encode_b(&op.tb, Bmat, ldb, N, K, bn, chan);
+  } else {
+    r = dk_tmap_encode_2d(&op.tb, Bmat, DK_BF16, N, K, ldb, bn);
+  }
   if (r != 0) return r;
+  op.i[15] = use_tma ? 1 : 0;
   op.ep = *ep;
   op.has_td = ep->d != nullptr && dk_gemm_encode_output(&op.td, ep->d, ep->ldd, M, N, ep->d_fp32) == 0;
   op.has_tm = ep->mask != nullptr && dk_gemm_encode_output(&op.tm, ep->mask, ep->ld_mask, M, N, 0) == 0;

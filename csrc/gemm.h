@@ -62,6 +62,17 @@ int dk_conv_gemm_launch(const void* src, int SH, int SW, int C, int GH, int GW, 
                         int div, const void* tmap_b, const void* tmap_d, const void* tmap_m, const DkGemmEpilogue* ep,
                         int M, int N, int K, int bn, void* stream);
 int dk_conv_pick_bn(int N);
+// implicit-GEMM convolution fed by TMA im2col descriptors (conv_tma.cu): persistent, double-buffered TMEM
+int dk_conv_tma_supported(int C, int div, int N, int ldd, int d_fp32);
+int dk_conv_tma_encode_a(void* out_tmap, const void* src, int B, int SH, int SW, int C, int GH, int GW, int mul, int off,
+                         int chan);
+int dk_conv_tma_encode_b(void* out_tmap, const void* W, long ldw, int N, int K, int bn, int chan);
+int dk_conv_tma_bn(int N);
+int dk_conv_tma_launch(const void* tmap_a, const void* tmap_b, const void* tmap_d, const void* tmap_m,
+                       const DkGemmEpilogue* ep, int C, int GH, int GW, int KH, int KW, int mul, int off, int M, int N,
+                       void* stream);
+int dk_conv_tma(const void* src, int B, int SH, int SW, int C, int GH, int GW, int KH, int KW, int mul, int off,
+                const void* Wmat, long ldw, const DkGemmEpilogue* ep, int M, int N, void* stream);
 int dk_conv_gather_mode(int mode);
 int dk_conv_gemm(const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW, int mul, int off, int div,
                  const void* Bmat, long ldb, const DkGemmEpilogue* ep, int M, int N, int K, void* stream);

@@ -87,6 +87,8 @@ _SIGNATURES = {
     "dk_conv_gemm": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, C.POINTER(GemmEpilogue), i32, i32,
                            i32, vp]),
     "dk_conv_weight_flip": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "dk_conv_tma": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, C.POINTER(GemmEpilogue), i32, i32, vp]),
+    "dk_conv_tma_supported": (i32, [i32, i32, i32, i32, i32]),
     "dk_conv_pick_bn": (i32, [i32]),
     "dk_conv_gather_mode": (i32, [i32]),
     "dk_conv_wgrad": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, i64, i32, i32, i32, vp]),

@@ -516,7 +516,10 @@ class NativeReplica(Replica):
             # implicit GEMM (DK_IMPLICIT_CONV=1): the forward and dgrad GEMMs gather their A operand from
             # the NHWC activation inside the kernel; the column matrix is then only needed by the wgrad
             # GEMM, so im2col moves off the critical path onto the wgrad branch of the backward list
-            implicit = (os.environ.get("DK_IMPLICIT_CONV", "0") == "1" and Cin % 8 == 0 and Nout % 8 == 0
+            # default: layers the TMA-im2col kernel can feed (Cin a multiple of 64, or exactly 32); DK_IMPLICIT_CONV=1
+            # also sends the other Cin % 8 == 0 layers to the thread-gather kernel, DK_IMPLICIT_CONV=0 disables both
+            mode = os.environ.get("DK_IMPLICIT_CONV", "auto")
+            implicit = (mode != "0" and (mode == "1" or Cin % 64 == 0 or Cin == 32) and Cin % 8 == 0 and Nout % 8 == 0
                         and cur["ld"] == Cin and wbld == K and b.kh == b.kw and not is_last)
             im2col_args = [cur["t"].data_ptr(), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad, OH, OW, col.data_ptr(), _r8(K)]
             # EXPERIMENTAL (DK_IMPLICIT_WGRAD=1, needs DK_IMPLICIT_CONV=1): the wgrad gathers too, so no column

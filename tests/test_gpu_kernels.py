@@ -419,12 +419,10 @@ def test_implicit_gemm_conv_forward_and_dgrad(N, B, H, Cin, Cout, k, stride, pad
     assert torch.allclose(dx.float(), gref, atol=0.03 * float(gref.abs().max()) + 1e-3, rtol=3e-2)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DK_EXPERIMENTAL") != "1",
-                    reason="conv_wgrad_kernel has not been validated on hardware yet (set DK_EXPERIMENTAL=1 to run)")
 @pytest.mark.parametrize("B,H,Cin,Cout,k,stride,pad,splits", [(4, 16, 32, 32, 3, 1, 1, 4), (3, 14, 32, 64, 3, 1, 0, 1),
                                                               (2, 12, 64, 64, 3, 2, 1, 3)])
 def test_implicit_gemm_conv_wgrad_experimental(N, B, H, Cin, Cout, k, stride, pad, splits):
-    """EXPERIMENTAL implicit weight gradient vs autograd (first thing to validate in the next GPU session)."""
+    """Implicit weight gradient (cp.async gather of the MN-major B operand) vs autograd."""
     torch.manual_seed(19)
     OH = (H + 2 * pad - k) // stride + 1
     x = bf(torch.randn(B, H, H, Cin, device="cuda"))
@@ -515,3 +513,43 @@ def test_fused_dense_backward_update_kernel(N, B, comm, opt):
         assert torch.allclose(s0, s0r, atol=1e-4, rtol=1e-3) and torch.allclose(s1, s1r, atol=1e-5, rtol=1e-2)
     assert torch.allclose(Wb.float(), W, atol=1e-2, rtol=1e-2)
     assert int(step) == 4 and int(done) == 0
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,k,stride,pad", [(4, 16, 32, 32, 3, 1, 1), (3, 14, 32, 64, 3, 1, 0), (2, 12, 64, 64, 3, 2, 1),
+                                                       (5, 9, 64, 24, 1, 1, 0), (2, 30, 32, 32, 3, 1, 0), (3, 10, 128, 160, 3, 1, 1)])
+def test_tma_im2col_conv_forward_and_dgrad(N, B, H, Cin, Cout, k, stride, pad):
+    """Persistent implicit-GEMM convolution whose A operand is produced by TMA im2col descriptors
+    (cp.async.bulk.tensor.4d...im2col): forward with bias + ReLU, and (stride 1) the input gradient with a fused
+    dReLU mask, against F.conv2d / autograd."""
+    torch.manual_seed(23)
+    OH = (H + 2 * pad - k) // stride + 1
+    x = bf(torch.randn(B, H, H, Cin, device="cuda"))
+    w = bf(torch.randn(Cout, k, k, Cin, device="cuda") * 0.1)
+    bias = torch.randn(Cout, device="cuda")
+    K, M = k * k * Cin, B * OH * OH
+    ldo = (Cout + 7) // 8 * 8
+    out = torch.zeros(M, ldo, dtype=torch.bfloat16, device="cuda")
+    ep = N.GemmEpilogue()
+    ep.d, ep.ldd, ep.alpha, ep.bias, ep.act = out.data_ptr(), ldo, 1.0, bias.data_ptr(), 1
+    N.check(N.lib().dk_conv_tma(x.data_ptr(), B, H, H, Cin, OH, OH, k, k, stride, pad, w.data_ptr(), K, C.byref(ep), M, Cout,
+                                st()), "conv tma fwd")
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.float().permute(0, 3, 1, 2)
+    pre = F.conv2d(xr, wr, bias, stride=stride, padding=pad)
+    ref = torch.relu(pre).permute(0, 2, 3, 1).reshape(M, Cout)
+    assert torch.allclose(out[:, :Cout].float(), ref, atol=0.03 * K ** 0.5 * 0.1 + 0.02, rtol=2e-2)
+    if stride != 1 or not N.lib().dk_conv_tma_supported(Cout, 1, Cin, Cin, 0):
+        return
+    dz = bf(torch.randn(B, OH, OH, Cout, device="cuda"))
+    wd = torch.zeros(Cin, k * k * Cout, dtype=torch.bfloat16, device="cuda")
+    N.check(N.lib().dk_conv_weight_flip(w.data_ptr(), K, wd.data_ptr(), k * k * Cout, Cout, Cin, k, k, st()), "flip")
+    mask = bf(torch.randn(B * H * H, Cin, device="cuda"))
+    dx = torch.zeros(B * H * H, Cin, dtype=torch.bfloat16, device="cuda")
+    ep2 = N.GemmEpilogue()
+    ep2.d, ep2.ldd, ep2.alpha, ep2.mask, ep2.ld_mask = dx.data_ptr(), Cin, 1.0, mask.data_ptr(), Cin
+    N.check(N.lib().dk_conv_tma(dz.data_ptr(), B, OH, OH, Cout, H, H, k, k, 1, k - 1 - pad, wd.data_ptr(), k * k * Cout,
+                                C.byref(ep2), B * H * H, Cin, st()), "conv tma dgrad")
+    pre.backward(dz.float().permute(0, 3, 1, 2))
+    gref = xr.grad.permute(0, 2, 3, 1).reshape(B * H * H, Cin)
+    gref = torch.where(mask.float() > 0, gref, torch.zeros_like(gref))
+    assert torch.allclose(dx.float(), gref, atol=0.03 * float(gref.abs().max()) + 1e-3, rtol=3e-2)

@@ -72,18 +72,20 @@ def test_compact_lowering_of_small_batch_mlp(monkeypatch, native_lib):
 def test_default_lowering(model_name, batch, monkeypatch, native_lib):
     lib, sizes = _lower(model_name, batch, monkeypatch, native_lib)
     assert sizes["L_step"] > 0 and sizes["L_bwd"] > sizes["L_step"] // 2 and sizes["L_fwd"] > 0
-    assert lib.calls["dk_engine_add_gemm"] > 0 and lib.calls["dk_engine_add_conv_gemm"] == 0
+    assert lib.calls["dk_engine_add_gemm"] > 0
+    # implicit (TMA-im2col) convolution is the default for layers with 32 / 64k input channels
+    assert (lib.calls["dk_engine_add_conv_gemm"] > 0) == (model_name in ("mnist_convnet", "cifar10_cnn", "resnet18"))
     assert lib.ops["OP_OPTIM"] == 1 and lib.ops["OP_FORK"] == lib.ops["OP_FORK"]  # one optimizer launch per step
     if model_name in ("mnist_mlp", "cifar10_cnn"):  # head input width is a multiple of 8 (200 / 512)
         assert lib.ops["OP_HEAD"] == 1 and lib.ops["OP_XENT"] == 1  # fused head in training, softmax kernel in inference
     elif model_name in ("higgs_mlp", "mnist_convnet"):  # 500 / 225 inputs: the three-kernel head
         assert lib.ops["OP_HEAD"] == 0 and lib.ops["OP_XENT"] == 2
     if "cnn" in model_name or "convnet" in model_name:
-        assert lib.ops["OP_RELU_MASK"] == 0  # every conv dReLU is fused into col2im / pool backward
+        assert lib.ops["OP_RELU_MASK"] == 0  # every conv dReLU is fused into the dgrad epilogue / col2im / pool backward
 
 
 @pytest.mark.parametrize("env", [dict(DK_FUSED_HEAD="0"), dict(DK_SIDE_STREAMS="1"), dict(DK_IMPLICIT_CONV="1"),
-                                 dict(DK_IMPLICIT_CONV="1", DK_IMPLICIT_WGRAD="1")],
+                                 dict(DK_IMPLICIT_CONV="1", DK_IMPLICIT_WGRAD="1"), dict(DK_IMPLICIT_CONV="0")],
                          ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 @pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 512), ("cifar10_cnn", 32), ("resnet18", 4)])
 def test_lowering_under_every_switch(model_name, batch, env, monkeypatch, native_lib):
@@ -92,11 +94,13 @@ def test_lowering_under_every_switch(model_name, batch, env, monkeypatch, native
     conv_model = model_name != "mnist_mlp"
     if env.get("DK_FUSED_HEAD") == "0":
         assert lib.ops["OP_HEAD"] == 0 and lib.ops["OP_XENT"] == 2
+    if env.get("DK_IMPLICIT_CONV") == "0":
+        assert lib.calls["dk_engine_add_conv_gemm"] == 0
     if env.get("DK_IMPLICIT_CONV") == "1" and conv_model:
         assert lib.calls["dk_engine_add_conv_gemm"] > 0 and lib.ops["OP_WFLIP"] > 0
         if env.get("DK_IMPLICIT_WGRAD") == "1":
             assert lib.calls["dk_engine_add_conv_wgrad"] > 0
         else:
             assert lib.calls["dk_engine_add_conv_wgrad"] == 0 and lib.ops["OP_IM2COL"] > 0
-    if env.get("DK_SIDE_STREAMS") == "1":
+    if env.get("DK_SIDE_STREAMS") == "1" and not conv_model:  # conv models also join the im2col branch per layer
         assert lib.ops["OP_JOIN"] == 1
