@@ -301,6 +301,195 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Weight gradient of a convolution with the im2col operand produced by TMA:
+//     dW[co, (kh, kw, c)] += sum_m dZ[m, co] * X[b(m), y(m) s - p + kh, x(m) s - p + kw, c]
+// i.e. D[M = Cout, N = taps * C] = A^T B with GEMM-K = the B * OH * OW output positions.  Per 64 positions the
+// producer issues ONE tiled load of dZ (MN-major A) and one im2col load per (tap, 64-channel chunk) "unit"
+// (MN-major B: [64 positions x chan channels], exactly what an im2col load writes); the MMA warp issues
+// 4 tcgen05.mma per unit into that unit's TMEM column range, so the whole [Cout x units * chan] gradient block
+// stays in TMEM while the CTA streams its share of the positions (split-K across the persistent grid), and
+// is added into the fp32 gradient with TMA reduce-add at the end.  The bias gradient (column sums of dZ)
+// comes from one more N = 16 MMA against a tile of ones.  No column matrix, no im2col / colsum kernels.
+// ---------------------------------------------------------------------------------------------
+struct WgradGeom {
+  int GH, GW, mul, off;
+  int KW, c_chunks;        // filter width, C / chan
+  int unit0, units;        // (tap, channel-chunk) units handled by this launch: unit = tap * c_chunks + chunk
+  int total_pb;            // 64-position blocks
+  int Cout, Ktot;          // dW is [Cout, Ktot] fp32
+};
+
+template <int CHAN>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_d, const WgradGeom g, float* __restrict__ bias_grad,
+                      const int stages, const int stage_bytes) {
+  constexpr int kABytes = 128 * 128;               // dZ^T tile: two [64 positions x 64 co] boxes
+  constexpr int kUnitBytes = 64 * CHAN * 2;        // one im2col box
+  constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kIdesc = make_idesc(1u, 128, CHAN) | (1u << 15) | (1u << 16);   // A and B MN-major
+  constexpr uint32_t kIdescBias = make_idesc(1u, 128, 16) | (1u << 15);
+  constexpr uint32_t kStepA = 2048 >> 4;           // 16 positions x 128 B
+  constexpr uint32_t kStepB = (16 * CHAN * 2) >> 4;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* ones = smem + stages * stage_bytes;
+  uint8_t* out_stage = ones + 2048;                // 4 epilogue warps x 4 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + 4 * 4096);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full_bar = empty_bar + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int per = (g.total_pb + gridDim.x - 1) / gridDim.x;
+  const int pb_begin = blockIdx.x * per;
+  const int pb_end = min(g.total_pb, pb_begin + per);
+  const int num_pb = pb_end - pb_begin;
+  const bool do_bias = bias_grad != nullptr;
+  if (num_pb <= 0) return;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_d);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    st_shared_v4(smem_u32(ones) + t * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  DK_PDL_WAIT();
+  DK_PDL_TRIGGER();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * stage_bytes;
+        mbar_expect_tx(&full_bar[stage], kABytes + g.units * kUnitBytes);
+        const int m0 = pb * 64;
+        tma_load_2d(sa, &tmap_a, 0, m0, &full_bar[stage]);
+        tma_load_2d(sa + 8192, &tmap_a, 64, m0, &full_bar[stage]);
+        const int b = m0 / (g.GH * g.GW);
+        const int rem = m0 - b * g.GH * g.GW;
+        const int y = rem / g.GW, x = rem - y * g.GW;
+        const int w0 = x * g.mul - g.off, h0 = y * g.mul - g.off;
+        int unit = g.unit0;
+        int tap = unit / g.c_chunks, cc = unit - tap * g.c_chunks;
+        int kh = tap / g.KW, kw = tap - kh * g.KW;
+        for (int u = 0; u < g.units; ++u) {
+          tma_load_im2col_4d(sa + kABytes + u * kUnitBytes, &tmap_b, cc * CHAN, w0, h0, b, kw, kh, &full_bar[stage]);
+          if (++cc == g.c_chunks) {
+            cc = 0;
+            if (++kw == g.KW) { kw = 0; ++kh; }
+          }
+        }
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < num_pb; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint64_t adesc = make_smem_desc_sw128_mn(sa);
+        const uint64_t odesc = make_smem_desc_sw128(smem_u32(ones));
+        for (int u = 0; u < g.units; ++u) {
+          // MN-major B tile of [64 positions][CHAN channels]: 8-position groups CHAN * 16 bytes apart
+          uint64_t bdesc = 0;
+          const uint32_t sb = sa + kABytes + u * kUnitBytes;
+          bdesc |= static_cast<uint64_t>((sb & 0x3FFFF) >> 4);
+          bdesc |= static_cast<uint64_t>(1) << 16;
+          bdesc |= static_cast<uint64_t>((8 * CHAN * 2) >> 4) << 32;
+          bdesc |= static_cast<uint64_t>(1) << 46;
+          bdesc |= static_cast<uint64_t>(CHAN == 64 ? 2 : 4) << 61;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + u * CHAN, adesc + kStepA * k, bdesc + kStepB * k, kIdesc, (i | k) != 0);
+        }
+        if (do_bias) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + 496, adesc + kStepA * k, odesc + 2 * k, kIdescBias, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (i == num_pb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
+    // ---- epilogue: TMEM -> swizzled smem -> TMA reduce-add into the fp32 gradient (rows = co) ----
+    const int quarter = warp & 3;
+    const int co = quarter * 32 + lane;
+    const uint32_t region = smem_u32(out_stage) + (warp - 2) * 4096;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    if (quarter * 32 < g.Cout) {
+      const int ncols = g.units * CHAN;
+      const int n_base = g.unit0 * CHAN;   // units are contiguous in the (tap, c) column order
+#pragma unroll 1
+      for (int c = 0; c < ncols; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(trow + c, r);
+        tmem_ld_wait();
+        if (lane == 0) tma_store_wait_read<0>();   // the previous chunk's reduce has read the staging slot
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 8; ++t) st_shared_v4(region + sw128_off(lane, t), r[4 * t], r[4 * t + 1], r[4 * t + 2], r[4 * t + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tmap_d, region, n_base + c, quarter * 32);
+          tma_store_commit();
+        }
+      }
+      if (do_bias) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(trow + 496, r);
+        tmem_ld_wait();
+        if (co < g.Cout) atomicAdd(bias_grad + co, __uint_as_float(r[0]));
+      }
+      if (lane == 0) tma_store_wait_read<0>();
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                      const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -358,8 +547,16 @@ int dk_conv_tma_supported(int C, int div, int N, int ldd, int d_fp32) {
 
 // im2col tensor map over the NHWC activation S [B, SH, SW, C] (bf16) for a GH x GW grid of output positions:
 // base pixel of position (y, x) = (y * mul - off, x * mul - off); 128 positions x `chan` channels per load.
+static int encode_im2col(void* out_tmap, const void* src, int B, int SH, int SW, int C, int GH, int GW, int mul, int off,
+                         int chan, int pixels);
+
 int dk_conv_tma_encode_a(void* out_tmap, const void* src, int B, int SH, int SW, int C, int GH, int GW, int mul, int off,
                          int chan) {
+  return encode_im2col(out_tmap, src, B, SH, SW, C, GH, GW, mul, off, chan, dk::kConvBlockM);
+}
+
+static int encode_im2col(void* out_tmap, const void* src, int B, int SH, int SW, int C, int GH, int GW, int mul, int off,
+                         int chan, int pixels) {
   auto fn = dk::get_im2col_fn();
   if (fn == nullptr) return -1;
   if ((reinterpret_cast<uintptr_t>(src) & 15) != 0 || (C * 2) % 16 != 0) return -2;
@@ -372,7 +569,7 @@ int dk_conv_tma_encode_a(void* out_tmap, const void* src, int B, int SH, int SW,
   int upper[2] = {(GW - 1) * mul - off - (SW - 1), (GH - 1) * mul - off - (SH - 1)};
   cuuint32_t estride[4] = {1, static_cast<cuuint32_t>(mul), static_cast<cuuint32_t>(mul), 1};
   CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_tmap), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim,
-                  gstride, lower, upper, static_cast<cuuint32_t>(chan), dk::kConvBlockM, estride,
+                  gstride, lower, upper, static_cast<cuuint32_t>(chan), static_cast<cuuint32_t>(pixels), estride,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, chan == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -100 - static_cast<int>(r);
@@ -421,6 +618,90 @@ int dk_conv_tma_launch(const void* tmap_a, const void* tmap_b, const void* tmap_
 }
 
 int dk_conv_tma_bn(int N) { return N <= 64 ? 64 : 128; }
+
+// units (tap, channel chunk) one wgrad launch can hold: TMEM columns (496 + 16 for the bias gradient) and two
+// pipeline stages of shared memory
+int dk_conv_wgrad_tma_units(int C) {
+  const int chan = C % 64 == 0 ? 64 : 32;
+  const int by_tmem = 496 / chan;
+  const int by_smem = (96 * 1024 - 16384) / (64 * chan * 2);
+  return by_tmem < by_smem ? by_tmem : by_smem;
+}
+
+int dk_conv_wgrad_tma_supported(int C, int Cout, long lddz, long lddw) {
+  return ((C % 64 == 0 || C == 32) && Cout <= 128 && Cout % 8 == 0 && lddz % 8 == 0 && lddw % 4 == 0) ? 1 : 0;
+}
+
+int dk_conv_wgrad_tma_encode(void* tmap_a, void* tmap_b, void* tmap_d, const void* src, int B, int SH, int SW, int C, int GH,
+                             int GW, int KH, int KW, int stride, int pad, const void* dz, long lddz, float* dw, long lddw,
+                             int Cout) {
+  const int chan = C % 64 == 0 ? 64 : 32;
+  int r = dk_tmap_encode_2d(tmap_a, dz, DK_BF16, static_cast<long>(B) * GH * GW, Cout, lddz, 64);
+  if (r != 0) return r;
+  r = encode_im2col(tmap_b, src, B, SH, SW, C, GH, GW, stride, pad, chan, 64);
+  if (r != 0) return r;
+  return dk_gemm_encode_output(tmap_d, dw, lddw, Cout, KH * KW * C, 1);
+}
+
+int dk_conv_wgrad_tma_launch(const void* tmap_a, const void* tmap_b, const void* tmap_d, int B, int C, int GH, int GW, int KH,
+                             int KW, int stride, int pad, int Cout, int unit0, int units, float* bias_grad, void* stream) {
+  const int chan = C % 64 == 0 ? 64 : 32;
+  dk::WgradGeom g;
+  g.GH = GH; g.GW = GW; g.mul = stride; g.off = pad; g.KW = KW; g.c_chunks = C / chan; g.unit0 = unit0; g.units = units;
+  const long rows = static_cast<long>(B) * GH * GW;
+  g.total_pb = static_cast<int>((rows + 63) / 64);
+  g.Cout = Cout; g.Ktot = KH * KW * C;
+  if (units < 1 || units > dk_conv_wgrad_tma_units(C) || unit0 + units > KH * KW * g.c_chunks) return -3;
+  const int unit_bytes = 64 * chan * 2;
+  const int stage_bytes = 16384 + units * unit_bytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return -4;
+  const int smem = stages * stage_bytes + 2048 + 4 * 4096 + 256 + 1024;
+  static int sm_count[64] = {};
+  static bool configured[2][64] = {};
+  int dev = 0;
+  DK_HOST_CHECK(cudaGetDevice(&dev));
+  if (sm_count[dev & 63] == 0) DK_HOST_CHECK(cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  const int which = chan == 64 ? 1 : 0;
+  if (!configured[which][dev & 63]) {
+    if (chan == 64)
+      DK_HOST_CHECK(cudaFuncSetAttribute(dk::conv_wgrad_tma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else
+      DK_HOST_CHECK(cudaFuncSetAttribute(dk::conv_wgrad_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[which][dev & 63] = true;
+  }
+  int grid = sm_count[dev & 63];
+  if (grid > g.total_pb) grid = g.total_pb;
+  const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(tmap_a);
+  const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(tmap_b);
+  const CUtensorMap& td = *reinterpret_cast<const CUtensorMap*>(tmap_d);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (chan == 64)
+    DK_HOST_CHECK(DK_LAUNCH(dk::conv_wgrad_tma_kernel<64>, grid, 192, smem, st, ta, tb, td, g, bias_grad, stages, stage_bytes));
+  else
+    DK_HOST_CHECK(DK_LAUNCH(dk::conv_wgrad_tma_kernel<32>, grid, 192, smem, st, ta, tb, td, g, bias_grad, stages, stage_bytes));
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// one-shot variant (tests): dW (zeroed by the caller) += wgrad, bias_grad (zeroed, may be NULL) += colsum(dZ)
+int dk_conv_wgrad_tma(const void* src, int B, int SH, int SW, int C, int GH, int GW, int KH, int KW, int stride, int pad,
+                      const void* dz, long lddz, float* dw, long lddw, int Cout, float* bias_grad, void* stream) {
+  alignas(64) CUtensorMap ta, tb, td;
+  int r = dk_conv_wgrad_tma_encode(&ta, &tb, &td, src, B, SH, SW, C, GH, GW, KH, KW, stride, pad, dz, lddz, dw, lddw, Cout);
+  if (r != 0) return r;
+  const int chan = C % 64 == 0 ? 64 : 32;
+  const int total_units = KH * KW * (C / chan), per = dk_conv_wgrad_tma_units(C);
+  for (int u0 = 0; u0 < total_units; u0 += per) {
+    const int n = total_units - u0 < per ? total_units - u0 : per;
+    r = dk_conv_wgrad_tma_launch(&ta, &tb, &td, B, C, GH, GW, KH, KW, stride, pad, Cout, u0, n, u0 == 0 ? bias_grad : nullptr, stream);
+    if (r != 0) return r;
+  }
+  return 0;
+}
+
+
 
 // one-shot variant (tests): encodes every tensor map first
 int dk_conv_tma(const void* src, int B, int SH, int SW, int C, int GH, int GW, int KH, int KW, int mul, int off,

@@ -120,6 +120,10 @@ int run_op(Engine* e, Op& op, void* main_stream) {
       // w, ldw, wd, ldwd, Cout, Cin, KH, KW
       return dk_conv_weight_flip(resolve(e, a[0]), (int)a[1], resolve(e, a[2]), (int)a[3], (int)a[4], (int)a[5], (int)a[6],
                                  (int)a[7], st);
+    case DK_OP_CONV_WGRAD_TMA:
+      // B, C, GH, GW, KH, KW, stride, pad, Cout, unit0, units, bias_grad (dZ / im2col / dW maps pre-encoded)
+      return dk_conv_wgrad_tma_launch(&op.ta, &op.tb, &op.td, (int)a[0], (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5],
+                                      (int)a[6], (int)a[7], (int)a[8], (int)a[9], (int)a[10], rp<float>(e, a[11]), st);
     case DK_OP_BWD_UPDATE: {
       for (int l = 0; l < DK_BWD_MAX_LAYERS; ++l)
         if (op.bwd_slot[l] >= 0) {
@@ -474,6 +478,36 @@ int dk_engine_add_conv_gemm(void* h, int list, const void* src, int SH, int SW, 
   op.i[8] = mul; op.i[9] = off; op.i[10] = div; op.i[11] = M; op.i[12] = N; op.i[13] = K; op.i[14] = bn;
   e->lists[list].push_back(op);
   return static_cast<int>(e->lists[list].size()) - 1;
+}
+
+int dk_engine_add_conv_wgrad_tma(void* h, int list, const void* src, int B, int SH, int SW, int C, int GH, int GW, int KH,
+                                 int KW, int stride, int pad, const void* dz, long lddz, float* dw, long lddw, int Cout,
+                                 float* bias_grad) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (list < 0 || list >= (int)e->lists.size()) return -1;
+  if (!dk_conv_wgrad_tma_supported(C, Cout, lddz, lddw)) return -2;
+  Op op;
+  memset(&op, 0, sizeof(op));
+  op.dyn_a_slot = -1;
+  op.kind = DK_OP_CONV_WGRAD_TMA;
+  op.stream_id = e->build_stream;
+  int r = dk_conv_wgrad_tma_encode(&op.ta, &op.tb, &op.td, src, B, SH, SW, C, GH, GW, KH, KW, stride, pad, dz, lddz, dw, lddw, Cout);
+  if (r != 0) return r;
+  const int chan = C % 64 == 0 ? 64 : 32;
+  const int total = KH * KW * (C / chan), per = dk_conv_wgrad_tma_units(C);
+  // balanced blocks of units (e.g. 9 taps of 64 channels -> 5 + 4 rather than 7 + 2)
+  const int launches = (total + per - 1) / per;
+  const int each = (total + launches - 1) / launches;
+  int last = -1;
+  for (int u0 = 0; u0 < total; u0 += each) {
+    const int n = total - u0 < each ? total - u0 : each;
+    op.i[0] = B; op.i[1] = C; op.i[2] = GH; op.i[3] = GW; op.i[4] = KH; op.i[5] = KW; op.i[6] = stride; op.i[7] = pad;
+    op.i[8] = Cout; op.i[9] = u0; op.i[10] = n;
+    op.i[11] = u0 == 0 ? (int64_t)(uintptr_t)bias_grad : 0;
+    e->lists[list].push_back(op);
+    last = static_cast<int>(e->lists[list].size()) - 1;
+  }
+  return last;
 }
 
 int dk_engine_add_conv_wgrad(void* h, int list, const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW,

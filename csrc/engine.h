@@ -52,7 +52,8 @@ enum {
   DK_OP_CONV_GEMM = 38,
   DK_OP_WFLIP = 39,
   DK_OP_CONV_WGRAD = 40,  // experimental
-  DK_OP_BWD_UPDATE = 41   // fused wgrad + bias-grad + optimizer (+ PS exchange) of every dense layer
+  DK_OP_BWD_UPDATE = 41,  // fused wgrad + bias-grad + optimizer (+ PS exchange) of every dense layer
+  DK_OP_CONV_WGRAD_TMA = 42  // convolution weight (+ bias) gradient, im2col operand produced by TMA
 };
 
 #ifdef __cplusplus
@@ -85,6 +86,11 @@ int dk_engine_add_conv_gemm(void* h, int list, const void* src, int SH, int SW, 
 // EXPERIMENTAL implicit wgrad (conv_wgrad_kernel): dW [Cout, KH KW C] fp32 (zeroed) += dZ^T [rows, Cout] * gather(src)
 int dk_engine_add_conv_wgrad(void* h, int list, const void* src, int SH, int SW, int C, int GH, int GW, int KH, int KW,
                              int stride, int pad, const void* dz, long lddz, float* dw, long lddw, int Cout, int rows);
+// TMA-im2col weight gradient: dW [Cout, KH KW C] fp32 (zeroed) += dZ^T im2col(src); bias_grad (zeroed, may be NULL) += colsum(dZ).
+// Adds one op per block of (tap, channel-chunk) units that fits TMEM / shared memory.
+int dk_engine_add_conv_wgrad_tma(void* h, int list, const void* src, int B, int SH, int SW, int C, int GH, int GW, int KH,
+                                 int KW, int stride, int pad, const void* dz, long lddz, float* dw, long lddw, int Cout,
+                                 float* bias_grad);
 int dk_engine_run(void* h, int list, void* stream);
 int dk_engine_list_size(void* h, int list);
 int dk_engine_list_kernels(void* h, int list);

@@ -71,6 +71,16 @@ int dk_conv_tma_bn(int N);
 int dk_conv_tma_launch(const void* tmap_a, const void* tmap_b, const void* tmap_d, const void* tmap_m,
                        const DkGemmEpilogue* ep, int C, int GH, int GW, int KH, int KW, int mul, int off, int M, int N,
                        void* stream);
+// TMA-im2col weight gradient (+ bias gradient), see conv_wgrad_tma_kernel
+int dk_conv_wgrad_tma_units(int C);
+int dk_conv_wgrad_tma_supported(int C, int Cout, long lddz, long lddw);
+int dk_conv_wgrad_tma_encode(void* tmap_a, void* tmap_b, void* tmap_d, const void* src, int B, int SH, int SW, int C, int GH,
+                             int GW, int KH, int KW, int stride, int pad, const void* dz, long lddz, float* dw, long lddw,
+                             int Cout);
+int dk_conv_wgrad_tma_launch(const void* tmap_a, const void* tmap_b, const void* tmap_d, int B, int C, int GH, int GW, int KH,
+                             int KW, int stride, int pad, int Cout, int unit0, int units, float* bias_grad, void* stream);
+int dk_conv_wgrad_tma(const void* src, int B, int SH, int SW, int C, int GH, int GW, int KH, int KW, int stride, int pad,
+                      const void* dz, long lddz, float* dw, long lddw, int Cout, float* bias_grad, void* stream);
 int dk_conv_tma(const void* src, int B, int SH, int SW, int C, int GH, int GW, int KH, int KW, int mul, int off,
                 const void* Wmat, long ldw, const DkGemmEpilogue* ep, int M, int N, void* stream);
 int dk_conv_gather_mode(int mode);

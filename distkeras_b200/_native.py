@@ -62,7 +62,7 @@ OP_PS_COMMIT, OP_PS_PULL, OP_PS_EXCHANGE, OP_PS_ELASTIC, OP_PS_DAMPED, OP_PS_TIC
 OP_LOCK_ACQUIRE, OP_LOCK_RELEASE, OP_EAMSGD_PRE, OP_EAMSGD_POST, OP_CAST, OP_ELOSS = 19, 20, 21, 22, 23, 24
 OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D, OP_FORK, OP_JOIN, OP_GEMM_PULL = 25, 26, 27, 28, 29, 30, 31
 OP_BN_FWD, OP_BN_INF, OP_BN_BWD, OP_GAP_FWD, OP_GAP_BWD, OP_HEAD = 32, 33, 34, 35, 36, 37
-OP_CONV_GEMM, OP_WFLIP, OP_CONV_WGRAD, OP_BWD_UPDATE = 38, 39, 40, 41
+OP_CONV_GEMM, OP_WFLIP, OP_CONV_WGRAD, OP_BWD_UPDATE, OP_CONV_WGRAD_TMA = 38, 39, 40, 41, 42
 GEMM_TF32, GEMM_A_MN, GEMM_B_MN, GEMM_PERSISTENT, GEMM_PAIR, GEMM_SHORT_A = 1, 2, 4, 8, 16, 32
 
 OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6}
@@ -89,6 +89,8 @@ _SIGNATURES = {
     "dk_conv_weight_flip": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "dk_conv_tma": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, C.POINTER(GemmEpilogue), i32, i32, vp]),
     "dk_conv_tma_supported": (i32, [i32, i32, i32, i32, i32]),
+    "dk_conv_wgrad_tma": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, i64, i32, vp, vp]),
+    "dk_conv_wgrad_tma_supported": (i32, [i32, i32, i64, i64]),
     "dk_conv_pick_bn": (i32, [i32]),
     "dk_conv_gather_mode": (i32, [i32]),
     "dk_conv_wgrad": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, i64, i32, i32, i32, vp]),
@@ -164,6 +166,7 @@ _SIGNATURES = {
                                       C.POINTER(GemmEpilogue)]),
     "dk_engine_add_gemm": (i32, [vp, i32, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, C.POINTER(GemmEpilogue)]),
     "dk_engine_add_gemm_pull": (i32, [vp, i32, vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, C.POINTER(GemmEpilogue)]),
+    "dk_engine_add_conv_wgrad_tma": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, i64, i32, vp]),
     "dk_engine_add_gemm_slot": (i32, [vp, i32, i32, i64, vp, i64, i32, i32, i32, i32, i32, i32, C.POINTER(GemmEpilogue)]),
     "dk_engine_add_bwd_update": (i32, [vp, i32, C.POINTER(BwdUpdateDesc)]),
     "dk_bwd_update": (i32, [C.POINTER(BwdUpdateDesc), vp]),

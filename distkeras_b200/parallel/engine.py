@@ -511,8 +511,6 @@ class NativeReplica(Replica):
             H, Wd, Cin = b.in_shape
             OH, OW, _ = b.out_shape
             rows = B * OH * OW
-            col = self._buf(rows, _r8(K))
-            a_in = dict(t=col, rows=rows, cols=K, ld=_r8(K), nhwc=None)
             # implicit GEMM (DK_IMPLICIT_CONV=1): the forward and dgrad GEMMs gather their A operand from
             # the NHWC activation inside the kernel; the column matrix is then only needed by the wgrad
             # GEMM, so im2col moves off the critical path onto the wgrad branch of the backward list
@@ -521,10 +519,21 @@ class NativeReplica(Replica):
             mode = os.environ.get("DK_IMPLICIT_CONV", "auto")
             implicit = (mode != "0" and (mode == "1" or Cin % 64 == 0 or Cin == 32) and Cin % 8 == 0 and Nout % 8 == 0
                         and cur["ld"] == Cin and wbld == K and b.kh == b.kw and not is_last)
-            im2col_args = [cur["t"].data_ptr(), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad, OH, OW, col.data_ptr(), _r8(K)]
-            # EXPERIMENTAL (DK_IMPLICIT_WGRAD=1, needs DK_IMPLICIT_CONV=1): the wgrad gathers too, so no column
-            # matrix is built at all for this layer
-            implicit_wgrad = implicit and os.environ.get("DK_IMPLICIT_WGRAD", "0") == "1" and Nout <= 128
+            # weight gradient of an implicit layer: "tma" (default when the geometry allows: im2col operand produced
+            # by TMA, no column matrix, bias gradient from the ones-tile MMA), "gather" (DK_IMPLICIT_WGRAD=1: the
+            # cp.async gather kernel) or "explicit" (column matrix built on a side branch for a plain GEMM)
+            wgrad_mode = "explicit"
+            if implicit and os.environ.get("DK_IMPLICIT_WGRAD", "auto") == "1" and Nout <= 128:
+                wgrad_mode = "gather"
+            elif (implicit and os.environ.get("DK_IMPLICIT_WGRAD", "auto") != "0" and _r8(Nout) == Nout
+                  and self.lib.dk_conv_wgrad_tma_supported(Cin, Nout, Nout, K)):
+                wgrad_mode = "tma"
+            implicit_wgrad = wgrad_mode != "explicit"
+            need_col = (not implicit) or (self.training and not implicit_wgrad)
+            col = self._buf(rows, _r8(K)) if need_col else None
+            a_in = dict(t=col, rows=rows, cols=K, ld=_r8(K), nhwc=None)
+            im2col_args = [cur["t"].data_ptr(), B, H, Wd, Cin, b.kh, b.kw, b.stride, b.pad, OH, OW,
+                           col.data_ptr() if need_col else 0, _r8(K)]
             for lst in lists:
                 if not implicit:
                     self._add(lst, N.OP_IM2COL, im2col_args)
@@ -654,12 +663,23 @@ class NativeReplica(Replica):
                 self._add(lst, N.OP_FORK, [sid])
                 self._forked.add(sid)
             self.lib.dk_engine_set_build_stream(self.engine, s_bias)
-            if bseg is not None:
+            if bseg is not None and not (implicit and wgrad_mode == "tma"):   # the TMA wgrad kernel also sums dZ
                 self._add(lst, N.OP_COLSUM, [grad["t"].data_ptr(), rows, Nout, grad["ld"], g_ptr + 4 * bseg.offset],
                           [1.0])
             self.lib.dk_engine_set_build_stream(self.engine, s_wgrad)
             # wgrad: dW[Nout, K] = dZ^T[Nout, rows] * In[rows, K]  (both operands MN-major views)
-            if implicit and implicit_wgrad:
+            if implicit and wgrad_mode == "tma":
+                if grad["ld"] != Nout:
+                    raise UnsupportedByNativeEngine("implicit wgrad needs an unpadded output gradient")
+                Hh, Ww, Ci = b.in_shape
+                Oh, Ow, _ = b.out_shape
+                r = self.lib.dk_engine_add_conv_wgrad_tma(
+                    self.engine, lst, C.c_void_p(inp["t"].data_ptr()), B, Hh, Ww, Ci, Oh, Ow, b.kh, b.kw, b.stride, b.pad,
+                    C.c_void_p(grad["t"].data_ptr()), grad["ld"], C.c_void_p(g_ptr + 4 * kseg.offset), K, Nout,
+                    C.c_void_p(g_ptr + 4 * bseg.offset) if bseg is not None else None)
+                if r < 0:
+                    raise RuntimeError(f"dk_engine_add_conv_wgrad_tma failed: {r}")
+            elif implicit and implicit_wgrad:
                 if grad["ld"] != Nout:
                     raise UnsupportedByNativeEngine("implicit wgrad needs an unpadded output gradient")
                 Hh, Ww, Ci = b.in_shape

@@ -24,6 +24,15 @@ def _cnn(seed=0):
                        Dense(32, activation="relu"), Dense(10, activation="softmax")], seed=seed)
 
 
+def _cnn_tma(seed=0):
+    """32 / 64-channel 3x3 convolutions: every conv runs on the TMA-im2col kernels (forward, dgrad, wgrad)."""
+    from distkeras_b200.models import Conv2D, Dense, Flatten, MaxPooling2D, Sequential
+
+    return Sequential([Conv2D(32, 3, padding="same", activation="relu", input_shape=(10, 10, 32)),
+                       Conv2D(64, 3, padding="valid", activation="relu"), Conv2D(64, 3, padding="same", activation="relu"),
+                       MaxPooling2D(2), Flatten(), Dense(10, activation="softmax")], seed=seed)
+
+
 def _resnet(seed=0):
     from distkeras_b200.models import (Activation, BatchNormalization, Conv2D, Dense, GlobalAveragePooling2D,
                                        MaxPooling2D, ResidualBlock, Sequential)
@@ -33,14 +42,17 @@ def _resnet(seed=0):
                        GlobalAveragePooling2D(), Dense(10, activation="softmax")], seed=seed)
 
 
-@pytest.mark.parametrize("maker,in_shape,implicit", [(_mlp, (64,), False), (_cnn, (12, 12, 1), False),
+@pytest.mark.parametrize("maker,in_shape,implicit", [(_mlp, (64,), False), (_cnn, (12, 12, 1), False), (_cnn_tma, (10, 10, 32), None),
                                                      (_resnet, (16, 16, 3), False), (_cnn, (12, 12, 1), True),
                                                      (_resnet, (16, 16, 3), True)])
 def test_native_gradients_match_autograd(maker, in_shape, implicit, monkeypatch):
     """``implicit``: forward / dgrad convolutions on the implicit-GEMM kernel (DK_IMPLICIT_CONV=1)."""
     from distkeras_b200.parallel.engine import NativeReplica
 
-    monkeypatch.setenv("DK_IMPLICIT_CONV", "1" if implicit else "0")
+    if implicit is None:
+        monkeypatch.delenv("DK_IMPLICIT_CONV", raising=False)   # default: TMA-im2col kernels where the geometry allows
+    else:
+        monkeypatch.setenv("DK_IMPLICIT_CONV", "1" if implicit else "0")
     from distkeras_b200.parallel.replica import TorchReplica
 
     B = 128

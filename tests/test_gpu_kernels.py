@@ -553,3 +553,26 @@ def test_tma_im2col_conv_forward_and_dgrad(N, B, H, Cin, Cout, k, stride, pad):
     gref = xr.grad.permute(0, 2, 3, 1).reshape(B * H * H, Cin)
     gref = torch.where(mask.float() > 0, gref, torch.zeros_like(gref))
     assert torch.allclose(dx.float(), gref, atol=0.03 * float(gref.abs().max()) + 1e-3, rtol=3e-2)
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,k,stride,pad", [(4, 16, 32, 32, 3, 1, 1), (3, 14, 32, 64, 3, 1, 0), (2, 12, 64, 64, 3, 2, 1),
+                                                       (6, 9, 64, 24, 1, 1, 0), (3, 10, 128, 128, 3, 1, 1)])
+def test_tma_im2col_conv_wgrad(N, B, H, Cin, Cout, k, stride, pad):
+    """Weight gradient with the im2col operand produced by TMA (split-K over a persistent grid, the gradient block
+    resident in TMEM, TMA reduce-add) + bias gradient from the ones-tile MMA, against autograd."""
+    torch.manual_seed(29)
+    OH = (H + 2 * pad - k) // stride + 1
+    x = bf(torch.randn(B, H, H, Cin, device="cuda"))
+    dz = bf(torch.randn(B, OH, OH, Cout, device="cuda"))
+    K = k * k * Cin
+    dw = torch.zeros(Cout, K, dtype=torch.float32, device="cuda")
+    db = torch.zeros(Cout, dtype=torch.float32, device="cuda")
+    assert N.lib().dk_conv_wgrad_tma_supported(Cin, Cout, Cout, K)
+    N.check(N.lib().dk_conv_wgrad_tma(x.data_ptr(), B, H, H, Cin, OH, OH, k, k, stride, pad, dz.data_ptr(), Cout, dw.data_ptr(),
+                                      K, Cout, db.data_ptr(), st()), "conv wgrad tma")
+    w = torch.zeros(Cout, Cin, k, k, device="cuda", requires_grad=True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), w, None, stride=stride, padding=pad).backward(dz.float().permute(0, 3, 1, 2))
+    ref = w.grad.permute(0, 2, 3, 1).reshape(Cout, K)  # [Cout, (kh, kw, c)]
+    rows = B * OH * OH
+    assert torch.allclose(dw, ref, atol=2e-3 * rows ** 0.5, rtol=1e-3), float((dw - ref).abs().max())
+    assert torch.allclose(db, dz.float().sum(dim=(0, 1, 2)), atol=2e-3 * rows ** 0.5, rtol=1e-3)

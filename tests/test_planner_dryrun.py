@@ -13,7 +13,7 @@ from distkeras_b200.models import ZOO
 from distkeras_b200.parallel import engine as eng
 
 GPU_ONLY = ("dk_engine_add_gemm", "dk_engine_add_gemm_pull", "dk_engine_add_conv_gemm", "dk_engine_add_conv_wgrad",
-            "dk_engine_add_gemm_slot", "dk_engine_add_bwd_update")
+            "dk_engine_add_gemm_slot", "dk_engine_add_bwd_update", "dk_engine_add_conv_wgrad_tma")
 OP_NAMES = {v: k for k, v in vars(N).items() if k.startswith("OP_") and isinstance(v, int)}
 
 
@@ -100,7 +100,7 @@ def test_lowering_under_every_switch(model_name, batch, env, monkeypatch, native
         assert lib.calls["dk_engine_add_conv_gemm"] > 0 and lib.ops["OP_WFLIP"] > 0
         if env.get("DK_IMPLICIT_WGRAD") == "1":
             assert lib.calls["dk_engine_add_conv_wgrad"] > 0
-        else:
-            assert lib.calls["dk_engine_add_conv_wgrad"] == 0 and lib.ops["OP_IM2COL"] > 0
+        else:  # default: the TMA-im2col weight gradient wherever the geometry allows it
+            assert lib.calls["dk_engine_add_conv_wgrad"] == 0 and lib.calls["dk_engine_add_conv_wgrad_tma"] > 0
     if env.get("DK_SIDE_STREAMS") == "1" and not conv_model:  # conv models also join the im2col branch per layer
         assert lib.ops["OP_JOIN"] == 1
