@@ -334,6 +334,17 @@ class NativeReplica(Replica):
         cur = dict(t=x0, rows=B, cols=F, ld=_r8(F), nhwc=in_shape if len(in_shape) == 3 else None,
                    slot=SLOT_XB if self.compact else None)
         first = self.blocks[0]
+        # First convolution with 1 / 3 input channels (MNIST, CIFAR): the input stage writes the image with its
+        # channels zero-padded to 32, so this layer too runs on the TMA-im2col kernels (forward + weight gradient)
+        # and no column matrix exists anywhere in the network.
+        self._cpad = 0
+        if (first.kind == "conv" and os.environ.get("DK_IMPLICIT_CONV", "auto") != "0" and first.in_shape[-1] < 32
+                and first.kh == first.kw and first.n_out % 8 == 0 and first.n_out <= 128 and len(self.blocks) > 1
+                and os.environ.get("DK_PAD_INPUT_CHANNELS", "1") != "0"):
+            H0, W0, C0 = first.in_shape
+            self._cpad = 32
+            x0 = self._buf(B * H0 * W0, 32)
+            cur = dict(t=x0, rows=B * H0 * W0, cols=32, ld=32, nhwc=(H0, W0, 32), slot=None, cpad=32)
         x0f = None
         if self.pull_center_ptr and first.kind == "dense" and first.k_in % 8 == 0 and F % 8 == 0:
             self.L_step_pull = self.lib.dk_engine_new_list(self.engine)
@@ -349,6 +360,12 @@ class NativeReplica(Replica):
         for lst in ([] if self.compact else self._lists):
             if nbn:
                 self._add(lst, N.OP_MEMSET, [self._bn_scratch.data_ptr(), 0, nbn * 4])
+            if self._cpad:   # rows = pixels, 3 (or 1) valid channels of 32
+                H0, W0, C0 = first.in_shape
+                self._add(lst, N.OP_INPUT,
+                          [-(SLOT_X + 1), self.in_dtype, B * H0 * W0, C0, x0.data_ptr(), 32, 0, 0,
+                           self.step_counter.data_ptr() if lst in self._train_lists else 0, 0, C0], [self.scale, self.shift])
+                continue
             self._add(lst, N.OP_INPUT,
                       [-(SLOT_X + 1), self.in_dtype, B, F, x0.data_ptr(), cur["ld"], 0, 0,
                        self.step_counter.data_ptr() if lst in self._train_lists else 0,
@@ -499,7 +516,15 @@ class NativeReplica(Replica):
         kseg = self._seg(b.layer_index, b.seg_prefix + "kernel")
         bseg = self._seg(b.layer_index, b.seg_prefix + "bias") if b.use_bias else None
         K, Nout = b.k_in, b.n_out
-        if K % 8 == 0:  # bf16 weight shadow [Nout, K] with a TMA-legal leading dimension
+        cpad = cur.get("cpad", 0) if b.kind == "conv" else 0     # channels physically stored per input pixel
+        if cpad:
+            # weights [Nout, kh, kw, Cin] scattered into a zero-padded [Nout, kh, kw, cpad] shadow before every step
+            taps, c_real = b.kh * b.kw, b.in_shape[-1]
+            K = taps * cpad
+            wpad = self._buf(Nout, K)
+            wbp, wbld = wpad.data_ptr(), K
+            self._pad_refresh.append((wpad.data_ptr(), cpad * 2, wb_ptr + 2 * kseg.offset, c_real * 2, c_real * 2, Nout * taps))
+        elif K % 8 == 0:  # bf16 weight shadow [Nout, K] with a TMA-legal leading dimension
             wbp, wbld = wb_ptr + 2 * kseg.offset, K
         else:
             pad = self._buf(Nout, _r8(K))
@@ -509,6 +534,9 @@ class NativeReplica(Replica):
         implicit = False
         if b.kind == "conv":
             H, Wd, Cin = b.in_shape
+            c_real = Cin
+            if cpad:
+                Cin = cpad
             OH, OW, _ = b.out_shape
             rows = B * OH * OW
             # implicit GEMM (DK_IMPLICIT_CONV=1): the forward and dgrad GEMMs gather their A operand from
@@ -671,14 +699,23 @@ class NativeReplica(Replica):
             if implicit and wgrad_mode == "tma":
                 if grad["ld"] != Nout:
                     raise UnsupportedByNativeEngine("implicit wgrad needs an unpadded output gradient")
-                Hh, Ww, Ci = b.in_shape
+                Hh, Ww, _ = b.in_shape
+                Ci = Cin
                 Oh, Ow, _ = b.out_shape
+                dw_ptr = g_ptr + 4 * kseg.offset
+                if cpad:   # gradient w.r.t. the channel-padded weights: scratch block, real channels copied out below
+                    dwpad = self._buf(Nout, K, dtype=torch.float32)
+                    dw_ptr = dwpad.data_ptr()
+                    self._add(lst, N.OP_MEMSET, [dw_ptr, 0, Nout * K * 4])
                 r = self.lib.dk_engine_add_conv_wgrad_tma(
                     self.engine, lst, C.c_void_p(inp["t"].data_ptr()), B, Hh, Ww, Ci, Oh, Ow, b.kh, b.kw, b.stride, b.pad,
-                    C.c_void_p(grad["t"].data_ptr()), grad["ld"], C.c_void_p(g_ptr + 4 * kseg.offset), K, Nout,
+                    C.c_void_p(grad["t"].data_ptr()), grad["ld"], C.c_void_p(dw_ptr), K, Nout,
                     C.c_void_p(g_ptr + 4 * bseg.offset) if bseg is not None else None)
                 if r < 0:
                     raise RuntimeError(f"dk_engine_add_conv_wgrad_tma failed: {r}")
+                if cpad:
+                    self._add(lst, N.OP_MEMCPY2D, [g_ptr + 4 * kseg.offset, c_real * 4, dw_ptr, cpad * 4, c_real * 4,
+                                                   Nout * b.kh * b.kw])
             elif implicit and implicit_wgrad:
                 if grad["ld"] != Nout:
                     raise UnsupportedByNativeEngine("implicit wgrad needs an unpadded output gradient")

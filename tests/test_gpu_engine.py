@@ -79,8 +79,10 @@ def test_native_gradients_match_autograd(maker, in_shape, implicit, monkeypatch)
     # bf16 activations / gradients: errors grow towards the input through the BatchNorm stack; the
     # ResNet bounds are the level torch.autocast(bf16)+cuDNN shows on the same net (profiles/bf16_grad_error.txt)
     worst, median = max(errs), sorted(errs)[len(errs) // 2]
-    assert worst[0] < (0.35 if maker is _resnet else 0.05), sorted(errs, reverse=True)[:6]
-    assert median[0] < (0.15 if maker is _resnet else 0.05), sorted(errs, reverse=True)[:6]
+    # (_cnn_tma: three 288 .. 576-term bf16 convolutions deep, every dZ rounded to bf16 on the way down)
+    lim = {_resnet: (0.35, 0.15), _cnn_tma: (0.12, 0.08)}.get(maker, (0.05, 0.05))
+    assert worst[0] < lim[0], sorted(errs, reverse=True)[:6]
+    assert median[0] < lim[1], sorted(errs, reverse=True)[:6]
     probs = nat.predict(x).cpu()
     want = torch.softmax(model.forward(x, logits=True), 1)
     assert torch.allclose(probs, want, atol=0.03)
