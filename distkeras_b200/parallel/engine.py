@@ -532,11 +532,13 @@ class NativeReplica(Replica):
             self._pad_refresh.append((pad.data_ptr(), _r8(K) * 2, wb_ptr + 2 * kseg.offset, K * 2, K * 2, Nout))
         inp = cur
         implicit = False
+        cin_eff = c_real = 0
         if b.kind == "conv":
             H, Wd, Cin = b.in_shape
             c_real = Cin
             if cpad:
                 Cin = cpad
+            cin_eff = Cin
             OH, OW, _ = b.out_shape
             rows = B * OH * OW
             # implicit GEMM (DK_IMPLICIT_CONV=1): the forward and dgrad GEMMs gather their A operand from
@@ -700,7 +702,7 @@ class NativeReplica(Replica):
                 if grad["ld"] != Nout:
                     raise UnsupportedByNativeEngine("implicit wgrad needs an unpadded output gradient")
                 Hh, Ww, _ = b.in_shape
-                Ci = Cin
+                Ci = cin_eff
                 Oh, Ow, _ = b.out_shape
                 dw_ptr = g_ptr + 4 * kseg.offset
                 if cpad:   # gradient w.r.t. the channel-padded weights: scratch block, real channels copied out below
