@@ -340,7 +340,9 @@ class NativeReplica(Replica):
         self._cpad = 0
         if (first.kind == "conv" and os.environ.get("DK_IMPLICIT_CONV", "auto") != "0" and first.in_shape[-1] < 32
                 and first.kh == first.kw and first.n_out % 8 == 0 and first.n_out <= 128 and len(self.blocks) > 1
-                and os.environ.get("DK_PAD_INPUT_CHANNELS", "1") != "0"):
+                and (os.environ.get("DK_PAD_INPUT_CHANNELS", "auto") == "1"      # "1": always; "auto": not for 1-channel
+                     or (os.environ.get("DK_PAD_INPUT_CHANNELS", "auto") == "auto"   # images (32x the bytes: the explicit
+                         and first.in_shape[-1] >= 3))):                              # K = 9 path measured faster there)
             H0, W0, C0 = first.in_shape
             self._cpad = 32
             x0 = self._buf(B * H0 * W0, 32)
