@@ -137,7 +137,7 @@ __device__ __forceinline__ float ld_sys_f(const float* addr) {
 
 // one parameter: optimizer rule (+ bf16 shadow when no exchange follows)
 template <int KIND>
-__device__ __forceinline__ void update_scalar(const BwdUpdateDev& p, long idx, float g, float lr, float corr,
+__device__ __forceinline__ void update_scalar(const BwdUpdateDev& p, long idx, float g, float lr, const OptimCorr& corr,
                                               bool write_shadow) {
   float w = p.w[idx];
   float s0 = p.s0 != nullptr ? p.s0[idx] : 0.f;
@@ -191,10 +191,10 @@ template <int KIND>
 __device__ __forceinline__ void bwd_epilogue(const BwdUpdateDev& p, const BwdLayerDev& ly, const int m0, const int n0,
                                              const int quarter, const int half, const int lane, const uint32_t tmem_base,
                                              const uint32_t gslot, const uint32_t tiles, const uint32_t wb_tile,
-                                             uint64_t* state_bar, const bool has_bias, const float lr, const float corr,
+                                             uint64_t* state_bar, const bool has_bias, const float lr, const OptimCorr& corr,
                                              const float cs, float bw, float bs0, float bs1) {
   constexpr bool kS0 = KIND != DK_OPT_SGD;
-  constexpr bool kS1 = KIND == DK_OPT_ADAM || KIND == DK_OPT_ADADELTA || KIND == DK_OPT_ADAMAX;
+  constexpr bool kS1 = KIND == DK_OPT_ADAM || KIND == DK_OPT_ADADELTA || KIND == DK_OPT_ADAMAX || KIND == DK_OPT_NADAM;
   const bool comm = p.comm_mode != DK_COMM_NONE;
   const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
   const int nbase = n0 + half * 32;                  // first column of this warp's slice
@@ -396,7 +396,7 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
   const int num_kb = (p.batch + 63) / 64;
   const int kind = p.opt.kind;
   const bool use_s0 = kind != DK_OPT_SGD;
-  const bool use_s1 = kind == DK_OPT_ADAM || kind == DK_OPT_ADADELTA || kind == DK_OPT_ADAMAX;
+  const bool use_s1 = kind == DK_OPT_ADAM || kind == DK_OPT_ADADELTA || kind == DK_OPT_ADAMAX || kind == DK_OPT_NADAM;
   const bool use_w1 = p.comm_mode == DK_COMM_EXCHANGE;
 
   if (warp == 0 && lane == 0) {
@@ -498,11 +498,9 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
     // everything that only depends on the previous step is fetched while the operands / state tiles are in
     // flight: step number -> learning rate and bias correction, DynSGD scale, this lane's bias parameter
     const int t = max(*p.step, 1);
-    float lr = p.opt.lr, corr = 1.f;
-    if (p.opt.decay > 0.f) lr = __fdividef(lr, 1.f + p.opt.decay * static_cast<float>(t - 1));
-    if (kind == DK_OPT_ADAM)
-      corr = __fdividef(sqrtf(1.f - __powf(p.opt.p1, static_cast<float>(t))), 1.f - __powf(p.opt.p0, static_cast<float>(t)));
-    if (kind == DK_OPT_ADAMAX) corr = __fdividef(1.f, 1.f - __powf(p.opt.p0, static_cast<float>(t)));
+    float lr;
+    OptimCorr corr;
+    optim_prelude(p.opt, t, lr, corr);
     const float cs = p.comm_mode != DK_COMM_NONE
                          ? (p.scale_dev != nullptr ? p.comm_scale * __ldg(p.scale_dev) : p.comm_scale) : 0.f;
     float bw = 0.f, bs0 = 0.f, bs1 = 0.f;
@@ -522,6 +520,7 @@ dense_bwd_update_kernel(const __grid_constant__ BwdUpdateDev p) {
       case DK_OPT_RMSPROP: bwd_epilogue<DK_OPT_RMSPROP>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
       case DK_OPT_ADAM: bwd_epilogue<DK_OPT_ADAM>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
       case DK_OPT_ADADELTA: bwd_epilogue<DK_OPT_ADADELTA>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
+      case DK_OPT_NADAM: bwd_epilogue<DK_OPT_NADAM>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
       default: bwd_epilogue<DK_OPT_ADAMAX>(p, ly, m0, n0, quarter, half, lane, tmem_base, gslot, tl, wbt, state_bar, has_bias, lr, corr, cs, bw, bs0, bs1); break;
     }
     tcgen05_fence_before();

@@ -9,7 +9,8 @@ enum {
   DK_OPT_RMSPROP = 3,
   DK_OPT_ADAM = 4,
   DK_OPT_ADADELTA = 5,
-  DK_OPT_ADAMAX = 6
+  DK_OPT_ADAMAX = 6,
+  DK_OPT_NADAM = 7   // Adam with Nesterov momentum (Dozat 2016), constant beta_1 (no momentum-decay schedule)
 };
 
 enum { DK_IN_U8 = 0, DK_IN_F32 = 1, DK_IN_BF16 = 2 };

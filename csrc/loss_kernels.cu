@@ -660,7 +660,8 @@ elementwise_loss_kernel(int kind, const float* __restrict__ out, const float* __
 }
 
 // LabelIndexTransformer rule (distkeras/transformers.py:321-332) + AccuracyEvaluator count
-// (evaluators.py:42-48): first index whose activation >= threshold, else arg-max; counts matches.
+// (evaluators.py:42-48): first index whose activation >= threshold, else the arg-max over the positive
+// entries, else default_index; counts matches.
 __global__ void __launch_bounds__(256)
 label_index_kernel(const float* __restrict__ probs, int B, int C, float threshold, int default_index,
                    int* __restrict__ out_index, const int* __restrict__ labels, int* correct_count) {
@@ -669,7 +670,7 @@ label_index_kernel(const float* __restrict__ probs, int B, int C, float threshol
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < B; r += gridDim.x * blockDim.x) {
     const float* p = probs + static_cast<size_t>(r) * C;
     int idx = -1;
-    float best = -INFINITY;
+    float best = 0.f;  // the reference's running maximum starts at 0: no positive entry -> default_index
     int arg = default_index;
     for (int c = 0; c < C; ++c) {
       const float v = p[c];

@@ -20,6 +20,13 @@ struct OptimArgs {
   float grad_scale;
 };
 
+// step-dependent scalars of the bias-corrected rules (computed once per thread from the step number t)
+struct OptimCorr {
+  float c0;  // Adam: sqrt(1 - b2^t) / (1 - b1^t); Adamax: 1 / (1 - b1^t); Nadam: 1 / (1 - b2^t)
+  float c1;  // Nadam: b1 / (1 - b1^(t+1))
+  float c2;  // Nadam: (1 - b1) / (1 - b1^t)
+};
+
 // MUFU.SQRT (1 ulp-ish): the IEEE-rounded sqrtf costs ~10 instructions and a slow-path branch per element
 __device__ __forceinline__ float fast_sqrt(float x) {
   float y;
@@ -29,7 +36,8 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 
 template <int KIND>
 __device__ __forceinline__ void optim_update(float& w, float g, float& s0, float& s1, float lr,
-                                             const OptimArgs& a, float corr) {
+                                             const OptimArgs& a, const OptimCorr& k) {
+  const float corr = k.c0;
   if constexpr (KIND == DK_OPT_SGD) {
     w -= lr * g;
   } else if constexpr (KIND == DK_OPT_MOMENTUM) {
@@ -55,31 +63,27 @@ __device__ __forceinline__ void optim_update(float& w, float g, float& s0, float
     s0 = a.p0 * s0 + (1.f - a.p0) * g;
     s1 = fmaxf(a.p1 * s1, fabsf(g));
     w -= lr * corr * __fdividef(s0, s1 + a.eps);
+  } else if constexpr (KIND == DK_OPT_NADAM) {
+    s0 = a.p0 * s0 + (1.f - a.p0) * g;
+    s1 = a.p1 * s1 + (1.f - a.p1) * g * g;
+    const float mhat = k.c1 * s0 + k.c2 * g;
+    w -= lr * __fdividef(mhat, fast_sqrt(s1 * k.c0) + a.eps);
   }
 }
 
 
-// learning rate after decay and the bias-correction factor of step t (>= 1)
-__device__ __forceinline__ void optim_prelude(const OptimArgs& a, int t, float& lr, float& corr) {
+// learning rate after decay and the bias-correction scalars of step t (>= 1)
+__device__ __forceinline__ void optim_prelude(const OptimArgs& a, int t, float& lr, OptimCorr& k) {
   lr = a.lr;
-  if (a.decay > 0.f) lr = lr / (1.f + a.decay * static_cast<float>(t - 1));
-  corr = 1.f;
-  if (a.kind == DK_OPT_ADAM)
-    corr = sqrtf(1.f - powf(a.p1, static_cast<float>(t))) / (1.f - powf(a.p0, static_cast<float>(t)));
-  if (a.kind == DK_OPT_ADAMAX) corr = 1.f / (1.f - powf(a.p0, static_cast<float>(t)));
-}
-
-// run-time dispatch (warp-uniform branch) for kernels that are not templated on the rule
-__device__ __forceinline__ void optim_update_rt(int kind, float& w, float g, float& s0, float& s1, float lr,
-                                                const OptimArgs& a, float corr) {
-  switch (kind) {
-    case DK_OPT_SGD: optim_update<DK_OPT_SGD>(w, g, s0, s1, lr, a, corr); break;
-    case DK_OPT_MOMENTUM: optim_update<DK_OPT_MOMENTUM>(w, g, s0, s1, lr, a, corr); break;
-    case DK_OPT_ADAGRAD: optim_update<DK_OPT_ADAGRAD>(w, g, s0, s1, lr, a, corr); break;
-    case DK_OPT_RMSPROP: optim_update<DK_OPT_RMSPROP>(w, g, s0, s1, lr, a, corr); break;
-    case DK_OPT_ADAM: optim_update<DK_OPT_ADAM>(w, g, s0, s1, lr, a, corr); break;
-    case DK_OPT_ADADELTA: optim_update<DK_OPT_ADADELTA>(w, g, s0, s1, lr, a, corr); break;
-    default: optim_update<DK_OPT_ADAMAX>(w, g, s0, s1, lr, a, corr); break;
+  if (a.decay > 0.f) lr = __fdividef(lr, 1.f + a.decay * static_cast<float>(t - 1));
+  k.c0 = 1.f; k.c1 = 0.f; k.c2 = 0.f;
+  const float tf = static_cast<float>(t);
+  if (a.kind == DK_OPT_ADAM) k.c0 = __fdividef(sqrtf(1.f - __powf(a.p1, tf)), 1.f - __powf(a.p0, tf));
+  if (a.kind == DK_OPT_ADAMAX) k.c0 = __fdividef(1.f, 1.f - __powf(a.p0, tf));
+  if (a.kind == DK_OPT_NADAM) {
+    k.c0 = __fdividef(1.f, 1.f - __powf(a.p1, tf));
+    k.c1 = __fdividef(a.p0, 1.f - __powf(a.p0, tf + 1.f));
+    k.c2 = __fdividef(1.f - a.p0, 1.f - __powf(a.p0, tf));
   }
 }
 

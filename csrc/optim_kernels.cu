@@ -15,14 +15,11 @@ template <int KIND>
 __global__ void __launch_bounds__(256) optim_kernel(const OptimArgs a) {
   DK_PDL_ENTER();
   constexpr bool kS0 = KIND != DK_OPT_SGD;
-  constexpr bool kS1 = KIND == DK_OPT_ADAM || KIND == DK_OPT_ADADELTA || KIND == DK_OPT_ADAMAX;
+  constexpr bool kS1 = KIND == DK_OPT_ADAM || KIND == DK_OPT_ADADELTA || KIND == DK_OPT_ADAMAX || KIND == DK_OPT_NADAM;
   const int t = a.step != nullptr ? max(*a.step, 1) : 1;
-  float lr = a.lr;
-  if (a.decay > 0.f) lr = lr / (1.f + a.decay * static_cast<float>(t - 1));
-  float corr = 1.f;
-  if constexpr (KIND == DK_OPT_ADAM)
-    corr = sqrtf(1.f - powf(a.p1, static_cast<float>(t))) / (1.f - powf(a.p0, static_cast<float>(t)));
-  if constexpr (KIND == DK_OPT_ADAMAX) corr = 1.f / (1.f - powf(a.p0, static_cast<float>(t)));
+  float lr;
+  OptimCorr corr;
+  optim_prelude(a, t, lr, corr);
 
   const long n4 = a.n >> 2;
   const long stride = static_cast<long>(gridDim.x) * blockDim.x;
@@ -133,6 +130,7 @@ int dk_optim_step(int kind, float* w, const float* g, float* s0, float* s1, void
     case DK_OPT_ADAM: DK_HOST_CHECK(DK_LAUNCH(optim_kernel<DK_OPT_ADAM>, grid, 256, 0, st, a)); break;
     case DK_OPT_ADADELTA: DK_HOST_CHECK(DK_LAUNCH(optim_kernel<DK_OPT_ADADELTA>, grid, 256, 0, st, a)); break;
     case DK_OPT_ADAMAX: DK_HOST_CHECK(DK_LAUNCH(optim_kernel<DK_OPT_ADAMAX>, grid, 256, 0, st, a)); break;
+    case DK_OPT_NADAM: DK_HOST_CHECK(DK_LAUNCH(optim_kernel<DK_OPT_NADAM>, grid, 256, 0, st, a)); break;
     default: return -1;
   }
   DK_HOST_CHECK(cudaGetLastError());

@@ -65,7 +65,7 @@ OP_BN_FWD, OP_BN_INF, OP_BN_BWD, OP_GAP_FWD, OP_GAP_BWD, OP_HEAD = 32, 33, 34, 3
 OP_CONV_GEMM, OP_WFLIP, OP_CONV_WGRAD, OP_BWD_UPDATE, OP_CONV_WGRAD_TMA = 38, 39, 40, 41, 42
 GEMM_TF32, GEMM_A_MN, GEMM_B_MN, GEMM_PERSISTENT, GEMM_PAIR, GEMM_SHORT_A = 1, 2, 4, 8, 16, 32
 
-OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6}
+OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6, "nadam": 7}
 IN_U8, IN_F32, IN_BF16 = 0, 1, 2
 LOSS_XENT, LOSS_MSE, LOSS_BCE = 0, 1, 2
 

@@ -22,15 +22,36 @@ def _to_index(t: torch.Tensor) -> torch.Tensor:
 
 
 class AccuracyEvaluator(Evaluator):
-    """``count(prediction == label) / count`` (``evaluators.py:28-48``) as one reduction."""
+    """``count(prediction == label) / count`` (``evaluators.py:28-48``) as one reduction.  A column of probability
+    vectors on a GPU box is reduced by ``dk_label_index`` (arg-max + compare + count in one pass over HBM)."""
 
     def evaluate(self, dataframe: Dataset) -> float:
         n = dataframe.count()
         if n == 0:
             return 0.0
-        pred = _to_index(dataframe[self.prediction_column])
+        pred = dataframe[self.prediction_column]
         label = _to_index(dataframe[self.label_column])
-        return float((pred == label).sum().item()) / float(n)
+        if torch.cuda.is_available() and pred.dim() == 2 and pred.shape[1] > 1 and pred.dtype.is_floating_point:
+            return self._evaluate_cuda(pred, label) / float(n)
+        return float((_to_index(pred) == label).sum().item()) / float(n)
+
+    @staticmethod
+    def _evaluate_cuda(pred: torch.Tensor, label: torch.Tensor) -> int:
+        from . import _native as N
+
+        p = pred.to("cuda", torch.float32).contiguous()
+        y = label.to("cuda", torch.int32).contiguous()
+        idx = torch.empty(p.shape[0], dtype=torch.int32, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        # a threshold no probability reaches: the rule degenerates to the arg-max; rows without a positive entry
+        # come back as -1 and are resolved with a plain arg-max (never happens for softmax / sigmoid outputs)
+        N.check(N.lib().dk_label_index(p.data_ptr(), p.shape[0], p.shape[1], float("inf"), -1, idx.data_ptr(),
+                                       y.data_ptr(), cnt.data_ptr(), N.current_stream()), "dk_label_index")
+        correct = int(cnt.item())
+        odd = idx < 0
+        if bool(odd.any()):
+            correct += int((p[odd].argmax(dim=1).to(torch.int32) == y[odd]).sum().item())
+        return correct
 
 
 class F1Evaluator(Evaluator):

@@ -783,7 +783,11 @@ def prepare_input(x, input_shape: Tuple[int, ...], device) -> torch.Tensor:
     return x
 
 
-def model_from_config(cfg: dict) -> Sequential:
+def model_from_config(cfg: dict):
+    if cfg.get("class_name") == "Model":  # functional graph (several inputs / outputs)
+        from .functional import Model
+
+        return Model.from_config(cfg)
     layers = []
     for lc in cfg["layers"]:
         cls = LAYER_CLASSES[lc["class_name"]]
@@ -791,7 +795,7 @@ def model_from_config(cfg: dict) -> Sequential:
     return Sequential(layers, name=cfg.get("name", "sequential"))
 
 
-def model_from_json(text: str) -> Sequential:
+def model_from_json(text: str):
     return model_from_config(json.loads(text))
 
 

@@ -22,6 +22,9 @@ _DEFAULTS = {
     "adam": dict(lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, decay=0.0),
     "adadelta": dict(lr=1.0, rho=0.95, epsilon=1e-7, decay=0.0),
     "adamax": dict(lr=0.002, beta_1=0.9, beta_2=0.999, epsilon=1e-7, decay=0.0),
+    # Nesterov Adam (Dozat 2016) with a constant beta_1: Keras' momentum-decay schedule (schedule_decay) is
+    # accepted and ignored
+    "nadam": dict(lr=0.002, beta_1=0.9, beta_2=0.999, epsilon=1e-7, decay=0.0, schedule_decay=0.004),
 }
 
 
@@ -81,6 +84,10 @@ def Adadelta(lr=1.0, rho=0.95, epsilon=1e-7, decay=0.0):
     return OptimizerSpec("adadelta", lr=lr, rho=rho, epsilon=epsilon, decay=decay)
 
 
+def Nadam(lr=0.002, beta_1=0.9, beta_2=0.999, epsilon=1e-7, schedule_decay=0.004):
+    return OptimizerSpec("nadam", lr=lr, beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, schedule_decay=schedule_decay)
+
+
 def Adamax(lr=0.002, beta_1=0.9, beta_2=0.999, epsilon=1e-7, decay=0.0):
     return OptimizerSpec("adamax", lr=lr, beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, decay=decay)
 
@@ -103,12 +110,12 @@ class FlatOptimizer:
             self.p0, self.p1 = float(c["momentum"]), 0.0
         elif name in ("rmsprop", "adadelta"):
             self.p0, self.p1 = float(c["rho"]), 0.0
-        elif name in ("adam", "adamax"):
+        elif name in ("adam", "adamax", "nadam"):
             self.p0, self.p1 = float(c["beta_1"]), float(c["beta_2"])
         else:
             self.p0 = self.p1 = 0.0
         need0 = self.kernel_kind != "sgd"
-        need1 = self.kernel_kind in ("adam", "adadelta", "adamax")
+        need1 = self.kernel_kind in ("adam", "adadelta", "adamax", "nadam")
         self.s0 = torch.zeros(numel, dtype=torch.float32, device=device) if need0 else None
         self.s1 = torch.zeros(numel, dtype=torch.float32, device=device) if need1 else None
         self.t = 0
@@ -181,5 +188,10 @@ class FlatOptimizer:
             self.s0.mul_(self.p0).add_((1 - self.p0) * g)
             torch.maximum(self.p1 * self.s1, g.abs(), out=self.s1)
             w.sub_(lr / (1 - self.p0 ** t) * self.s0 / (self.s1 + self.eps))
+        elif k == "nadam":
+            self.s0.mul_(self.p0).add_((1 - self.p0) * g)
+            self.s1.mul_(self.p1).add_((1 - self.p1) * g * g)
+            mhat = self.p0 * self.s0 / (1 - self.p0 ** (t + 1)) + (1 - self.p0) * g / (1 - self.p0 ** t)
+            w.sub_(lr * mhat / ((self.s1 / (1 - self.p1 ** t)).sqrt() + self.eps))
         else:  # pragma: no cover
             raise AssertionError(k)

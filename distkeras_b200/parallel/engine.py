@@ -85,6 +85,8 @@ def _bn_block(layer_index, layer: BatchNormalization, shape, prefix="") -> _Bloc
 def _group_layers(model: Sequential) -> List[_Block]:
     """Fold Activation / Dropout layers into the preceding block; expand residual blocks."""
     blocks: List[_Block] = []
+    if not isinstance(model, Sequential):
+        raise UnsupportedByNativeEngine("functional (multi-input / multi-output) model")
     model.build()
     for li, layer in enumerate(model.layers):
         in_shape, out_shape = model.shapes[li], model.shapes[li + 1]
@@ -1068,20 +1070,25 @@ def try_native_replica(model: Sequential, optimizer, loss: str, batch_size: int,
         return None
 
 
-def native_predict(model: Sequential, x: torch.Tensor, batch_size: int, device) -> Optional[torch.Tensor]:
-    """Batched inference through the native engine (reference op K14); ``None`` if not lowerable."""
+def native_predict(model: Sequential, x: torch.Tensor, batch_size: int, device, label_index=None):
+    """Batched inference through the native engine (reference op K14); ``None`` if not lowerable.
+
+    ``label_index=(activation_threshold, default_index)`` also runs the LabelIndexTransformer rule
+    (``distkeras/transformers.py:302-350``) on every batch of probabilities while they are still in HBM (one
+    ``dk_label_index`` launch per batch) and returns ``(probs, indices)``."""
     dev = torch.device(device)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     n = int(x.shape[0])
     if n == 0:
-        return torch.empty(0, model.output_shape[-1])
+        empty = torch.empty(0, model.output_shape[-1])
+        return empty if label_index is None else (empty, torch.empty(0, dtype=torch.int64))
     bs = min(batch_size, max(8, _r8(n)))
     in_dtype = "u8" if x.dtype == torch.uint8 else "f32"
     try:
         rep = NativeReplica(model, "sgd", "categorical_crossentropy", bs, idx, in_dtype=in_dtype, training=False)
     except UnsupportedByNativeEngine:
         return None
-    outs = []
+    outs, idxs = [], []
     flat = x.reshape(n, -1)
     for i in range(0, n, bs):
         chunk = flat[i:i + bs]
@@ -1089,6 +1096,15 @@ def native_predict(model: Sequential, x: torch.Tensor, batch_size: int, device) 
         if m < bs:
             pad = torch.zeros(bs - m, flat.shape[1], dtype=flat.dtype)
             chunk = torch.cat([chunk, pad], dim=0)
-        outs.append(rep.predict(chunk)[:m].cpu())
+        probs = rep.predict(chunk)
+        if label_index is not None:
+            out_idx = torch.empty(bs, dtype=torch.int32, device=probs.device)
+            N.check(rep.lib.dk_label_index(probs.data_ptr(), bs, probs.shape[1], float(label_index[0]),
+                                           int(label_index[1]), out_idx.data_ptr(), None, None,
+                                           C.c_void_p(N.current_stream())), "dk_label_index")
+            idxs.append(out_idx[:m].cpu().to(torch.int64))
+        outs.append(probs[:m].cpu())
     rep.close()
+    if label_index is not None:
+        return torch.cat(outs, dim=0), torch.cat(idxs, dim=0)
     return torch.cat(outs, dim=0)

@@ -495,7 +495,7 @@ class FabricEagerWorker:
 
     def __init__(self, model, optimizer, loss: str, algorithm: dict, region: FabricRegion, worker_id: int,
                  batch_size: int, device_index: int, in_dtype: str, input_affine=(1.0, 0.0), comm: str = "exchange",
-                 strict: bool = False, dense_labels: bool = False, seed: int = 0):
+                 strict: bool = False, dense_labels: bool = False, seed: int = 0, loss_weights=None, metrics=("accuracy",)):
         from .replica import TorchReplica
 
         self.alg = dict(algorithm)
@@ -506,7 +506,8 @@ class FabricEagerWorker:
         self.device = torch.device("cuda", device_index)
         torch.cuda.set_device(self.device)
         model = model.copy().to(self.device)
-        self.rep = TorchReplica(model, optimizer, loss, device=self.device, seed=seed + worker_id)
+        self.rep = TorchReplica(model, optimizer, loss, device=self.device, seed=seed + worker_id,
+                                loss_weights=loss_weights, metrics=metrics)
         self.lib = N.lib()
         self.scale, self.shift = float(input_affine[0]), float(input_affine[1])
         self.W = self.rep.W.data
@@ -586,32 +587,46 @@ class FabricEagerWorker:
         self.drain()
         self.initial_pull()
 
-    def train_partition(self, part: Partition, features_col: str, label_col: str, num_epoch: int = 1) -> None:
-        x_all, y_all = part.column(features_col), part.column(label_col)
+    def train_partition(self, part: Partition, features_col, label_col, num_epoch: int = 1) -> None:
+        """``features_col`` / ``label_col`` may be lists: one column per model input / output (functional
+        models, ``distkeras/workers.py:65-66, 140-148``); several feature columns feed a single-input model
+        concatenated."""
+        fcols = list(features_col) if isinstance(features_col, (list, tuple)) else [features_col]
+        lcols = list(label_col) if isinstance(label_col, (list, tuple)) else [label_col]
+        xs_all = [part.column(c) for c in fcols]
+        ys_all = [part.column(c) for c in lcols]
+        multi_in = int(getattr(self.rep.model, "num_inputs", 1)) > 1
+        losses = self.rep.losses
         pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd")
-        n = x_all.shape[0] // self.B
+        n = xs_all[0].shape[0] // self.B
+        row_bytes = sum(x[0].numel() * x.element_size() for x in xs_all)
         for _ in range(num_epoch):
             for b in range(n):
                 self.iteration += 1
                 fault_injection_point(self.worker_id, self.iteration)
-                x = x_all[b * self.B:(b + 1) * self.B].to(self.device, non_blocking=True).float()
+                lo, hi = b * self.B, (b + 1) * self.B
+                xs = [x[lo:hi].to(self.device, non_blocking=True).float() for x in xs_all]
                 if self.scale != 1.0 or self.shift != 0.0:
-                    x = x * self.scale + self.shift
-                y = y_all[b * self.B:(b + 1) * self.B].to(self.device, non_blocking=True)
-                self.h2d_bytes += x_all[0].numel() * x_all.element_size() * self.B
+                    xs = [x * self.scale + self.shift for x in xs]
+                if not multi_in:
+                    xs = xs[0] if len(xs) == 1 else torch.cat([x.reshape(x.shape[0], -1) for x in xs], dim=1)
+                ys = []
+                for y_col, ls in zip(ys_all, losses if len(losses) == len(ys_all) else [losses[0]] * len(ys_all)):
+                    y = y_col[lo:hi].to(self.device, non_blocking=True)
+                    ys.append(y.long() if (y.dim() == 1 and "crossentropy" in str(ls)) else y)
+                self.h2d_bytes += row_bytes * self.B
                 if pre_batch and self.iteration % self.tau == 0:
                     self._comm_ops()
                 if self.alg["kind"] == "eamsgd":
                     N.check(self.lib.dk_eamsgd_pre(self.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(), None,
                                                    self.P, float(self.alg["momentum"]), self._stream()), "eamsgd_pre")
-                loss, acc = self.rep.train_on_batch(
-                    x, y.long() if (y.dim() == 1 and "crossentropy" in str(self.rep.loss)) else y)
+                h = self.rep.train_on_batch(xs, ys if len(ys) > 1 else ys[0])
                 if self.alg["kind"] == "eamsgd":
                     N.check(self.lib.dk_eamsgd_post(self.W.data_ptr(), self.mom.data_ptr(), self.wcopy.data_ptr(), None,
                                                     self.P, float(self.alg["eta"]), self._stream()), "eamsgd_post")
-                self.d2h_bytes += 8
-                self.history.append({"history": [loss, acc], "worker_id": self.worker_id, "iteration": self.iteration,
-                                     "timestamp": time.time()})
+                self.d2h_bytes += 4 * len(h)
+                self.history.append({"history": [float(v) for v in h], "worker_id": self.worker_id,
+                                     "iteration": self.iteration, "timestamp": time.time()})
                 if not pre_batch and self.iteration % self.tau == 0:
                     self._comm_ops()
         self.drain()
@@ -786,7 +801,7 @@ def _scratch_i32(worker) -> torch.Tensor:
 
 def _affine_for(dataset: Dataset, features_col: str):
     """uint8 features are shipped raw and normalised to [0, 1] on the device (fused MinMax)."""
-    x = dataset[features_col]
+    x = dataset[features_col[0] if isinstance(features_col, (list, tuple)) else features_col]
     if x.dtype == torch.uint8:
         return "u8", (1.0 / 255.0, 0.0)
     return "f32", (1.0, 0.0)
@@ -885,7 +900,8 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
             warnings.warn(f"the native sm_100a engine does not lower this model ({exc}); the replica runs on the "
                           "autograd executor (cuBLAS / cuDNN), the parameter-server program stays in-kernel")
             worker = FabricEagerWorker(model, trainer.worker_optimizer, trainer.loss, alg, region, wid,
-                                       trainer.batch_size, local, in_dtype, affine, **wkw)
+                                       trainer.batch_size, local, in_dtype, affine, loss_weights=trainer.loss_weights,
+                                       metrics=trainer.metrics, **wkw)
         worker.initial_pull()
         worker.capture()
         static = getattr(trainer, "shard_mode", "dynamic" if trainer.parallelism_factor > 1 else "static") == "static"
@@ -1102,11 +1118,17 @@ def train_distributed_fabric(trainer, dataset: Dataset):
 # ------------------------------------------------------------------------------------------------
 # single-GPU / averaging trainers on the native engine
 # ------------------------------------------------------------------------------------------------
-def _sequential_native(trainer, part: Partition, model, device_index: int, worker_id: int, num_epoch: int):
+def _sequential_native(trainer, part: Partition, model, device_index: int, worker_id: int, num_epoch: int,
+                       init_flat: Optional[torch.Tensor] = None, device_result: bool = False):
+    """One replica, one partition, ``num_epoch`` passes through the native engine.  ``init_flat`` (a device
+    tensor) overrides the model's weights without a host round trip; ``device_result`` returns the trained flat
+    buffer as a device tensor instead of writing it back into ``model`` (both: ``train_averaging_native``)."""
     dataset = part.dataset
     in_dtype, affine = _affine_for(dataset, trainer.features_column)
     rep = NativeReplica(model, trainer.worker_optimizer, trainer.loss, trainer.batch_size, device_index,
                         in_dtype=in_dtype, input_affine=affine, hist_slots=4096)
+    if init_flat is not None:
+        rep.set_flat(init_flat)
     x_all, y_all = part.column(trainer.features_column), part.column(trainer.label_column)
     if rep.dense_labels:   # regression targets (mse on a linear head): fp32 [n, n_out], never argmax'd
         y_all = y_all.to(torch.float32).reshape(y_all.shape[0], -1)
@@ -1140,6 +1162,10 @@ def _sequential_native(trainer, part: Partition, model, device_index: int, worke
                 it += 1
                 history.append({"history": [float(recs[j, 0]), float(recs[j, 1])], "worker_id": worker_id,
                                 "iteration": it, "timestamp": now})
+    if device_result:
+        flat = rep.W.detach().clone()
+        rep.close()
+        return flat, history
     model.set_flat_weights(rep.W.detach().cpu())
     rep.close()
     return model, history
@@ -1160,8 +1186,11 @@ def train_single_native(trainer, dataset: Dataset):
 
 
 def train_averaging_native(trainer, dataset: Dataset):
-    """``AveragingTrainer`` on the GPUs of this process: one replica per device trained in turn
-    streams, then the per-epoch mean computed by the in-kernel P2P all-reduce (``dk_ps_average``)."""
+    """``AveragingTrainer`` on the GPUs of this process (reference op K13, ``trainers.py:190-247``): one replica per
+    device trains its partition (one host thread each, launches are asynchronous), then the epoch's mean is a
+    reduce-scatter + all-gather over peer memory -- device ``r`` launches ``dk_ps_average`` on slice ``r`` only:
+    it reads that slice from every replica over NVLink, averages, and writes the result into every replica.  The
+    replicas of the next epoch start from those device buffers; the host sees the weights once, at the end."""
     ndev = torch.cuda.device_count()
     W = trainer.num_workers
     parts = dataset.repartition(W).partitions(W)
@@ -1170,10 +1199,16 @@ def train_averaging_native(trainer, dataset: Dataset):
     lib = N.lib()
     import threading
 
+    flats: List[Optional[torch.Tensor]] = [None] * W
+    host_synced = True            # does `master` (host) hold the current mean?
+    eager = [False]               # a replica fell back to the autograd worker: it restarts from the host model
     for epoch in range(trainer.num_epoch):
-        flats: List[Optional[torch.Tensor]] = [None] * W
         hists: List[list] = [[] for _ in range(W)]
         errors: list = []
+        if eager[0] and not host_synced:
+            master.set_flat_weights(flats[0].cpu())
+            trainer.master_model = serialize_keras_model(master)
+            host_synced = True
 
         def run(w: int) -> None:
             try:
@@ -1181,15 +1216,18 @@ def train_averaging_native(trainer, dataset: Dataset):
                 torch.cuda.set_device(dev)
                 with torch.cuda.stream(torch.cuda.Stream(device=dev)):
                     try:
-                        m, h = _sequential_native(trainer, parts[w], master.copy(), dev, w, 1)
+                        flat, h = _sequential_native(trainer, parts[w], master.copy(), dev, w, 1, init_flat=flats[w],
+                                                     device_result=True)
                     except UnsupportedByNativeEngine:
                         # models the planner does not lower (tanh hidden layers, Reshape, ...): the
                         # autograd SequentialWorker trains this replica on the same GPU
                         from ..trainers import _run_tasks
 
+                        eager[0] = True
                         res, ws = _run_tasks(trainer.allocate_worker(), [parts[w]], 1, lambda tid: f"cuda:{dev}")
-                        m, h = deserialize_keras_model(res[0][0]), ws[0].training_history
-                    flats[w] = m.get_flat_weights().to(f"cuda:{dev}", torch.float32).contiguous()
+                        flat = deserialize_keras_model(res[0][0]).get_flat_weights().to(f"cuda:{dev}", torch.float32)
+                        h = ws[0].training_history
+                    flats[w] = flat.contiguous()
                     torch.cuda.current_stream().synchronize()
                 for rec in h:
                     rec["epoch"] = epoch
@@ -1197,8 +1235,9 @@ def train_averaging_native(trainer, dataset: Dataset):
             except BaseException as exc:
                 errors.append(exc)
 
-        # one host thread per replica: launches are asynchronous, so the W replicas train
-        # concurrently (one per GPU when W <= #GPUs)
+        if eager[0] and epoch > 0:
+            # the autograd workers read trainer.master_model (host), which was refreshed above
+            flats = [None] * W
         threads = [threading.Thread(target=run, args=(w,), daemon=True) for w in range(W)]
         for t in threads:
             t.start()
@@ -1208,29 +1247,49 @@ def train_averaging_native(trainer, dataset: Dataset):
             raise errors[0]
         for h in hists:
             history += h
-        distinct = sorted({f.device.index for f in flats})
-        if len(distinct) == W and W <= 16 and all(
-                a == b or lib.dk_can_access_peer(a, b) for a in distinct for b in distinct):
-            for a in distinct:
-                for b in distinct:
-                    if a != b:
-                        N.check(lib.dk_enable_peer_access(a, b), "peer access")
-            arr = (C.c_void_p * W)(*[f.data_ptr() for f in flats])
-            torch.cuda.set_device(flats[0].device)
-            n = flats[0].numel()
-            N.check(lib.dk_ps_average(arr, W, 0, n, C.c_void_p(N.current_stream())), "dk_ps_average")
-            torch.cuda.synchronize()
-            mean = flats[0].cpu()
-        else:
-            torch.cuda.set_device(0)
-            stack = torch.stack([f.to("cuda:0") for f in flats])
-            arr = (C.c_void_p * W)(*[stack[i].data_ptr() for i in range(W)])
-            N.check(lib.dk_ps_average(arr, W, 0, stack.shape[1], C.c_void_p(N.current_stream())), "dk_ps_average")
-            torch.cuda.synchronize()
-            mean = stack[0].cpu()
-        master.set_flat_weights(mean)
-        trainer.master_model = serialize_keras_model(master)
+        _average_replicas(flats, lib)
+        host_synced = False
+    if not host_synced and flats[0] is not None:
+        master.set_flat_weights(flats[0].cpu())
+    trainer.master_model = serialize_keras_model(master)
     return master, history
+
+
+def _average_replicas(flats: List[torch.Tensor], lib) -> None:
+    """In place: every tensor of ``flats`` becomes the element-wise mean.  One replica per device with full peer
+    access: reduce-scatter + all-gather (device r owns slice r); otherwise one kernel on the first device over
+    staged copies."""
+    W = len(flats)
+    n = flats[0].numel()
+    devs = [f.device.index for f in flats]
+    peer_ok = len(set(devs)) == W and W <= 16 and all(
+        a == b or lib.dk_can_access_peer(a, b) for a in devs for b in devs)
+    if peer_ok:
+        for a in devs:
+            for b in devs:
+                if a != b:
+                    N.check(lib.dk_enable_peer_access(a, b), "peer access")
+        arr = (C.c_void_p * W)(*[f.data_ptr() for f in flats])
+        per = (n + W - 1) // W
+        per = (per + 3) // 4 * 4                       # slice bounds keep float4 alignment
+        for r, f in enumerate(flats):
+            lo, hi = min(n, r * per), min(n, (r + 1) * per)
+            if hi <= lo:
+                continue
+            with torch.cuda.device(f.device):
+                N.check(lib.dk_ps_average(arr, W, lo, hi, C.c_void_p(N.current_stream())), "dk_ps_average")
+        for f in flats:
+            torch.cuda.synchronize(f.device)
+        return
+    first = flats[0].device
+    with torch.cuda.device(first):
+        stack = torch.stack([f.to(first) for f in flats])
+        arr = (C.c_void_p * W)(*[stack[i].data_ptr() for i in range(W)])
+        N.check(lib.dk_ps_average(arr, W, 0, n, C.c_void_p(N.current_stream())), "dk_ps_average")
+        torch.cuda.synchronize(first)
+        for f in flats:
+            f.copy_(stack[0])
+        torch.cuda.synchronize(first)
 
 
 def train_ensemble_native(trainer, dataset: Dataset):

@@ -121,8 +121,9 @@ class OneHotTransformer(Transformer):
 
 class LabelIndexTransformer(Transformer):
     """Prediction vector -> class index: the FIRST element >= ``activation_threshold``, otherwise
-    the arg-max, otherwise ``default_index`` (``transformers.py:302-350``).  The same rule runs
-    as a fused kernel in the native predictor (``dk_label_index``)."""
+    the arg-max, otherwise ``default_index`` (``transformers.py:302-350``).  With a GPU present the
+    column goes through the one-pass kernel ``dk_label_index`` (``csrc/loss_kernels.cu``); the PyTorch
+    expression below is the CPU path and the oracle the kernel is tested against."""
 
     def __init__(self, output_dim, input_col="prediction", output_col="prediction_index", default_index=0,
                  activation_threshold=0.55):
@@ -135,8 +136,20 @@ class LabelIndexTransformer(Transformer):
     def get_index(self, vector) -> int:
         return int(self.indices(torch.as_tensor(np.asarray(vector, dtype=np.float32)).reshape(1, -1))[0])
 
-    def indices(self, p: torch.Tensor) -> torch.Tensor:
+    def indices(self, p: torch.Tensor, device=None) -> torch.Tensor:
         p = p[:, :self.output_dimensionality].to(torch.float32)
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        if str(device).startswith("cuda") and p.shape[0] > 0:
+            from . import _native as N
+
+            pd = p.to(device).contiguous()
+            out = torch.empty(pd.shape[0], dtype=torch.int32, device=pd.device)
+            with torch.cuda.device(pd.device):
+                N.check(N.lib().dk_label_index(pd.data_ptr(), pd.shape[0], pd.shape[1], self.activation_threshold,
+                                               self.default_index, out.data_ptr(), None, None, N.current_stream()),
+                        "dk_label_index")
+            return out.to(torch.int64).cpu()
         above = p >= self.activation_threshold
         first_above = torch.where(above.any(dim=1), above.float().argmax(dim=1), torch.full((p.shape[0],), -1))
         best, arg = p.max(dim=1)

@@ -56,6 +56,16 @@ class Worker:
         self.training_history: List[dict] = []
         self.iteration = 1
         self._error: Optional[BaseException] = None
+        # a functional model with several inputs takes the feature columns one per input (the reference's
+        # list-valued features_col, workers.py:65-66); a single-input model gets them concatenated
+        self._multi_input = False
+        try:
+            import json as _json
+
+            spec = _json.loads(self.model["model"]) if isinstance(self.model.get("model"), str) else {}
+            self._multi_input = spec.get("class_name") == "Model" and len(spec.get("inputs", [])) > 1
+        except (ValueError, AttributeError, TypeError):
+            pass
 
     # -- small accessors ----------------------------------------------------------------------
     def set_max_prefetch(self, max_mini_batches: int) -> None:
@@ -84,7 +94,8 @@ class Worker:
         model = deserialize_keras_model(self.model)
         device = torch.device(self.device) if self.device is not None else torch.device("cpu")
         model.to(device)
-        self.replica = TorchReplica(model, self.optimizer, self.loss, device=device)
+        self.replica = TorchReplica(model, self.optimizer, self.loss, device=device, loss_weights=self.loss_weights,
+                                    metrics=self.metrics)
 
     # -- data -----------------------------------------------------------------------------------
     def get_next_minibatch(self):
@@ -105,7 +116,7 @@ class Worker:
         if isinstance(iterator, Partition):
             for batch in iterator.batches(fcols + lcols, self.batch_size, drop_last=True):
                 xs, ys = batch[:len(fcols)], batch[len(fcols):]
-                yield self._merge_columns(xs), (ys[0] if len(ys) == 1 else list(ys))
+                yield (list(xs) if self._multi_input else self._merge_columns(xs)), (ys[0] if len(ys) == 1 else list(ys))
             return
         rows = []
         for row in iterator:
@@ -114,7 +125,7 @@ class Worker:
                 xs = [torch.as_tensor(np.stack([np.asarray(r[c]) for r in rows])) for c in fcols]
                 ys = [torch.as_tensor(np.stack([np.asarray(r[c]) for r in rows])) for c in lcols]
                 rows = []
-                yield self._merge_columns(xs), (ys[0] if len(ys) == 1 else ys)
+                yield (xs if self._multi_input else self._merge_columns(xs)), (ys[0] if len(ys) == 1 else ys)
 
     @staticmethod
     def _merge_columns(xs):

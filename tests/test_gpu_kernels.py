@@ -64,7 +64,7 @@ def test_gemm_tf32(N):
     assert torch.allclose(out, a @ b.t(), atol=0.15, rtol=1e-2)
 
 
-@pytest.mark.parametrize("name", ["sgd", "momentum", "adagrad", "rmsprop", "adam", "adadelta", "adamax"])
+@pytest.mark.parametrize("name", ["sgd", "momentum", "adagrad", "rmsprop", "adam", "adadelta", "adamax", "nadam"])
 def test_fused_optimizer_matches_reference(N, name):
     from distkeras_b200.ops.flat_optim import FlatOptimizer
 
@@ -231,9 +231,24 @@ def test_label_index_kernel(N):
     idx = torch.zeros(500, dtype=torch.int32, device="cuda")
     cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     N.check(N.lib().dk_label_index(p.data_ptr(), 500, 10, 0.55, 0, idx.data_ptr(), labels.data_ptr(), cnt.data_ptr(), st()))
-    want = LabelIndexTransformer(10).indices(p.cpu())
+    want = LabelIndexTransformer(10).indices(p.cpu(), device="cpu")
     assert torch.equal(idx.cpu().long(), want)
     assert int(cnt) == int((want == labels.cpu().long()).sum())
+
+
+def test_label_index_transformer_runs_the_kernel_and_matches_the_cpu_rule(N):
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.transformers import LabelIndexTransformer
+
+    torch.manual_seed(10)
+    p = torch.softmax(torch.randn(1000, 7) * 3, 1)
+    p[:50] = 0.0                      # no positive entry: default index
+    p[50:100, 3] = 0.6                # two entries over the threshold: the first wins
+    p[50:100, 5] = 0.9
+    t = LabelIndexTransformer(7, default_index=2, activation_threshold=0.55)
+    got = t.transform(Dataset({"prediction": p}))["prediction_index"]
+    assert torch.equal(got.long(), t.indices(p, device="cpu"))
+    assert set(got[:50].tolist()) == {2.0} and set(got[50:100].tolist()) == {3.0}
 
 
 def test_gemm_pull_fused_kernel(N):

@@ -223,6 +223,32 @@ def test_emperor_scheme_decays_learning_rate():
     assert t.get_learning_rate() < 0.1 and t.get_num_epoch() == 1
 
 
+def test_nadam_is_adam_with_a_nesterov_look_ahead():
+    """Nadam with a constant beta_1 (Dozat 2016, algorithm 8 without the momentum-decay schedule), float64 oracle."""
+    torch.manual_seed(1)
+    n, lr, b1, b2, eps = 101, 0.02, 0.9, 0.999, 1e-7
+    w0 = torch.randn(n)
+    grads = [torch.randn(n) for _ in range(6)]
+    opt = FlatOptimizer({"class_name": "nadam", "config": {"lr": lr}}, n, "cpu")
+    w = w0.clone()
+    for g in grads:
+        opt.step(w, g)
+    x, m, v = w0.double(), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    for t, g in enumerate(grads, 1):
+        g = g.double()
+        m = b1 * m + (1 - b1) * g
+        v = b2 * v + (1 - b2) * g * g
+        look_ahead = b1 * m / (1 - b1 ** (t + 1)) + (1 - b1) * g / (1 - b1 ** t)
+        x = x - lr * look_ahead / ((v / (1 - b2 ** t)).sqrt() + eps)
+    assert torch.allclose(w.double(), x, atol=1e-5)
+    # and it differs from plain Adam on the same gradients
+    adam = FlatOptimizer({"class_name": "adam", "config": {"lr": lr}}, n, "cpu")
+    wa = w0.clone()
+    for g in grads:
+        adam.step(wa, g)
+    assert (wa - w).abs().max() > 1e-3
+
+
 @pytest.mark.parametrize("name", ["sgd", "adagrad", "rmsprop", "adam", "adadelta", "adamax"])
 def test_flat_optimizer_matches_torch(name):
     torch.manual_seed(0)
