@@ -297,6 +297,78 @@ __global__ void ps_ticket_kernel(unsigned* ctrl, const unsigned* last_update, fl
   }
 }
 
+// Device-side rendezvous of `workers` ranks (synchronous EASGD): instance r of the barrier completes when the
+// monotonic arrival counter reaches (r + 1) * workers.  Release on arrive / acquire on the spin make every rank's
+// earlier center updates visible to every rank's later center reads.  A rank that waits longer than the timeout
+// (a peer died) or sees the stop flag marks the rendezvous broken and moves on instead of hanging the GPU.
+__global__ void ps_barrier_kernel(unsigned* ctrl, unsigned workers, unsigned* round, unsigned* broken,
+                                  unsigned long long timeout_ns) {
+  DK_PDL_ENTER();
+  const unsigned r = *round;
+  *round = r + 1u;
+  if (*broken != 0u) return;
+  const unsigned target = (r + 1u) * workers;
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+  asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(ctrl + DK_CTRL_BARRIER) : "memory");
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned seen, stop;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctrl + DK_CTRL_BARRIER) : "memory");
+    if (static_cast<int>(seen - target) >= 0) break;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(stop) : "l"(ctrl + DK_CTRL_STOP) : "memory");
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (stop != 0u || t1 - t0 > timeout_ns) {
+      *broken = 1u;
+      break;
+    }
+    __nanosleep(100);
+  }
+}
+
+// Synchronous EASGD, phase 1: elastic difference against the (quiescent) center; the worker moves, the center is
+// only read.  Phase 2 (after everybody has read): the center absorbs the stored difference.
+__global__ void __launch_bounds__(kPsThreads)
+ps_easgd_read_kernel(const float* __restrict__ center, float* __restrict__ w, __nv_bfloat16* __restrict__ wb,
+                     float* __restrict__ e_out, long n, float alpha) {
+  DK_PDL_ENTER();
+  flat_pipeline(
+      n, [&](long i) { return *reinterpret_cast<const float4*>(w + i); },
+      [&](long i, const float4&) { return ld_sys_v4(center + i); },
+      [&](long i, const float4& x0, const float4& c) {
+        float4 x = x0;
+        const float4 e = make_float4(alpha * (x.x - c.x), alpha * (x.y - c.y), alpha * (x.z - c.z),
+                                     alpha * (x.w - c.w));
+        x.x -= e.x; x.y -= e.y; x.z -= e.z; x.w -= e.w;
+        *reinterpret_cast<float4*>(w + i) = x;
+        *reinterpret_cast<float4*>(e_out + i) = e;
+        if (wb != nullptr) st_bf16x4(wb + i, x);
+      },
+      [&](long i) {
+        const float c = ld_sys(center + i);
+        const float e = alpha * (w[i] - c);
+        const float x = w[i] - e;
+        w[i] = x;
+        e_out[i] = e;
+        if (wb != nullptr) wb[i] = __float2bfloat16_rn(x);
+      });
+}
+
+__global__ void __launch_bounds__(kPsThreads)
+ps_easgd_add_kernel(float* __restrict__ center, const float* __restrict__ e, long n, unsigned* ctrl, int worker) {
+  DK_PDL_ENTER();
+  flat_pipeline(
+      n, [&](long i) { return *reinterpret_cast<const float4*>(e + i); },
+      [&](long, const float4&) { return NoRegs{}; },
+      [&](long i, const float4& v, const NoRegs&) { red_add_v4_sys(center + i, v); },
+      [&](long i) { red_add_sys(center + i, e[i]); });
+  if (ctrl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(ctrl + DK_CTRL_NUM_UPDATES) : "memory");
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(ctrl + DK_CTRL_HEARTBEAT + worker) : "memory");
+  }
+}
+
 // Host-visible fetch-add on a control word (dynamic shard queue: workers claim the next data
 // partition; the replacement for Spark's task scheduler + `parallelism_factor` over-partitioning).
 __global__ void ps_fetch_add_kernel(unsigned* word, unsigned inc, unsigned* out) {
@@ -434,6 +506,26 @@ int dk_ps_ticket(unsigned* ctrl, const unsigned* last_update, float* scale_out, 
 
 int dk_ps_fetch_add(unsigned* word, unsigned inc, unsigned* out, void* stream) {
   DK_HOST_CHECK(DK_LAUNCH(ps_fetch_add_kernel, 1, 1, 0, (cudaStream_t)stream, word, inc, out));
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_ps_barrier(unsigned* ctrl, int workers, unsigned* round, unsigned* broken, int timeout_ms, void* stream) {
+  DK_HOST_CHECK(DK_LAUNCH(ps_barrier_kernel, 1, 1, 0, (cudaStream_t)stream, ctrl, static_cast<unsigned>(workers), round,
+                          broken, static_cast<unsigned long long>(timeout_ms) * 1000000ull));
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_ps_easgd_read(const float* center, float* w, void* wb, float* e, long n, float alpha, void* stream) {
+  DK_HOST_CHECK(DK_LAUNCH(ps_easgd_read_kernel, ps_grid(n), kPsThreads, 0, (cudaStream_t)stream, center, w,
+                          reinterpret_cast<__nv_bfloat16*>(wb), e, n, alpha));
+  DK_HOST_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dk_ps_easgd_add(float* center, const float* e, long n, unsigned* ctrl, int worker, void* stream) {
+  DK_HOST_CHECK(DK_LAUNCH(ps_easgd_add_kernel, ps_grid(n), kPsThreads, 0, (cudaStream_t)stream, center, e, n, ctrl, worker));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }

@@ -71,6 +71,7 @@ LOSS_XENT, LOSS_MSE, LOSS_BCE = 0, 1, 2
 
 # control block words (csrc/ps.h)
 CTRL_NUM_UPDATES, CTRL_LOCK_NEXT, CTRL_LOCK_SERVING, CTRL_STOP, CTRL_SHARD_NEXT, CTRL_WORKERS_DONE = 0, 1, 2, 3, 4, 5
+CTRL_BARRIER = 6
 CTRL_HEARTBEAT, CTRL_DONE_FLAGS, CTRL_STALENESS_HIST, CTRL_WORDS = 16, 56, 96, 128
 CTRL_MAX_WORKERS = 40
 
@@ -103,6 +104,9 @@ _SIGNATURES = {
     "dk_ps_damped_exchange": (i32, [vp, vp, vp, vp, i64, f32, f32, vp, i32, u32, vp]),
     "dk_ps_ticket": (i32, [vp, vp, vp, vp]),
     "dk_ps_fetch_add": (i32, [vp, u32, vp, vp]),
+    "dk_ps_barrier": (i32, [vp, i32, vp, vp, i32, vp]),
+    "dk_ps_easgd_read": (i32, [vp, vp, vp, vp, i64, f32, vp]),
+    "dk_ps_easgd_add": (i32, [vp, vp, i64, vp, i32, vp]),
     "dk_ps_lock_acquire": (i32, [vp, vp, vp]),
     "dk_ps_lock_release": (i32, [vp, vp, vp]),
     "dk_ps_average": (i32, [C.POINTER(vp), i32, i64, i64, vp]),

@@ -121,6 +121,8 @@ class FabricWorker:
         if self.alg["kind"] == "eamsgd":
             self.mom = torch.zeros(rep.P, dtype=torch.float32, device=dev)
             self.wcopy = torch.zeros(rep.P, dtype=torch.float32, device=dev)
+        if self.alg["kind"] == "easgd":
+            _easgd_state(self, rep.P, dev)
         # double-buffered region staging
         n = self.n_max
         self.x_stage = [torch.zeros(n * self.B, self.F, dtype=rep.in_torch_dtype, device=dev) for _ in (0, 1)]
@@ -174,6 +176,8 @@ class FabricWorker:
             N.check(lib.dk_ps_ticket(ctrl, self.last_update.data_ptr(), self.scale_dev.data_ptr(), st), "ticket")
             k += 1
         shards = self.shards or [(0, self.rep.P, reg.center_ptr)]
+        if self.alg["kind"] == "easgd":
+            return k + _easgd_round(self, shards, self.rep.W.data_ptr(), self.rep.Wb.data_ptr(), st)
         for i, (lo, hi, cptr) in enumerate(shards):
             # the control block (update counter, heartbeat) is bumped once per commit: by shard 0
             k += self._comm_range(lo, hi, cptr, ctrl if i == 0 else None, st)
@@ -253,7 +257,7 @@ class FabricWorker:
         rep, tau = self.rep, self.tau
         seg = rep.hist[parity * self.n_max:parity * self.n_max + n]
         seg.zero_()
-        pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd")
+        pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd", "easgd")
         kernels = exchanges = 0
         if rep.compact:
             before = rep.launches()
@@ -519,6 +523,8 @@ class FabricEagerWorker:
         if self.alg["kind"] == "eamsgd":
             self.mom = torch.zeros_like(self.W)
             self.wcopy = torch.zeros_like(self.W)
+        if self.alg["kind"] == "easgd":
+            _easgd_state(self, self.P, self.device)
         self.compute = torch.cuda.current_stream(self.device)
         self.history: List[dict] = []
         self.iteration = 0
@@ -554,6 +560,8 @@ class FabricEagerWorker:
         elif k in ("aeasgd", "eamsgd"):
             N.check(lib.dk_ps_elastic(c, W, None, self.P, float(self.alg["alpha"]), ctrl, self.worker_id,
                                       self.iteration, st), "elastic")
+        elif k == "easgd":
+            _easgd_round(self, [(0, self.P, reg.center_ptr)], W, 0, st)
         elif k == "experimental":
             N.check(lib.dk_ps_damped_exchange(c, W, W1, None, self.P, 1.0 / self.tau, float(self.alg["inv_lr"]), ctrl,
                                               self.worker_id, self.iteration, st), "damped_exchange")
@@ -597,7 +605,7 @@ class FabricEagerWorker:
         ys_all = [part.column(c) for c in lcols]
         multi_in = int(getattr(self.rep.model, "num_inputs", 1)) > 1
         losses = self.rep.losses
-        pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd")
+        pre_batch = self.alg["kind"] in ("downpour", "aeasgd", "eamsgd", "easgd")
         n = xs_all[0].shape[0] // self.B
         row_bytes = sum(x[0].numel() * x.element_size() for x in xs_all)
         for _ in range(num_epoch):
@@ -630,6 +638,41 @@ class FabricEagerWorker:
                 if not pre_batch and self.iteration % self.tau == 0:
                     self._comm_ops()
         self.drain()
+
+
+def _easgd_state(worker, numel: int, device) -> None:
+    """Device state of the synchronous-EASGD rendezvous: the stored elastic difference, this worker's barrier
+    instance counter (advanced by the barrier kernel itself, so captured graphs replay correctly) and the
+    broken-rendezvous flag (a peer did not show up within ``DK_BARRIER_TIMEOUT_MS``: stop waiting for it)."""
+    worker.E = torch.zeros(numel, dtype=torch.float32, device=device)
+    worker.bar_round = torch.zeros(1, dtype=torch.int32, device=device)
+    worker.bar_broken = torch.zeros(1, dtype=torch.int32, device=device)
+    worker.bar_timeout_ms = int(os.environ.get("DK_BARRIER_TIMEOUT_MS", "10000"))
+
+
+def _easgd_round(worker, shards, w_ptr: int, wb_ptr: int, st) -> int:
+    """One synchronous-EASGD round on the current stream (``docs/optimizers.md:22-31`` of the reference; the
+    thread-backend oracle is ``workers.EASGDWorker``): rendezvous (every rank's previous center update has
+    landed) -> ``E = alpha (W - C)``, ``W -= E`` reading the quiescent center -> rendezvous (everybody has read)
+    -> ``C += E``.  Returns the number of kernels."""
+    lib, reg = worker.lib, worker.region
+    ctrl = C.c_void_p(reg.ctrl_ptr)
+    nw = int(worker.alg.get("workers", 1))
+    alpha = float(worker.alg["alpha"])
+
+    def meet():
+        N.check(lib.dk_ps_barrier(ctrl, nw, worker.bar_round.data_ptr(), worker.bar_broken.data_ptr(),
+                                  worker.bar_timeout_ms, st), "barrier")
+
+    meet()
+    for lo, hi, cptr in shards:
+        N.check(lib.dk_ps_easgd_read(C.c_void_p(cptr), w_ptr + 4 * lo, (wb_ptr + 2 * lo) if wb_ptr else None,
+                                     worker.E.data_ptr() + 4 * lo, hi - lo, alpha, st), "easgd_read")
+    meet()
+    for i, (lo, hi, cptr) in enumerate(shards):
+        N.check(lib.dk_ps_easgd_add(C.c_void_p(cptr), worker.E.data_ptr() + 4 * lo, hi - lo, ctrl if i == 0 else None,
+                                    worker.worker_id, st), "easgd_add")
+    return 2 + 2 * len(shards)
 
 
 class FabricExchange:
@@ -882,6 +925,18 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
     parts = dataset.repartition(n_parts).partitions(n_parts)
     history: List[dict] = []
     stats = {"kernels_per_window": 0, "windows": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+    sync_rows = None
+    if alg["kind"] == "easgd":
+        # lock step: every worker trains the same number of mini-batches (the shortest shard decides), so every
+        # rank runs the same number of rendezvous
+        alg["workers"] = len(worker_ranks)
+        n_parts = len(worker_ranks)
+        if getattr(trainer, "data_is_local_shard", False):
+            rows = [exchange_obj(len(dataset) if rank == r else None, r) for r in range(world)]
+            sync_rows = min(rows[r] for r in worker_ranks)
+        else:
+            sync_rows = min(len(p) for p in dataset.repartition(n_parts).partitions(n_parts))
+        sync_rows = sync_rows // trainer.batch_size * trainer.batch_size
     if rank in worker_ranks:
         dataset.pin_memory()
         parts = dataset.repartition(n_parts).partitions(n_parts)
@@ -911,6 +966,10 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
             static = True
             f = max(1, int(trainer.parallelism_factor))
             my_parts = dataset.repartition(f).partitions(f)
+        if sync_rows is not None:
+            static = True
+            src = dataset.partitions(1)[0] if getattr(trainer, "data_is_local_shard", False) else parts[wid]
+            my_parts = [Partition(src.dataset, src.index, src.start, src.start + sync_rows)]
         torch.cuda.synchronize()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -477,7 +477,7 @@ class AsynchronousDistributedTrainer(DistributedTrainer):
 class SynchronousDistributedTrainer(DistributedTrainer):
     """Base of the synchronous parameter-server trainers: one partition per worker, all workers alive at
     the same time (the reference names it in ``docs/optimizers.md:22-31`` / ``workflow.ipynb:112`` but ships
-    no implementation).  Runs on the thread / socket backends."""
+    no implementation).  Runs on the thread / socket backends; ``EASGD`` also on the fabric."""
 
     def _num_partitions(self) -> int:
         return self.num_workers
@@ -529,6 +529,11 @@ class EASGD(SynchronousDistributedTrainer):
                         learning_rate=self.learning_rate, **_worker_kwargs(self))
         w.barrier = threading.Barrier(self.num_workers)
         return w
+
+    def algorithm(self) -> dict:
+        """Fabric backend: the rendezvous is a device-side barrier on the PS control block (``dk_ps_barrier``),
+        the elastic read and the center update are two kernels with a barrier between them."""
+        return {"kind": "easgd", "window": self.communication_window, "alpha": self.rho * self.learning_rate}
 
 
 class DOWNPOUR(AsynchronousDistributedTrainer):

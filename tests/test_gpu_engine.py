@@ -135,6 +135,7 @@ def test_fabric_adag_matches_cpu_oracle_single_worker():
 @pytest.mark.parametrize("name,kw", [
     ("ADAG", dict(communication_window=4)), ("DOWNPOUR", dict(communication_window=3)),
     ("AEASGD", dict(communication_window=4, rho=1.0, learning_rate=0.1)),
+    ("EASGD", dict(communication_window=4, rho=1.0, learning_rate=0.1)),
     ("EAMSGD", dict(communication_window=4, rho=0.1, learning_rate=1.0, momentum=0.5)),
     ("DynSGD", dict(communication_window=3)), ("Experimental", dict(communication_window=3)),
 ])
@@ -315,6 +316,55 @@ def test_exchange_fused_into_backward_matches_flat_kernels(name, kw):
 
 def _needs_gpus(n):
     return pytest.mark.skipif(torch.cuda.device_count() < n, reason=f"needs {n} GPUs")
+
+
+def _easgd_pair(num_workers):
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.trainers import EASGD
+
+    torch.manual_seed(0)
+    n, B, tau = 32 * 64, 64, 4
+    ds = Dataset({"features": torch.rand(n, 64), "label": torch.randint(0, 10, (n,)).to(torch.int32)})
+    outs = {}
+    for backend in ("thread", "fabric"):
+        t = EASGD(_mlp(0), {"class_name": "sgd", "config": {"lr": 0.05}}, "categorical_crossentropy",
+                  num_workers=num_workers, batch_size=B, communication_window=tau, rho=1.0, learning_rate=0.3)
+        t.backend = backend
+        outs[backend] = (t.train(ds).get_flat_weights().cpu(), t.num_updates(), t.get_history())
+    return outs, (n // B) // num_workers // tau
+
+
+def test_fabric_sync_easgd_matches_thread_oracle_single_worker():
+    """Device-side rendezvous + read / add kernels against workers.EASGDWorker (one worker: deterministic)."""
+    outs, rounds = _easgd_pair(1)
+    rel = float((outs["thread"][0] - outs["fabric"][0]).norm() / outs["thread"][0].norm())
+    assert rel < 0.02, rel
+    assert outs["fabric"][1] == outs["thread"][1] == 1 + rounds
+
+
+@_needs_gpus(2)
+def test_fabric_sync_easgd_two_ranks_in_lock_step():
+    """Two ranks meet on the barrier word in GPU 0's control block every window; lock step makes the run
+    deterministic up to the order of the two red.adds, so it tracks the thread backend closely."""
+    outs, rounds = _easgd_pair(2)
+    rel = float((outs["thread"][0] - outs["fabric"][0]).norm() / outs["thread"][0].norm())
+    assert rel < 0.02, rel
+    assert outs["fabric"][1] == outs["thread"][1] == 1 + 2 * rounds
+    assert {r["worker_id"] for r in outs["fabric"][2]} == {0, 1}
+
+
+def test_average_replicas_in_place():
+    from distkeras_b200 import _native as N
+    from distkeras_b200.parallel.runtime import _average_replicas
+
+    torch.manual_seed(0)
+    ndev = torch.cuda.device_count()
+    W = 2 if ndev < 2 else min(ndev, 8)
+    flats = [torch.randn(100003, device=f"cuda:{i % ndev}") for i in range(W)]
+    want = torch.stack([f.cpu() for f in flats]).mean(0)
+    _average_replicas(flats, N.lib())
+    for f in flats:
+        assert torch.allclose(f.cpu(), want, atol=1e-6)
 
 
 @_needs_gpus(2)

@@ -47,8 +47,18 @@ def main():
             "exchange(atom.v4)": lambda: lib.dk_ps_exchange(c, w.data_ptr(), w1.data_ptr(), wb.data_ptr(), n, 1e-6, None,
                                                             ctrl, rank, 0, None, st),
             "elastic(ld+red)": lambda: lib.dk_ps_elastic(c, w.data_ptr(), wb.data_ptr(), n, 1e-6, ctrl, rank, 0, st),
+            "strict(lock+commit+pull)": lambda: strict_exchange(),
         }
-        writer_sets = sorted({1, max(1, (world - 1) // 2), max(1, world - 1)}) if world > 1 else [1]
+        ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+        def strict_exchange():
+            # the reference's mutex semantics: whole commit + pull sequences are serialised by the ticket lock
+            lib.dk_ps_lock_acquire(ctrl, ticket.data_ptr(), st)
+            lib.dk_ps_commit(c, w.data_ptr(), w1.data_ptr(), n, 1e-6, None, ctrl, rank, 0, st)
+            lib.dk_ps_pull(c, w.data_ptr(), w1.data_ptr(), wb.data_ptr(), n, ctrl, None, st)
+            return lib.dk_ps_lock_release(ctrl, ticket.data_ptr(), st)
+
+        writer_sets = sorted({v for v in (1, 2, 4, world - 1) if 1 <= v <= world - 1}) if world > 1 else [1]
         for name, op in ops.items():
             for nw in writer_sets:
                 active = (world == 1) or (1 <= rank <= nw)
