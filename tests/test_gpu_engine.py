@@ -399,15 +399,17 @@ def test_spawned_multi_gpu_fabric(dedicated):
     y = torch.randint(0, 10, (n,), generator=g)
     x = (proto[y] + torch.randint(0, 56, (n, 64), generator=g)).clamp(0, 255).to(torch.uint8)
     ds = Dataset({"features": x, "label": y.to(torch.int32)})
-    workers = 1 if dedicated else 2
+    ndev = min(torch.cuda.device_count(), 8)
+    workers = max(1, ndev - 1) if dedicated else ndev     # every GPU of the box takes part
     t = ADAG(_mlp(0), {"class_name": "adam", "config": {"lr": 0.003}}, "categorical_crossentropy",
              num_workers=workers, batch_size=B, communication_window=4)
     t.backend, t.dedicated_ps = "fabric", dedicated
     model = t.train(ds)
     h = t.get_history()
     assert {r["worker_id"] for r in h} == set(range(workers))
-    assert len(h) == n // B
-    assert t.num_updates() == 1 + (n // B) // 4
+    per_worker = (n // workers) // B                     # full mini-batches of one worker's shard
+    assert len(h) == workers * per_worker
+    assert t.num_updates() == 1 + workers * (per_worker // 4)
     model.compile("categorical_crossentropy")
     assert model.evaluate(x.float() / 255.0, y)[1] > 0.8
 

@@ -243,6 +243,7 @@ def test_label_index_transformer_runs_the_kernel_and_matches_the_cpu_rule(N):
     torch.manual_seed(10)
     p = torch.softmax(torch.randn(1000, 7) * 3, 1)
     p[:50] = 0.0                      # no positive entry: default index
+    p[50:100] = 0.01
     p[50:100, 3] = 0.6                # two entries over the threshold: the first wins
     p[50:100, 5] = 0.9
     t = LabelIndexTransformer(7, default_index=2, activation_threshold=0.55)
