@@ -147,6 +147,69 @@ def auto_steps_per_graph(tau: int, batch: int) -> int:
     return max(1, min(64, -(-8192 // (tau * batch)))) * tau
 
 
+def nccl_baseline_arm(args) -> None:
+    """Same model / trainer / batch / window through ``backend="nccl"`` (distkeras_b200/parallel/nccl_baseline.py):
+    cuBLAS autograd replicas, one bulk-synchronous all-reduce per window, inputs from pinned host memory every step.
+    Timed like the reference arm: steady state from the per-step history timestamps of the slowest rank."""
+    import torch
+
+    from distkeras_b200 import trainers
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.models import ZOO
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count()
+    torch.cuda.set_device(local)
+    B = args.batch or DEFAULT_BATCH[args.model]
+    tau = args.window or DEFAULT_WINDOW[args.algo]
+    K, W = max(1, int(args.steps)), max(3, int(args.warmup))
+    steps = W + max(K, 400)
+    in_shape = IN_SHAPE[args.model]
+    model = ZOO[args.model](seed=0)
+    model.build()
+    classes = model.output_shape[-1]
+    g = torch.Generator().manual_seed(1234 + rank)
+    if args.model == "higgs_mlp":
+        x = torch.randn(steps * B, *in_shape, generator=g)
+    else:
+        x = torch.randint(0, 256, (steps * B,) + tuple(in_shape), dtype=torch.uint8, generator=g)
+    y = torch.randint(0, classes, (steps * B,), generator=g).to(torch.int32)
+    TrainerCls = {"adag": trainers.ADAG, "downpour": trainers.DOWNPOUR, "aeasgd": trainers.AEASGD,
+                  "dynsgd": trainers.DynSGD, "eamsgd": trainers.EAMSGD, "experimental": trainers.Experimental}[args.algo]
+    kw = dict(num_workers=world, batch_size=B, communication_window=tau)
+    if args.algo in ("aeasgd", "eamsgd"):
+        kw.update(rho=0.1, learning_rate=0.1)
+    t = TrainerCls(model, args.optimizer, "categorical_crossentropy", **kw)
+    t.backend = "nccl"
+    t.data_is_local_shard = True
+    sampler = ClockSampler(world)
+    if rank == 0:
+        sampler.start()
+        sampler.mark_start()
+    t.train(Dataset({"features": x, "label": y}))
+    if rank != 0:
+        return
+    sampler.mark_end()
+    clocks = sampler.stop()
+    per_worker = {}
+    for rec in t.get_history():
+        per_worker.setdefault(rec["worker_id"], []).append(rec["timestamp"])
+    timed = steps - W - 1
+    ms = max((ts[-1] - ts[W]) / timed for ts in per_worker.values()) * 1e3
+    row_bytes = int(x[0].numel() * x.element_size() + 4)
+    value = world * B / (ms * 1e-3)
+    print(json.dumps({
+        "metric": f"{args.model} {args.algo.upper()} training throughput (samples/s, whole job)", "impl": "nccl-baseline",
+        "value": value, "unit": "samples/s", "n_gpus": world, "steps": timed, "warmup": W, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (tf32 off) autograd", "data": "synthetic",
+        "config": {"model": args.model, "trainer": TrainerCls.__name__, "batch_per_worker": B, "global_batch": world * B,
+                   "communication_window": tau, "worker_optimizer": args.optimizer,
+                   "parallelism": f"bulk-synchronous all-reduce every window, dp{world}"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": world * B * row_bytes, "d2h_bytes_per_step": world * 8},
+        "gpu_launches": 0, "clocks": clocks,
+        "note": "library kernels only (cuBLAS via autograd, NCCL all-reduce); host wall clock between history records"}))
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,10 +228,15 @@ def main() -> None:
     ap.add_argument("--no-fuse-comm", action="store_true",
                     help="A/B: window-boundary exchange as separate kernels instead of inside the backward-update kernel")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--backend", default="fabric", choices=["fabric", "nccl"],
+                    help="nccl = the library-only baseline trainer (autograd replicas + all-reduce), e2e only")
     args = ap.parse_args()
 
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.backend == "nccl":
+        nccl_baseline_arm(args)
         return
 
     import torch

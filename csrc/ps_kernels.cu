@@ -385,9 +385,18 @@ __global__ void ps_lock_acquire_kernel(unsigned* ctrl, unsigned* my_ticket) {
   asm volatile("atom.relaxed.sys.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(ctrl + DK_CTRL_LOCK_NEXT) : "memory");
   *my_ticket = t;
   unsigned serving;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   do {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(serving) : "l"(ctrl + DK_CTRL_LOCK_SERVING) : "memory");
-    if (serving != t) __nanosleep(200);
+    if (serving != t) {
+      __nanosleep(200);
+      // the holder died with the lock (rank loss): after 10 s take it over instead of spinning forever -- the
+      // release below publishes ticket + 1, which also un-sticks everybody queued behind this waiter
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) break;
+    }
   } while (serving != t);
 }
 

@@ -867,9 +867,11 @@ def setup_center_shards(model, rank: int, world: int, local: int, exchange_obj):
     return regions, shards, bounds
 
 
-def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, barrier) -> dict:
+def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, barrier,
+                control: Optional["LocalControl"] = None) -> dict:
     """Body shared by the SPMD (torchrun) and the spawned modes.  ``exchange_obj(obj, src)``
-    broadcasts a picklable object from rank ``src``; ``barrier()`` synchronises all ranks."""
+    broadcasts a picklable object from rank ``src``; ``barrier()`` synchronises all ranks.  ``control`` (spawned
+    mode) is the shard table that lets the survivors take over the partitions of a rank that died."""
     from ..parameter_servers import FabricParameterServer
 
     local = int(os.environ.get("LOCAL_RANK", rank)) % torch.cuda.device_count()
@@ -1001,7 +1003,27 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
                     worker.recover()
                     del worker.history[mark:]
 
-        if static:
+        if control is not None and sync_rows is None and not getattr(trainer, "data_is_local_shard", False):
+            # spawned ranks: claims go through the shard table so the launcher can re-queue a dead rank's work
+            if static:
+                for part in my_parts:
+                    control.claim(part.index, rank)
+                for part in my_parts:
+                    run_task(part)
+                    control.finish(part.index)
+            while True:
+                idx = control.try_claim(rank, n_parts)
+                if idx is not None:
+                    if static:   # only reachable after a peer died: its shard was re-queued
+                        log_event("fabric.requeued_partition", rank=rank, partition=idx)
+                        worker.recover()
+                    run_task(parts[idx])
+                    control.finish(idx)
+                    continue
+                if control.all_done(n_parts):
+                    break
+                time.sleep(0.01)
+        elif static:
             for part in my_parts:
                 run_task(part)
         else:
@@ -1112,14 +1134,174 @@ def _dist_helpers(dist):
     return exchange_obj, barrier
 
 
+class LocalControl:
+    """Control plane of the ranks a driver process spawns (one per GPU): shared-memory flags + files in the job's
+    scratch directory instead of a gloo process group, because it has to keep working when a rank disappears.
+
+    * ``alive[r]``: cleared by the launcher when process ``r`` exits abnormally; ``barrier`` skips dead ranks.
+    * ``claimed[i]`` (rank + 1, 0 = free) / ``done[i]``: the shard table.  A worker claims a data partition under
+      ``lock``; the launcher frees the unfinished claims of a dead rank, and the survivors -- which keep polling the
+      table until every partition is done -- pick them up (the Spark scheduler's task re-submission,
+      ``/root/reference/distkeras/workers.py:286-288`` runs again on the new executor: pull, then train).
+    """
+
+    MAX_PARTS = 8192
+
+    def __init__(self, world: int, scratch: str):
+        import multiprocessing as mp
+
+        ctx = mp.get_context("spawn")
+        self.world, self.scratch = world, scratch
+        self.alive = ctx.Array("b", [1] * world, lock=False)
+        self.gen = ctx.Array("l", [0] * world, lock=False)
+        self.claimed = ctx.Array("i", [0] * self.MAX_PARTS, lock=False)
+        self.done = ctx.Array("b", [0] * self.MAX_PARTS, lock=False)
+        self.lock = ctx.Lock()
+        self._seq = 0
+
+    # -- collectives --------------------------------------------------------------------------------
+    def barrier(self, rank: int, timeout: float = 1800.0) -> None:
+        self.gen[rank] += 1
+        mine = self.gen[rank]
+        t0 = time.time()
+        while any(self.alive[r] and self.gen[r] < mine for r in range(self.world)):
+            if time.time() - t0 > timeout:
+                raise RuntimeError("fabric control barrier timed out")
+            time.sleep(0.002)
+
+    def exchange_obj(self, rank: int, obj, src: int, timeout: float = 600.0):
+        import pickle
+
+        self._seq += 1
+        path = os.path.join(self.scratch, f"xchg_{self._seq}_{src}.pkl")
+        if rank == src:
+            with open(path + ".tmp", "wb") as f:
+                pickle.dump(obj, f)
+            os.replace(path + ".tmp", path)
+            return obj
+        t0 = time.time()
+        while not os.path.exists(path):
+            if not self.alive[src]:
+                raise RuntimeError(f"rank {src} died before publishing object {self._seq}")
+            if time.time() - t0 > timeout:
+                raise RuntimeError("fabric control exchange timed out")
+            time.sleep(0.002)
+        with open(path, "rb") as f:
+            return pickle.load(f)
+
+    # -- shard table --------------------------------------------------------------------------------
+    def claim(self, index: int, rank: int) -> None:
+        self.claimed[index] = rank + 1
+
+    def try_claim(self, rank: int, n_parts: int) -> Optional[int]:
+        with self.lock:
+            for i in range(n_parts):
+                if not self.done[i] and self.claimed[i] == 0:
+                    self.claimed[i] = rank + 1
+                    return i
+        return None
+
+    def finish(self, index: int) -> None:
+        self.done[index] = 1
+
+    def all_done(self, n_parts: int) -> bool:
+        return all(self.done[i] for i in range(n_parts))
+
+    def release_claims_of(self, rank: int) -> List[int]:
+        """Launcher side: free the unfinished partitions of a dead rank; returns their indices."""
+        freed = []
+        with self.lock:
+            for i in range(self.MAX_PARTS):
+                if self.claimed[i] == rank + 1 and not self.done[i]:
+                    self.claimed[i] = 0
+                    freed.append(i)
+        return freed
+
+
+def _spawn_entry_local(rank: int, world: int, control: LocalControl, payload_path: str, scratch: str) -> None:
+    """Body of a rank spawned by the driver-style launcher (fabric entry): no process group at all."""
+    os.environ.update({"RANK": str(rank), "LOCAL_RANK": str(rank), "WORLD_SIZE": str(world)})
+    payload = torch.load(payload_path, weights_only=False)
+    trainer, dataset = payload["trainer"], payload["dataset"]
+    res = _rank_train(trainer, dataset, rank, world, lambda obj, src: control.exchange_obj(rank, obj, src),
+                      lambda: control.barrier(rank), control=control)
+    torch.save(res, os.path.join(scratch, f"result_{rank}.pt.tmp"))
+    os.replace(os.path.join(scratch, f"result_{rank}.pt.tmp"), os.path.join(scratch, f"result_{rank}.pt"))
+    control.barrier(rank)
+
+
+def _launch_local(trainer, dataset: Dataset, world: int):
+    """Spawn ``world`` ranks, watch them, survive the loss of worker ranks when the trainer asks for it
+    (``tolerate_worker_failures``): the dead rank's unfinished partitions go back to the shard table, the
+    survivors retrain them from the current center.  Losing rank 0 (it owns the center) ends the job, as losing
+    the Spark driver does in the reference."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    tmp = tempfile.mkdtemp(prefix="dk_fabric_")
+    payload_path = os.path.join(tmp, "payload.pt")
+    ps_obj, trainer.parameter_server = trainer.parameter_server, None
+    torch.save({"trainer": trainer, "dataset": dataset, "entry": "fabric"}, payload_path)
+    trainer.parameter_server = ps_obj
+    control = LocalControl(world, tmp)
+    procs = [ctx.Process(target=_spawn_entry_local, args=(r, world, control, payload_path, tmp), daemon=False)
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    tolerate = bool(getattr(trainer, "tolerate_worker_failures", False))
+    lost: List[dict] = []
+    fatal = None
+    try:
+        while any(p.exitcode is None for p in procs):
+            for r, p in enumerate(procs):
+                if p.exitcode is not None and p.exitcode != 0 and control.alive[r]:
+                    control.alive[r] = 0
+                    freed = control.release_claims_of(r)
+                    lost.append({"rank": r, "exitcode": p.exitcode, "requeued_partitions": freed})
+                    log_event("fabric.rank_lost", rank=r, exitcode=p.exitcode, requeued=freed)
+                    if r == 0 or not tolerate:
+                        fatal = RuntimeError(f"fabric rank {r} exited with code {p.exitcode}"
+                                             + ("" if r == 0 else " (set tolerate_worker_failures to survive "
+                                                                  "the loss of worker ranks)"))
+                        break
+            if fatal is not None:
+                break
+            time.sleep(0.02)
+    finally:
+        if fatal is not None:
+            for p in procs:
+                if p.exitcode is None:
+                    p.terminate()
+        for p in procs:
+            p.join(timeout=30)
+    if fatal is not None:
+        raise fatal
+    res = torch.load(os.path.join(tmp, "result_0.pt"), weights_only=False)
+    history, all_stats = [], []
+    for r in range(world):
+        path = os.path.join(tmp, f"result_{r}.pt")
+        if os.path.exists(path):
+            rr = res if r == 0 else torch.load(path, weights_only=False)
+            history += rr["history"]
+            all_stats.append(rr["stats"])
+        else:
+            all_stats.append({"lost": True})
+    res["history"], res["all_stats"], res["lost_ranks"] = history, all_stats, lost
+    import shutil
+
+    shutil.rmtree(tmp, ignore_errors=True)
+    return res
+
+
 def _spawn_entry(rank: int, world: int, port: int, payload_path: str, result_path: str) -> None:
     os.environ.update({"RANK": str(rank), "LOCAL_RANK": str(rank), "WORLD_SIZE": str(world),
                        "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
     payload = torch.load(payload_path, weights_only=False)
     trainer, dataset = payload["trainer"], payload["dataset"]
-    dist = _init_pg("gloo")
+    entry = payload.get("entry", "fabric")
+    dist = _init_pg("cpu:gloo,cuda:nccl" if (entry != "fabric" and torch.cuda.is_available()) else "gloo")
     exchange_obj, barrier = _dist_helpers(dist)
-    res = _rank_train(trainer, dataset, rank, world, exchange_obj, barrier)
+    res = _rank_entry(entry)(trainer, dataset, rank, world, exchange_obj, barrier)
     gathered = [None] * world
     dist.all_gather_object(gathered, {"history": res["history"], "stats": res["stats"]})
     if rank == 0:
@@ -1130,15 +1312,30 @@ def _spawn_entry(rank: int, world: int, port: int, payload_path: str, result_pat
     dist.destroy_process_group()
 
 
-def train_distributed_fabric(trainer, dataset: Dataset):
+def _rank_entry(name: str):
+    if name == "nccl":
+        from .nccl_baseline import rank_train_nccl
+
+        return rank_train_nccl
+    return _rank_train
+
+
+def train_distributed_nccl(trainer, dataset: Dataset):
+    """The library-collectives baseline (``backend="nccl"``): same launcher, ``nccl_baseline.rank_train_nccl``
+    as the per-rank body."""
+    return train_distributed_fabric(trainer, dataset, entry="nccl")
+
+
+def train_distributed_fabric(trainer, dataset: Dataset, entry: str = "fabric"):
     """Run a PS trainer on the NVLink fabric.  Under ``torchrun`` every rank calls this (SPMD);
     from a plain driver process the ranks are spawned here, one per GPU."""
     env = _spmd_env()
+    rank_fn = _rank_entry(entry)
     if env is not None:
         rank, world = env
         dist = _init_pg()
         exchange_obj, barrier = _dist_helpers(dist)
-        res = _rank_train(trainer, dataset, rank, world, exchange_obj, barrier)
+        res = rank_fn(trainer, dataset, rank, world, exchange_obj, barrier)
         gathered = [None] * world
         dist.all_gather_object(gathered, {"history": res["history"], "stats": res["stats"]})
         history = [h for g in gathered for h in g["history"]]
@@ -1147,20 +1344,31 @@ def train_distributed_fabric(trainer, dataset: Dataset):
         trainer.fabric_stats = [g["stats"] for g in gathered]
         trainer.fabric_num_updates, trainer.staleness_histogram = box[1], box[2]
         return deserialize_keras_model(box[0]), history
-    world = min(max(1, trainer.num_workers + (1 if getattr(trainer, "dedicated_ps", False) else 0)),
-                torch.cuda.device_count())
+    if entry == "nccl":   # one rank per worker; on a CPU-only host the collectives run over gloo
+        world = min(max(1, trainer.num_workers), torch.cuda.device_count() or trainer.num_workers)
+    else:
+        # one rank per GPU; ranks_per_gpu > 1 packs several ranks on a device (CUDA IPC works within a device:
+        # how the multi-rank logic is exercised on a one-GPU box)
+        world = min(max(1, trainer.num_workers + (1 if getattr(trainer, "dedicated_ps", False) else 0)),
+                    torch.cuda.device_count() * max(1, int(getattr(trainer, "ranks_per_gpu", 1))))
     if world == 1:
         # single GPU: PS and worker share the device, no extra process needed
-        res = _rank_train(trainer, dataset, 0, 1, lambda obj, src: obj, lambda: None)
+        res = rank_fn(trainer, dataset, 0, 1, lambda obj, src: obj, lambda: None)
         trainer.fabric_stats = [res["stats"]]
         trainer.fabric_num_updates, trainer.staleness_histogram = res["num_updates"], res["staleness_hist"]
+        return deserialize_keras_model(res["model"]), res["history"]
+    if entry == "fabric":
+        res = _launch_local(trainer, dataset, world)
+        trainer.fabric_stats = res.get("all_stats")
+        trainer.fabric_num_updates, trainer.staleness_histogram = res["num_updates"], res["staleness_hist"]
+        trainer.lost_ranks = res.get("lost_ranks", [])
         return deserialize_keras_model(res["model"]), res["history"]
     import torch.multiprocessing as mp
 
     tmp = tempfile.mkdtemp(prefix="dk_fabric_")
     payload_path, result_path = os.path.join(tmp, "payload.pt"), os.path.join(tmp, "result.pt")
     ps_obj, trainer.parameter_server = trainer.parameter_server, None
-    torch.save({"trainer": trainer, "dataset": dataset}, payload_path)
+    torch.save({"trainer": trainer, "dataset": dataset, "entry": entry}, payload_path)
     trainer.parameter_server = ps_obj
     mp.spawn(_spawn_entry, args=(world, _free_port(), payload_path, result_path), nprocs=world, join=True)
     res = torch.load(result_path, weights_only=False)
@@ -1342,12 +1550,14 @@ def _average_replicas(flats: List[torch.Tensor], lib) -> None:
         return
     first = flats[0].device
     with torch.cuda.device(first):
-        stack = torch.stack([f.to(first) for f in flats])
+        stack = torch.empty(W, (n + 3) // 4 * 4, dtype=torch.float32, device=first)   # rows stay 16-byte aligned
+        for i, f in enumerate(flats):
+            stack[i, :n].copy_(f)
         arr = (C.c_void_p * W)(*[stack[i].data_ptr() for i in range(W)])
         N.check(lib.dk_ps_average(arr, W, 0, n, C.c_void_p(N.current_stream())), "dk_ps_average")
         torch.cuda.synchronize(first)
         for f in flats:
-            f.copy_(stack[0])
+            f.copy_(stack[0, :n])
         torch.cuda.synchronize(first)
 
 

@@ -7,7 +7,7 @@ accessors: ``Trainer``, ``SingleTrainer``, ``AveragingTrainer``, ``EnsembleTrain
 
 Where the reference fans work out with ``rdd.mapPartitionsWithIndex(worker.train).collect()`` on
 Spark and hosts the parameter server in a driver thread behind a TCP socket
-(``trainers.py:488-532``), this module has three execution backends selected by ``backend=``:
+(``trainers.py:488-532``), this module has four execution backends selected by ``backend=``:
 
 ``"fabric"``  (default when CUDA is present) one process per GPU; the center variable lives in GPU
               0's HBM, workers run CUDA-graph windows of native kernels and commit / pull with
@@ -15,6 +15,9 @@ Spark and hosts the parameter server in a driver thread behind a TCP socket
 ``"thread"``  (default on CPU) worker threads + in-process parameter server: the semantic oracle.
 ``"socket"``  worker threads + the TCP parameter server: the reference's wire path, kept for
               multi-host control and parity tests.
+``"nccl"``    the library-only baseline: autograd replicas (cuBLAS / cuDNN) + bulk-synchronous
+              ``torch.distributed`` all-reduces every window (``parallel/nccl_baseline.py``); the
+              number the fabric backend is measured against.
 """
 from __future__ import annotations
 
@@ -407,6 +410,15 @@ class DistributedTrainer(Trainer):
             self.record_training_end()
             self.worker_failures = [f for st in (getattr(self, "fabric_stats", None) or [])
                                     for f in (st or {}).get("failures", [])]
+            self._save_final_checkpoint(model, self.num_updates())
+            return model
+        if backend == "nccl":
+            # library-only baseline: autograd replicas + torch.distributed collectives (parallel/nccl_baseline.py)
+            from .parallel.runtime import train_distributed_nccl
+
+            self.record_training_start()
+            model, self.history = train_distributed_nccl(self, dataframe)
+            self.record_training_end()
             self._save_final_checkpoint(model, self.num_updates())
             return model
         if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1 and backend in ("socket", "spmd"):

@@ -34,7 +34,15 @@ _FIRED: set = set()
 
 def fault_injection_point(worker_id: int, iteration: int) -> None:
     """Test hook: ``DK_FAULT=<worker>:<iteration>`` makes that worker fail there.  Like
-    a real crash the fault fires ONCE per process and spec, so a retried task gets past it."""
+    a real crash the fault fires ONCE per process and spec, so a retried task gets past it.
+    ``DK_FAULT_KILL=<worker>:<iteration>`` ends the whole process there instead (``os._exit``): the rank-loss case
+    the fabric launcher survives by re-queueing the dead rank's shards."""
+    kill = os.environ.get("DK_FAULT_KILL")
+    if kill:
+        # process-level loss (a rank that disappears: OOM kill, node failure): no exception, no cleanup
+        w, it = kill.split(":")
+        if int(w) == int(worker_id) and int(it) == int(iteration):
+            os._exit(17)
     spec = os.environ.get("DK_FAULT")
     if not spec or spec in _FIRED:
         return

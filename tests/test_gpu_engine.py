@@ -414,6 +414,36 @@ def test_spawned_multi_gpu_fabric(dedicated):
     assert model.evaluate(x.float() / 255.0, y)[1] > 0.8
 
 
+def test_losing_a_worker_rank_requeues_its_partition(monkeypatch):
+    """Process-level loss: rank 1 disappears (os._exit) at the start of its second epoch.  The launcher frees its
+    partition in the shard table, rank 0 re-pulls and retrains it; the commits rank 1 made before dying stay in the
+    center.  Two ranks share the GPU when the box has only one."""
+    from distkeras_b200.data import Dataset
+    from distkeras_b200.trainers import ADAG
+
+    g = torch.Generator().manual_seed(0)
+    n, B = 8192, 128
+    proto = torch.randint(0, 200, (10, 64), generator=g)
+    y = torch.randint(0, 10, (n,), generator=g)
+    x = (proto[y] + torch.randint(0, 56, (n, 64), generator=g)).clamp(0, 255).to(torch.uint8)
+    ds = Dataset({"features": x, "label": y.to(torch.int32)})
+    per = n // 2 // B                                         # 32 mini-batches per partition and epoch
+    monkeypatch.setenv("DK_FAULT_KILL", f"1:{per + 8}")
+    t = ADAG(_mlp(0), {"class_name": "adam", "config": {"lr": 0.003}}, "categorical_crossentropy", num_workers=2,
+             batch_size=B, num_epoch=2, communication_window=4)
+    t.backend, t.ranks_per_gpu = "fabric", 2
+    with pytest.raises(RuntimeError, match="rank 1 exited"):
+        t.train(ds)                                           # default: a lost rank ends the job
+    t.tolerate_worker_failures = True
+    model = t.train(ds)
+    assert [l["rank"] for l in t.lost_ranks] == [1] and t.lost_ranks[0]["requeued_partitions"] == [1]
+    h = t.get_history()
+    assert {r["worker_id"] for r in h} == {0} and len(h) == 2 * (2 * per)   # own shard + the re-queued one, 2 epochs each
+    assert t.num_updates() == 1 + (2 * per) // 4 + per // 4 + (2 * per) // 4
+    model.compile("categorical_crossentropy")
+    assert model.evaluate(x.float() / 255.0, y)[1] > 0.8
+
+
 def test_smoke_entry():
     import __graft_entry__
 

@@ -373,3 +373,20 @@ def test_single_worker_center_matches_hand_replay(rule, cls, kw, hp):
     t.backend = "thread"
     got = t.train(ds).get_flat_weights()
     assert torch.allclose(got, want, atol=2e-5), (rule, float((got - want).abs().max()))
+
+
+@pytest.mark.parametrize("cls,kw", [(ADAG, dict(communication_window=4)),
+                                    (AEASGD, dict(communication_window=4, rho=1.0, learning_rate=0.1)),
+                                    (EAMSGD, dict(communication_window=4, rho=0.1, learning_rate=1.0, momentum=0.5))])
+def test_library_collectives_baseline_backend(cls, kw):
+    """backend="nccl" (gloo on a CPU host): two spawned ranks, bulk-synchronous all-reduce every window."""
+    ds = tiny_data(1024)
+    t = cls(tiny_model(0), {"class_name": "adam", "config": {"lr": 0.02}}, "categorical_crossentropy", num_workers=2,
+            batch_size=16, num_epoch=2, **kw)
+    t.backend = "nccl"
+    model = t.train(ds)
+    h = t.get_history()
+    assert len(h) == 2 * 2 * (512 // 16) and {r["worker_id"] for r in h} == {0, 1}
+    assert t.num_updates() == 1 + 2 * (2 * (512 // 16) // 4)
+    model.compile("categorical_crossentropy")
+    assert model.evaluate(ds["features"], ds["label"])[1] > 0.6

@@ -128,3 +128,41 @@ def test_spmd_gloo_two_processes(tmp_path):
     assert len(sums) == 1  # both ranks return the same final model
     assert all("HIST 32" in l for l in lines)
     assert all(float(l.split("ACC")[1].split()[0]) > 0.5 for l in lines)
+
+
+def test_local_control_shard_table_and_barrier(tmp_path):
+    """Control plane of the spawned fabric ranks: a dead rank's unfinished claims go back to the table and the
+    barrier stops waiting for it (the launcher flips ``alive``)."""
+    import threading
+
+    from distkeras_b200.parallel.runtime import LocalControl
+
+    c = LocalControl(3, str(tmp_path))
+    c.claim(0, 0)
+    c.claim(1, 1)
+    assert c.try_claim(2, 4) == 2 and c.try_claim(0, 4) == 3 and c.try_claim(0, 4) is None
+    c.finish(0)
+    c.finish(2)
+    assert not c.all_done(4)
+    c.alive[1] = 0
+    assert c.release_claims_of(1) == [1]                     # rank 1 died holding partition 1
+    assert c.try_claim(0, 4) == 1
+    for i in (1, 3):
+        c.finish(i)
+    assert c.all_done(4)
+    # barrier: ranks 0 and 2 meet, dead rank 1 is skipped
+    t = threading.Thread(target=c.barrier, args=(2,))
+    t.start()
+    c.barrier(0, timeout=10)
+    t.join(timeout=10)
+    assert not t.is_alive()
+    # object exchange through the scratch directory
+    out = {}
+    c2 = LocalControl(2, str(tmp_path))
+    th = threading.Thread(target=lambda: out.setdefault("v", c2.exchange_obj(1, None, 0, timeout=10)))
+    th.start()
+    c2._seq = 0
+    c3 = LocalControl(2, str(tmp_path))
+    c3.exchange_obj(0, {"a": 1}, 0)
+    th.join(timeout=10)
+    assert out["v"] == {"a": 1}

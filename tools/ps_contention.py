@@ -45,7 +45,7 @@ def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0)) % torch.cuda.device_count()
     torch.cuda.set_device(local)
-    d = runtime._init_pg()
+    d = runtime._init_pg("gloo")   # control plane only (several ranks may share a GPU: NCCL would refuse that)
     exchange_obj, barrier = runtime._dist_helpers(d)
     lib = N.lib()
     n, K = a.numel, a.rounds
@@ -237,7 +237,7 @@ def main():
             os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
             with open(a.out, "w") as f:
                 f.write(text + "\n")
-    flag = torch.tensor([0 if ok else 1], device="cuda")
+    flag = torch.tensor([0 if ok else 1])
     dist.all_reduce(flag, op=dist.ReduceOp.MAX)
     barrier()
     dist.destroy_process_group()
