@@ -33,6 +33,12 @@ NOTEBOOKS = [
     ("workflow.ipynb", {"synthetic_higgs(200000)": "synthetic_higgs(4096)", "num_epoch=2": "num_epoch=1"}),
     ("data_preparation.ipynb", {"synthetic_cifar10(2000": "synthetic_cifar10(200", "reshape(2000, -1)": "reshape(200, -1)"}),
     ("streaming_inference.ipynb", {"rows=1000": "rows=200"}),
+    ("mnist_preprocessing.ipynb", {"synthetic_mnist(4000": "synthetic_mnist(300"}),
+    ("mnist_analysis.ipynb", {"synthetic_mnist(60000": "synthetic_mnist(2048", "batch_size=4,": "batch_size=16,"}),
+    ("example_0_data_preprocessing.ipynb", {"'--rows', '20000'": "'--rows', '1000'"}),
+    ("example_1_analysis.ipynb", {"synthetic_higgs(200000)": "synthetic_higgs(6000)"}),
+    ("cifar-10-preprocessing.ipynb", {"synthetic_cifar10(1000": "synthetic_cifar10(100", "synthetic_cifar10(500": "synthetic_cifar10(50"}),
+    ("distributed_numpy_parsing.ipynb", {"range(8)": "range(4)"}),
 ]
 
 
