@@ -177,9 +177,6 @@ constexpr int kBwdStagesBytes = kBwdStages * (kBwdBlockM * 128 + kBwdBN * 128);
 constexpr int kBwdTileBytes = 2 * kBwdBlockM * 128;  // one fp32 state array of a 128 x 64 tile
 constexpr int kBwdSmemUse = kBwdStagesBytes + 2048 + 4 * kBwdTileBytes + kBwdBlockM * 128 + 256;
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 // Epilogue of one (quarter, half) = 32 rows x 32 columns slice of the accumulator tile, executed by one warp
 // with lane = row (the TMEM-native mapping).  The parameter state of the slice is already in shared memory
@@ -209,6 +206,8 @@ __device__ __forceinline__ void bwd_epilogue(const BwdUpdateDev& p, const BwdLay
       st_shared_v4(gslot + lane * 128 + ((c4 ^ (lane & 7)) << 4), r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
     __syncwarp();
   }
+  unsigned long long* const tr = (blockIdx.x == 0 && quarter == 2 && half == 0 && lane == 0) ? p.trace : nullptr;
+  trace_stamp(tr, 8);
   if (ly.maps != nullptr) {
     // =============================== TMA-fed path (k_in % 4 == 0) ===============================
     const uint32_t rowoff = (quarter * 32 + lane) * 128;          // this lane's row inside a half-tile
@@ -245,6 +244,7 @@ __device__ __forceinline__ void bwd_epilogue(const BwdUpdateDev& p, const BwdLay
         // 8 bf16 = 16-byte chunk (4 half + jj) of this row of the shadow tile
         st_shared_v4(wb_tile + rowoff + (((4 * half + jj) ^ (lane & 7)) << 4), packed[0], packed[1], packed[2], packed[3]);
       }
+      trace_stamp(tr, 9);
       if (comm) {
         // ---- window boundary: push the window's displacement, adopt the center ----
         __syncwarp();
@@ -313,14 +313,17 @@ __device__ __forceinline__ void bwd_epilogue(const BwdUpdateDev& p, const BwdLay
         if constexpr (kS1) tma_store_2d_addr(&ly.maps->st[kStS1], tS1 + sub_off, nbase, mbase);
         if (p.comm_mode == DK_COMM_EXCHANGE) tma_store_2d_addr(&ly.maps->st[kStW1], tW1 + sub_off, nbase, mbase);
       }
+      trace_stamp(tr, 10);
     }
     // the two halves of a quarter fill one [32 x 128 B] box of the bf16 shadow tile: pair barrier, one store
     named_bar_sync(1 + quarter, 64);
     if (half == 0 && lane == 0 && n0 < ly.k_in) tma_store_2d_addr(&ly.maps->st[kStWb], wb_tile + quarter * 4096, n0, mbase);
+    trace_stamp(tr, 11);
     if (lane == 0) {
       tma_store_commit();
       tma_store_wait_read<0>();
     }
+    trace_stamp(tr, 12);
   } else if (slice_live) {
     // ====== element-wise path (k_in % 4 != 0, e.g. the 30-feature Higgs input layer): lane = column group ======
     const int sub = lane >> 3, c4 = lane & 7;

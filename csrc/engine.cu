@@ -139,6 +139,8 @@ int run_op(Engine* e, Op& op, void* main_stream) {
                                   (a[4] & DK_GEMM_SHORT_A) ? dk_gemm_a_box_rows((int)a[0]) : 128);
         if (r != 0) return r;
       }
+      if (op.ep.head_w != nullptr && op.ep.head_label_slot >= 0)
+        op.ep.head_labels = reinterpret_cast<const int*>(e->slots[op.ep.head_label_slot]);
       return dk_gemm_tn_launch2(&op.ta, &op.tb, op.has_td ? &op.td : nullptr, op.has_tm ? &op.tm : nullptr, &op.ep,
                                 (int)a[0], (int)a[1], (int)a[2], (int)a[3], (int)a[4], (int)a[5], st);
     case DK_OP_XENT:

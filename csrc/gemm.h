@@ -33,6 +33,29 @@ typedef struct DkGemmEpilogue {
   int tma_store;         // set by the launcher: output goes through smem staging + TMA store
   int tma_mask;          // set by the launcher: mask tile is fetched with TMA
   unsigned long long* trace;  // diagnostics: 8 clock stamps of CTA (0, 0) (nullptr = off)
+  // ---- classifier head fused into the GEMM that produces its input (bn = 16, one M tile; head_w != nullptr) ----
+  // The GEMM computes H = act(A B^T + bias) [M, N]; the head is logits = H W3^T + b3 (C <= 16 classes), softmax
+  // cross-entropy against integer labels, dZ = (p - y) / M and dH = alpha (dZ W3) * (H > 0).  Every CTA adds its
+  // 16-column slice's contribution to the logits (fp32 red.add into head_acc [128, 16]), the CTAs of the grid meet on
+  // head_sync[0] (all co-resident: the grid is <= 32 CTAs), then every CTA finishes its own slice of dH; CTA 0 also
+  // writes dZ and the loss / accuracy record.  Nothing is reset on the way out: the arrival counter is monotonic and
+  // the logits scratch is double-buffered by launch parity (CTA 0 clears the other half at entry).
+  const dk_bf16* head_w;   // W3 (bf16 shadow) [C, N], leading dimension head_ldw
+  int head_ldw;
+  const float* head_bias;  // b3 [C] or nullptr
+  int head_c;
+  const int* head_labels;  // [M] class indices
+  int head_label_slot;     // engine: >= 0 -> head_labels is read from this slot when the list runs
+  float* head_acc;         // [2][128, 16] fp32 (double-buffered by launch parity), zero at creation
+  unsigned* head_sync;     // [2] u32: monotonic arrival counter, launch counter; zero at creation
+  dk_bf16* head_dz;        // [M, head_ldz] bf16 (columns >= C zero)
+  int head_ldz;
+  dk_bf16* head_dh;        // [M, head_lddh] bf16
+  int head_lddh;
+  float head_alpha;        // dropout keep-scale of the layer that produced H (1 if none)
+  float* head_hist;        // loss / accuracy record [hist_slots, 2]
+  const int* head_step;
+  int head_hist_slots;
 } DkGemmEpilogue;
 
 #ifdef __cplusplus

@@ -245,6 +245,221 @@ __device__ __forceinline__ void gemm_epilogue(const CUtensorMap& tmap_d, const C
   }
 }
 
+// Epilogue of the bn = 16 forward GEMM with the classifier head fused in (see DkGemmEpilogue::head_*): the
+// activation slice [128 x 16] of this CTA is written out, its contribution to the logits is red.add'ed to a
+// [128 x 16] fp32 scratch, the (<= 32, co-resident) CTAs of the grid meet on a counter, and every CTA then computes
+// softmax / dZ for its rows and its own 16 columns of dH = alpha (dZ W3) * (H > 0).  Replaces the stand-alone head
+// kernel (one launch + one dependent-kernel latency per step in the small-batch regime).
+__device__ __forceinline__ void gemm_epilogue_head(const GemmEpilogue& ep, const int M, const int N, const int m0,
+                                                   const int n0, const int warp, const int lane,
+                                                   const uint32_t tmem_base, uint64_t* tmem_full_bar) {
+  // This code runs once per launch: loops over the classes are kept rolled (instruction-cache misses cost more
+  // than the loop overhead) and the per-row class vector lives in shared memory, one conflict-free column per thread.
+  __shared__ __align__(16) float s_w3[16 * 16];  // W3[c][n0 + j] of this CTA's column slice (zero padded)
+  __shared__ float s_g[16][128];                 // [class][epilogue thread]: logits, then dZ
+  __shared__ float s_b3[16];
+  const int quarter = warp & 3;
+  const int tid = (warp - 2) * 32 + lane;        // 0..127 over the four epilogue warps
+  const int m = m0 + quarter * 32 + lane;
+  const bool row_ok = m < M;
+  const int C = ep.head_c;
+  for (int idx = tid; idx < 256; idx += 128) {
+    const int c = idx >> 4, jj = idx & 15;
+    s_w3[idx] = (c < C && n0 + jj < N) ? __bfloat162float(ep.head_w[static_cast<size_t>(c) * ep.head_ldw + n0 + jj]) : 0.f;
+  }
+  if (tid < 16) s_b3[tid] = (ep.head_bias != nullptr && tid < C) ? __ldg(ep.head_bias + tid) : 0.f;
+  unsigned long long* const trw = (blockIdx.x == 0 && warp == 4 && lane == 0) ? ep.trace : nullptr;
+  const int label = row_ok ? __ldg(ep.head_labels + m) : 0;
+  float bias_v[16];
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.bias != nullptr && n0 + 4 * q4 + 4 <= N) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + 4 * q4));
+    bias_v[4 * q4] = b4.x; bias_v[4 * q4 + 1] = b4.y; bias_v[4 * q4 + 2] = b4.z; bias_v[4 * q4 + 3] = b4.w;
+  }
+  // head_sync[0]: arrivals, never reset (launch L of the grid completes it to (L + 1) * target); head_sync[1] = L, the
+  // number of finished launches (written by one thread at the end of each).  The logits scratch is double-buffered
+  // by launch parity: this launch accumulates into acc[L & 1] while CTA 0 clears acc[(L + 1) & 1] -- whose last
+  // readers belonged to launch L - 1 -- so nothing has to be cleaned up on the way out.
+  const unsigned launch = *reinterpret_cast<volatile const unsigned*>(ep.head_sync + 1);
+  float* const acc = ep.head_acc + (launch & 1u) * (128 * 16);
+  if (blockIdx.x == 0) {
+    float4* nxt = reinterpret_cast<float4*>(ep.head_acc + ((launch + 1u) & 1u) * (128 * 16));
+    for (int i4 = tid; i4 < 128 * 16 / 4; i4 += 128) nxt[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  uint32_t drop_salt = 0, drop_thr = 0;
+  float keep_scale = 1.f;
+  if (ep.drop_p > 0.f) {
+    drop_salt = ep.drop_seed + (ep.step != nullptr ? static_cast<uint32_t>(*ep.step) : 0u) * 0x85EBCA77u;
+    drop_thr = static_cast<uint32_t>(ep.drop_p * 256.f + 0.5f);
+    keep_scale = 256.f / (256.f - static_cast<float>(drop_thr));
+  }
+  int slot = ep.head_step != nullptr ? (*ep.head_step - 1) : 0;
+  named_bar_sync(1, 128);
+  mbar_wait(tmem_full_bar, 0);
+  tcgen05_fence_after();
+  float v[16];
+  {
+    uint32_t r[16];
+    tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(r[jj]) + bias_v[jj];
+  }
+  // ---- the producing layer's own epilogue: (bias,) ReLU, inverted dropout (same hash as gemm_epilogue) ----
+  if (ep.act == 1) {
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) v[jj] = fmaxf(v[jj], 0.f);
+  }
+  if (ep.drop_p > 0.f) {
+#pragma unroll
+    for (int jj = 0; jj < 16; jj += 4) {
+      uint32_t h = (static_cast<uint32_t>(m) * static_cast<uint32_t>(N) + static_cast<uint32_t>(n0 + jj)) * 0x9E3779B1u ^ drop_salt;
+      h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) v[jj + t] = (((h >> (8 * t)) & 0xFFu) < drop_thr) ? 0.f : v[jj + t] * keep_scale;
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj) v[jj] = (n0 + jj < N) ? __bfloat162float(__float2bfloat16_rn(v[jj])) : 0.f;  // what the next layer reads
+  if (row_ok) {
+    if (ep.d != nullptr) {
+      __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(ep.d) + static_cast<size_t>(m) * ep.ldd + n0;
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        if (n0 + 8 * h8 + 8 <= N)
+          *reinterpret_cast<uint4*>(drow + 8 * h8) =
+              make_uint4(pack_bf16x2(v[8 * h8], v[8 * h8 + 1]), pack_bf16x2(v[8 * h8 + 2], v[8 * h8 + 3]),
+                         pack_bf16x2(v[8 * h8 + 4], v[8 * h8 + 5]), pack_bf16x2(v[8 * h8 + 6], v[8 * h8 + 7]));
+      }
+    }
+    // ---- this slice's share of the logits: four classes per 16-byte vector reduction ----
+#pragma unroll 1
+    for (int c4 = 0; c4 < C; c4 += 4) {
+      float s4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4* wr = reinterpret_cast<const float4*>(s_w3 + (c4 + u) * 16);   // rows >= C of s_w3 are zero
+        float a = 0.f;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 w4 = wr[q4];
+          a = fmaf(v[4 * q4], w4.x, fmaf(v[4 * q4 + 1], w4.y, fmaf(v[4 * q4 + 2], w4.z, fmaf(v[4 * q4 + 3], w4.w, a))));
+        }
+        s4[u] = a;
+      }
+      asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(acc + m * 16 + c4), "f"(s4[0]),
+                   "f"(s4[1]), "f"(s4[2]), "f"(s4[3])
+                   : "memory");
+    }
+  }
+  // ---- rendezvous of the grid's epilogue warps (warps without live rows only arrive) ----
+  trace_stamp(trw, 8);
+  __syncwarp();
+  const unsigned target = (launch + 1u) * (gridDim.x * 4u);
+  if (lane == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ep.head_sync) : "memory");   // cumulative over the warp's reds
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ep.head_sync) : "memory");
+    } while (static_cast<int>(seen - target) < 0);
+  }
+  __syncwarp();
+  trace_stamp(trw, 9);
+  // ---- softmax cross-entropy of this row, dZ, and this CTA's 16 columns of dH ----
+  float row_loss = 0.f, correct = 0.f;
+  if (row_ok) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      float4 a;
+      asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                   : "l"(acc + m * 16 + 4 * q4)
+                   : "memory");
+      s_g[4 * q4][tid] = a.x; s_g[4 * q4 + 1][tid] = a.y; s_g[4 * q4 + 2][tid] = a.z; s_g[4 * q4 + 3][tid] = a.w;
+    }
+    trace_stamp(trw, 10);
+    float mx = -INFINITY, zl = 0.f;
+    int amax = 0;
+    // modest unrolling: these loops are single-warp dependent chains (latency bound), but full unrolling of
+    // run-once code costs more in instruction-cache misses than it saves
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) {
+      const float z = s_g[c][tid] + s_b3[c];
+      s_g[c][tid] = z;
+      if (z > mx) { mx = z; amax = c; }
+      if (c == label) zl = z;
+    }
+    float se = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) {
+      const float e = __expf(s_g[c][tid] - mx);
+      s_g[c][tid] = e;
+      se += e;
+    }
+    const float lse = __logf(se) + mx, inv_se = __fdividef(1.f, se), inv_b = 1.f / static_cast<float>(M);
+    row_loss = lse - zl;
+    correct = amax == label ? 1.f : 0.f;
+    trace_stamp(trw, 11);
+    // the bf16-rounded gradient is what the weight-gradient GEMM sees: use the same value for dH
+#pragma unroll 4
+    for (int c = 0; c < 16; ++c)
+      s_g[c][tid] = c < C ? __bfloat162float(__float2bfloat16_rn((s_g[c][tid] * inv_se - (c == label ? 1.f : 0.f)) * inv_b)) : 0.f;
+    float d[16];
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) d[jj] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) {
+      const float gc = s_g[c][tid];
+      const float4* wr = reinterpret_cast<const float4*>(s_w3 + c * 16);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 w4 = wr[q4];
+        d[4 * q4] = fmaf(gc, w4.x, d[4 * q4]);
+        d[4 * q4 + 1] = fmaf(gc, w4.y, d[4 * q4 + 1]);
+        d[4 * q4 + 2] = fmaf(gc, w4.z, d[4 * q4 + 2]);
+        d[4 * q4 + 3] = fmaf(gc, w4.w, d[4 * q4 + 3]);
+      }
+    }
+    if (ep.head_dh != nullptr) {
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) d[jj] = (ep.act != 1 || v[jj] > 0.f) ? d[jj] * ep.head_alpha : 0.f;
+      __nv_bfloat16* hrow = ep.head_dh + static_cast<size_t>(m) * ep.head_lddh + n0;
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        if (n0 + 8 * h8 + 8 <= N)
+          *reinterpret_cast<uint4*>(hrow + 8 * h8) =
+              make_uint4(pack_bf16x2(d[8 * h8], d[8 * h8 + 1]), pack_bf16x2(d[8 * h8 + 2], d[8 * h8 + 3]),
+                         pack_bf16x2(d[8 * h8 + 4], d[8 * h8 + 5]), pack_bf16x2(d[8 * h8 + 6], d[8 * h8 + 7]));
+      }
+    }
+    if (blockIdx.x == 0 && ep.head_dz != nullptr) {
+      __nv_bfloat16* zrow = ep.head_dz + static_cast<size_t>(m) * ep.head_ldz;
+#pragma unroll 1
+      for (int h8 = 0; h8 < 2; ++h8) {
+        if (8 * h8 + 8 <= ep.head_ldz)
+          *reinterpret_cast<uint4*>(zrow + 8 * h8) =
+              make_uint4(pack_bf16x2(s_g[8 * h8][tid], s_g[8 * h8 + 1][tid]), pack_bf16x2(s_g[8 * h8 + 2][tid], s_g[8 * h8 + 3][tid]),
+                         pack_bf16x2(s_g[8 * h8 + 4][tid], s_g[8 * h8 + 5][tid]), pack_bf16x2(s_g[8 * h8 + 6][tid], s_g[8 * h8 + 7][tid]));
+      }
+    }
+  }
+  trace_stamp(trw, 12);
+  if (blockIdx.x == 0 && ep.head_hist != nullptr) {
+    const float l = warp_sum(row_loss), cr = warp_sum(correct);
+    if (lane == 0 && m0 + quarter * 32 < M) {
+      if (slot < 0) slot = 0;
+      if (ep.head_hist_slots > 0) slot %= ep.head_hist_slots;
+      const float inv_b = 1.f / static_cast<float>(M);
+      atomicAdd(ep.head_hist + 2 * slot, l * inv_b);
+      atomicAdd(ep.head_hist + 2 * slot + 1, cr * inv_b);
+    }
+  }
+  // ---- one thread publishes the launch count for the next launch (kernel boundary orders it) ----
+  if (blockIdx.x == 0 && warp == 2 && lane == 0) ep.head_sync[1] = launch + 1u;
+  trace_stamp(trw, 13);
+}
+
 // AMN / BMN: the operand is MN-major in global memory, i.e. stored as [K, M] (resp. [K, N])
 // row-major with the M (N) index contiguous.  TMA then loads [64 K-rows x 64 MN-elements] boxes
 // (one 128-byte swizzle row per K index) and the UMMA descriptor walks K in 8-row atoms
@@ -392,7 +607,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(tmem_full_bar, 0);
       trace_stamp(tr, 5);
     }
-    gemm_epilogue<BN>(tmap_d, tmap_m, ep, M, N, m0, n0, warp, lane, tmem_base, smem, tmem_full_bar, mask_bar);
+    bool head_done = false;
+    if constexpr (BN == 16 && !TF32 && !AMN && !BMN) {
+      if (ep.head_w != nullptr) {
+        gemm_epilogue_head(ep, M, N, m0, n0, warp, lane, tmem_base, tmem_full_bar);
+        head_done = true;
+      }
+    }
+    if (!head_done)
+      gemm_epilogue<BN>(tmap_d, tmap_m, ep, M, N, m0, n0, warp, lane, tmem_base, smem, tmem_full_bar, mask_bar);
     tcgen05_fence_before();
     if (warp == 2 && lane == 0) trace_stamp(tr, 6);
   }
@@ -1642,6 +1865,18 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
   L.stream = reinterpret_cast<cudaStream_t>(stream);
   if (M <= 0 || N <= 0 || K <= 0) return -3;
   const bool tf32 = flags & DK_GEMM_TF32, amn = flags & DK_GEMM_A_MN, bmn = flags & DK_GEMM_B_MN;
+  if (ep->head_w != nullptr) {
+    // fused classifier head: plain bn = 16 kernel, one M tile, a grid small enough to be co-resident
+    if (bn != 16 || M > dk::kBlockM || splits > 1 || (flags & ~DK_GEMM_SHORT_A) != 0 || (N + 15) / 16 > 32 || N % 8 != 0 ||
+        ep->head_c > 16 || ep->head_c < 1 || ep->head_labels == nullptr || ep->head_acc == nullptr ||
+        ep->head_sync == nullptr || ep->d_fp32 || ep->dt != nullptr || ep->mask != nullptr || ep->bias_along_m ||
+        (ep->ldd % 8) != 0 || (ep->head_lddh % 8) != 0 || (ep->head_ldz % 8) != 0)
+      return -9;
+    L.ep.tma_store = 0;
+    L.ep.tma_mask = 0;
+    L.td = nullptr;
+    L.tm = nullptr;
+  }
   if (flags & DK_GEMM_SHORT_A) {
     if ((flags & (DK_GEMM_PAIR | DK_GEMM_PERSISTENT | DK_GEMM_A_MN)) || M > dk::kBlockM) return -8;  // plain kernel, one M tile
     L.a_box_rows = dk_gemm_a_box_rows(M);

@@ -29,6 +29,11 @@ class GemmEpilogue(C.Structure):
         ("d", vp), ("ldd", i32), ("d_fp32", i32), ("accumulate", i32), ("dt", vp), ("lddt", i32),
         ("alpha", f32), ("drop_p", f32), ("drop_seed", u32), ("step", vp), ("tma_store", i32), ("tma_mask", i32),
         ("trace", vp),
+        # classifier head fused into the producing GEMM (csrc/gemm.h)
+        ("head_w", vp), ("head_ldw", i32), ("head_bias", vp), ("head_c", i32), ("head_labels", vp),
+        ("head_label_slot", i32), ("head_acc", vp), ("head_sync", vp), ("head_dz", vp), ("head_ldz", i32),
+        ("head_dh", vp), ("head_lddh", i32), ("head_alpha", f32), ("head_hist", vp), ("head_step", vp),
+        ("head_hist_slots", i32),
     ]
 
 

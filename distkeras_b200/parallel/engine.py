@@ -230,7 +230,7 @@ class NativeReplica(Replica):
         self._keep: list = []  # buffers referenced only by raw pointers
         # DK_TRACE=1: every GEMM / fused-update op of the training lists stamps the SM clock of its first CTA
         # at fixed points into a row of this buffer (tools/kernel_timeline.py)
-        self._trace = torch.zeros(64, 8, dtype=torch.int64, device=dev) if os.environ.get("DK_TRACE") == "1" else None
+        self._trace = torch.zeros(64, 16, dtype=torch.int64, device=dev) if os.environ.get("DK_TRACE") == "1" else None
         self._trace_names: list = []
         self.engine = self.lib.dk_engine_create()
         # L_step: training forward; L_bwd: loss + backward + optimizer; L_fwd: inference forward;
@@ -296,7 +296,7 @@ class NativeReplica(Replica):
         if self._trace is None or len(self._trace_names) >= self._trace.shape[0]:
             return 0
         self._trace_names.append(name)
-        return self._trace.data_ptr() + 64 * (len(self._trace_names) - 1)
+        return self._trace.data_ptr() + 128 * (len(self._trace_names) - 1)
 
     def _gemm(self, lst: int, A: int, lda: int, Bp: int, ldb: int, M: int, Nn: int, K: int, flags: int,
               ep: N.GemmEpilogue, bn: int = 0, splits: int = 0) -> None:
@@ -508,6 +508,32 @@ class NativeReplica(Replica):
                 return bn
         return 128
 
+    def _plan_head_in_forward(self, b: "_Block", bi: int, rows: int, Nout: int):
+        """Compact program: when block ``bi`` is the ReLU dense layer right below a softmax classifier the fused head
+        kernel would handle, the head moves into the epilogue of THIS layer's forward GEMM (``DkGemmEpilogue.head_*``):
+        one launch and one dependent-kernel latency less per step.  Returns the shared buffers (planned once) or None."""
+        if getattr(self, "_fwd_head", None) is not None and self._fwd_head["bi"] == bi:
+            return self._fwd_head
+        if (not self.compact or not self.training or os.environ.get("DK_HEAD_IN_FWD", "1") == "0" or self.dense_labels
+                or self.loss_kind != "xent" or bi + 2 != len(self.blocks) or b.kind != "dense" or b.act != "relu"
+                or rows > 128 or Nout % 8 != 0 or (Nout + 15) // 16 > 32):
+            return None
+        nb = self.blocks[bi + 1]
+        C_, Kh = nb.n_out, nb.k_in
+        if (nb.kind != "dense" or nb.act == "relu" or C_ > 16 or Kh != Nout or Kh % 8 != 0 or C_ * (Kh + 4) * 4 > 48 * 1024
+                or os.environ.get("DK_FUSED_HEAD", "1") == "0" or getattr(nb, "drop_p", 0) > 0):
+            return None
+        kseg = self._seg(nb.layer_index, nb.seg_prefix + "kernel")
+        bseg = self._seg(nb.layer_index, nb.seg_prefix + "bias") if nb.use_bias else None
+        ldz = _r8(C_)
+        dev = self.device
+        self._fwd_head = dict(
+            bi=bi, w=self.Wb.data_ptr() + 2 * kseg.offset, ldw=Kh, C=C_,
+            bias=(self.W.data_ptr() + 4 * bseg.offset) if bseg is not None else 0,
+            acc=torch.zeros(2, 128, 16, dtype=torch.float32, device=dev), sync=torch.zeros(2, dtype=torch.int32, device=dev),
+            dz=self._buf(rows, ldz), ldz=ldz, dh=self._buf(rows, Nout))
+        return self._fwd_head
+
     def _bn_slice(self, floats: int) -> int:
         ptr = self._bn_scratch.data_ptr() + 4 * self._bn_used
         self._bn_used += floats
@@ -588,6 +614,8 @@ class NativeReplica(Replica):
                       and K % 8 == 0 and a_in["ld"] % 8 == 0 and wbld == K and Nout * (K + 4) * 4 <= 48 * 1024
                       and b.act != "relu" and os.environ.get("DK_FUSED_HEAD", "1") != "0")
         self.head_fused = head_fused if is_last else getattr(self, "head_fused", False)
+        if is_last and getattr(self, "_fwd_head", None) is not None and not head_fused:
+            raise RuntimeError("planner bug: head moved into the forward GEMM but the classifier is not fusable")
         if is_last:
             ldl = _r8(Nout) if self.loss_kind == "xent" else Nout  # fp32 rows 16-byte aligned for TMA
             out = self._buf(rows, ldl, dtype=torch.float32)
@@ -628,6 +656,17 @@ class NativeReplica(Replica):
                 continue
             bn = self._narrow_bn(rows, Nout, 16) if self.compact else 0
             fl = N.GEMM_SHORT_A if (self.compact and rows < 128) else 0   # one short M tile: short TMA box
+            if lst in self._train_lists and bn == 16 and a_in.get("slot") is None:
+                fh = self._plan_head_in_forward(b, bi, rows, Nout)
+                if fh is not None:
+                    (ep.head_w, ep.head_ldw, ep.head_bias, ep.head_c) = fh["w"], fh["ldw"], fh["bias"], fh["C"]
+                    ep.head_labels, ep.head_label_slot = 0, SLOT_Y
+                    ep.head_acc, ep.head_sync = fh["acc"].data_ptr(), fh["sync"].data_ptr()
+                    ep.head_dz, ep.head_ldz = fh["dz"].data_ptr(), fh["ldz"]
+                    ep.head_dh, ep.head_lddh = fh["dh"].data_ptr(), Nout
+                    ep.head_alpha = 1.0 / (1.0 - b.drop_p) if b.drop_p > 0 else 1.0
+                    ep.head_hist, ep.head_step, ep.head_hist_slots = (self.hist.data_ptr(), self.step_counter.data_ptr(),
+                                                                      self.hist_slots)
             if a_in.get("slot") is not None:
                 ep.trace = self._trace_row(f"list{lst} gemm(slot) M={rows} N={Nout} K={K} bn={bn}") or None
                 r = self.lib.dk_engine_add_gemm_slot(self.engine, lst, a_in["slot"], a_in["ld"], C.c_void_p(wbp), wbld,
@@ -642,7 +681,13 @@ class NativeReplica(Replica):
         def backward(grad, premasked, need_dx, prev):
             lst = self._bwd_list
             head_din = None
-            if head_fused:
+            fh = getattr(self, "_fwd_head", None) if (head_fused and is_last) else None
+            if fh is not None:
+                # loss, dZ and dH were produced by the epilogue of the previous layer's forward GEMM
+                grad = dict(t=fh["dz"], rows=rows, cols=Nout, ld=fh["ldz"])
+                head_din = fh["dh"] if need_dx else None
+                fuse_mask = True
+            elif head_fused:
                 fuse_mask = prev is not None and prev.kind == "dense" and prev.act == "relu"
                 if prev is not None and prev.kind == "dense" and prev.drop_p > 0 and not fuse_mask:
                     raise UnsupportedByNativeEngine("dropout after a non-ReLU dense layer")

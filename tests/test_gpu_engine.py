@@ -291,6 +291,34 @@ def test_compact_program_matches_classic_program(B, optimizer):
         assert abs(l0 - l1) < 0.02 * max(1.0, abs(l0)) and abs(a0 - a1) <= 4.0 / B
 
 
+@pytest.mark.parametrize("B", [64, 40, 128])
+def test_head_in_forward_gemm_matches_head_kernel(B, monkeypatch):
+    """Classifier head in the epilogue of the second forward GEMM (partial logits red.add'ed across the CTAs of the
+    grid, in-kernel rendezvous, dZ / dH per CTA) against the stand-alone fused head kernel: same program otherwise."""
+    from distkeras_b200.models import mnist_mlp
+    from distkeras_b200.parallel.engine import NativeReplica
+
+    torch.manual_seed(0)
+    xs = torch.randint(0, 256, (8, B, 784), dtype=torch.uint8)
+    ys = torch.randint(0, 10, (8, B)).to(torch.int32)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DK_HEAD_IN_FWD", mode)
+        rep = NativeReplica(mnist_mlp(seed=1), "adam", "categorical_crossentropy", B, 0, in_dtype="u8",
+                            input_affine=(1 / 255.0, 0.0), seed=5)
+        assert rep.compact and (getattr(rep, "_fwd_head", None) is not None) == (mode == "1")
+        hist = [rep.train_on_batch(xs[i], ys[i]) for i in range(8)]
+        torch.cuda.synchronize()
+        out[mode] = (rep.W.cpu().clone(), hist)
+        if mode == "1":   # 8 launches: the launch counter says so, the next launch's half of the scratch is clean
+            assert int(rep._fwd_head["sync"][1]) == 8 and float(rep._fwd_head["acc"][0].abs().max()) == 0.0
+        rep.close()
+    w0, w1 = out["0"][0], out["1"][0]
+    assert float((w0 - w1).norm() / w0.norm()) < 2e-3
+    for (l0, a0), (l1, a1) in zip(out["0"][1], out["1"][1]):
+        assert abs(l0 - l1) < 0.01 * max(1.0, abs(l0)) and abs(a0 - a1) <= 2.0 / B
+
+
 @pytest.mark.parametrize("name,kw", [("ADAG", dict(communication_window=4)), ("DOWNPOUR", dict(communication_window=3)),
                                      ("DynSGD", dict(communication_window=3)),
                                      ("AEASGD", dict(communication_window=4, rho=1.0, learning_rate=0.1))])

@@ -41,7 +41,7 @@ class RecordingLib:
 
 
 def _lower(model_name, batch, monkeypatch, native_lib, **env):
-    for k in ("DK_IMPLICIT_CONV", "DK_IMPLICIT_WGRAD", "DK_SIDE_STREAMS", "DK_FUSED_HEAD", "DK_COMPACT", "DK_COMPACT_MAX_BATCH"):
+    for k in ("DK_IMPLICIT_CONV", "DK_IMPLICIT_WGRAD", "DK_SIDE_STREAMS", "DK_FUSED_HEAD", "DK_COMPACT", "DK_COMPACT_MAX_BATCH", "DK_HEAD_IN_FWD"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -62,9 +62,12 @@ def test_compact_lowering_of_small_batch_mlp(monkeypatch, native_lib):
     lib, sizes = _lower("mnist_mlp", 64, monkeypatch, native_lib)
     assert lib.calls["dk_engine_add_bwd_update"] == 1 and lib.calls["dk_engine_add_gemm_slot"] == 2  # L_step + L_fwd
     assert lib.ops["OP_OPTIM"] == 0 and lib.ops["OP_COLSUM"] == 0 and lib.ops["OP_MEMSET"] == 0
-    assert lib.ops["OP_INPUT"] == 2 and lib.ops["OP_HEAD"] == 1
-    # L_step: fwd1 (slot-fed), fwd2 | L_bwd: head, dgrad2, fused update | L_fwd: fwd1, fwd2, head GEMM, softmax
-    assert lib.calls["dk_engine_add_gemm"] == 4 and sizes["L_bwd"] == 1 and sizes["L_fwd"] == 1
+    # the classifier head rides in the epilogue of the second forward GEMM: no head op at all
+    assert lib.ops["OP_INPUT"] == 2 and lib.ops["OP_HEAD"] == 0
+    # L_step: fwd1 (slot-fed), fwd2 + head | L_bwd: dgrad2, fused update | L_fwd: fwd1, fwd2, head GEMM, softmax
+    assert lib.calls["dk_engine_add_gemm"] == 4 and sizes["L_bwd"] == 0 and sizes["L_fwd"] == 1
+    lib, sizes = _lower("mnist_mlp", 64, monkeypatch, native_lib, DK_HEAD_IN_FWD="0")
+    assert lib.ops["OP_HEAD"] == 1 and sizes["L_bwd"] == 1
 
 
 @pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 512), ("higgs_mlp", 128), ("mnist_convnet", 32),

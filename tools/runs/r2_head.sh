@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_engine.py -x -q -m gpu -k "head_in_forward or compact_program or fused_into_backward or adag_matches" > gpurun_out/pytest_head.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_head.log
+tail -15 gpurun_out/pytest_head.log
+timeout 300 python bench.py --skip-e2e > gpurun_out/bench_head_b64.json 2> gpurun_out/bench_head_b64.err; echo "rc=$?"; tail -2 gpurun_out/bench_head_b64.err
+DK_HEAD_IN_FWD=0 timeout 300 python bench.py --skip-e2e > gpurun_out/bench_nohead_b64.json 2> gpurun_out/bench_nohead_b64.err; echo "rc=$?"
+python - <<'PY'
+import json
+for f in ("bench_head_b64", "bench_nohead_b64"):
+    try:
+        d = json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1]); print(f, round(d["ms_per_step"]*1e3, 2), "us/step", d["kernels_per_step"])
+    except Exception as e: print(f, "ERR", e)
+PY
+DK_PDL=0 timeout 300 python tools/kernel_timeline.py --batch 64 2>&1 | tail -6 | cut -c1-140
+timeout 300 python tools/kernel_timeline.py --batch 64 2>&1 | tail -6 | cut -c1-200
