@@ -318,6 +318,22 @@ __device__ __forceinline__ void bwd_epilogue(const BwdUpdateDev& p, const BwdLay
     // the two halves of a quarter fill one [32 x 128 B] box of the bf16 shadow tile: pair barrier, one store
     named_bar_sync(1 + quarter, 64);
     if (half == 0 && lane == 0 && n0 < ly.k_in) tma_store_2d_addr(&ly.maps->st[kStWb], wb_tile + quarter * 4096, n0, mbase);
+    if (ly.wb_pad != nullptr && half == 1) {
+      // the TMA store above went to the 8-padded shadow; the flat shadow (rows 8-byte aligned: k_in % 4 == 0) gets the
+      // same 32 x 64 slice through plain stores -- half a warp per row, 8 bytes per lane, 128 contiguous bytes per row
+      const int c16 = (lane & 15) >> 1, h8 = lane & 1;
+      const int ncol = n0 + 8 * c16 + 4 * h8;
+#pragma unroll 1
+      for (int rr = 0; rr < 32; rr += 2) {
+        const int row = quarter * 32 + rr + (lane >> 4);
+        const int m = m0 + row;
+        if (m < ly.n_out && ncol < ly.k_in) {
+          uint32_t lo, hi;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(wb_tile + row * 128 + ((c16 ^ (row & 7)) << 4) + (h8 << 3)));
+          *reinterpret_cast<uint2*>(p.wb + ly.w_off + static_cast<long>(m) * ly.k_in + ncol) = make_uint2(lo, hi);
+        }
+      }
+    }
     trace_stamp(tr, 11);
     if (lane == 0) {
       tma_store_commit();
@@ -614,7 +630,12 @@ int dk_bwd_update_prepare(void* record, const DkBwdUpdateDesc* d) {
     for (int l = 0; l < d->nlayers; ++l) {
       const DkBwdLayerDesc& sd = d->layer[l];
       BwdLayerDev& ly = p.layer[l];
-      if (!ly.vec || sd.wb_pad != nullptr || sd.k_in % 8 != 0 || sd.w_off % 8 != 0) continue;  // bf16 rows 16-byte aligned too
+      // fp32 rows must be 16-byte aligned (k_in % 4 == 0).  The bf16 shadow tile leaves by TMA store into the flat
+      // shadow when its rows are 16-byte aligned too (k_in % 8 == 0), otherwise into the 8-padded shadow the GEMMs
+      // read (the flat copy is then written with plain 8-byte stores by the kernel).
+      const bool flat_rows_ok = sd.k_in % 8 == 0 && sd.wb_pad == nullptr;
+      const bool pad_rows_ok = sd.k_in % 8 != 0 && sd.wb_pad != nullptr && sd.ldwb_pad % 8 == 0;
+      if (!ly.vec || sd.k_in % 4 != 0 || sd.w_off % 8 != 0 || !(flat_rows_ok || pad_rows_ok)) continue;
       float* arrs[4] = {d->w, d->s0, d->s1, d->w1};
       bool ok = true;
       for (int a = 0; a < 4 && ok; ++a) {
@@ -622,8 +643,10 @@ int dk_bwd_update_prepare(void* record, const DkBwdUpdateDesc* d) {
         ok = dk_tmap_encode_2d(&host[l].ld[a], arrs[a] + sd.w_off, DK_F32, sd.n_out, sd.k_in, sd.k_in, kBwdBlockM) == 0 &&
              dk_tmap_encode_2d(&host[l].st[a], arrs[a] + sd.w_off, DK_F32, sd.n_out, sd.k_in, sd.k_in, 32) == 0;
       }
-      ok = ok && dk_tmap_encode_2d(&host[l].st[kStWb], reinterpret_cast<__nv_bfloat16*>(d->wb) + sd.w_off, DK_BF16, sd.n_out,
-                                   sd.k_in, sd.k_in, 32) == 0;
+      ok = ok && (flat_rows_ok
+                      ? dk_tmap_encode_2d(&host[l].st[kStWb], reinterpret_cast<__nv_bfloat16*>(d->wb) + sd.w_off, DK_BF16,
+                                          sd.n_out, sd.k_in, sd.k_in, 32)
+                      : dk_tmap_encode_2d(&host[l].st[kStWb], sd.wb_pad, DK_BF16, sd.n_out, sd.k_in, sd.ldwb_pad, 32)) == 0;
       if (ok) {
         any = true;
         ly.maps = reinterpret_cast<const StateMaps*>(static_cast<uintptr_t>(l + 1));  // patched to the device address below

@@ -266,15 +266,14 @@ class NativeReplica(Replica):
         blocks = self.blocks
         if any(b.kind != "dense" for b in blocks) or not (1 <= len(blocks) <= N.BWD_MAX_LAYERS):
             return False
+        # hidden widths: multiples of 4 (fp32 rows stay 16-byte aligned); widths that are not multiples of 8 (the Higgs
+        # MLP's 500) read their weights through the 8-padded bf16 shadow, which the fused update kernel refreshes itself
         for b in blocks[:-1]:
-            if b.n_out % 8 != 0:
-                return False
-        for b in blocks[1:]:
-            if b.k_in % 8 != 0:
+            if b.n_out % 4 != 0:
                 return False
         head = blocks[-1]
-        return (head.n_out <= 16 and head.act == "softmax" and head.k_in % 8 == 0
-                and head.n_out * (head.k_in + 4) * 4 <= 48 * 1024)
+        return (head.n_out <= 16 and head.act == "softmax" and head.k_in % 4 == 0
+                and head.n_out * (_r8(head.k_in) + 4) * 4 <= 48 * 1024)
 
     # ------------------------------------------------------------------------------------------
     # op-list helpers
@@ -610,8 +609,11 @@ class NativeReplica(Replica):
             a_in = cur
         # classifier head (<= 16 classes, softmax cross-entropy): in the training lists the forward
         # GEMM, the loss and the dgrad GEMM collapse into ONE kernel (dk_dense_softmax_head)
+        # (a head input width that is not a multiple of 8 -- the Higgs MLP's 500 -- runs on the 8-padded width: the pad
+        # columns of the activation buffer and of the padded weight shadow are zeros, so they add nothing)
+        Kh = wbld
         head_fused = (is_last and self.training and b.kind == "dense" and self.loss_kind == "xent" and Nout <= 16
-                      and K % 8 == 0 and a_in["ld"] % 8 == 0 and wbld == K and Nout * (K + 4) * 4 <= 48 * 1024
+                      and Kh == _r8(K) and a_in["ld"] == Kh and Nout * (Kh + 4) * 4 <= 48 * 1024
                       and b.act != "relu" and os.environ.get("DK_FUSED_HEAD", "1") != "0")
         self.head_fused = head_fused if is_last else getattr(self, "head_fused", False)
         if is_last and getattr(self, "_fwd_head", None) is not None and not head_fused:
@@ -692,12 +694,12 @@ class NativeReplica(Replica):
                 if prev is not None and prev.kind == "dense" and prev.drop_p > 0 and not fuse_mask:
                     raise UnsupportedByNativeEngine("dropout after a non-ReLU dense layer")
                 alpha = 1.0 / (1.0 - prev.drop_p) if (fuse_mask and prev.drop_p > 0) else 1.0
-                head_din = self._buf(rows, K) if need_dx else None
+                head_din = self._buf(rows, Kh) if need_dx else None
                 self._add(lst, N.OP_HEAD,
                           [-(a_in["slot"] + 1) if a_in.get("slot") is not None else a_in["t"].data_ptr(), a_in["ld"], wbp,
                            wbld, (wptr_f32 + 4 * bseg.offset) if bseg is not None else 0,
                            0 if self.dense_labels else -(SLOT_Y + 1), -(SLOT_Y + 1) if self.dense_labels else 0,
-                           rows, Nout, K, grad["t"].data_ptr(), grad["ld"], head_din.data_ptr() if need_dx else 0, K,
+                           rows, Nout, Kh, grad["t"].data_ptr(), grad["ld"], head_din.data_ptr() if need_dx else 0, Kh,
                            1 if fuse_mask else 0, self.hist.data_ptr(), self.step_counter.data_ptr(), self.hist_slots],
                           [alpha])
             if b.act == "relu" and not premasked:
@@ -719,7 +721,7 @@ class NativeReplica(Replica):
                 if not need_dx:
                     return None, True
                 if head_din is not None:
-                    return dict(t=head_din, rows=rows, cols=K, ld=K), fuse_mask
+                    return dict(t=head_din, rows=rows, cols=K, ld=head_din.shape[1]), fuse_mask
                 din = self._buf(rows, _r8(K))
                 ep = N.GemmEpilogue()
                 ep.d, ep.ldd, ep.alpha = din.data_ptr(), _r8(K), 1.0
@@ -786,7 +788,7 @@ class NativeReplica(Replica):
             if not need_dx:
                 return None, True
             if head_din is not None:  # the fused head already produced the (masked) input gradient
-                return dict(t=head_din, rows=rows, cols=K, ld=K), fuse_mask
+                return dict(t=head_din, rows=rows, cols=K, ld=head_din.shape[1]), fuse_mask
             if implicit and grad["ld"] == Nout:
                 H, Wd, Cin = b.in_shape
                 OH, OW, _ = b.out_shape
@@ -993,6 +995,12 @@ class NativeReplica(Replica):
         """Recompute the bf16 shadow from the fp32 master (after an external write to ``W``)."""
         N.check(self.lib.dk_cast_bf16(self.W.data_ptr(), self.Wb.data_ptr(), self.P, C.c_void_p(N.current_stream())),
                 "dk_cast_bf16")
+        self.refresh_pads()
+
+    def refresh_pads(self) -> None:
+        """Re-derive the 8-padded weight shadows from the flat bf16 shadow (after a pull or any other external write)."""
+        if hasattr(self, "L_pad"):
+            self._run(self.L_pad)
 
     weights_changed = refresh_shadow
 
@@ -1017,8 +1025,8 @@ class NativeReplica(Replica):
                 self._run(self.L_in_step)
                 staged_row = 0
             self.lib.dk_engine_set_slot(self.engine, SLOT_XB, C.c_void_p(xr.data_ptr() + staged_row * xr.shape[1] * 2))
-            if hasattr(self, "L_pad"):
-                self._run(self.L_pad)
+            # (no pad refresh here: the fused update kernel keeps the padded weight shadows current itself; whoever
+            # writes the flat shadow from outside -- a pull, set_flat -- calls refresh_pads())
             self._run(self.L_step)
             if comm and self.L_bwd_comm < 0:
                 raise RuntimeError("the replica was planned without a comm_spec")

@@ -177,13 +177,18 @@ class FabricWorker:
             k += 1
         shards = self.shards or [(0, self.rep.P, reg.center_ptr)]
         if self.alg["kind"] == "easgd":
-            return k + _easgd_round(self, shards, self.rep.W.data_ptr(), self.rep.Wb.data_ptr(), st)
+            k += _easgd_round(self, shards, self.rep.W.data_ptr(), self.rep.Wb.data_ptr(), st)
+            if self.rep.compact:
+                self.rep.refresh_pads()
+            return k
         for i, (lo, hi, cptr) in enumerate(shards):
             # the control block (update counter, heartbeat) is bumped once per commit: by shard 0
             k += self._comm_range(lo, hi, cptr, ctrl if i == 0 else None, st)
         if self.strict:
             N.check(lib.dk_ps_lock_release(ctrl, self.ticket.data_ptr(), st), "lock_release")
             k += 1
+        if self.rep.compact:
+            self.rep.refresh_pads()   # the exchange kernels wrote the flat bf16 shadow: padded copies follow
         return k
 
     def _comm_range(self, lo: int, hi: int, center_ptr: int, ctrl, st) -> int:
@@ -300,6 +305,7 @@ class FabricWorker:
                 N.check(self.lib.dk_ps_pull(C.c_void_p(cptr), rep.W.data_ptr() + 4 * lo, rep.W1.data_ptr() + 4 * lo,
                                             rep.Wb.data_ptr() + 2 * lo, hi - lo, C.c_void_p(reg.ctrl_ptr),
                                             self.last_update.data_ptr(), self._stream()), "pull")
+            rep.refresh_pads()
         self.compute.synchronize()
 
     def _warm_up(self) -> None:

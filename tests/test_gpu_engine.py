@@ -33,6 +33,15 @@ def _cnn_tma(seed=0):
                        MaxPooling2D(2), Flatten(), Dense(10, activation="softmax")], seed=seed)
 
 
+def _mlp_odd(seed=0):
+    """Hidden widths that are multiples of 4 but not of 8 (the Higgs MLP's 500 in small): padded weight shadows,
+    classifier head on the padded width."""
+    from distkeras_b200.models import Dense, Sequential
+
+    return Sequential([Dense(36, activation="relu", input_shape=(64,)), Dense(20, activation="relu"),
+                       Dense(10, activation="softmax")], seed=seed)
+
+
 def _resnet(seed=0):
     from distkeras_b200.models import (Activation, BatchNormalization, Conv2D, Dense, GlobalAveragePooling2D,
                                        MaxPooling2D, ResidualBlock, Sequential)
@@ -42,7 +51,7 @@ def _resnet(seed=0):
                        GlobalAveragePooling2D(), Dense(10, activation="softmax")], seed=seed)
 
 
-@pytest.mark.parametrize("maker,in_shape,implicit", [(_mlp, (64,), False), (_cnn, (12, 12, 1), False), (_cnn_tma, (10, 10, 32), None),
+@pytest.mark.parametrize("maker,in_shape,implicit", [(_mlp, (64,), False), (_mlp_odd, (64,), False), (_cnn, (12, 12, 1), False), (_cnn_tma, (10, 10, 32), None),
                                                      (_resnet, (16, 16, 3), False), (_cnn, (12, 12, 1), True),
                                                      (_resnet, (16, 16, 3), True)])
 def test_native_gradients_match_autograd(maker, in_shape, implicit, monkeypatch):
@@ -291,7 +300,32 @@ def test_compact_program_matches_classic_program(B, optimizer):
         assert abs(l0 - l1) < 0.02 * max(1.0, abs(l0)) and abs(a0 - a1) <= 4.0 / B
 
 
-@pytest.mark.parametrize("B", [64, 40, 128])
+@pytest.mark.parametrize("B", [64, 24])
+def test_compact_program_handles_widths_that_are_not_multiples_of_8(B):
+    """The Higgs MLP of the reference (30-500-500-500-2, adagrad, `example_1_analysis.ipynb`): 500-wide layers read
+    their weights through the 8-padded bf16 shadow, which the fused update kernel keeps current itself."""
+    from distkeras_b200.models import higgs_mlp
+    from distkeras_b200.parallel.engine import NativeReplica
+
+    torch.manual_seed(0)
+    xs = torch.randn(6, B, 30)
+    ys = torch.randint(0, 2, (6, B)).to(torch.int32)
+    out = {}
+    for compact in (False, True):
+        rep = NativeReplica(higgs_mlp(seed=2), "adagrad", "categorical_crossentropy", B, 0, in_dtype="f32", compact=compact,
+                            seed=3)
+        assert rep.compact == compact
+        hist = [rep.train_on_batch(xs[i], ys[i]) for i in range(6)]
+        torch.cuda.synchronize()
+        out[compact] = (rep.W.cpu().clone(), hist)
+        rep.close()
+    w0, w1 = out[False][0], out[True][0]
+    assert float((w0 - w1).norm() / w0.norm()) < 3e-3
+    for (l0, a0), (l1, a1) in zip(out[False][1], out[True][1]):
+        assert abs(l0 - l1) < 0.02 * max(1.0, abs(l0)) and abs(a0 - a1) <= 3.0 / B
+
+
+@pytest.mark.parametrize("B", [64, 40, 128, 8, 4])
 def test_head_in_forward_gemm_matches_head_kernel(B, monkeypatch):
     """Classifier head in the epilogue of the second forward GEMM (partial logits red.add'ed across the CTAs of the
     grid, in-kernel rendezvous, dZ / dH per CTA) against the stand-alone fused head kernel: same program otherwise."""

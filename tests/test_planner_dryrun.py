@@ -70,7 +70,15 @@ def test_compact_lowering_of_small_batch_mlp(monkeypatch, native_lib):
     assert lib.ops["OP_HEAD"] == 1 and sizes["L_bwd"] == 1
 
 
-@pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 512), ("higgs_mlp", 128), ("mnist_convnet", 32),
+def test_compact_lowering_of_the_higgs_mlp(monkeypatch, native_lib):
+    """500-wide layers (not a multiple of 8): compact program with padded weight shadows, head kernel on the padded width."""
+    lib, sizes = _lower("higgs_mlp", 64, monkeypatch, native_lib)
+    assert lib.calls["dk_engine_add_bwd_update"] == 1 and lib.ops["OP_HEAD"] == 1 and lib.ops["OP_OPTIM"] == 0
+    # L_step: fwd1 (slot), fwd2, fwd3 | L_bwd: head, dgrad3, dgrad2, update | L_fwd: 4 GEMMs + softmax; 4 padded shadows
+    assert lib.calls["dk_engine_add_gemm"] == 7 and lib.calls["dk_engine_add_gemm_slot"] == 2 and lib.ops["OP_MEMCPY2D"] == 4
+
+
+@pytest.mark.parametrize("model_name,batch", [("mnist_mlp", 512), ("higgs_mlp", 512), ("mnist_convnet", 32),
                                               ("cifar10_cnn", 32), ("resnet18", 4)])
 def test_default_lowering(model_name, batch, monkeypatch, native_lib):
     lib, sizes = _lower(model_name, batch, monkeypatch, native_lib)
@@ -79,10 +87,9 @@ def test_default_lowering(model_name, batch, monkeypatch, native_lib):
     # implicit (TMA-im2col) convolution is the default for layers with 32 / 64k input channels
     assert (lib.calls["dk_engine_add_conv_gemm"] > 0) == (model_name in ("mnist_convnet", "cifar10_cnn", "resnet18"))
     assert lib.ops["OP_OPTIM"] == 1 and lib.ops["OP_FORK"] == lib.ops["OP_FORK"]  # one optimizer launch per step
-    if model_name in ("mnist_mlp", "cifar10_cnn"):  # head input width is a multiple of 8 (200 / 512)
-        assert lib.ops["OP_HEAD"] == 1 and lib.ops["OP_XENT"] == 1  # fused head in training, softmax kernel in inference
-    elif model_name in ("higgs_mlp", "mnist_convnet"):  # 500 / 225 inputs: the three-kernel head
-        assert lib.ops["OP_HEAD"] == 0 and lib.ops["OP_XENT"] == 2
+    if model_name in ("mnist_mlp", "cifar10_cnn", "higgs_mlp", "mnist_convnet"):
+        # fused head in training (500 / 225-wide inputs run on the 8-padded width), softmax kernel in inference
+        assert lib.ops["OP_HEAD"] == 1 and lib.ops["OP_XENT"] == 1
     if "cnn" in model_name or "convnet" in model_name:
         assert lib.ops["OP_RELU_MASK"] == 0  # every conv dReLU is fused into the dgrad epilogue / col2im / pool backward
 

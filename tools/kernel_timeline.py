@@ -26,8 +26,11 @@ ap.add_argument("--optimizer", default="adam")
 a = ap.parse_args()
 model = ZOO[a.model](seed=0)
 model.build()
-rep = NativeReplica(model, a.optimizer, "categorical_crossentropy", a.batch, 0, in_dtype="u8", input_affine=(1 / 255.0, 0.0))
-x = torch.randint(0, 256, (a.batch, rep._input_feats), dtype=torch.uint8, device="cuda")
+f32_in = a.model == "higgs_mlp"
+rep = NativeReplica(model, a.optimizer, "categorical_crossentropy", a.batch, 0, in_dtype="f32" if f32_in else "u8",
+                    input_affine=(1.0, 0.0) if f32_in else (1 / 255.0, 0.0))
+x = (torch.randn(a.batch, rep._input_feats, device="cuda") if f32_in
+     else torch.randint(0, 256, (a.batch, rep._input_feats), dtype=torch.uint8, device="cuda"))
 y = torch.randint(0, model.output_shape[-1], (a.batch,), device="cuda").to(torch.int32)
 g = torch.cuda.CUDAGraph()
 for _ in range(3):
