@@ -327,6 +327,28 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
       : "memory");
 }
 
+// ---- cluster multicast (cta_group::1 kernels whose CTAs share an operand tile) ----
+// TMA load whose box lands at the same shared-memory offset in every CTA of `mask`; each destination CTA's mbarrier
+// (same offset) is credited with the box's bytes.
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+
+// commit of a single-CTA MMA group that arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns (one row per thread).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

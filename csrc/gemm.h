@@ -11,7 +11,10 @@ typedef uint16_t dk_bf16;
 
 enum { DK_BF16 = 0, DK_F32 = 1 };
 enum { DK_GEMM_TF32 = 1, DK_GEMM_A_MN = 2, DK_GEMM_B_MN = 4, DK_GEMM_PERSISTENT = 8, DK_GEMM_PAIR = 16,
-       DK_GEMM_SHORT_A = 32 /* K-major A of one short M tile: TMA box of ceil8(M) rows (plain kernel only) */ };
+       DK_GEMM_SHORT_A = 32 /* K-major A of one short M tile: TMA box of ceil8(M) rows (plain kernel only) */,
+       DK_GEMM_MCAST_A = 64 /* with SHORT_A: the CTAs of a thread-block cluster (along N) each load 1/cluster of the A
+                               k-block and multicast it to the others (dk_gemm_mcast_cluster(M) CTAs, A tensor map encoded
+                               with dk_gemm_mcast_box_rows(M) rows) */ };
 
 // Fused epilogue description: out = mask( act( alpha * acc + bias ) )
 typedef struct DkGemmEpilogue {
@@ -71,6 +74,8 @@ int dk_tmap_encode_2d(void* out_tmap, const void* base, int dtype, long rows, lo
                       int box_rows);
 int dk_gemm_pick_bn(int N);
 int dk_gemm_a_box_rows(int M);
+int dk_gemm_mcast_cluster(int M);    // CTAs per cluster for DK_GEMM_MCAST_A (1 = no multicast possible)
+int dk_gemm_mcast_box_rows(int M);   // rows of the A box each CTA loads
 int dk_gemm_pick_bn2(int M, int N);
 int dk_gemm_pick_bn_splitk(int M, int N, int K);
 int dk_gemm_tn_launch(const void* tmap_a, const void* tmap_b, const DkGemmEpilogue* ep, int M, int N,

@@ -476,8 +476,13 @@ __global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 2 : 1))
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
                const GemmEpilogue ep, const int M, const int N, const int K, const int kb_per_split,
-               const int a_box_rows) {
+               const int a_box_rows, const int cluster) {
   using S = GemmSmem<BN, STAGES, TF32>;
+  // cluster > 1 (DK_GEMM_MCAST_A): the CTAs of a cluster are neighbours along N and read the SAME A tile -- each loads
+  // a_box_rows / cluster rows of every k-block and multicasts them into all CTAs' stages; a stage is free again when
+  // every CTA of the cluster has consumed it (empty barriers count `cluster` commits, arrived by multicast).
+  const uint32_t crank = cluster > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << cluster) - 1u);
   // bytes one k-block of the A operand brings in (DK_GEMM_SHORT_A: a short single M tile uses a short box)
   const int a_stage_bytes = AMN ? S::kABytes : a_box_rows * 128;
   constexpr int kBlockK = TF32 ? 32 : 64;   // elements per 128-byte swizzle row
@@ -507,7 +512,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(total_kb, kb_begin + kb_per_split);
   const int num_kb = kb_end - kb_begin;
-  if (num_kb <= 0) return;  // uniform for the CTA
+  if (num_kb <= 0) return;  // uniform for the CTA (never with a cluster: split-K is off there)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -516,7 +521,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (ep.tma_mask) tma_prefetch_desc(&tmap_m);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], cluster > 1 ? cluster : 1);
     }
     mbar_init(tmem_full_bar, 1);
     for (int q = 0; q < 4; ++q) mbar_init(&mask_bar[q], 1);
@@ -528,6 +533,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (cluster > 1) cluster_sync_all();   // every CTA's barriers exist before anybody multicasts into them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) trace_stamp(tr, 1);
@@ -542,6 +548,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const int rows_per = cluster > 1 ? a_box_rows / cluster : 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStageBytes;
@@ -551,6 +558,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int c = 0; c < kBlockM / 64; ++c)
             tma_load_2d(sa + c * 8192, &tmap_a, m0 + c * 64, kb * kBlockK, &full_bar[stage]);
+        } else if (cluster > 1) {
+          // this CTA's slice of the shared A k-block (whole 8-row swizzle atoms), delivered to every CTA of the cluster
+          tma_load_2d_mcast(sa + crank * rows_per * 128, &tmap_a, kb * kBlockK, m0 + static_cast<int>(crank) * rows_per,
+                            &full_bar[stage], cmask);
         } else {
           tma_load_2d(sa, &tmap_a, kb * kBlockK, m0, &full_bar[stage]);
         }
@@ -592,7 +603,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           else
             umma_f16(tmem_base, adesc + kAStep * k, bdesc + kBStep * k, kIdesc, (kb | k) != 0);
         }
-        umma_commit(&empty_bar[stage]);              // frees the smem slot once the MMAs retire
+        if (cluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);   // ... in every CTA that multicasts into it
+        else umma_commit(&empty_bar[stage]);         // frees the smem slot once the MMAs retire
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulator complete
       }
       __syncwarp();
@@ -621,6 +633,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 
   __syncthreads();
+  if (cluster > 1) cluster_sync_all();   // nobody leaves while a peer may still arrive on its barriers
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -1276,6 +1289,7 @@ struct GemmLaunch {
   GemmEpilogue ep;
   int M, N, K, splits;
   int a_box_rows = kBlockM;
+  int cluster = 1;   // DK_GEMM_MCAST_A: CTAs per cluster sharing (and multicasting) the A tile
   cudaStream_t stream;
 };
 
@@ -1309,8 +1323,17 @@ static int launch_gemm(const GemmLaunch& L) {
   ep.tma_mask = (L.tm != nullptr && ep.tma_store && BN >= 64) ? 1 : 0;
   if (splits > 1 && !ep.d_fp32) return -6;
   dim3 grid((N + BN - 1) / BN, (M + kBlockM - 1) / kBlockM, splits);
+  if (L.cluster > 1) {
+    if (AMN || splits > 1 || grid.y != 1) return -8;
+    grid.x = (grid.x + L.cluster - 1) / L.cluster * L.cluster;   // whole clusters; the extra CTAs' tiles are clipped
+    DK_HOST_CHECK(launch_kernel_cluster(kern, grid, dim3(kGemmThreads), S::kTotal, stream, static_cast<unsigned>(L.cluster), ta, tb,
+                                        ep.tma_store ? *L.td : ta, ep.tma_mask ? *L.tm : ta, ep, M, N, K, kb_per_split,
+                                        L.a_box_rows, L.cluster));
+    DK_HOST_CHECK(cudaGetLastError());
+    return 0;
+  }
   DK_HOST_CHECK(DK_LAUNCH(kern, grid, kGemmThreads, S::kTotal, stream, ta, tb, ep.tma_store ? *L.td : ta, ep.tma_mask ? *L.tm : ta, ep, M,
-                                                  N, K, kb_per_split, L.a_box_rows));
+                                                  N, K, kb_per_split, L.a_box_rows, 1));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1824,6 +1847,16 @@ int dk_gemm_a_box_rows(int M) {
   return (M + 7) / 8 * 8;
 }
 
+// DK_GEMM_MCAST_A: the A box is split into whole 8-row swizzle atoms over the CTAs of a cluster (at most 8)
+int dk_gemm_mcast_cluster(int M) {
+  const int atoms = dk_gemm_a_box_rows(M) / 8;
+  for (int cl = 8; cl >= 2; --cl)
+    if (atoms % cl == 0) return cl;
+  return 1;
+}
+
+int dk_gemm_mcast_box_rows(int M) { return dk_gemm_a_box_rows(M) / dk_gemm_mcast_cluster(M); }
+
 int dk_gemm_pick_bn(int N) {
   if (N <= 16) return 16;
   if (N <= 32) return 32;
@@ -1867,7 +1900,7 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
   const bool tf32 = flags & DK_GEMM_TF32, amn = flags & DK_GEMM_A_MN, bmn = flags & DK_GEMM_B_MN;
   if (ep->head_w != nullptr) {
     // fused classifier head: plain bn = 16 kernel, one M tile, a grid small enough to be co-resident
-    if (bn != 16 || M > dk::kBlockM || splits > 1 || (flags & ~DK_GEMM_SHORT_A) != 0 || (N + 15) / 16 > 32 || N % 8 != 0 ||
+    if (bn != 16 || M > dk::kBlockM || splits > 1 || (flags & ~(DK_GEMM_SHORT_A | DK_GEMM_MCAST_A)) != 0 || (N + 15) / 16 > 32 || N % 8 != 0 ||
         ep->head_c > 16 || ep->head_c < 1 || ep->head_labels == nullptr || ep->head_acc == nullptr ||
         ep->head_sync == nullptr || ep->d_fp32 || ep->dt != nullptr || ep->mask != nullptr || ep->bias_along_m ||
         (ep->ldd % 8) != 0 || (ep->head_lddh % 8) != 0 || (ep->head_ldz % 8) != 0)
@@ -1880,6 +1913,12 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
   if (flags & DK_GEMM_SHORT_A) {
     if ((flags & (DK_GEMM_PAIR | DK_GEMM_PERSISTENT | DK_GEMM_A_MN)) || M > dk::kBlockM) return -8;  // plain kernel, one M tile
     L.a_box_rows = dk_gemm_a_box_rows(M);
+    if (flags & DK_GEMM_MCAST_A) {
+      L.cluster = dk_gemm_mcast_cluster(M);
+      if (splits > 1 || tf32 || bmn) return -8;
+    }
+  } else if (flags & DK_GEMM_MCAST_A) {
+    return -8;
   }
   if ((flags & DK_GEMM_PAIR) && !tf32) {
     // K-major B tensor maps must have been encoded with box_rows = bn / 2 (each CTA loads half the tile)
@@ -1990,7 +2029,9 @@ int dk_gemm_encode_operands(void* tmap_a, void* tmap_b, const void* A, long lda,
                             int M, int N, int K, int bn, int flags) {
   const int dt = (flags & DK_GEMM_TF32) ? DK_F32 : DK_BF16;
   int r = (flags & DK_GEMM_A_MN) ? dk_tmap_encode_2d(tmap_a, A, dt, K, M, lda, 64)
-                                 : dk_tmap_encode_2d(tmap_a, A, dt, M, K, lda, (flags & DK_GEMM_SHORT_A) ? dk_gemm_a_box_rows(M) : dk::kBlockM);
+                                 : dk_tmap_encode_2d(tmap_a, A, dt, M, K, lda,
+                                                     (flags & DK_GEMM_MCAST_A) ? dk_gemm_mcast_box_rows(M)
+                                                     : (flags & DK_GEMM_SHORT_A) ? dk_gemm_a_box_rows(M) : dk::kBlockM);
   if (r != 0) return r;
   return (flags & DK_GEMM_B_MN) ? dk_tmap_encode_2d(tmap_b, B, dt, K, N, ldb, 64)
                                 : dk_tmap_encode_2d(tmap_b, B, dt, N, K, ldb, (flags & DK_GEMM_PAIR) ? bn / 2 : bn);

@@ -68,7 +68,7 @@ OP_LOCK_ACQUIRE, OP_LOCK_RELEASE, OP_EAMSGD_PRE, OP_EAMSGD_POST, OP_CAST, OP_ELO
 OP_MEMCPY, OP_LABEL_INDEX, OP_COLSUM, OP_MEMCPY2D, OP_FORK, OP_JOIN, OP_GEMM_PULL = 25, 26, 27, 28, 29, 30, 31
 OP_BN_FWD, OP_BN_INF, OP_BN_BWD, OP_GAP_FWD, OP_GAP_BWD, OP_HEAD = 32, 33, 34, 35, 36, 37
 OP_CONV_GEMM, OP_WFLIP, OP_CONV_WGRAD, OP_BWD_UPDATE, OP_CONV_WGRAD_TMA = 38, 39, 40, 41, 42
-GEMM_TF32, GEMM_A_MN, GEMM_B_MN, GEMM_PERSISTENT, GEMM_PAIR, GEMM_SHORT_A = 1, 2, 4, 8, 16, 32
+GEMM_TF32, GEMM_A_MN, GEMM_B_MN, GEMM_PERSISTENT, GEMM_PAIR, GEMM_SHORT_A, GEMM_MCAST_A = 1, 2, 4, 8, 16, 32, 64
 
 OPT_KINDS = {"sgd": 0, "momentum": 1, "adagrad": 2, "rmsprop": 3, "adam": 4, "adadelta": 5, "adamax": 6, "nadam": 7}
 IN_U8, IN_F32, IN_BF16 = 0, 1, 2
@@ -84,6 +84,8 @@ _SIGNATURES = {
     # gemm
     "dk_tmap_encode_2d": (i32, [vp, vp, i32, i64, i64, i64, i32]),
     "dk_gemm_pick_bn": (i32, [i32]),
+    "dk_gemm_mcast_cluster": (i32, [i32]),
+    "dk_gemm_mcast_box_rows": (i32, [i32]),
     "dk_gemm_pick_bn2": (i32, [i32, i32]),
     "dk_gemm_pick_bn_splitk": (i32, [i32, i32, i32]),
     "dk_gemm_pick_splits_pair": (i32, [i32, i32, i32, i32]),

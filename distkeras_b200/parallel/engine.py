@@ -658,6 +658,10 @@ class NativeReplica(Replica):
                 continue
             bn = self._narrow_bn(rows, Nout, 16) if self.compact else 0
             fl = N.GEMM_SHORT_A if (self.compact and rows < 128) else 0   # one short M tile: short TMA box
+            # the CTAs of a forward GEMM all read the same activation tile: clusters of up to 8 neighbours load 1/8 of
+            # each k-block and multicast it, so an SM ingests its weights plus an eighth of the activations
+            if fl and bn == 16 and os.environ.get("DK_GEMM_MCAST", "0") == "1" and self.lib.dk_gemm_mcast_cluster(rows) > 1:
+                fl |= N.GEMM_MCAST_A
             if lst in self._train_lists and bn == 16 and a_in.get("slot") is None:
                 fh = self._plan_head_in_forward(b, bi, rows, Nout)
                 if fh is not None:

@@ -300,6 +300,29 @@ def test_compact_program_matches_classic_program(B, optimizer):
         assert abs(l0 - l1) < 0.02 * max(1.0, abs(l0)) and abs(a0 - a1) <= 4.0 / B
 
 
+@pytest.mark.parametrize("B", [64, 24, 128])
+def test_cluster_multicast_of_the_activation_tile(B, monkeypatch):
+    """DK_GEMM_MCAST=1: the CTAs of a forward GEMM form clusters (8, 3 and 8 CTAs here), each loads its share of the
+    activation k-block and multicasts it; stages are released by multicast commits.  Same numbers as without."""
+    from distkeras_b200.models import mnist_mlp
+    from distkeras_b200.parallel.engine import NativeReplica
+
+    torch.manual_seed(0)
+    xs = torch.randint(0, 256, (5, B, 784), dtype=torch.uint8)
+    ys = torch.randint(0, 10, (5, B)).to(torch.int32)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DK_GEMM_MCAST", mode)
+        rep = NativeReplica(mnist_mlp(seed=1), "adam", "categorical_crossentropy", B, 0, in_dtype="u8",
+                            input_affine=(1 / 255.0, 0.0), seed=5)
+        hist = [rep.train_on_batch(xs[i], ys[i]) for i in range(5)]
+        torch.cuda.synchronize()
+        out[mode] = (rep.W.cpu().clone(), hist)
+        rep.close()
+    assert torch.equal(out["0"][0], out["1"][0])              # same MMAs on the same operands: bit-identical
+    assert out["0"][1] == out["1"][1]
+
+
 @pytest.mark.parametrize("B", [64, 24])
 def test_compact_program_handles_widths_that_are_not_multiples_of_8(B):
     """The Higgs MLP of the reference (30-500-500-500-2, adagrad, `example_1_analysis.ipynb`): 500-wide layers read
