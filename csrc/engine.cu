@@ -136,7 +136,8 @@ int run_op(Engine* e, Op& op, void* main_stream) {
       // M, N, K, bn, flags (tensor maps + epilogue pre-encoded)
       if (op.dyn_a_slot >= 0) {
         int r = dk_tmap_encode_2d(&op.ta, e->slots[op.dyn_a_slot], DK_BF16, a[0], a[2], op.dyn_lda,
-                                  (a[4] & DK_GEMM_MCAST_A) ? dk_gemm_mcast_box_rows((int)a[0])
+                                  DK_GEMM_TILE_ROWS_OF(a[4]) ? (int)DK_GEMM_TILE_ROWS_OF(a[4])
+                                  : (a[4] & DK_GEMM_MCAST_A) ? dk_gemm_mcast_box_rows((int)a[0])
                                   : (a[4] & DK_GEMM_SHORT_A) ? dk_gemm_a_box_rows((int)a[0]) : 128);
         if (r != 0) return r;
       }

@@ -15,6 +15,11 @@ enum { DK_GEMM_TF32 = 1, DK_GEMM_A_MN = 2, DK_GEMM_B_MN = 4, DK_GEMM_PERSISTENT 
        DK_GEMM_MCAST_A = 64 /* with SHORT_A: the CTAs of a thread-block cluster (along N) each load 1/cluster of the A
                                k-block and multicast it to the others (dk_gemm_mcast_cluster(M) CTAs, A tensor map encoded
                                with dk_gemm_mcast_box_rows(M) rows) */ };
+// With DK_GEMM_SHORT_A, bits 8..15 of `flags` may carry the height of the M tile (a multiple of 8, < 128): the GEMM then
+// runs ceil(M / rows) CTAs along M, each loading only its `rows` rows of A -- at the reference's batch sizes the forward
+// GEMMs are bound by the bytes one SM can ingest, so splitting the 64-row batch over 2-4 CTAs shortens the K loop.
+#define DK_GEMM_TILE_ROWS(r) (((r) & 0xFF) << 8)
+#define DK_GEMM_TILE_ROWS_OF(flags) (((flags) >> 8) & 0xFF)
 
 // Fused epilogue description: out = mask( act( alpha * acc + bias ) )
 typedef struct DkGemmEpilogue {

@@ -250,8 +250,8 @@ __device__ __forceinline__ void gemm_epilogue(const CUtensorMap& tmap_d, const C
 // [128 x 16] fp32 scratch, the (<= 32, co-resident) CTAs of the grid meet on a counter, and every CTA then computes
 // softmax / dZ for its rows and its own 16 columns of dH = alpha (dZ W3) * (H > 0).  Replaces the stand-alone head
 // kernel (one launch + one dependent-kernel latency per step in the small-batch regime).
-__device__ __forceinline__ void gemm_epilogue_head(const GemmEpilogue& ep, const int M, const int N, const int m0,
-                                                   const int n0, const int warp, const int lane,
+__device__ __forceinline__ void gemm_epilogue_head(const GemmEpilogue& ep, const int M, const int m_end, const int N,
+                                                   const int m0, const int n0, const int warp, const int lane,
                                                    const uint32_t tmem_base, uint64_t* tmem_full_bar) {
   // This code runs once per launch: loops over the classes are kept rolled (instruction-cache misses cost more
   // than the loop overhead) and the per-row class vector lives in shared memory, one conflict-free column per thread.
@@ -261,7 +261,7 @@ __device__ __forceinline__ void gemm_epilogue_head(const GemmEpilogue& ep, const
   const int quarter = warp & 3;
   const int tid = (warp - 2) * 32 + lane;        // 0..127 over the four epilogue warps
   const int m = m0 + quarter * 32 + lane;
-  const bool row_ok = m < M;
+  const bool row_ok = m < m_end;      // (M = the whole mini-batch: loss / gradient scale; m_end = end of this CTA's M tile)
   const int C = ep.head_c;
   for (int idx = tid; idx < 256; idx += 128) {
     const int c = idx >> 4, jj = idx & 15;
@@ -283,7 +283,7 @@ __device__ __forceinline__ void gemm_epilogue_head(const GemmEpilogue& ep, const
   // readers belonged to launch L - 1 -- so nothing has to be cleaned up on the way out.
   const unsigned launch = *reinterpret_cast<volatile const unsigned*>(ep.head_sync + 1);
   float* const acc = ep.head_acc + (launch & 1u) * (128 * 16);
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
     float4* nxt = reinterpret_cast<float4*>(ep.head_acc + ((launch + 1u) & 1u) * (128 * 16));
     for (int i4 = tid; i4 < 128 * 16 / 4; i4 += 128) nxt[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -356,7 +356,7 @@ __device__ __forceinline__ void gemm_epilogue_head(const GemmEpilogue& ep, const
   // ---- rendezvous of the grid's epilogue warps (warps without live rows only arrive) ----
   trace_stamp(trw, 8);
   __syncwarp();
-  const unsigned target = (launch + 1u) * (gridDim.x * 4u);
+  const unsigned target = (launch + 1u) * (gridDim.x * gridDim.y * 4u);
   if (lane == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ep.head_sync) : "memory");   // cumulative over the warp's reds
     unsigned seen;
@@ -447,7 +447,7 @@ __device__ __forceinline__ void gemm_epilogue_head(const GemmEpilogue& ep, const
   trace_stamp(trw, 12);
   if (blockIdx.x == 0 && ep.head_hist != nullptr) {
     const float l = warp_sum(row_loss), cr = warp_sum(correct);
-    if (lane == 0 && m0 + quarter * 32 < M) {
+    if (lane == 0 && m0 + quarter * 32 < m_end) {
       if (slot < 0) slot = 0;
       if (ep.head_hist_slots > 0) slot %= ep.head_hist_slots;
       const float inv_b = 1.f / static_cast<float>(M);
@@ -456,7 +456,7 @@ __device__ __forceinline__ void gemm_epilogue_head(const GemmEpilogue& ep, const
     }
   }
   // ---- one thread publishes the launch count for the next launch (kernel boundary orders it) ----
-  if (blockIdx.x == 0 && warp == 2 && lane == 0) ep.head_sync[1] = launch + 1u;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) ep.head_sync[1] = launch + 1u;
   trace_stamp(trw, 13);
 }
 
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 2 : 1))
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
                const GemmEpilogue ep, const int M, const int N, const int K, const int kb_per_split,
-               const int a_box_rows, const int cluster) {
+               const int a_box_rows, const int cluster, const int tile_m) {
   using S = GemmSmem<BN, STAGES, TF32>;
   // cluster > 1 (DK_GEMM_MCAST_A): the CTAs of a cluster are neighbours along N and read the SAME A tile -- each loads
   // a_box_rows / cluster rows of every k-block and multicasts them into all CTAs' stages; a stage is free again when
@@ -507,7 +507,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * kBlockM;
+  const int m0 = blockIdx.y * tile_m;          // tile_m < 128 (DK_GEMM_TILE_ROWS): short M tiles, rows past it are not this CTA's
+  const int m_end = min(M, m0 + tile_m);
   const int total_kb = (K + kBlockK - 1) / kBlockK;
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(total_kb, kb_begin + kb_per_split);
@@ -622,12 +623,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     bool head_done = false;
     if constexpr (BN == 16 && !TF32 && !AMN && !BMN) {
       if (ep.head_w != nullptr) {
-        gemm_epilogue_head(ep, M, N, m0, n0, warp, lane, tmem_base, tmem_full_bar);
+        gemm_epilogue_head(ep, M, m_end, N, m0, n0, warp, lane, tmem_base, tmem_full_bar);
         head_done = true;
       }
     }
     if (!head_done)
-      gemm_epilogue<BN>(tmap_d, tmap_m, ep, M, N, m0, n0, warp, lane, tmem_base, smem, tmem_full_bar, mask_bar);
+      gemm_epilogue<BN>(tmap_d, tmap_m, ep, m_end, N, m0, n0, warp, lane, tmem_base, smem, tmem_full_bar, mask_bar);
     tcgen05_fence_before();
     if (warp == 2 && lane == 0) trace_stamp(tr, 6);
   }
@@ -1290,6 +1291,7 @@ struct GemmLaunch {
   int M, N, K, splits;
   int a_box_rows = kBlockM;
   int cluster = 1;   // DK_GEMM_MCAST_A: CTAs per cluster sharing (and multicasting) the A tile
+  int tile_m = kBlockM;   // DK_GEMM_TILE_ROWS: height of the M tile (short tiles: several CTAs along M for M < 128)
   cudaStream_t stream;
 };
 
@@ -1322,18 +1324,19 @@ static int launch_gemm(const GemmLaunch& L) {
   ep.tma_store = (L.td != nullptr && fits && wide && ep.dt == nullptr) ? 1 : 0;
   ep.tma_mask = (L.tm != nullptr && ep.tma_store && BN >= 64) ? 1 : 0;
   if (splits > 1 && !ep.d_fp32) return -6;
-  dim3 grid((N + BN - 1) / BN, (M + kBlockM - 1) / kBlockM, splits);
+  dim3 grid((N + BN - 1) / BN, (M + L.tile_m - 1) / L.tile_m, splits);
+  if (L.tile_m != kBlockM && (ep.tma_store || ep.tma_mask || AMN || splits > 1)) return -8;   // short tiles: direct-store epilogue only
   if (L.cluster > 1) {
     if (AMN || splits > 1 || grid.y != 1) return -8;
     grid.x = (grid.x + L.cluster - 1) / L.cluster * L.cluster;   // whole clusters; the extra CTAs' tiles are clipped
     DK_HOST_CHECK(launch_kernel_cluster(kern, grid, dim3(kGemmThreads), S::kTotal, stream, static_cast<unsigned>(L.cluster), ta, tb,
                                         ep.tma_store ? *L.td : ta, ep.tma_mask ? *L.tm : ta, ep, M, N, K, kb_per_split,
-                                        L.a_box_rows, L.cluster));
+                                        L.a_box_rows, L.cluster, L.tile_m));
     DK_HOST_CHECK(cudaGetLastError());
     return 0;
   }
   DK_HOST_CHECK(DK_LAUNCH(kern, grid, kGemmThreads, S::kTotal, stream, ta, tb, ep.tma_store ? *L.td : ta, ep.tma_mask ? *L.tm : ta, ep, M,
-                                                  N, K, kb_per_split, L.a_box_rows, 1));
+                                                  N, K, kb_per_split, L.a_box_rows, 1, L.tile_m));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1900,7 +1903,8 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
   const bool tf32 = flags & DK_GEMM_TF32, amn = flags & DK_GEMM_A_MN, bmn = flags & DK_GEMM_B_MN;
   if (ep->head_w != nullptr) {
     // fused classifier head: plain bn = 16 kernel, one M tile, a grid small enough to be co-resident
-    if (bn != 16 || M > dk::kBlockM || splits > 1 || (flags & ~(DK_GEMM_SHORT_A | DK_GEMM_MCAST_A)) != 0 || (N + 15) / 16 > 32 || N % 8 != 0 ||
+    if (bn != 16 || M > dk::kBlockM || splits > 1 || (flags & ~(DK_GEMM_SHORT_A | DK_GEMM_MCAST_A | 0xFF00)) != 0 ||
+        ((N + 15) / 16) * (DK_GEMM_TILE_ROWS_OF(flags) ? (M + DK_GEMM_TILE_ROWS_OF(flags) - 1) / DK_GEMM_TILE_ROWS_OF(flags) : 1) > 64 || N % 8 != 0 ||
         ep->head_c > 16 || ep->head_c < 1 || ep->head_labels == nullptr || ep->head_acc == nullptr ||
         ep->head_sync == nullptr || ep->d_fp32 || ep->dt != nullptr || ep->mask != nullptr || ep->bias_along_m ||
         (ep->ldd % 8) != 0 || (ep->head_lddh % 8) != 0 || (ep->head_ldz % 8) != 0)
@@ -1911,8 +1915,14 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
     L.tm = nullptr;
   }
   if (flags & DK_GEMM_SHORT_A) {
-    if ((flags & (DK_GEMM_PAIR | DK_GEMM_PERSISTENT | DK_GEMM_A_MN)) || M > dk::kBlockM) return -8;  // plain kernel, one M tile
+    if ((flags & (DK_GEMM_PAIR | DK_GEMM_PERSISTENT | DK_GEMM_A_MN)) || M > dk::kBlockM) return -8;  // plain kernel, M <= 128
     L.a_box_rows = dk_gemm_a_box_rows(M);
+    const int tr = DK_GEMM_TILE_ROWS_OF(flags);
+    if (tr != 0) {
+      if (tr % 8 != 0 || tr >= dk::kBlockM || (flags & DK_GEMM_MCAST_A)) return -8;
+      L.a_box_rows = tr;
+      L.tile_m = tr;
+    }
     if (flags & DK_GEMM_MCAST_A) {
       L.cluster = dk_gemm_mcast_cluster(M);
       if (splits > 1 || tf32 || bmn) return -8;
@@ -2030,7 +2040,8 @@ int dk_gemm_encode_operands(void* tmap_a, void* tmap_b, const void* A, long lda,
   const int dt = (flags & DK_GEMM_TF32) ? DK_F32 : DK_BF16;
   int r = (flags & DK_GEMM_A_MN) ? dk_tmap_encode_2d(tmap_a, A, dt, K, M, lda, 64)
                                  : dk_tmap_encode_2d(tmap_a, A, dt, M, K, lda,
-                                                     (flags & DK_GEMM_MCAST_A) ? dk_gemm_mcast_box_rows(M)
+                                                     DK_GEMM_TILE_ROWS_OF(flags) ? DK_GEMM_TILE_ROWS_OF(flags)
+                                                     : (flags & DK_GEMM_MCAST_A) ? dk_gemm_mcast_box_rows(M)
                                                      : (flags & DK_GEMM_SHORT_A) ? dk_gemm_a_box_rows(M) : dk::kBlockM);
   if (r != 0) return r;
   return (flags & DK_GEMM_B_MN) ? dk_tmap_encode_2d(tmap_b, B, dt, K, N, ldb, 64)

@@ -662,6 +662,15 @@ class NativeReplica(Replica):
             # each k-block and multicast it, so an SM ingests its weights plus an eighth of the activations
             if fl and bn == 16 and os.environ.get("DK_GEMM_MCAST", "0") == "1" and self.lib.dk_gemm_mcast_cluster(rows) > 1:
                 fl |= N.GEMM_MCAST_A
+            elif fl and bn == 16 and os.environ.get("DK_SPLIT_M", "1") != "0":
+                # the K loop of these GEMMs is bound by the bytes ONE SM can ingest (~50 GB/s): split the mini-batch
+                # over 2 or 4 CTAs along M while the grid still fits the SMs (rows per CTA in bits 8..15 of the flags)
+                n_tiles = (Nout + 15) // 16
+                for split in (4, 2):
+                    tr = rows // split
+                    if rows % split == 0 and tr % 8 == 0 and n_tiles * split <= min(148, 64 if lst in self._train_lists and bi + 2 == len(self.blocks) else 148):
+                        fl |= tr << 8
+                        break
             if lst in self._train_lists and bn == 16 and a_in.get("slot") is None:
                 fh = self._plan_head_in_forward(b, bi, rows, Nout)
                 if fh is not None:
