@@ -327,6 +327,16 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
       : "memory");
 }
 
+// 3-D tiled load (used with the [64 elements, rows, k-chunks] view of a K-major operand: several k-blocks per request)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ---- cluster multicast (cta_group::1 kernels whose CTAs share an operand tile) ----
 // TMA load whose box lands at the same shared-memory offset in every CTA of `mask`; each destination CTA's mbarrier
 // (same offset) is credited with the box's bytes.

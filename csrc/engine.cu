@@ -140,6 +140,12 @@ int run_op(Engine* e, Op& op, void* main_stream) {
                                   : (a[4] & DK_GEMM_MCAST_A) ? dk_gemm_mcast_box_rows((int)a[0])
                                   : (a[4] & DK_GEMM_SHORT_A) ? dk_gemm_a_box_rows((int)a[0]) : 128);
         if (r != 0) return r;
+        if (DK_GEMM_KCH_OF(a[4]) > 1) {
+          r = dk_tmap_encode_kchunks(&op.td, e->slots[op.dyn_a_slot], a[0], a[2], op.dyn_lda,
+                                     DK_GEMM_TILE_ROWS_OF(a[4]) ? (int)DK_GEMM_TILE_ROWS_OF(a[4]) : dk_gemm_a_box_rows((int)a[0]),
+                                     (int)DK_GEMM_KCH_OF(a[4]));
+          if (r != 0) return r;
+        }
       }
       if (op.ep.head_w != nullptr && op.ep.head_label_slot >= 0)
         op.ep.head_labels = reinterpret_cast<const int*>(e->slots[op.ep.head_label_slot]);
@@ -392,8 +398,19 @@ int dk_engine_add_gemm(void* h, int list, const void* A, long lda, const void* B
   int r = dk_gemm_encode_operands(&op.ta, &op.tb, A, lda, B, ldb, M, N, K, bn, flags);
   if (r != 0) return r;
   op.ep = *ep;
-  op.has_td = ep->d != nullptr && dk_gemm_encode_output(&op.td, ep->d, ep->ldd, M, N, ep->d_fp32) == 0;
-  op.has_tm = ep->mask != nullptr && dk_gemm_encode_output(&op.tm, ep->mask, ep->ld_mask, M, N, 0) == 0;
+  if (DK_GEMM_KCH_OF(flags) > 1) {
+    // several k-blocks per TMA request: the two extra tensor-map slots carry the 3-D [64, rows, k-chunks] operand views
+    const int kch = DK_GEMM_KCH_OF(flags);
+    const int a_rows = DK_GEMM_TILE_ROWS_OF(flags) ? DK_GEMM_TILE_ROWS_OF(flags) : dk_gemm_a_box_rows(M);
+    if ((flags & (DK_GEMM_A_MN | DK_GEMM_B_MN | DK_GEMM_TF32)) || !(flags & DK_GEMM_SHORT_A)) return -6;
+    r = dk_tmap_encode_kchunks(&op.td, A, M, K, lda, a_rows, kch);
+    if (r == 0) r = dk_tmap_encode_kchunks(&op.tm, B, N, K, ldb, bn, kch);
+    if (r != 0) return r;
+    op.has_td = op.has_tm = 1;
+  } else {
+    op.has_td = ep->d != nullptr && dk_gemm_encode_output(&op.td, ep->d, ep->ldd, M, N, ep->d_fp32) == 0;
+    op.has_tm = ep->mask != nullptr && dk_gemm_encode_output(&op.tm, ep->mask, ep->ld_mask, M, N, 0) == 0;
+  }
   if (splits == 0)  // auto: split-K only for plain fp32 accumulations (wgrad)
     splits = (ep->d_fp32 && ep->bias == nullptr && ep->act == 0 && ep->mask == nullptr)
                  ? dk_gemm_pick_splits(M, N, K, bn, flags & DK_GEMM_TF32)

@@ -20,6 +20,13 @@ enum { DK_GEMM_TF32 = 1, DK_GEMM_A_MN = 2, DK_GEMM_B_MN = 4, DK_GEMM_PERSISTENT 
 // GEMMs are bound by the bytes one SM can ingest, so splitting the 64-row batch over 2-4 CTAs shortens the K loop.
 #define DK_GEMM_TILE_ROWS(r) (((r) & 0xFF) << 8)
 #define DK_GEMM_TILE_ROWS_OF(flags) (((flags) >> 8) & 0xFF)
+// Bits 16..19: k-blocks per TMA request (plain kernel, K-major bf16 operands, bn <= 32).  A cp.async.bulk.tensor costs
+// ~190 cycles of TMA-unit time whatever its size (tools/microbench/tma_request.cu), so a short-M GEMM that issues one A and
+// one B request per 64-wide k-block is request-bound; with kch > 1 a pipeline stage holds kch k-blocks, filled by ONE 3-D
+// request per operand (tensor viewed as [64 elements, rows, k-chunks]; maps passed in the tmap_d / tmap_m arguments, encoded
+// by dk_tmap_encode_kchunks); the K tail (a partial last chunk cannot be expressed in that view) falls back to 2-D requests.
+#define DK_GEMM_KCH(n) (((n) & 0xF) << 16)
+#define DK_GEMM_KCH_OF(flags) (((flags) >> 16) & 0xF)
 
 // Fused epilogue description: out = mask( act( alpha * acc + bias ) )
 typedef struct DkGemmEpilogue {
@@ -77,6 +84,7 @@ extern "C" {
 // leading dimension ld (elements), box = [box_rows, 128 bytes], SWIZZLE_128B, zero OOB fill.
 int dk_tmap_encode_2d(void* out_tmap, const void* base, int dtype, long rows, long cols, long ld,
                       int box_rows);
+int dk_tmap_encode_kchunks(void* out_tmap, const void* base, long rows, long K, long ld, int box_rows, int kch);
 int dk_gemm_pick_bn(int N);
 int dk_gemm_a_box_rows(int M);
 int dk_gemm_mcast_cluster(int M);    // CTAs per cluster for DK_GEMM_MCAST_A (1 = no multicast possible)

@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 2 : 1))
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
                const GemmEpilogue ep, const int M, const int N, const int K, const int kb_per_split,
-               const int a_box_rows, const int cluster, const int tile_m) {
+               const int a_box_rows, const int cluster, const int tile_m, const int kch) {
   using S = GemmSmem<BN, STAGES, TF32>;
   // cluster > 1 (DK_GEMM_MCAST_A): the CTAs of a cluster are neighbours along N and read the SAME A tile -- each loads
   // a_box_rows / cluster rows of every k-block and multicasts them into all CTAs' stages; a stage is free again when
@@ -518,8 +518,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if (ep.tma_store) tma_prefetch_desc(&tmap_d);
-    if (ep.tma_mask) tma_prefetch_desc(&tmap_m);
+    if (ep.tma_store || kch > 1) tma_prefetch_desc(&tmap_d);
+    if (ep.tma_mask || kch > 1) tma_prefetch_desc(&tmap_m);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], cluster > 1 ? cluster : 1);
@@ -550,6 +550,32 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const int rows_per = cluster > 1 ? a_box_rows / cluster : 0;
+      if (kch > 1) {
+        // ---- several k-blocks per request (DK_GEMM_KCH): tmap_d / tmap_m are the 3-D views of A / B ----
+        const int a_chunk = a_stage_bytes, b_chunk = S::kBBytes, stage_bytes = kch * (a_chunk + b_chunk);
+        const int nst = min(STAGES, STAGES * S::kStageBytes / stage_bytes);
+        const int groups = (total_kb + kch - 1) / kch;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + kch * a_chunk;
+          const int nch = min(kch, total_kb - g * kch);
+          mbar_expect_tx(&full_bar[stage], nch * (a_chunk + b_chunk));
+          if ((g + 1) * kch * kBlockK <= K) {          // every chunk of the group is fully inside K: one request each
+            tma_load_3d(sa, &tmap_d, 0, m0, g * kch, &full_bar[stage]);
+            tma_load_3d(sb, &tmap_m, 0, n0, g * kch, &full_bar[stage]);
+          } else {                                      // K tail: per-chunk 2-D requests (out-of-range columns zero-filled)
+            for (int c = 0; c < nch; ++c) {
+              tma_load_2d(sa + c * a_chunk, &tmap_a, (g * kch + c) * kBlockK, m0, &full_bar[stage]);
+              tma_load_2d(sb + c * b_chunk, &tmap_b, (g * kch + c) * kBlockK, n0, &full_bar[stage]);
+            }
+          }
+          if (++stage == nst) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      } else
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStageBytes;
@@ -583,6 +609,35 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ------------------------------ MMA issuer --------------------------------
     int stage = 0;
     uint32_t phase = 0;
+    if (kch > 1) {
+      const int a_chunk = a_stage_bytes, b_chunk = S::kBBytes, stage_bytes = kch * (a_chunk + b_chunk);
+      const int nst = min(STAGES, STAGES * S::kStageBytes / stage_bytes);
+      const int groups = (total_kb + kch - 1) / kch;
+      for (int g = 0; g < groups; ++g) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (g == 0 && lane == 0) trace_stamp(tr, 3);
+        if (g == groups - 1 && lane == 0) trace_stamp(tr, 4);
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + kch * a_chunk;
+          const int nch = min(kch, total_kb - g * kch);
+          for (int c = 0; c < nch; ++c) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + c * a_chunk);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + c * b_chunk);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (g | c | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (g == groups - 1) umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+        if (++stage == nst) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    } else
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tcgen05_fence_after();
@@ -1292,6 +1347,7 @@ struct GemmLaunch {
   int a_box_rows = kBlockM;
   int cluster = 1;   // DK_GEMM_MCAST_A: CTAs per cluster sharing (and multicasting) the A tile
   int tile_m = kBlockM;   // DK_GEMM_TILE_ROWS: height of the M tile (short tiles: several CTAs along M for M < 128)
+  int kch = 0;            // DK_GEMM_KCH: k-blocks per TMA request (td / tm then carry the 3-D operand views)
   cudaStream_t stream;
 };
 
@@ -1326,17 +1382,26 @@ static int launch_gemm(const GemmLaunch& L) {
   if (splits > 1 && !ep.d_fp32) return -6;
   dim3 grid((N + BN - 1) / BN, (M + L.tile_m - 1) / L.tile_m, splits);
   if (L.tile_m != kBlockM && (ep.tma_store || ep.tma_mask || AMN || splits > 1)) return -8;   // short tiles: direct-store epilogue only
+  const int kch = L.kch > 1 ? L.kch : 0;
+  if (kch) {
+    // stages of kch k-blocks must fit the kernel's shared-memory pool at least twice; td / tm are operand views here
+    if (TF32 || AMN || BMN || BN > 32 || splits > 1 || L.cluster > 1 || L.td == nullptr || L.tm == nullptr ||
+        2 * kch * (L.a_box_rows * 128 + S::kBBytes) > STAGES * S::kStageBytes)
+      return -8;
+    ep.tma_store = 0;
+    ep.tma_mask = 0;
+  }
   if (L.cluster > 1) {
     if (AMN || splits > 1 || grid.y != 1) return -8;
     grid.x = (grid.x + L.cluster - 1) / L.cluster * L.cluster;   // whole clusters; the extra CTAs' tiles are clipped
     DK_HOST_CHECK(launch_kernel_cluster(kern, grid, dim3(kGemmThreads), S::kTotal, stream, static_cast<unsigned>(L.cluster), ta, tb,
                                         ep.tma_store ? *L.td : ta, ep.tma_mask ? *L.tm : ta, ep, M, N, K, kb_per_split,
-                                        L.a_box_rows, L.cluster, L.tile_m));
+                                        L.a_box_rows, L.cluster, L.tile_m, 0));
     DK_HOST_CHECK(cudaGetLastError());
     return 0;
   }
-  DK_HOST_CHECK(DK_LAUNCH(kern, grid, kGemmThreads, S::kTotal, stream, ta, tb, ep.tma_store ? *L.td : ta, ep.tma_mask ? *L.tm : ta, ep, M,
-                                                  N, K, kb_per_split, L.a_box_rows, 1, L.tile_m));
+  DK_HOST_CHECK(DK_LAUNCH(kern, grid, kGemmThreads, S::kTotal, stream, ta, tb, (ep.tma_store || kch) ? *L.td : ta,
+                          (ep.tma_mask || kch) ? *L.tm : ta, ep, M, N, K, kb_per_split, L.a_box_rows, 1, L.tile_m, kch));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1845,6 +1910,23 @@ int dk_tmap_encode_2d(void* out_tmap, const void* base, int dtype, long rows, lo
 // Rows of the TMA box of a K-major A operand: a single short M tile (M < 128, the small-batch regime) is
 // loaded with a box of just ceil8(M) rows -- half the shared-memory fill of a 128-row box whose rows past M
 // would only be zero-filled; the accumulator rows past M are never stored.
+// [rows, K] row-major bf16 operand viewed as [64 elements, rows, K / 64 full chunks]: box = [64, box_rows, kch]
+int dk_tmap_encode_kchunks(void* out_tmap, const void* base, long rows, long K, long ld, int box_rows, int kch) {
+  auto fn = dk::get_encode_fn();
+  if (fn == nullptr) return -1;
+  const long full = K / 64;
+  if (full < 1 || kch < 1 || kch > 16 || box_rows < 1 || box_rows > 256) return -3;
+  if ((ld * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return -2;
+  cuuint64_t gdim[3] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(full)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, 128};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(kch)};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_tmap), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim,
+                  gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -4;
+}
+
 int dk_gemm_a_box_rows(int M) {
   if (M >= dk::kBlockM) return dk::kBlockM;
   return (M + 7) / 8 * 8;
@@ -1903,7 +1985,7 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
   const bool tf32 = flags & DK_GEMM_TF32, amn = flags & DK_GEMM_A_MN, bmn = flags & DK_GEMM_B_MN;
   if (ep->head_w != nullptr) {
     // fused classifier head: plain bn = 16 kernel, one M tile, a grid small enough to be co-resident
-    if (bn != 16 || M > dk::kBlockM || splits > 1 || (flags & ~(DK_GEMM_SHORT_A | DK_GEMM_MCAST_A | 0xFF00)) != 0 ||
+    if (bn != 16 || M > dk::kBlockM || splits > 1 || (flags & ~(DK_GEMM_SHORT_A | DK_GEMM_MCAST_A | 0xFFF00)) != 0 ||
         ((N + 15) / 16) * (DK_GEMM_TILE_ROWS_OF(flags) ? (M + DK_GEMM_TILE_ROWS_OF(flags) - 1) / DK_GEMM_TILE_ROWS_OF(flags) : 1) > 64 || N % 8 != 0 ||
         ep->head_c > 16 || ep->head_c < 1 || ep->head_labels == nullptr || ep->head_acc == nullptr ||
         ep->head_sync == nullptr || ep->d_fp32 || ep->dt != nullptr || ep->mask != nullptr || ep->bias_along_m ||
@@ -1911,9 +1993,13 @@ int dk_gemm_tn_launch2(const void* tmap_a, const void* tmap_b, const void* tmap_
       return -9;
     L.ep.tma_store = 0;
     L.ep.tma_mask = 0;
-    L.td = nullptr;
-    L.tm = nullptr;
+    if (DK_GEMM_KCH_OF(flags) <= 1) {   // (with DK_GEMM_KCH the two extra maps are operand views, not output / mask maps)
+      L.td = nullptr;
+      L.tm = nullptr;
+    }
   }
+  L.kch = DK_GEMM_KCH_OF(flags);
+  if (L.kch > 1 && (flags & (DK_GEMM_PAIR | DK_GEMM_PERSISTENT | DK_GEMM_A_MN | DK_GEMM_B_MN | DK_GEMM_TF32 | DK_GEMM_MCAST_A))) return -8;
   if (flags & DK_GEMM_SHORT_A) {
     if ((flags & (DK_GEMM_PAIR | DK_GEMM_PERSISTENT | DK_GEMM_A_MN)) || M > dk::kBlockM) return -8;  // plain kernel, M <= 128
     L.a_box_rows = dk_gemm_a_box_rows(M);

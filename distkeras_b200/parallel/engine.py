@@ -533,6 +533,23 @@ class NativeReplica(Replica):
             dz=self._buf(rows, ldz), ldz=ldz, dh=self._buf(rows, Nout))
         return self._fwd_head
 
+    @staticmethod
+    def _pick_kch(K: int, a_rows: int, bn: int = 16, pool: int = 12 * 18432) -> int:
+        """k-blocks per TMA request for a short-M forward GEMM (``DK_GEMM_KCH``): groups of ``kch`` whole 64-wide
+        chunks go out as one 3-D request per operand, the K tail as 2-D requests; pick the ``kch`` with the fewest
+        requests whose stage fits the kernel's shared-memory pool at least twice (0 = keep one k-block per request)."""
+        full, total = K // 64, -(-K // 64)
+        per = a_rows * 128 + bn * 128
+        best, best_req = 0, 2 * total
+        # requests up to ~16 KB cost the same TMA service time; bigger ones delay the first MMA (nothing of a request can
+        # be consumed before all of it has landed)
+        cap = max(2, 16384 // (max(a_rows, bn) * 128))
+        for kch in range(2, min(15, full, cap, pool // (2 * per)) + 1):
+            req = 2 * (full // kch) + 2 * (total - (full // kch) * kch)
+            if req < best_req:
+                best, best_req = kch, req
+        return best
+
     def _bn_slice(self, floats: int) -> int:
         ptr = self._bn_scratch.data_ptr() + 4 * self._bn_used
         self._bn_used += floats
@@ -666,11 +683,16 @@ class NativeReplica(Replica):
                 # the K loop of these GEMMs is bound by the bytes ONE SM can ingest (~50 GB/s): split the mini-batch
                 # over 2 or 4 CTAs along M while the grid still fits the SMs (rows per CTA in bits 8..15 of the flags)
                 n_tiles = (Nout + 15) // 16
+                a_rows = _r8(rows)
                 for split in (4, 2):
                     tr = rows // split
                     if rows % split == 0 and tr % 8 == 0 and n_tiles * split <= min(148, 64 if lst in self._train_lists and bi + 2 == len(self.blocks) else 148):
                         fl |= tr << 8
+                        a_rows = tr
                         break
+            if fl and bn == 16 and not (fl & N.GEMM_MCAST_A) and os.environ.get("DK_GEMM_KCH", "1") != "0":
+                # a TMA request costs ~190 cycles whatever its size: load several 64-wide k-blocks per request (3-D view)
+                fl |= self._pick_kch(K, a_rows if fl >> 8 else _r8(rows)) << 16
             if lst in self._train_lists and bn == 16 and a_in.get("slot") is None:
                 fh = self._plan_head_in_forward(b, bi, rows, Nout)
                 if fh is not None:
