@@ -72,8 +72,12 @@ template <int BN, int STAGES, int KBYTES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_m,
-                const GemmEpilogue ep, const ConvGeom g, const int M, const int N) {
+                const GemmEpilogue ep, const ConvGeom g, const int M, const int N, const int wres) {
   using S = ConvTmaSmem<BN, STAGES, KBYTES>;
+  // wres: the layer has ONE tile along N and its whole weight matrix fits next to the pipeline, so every k-block's B
+  // tile is loaded once per CTA (num_kb requests in total) instead of once per k-block of every tile -- a TMA request
+  // costs ~190 cycles whatever its size, and with 9 taps x (A + B) requests per 128-pixel tile this kernel is
+  // request-bound.  The stage pool then holds [resident weights | A-only stages].
   constexpr int kKElems = KBYTES / 2;      // bf16 channels per k-block
   constexpr int kMmaPerStage = kKElems / 16;
   constexpr uint32_t kTmemCols = 2 * BN;   // two accumulators
@@ -90,11 +94,16 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint64_t* mask_bar = tmem_empty_bar + 2;        // [8 epilogue warps]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 8);
+  uint64_t* w_bar = mask_bar + 8;                 // resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = g.taps * g.c_chunks;
+  const int wres_bytes = wres ? num_kb * S::kBBytes : 0;
+  const int a_stride = wres ? S::kABytes : S::kStageBytes;          // bytes between pipeline stages
+  const int nst = wres ? min(STAGES, (STAGES * S::kStageBytes - wres_bytes) / S::kABytes) : STAGES;
+  uint8_t* stages = smem + wres_bytes;
   const int n_tiles = (N + BN - 1) / BN;
   const int m_tiles = (M + kConvBlockM - 1) / kConvBlockM;
   const int num_tiles = n_tiles * m_tiles;
@@ -113,6 +122,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_init(&tmem_empty_bar[a], 8);
     }
     for (int i = 0; i < 8; ++i) mbar_init(&mask_bar[i], 1);
+    mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -131,6 +141,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      if (wres) {
+        mbar_expect_tx(w_bar, wres_bytes);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem + kb * S::kBBytes, &tmap_b, kb * kKElems, 0, w_bar);
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * kConvBlockM, n0 = (tile % n_tiles) * BN;
         // first output position of the tile -> base pixel of its receptive field
@@ -141,17 +155,17 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         int tap = 0, cc = 0, kh = 0, kw = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sa = stages + stage * a_stride;
           uint8_t* sb = sa + S::kABytes;
-          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          mbar_expect_tx(&full_bar[stage], wres ? S::kABytes : S::kStageBytes);
           tma_load_im2col_4d(sa, &tmap_a, cc * kKElems, w0, h0, b, kw, kh, &full_bar[stage]);
-          tma_load_2d(sb, &tmap_b, kb * kKElems, n0, &full_bar[stage]);
+          if (!wres) tma_load_2d(sb, &tmap_b, kb * kKElems, n0, &full_bar[stage]);
           if (++cc == g.c_chunks) {
             cc = 0;
             ++tap;
             if (++kw == g.KW) { kw = 0; ++kh; }
           }
-          if (++stage == STAGES) {
+          if (++stage == nst) {
             stage = 0;
             phase ^= 1;
           }
@@ -163,6 +177,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    if (wres) mbar_wait(w_bar, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);
@@ -172,16 +187,16 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sa = smem_u32(stages + stage * a_stride);
           const uint64_t adesc = make_kmajor_desc<KBYTES>(sa);
-          const uint64_t bdesc = make_kmajor_desc<KBYTES>(sa + S::kABytes);
+          const uint64_t bdesc = make_kmajor_desc<KBYTES>(wres ? smem_u32(smem + kb * S::kBBytes) : sa + S::kABytes);
 #pragma unroll
           for (int k = 0; k < kMmaPerStage; ++k) umma_f16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
           umma_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);
         }
         __syncwarp();
-        if (++stage == STAGES) {
+        if (++stage == nst) {
           stage = 0;
           phase ^= 1;
         }
@@ -530,7 +545,15 @@ static int launch_conv_tma(const CUtensorMap* ta, const CUtensorMap* tb, const C
   ep.tma_mask = tm != nullptr ? 1 : 0;
   const int tiles = ((M + kConvBlockM - 1) / kConvBlockM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count[dev & 63] ? tiles : sm_count[dev & 63];
-  DK_HOST_CHECK(DK_LAUNCH(kern, grid, kConvThreads, S::kTotal, stream, *ta, *tb, *td, ep.tma_mask ? *tm : *ta, ep, g, M, N));
+  // resident weights: one tile along N, the weight matrix + at least two A stages fit the stage pool (DK_CONV_WRES=0: off)
+  static int wres_env = -1;
+  if (wres_env < 0) {
+    const char* we = getenv("DK_CONV_WRES");
+    wres_env = (we != nullptr && we[0] == '0') ? 0 : 1;
+  }
+  const int num_kb = g.taps * g.c_chunks;
+  const int wres = (wres_env && N <= BN && num_kb * S::kBBytes + 2 * S::kABytes <= STAGES * S::kStageBytes) ? 1 : 0;
+  DK_HOST_CHECK(DK_LAUNCH(kern, grid, kConvThreads, S::kTotal, stream, *ta, *tb, *td, ep.tma_mask ? *tm : *ta, ep, g, M, N, wres));
   DK_HOST_CHECK(cudaGetLastError());
   return 0;
 }
