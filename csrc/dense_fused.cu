@@ -48,7 +48,8 @@ constexpr int kBwdStages = 2;  // GEMM-K = the mini-batch: one or two 64-row k-b
 enum { kStW = 0, kStS0 = 1, kStS1 = 2, kStW1 = 3, kStWb = 4 };
 struct StateMaps {
   alignas(64) CUtensorMap ld[4];  // W, s0, s1, W1: fp32 [n_out, k_in], box 32 cols x 128 rows, SWIZZLE_128B
-  alignas(64) CUtensorMap st[5];  // W, s0, s1, W1: box 32 x 32; Wb: bf16 box 64 cols x 32 rows
+  alignas(64) CUtensorMap st[5];  // W, s0, s1, W1: box 32 x 32; Wb: bf16 box 64 cols x 32 rows (kept for reference / tools)
+  alignas(64) CUtensorMap wb128;  // Wb: bf16 box 64 cols x 128 rows: the whole shadow tile in one store
 };
 
 struct BwdLayerDev {
@@ -303,21 +304,22 @@ __device__ __forceinline__ void bwd_epilogue(const BwdUpdateDev& p, const BwdLay
                        : "memory");
         }
       }
-      // ---- write the slice back: TMA stores out of the swizzled tiles (clipped at the matrix edge) ----
+      // ---- write the half-tile back: ONE TMA store per array for the four warps of this half (a request costs the
+      //      TMA unit ~190 cycles whatever its size: 3 + 3 + 1 stores per tile instead of 8 x 3 + 4), out of the
+      //      swizzled tiles through the same [128 x 32] maps that loaded them (clipped at the matrix edge) ----
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t sub_off = quarter * 4096;
-        tma_store_2d_addr(&ly.maps->st[kStW], tW + sub_off, nbase, mbase);
-        if constexpr (kS0) tma_store_2d_addr(&ly.maps->st[kStS0], tS0 + sub_off, nbase, mbase);
-        if constexpr (kS1) tma_store_2d_addr(&ly.maps->st[kStS1], tS1 + sub_off, nbase, mbase);
-        if (p.comm_mode == DK_COMM_EXCHANGE) tma_store_2d_addr(&ly.maps->st[kStW1], tW1 + sub_off, nbase, mbase);
+      named_bar_sync(5 + half, 128);
+      if (quarter == 0 && lane == 0) {
+        tma_store_2d_addr(&ly.maps->ld[kStW], tW, nbase, m0);
+        if constexpr (kS0) tma_store_2d_addr(&ly.maps->ld[kStS0], tS0, nbase, m0);
+        if constexpr (kS1) tma_store_2d_addr(&ly.maps->ld[kStS1], tS1, nbase, m0);
+        if (p.comm_mode == DK_COMM_EXCHANGE) tma_store_2d_addr(&ly.maps->ld[kStW1], tW1, nbase, m0);
       }
       trace_stamp(tr, 10);
     }
-    // the two halves of a quarter fill one [32 x 128 B] box of the bf16 shadow tile: pair barrier, one store
-    named_bar_sync(1 + quarter, 64);
-    if (half == 0 && lane == 0 && n0 < ly.k_in) tma_store_2d_addr(&ly.maps->st[kStWb], wb_tile + quarter * 4096, n0, mbase);
+    // all eight warps have filled the [128 x 128 B] bf16 shadow tile: one store
+    named_bar_sync(7, 256);
+    if (quarter == 0 && half == 0 && lane == 0 && n0 < ly.k_in) tma_store_2d_addr(&ly.maps->wb128, wb_tile, n0, m0);
     if (ly.wb_pad != nullptr && half == 1) {
       // the TMA store above went to the 8-padded shadow; the flat shadow (rows 8-byte aligned: k_in % 4 == 0) gets the
       // same 32 x 64 slice through plain stores -- half a warp per row, 8 bytes per lane, 128 contiguous bytes per row
@@ -647,6 +649,10 @@ int dk_bwd_update_prepare(void* record, const DkBwdUpdateDesc* d) {
                       ? dk_tmap_encode_2d(&host[l].st[kStWb], reinterpret_cast<__nv_bfloat16*>(d->wb) + sd.w_off, DK_BF16,
                                           sd.n_out, sd.k_in, sd.k_in, 32)
                       : dk_tmap_encode_2d(&host[l].st[kStWb], sd.wb_pad, DK_BF16, sd.n_out, sd.k_in, sd.ldwb_pad, 32)) == 0;
+      ok = ok && (flat_rows_ok
+                      ? dk_tmap_encode_2d(&host[l].wb128, reinterpret_cast<__nv_bfloat16*>(d->wb) + sd.w_off, DK_BF16,
+                                          sd.n_out, sd.k_in, sd.k_in, kBwdBlockM)
+                      : dk_tmap_encode_2d(&host[l].wb128, sd.wb_pad, DK_BF16, sd.n_out, sd.k_in, sd.ldwb_pad, kBwdBlockM)) == 0;
       if (ok) {
         any = true;
         ly.maps = reinterpret_cast<const StateMaps*>(static_cast<uintptr_t>(l + 1));  // patched to the device address below
