@@ -342,7 +342,8 @@ class FabricWorker:
                 raise ValueError(f"region of {n} steps exceeds the staging capacity ({self.n_max})")
             torch.cuda.synchronize(self.rep.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self.compute):
+            # thread_local: the checkpointer / watchdog threads issue their own copies and synchronisations meanwhile
+            with torch.cuda.graph(g, stream=self.compute, capture_error_mode="thread_local"):
                 self._graph_kernels[key], self._graph_exchanges[key] = self._region_program(parity, n, key[2])
             torch.cuda.synchronize(self.rep.device)
             self._graphs[key] = g
