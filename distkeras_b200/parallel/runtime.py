@@ -979,6 +979,12 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
             static = True
             src = dataset.partitions(1)[0] if getattr(trainer, "data_is_local_shard", False) else parts[wid]
             my_parts = [Partition(src.dataset, src.index, src.start, src.start + sync_rows)]
+        use_table = control is not None and sync_rows is None and not getattr(trainer, "data_is_local_shard", False)
+        if use_table and static:
+            # statically assigned partitions are claimed BEFORE the start barrier: a fast rank that runs out of work
+            # must never find a slower peer's partition unclaimed (it would be trained twice)
+            for part in my_parts:
+                control.claim(part.index, rank)
         torch.cuda.synchronize()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -1010,11 +1016,9 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
                     worker.recover()
                     del worker.history[mark:]
 
-        if control is not None and sync_rows is None and not getattr(trainer, "data_is_local_shard", False):
+        if use_table:
             # spawned ranks: claims go through the shard table so the launcher can re-queue a dead rank's work
             if static:
-                for part in my_parts:
-                    control.claim(part.index, rank)
                 for part in my_parts:
                     run_task(part)
                     control.finish(part.index)
