@@ -13,7 +13,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SWITCHES = ("DK_CONV_LDGSTS", "DK_BACKEND", "DK_COMM", "DK_STRICT", "DK_DEDICATED_PS", "DK_LOG", "DK_NVTX", "DK_NUMA", "DK_FAULT",
-            "DK_PERSISTENT", "DK_PAIR", "DK_PDL", "DK_SIDE_STREAMS", "DK_FUSED_HEAD", "DK_IMPLICIT_CONV", "DK_IMPLICIT_WGRAD", "DK_EXPERIMENTAL")
+            "DK_FAULT_KILL", "DK_PERSISTENT", "DK_PAIR", "DK_PDL", "DK_SIDE_STREAMS", "DK_FUSED_HEAD", "DK_IMPLICIT_CONV",
+            "DK_IMPLICIT_WGRAD", "DK_EXPERIMENTAL", "DK_COMPACT", "DK_COMPACT_MAX_BATCH", "DK_HEAD_IN_FWD", "DK_GEMM_KCH",
+            "DK_SPLIT_M", "DK_GEMM_MCAST", "DK_CONV_TMA", "DK_CONV_WRES", "DK_PAD_INPUT_CHANNELS", "DK_BARRIER_TIMEOUT_MS",
+            "DK_TRACE")
 
 
 def info() -> dict:
@@ -24,7 +27,7 @@ def info() -> dict:
     lib_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdistkeras_b200.so")
     out = {"torch": torch.__version__, "cuda_available": torch.cuda.is_available(),
            "native_library": lib_path if os.path.exists(lib_path) else None,
-           "backends": ["thread", "socket"] + (["fabric"] if torch.cuda.is_available() else []),
+           "backends": ["thread", "socket", "nccl"] + (["fabric"] if torch.cuda.is_available() else []),
            "switches": {k: os.environ[k] for k in SWITCHES if k in os.environ}, "devices": []}
     if torch.cuda.is_available():
         for i in range(torch.cuda.device_count()):
