@@ -1018,22 +1018,11 @@ def _rank_train(trainer, dataset: Dataset, rank: int, world: int, exchange_obj, 
 
         if use_table:
             # spawned ranks: claims go through the shard table so the launcher can re-queue a dead rank's work
-            if static:
-                for part in my_parts:
-                    run_task(part)
-                    control.finish(part.index)
-            while True:
-                idx = control.try_claim(rank, n_parts)
-                if idx is not None:
-                    if static:   # only reachable after a peer died: its shard was re-queued
-                        log_event("fabric.requeued_partition", rank=rank, partition=idx)
-                        worker.recover()
-                    run_task(parts[idx])
-                    control.finish(idx)
-                    continue
-                if control.all_done(n_parts):
-                    break
-                time.sleep(0.01)
+            def on_requeue(idx: int) -> None:   # only reachable in static mode after a peer died
+                log_event("fabric.requeued_partition", rank=rank, partition=idx)
+                worker.recover()
+
+            drain_shard_table(control, rank, parts, my_parts if static else None, run_task, on_requeue)
         elif static:
             for part in my_parts:
                 run_task(part)
@@ -1227,6 +1216,31 @@ class LocalControl:
                     self.claimed[i] = 0
                     freed.append(i)
         return freed
+
+
+def drain_shard_table(control: "LocalControl", rank: int, parts: list, my_parts: Optional[list], run_task, on_requeue=None) -> int:
+    """A rank's task loop over the shard table.  ``my_parts`` (static assignment; ALREADY claimed by this rank before the
+    start barrier) are run first; then the rank keeps polling: any partition that is neither done nor claimed -- the
+    dynamic queue, or what the launcher freed after a peer died -- is claimed under the table's lock and run, until
+    every partition is done.  Returns the number of partitions this rank ran."""
+    n_parts = len(parts)
+    ran = 0
+    for part in my_parts or ():
+        run_task(part)
+        control.finish(part.index)
+        ran += 1
+    while True:
+        idx = control.try_claim(rank, n_parts)
+        if idx is not None:
+            if my_parts is not None and on_requeue is not None:
+                on_requeue(idx)
+            run_task(parts[idx])
+            control.finish(idx)
+            ran += 1
+            continue
+        if control.all_done(n_parts):
+            return ran
+        time.sleep(0.01)
 
 
 def _spawn_entry_local(rank: int, world: int, control: LocalControl, payload_path: str, scratch: str) -> None:

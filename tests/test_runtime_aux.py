@@ -166,3 +166,58 @@ def test_local_control_shard_table_and_barrier(tmp_path):
     c3.exchange_obj(0, {"a": 1}, 0)
     th.join(timeout=10)
     assert out["v"] == {"a": 1}
+
+
+@pytest.mark.parametrize("static", [True, False])
+def test_shard_table_runs_every_partition_exactly_once_with_skewed_ranks_and_a_lost_rank(static, tmp_path):
+    """The task loop of the spawned fabric ranks (threads stand in for the processes): ranks reach the start barrier at
+    very different times, one rank dies holding a partition.  Every partition must be trained exactly once by a live
+    rank -- statically assigned ones are claimed BEFORE the barrier, so a fast rank never steals a slow peer's shard."""
+    import random
+    import threading
+    import time
+    from types import SimpleNamespace
+
+    from distkeras_b200.parallel.runtime import LocalControl, drain_shard_table
+
+    world, per_rank = 6, 2
+    n_parts = world * per_rank
+    parts = [SimpleNamespace(index=i) for i in range(n_parts)]
+    control = LocalControl(world, str(tmp_path))
+    start = threading.Barrier(world)
+    runs, lock = [], threading.Lock()
+    dead_rank = 4
+
+    def rank_body(rank):
+        rng = random.Random(rank)
+        time.sleep(rng.random() * 0.3)                          # set-up skew (graph capture, module load)
+        mine = [parts[i] for i in range(rank, n_parts, world)] if static else None
+        for p in mine or ():
+            control.claim(p.index, rank)
+        start.wait()
+
+        def run_task(part):
+            if rank == dead_rank and (not static or part.index == mine[-1].index):
+                raise SystemExit                                # the process vanishes in the middle of this partition
+            time.sleep(0.002 * (1 + rank))
+            with lock:
+                runs.append((part.index, rank))
+
+        try:
+            drain_shard_table(control, rank, parts, mine, run_task)
+        except SystemExit:
+            time.sleep(0.05)                                    # the launcher notices a little later
+            control.alive[rank] = 0
+            control.release_claims_of(rank)
+
+    threads = [threading.Thread(target=rank_body, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=30)
+    assert not any(t.is_alive() for t in threads)
+    assert sorted(i for i, _ in runs) == list(range(n_parts))   # exactly once each
+    assert control.all_done(n_parts)
+    if static:   # nobody but the owner (or, for the orphan, a survivor) touched a statically assigned partition
+        for idx, r in runs:
+            assert r == idx % world or idx % world == dead_rank
