@@ -14,6 +14,7 @@ CASES = [
     ("higgs_workflow.py", ["--rows", "4096"], "DOWNPOUR"),
     ("streaming_inference.py", [], "micro-batch"),
     ("custom_optimizer.py", ["--route", "python", "--rows", "2048"], "ClippedDownpour"),
+    ("kafka_producer.py", ["--sink", "stdout", "--bursts", "2", "--rows", "3", "--interval", "0"], '"features"'),
 ]
 
 
@@ -39,6 +40,7 @@ NOTEBOOKS = [
     ("example_1_analysis.ipynb", {"synthetic_higgs(200000)": "synthetic_higgs(6000)"}),
     ("cifar-10-preprocessing.ipynb", {"synthetic_cifar10(1000": "synthetic_cifar10(100", "synthetic_cifar10(500": "synthetic_cifar10(50"}),
     ("distributed_numpy_parsing.ipynb", {"range(8)": "range(4)"}),
+    ("kafka_spark_high_throughput_ml_pipeline.ipynb", {"synthetic_higgs(20000)": "synthetic_higgs(2048)", "'--rows', '1000'": "'--rows', '200'"}),
 ]
 
 

@@ -291,6 +291,65 @@ NOTEBOOKS["distributed_numpy_parsing"] = [
 ]
 
 
+# ------------------------------------------------------------------------------------------------------------------
+NOTEBOOKS["kafka_spark_high_throughput_ml_pipeline"] = [
+    ("md", "# High-throughput streaming inference\n\nCounterpart of the reference's `kafka_spark_high_throughput_ml_pipeline.ipynb`: a producer "
+           "(`kafka_producer.py`) pushes JSON events to a topic; the pipeline collects them into micro-batches, turns the JSON into rows "
+           "(`json_to_dataframe_row`), standardises the features with the statistics of the training set, scores them with "
+           "`ModelPredictor`, indexes the prediction and keeps the events classified as signal.  There is no broker in this "
+           "sandbox, so the topic is a spool directory (`--sink spool`); with the `kafka` package and a broker the same producer "
+           "takes `--sink kafka`."),
+    ("code", HEADER + "import glob, json, subprocess\n"
+             "from distkeras_b200.data import Dataset, synthetic_higgs\n"
+             "from distkeras_b200.models import Sequential, Dense, Dropout, Activation\n"
+             "from distkeras_b200.trainers import SingleTrainer\n"
+             "from distkeras_b200.predictors import ModelPredictor\n"
+             "from distkeras_b200.transformers import LabelIndexTransformer, OneHotTransformer, StandardTransformer\n"
+             "from distkeras_b200.utils import json_to_dataframe_row\n"
+             "topic = tempfile.mkdtemp(prefix='Machine_Learning_')"),
+    ("md", "## A model to serve\nThe 500-1000-500 perceptron of the reference notebook, trained for one pass on synthetic Higgs events."),
+    ("code", "train = synthetic_higgs(20000)\n"
+             "scaler = StandardTransformer(['features'])\n"
+             "train = OneHotTransformer(2, 'label', 'label_encoded').transform(scaler.transform(train))\n"
+             "mu, sd = scaler.means['features'].clone(), scaler.stddevs['features'].clone()   # statistics of the training set\n"
+             "model = Sequential()\n"
+             "model.add(Dense(500, input_shape=(30,)))\nmodel.add(Activation('relu'))\nmodel.add(Dropout(0.3))\n"
+             "model.add(Dense(1000))\nmodel.add(Activation('relu'))\nmodel.add(Dropout(0.3))\n"
+             "model.add(Dense(500))\nmodel.add(Activation('relu'))\n"
+             "model.add(Dense(2))\nmodel.add(Activation('softmax'))\n"
+             "trainer = SingleTrainer(model, 'adagrad', 'categorical_crossentropy', features_col='features_normalized',\n"
+             "                        label_col='label_encoded', batch_size=64, num_epoch=1)\n"
+             "model = trainer.train(train)\nprint('trained in %.2f s' % trainer.get_training_time())"),
+    ("md", "## Start the producer\nA separate process, as in production: bursts of JSON messages every 0.2 s (5 s in the reference)."),
+    ("code", "producer = subprocess.Popen([sys.executable, 'kafka_producer.py', '--sink', 'spool', '--dir', topic,\n"
+             "                             '--bursts', '5', '--rows', '1000', '--interval', '0.2'])"),
+    ("md", "## The streaming job\nEvery micro-batch interval: read what arrived, JSON -> rows -> `Dataset`, standardise, predict, index, filter."),
+    ("code", "predictor = ModelPredictor(model, features_col='features_normalized')\n"
+             "indexer = LabelIndexTransformer(output_dim=2)\n"
+             "seen, total, signal = set(), 0, 0\n"
+             "t0 = time.time()\n"
+             "while True:\n"
+             "    time.sleep(0.25)                                  # micro-batch interval (10 s in the reference)\n"
+             "    files = sorted(f for f in glob.glob(os.path.join(topic, 'burst_*.jsonl')) if f not in seen)\n"
+             "    rows = []\n"
+             "    for f in files:\n"
+             "        seen.add(f)\n"
+             "        with open(f) as fh:\n"
+             "            rows += [json_to_dataframe_row(line) for line in fh if line.strip()]\n"
+             "    if rows:\n"
+             "        batch = Dataset.from_rows(rows)\n"
+             "        batch = batch.with_column('features_normalized', (batch['features'].float() - mu) / sd)\n"
+             "        out = indexer.transform(predictor.predict(batch))\n"
+             "        hits = out.filter(lambda d: d['prediction_index'] == 1.0).count()\n"
+             "        total, signal = total + batch.count(), signal + hits\n"
+             "        print('micro-batch: %5d events, %5d classified as signal' % (batch.count(), hits))\n"
+             "    elif os.path.exists(os.path.join(topic, '_DONE')):\n"
+             "        break\n"
+             "producer.wait()\n"
+             "print('%d events in %.2f s -> %.0f events/s, %d signal candidates' % (total, time.time() - t0, total / (time.time() - t0), signal))"),
+]
+
+
 def notebook(cells):
     out = []
     for kind, src in cells:
