@@ -109,7 +109,9 @@ t.backend = "socket"
 model = t.train(ds)
 model.compile("categorical_crossentropy")
 acc = model.evaluate(ds["features"], ds["label"])[1]
-print("RANK", os.environ["RANK"], "HIST", len(t.get_history()), "ACC", round(acc, 3), "SUM", float(model.get_flat_weights().sum()))
+line = " ".join(map(str, ("RANK", os.environ["RANK"], "HIST", len(t.get_history()), "ACC", round(acc, 3), "SUM",
+                           float(model.get_flat_weights().sum()))))
+os.write(1, (line + "\n").encode())   # one write per rank: the two ranks share the pipe, print() would interleave its pieces
 """
 
 
@@ -117,10 +119,17 @@ def test_spmd_gloo_two_processes(tmp_path):
     """torchrun-style world_size=2 on CPU: rank 0 hosts the TCP parameter server, both ranks train."""
     script = tmp_path / "spmd.py"
     script.write_text(SPMD_SCRIPT.format(root=ROOT))
-    port = 29600 + os.getpid() % 300
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
-                       capture_output=True, text=True, timeout=240, env={**os.environ, "DK_BACKEND": "socket"})
+    import socket
+
+    for attempt in range(3):   # a rendezvous port picked here can be taken by the time torchrun binds it: retry on a new one
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                           capture_output=True, text=True, timeout=240, env={**os.environ, "DK_BACKEND": "socket"})
+        if r.returncode == 0:
+            break
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("RANK")]
     assert len(lines) == 2
